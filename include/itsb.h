@@ -1,0 +1,215 @@
+/*
+ * itsb.h -- C ABI of libitsim_b200.so, the B200-native batched discrete-event engine behind ITsim's modelling API.
+ *
+ * The reference has no FFI: its seam is Python-level (ITsim objects calling greensim).  Each
+ * entry point below names the reference interface it replaces (paths relative to /root/reference).  Plain pointers
+ * and sizes only; the caller (numpy / ctypes) owns every buffer passed in or out, the library
+ * copies on load and owns all device memory until itsb_destroy.  One host thread drives one engine; engines on
+ * different GPUs are independent.  There is no CPU execution path: without a CUDA device every compute entry
+ * point fails with ITSB_ERR_NO_DEVICE.
+ *
+ * Return convention: 0 = OK; negative = engine error (ITSB_ERR_*); positive = a model-level exception of the
+ * reference raised in some replica (ITSB_EXC_*), retrievable per replica with itsb_replica_status.
+ */
+#ifndef ITSB_H
+#define ITSB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ITSB_ABI_VERSION 1
+
+/* ---- engine errors (negative) ------------------------------------------------------------------------------ */
+#define ITSB_OK                    0
+#define ITSB_ERR_NO_DEVICE        -1   /* no CUDA device / driver: the product has no CPU fallback            */
+#define ITSB_ERR_BAD_MODEL        -2   /* malformed tables (bounds, sizes, versions)                          */
+#define ITSB_ERR_CUDA             -3   /* a CUDA runtime call failed; see itsb_last_error                     */
+#define ITSB_ERR_STATE            -4   /* call order (e.g. run before init_replicas)                          */
+#define ITSB_ERR_CAP_EVENTS       -10  /* per-replica event pool exhausted                                    */
+#define ITSB_ERR_CAP_PROCS        -11  /* per-replica process slots exhausted                                 */
+#define ITSB_ERR_CAP_SOCKETS      -12  /* per-replica socket slots exhausted                                  */
+#define ITSB_ERR_CAP_PACKETS      -13  /* per-replica in-flight packet slots exhausted                        */
+#define ITSB_ERR_CAP_ARENA        -14  /* per-replica queue arena (HBM) exhausted                             */
+#define ITSB_ERR_BAD_OPCODE       -15
+#define ITSB_ERR_NCCL             -20
+
+/* ---- model-level exceptions of the reference (positive) ------------------------------------------------------ */
+#define ITSB_EXC_NO_SUCH_ADDRESS   1   /* itsim/network/link.py:18-22; overrides CannotForward :293-297        */
+#define ITSB_EXC_NO_ROUTE          2   /* itsim/machine/node.py:59-66                                          */
+#define ITSB_EXC_PORT_IN_USE       3   /* itsim/machine/node.py:41-49; network_simple_overrides.py:343-344     */
+#define ITSB_EXC_PORTS_EXHAUSTED   4   /* itsim/machine/node.py:52-56                                          */
+#define ITSB_EXC_SOCKET_CLOSED     5   /* ValueError("Socket is closed"), itsim/machine/socket.py:105,130,138  */
+#define ITSB_EXC_NEGATIVE_DELAY    6   /* greensim Simulator._schedule ValueError                              */
+#define ITSB_EXC_UNCAUGHT          7   /* a non-Interrupt exception left a process body (aborts Simulator.run) */
+
+/* ---- trace / event kinds: the shared definition of a "simulated event"  -------------- */
+#define ITSB_EV_PROC_START 1
+#define ITSB_EV_TIMER      2
+#define ITSB_EV_TX_BEGIN   3
+#define ITSB_EV_TX_END     4
+#define ITSB_EV_DELIVER    5
+#define ITSB_EV_WAKE       6
+#define ITSB_EV_THROW      7
+#define ITSB_EV_STOP       8
+#define ITSB_NUM_KINDS     9
+
+typedef struct itsb_trace_rec {   /* 16 bytes, little endian; same layout as oracle/evtrace.py TRACE_DTYPE */
+    double   t;
+    uint8_t  kind;
+    uint8_t  prog;
+    uint16_t node;
+    uint32_t aux;
+} itsb_trace_rec;
+
+/* ---- telemetry: what the datastore would have been told, reduced on device ---------------------------------- */
+#define ITSB_LAT_BINS 64
+/* slots of the uint64 telemetry vector returned by itsb_read_telemetry / reduced by itsb_allreduce_telemetry */
+#define ITSB_TM_KIND0            0                      /* [0..8]  events per kind (index = ITSB_EV_*)           */
+#define ITSB_TM_PACKETS_SENT     9
+#define ITSB_TM_BYTES_SENT       10
+#define ITSB_TM_PACKETS_RECEIVED 11                     /* packets returned by a recv()                        */
+#define ITSB_TM_BYTES_RECEIVED   12
+#define ITSB_TM_DELIVERED        13                     /* deliveries that found a socket                      */
+#define ITSB_TM_DROPPED          14                     /* deliveries dropped at the node                      */
+#define ITSB_TM_USER0            15                     /* [15..22] model counters (STAT op)                   */
+#define ITSB_TM_LAT0             23                     /* [23..86] transit-delay histogram, log2-spaced bins  */
+#define ITSB_TM_SIZE             (ITSB_TM_LAT0 + ITSB_LAT_BINS)
+
+/* ---- model description: flat struct-of-arrays tables produced by the host-side compiler ---------------------- */
+
+typedef struct itsb_dist {        /* one variate generator chain (itsim/random.py:14-29 + greensim.random)       */
+    uint32_t kind;                /* ITSB_DIST_*                                                                 */
+    uint32_t flags;               /* ITSB_DF_*                                                                   */
+    double   p0, p1;              /* constant: p0; uniform: a,b; expo: lambd=1/mean; normal: mu,sigma; choice: n */
+    double   slope, shift;        /* linear(gen, slope, shift)            (ITSB_DF_LINEAR)                       */
+    double   lower, upper;        /* bounded(gen, lower, upper)           (ITSB_DF_LOWER / ITSB_DF_UPPER)        */
+} itsb_dist;
+
+#define ITSB_DIST_CONSTANT 0
+#define ITSB_DIST_UNIFORM  1
+#define ITSB_DIST_EXPO     2
+#define ITSB_DIST_NORMAL   3
+#define ITSB_DIST_CHOICE   4
+#define ITSB_DF_LINEAR 1u
+#define ITSB_DF_LOWER  2u
+#define ITSB_DF_UPPER  4u
+#define ITSB_DF_INT    8u         /* project_int: truncate toward zero                                           */
+
+typedef struct itsb_net {         /* one broadcast domain: override Network (overrides.py:189-291) or Link        */
+    uint32_t cidr_net, cidr_mask; /* network address and netmask                                                 */
+    uint32_t bcast;               /* broadcast address                                                           */
+    uint32_t first_node, n_nodes; /* members = node indices [first_node, first_node + n_nodes), in link order     */
+    uint32_t lat_dist, bw_dist;   /* indices into the distribution table (already bounded as the reference does)  */
+    uint32_t mode;                /* ITSB_NET_OVERRIDE: TX process, delay = lat + len/bw ; ITSB_NET_LINK: draw at
+                                     send, delay = lat + 8*len/bw (itsim/network/link.py:82-86)                  */
+} itsb_net;
+#define ITSB_NET_OVERRIDE 0
+#define ITSB_NET_LINK     1
+
+typedef struct itsb_node {        /* static part of a node                                                        */
+    uint32_t addr;                /* IPv4 address on its network                                                  */
+    uint32_t net;                 /* index into nets                                                              */
+    uint32_t host;                /* hostname id (payload field f0 compares against it)                           */
+    uint32_t flags;
+} itsb_node;
+
+typedef struct itsb_entry {       /* program entry point                                                          */
+    uint32_t pc;                  /* first instruction                                                            */
+    uint32_t prog;                /* program id reported in trace records                                         */
+} itsb_entry;
+
+typedef struct itsb_initproc {    /* process installed at t=0, in installation order (Endpoint.install)           */
+    uint32_t entry, node;
+    uint32_t r[4];
+} itsb_initproc;
+
+typedef struct itsb_caps {        /* per-replica capacities; exceeding one flags the replica with ITSB_ERR_CAP_*  */
+    uint32_t max_events, max_procs, max_sockets, max_packets;
+    uint32_t arena_nodes;         /* 32-byte queue/list nodes in HBM                                              */
+    uint32_t trace_records;       /* per-replica trace capacity (0 = tracing off)                                 */
+} itsb_caps;
+
+typedef struct itsb_model_desc {
+    uint32_t abi_version;
+    uint32_t n_code, n_entries, n_dists, n_consts, n_nets, n_nodes, n_init;
+    itsb_caps caps;
+} itsb_model_desc;
+
+/* blobs[] order for itsb_load_model */
+#define ITSB_BLOB_CODE    0   /* uint64[n_code]      instruction words (see itsim_b200/ir.py)                      */
+#define ITSB_BLOB_ENTRIES 1   /* itsb_entry[n_entries]                                                            */
+#define ITSB_BLOB_DISTS   2   /* itsb_dist[n_dists]                                                               */
+#define ITSB_BLOB_CONSTS  3   /* double[n_consts]                                                                 */
+#define ITSB_BLOB_NETS    4   /* itsb_net[n_nets]                                                                 */
+#define ITSB_BLOB_NODES   5   /* itsb_node[n_nodes]                                                               */
+#define ITSB_BLOB_INIT    6   /* itsb_initproc[n_init]                                                            */
+#define ITSB_NUM_BLOBS    7
+
+typedef struct itsb_engine itsb_engine;
+
+/* Replaces: Simulator() construction (itsim/simulator.py:9; greensim.Simulator.__init__).  Binds a CUDA device. */
+int itsb_create(int device, itsb_engine** out);
+
+/* Replaces: the Python object graph a model script builds (Link/Network, Endpoint, install(): network_simple.py:
+ * 331-387; itsim/machine/node.py:84-133,279-283).  Copies the tables to the device.                              */
+int itsb_load_model(itsb_engine* e, const itsb_model_desc* desc, const void* const* blobs, const size_t* sizes);
+
+/* Replaces: launching N interpreters with N seeds.  Replica r uses Philox key (seed, first_replica_id + r); all
+ * replicas start from the model's initial state at t = 0.  Allocates per-replica state in HBM.                   */
+int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first_replica_id);
+
+/* Replaces: Simulator.run(duration) (greensim; subclassed at itsim/simulator.py:9) for every replica at once.
+ * Re-entrant like the reference: state stays on the device, a later call continues.  events_done (may be NULL)
+ * receives the number of simulated events (section 8-d definition) processed by this call over all replicas.
+ * Returns 0, or the first non-zero replica status (itsb_replica_status tells which).                              */
+int itsb_run(itsb_engine* e, double duration, uint64_t* events_done);
+
+/* Asynchronous halves of itsb_run, for callers that overlap host work or time with their own events.            */
+int itsb_run_async(itsb_engine* e, double duration);
+int itsb_sync(itsb_engine* e, uint64_t* events_done);
+/* Device time of the last completed run in milliseconds (CUDA events on the engine's stream).                   */
+int itsb_last_run_ms(itsb_engine* e, float* ms);
+/* Number of kernel launches issued by this engine so far.                                                        */
+int itsb_launch_count(itsb_engine* e, uint64_t* launches);
+
+/* Replaces: Simulator.now() per replica.  dst receives n doubles starting at replica `first`.                     */
+int itsb_read_now(itsb_engine* e, uint64_t first, uint64_t n, double* dst);
+
+/* Replaces: reading the event log of one replica (the reference has none; the oracle's tracer defines it).       */
+int itsb_read_trace(itsb_engine* e, uint64_t replica, itsb_trace_rec* dst, size_t cap, size_t* n_total);
+
+/* Replaces: the records itsim/logging.py + itsim/datastore would receive (README.md:18-50), reduced on the device:
+ * ITSB_TM_SIZE uint64 counters / histogram bins summed over this engine's replicas.                               */
+int itsb_read_telemetry(itsb_engine* e, uint64_t* dst, size_t n);
+
+/* Per-replica counters (ITSB_TM_SIZE uint64 each), for parity checks on sampled replicas.                          */
+int itsb_read_replica_telemetry(itsb_engine* e, uint64_t replica, uint64_t* dst, size_t n);
+
+/* Sums the telemetry vector over all ranks (ncclAllReduce, SUM, uint64) -- the only collective on this path.
+ * nccl_comm is an ncclComm_t created by the caller; the reduced vector is left on the device and in dst.          */
+int itsb_allreduce_telemetry(itsb_engine* e, void* nccl_comm, uint64_t* dst, size_t n);
+/* Helpers so a ctypes host can build the communicator without an NCCL binding of its own.                         */
+int itsb_nccl_unique_id(void* id128, size_t cap);
+int itsb_nccl_comm_init(itsb_engine* e, int nranks, int rank, const void* id128, void** comm_out);
+int itsb_nccl_comm_destroy(void* comm);
+
+/* status of one replica: 0, ITSB_ERR_CAP_* or ITSB_EXC_*; detail = offending value (address, port, pc...).        */
+int itsb_replica_status(itsb_engine* e, uint64_t replica, int32_t* status, uint64_t* detail);
+/* index of the first replica with non-zero status, or -1.                                                         */
+int64_t itsb_first_failed_replica(itsb_engine* e);
+
+/* bytes of per-replica state staged HBM<->shared memory per run (S_in + S_out of the roofline accounting).        */
+int itsb_state_bytes(itsb_engine* e, uint64_t* hot_bytes, uint64_t* arena_bytes);
+
+const char* itsb_last_error(itsb_engine* e);
+void itsb_destroy(itsb_engine* e);
+int itsb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ITSB_H */

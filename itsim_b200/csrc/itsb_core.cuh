@@ -1,0 +1,1061 @@
+/*
+ * itsb_core.cuh -- the per-replica discrete-event engine: one warp advances one replica.
+ *
+ * What it replaces (reference = pure Python on greensim, /root/reference):
+ *   event loop / heap            greensim.Simulator.run/_schedule     (itsim/simulator.py:9)
+ *   processes, advance, throw    greensim.Process/advance/interrupt   (itsim/simulator.py:80-83; rows a2)
+ *   Signal / Queue waits         greensim.Signal.wait/turn_on         (rows a3); used by sockets and the wake signal
+ *   transmission + fan-out       Network.transmit                     (network_simple_overrides.py:273-291; row a16)
+ *                                Link._transfer_packet                (itsim/network/link.py:70-86; row a5)
+ *   delivery at a node           Node._receive / Node._receive_packet (overrides.py:379-382; node.py:232-243; a7)
+ *   sockets, ports               open_socket/bind/get_port_free       (overrides.py:337-369,469-476; rows a8-a9)
+ *   variates                     greensim.random + itsim.random       (itsim/random.py:14-29; row a14)
+ *
+ * Execution model.  All lanes of the warp run this code with warp-uniform control flow; replica state lives in the
+ * warp's slice of shared memory.  Scalar bookkeeping is executed redundantly by every lane (same value, same
+ * address), so each lane is self-consistent without fences; the lane-parallel phases -- the event-pool minimum
+ * (strided scan + redux min-reduction), the delivery fan-out over a link's recipients (ballot / prefix ranks), slot
+ * allocation -- end with a warp sync.  The socket packet queues and remembered-packet lists live in a per-replica
+ * arena in HBM (they grow to thousands of packets while a workstation sleeps).
+ *
+ * The same source builds with ITSB_W == 1 (one "lane") as a plain C++ translation unit; that build exists only so
+ * the unit tests can exercise the interpreter without a GPU (tests/hostemu).  The product library never contains it.
+ */
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+#include "../../include/itsb.h"
+#include "itsb_ir.h"
+
+#if defined(__CUDACC__)
+#define ITSB_W 32
+#define ITSB_FN __device__ __forceinline__
+#define ITSB_FN_NOINLINE __device__ __noinline__
+#else
+#define ITSB_W 1
+#define ITSB_FN static inline
+#define ITSB_FN_NOINLINE static
+#endif
+
+namespace itsb {
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+static const u16 NIL16 = 0xFFFF;
+static const u32 NIL32 = 0xFFFFFFFFu;
+static const u64 T_EMPTY = 0x7FF0000000000000ull; /* +inf: empty event slot */
+
+/* ---- warp primitives (trivial when ITSB_W == 1) --------------------------------------------------------------- */
+#if defined(__CUDACC__)
+ITSB_FN int lane_id() { return (int)(threadIdx.x & 31); }
+ITSB_FN u32 w_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+ITSB_FN u32 w_shfl(u32 v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
+ITSB_FN u32 w_min(u32 v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
+ITSB_FN u32 w_add(u32 v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
+ITSB_FN void w_sync() { __syncwarp(); }
+ITSB_FN u32 w_excl_scan(u32 v, u32* total) {
+    u32 x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+        if (lane_id() >= d) x += y;
+    }
+    *total = __shfl_sync(0xFFFFFFFFu, x, 31);
+    return x - v;
+}
+ITSB_FN u32 lanemask_lt() { return (1u << lane_id()) - 1u; }
+ITSB_FN int popc(u32 v) { return __popc(v); }
+ITSB_FN int ffs32(u32 v) { return __ffs(v); }
+ITSB_FN u64 dbits(double d) { return (u64)__double_as_longlong(d); }
+ITSB_FN double bitsd(u64 b) { return __longlong_as_double((long long)b); }
+ITSB_FN u32 mulhi32(u32 a, u32 b) { return __umulhi(a, b); }
+#else
+ITSB_FN int lane_id() { return 0; }
+ITSB_FN u32 w_ballot(bool p) { return p ? 1u : 0u; }
+ITSB_FN u32 w_shfl(u32 v, int) { return v; }
+ITSB_FN u32 w_min(u32 v) { return v; }
+ITSB_FN u32 w_add(u32 v) { return v; }
+ITSB_FN void w_sync() {}
+ITSB_FN u32 w_excl_scan(u32 v, u32* total) { *total = v; return 0; }
+ITSB_FN u32 lanemask_lt() { return 0; }
+ITSB_FN int popc(u32 v) { return __builtin_popcount(v); }
+ITSB_FN int ffs32(u32 v) { return __builtin_ffs((int)v); }
+ITSB_FN u64 dbits(double d) { u64 b; memcpy(&b, &d, 8); return b; }
+ITSB_FN double bitsd(u64 b) { double d; memcpy(&d, &b, 8); return d; }
+ITSB_FN u32 mulhi32(u32 a, u32 b) { return (u32)(((u64)a * (u64)b) >> 32); }
+#endif
+
+/* ---- per-replica state ------------------------------------------------------------------------------------------ */
+
+struct Hdr {                /* 64 bytes */
+    double now;
+    u64 draws;              /* Philox draw index (oracle/philox.py stream layout) */
+    u32 seq;                /* greensim's insertion counter */
+    int32_t status;         /* 0, ITSB_ERR_CAP_* or ITSB_EXC_* */
+    u64 detail;
+    u32 arena_free_top;
+    u32 trace_count;
+    u16 ev_free_top, pcb_free_top, sock_free_top, pkt_free_top;
+    u32 replica_lo, replica_hi;
+    u32 pad[2];
+};
+
+struct Pcb {                /* 48 bytes: one greensim process */
+    u16 pc;
+    u8 state;
+    u8 prog;
+    u16 node;
+    u16 gen;
+    u16 wnext, wprev;       /* waiter-list links */
+    u16 wsig;               /* what it waits on: WS_* | index */
+    u16 timer_ev;           /* event slot of its pending advance() wake-up */
+    u16 sock;
+    u16 exc;                /* last exception delivered */
+    u32 list_head, list_tail; /* remembered-packet list (arena nodes) */
+    u32 r[4];
+    u32 pad[1];
+};
+
+enum { PS_FREE = 0, PS_UNSTARTED = 1, PS_RUNNING = 2, PS_TIMER = 3, PS_WAIT = 4, PS_RESUMING = 5 };
+enum { WS_NONE = 0, WS_SOCK = 0x4000, WS_NODE = 0x8000 };
+
+struct Sock {               /* 24 bytes */
+    u16 port;
+    u16 node;
+    u16 next;               /* next socket of the same node */
+    u16 wait_head, wait_tail;
+    u16 owner;
+    u32 q_head, q_tail;     /* FIFO of arena nodes */
+    u32 q_len;
+};
+
+struct NodeDyn {            /* 16 bytes */
+    u16 sock_head;
+    u16 port_cursor;        /* next candidate of the unprivileged-port cycle (overrides.py:469) */
+    u16 wake_head, wake_tail;
+    u32 epoch;              /* bumped by sleep() and wake_up(); stands for _time_awoken (network_simple.py:51-57) */
+    u32 awake;
+};
+
+struct Pkt {                /* 32 bytes: a packet in flight */
+    u32 src_ip, dst_ip;
+    u32 ports;              /* src | dst << 16 */
+    u32 size;
+    u32 tag, f0, f1;
+    u32 meta;               /* src node | net << 16 */
+};
+
+struct ArenaNode {          /* 32 bytes = one DRAM sector */
+    u32 next;
+    u32 src_ip;
+    u32 ports;
+    u32 size;
+    u32 tag, f0, f1;
+    u32 pad;
+};
+
+struct Layout {             /* byte offsets inside one replica's hot block */
+    u32 hot_bytes;
+    u32 off_ev_t, off_ev_seq, off_ev_data, off_ev_free;
+    u32 off_pcb, off_pcb_free, off_sock, off_sock_free, off_node, off_pkt, off_pkt_free, off_stats;
+    u32 max_ev, max_proc, max_sock, max_pkt, n_nodes;
+    u32 arena_nodes, trace_cap;
+};
+
+struct Model {              /* device pointers to the static tables */
+    const u64* code;
+    const itsb_entry* entries;
+    const itsb_dist* dists;
+    const double* consts;
+    const itsb_net* nets;
+    const itsb_node* nodes;
+    const itsb_initproc* init;
+    u32 n_code, n_entries, n_dists, n_consts, n_nets, n_nodes, n_init;
+};
+
+struct Rep {                /* working view of one replica (pointers into the hot block + HBM side buffers) */
+    Hdr* hdr;
+    u64* ev_t;
+    u32* ev_seq;
+    u32* ev_data;
+    u16* ev_free;
+    Pcb* pcb;
+    u16* pcb_free;
+    Sock* sock;
+    u16* sock_free;
+    NodeDyn* node;
+    Pkt* pkt;
+    u16* pkt_free;
+    u64* stats;
+    ArenaNode* arena;       /* HBM */
+    u32* arena_free;        /* HBM */
+    itsb_trace_rec* trace;  /* HBM or null */
+    const Model* m;
+    const Layout* L;
+    /* volatile interpreter registers: valid only inside one activation of a process */
+    u32 pk_src_ip, pk_src_port, pk_size, pk_tag, pk_f0, pk_f1;
+    u32 ent_ip, ent_port;
+    u64 events;             /* simulated events processed by this call */
+    u32 rng_w[4];
+    u64 rng_block;
+};
+
+ITSB_FN void bind_views(Rep& R, unsigned char* hot, const Layout* L) {
+    R.L = L;
+    R.hdr = (Hdr*)hot;
+    R.ev_t = (u64*)(hot + L->off_ev_t);
+    R.ev_seq = (u32*)(hot + L->off_ev_seq);
+    R.ev_data = (u32*)(hot + L->off_ev_data);
+    R.ev_free = (u16*)(hot + L->off_ev_free);
+    R.pcb = (Pcb*)(hot + L->off_pcb);
+    R.pcb_free = (u16*)(hot + L->off_pcb_free);
+    R.sock = (Sock*)(hot + L->off_sock);
+    R.sock_free = (u16*)(hot + L->off_sock_free);
+    R.node = (NodeDyn*)(hot + L->off_node);
+    R.pkt = (Pkt*)(hot + L->off_pkt);
+    R.pkt_free = (u16*)(hot + L->off_pkt_free);
+    R.stats = (u64*)(hot + L->off_stats);
+    R.events = 0;
+    R.rng_block = ~0ull;
+}
+
+ITSB_FN void fail(Rep& R, int status, u64 detail) {
+    if (R.hdr->status == 0) {
+        R.hdr->status = status;
+        R.hdr->detail = detail;
+    }
+}
+
+/* ---- event data word: kind[0:4] exc[4:12] proc-or-packet[12:22] gen[22:32] ------------------------------------- */
+ITSB_FN u32 ev_pack(u32 kind, u32 idx, u32 gen, u32 exc) {
+    return kind | ((exc & 0xFF) << 4) | ((idx & 0x3FF) << 12) | ((gen & 0x3FF) << 22);
+}
+ITSB_FN u32 ev_kind(u32 d) { return d & 0xF; }
+ITSB_FN u32 ev_exc(u32 d) { return (d >> 4) & 0xFF; }
+ITSB_FN u32 ev_idx(u32 d) { return (d >> 12) & 0x3FF; }
+ITSB_FN u32 ev_gen(u32 d) { return (d >> 22) & 0x3FF; }
+
+/* ---- Philox4x32-10 stream (same definition as oracle/philox.py) --------------------------------------------------- */
+ITSB_FN void philox_block(u32 seed_lo, u32 seed_hi, u32 rep_lo, u32 rep_hi, u64 block, u32 out[4]) {
+    u32 c0 = (u32)block, c1 = (u32)(block >> 32), c2 = seed_hi, c3 = rep_hi;
+    u32 k0 = seed_lo, k1 = rep_lo;
+#pragma unroll
+    for (int rnd = 0; rnd < 10; ++rnd) {
+        if (rnd) { k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+        u32 hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        u32 hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        u32 n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct Seed { u32 lo, hi; };
+
+ITSB_FN void rng_next(Rep& R, Seed seed, u32& a, u32& b) {
+    u64 d = R.hdr->draws;
+    R.hdr->draws = d + 1;
+    u64 block = d >> 1;
+    if (block != R.rng_block) {
+        R.rng_block = block;
+        philox_block(seed.lo, seed.hi, R.hdr->replica_lo, R.hdr->replica_hi, block, R.rng_w);
+    }
+    u32 half = (u32)(d & 1);
+    a = half ? R.rng_w[2] : R.rng_w[0];
+    b = half ? R.rng_w[3] : R.rng_w[1];
+}
+
+ITSB_FN double rng_random(Rep& R, Seed seed) {  /* CPython's 53-bit construction */
+    u32 a, b;
+    rng_next(R, seed, a, b);
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+}
+
+/* One value of a generator chain: kind -> linear -> bounded -> project_int (itsim/random.py:29). */
+ITSB_FN double draw_dist(Rep& R, Seed seed, const itsb_dist& D) {
+    double x;
+    switch (D.kind) {
+    case ITSB_DIST_CONSTANT:
+        x = D.p0;
+        break;
+    case ITSB_DIST_UNIFORM:  /* random.uniform: a + (b - a) * random() */
+        x = D.p0 + (D.p1 - D.p0) * rng_random(R, seed);
+        break;
+    case ITSB_DIST_EXPO:     /* random.expovariate(lambd): -log(1 - random()) / lambd */
+        x = -log(1.0 - rng_random(R, seed)) / D.p0;
+        break;
+    case ITSB_DIST_NORMAL: { /* random.normalvariate: Kinderman-Monahan ratio of uniforms */
+        double z;
+        for (;;) {
+            double u1 = rng_random(R, seed);
+            double u2 = 1.0 - rng_random(R, seed);
+            z = 1.7155277699214135 * (u1 - 0.5) / u2;
+            double zz = z * z / 4.0;
+            if (zz <= -log(u2)) break;
+        }
+        x = D.p0 + z * D.p1;
+        break;
+    }
+    case ITSB_DIST_CHOICE: { /* random.choice -> _randbelow_with_getrandbits(n) */
+        u32 n = (u32)D.p0;
+        u32 k = 32 - (u32)
+#if defined(__CUDACC__)
+            __clz((int)n);
+#else
+            __builtin_clz(n);
+#endif
+        u32 r;
+        for (;;) {
+            u32 a, b;
+            rng_next(R, seed, a, b);
+            r = a >> (32 - k);
+            if (r < n) break;
+        }
+        x = (double)r;
+        break;
+    }
+    default:
+        x = 0.0;
+    }
+    if (D.flags & ITSB_DF_LINEAR) x = D.slope * x + D.shift;
+    if ((D.flags & ITSB_DF_LOWER) && x < D.lower) x = D.lower;
+    if ((D.flags & ITSB_DF_UPPER) && x > D.upper) x = D.upper;
+    if (D.flags & ITSB_DF_INT) x = (double)(long long)x;
+    return x;
+}
+
+/* ---- telemetry ------------------------------------------------------------------------------------------------------ */
+ITSB_FN void stat_add(Rep& R, u32 slot, u64 v) { R.stats[slot] += v; }
+
+ITSB_FN void trace_put(Rep& R, u32 kind, u32 prog, u32 node, u32 aux) {
+    if (R.trace) {
+        u32 n = R.hdr->trace_count;
+        if (n < R.L->trace_cap && lane_id() == 0) {
+            itsb_trace_rec rec;
+            rec.t = R.hdr->now; rec.kind = (u8)kind; rec.prog = (u8)prog; rec.node = (u16)node; rec.aux = aux;
+            R.trace[n] = rec;
+        }
+        R.hdr->trace_count = n + 1;
+    }
+}
+
+ITSB_FN void count_event(Rep& R, u32 kind, u32 prog, u32 node, u32 aux) {
+    R.stats[ITSB_TM_KIND0 + kind] += 1;
+    R.events += 1;
+    trace_put(R, kind, prog, node, aux);
+}
+
+/* transit-delay histogram: bin = clamp(floor(log2(delay / 1us)), 0, 63) via the exponent field */
+ITSB_FN u32 latency_bin(double delay) {
+    double scaled = delay * 1.0e6;
+    if (!(scaled >= 1.0)) return 0;
+    u32 e = (u32)((dbits(scaled) >> 52) & 0x7FF) - 1023u;
+    return e > (ITSB_LAT_BINS - 1) ? (ITSB_LAT_BINS - 1) : e;
+}
+
+/* ---- event pool -------------------------------------------------------------------------------------------------------- */
+ITSB_FN int ev_push(Rep& R, double t, u32 data) {
+    u32 top = R.hdr->ev_free_top;
+    if (top == 0) { fail(R, ITSB_ERR_CAP_EVENTS, R.hdr->seq); return -1; }
+    top -= 1;
+    R.hdr->ev_free_top = (u16)top;
+    u32 slot = R.ev_free[top];
+    R.ev_t[slot] = dbits(t);
+    R.ev_seq[slot] = R.hdr->seq;
+    R.hdr->seq += 1;
+    R.ev_data[slot] = data;
+    return (int)slot;
+}
+
+ITSB_FN void ev_release(Rep& R, u32 slot) {
+    R.ev_t[slot] = T_EMPTY;
+    u32 top = R.hdr->ev_free_top;
+    R.ev_free[top] = (u16)slot;
+    R.hdr->ev_free_top = (u16)(top + 1);
+}
+
+/* Index of the minimum (t, seq) entry, or -1.  Each lane scans a strided slice, then three redux min-reductions. */
+ITSB_FN int ev_min(Rep& R, u64& tbits, u32& seq) {
+    u64 bt = T_EMPTY;
+    u32 bs = NIL32;
+    u32 bi = NIL32;
+    const u32 n = R.L->max_ev;
+    for (u32 i = (u32)lane_id(); i < n; i += ITSB_W) {
+        u64 t = R.ev_t[i];
+        u32 s = R.ev_seq[i];
+        if (t < bt || (t == bt && s < bs)) { bt = t; bs = s; bi = i; }
+    }
+    u32 hi = (u32)(bt >> 32);
+    u32 mhi = w_min(hi);
+    if (mhi >= 0x7FF00000u) return -1;
+    bool cand = (hi == mhi);
+    u32 lo = cand ? (u32)bt : NIL32;
+    u32 mlo = w_min(lo);
+    cand = cand && (lo == mlo);
+    u32 sq = cand ? bs : NIL32;
+    u32 msq = w_min(sq);
+    cand = cand && (sq == msq);
+    int winner = ffs32(w_ballot(cand)) - 1;
+    u32 idx = w_shfl(bi, winner);
+    tbits = ((u64)mhi << 32) | mlo;
+    seq = msq;
+    return (int)idx;
+}
+
+/* ---- slots ------------------------------------------------------------------------------------------------------------- */
+ITSB_FN int pcb_alloc(Rep& R) {
+    u32 top = R.hdr->pcb_free_top;
+    if (top == 0) { fail(R, ITSB_ERR_CAP_PROCS, 0); return -1; }
+    top -= 1;
+    R.hdr->pcb_free_top = (u16)top;
+    return (int)R.pcb_free[top];
+}
+
+ITSB_FN u32 arena_alloc(Rep& R) {
+    u32 top = R.hdr->arena_free_top;
+    if (top == 0) { fail(R, ITSB_ERR_CAP_ARENA, 0); return NIL32; }
+    top -= 1;
+    R.hdr->arena_free_top = top;
+    return R.arena_free[top];
+}
+
+ITSB_FN void arena_release(Rep& R, u32 idx) {
+    u32 top = R.hdr->arena_free_top;
+    R.arena_free[top] = idx;   /* every lane stores the same word: each lane stays self-consistent */
+    R.hdr->arena_free_top = top + 1;
+}
+
+ITSB_FN u32 handle_of(Rep& R, u32 p) { return p | ((u32)R.pcb[p].gen << 16); }
+
+/* Creates a process in PS_UNSTARTED and schedules its first switch (greensim add / add_in). */
+ITSB_FN int proc_spawn(Rep& R, u32 entry, u32 node, const u32 regs[4], double delay) {
+    int p = pcb_alloc(R);
+    if (p < 0) return -1;
+    Pcb& P = R.pcb[p];
+    const itsb_entry E = R.m->entries[entry];
+    P.pc = (u16)E.pc;
+    P.state = PS_UNSTARTED;
+    P.prog = (u8)E.prog;
+    P.node = (u16)node;
+    P.wnext = NIL16; P.wprev = NIL16; P.wsig = WS_NONE; P.timer_ev = NIL16; P.sock = NIL16; P.exc = 0;
+    P.list_head = NIL32; P.list_tail = NIL32;
+    P.r[0] = regs[0]; P.r[1] = regs[1]; P.r[2] = regs[2]; P.r[3] = regs[3];
+    ev_push(R, R.hdr->now + delay, ev_pack(ITSB_EV_PROC_START, (u32)p, P.gen, 0));
+    return p;
+}
+
+ITSB_FN void list_free_all(Rep& R, Pcb& P) {
+    u32 n = P.list_head;
+    while (n != NIL32) {
+        u32 nx = R.arena[n].next;
+        arena_release(R, n);
+        n = nx;
+    }
+    P.list_head = NIL32; P.list_tail = NIL32;
+}
+
+ITSB_FN void proc_exit(Rep& R, u32 p) {
+    Pcb& P = R.pcb[p];
+    list_free_all(R, P);
+    P.state = PS_FREE;
+    P.gen = (u16)((P.gen + 1) & 0x3FF);
+    u32 top = R.hdr->pcb_free_top;
+    R.pcb_free[top] = (u16)p;
+    R.hdr->pcb_free_top = (u16)(top + 1);
+}
+
+/* ---- waiter lists (greensim Queue: FIFO by join order) --------------------------------------------------------------- */
+ITSB_FN void waiters_append(Rep& R, u16& head, u16& tail, u32 p, u16 wsig) {
+    Pcb& P = R.pcb[p];
+    P.wnext = NIL16;
+    P.wprev = tail;
+    P.wsig = wsig;
+    if (tail == NIL16) head = (u16)p; else R.pcb[tail].wnext = (u16)p;
+    tail = (u16)p;
+}
+
+ITSB_FN void waiters_unlink(Rep& R, u16& head, u16& tail, u32 p) {
+    Pcb& P = R.pcb[p];
+    if (P.wprev == NIL16) head = P.wnext; else R.pcb[P.wprev].wnext = P.wnext;
+    if (P.wnext == NIL16) tail = P.wprev; else R.pcb[P.wnext].wprev = P.wprev;
+    P.wnext = NIL16; P.wprev = NIL16; P.wsig = WS_NONE;
+}
+
+/* Signal.turn_on: resume every waiter in order (each resume = _schedule(0, switch)). */
+ITSB_FN void waiters_resume_all(Rep& R, u16& head, u16& tail) {
+    u16 p = head;
+    while (p != NIL16) {
+        Pcb& P = R.pcb[p];
+        u16 nx = P.wnext;
+        P.wnext = NIL16; P.wprev = NIL16; P.wsig = WS_NONE;
+        P.state = PS_RESUMING;
+        ev_push(R, R.hdr->now, ev_pack(ITSB_EV_WAKE, p, P.gen, 0));
+        p = nx;
+    }
+    head = NIL16; tail = NIL16;
+}
+
+/* ---- sockets ------------------------------------------------------------------------------------------------------------ */
+ITSB_FN int sock_find(Rep& R, u32 node, u32 dst_ip, u32 dst_port) {
+    const itsb_node N = R.m->nodes[node];
+    if (dst_ip != N.addr && dst_ip != R.m->nets[N.net].bcast) return -1;
+    u16 s = R.node[node].sock_head;
+    while (s != NIL16) {
+        if (R.sock[s].port == dst_port) return (int)s;
+        s = R.sock[s].next;
+    }
+    return -1;
+}
+
+ITSB_FN bool port_in_use(Rep& R, u32 node, u32 port) {
+    u16 s = R.node[node].sock_head;
+    while (s != NIL16) {
+        if (R.sock[s].port == port) return true;
+        s = R.sock[s].next;
+    }
+    return false;
+}
+
+/* open_socket (overrides.py:337-369): port 0 takes the next free port of the persistent 1024..65535 cycle. */
+ITSB_FN int sock_open(Rep& R, u32 p, u32 port) {
+    Pcb& P = R.pcb[p];
+    NodeDyn& N = R.node[P.node];
+    if (port == 0) {
+        u32 c = N.port_cursor;
+        for (;;) {
+            u32 cand = c;
+            c = (c == 65535u) ? 1024u : c + 1u;
+            if (!port_in_use(R, P.node, cand)) { port = cand; break; }
+        }
+        N.port_cursor = (u16)c;
+    } else if (port_in_use(R, P.node, port)) {
+        fail(R, ITSB_EXC_PORT_IN_USE, port);
+        return -1;
+    }
+    u32 top = R.hdr->sock_free_top;
+    if (top == 0) { fail(R, ITSB_ERR_CAP_SOCKETS, port); return -1; }
+    top -= 1;
+    R.hdr->sock_free_top = (u16)top;
+    u32 s = R.sock_free[top];
+    Sock& S = R.sock[s];
+    S.port = (u16)port; S.node = P.node; S.owner = (u16)p;
+    S.wait_head = NIL16; S.wait_tail = NIL16;
+    S.q_head = NIL32; S.q_tail = NIL32; S.q_len = 0;
+    S.next = N.sock_head;
+    N.sock_head = (u16)s;
+    P.sock = (u16)s;
+    return (int)s;
+}
+
+ITSB_FN void sock_close(Rep& R, u32 p) {
+    Pcb& P = R.pcb[p];
+    u32 s = P.sock;
+    if (s == NIL16) return;
+    Sock& S = R.sock[s];
+    NodeDyn& N = R.node[S.node];
+    /* unlink from the node's socket list */
+    if (N.sock_head == s) N.sock_head = S.next;
+    else {
+        u16 q = N.sock_head;
+        while (q != NIL16 && R.sock[q].next != s) q = R.sock[q].next;
+        if (q != NIL16) R.sock[q].next = S.next;
+    }
+    /* drop queued packets */
+    u32 n = S.q_head;
+    while (n != NIL32) {
+        u32 nx = R.arena[n].next;
+        arena_release(R, n);
+        n = nx;
+    }
+    S.q_head = NIL32; S.q_tail = NIL32; S.q_len = 0;
+    S.port = 0;
+    u32 top = R.hdr->sock_free_top;
+    R.sock_free[top] = (u16)s;
+    R.hdr->sock_free_top = (u16)(top + 1);
+    P.sock = NIL16;
+}
+
+/* ---- transmission ---------------------------------------------------------------------------------------------------------- */
+ITSB_FN int pkt_alloc(Rep& R) {
+    u32 top = R.hdr->pkt_free_top;
+    if (top == 0) { fail(R, ITSB_ERR_CAP_PACKETS, 0); return -1; }
+    top -= 1;
+    R.hdr->pkt_free_top = (u16)top;
+    return (int)R.pkt_free[top];
+}
+
+ITSB_FN void pkt_release(Rep& R, u32 k) {
+    u32 top = R.hdr->pkt_free_top;
+    R.pkt_free[top] = (u16)k;
+    R.hdr->pkt_free_top = (u16)(top + 1);
+}
+
+/* Socket.send -> Node._send_to_network -> Network.transmit (overrides.py:122-125,371-377,273-291): the packet
+ * becomes a transmission process started with sim.add, i.e. one TX_BEGIN event at the current time. */
+ITSB_FN void net_send(Rep& R, u32 p, u32 dst_ip, u32 dst_port, u32 size, u32 tag, u32 f0, u32 f1) {
+    Pcb& P = R.pcb[p];
+    if (P.sock == NIL16) { fail(R, ITSB_EXC_SOCKET_CLOSED, P.pc); return; }
+    const itsb_node N = R.m->nodes[P.node];
+    const itsb_net NET = R.m->nets[N.net];
+    if (dst_ip != NET.bcast) {
+        /* must be a member of the network: members have consecutive node indices; find by address */
+        bool found = false;
+        for (u32 i = (u32)lane_id(); i < NET.n_nodes; i += ITSB_W)
+            if (R.m->nodes[NET.first_node + i].addr == dst_ip) found = true;
+        if (w_ballot(found) == 0) { fail(R, ITSB_EXC_NO_SUCH_ADDRESS, dst_ip); return; }
+    }
+    int k = pkt_alloc(R);
+    if (k < 0) return;
+    Pkt& K = R.pkt[k];
+    K.src_ip = N.addr; K.dst_ip = dst_ip;
+    K.ports = (u32)R.sock[P.sock].port | (dst_port << 16);
+    K.size = size; K.tag = tag; K.f0 = f0; K.f1 = f1;
+    K.meta = (u32)P.node | (N.net << 16);
+    stat_add(R, ITSB_TM_PACKETS_SENT, 1);
+    stat_add(R, ITSB_TM_BYTES_SENT, size);
+    ev_push(R, R.hdr->now, ev_pack(ITSB_EV_TX_BEGIN, (u32)k, 0, 0));
+}
+
+/* transmission(): advance(next(latency) + len(packet) / next(bandwidth))  (overrides.py:287-288) */
+ITSB_FN void on_tx_begin(Rep& R, Seed seed, u32 k) {
+    Pkt& K = R.pkt[k];
+    const itsb_net NET = R.m->nets[K.meta >> 16];
+    count_event(R, ITSB_EV_TX_BEGIN, 9, K.meta & 0xFFFF, K.size);
+    double lat = draw_dist(R, seed, R.m->dists[NET.lat_dist]);
+    double bw = draw_dist(R, seed, R.m->dists[NET.bw_dist]);
+    double delay = lat + (double)K.size / bw;
+    if (delay < 0.0) { fail(R, ITSB_EXC_NEGATIVE_DELAY, k); return; }
+    stat_add(R, ITSB_TM_LAT0 + latency_bin(delay), 1);
+    ev_push(R, R.hdr->now + delay, ev_pack(ITSB_EV_TX_END, k, 0, 0));
+}
+
+/* for node in receivers: sim.add(node._receive, packet)  -- one pool entry stands for the R consecutive pushes */
+ITSB_FN void on_tx_end(Rep& R, u32 k) {
+    Pkt& K = R.pkt[k];
+    const itsb_net NET = R.m->nets[K.meta >> 16];
+    u32 count = (K.dst_ip == NET.bcast) ? NET.n_nodes : 1u;
+    count_event(R, ITSB_EV_TX_END, 9, K.meta & 0xFFFF, K.size);
+    ev_push(R, R.hdr->now, ev_pack(ITSB_EV_DELIVER, k, 0, 0));
+    R.hdr->seq += count - 1;
+}
+
+/* Node._receive for every recipient, in link order (overrides.py:379-382), lane-parallel. */
+ITSB_FN void on_deliver(Rep& R, u32 k) {
+    const Pkt K = R.pkt[k];
+    const itsb_net NET = R.m->nets[K.meta >> 16];
+    const bool bcast = (K.dst_ip == NET.bcast);
+    u32 first = NET.first_node, count = NET.n_nodes;
+    if (!bcast) {
+        u32 hit = NIL32;
+        for (u32 i = (u32)lane_id(); i < NET.n_nodes; i += ITSB_W)
+            if (R.m->nodes[NET.first_node + i].addr == K.dst_ip) hit = i;
+        u32 m = w_min(hit);
+        first = NET.first_node + m;
+        count = 1;
+    }
+    const u32 dst_port = K.ports >> 16;
+    const double now = R.hdr->now;
+    for (u32 base = 0; base < count; base += ITSB_W) {
+        u32 i = base + (u32)lane_id();
+        bool valid = i < count;
+        u32 node = first + i;
+        int s = valid ? sock_find(R, node, K.dst_ip, dst_port) : -1;
+        bool acc = s >= 0;
+        u32 amask = w_ballot(acc);
+        u32 n_acc = (u32)popc(amask);
+        u32 n_valid = (u32)popc(w_ballot(valid));
+        /* trace: one DELIVER record per recipient */
+        if (R.trace && valid) {
+            u32 n = R.hdr->trace_count + i - base;
+            if (n < R.L->trace_cap) {
+                itsb_trace_rec rec;
+                rec.t = now; rec.kind = ITSB_EV_DELIVER; rec.prog = 10; rec.node = (u16)node;
+                rec.aux = (K.size & 0x7FFFFFFFu) | (acc ? 0x80000000u : 0u);
+                R.trace[n] = rec;
+            }
+        }
+        if (R.trace) R.hdr->trace_count += n_valid;
+        /* enqueue a copy on each accepting socket */
+        u32 atop = R.hdr->arena_free_top;
+        if (atop < n_acc) { fail(R, ITSB_ERR_CAP_ARENA, k); return; }
+        u32 nwait = 0;
+        if (acc) {
+            u32 rank = (u32)popc(amask & lanemask_lt());
+            u32 an = R.arena_free[atop - 1 - rank];
+            ArenaNode A;
+            A.next = NIL32; A.src_ip = K.src_ip; A.ports = K.ports; A.size = K.size;
+            A.tag = K.tag; A.f0 = K.f0; A.f1 = K.f1; A.pad = 0;
+            R.arena[an] = A;
+            Sock& S = R.sock[s];
+            if (S.q_tail == NIL32) S.q_head = an; else R.arena[S.q_tail].next = an;
+            S.q_tail = an;
+            S.q_len += 1;
+            for (u16 w = S.wait_head; w != NIL16; w = R.pcb[w].wnext) nwait += 1;
+        }
+        R.hdr->arena_free_top = atop - n_acc;
+        /* _enqueue -> packet signal turn_on: resume this socket's waiters (normally the one blocked in recv) */
+        u32 total;
+        u32 before = w_excl_scan(nwait, &total);
+        u32 etop = R.hdr->ev_free_top;
+        if (etop < total) { fail(R, ITSB_ERR_CAP_EVENTS, k); return; }
+        if (nwait) {
+            Sock& S = R.sock[s];
+            u32 j = 0;
+            u16 w = S.wait_head;
+            while (w != NIL16) {
+                Pcb& P = R.pcb[w];
+                u16 nx = P.wnext;
+                P.wnext = NIL16; P.wprev = NIL16; P.wsig = WS_NONE; P.state = PS_RESUMING;
+                u32 slot = R.ev_free[etop - 1 - (before + j)];
+                R.ev_t[slot] = dbits(now);
+                R.ev_seq[slot] = R.hdr->seq + before + j;
+                R.ev_data[slot] = ev_pack(ITSB_EV_WAKE, w, P.gen, 0);
+                j += 1;
+                w = nx;
+            }
+            S.wait_head = NIL16; S.wait_tail = NIL16;
+        }
+        w_sync();
+        R.hdr->ev_free_top = (u16)(etop - total);
+        R.hdr->seq += total;
+        R.stats[ITSB_TM_KIND0 + ITSB_EV_DELIVER] += n_valid;
+        R.stats[ITSB_TM_DELIVERED] += n_acc;
+        R.stats[ITSB_TM_DROPPED] += n_valid - n_acc;
+        R.events += n_valid;
+        w_sync();
+    }
+    pkt_release(R, k);
+}
+
+/* ---- interpreter ------------------------------------------------------------------------------------------------------------- */
+ITSB_FN u32 src_val(Rep& R, u32 p, u32 s) {
+    Pcb& P = R.pcb[p];
+    if (s < 4) return P.r[s];
+    switch (s) {
+    case SRC_PKT_SRC_IP: return R.pk_src_ip;
+    case SRC_PKT_SRC_PORT: return R.pk_src_port;
+    case SRC_PKT_SIZE: return R.pk_size;
+    case SRC_PKT_TAG: return R.pk_tag;
+    case SRC_PKT_F0: return R.pk_f0;
+    case SRC_PKT_F1: return R.pk_f1;
+    case SRC_ENT_IP: return R.ent_ip;
+    case SRC_ENT_PORT: return R.ent_port;
+    case SRC_NODE_ADDR: return R.m->nodes[P.node].addr;
+    case SRC_NODE_INDEX: return P.node;
+    case SRC_NODE_HOST: return R.m->nodes[P.node].host;
+    case SRC_NODE_EPOCH: return R.node[P.node].epoch;
+    case SRC_NODE_BCAST: return R.m->nets[R.m->nodes[P.node].net].bcast;
+    case SRC_SELF: return handle_of(R, p);
+    case SRC_EXC: return P.exc;
+    default: return 0;
+    }
+}
+
+/* Runs process p from its pc until it blocks or ends. */
+ITSB_FN void run_process(Rep& R, Seed seed, u32 p) {
+    Pcb& P = R.pcb[p];
+    P.state = PS_RUNNING;
+    for (u32 steps = 0; ; ++steps) {
+        if (R.hdr->status != 0) return;
+        const u64 ins = R.m->code[P.pc];
+        const u32 op = (u32)(ins & 0xFF), a = (u32)((ins >> 8) & 0xFF), b = (u32)((ins >> 16) & 0xFF),
+                  c = (u32)((ins >> 24) & 0xFF), imm = (u32)(ins >> 32);
+        switch (op) {
+        case OP_NOP:
+            P.pc += 1;
+            break;
+        case OP_EXIT:
+            proc_exit(R, p);
+            return;
+        case OP_JMP:
+            P.pc = (u16)imm;
+            break;
+        case OP_LI:
+            P.r[a] = imm; P.pc += 1;
+            break;
+        case OP_MOV:
+            P.r[a] = src_val(R, p, b); P.pc += 1;
+            break;
+        case OP_ADDI:
+            P.r[a] = src_val(R, p, b) + imm; P.pc += 1;
+            break;
+        case OP_JEQ:
+            P.pc = (src_val(R, p, a) == src_val(R, p, b)) ? (u16)imm : (u16)(P.pc + 1);
+            break;
+        case OP_JNE:
+            P.pc = (src_val(R, p, a) != src_val(R, p, b)) ? (u16)imm : (u16)(P.pc + 1);
+            break;
+        case OP_JEQI:
+            P.pc = (src_val(R, p, a) == (imm >> 16)) ? (u16)(imm & 0xFFFF) : (u16)(P.pc + 1);
+            break;
+        case OP_JNEI:
+            P.pc = (src_val(R, p, a) != (imm >> 16)) ? (u16)(imm & 0xFFFF) : (u16)(P.pc + 1);
+            break;
+        case OP_DRAWI:
+            P.r[a] = (u32)(int32_t)(long long)draw_dist(R, seed, R.m->dists[imm]);
+            P.pc += 1;
+            break;
+        case OP_DRAW_ADDI: {
+            double v = (double)(int32_t)src_val(R, p, b) + draw_dist(R, seed, R.m->dists[imm]);
+            P.r[a] = (u32)(int32_t)(long long)v;
+            P.pc += 1;
+            break;
+        }
+        case OP_ADVANCE:
+        case OP_ADVANCE_C: {
+            double d = (op == OP_ADVANCE) ? draw_dist(R, seed, R.m->dists[imm & 0xFFFF]) : R.m->consts[imm & 0xFFFF];
+            if (d < 0.0) { fail(R, ITSB_EXC_NEGATIVE_DELAY, P.pc); return; }
+            int slot = ev_push(R, R.hdr->now + d, ev_pack(ITSB_EV_TIMER, p, P.gen, 0));
+            P.timer_ev = (u16)slot;
+            P.state = PS_TIMER;
+            return;  /* pc stays on the ADVANCE; the TIMER event moves it on */
+        }
+        case OP_OPEN:
+            if (sock_open(R, p, imm & 0xFFFF) < 0) return;
+            P.pc += 1;
+            break;
+        case OP_CLOSE:
+            sock_close(R, p);
+            P.pc += 1;
+            break;
+        case OP_SEND: {
+            u32 dst_ip, dst_port = imm & 0xFFFF;
+            switch (a) {
+            case DST_BCAST: dst_ip = src_val(R, p, SRC_NODE_BCAST); break;
+            case DST_PKT_SRC: dst_ip = R.pk_src_ip; dst_port = R.pk_src_port; break;
+            case DST_ENT: dst_ip = R.ent_ip; dst_port = R.ent_port; break;
+            case DST_SELF: dst_ip = src_val(R, p, SRC_NODE_ADDR); break;
+            default: dst_ip = P.r[2]; dst_port = P.r[3] & 0xFFFF; break;
+            }
+            u32 f0s = (imm >> 16) & 0xFF, f1s = (imm >> 24) & 0xFF;
+            net_send(R, p, dst_ip, dst_port, src_val(R, p, b), c,
+                     f0s == SRC_NONE ? 0 : src_val(R, p, f0s), f1s == SRC_NONE ? 0 : src_val(R, p, f1s));
+            P.pc += 1;
+            break;
+        }
+        case OP_RECV: {
+            /* while queue.empty(): signal.wait()  (overrides.py:135-138) */
+            if (P.sock == NIL16) { fail(R, ITSB_EXC_SOCKET_CLOSED, P.pc); return; }
+            Sock& S = R.sock[P.sock];
+            if (S.q_len == 0) {
+                waiters_append(R, S.wait_head, S.wait_tail, p, (u16)(WS_SOCK | P.sock));
+                P.state = PS_WAIT;
+                return;
+            }
+            u32 n = S.q_head;
+            const ArenaNode A = R.arena[n];
+            S.q_head = A.next;
+            if (A.next == NIL32) S.q_tail = NIL32;
+            S.q_len -= 1;
+            arena_release(R, n);
+            R.pk_src_ip = A.src_ip; R.pk_src_port = A.ports & 0xFFFF; R.pk_size = A.size;
+            R.pk_tag = A.tag; R.pk_f0 = A.f0; R.pk_f1 = A.f1;
+            stat_add(R, ITSB_TM_PACKETS_RECEIVED, 1);
+            stat_add(R, ITSB_TM_BYTES_RECEIVED, A.size);
+            P.pc += 1;
+            break;
+        }
+        case OP_WAIT_AWAKE: {
+            NodeDyn& N = R.node[P.node];
+            if (!N.awake) {
+                waiters_append(R, N.wake_head, N.wake_tail, p, (u16)(WS_NODE | P.node));
+                P.state = PS_WAIT;
+                return;
+            }
+            if (a != SRC_NONE) P.r[a] = N.epoch;
+            P.pc += 1;
+            break;
+        }
+        case OP_JASLEEP:
+            P.pc = (R.node[P.node].epoch != src_val(R, p, a)) ? (u16)imm : (u16)(P.pc + 1);
+            break;
+        case OP_NODE_SLEEP: {
+            NodeDyn& N = R.node[P.node];
+            N.awake = 0; N.epoch += 1;
+            P.pc += 1;
+            break;
+        }
+        case OP_NODE_WAKE: {
+            NodeDyn& N = R.node[P.node];
+            N.awake = 1;
+            waiters_resume_all(R, N.wake_head, N.wake_tail);
+            N.epoch += 1;
+            P.pc += 1;
+            break;
+        }
+        case OP_SPAWN: {
+            int child = proc_spawn(R, imm, P.node, P.r, 0.0);
+            if (child < 0) return;
+            if (a != SRC_NONE) P.r[a] = handle_of(R, (u32)child);
+            P.pc += 1;
+            break;
+        }
+        case OP_THROW: {
+            u32 h = src_val(R, p, a);
+            ev_push(R, R.hdr->now, ev_pack(ITSB_EV_THROW, h & 0x3FF, (h >> 16) & 0x3FF, imm));
+            P.pc += 1;
+            break;
+        }
+        case OP_LIST_CLEAR:
+            list_free_all(R, P);
+            P.pc += 1;
+            break;
+        case OP_LIST_PUSH: {
+            u32 n = arena_alloc(R);
+            if (n == NIL32) return;
+            ArenaNode A;
+            A.next = NIL32; A.src_ip = R.pk_src_ip; A.ports = R.pk_src_port; A.size = R.pk_size;
+            A.tag = R.pk_tag; A.f0 = R.pk_f0; A.f1 = R.pk_f1; A.pad = 0;
+            R.arena[n] = A;
+            if (P.list_tail != NIL32) R.arena[P.list_tail].next = n;
+            if (P.list_tail == NIL32) P.list_head = n;
+            P.list_tail = n;
+            P.pc += 1;
+            break;
+        }
+        case OP_LIST_TAKE: {
+            u32 key = src_val(R, p, a);
+            u32 prev = NIL32, n = P.list_head;
+            bool found = false;
+            while (n != NIL32) {
+                const ArenaNode A = R.arena[n];
+                if (A.f0 == key) {
+                    R.ent_ip = A.src_ip; R.ent_port = A.ports & 0xFFFF;
+                    if (prev == NIL32) P.list_head = A.next;
+                    else R.arena[prev].next = A.next;
+                    if (P.list_tail == n) P.list_tail = prev;
+                    arena_release(R, n);
+                    found = true;
+                    break;
+                }
+                prev = n; n = A.next;
+            }
+            P.pc = found ? (u16)(P.pc + 1) : (u16)imm;
+            break;
+        }
+        case OP_STAT:
+            stat_add(R, ITSB_TM_USER0 + (imm & 7), 1);
+            P.pc += 1;
+            break;
+        default:
+            fail(R, ITSB_ERR_BAD_OPCODE, P.pc);
+            return;
+        }
+    }
+}
+
+/* An exception arrives at a blocked process (greenlet.throw): leave whatever it was parked in, then run its handler.
+ * greensim would leave a "ghost" wake-up / queue entry for non-Interrupt exceptions; ghosts are no-ops, so the
+ * engine removes them instead (same model-visible order). */
+ITSB_FN void deliver_exception(Rep& R, Seed seed, u32 p, u32 exc) {
+    Pcb& P = R.pcb[p];
+    if (P.state == PS_TIMER && P.timer_ev != NIL16) {
+        ev_release(R, P.timer_ev);
+        P.timer_ev = NIL16;
+    } else if (P.state == PS_WAIT) {
+        if (P.wsig & WS_NODE) { NodeDyn& N = R.node[P.wsig & 0x3FFF]; waiters_unlink(R, N.wake_head, N.wake_tail, p); }
+        else if (P.wsig & WS_SOCK) { Sock& S = R.sock[P.wsig & 0x3FFF]; waiters_unlink(R, S.wait_head, S.wait_tail, p); }
+    }
+    P.exc = (u16)exc;
+    const u64 ins = R.m->code[P.pc];
+    u32 handler = (u32)(ins >> 48);
+    if (handler == 0) {
+        if (!(exc & EXC_INTERRUPT_CLASS)) { fail(R, ITSB_EXC_UNCAUGHT, ((u64)exc << 32) | P.pc); return; }
+        sock_close(R, p);
+        proc_exit(R, p);
+        return;
+    }
+    P.pc = (u16)handler;
+    run_process(R, seed, p);
+}
+
+/* Simulator.run(duration): pops (t, seq)-ordered events until the stop event. */
+ITSB_FN void run_replica(Rep& R, Seed seed, double duration) {
+    Hdr* H = R.hdr;
+    if (H->status != 0) return;
+    const double t_stop = H->now + duration;
+    const u64 t_stop_bits = dbits(t_stop);
+    const u32 stop_seq = H->seq;
+    H->seq += 1;
+    for (;;) {
+        if (H->status != 0) break;
+        u64 tb; u32 seq;
+        int slot = ev_min(R, tb, seq);
+        if (slot < 0) break;                                  /* heap empty: the clock stays where it is */
+        if (tb > t_stop_bits || (tb == t_stop_bits && seq > stop_seq)) {
+            H->now = t_stop;
+            count_event(R, ITSB_EV_STOP, 0, 0, 0);
+            break;
+        }
+        const u32 data = R.ev_data[slot];
+        ev_release(R, (u32)slot);
+        H->now = bitsd(tb);
+        const u32 kind = ev_kind(data), idx = ev_idx(data);
+        switch (kind) {
+        case ITSB_EV_TX_BEGIN: on_tx_begin(R, seed, idx); break;
+        case ITSB_EV_TX_END: on_tx_end(R, idx); break;
+        case ITSB_EV_DELIVER: on_deliver(R, idx); break;
+        case ITSB_EV_PROC_START:
+        case ITSB_EV_TIMER:
+        case ITSB_EV_WAKE: {
+            Pcb& P = R.pcb[idx];
+            if (P.state == PS_FREE || P.gen != ev_gen(data)) break;   /* ghost hop: target finished */
+            if (kind == ITSB_EV_TIMER) {
+                if (P.state != PS_TIMER || P.timer_ev != (u16)slot) break;
+                P.timer_ev = NIL16;
+                P.pc += 1;
+            } else if (kind == ITSB_EV_WAKE) {
+                if (P.state != PS_RESUMING) break;
+            } else if (P.state != PS_UNSTARTED) break;
+            count_event(R, kind, P.prog, P.node, 0);
+            run_process(R, seed, idx);
+            break;
+        }
+        case ITSB_EV_THROW: {
+            Pcb& P = R.pcb[idx];
+            if (P.state == PS_FREE || P.gen != ev_gen(data)) break;   /* ghost hop */
+            count_event(R, ITSB_EV_THROW, P.prog, P.node, ev_exc(data));
+            if (P.state == PS_UNSTARTED) { proc_exit(R, idx); break; }  /* never ran: dies on the spot */
+            deliver_exception(R, seed, idx, ev_exc(data));
+            break;
+        }
+        default:
+            fail(R, ITSB_ERR_BAD_OPCODE, data);
+        }
+    }
+}
+
+/* Builds the t = 0 state of a replica: empty tables, free lists, and the model's installed processes in
+ * installation order (Endpoint.install -> sim.add, overrides.py:423-424; network_simple.py:366-385). */
+ITSB_FN void init_replica(Rep& R, u64 replica_id) {
+    const Layout* L = R.L;
+    Hdr* H = R.hdr;
+    H->now = 0.0; H->draws = 0; H->seq = 0; H->status = 0; H->detail = 0;
+    H->trace_count = 0;
+    H->replica_lo = (u32)replica_id; H->replica_hi = (u32)(replica_id >> 32);
+    H->pad[0] = 0; H->pad[1] = 0;
+    for (u32 i = 0; i < L->max_ev; ++i) { R.ev_t[i] = T_EMPTY; R.ev_seq[i] = 0; R.ev_data[i] = 0; R.ev_free[i] = (u16)(L->max_ev - 1 - i); }
+    H->ev_free_top = (u16)L->max_ev;
+    for (u32 i = 0; i < L->max_proc; ++i) { memset(&R.pcb[i], 0, sizeof(Pcb)); R.pcb_free[i] = (u16)(L->max_proc - 1 - i); }
+    H->pcb_free_top = (u16)L->max_proc;
+    for (u32 i = 0; i < L->max_sock; ++i) { memset(&R.sock[i], 0, sizeof(Sock)); R.sock_free[i] = (u16)(L->max_sock - 1 - i); }
+    H->sock_free_top = (u16)L->max_sock;
+    for (u32 i = 0; i < L->max_pkt; ++i) { memset(&R.pkt[i], 0, sizeof(Pkt)); R.pkt_free[i] = (u16)(L->max_pkt - 1 - i); }
+    H->pkt_free_top = (u16)L->max_pkt;
+    for (u32 i = 0; i < L->n_nodes; ++i) {
+        NodeDyn& N = R.node[i];
+        N.sock_head = NIL16; N.port_cursor = 1024; N.wake_head = NIL16; N.wake_tail = NIL16; N.epoch = 0; N.awake = 0;
+    }
+    for (u32 i = 0; i < ITSB_TM_SIZE; ++i) R.stats[i] = 0;
+    H->arena_free_top = L->arena_nodes;
+    for (u32 i = 0; i < R.m->n_init; ++i) {
+        const itsb_initproc I = R.m->init[i];
+        proc_spawn(R, I.entry, I.node, I.r, 0.0);
+    }
+}
+
+}  // namespace itsb

@@ -1,0 +1,89 @@
+/*
+ * itsb_host_common.h -- host-side helpers shared by the CUDA library (itsb_abi.cu) and the test-only host
+ * emulation build (tests/hostemu): model validation and the per-replica hot-block layout.
+ */
+#pragma once
+#include <stdio.h>
+#include <string>
+#include "itsb_core.cuh"
+
+namespace itsb {
+
+static inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+/* Lays the tables of one replica out in a single contiguous block (16-byte aligned regions, total a multiple of
+ * 128 bytes so replicas move with aligned 128-bit / bulk copies). */
+static inline Layout compute_layout(const itsb_model_desc& d) {
+    Layout L;
+    memset(&L, 0, sizeof(L));
+    const itsb_caps& c = d.caps;
+    L.max_ev = c.max_events; L.max_proc = c.max_procs; L.max_sock = c.max_sockets; L.max_pkt = c.max_packets;
+    L.n_nodes = d.n_nodes; L.arena_nodes = c.arena_nodes; L.trace_cap = c.trace_records;
+    uint32_t off = align_up((uint32_t)sizeof(Hdr), 16);
+    L.off_ev_t = off;      off = align_up(off + 8 * L.max_ev, 16);
+    L.off_ev_seq = off;    off = align_up(off + 4 * L.max_ev, 16);
+    L.off_ev_data = off;   off = align_up(off + 4 * L.max_ev, 16);
+    L.off_ev_free = off;   off = align_up(off + 2 * L.max_ev, 16);
+    L.off_pcb = off;       off = align_up(off + (uint32_t)sizeof(Pcb) * L.max_proc, 16);
+    L.off_pcb_free = off;  off = align_up(off + 2 * L.max_proc, 16);
+    L.off_sock = off;      off = align_up(off + (uint32_t)sizeof(Sock) * L.max_sock, 16);
+    L.off_sock_free = off; off = align_up(off + 2 * L.max_sock, 16);
+    L.off_node = off;      off = align_up(off + (uint32_t)sizeof(NodeDyn) * L.n_nodes, 16);
+    L.off_pkt = off;       off = align_up(off + (uint32_t)sizeof(Pkt) * L.max_pkt, 16);
+    L.off_pkt_free = off;  off = align_up(off + 2 * L.max_pkt, 16);
+    L.off_stats = off;     off = align_up(off + 8 * ITSB_TM_SIZE, 16);
+    L.hot_bytes = align_up(off, 128);
+    return L;
+}
+
+static inline bool validate_model(const itsb_model_desc& d, const void* const* blobs, const size_t* sizes,
+                                  std::string& why) {
+    char buf[256];
+    if (d.abi_version != ITSB_ABI_VERSION) { why = "abi_version mismatch"; return false; }
+    const size_t want[ITSB_NUM_BLOBS] = {
+        (size_t)d.n_code * 8, (size_t)d.n_entries * sizeof(itsb_entry), (size_t)d.n_dists * sizeof(itsb_dist),
+        (size_t)d.n_consts * 8, (size_t)d.n_nets * sizeof(itsb_net), (size_t)d.n_nodes * sizeof(itsb_node),
+        (size_t)d.n_init * sizeof(itsb_initproc)};
+    for (int i = 0; i < ITSB_NUM_BLOBS; ++i) {
+        if (sizes[i] != want[i] || (want[i] && !blobs[i])) {
+            snprintf(buf, sizeof buf, "blob %d: %zu bytes given, %zu expected", i, sizes[i], want[i]);
+            why = buf; return false;
+        }
+    }
+    const itsb_caps& c = d.caps;
+    if (c.max_events < 8 || c.max_events > 65535 || c.max_procs < 1 || c.max_procs > 1024 || c.max_sockets < 1 ||
+        c.max_sockets > 0x3FFF || c.max_packets < 1 || c.max_packets > 1024 || c.arena_nodes < 1) {
+        why = "capacity out of range"; return false;
+    }
+    if (d.n_nodes == 0 || d.n_nodes > 0x3FFF || d.n_code == 0 || d.n_code > 65535) { why = "table size out of range"; return false; }
+    const uint64_t* code = (const uint64_t*)blobs[ITSB_BLOB_CODE];
+    for (uint32_t i = 0; i < d.n_code; ++i) {
+        uint32_t op = (uint32_t)(code[i] & 0xFF), imm = (uint32_t)(code[i] >> 32);
+        if (op >= OP_COUNT) { snprintf(buf, sizeof buf, "code[%u]: bad opcode %u", i, op); why = buf; return false; }
+        bool has_dist = op == OP_DRAWI || op == OP_DRAW_ADDI;
+        if (has_dist && imm >= d.n_dists) { snprintf(buf, sizeof buf, "code[%u]: dist out of range", i); why = buf; return false; }
+        if (op == OP_ADVANCE && (imm & 0xFFFF) >= d.n_dists) { why = "ADVANCE dist out of range"; return false; }
+        if (op == OP_ADVANCE_C && (imm & 0xFFFF) >= d.n_consts) { why = "ADVANCE_C const out of range"; return false; }
+        if (op == OP_SPAWN && imm >= d.n_entries) { why = "SPAWN entry out of range"; return false; }
+        if ((op == OP_JMP || op == OP_JEQ || op == OP_JNE || op == OP_JASLEEP || op == OP_LIST_TAKE) && imm >= d.n_code) {
+            snprintf(buf, sizeof buf, "code[%u]: jump out of range", i); why = buf; return false;
+        }
+        if ((op == OP_JEQI || op == OP_JNEI) && (imm & 0xFFFF) >= d.n_code) { why = "jump out of range"; return false; }
+    }
+    const itsb_entry* en = (const itsb_entry*)blobs[ITSB_BLOB_ENTRIES];
+    for (uint32_t i = 0; i < d.n_entries; ++i) if (en[i].pc >= d.n_code) { why = "entry pc out of range"; return false; }
+    const itsb_net* nets = (const itsb_net*)blobs[ITSB_BLOB_NETS];
+    for (uint32_t i = 0; i < d.n_nets; ++i) {
+        if (nets[i].first_node + nets[i].n_nodes > d.n_nodes || nets[i].lat_dist >= d.n_dists || nets[i].bw_dist >= d.n_dists) {
+            why = "net table out of range"; return false;
+        }
+    }
+    const itsb_node* nodes = (const itsb_node*)blobs[ITSB_BLOB_NODES];
+    for (uint32_t i = 0; i < d.n_nodes; ++i) if (nodes[i].net >= d.n_nets) { why = "node.net out of range"; return false; }
+    const itsb_initproc* ip = (const itsb_initproc*)blobs[ITSB_BLOB_INIT];
+    for (uint32_t i = 0; i < d.n_init; ++i) if (ip[i].entry >= d.n_entries || ip[i].node >= d.n_nodes) { why = "init proc out of range"; return false; }
+    if (d.n_init > c.max_procs || d.n_init > c.max_events) { why = "more installed processes than slots"; return false; }
+    return true;
+}
+
+}  // namespace itsb

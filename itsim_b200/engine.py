@@ -1,0 +1,130 @@
+"""
+Engine: one batch of replicas of one compiled model on one GPU, driven through the C ABI.
+
+Mirrors the reference's run-time surface -- ``Simulator.run(duration)`` / ``Simulator.now()`` (greensim, subclassed
+at ``itsim/simulator.py:9``; repeated ``run`` continues, ``tests/machine/process_management/test_thread.py:148-152``)
+-- for N replicas at once.
+"""
+import ctypes as C
+from typing import Any, Dict, Optional
+
+import numpy as np
+
+from . import _lib as L
+
+
+class Engine:
+
+    def __init__(self, compiled: "Any", device: int = 0, lib: Optional[C.CDLL] = None) -> None:
+        self._lib = lib if lib is not None else L.load()
+        self._h = C.c_void_p()
+        self._check(self._lib.itsb_create(device, C.byref(self._h)), "itsb_create")
+        self.compiled = compiled
+        blobs = compiled.blobs()
+        ptrs = (C.c_void_p * len(blobs))(*[b.ctypes.data if b.size else None for b in blobs])
+        sizes = (C.c_size_t * len(blobs))(*[b.nbytes for b in blobs])
+        self._check(self._lib.itsb_load_model(self._h, C.byref(compiled.desc()), ptrs, sizes), "itsb_load_model")
+        self.n_replicas = 0
+
+    # -- plumbing ----------------------------------------------------------------------------------------
+    def _check(self, rc: int, where: str) -> None:
+        if rc != 0:
+            detail = ""
+            if self._h:
+                msg = self._lib.itsb_last_error(self._h)
+                detail = msg.decode() if msg else ""
+                bad = self._lib.itsb_first_failed_replica(self._h) if self.__dict__.get("n_replicas") else -1
+                if bad >= 0:
+                    st, dt = C.c_int32(), C.c_uint64()
+                    self._lib.itsb_replica_status(self._h, bad, C.byref(st), C.byref(dt))
+                    detail += f" replica {bad}: status {st.value}, detail {dt.value:#x}"
+            raise L.EngineError(rc, where, detail)
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.itsb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- replicas ------------------------------------------------------------------------------------------
+    def init_replicas(self, n: int, seed: int = 0, first_replica_id: int = 0) -> None:
+        self._check(self._lib.itsb_init_replicas(self._h, n, seed, first_replica_id), "itsb_init_replicas")
+        self.n_replicas = n
+
+    def run(self, duration: float) -> int:
+        """``Simulator.run(duration)`` on every replica; returns simulated events processed by this call."""
+        done = C.c_uint64()
+        self._check(self._lib.itsb_run(self._h, float(duration), C.byref(done)), "itsb_run")
+        return done.value
+
+    def run_async(self, duration: float) -> None:
+        self._check(self._lib.itsb_run_async(self._h, float(duration)), "itsb_run_async")
+
+    def sync(self) -> int:
+        done = C.c_uint64()
+        self._check(self._lib.itsb_sync(self._h, C.byref(done)), "itsb_sync")
+        return done.value
+
+    def last_run_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self._lib.itsb_last_run_ms(self._h, C.byref(ms)), "itsb_last_run_ms")
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        self._check(self._lib.itsb_launch_count(self._h, C.byref(n)), "itsb_launch_count")
+        return n.value
+
+    def now(self, first: int = 0, n: Optional[int] = None) -> np.ndarray:
+        n = self.n_replicas - first if n is None else n
+        out = np.zeros(n, dtype=np.float64)
+        self._check(self._lib.itsb_read_now(self._h, first, n, out.ctypes.data), "itsb_read_now")
+        return out
+
+    def trace(self, replica: int = 0) -> np.ndarray:
+        cap = self.compiled.caps.trace_records
+        out = np.zeros(cap, dtype=L.TRACE_DTYPE)
+        total = C.c_size_t()
+        self._check(self._lib.itsb_read_trace(self._h, replica, out.ctypes.data, cap, C.byref(total)), "itsb_read_trace")
+        self.trace_total = total.value
+        return out[:min(cap, total.value)]
+
+    def telemetry(self) -> np.ndarray:
+        out = np.zeros(L.TM_SIZE, dtype=np.uint64)
+        self._check(self._lib.itsb_read_telemetry(self._h, out.ctypes.data, L.TM_SIZE), "itsb_read_telemetry")
+        return out
+
+    def replica_telemetry(self, replica: int) -> np.ndarray:
+        out = np.zeros(L.TM_SIZE, dtype=np.uint64)
+        self._check(self._lib.itsb_read_replica_telemetry(self._h, replica, out.ctypes.data, L.TM_SIZE),
+                    "itsb_read_replica_telemetry")
+        return out
+
+    def allreduce_telemetry(self, comm: C.c_void_p) -> np.ndarray:
+        out = np.zeros(L.TM_SIZE, dtype=np.uint64)
+        self._check(self._lib.itsb_allreduce_telemetry(self._h, comm, out.ctypes.data, L.TM_SIZE),
+                    "itsb_allreduce_telemetry")
+        return out
+
+    def state_bytes(self) -> Dict[str, int]:
+        hot, arena = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.itsb_state_bytes(self._h, C.byref(hot), C.byref(arena)), "itsb_state_bytes")
+        return {"hot": hot.value, "arena": arena.value}
+
+
+def summarize(tm: np.ndarray) -> Dict[str, Any]:
+    """Names the slots of a telemetry vector."""
+    return {
+        "events": int(tm[L.TM_KIND0:L.TM_KIND0 + L.NUM_KINDS].sum()),
+        "counts": {L.KIND_NAMES[k]: int(tm[L.TM_KIND0 + k]) for k in range(1, L.NUM_KINDS)},
+        "packets_sent": int(tm[L.TM_PACKETS_SENT]), "bytes_sent": int(tm[L.TM_BYTES_SENT]),
+        "packets_received": int(tm[L.TM_PACKETS_RECEIVED]), "bytes_received": int(tm[L.TM_BYTES_RECEIVED]),
+        "delivered": int(tm[L.TM_DELIVERED]), "dropped": int(tm[L.TM_DROPPED]),
+        "user": [int(v) for v in tm[L.TM_USER0:L.TM_USER0 + 8]],
+        "latency_hist": [int(v) for v in tm[L.TM_LAT0:L.TM_LAT0 + L.LAT_BINS]],
+    }

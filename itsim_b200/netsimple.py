@@ -1,0 +1,199 @@
+"""
+The flagship workload: ``examples/network_simple`` (reference ``examples/network_simple/network_simple.py:42-387``
+on the override classes of ``network_simple_overrides.py``), built on this package's modelling API and compiled for
+the engine.  ``build()`` mirrors ``init()`` (network_simple.py:311-387); each ``_prog_*`` restates one process body
+as an IR program, citing the lines it follows.  RNG draw order per replica follows SURVEY.md Appendix B.
+"""
+from ipaddress import ip_network
+from typing import Optional
+
+from . import ir
+from .ir import (DST_BCAST, DST_ENT, DST_PKT_SRC, DST_SELF, NODE_ADDR, NODE_HOST, PKT_F0, PKT_F1, PKT_SIZE, PKT_TAG,
+                 R0, R1, R2, R3, SELF)
+from .model import Endpoint, Network, Simulator, Workstation
+from .random import constant, distribution_index, expo, normal, num_bytes
+from .units import B, GbPS, H, MIN, MS, US
+
+# program ids reported in trace records (shared with oracle/netsimple.py)
+PROG_DHCP_SERVE, PROG_BLINKING, PROG_CLIENT, PROG_MDNS, PROG_LLMNR = 1, 2, 3, 4, 5
+PROG_QUERY_MDNS, PROG_QUERY_LLMNR, PROG_TIMEOUT_HELPER, PROG_TX, PROG_DELIVER = 6, 7, 8, 9, 10
+
+# payload "content" values (network_simple.py:135-149,152-167,190-221)
+TAG_DISCOVER, TAG_OFFER, TAG_REQUEST, TAG_ACK, TAG_QUERY, TAG_RESOLVE, TAG_IAM = 1, 2, 3, 4, 5, 6, 7
+
+EXC_COMPLETE = 1          # Workstation._Complete (network_simple.py:78-79): a plain Exception, not an Interrupt
+STAT_QUERIES, STAT_RESOLVED, STAT_TIMEOUTS = 0, 1, 2
+
+NUM_ADDRESSES_RESERVED = 2
+MIN_NUM_ENDPOINTS = 3
+
+
+def _programs(sim: Simulator, num_workstations: int) -> None:
+    a = sim.asm
+    d_awake = sim.dist(expo(2.0 * H))                                         # network_simple.py:101
+    d_sleeping = sim.dist(expo(10.0 * MIN))                                   # :102
+    d_ready = sim.dist(expo(5.0 * US))                                        # :103
+    d_dhcp = sim.dist(num_bytes(normal(100.0 * B, 30.0 * B), header=240 * B))  # :128
+    d_dns = sim.dist(num_bytes(expo(192.0 * B), header=68 * B, upper=576 * B))  # :171
+    d_gap = sim.dist(expo(2.0 * MIN))                                         # :249
+    d_delta = sim.dist(normal(0.0 * B, 10.0 * B))                             # :250
+    d_name = sim.dist(distribution_index(num_workstations))                   # :371
+    c_timeout = sim.const(5.0)                                                # :263
+
+    # dhcp_serve, network_simple.py:152-167
+    a.program("dhcp_serve", PROG_DHCP_SERVE)
+    a.open(67)
+    a.label("loop")
+    a.recv()
+    a.jeqi(PKT_TAG, TAG_DISCOVER, "offer")
+    a.jeqi(PKT_TAG, TAG_REQUEST, "ack")
+    a.jmp("loop")
+    a.label("offer")
+    a.drawi(R0, d_dhcp)
+    a.send(DST_PKT_SRC, R0, TAG_OFFER)
+    a.jmp("loop")
+    a.label("ack")
+    a.drawi(R0, d_dhcp)
+    a.send(DST_PKT_SRC, R0, TAG_ACK)
+    a.jmp("loop")
+
+    # workstation_blinking + get_address_from_dhcp, network_simple.py:106-121,131-149
+    a.program("blinking", PROG_BLINKING)
+    a.label("loop")
+    a.node_sleep()
+    a.advance(d_sleeping)
+    a.open(68)
+    a.drawi(R0, d_dhcp)
+    a.send(DST_BCAST, R0, TAG_DISCOVER, port=67)
+    a.recv()
+    a.drawi(R0, d_dhcp)
+    a.send(DST_PKT_SRC, R0, TAG_REQUEST)
+    a.recv()
+    a.close()
+    a.advance(d_ready)
+    a.node_wake()
+    a.advance(d_awake)
+    a.jmp("loop")
+
+    # mdns_daemon, network_simple.py:174-222
+    a.program("mdns", PROG_MDNS)
+    a.label("top")
+    a.list_clear()
+    a.open(5353)
+    a.label("loop")
+    a.wait_awake(R0)                 # with ws.awake(): wait, remember when we awoke
+    a.recv()
+    a.jasleep(R0, "asleep")          # leaving the with: FellAsleep if the machine slept meanwhile
+    a.jeqi(PKT_TAG, TAG_QUERY, "query")
+    a.jeqi(PKT_TAG, TAG_IAM, "iam")
+    a.jeqi(PKT_TAG, TAG_RESOLVE, "resolve")
+    a.jmp("loop")
+    a.label("query")
+    a.list_push()
+    a.send(DST_BCAST, PKT_SIZE, TAG_RESOLVE, port=5353, f0=PKT_F0)
+    a.jmp("loop")
+    a.label("iam")
+    a.list_take(PKT_F0, "loop")
+    a.send(DST_ENT, PKT_SIZE, TAG_IAM, f0=PKT_F0, f1=PKT_F1)
+    a.jmp("loop")
+    a.label("resolve")
+    a.jne(PKT_F0, NODE_HOST, "loop")
+    a.drawi(R1, d_dns)
+    a.send(DST_BCAST, R1, TAG_IAM, port=5353, f0=NODE_HOST, f1=NODE_ADDR)
+    a.jmp("loop")
+    a.label("asleep")
+    a.close()
+    a.jmp("top")
+
+    # llmnr_daemon, network_simple.py:225-246
+    a.program("llmnr", PROG_LLMNR)
+    a.label("top")
+    a.open(5355)
+    a.label("loop")
+    a.wait_awake(R0)
+    a.recv()
+    a.jasleep(R0, "asleep")
+    a.jnei(PKT_TAG, TAG_RESOLVE, "loop")
+    a.jne(PKT_F0, NODE_HOST, "loop")
+    a.drawi(R1, d_dns)
+    a.send(DST_PKT_SRC, R1, TAG_IAM, f0=NODE_HOST, f1=NODE_ADDR)
+    a.jmp("loop")
+    a.label("asleep")
+    a.close()
+    a.jmp("top")
+
+    # client_activity, network_simple.py:283-305
+    a.program("client", PROG_CLIENT)
+    a.label("loop")
+    a.wait_awake()                   # ws.wait_until_awake(logger)
+    a.wait_awake(R0)                 # with ws.awake():
+    a.advance(d_gap)
+    a.jasleep(R0, "loop")            # FellAsleep -> caught -> next round
+    a.label("pick")
+    a.drawi(R1, d_name)              # next(name_next_query): index into names_ws
+    a.addi(R1, R1, 1)                # hostname id of "Workstation-{index+1}"
+    a.jeq(R1, NODE_HOST, "pick")
+    a.stat(STAT_QUERIES)
+    a.drawi(R0, d_dns)               # size_packet_base
+    a.spawn("query_mdns")
+    a.spawn("query_llmnr")
+    a.jmp("loop")
+
+    # _query / _query_mdns / _query_llmnr, network_simple.py:253-280 with the timeout guard of :84-98
+    for name, prog in (("query_mdns", PROG_QUERY_MDNS), ("query_llmnr", PROG_QUERY_LLMNR)):
+        a.program(name, prog)
+        a.open(0)
+        a.draw_addi(R0, R0, d_delta)                 # int(size_packet_base + next(size_packet_delta))
+        if name == "query_mdns":
+            a.send(DST_SELF, R0, TAG_QUERY, port=5353, f0=R1)
+        else:
+            a.send(DST_BCAST, R0, TAG_RESOLVE, port=5355, f0=R1)
+        a.wait_awake(R2)                             # with ws.awake(),
+        a.mov(R3, SELF)
+        a.spawn("timeout_helper", rd=R3)             #      ws.timeout(5.0): helper gets our handle, we keep its
+        a.recv(handler="timed_out")
+        a.stat(STAT_RESOLVED)
+        a.throw(R3, EXC_COMPLETE)                    # leaving timeout(): stop the helper
+        a.jasleep(R2, "end")                         # leaving awake(): FellAsleep, swallowed at :268
+        a.label("end")
+        a.close()
+        a.exit()
+        a.label("timed_out")                         # _Complete in the body -> Workstation.Timeout, swallowed :266
+        a.stat(STAT_TIMEOUTS)
+        a.close()
+        a.exit()
+
+    # Workstation._wait_for_timeout, network_simple.py:92-98
+    a.program("timeout_helper", PROG_TIMEOUT_HELPER)
+    a.advance_const(c_timeout, handler="done")
+    a.throw(R3, EXC_COMPLETE)
+    a.label("done")
+    a.exit()
+
+
+def build(cidr: str = "192.168.4.0/24", num_endpoints: Optional[int] = None, trace_records: int = 0) -> Simulator:
+    """``init()`` of network_simple.py:311-387 (argument defaults :315-316)."""
+    sim = Simulator()
+    num_addresses = ip_network(cidr).num_addresses - NUM_ADDRESSES_RESERVED
+    if num_addresses < MIN_NUM_ENDPOINTS:
+        raise ValueError(f"Unsuitable CIDR prefix for simulating a non-trivial network: {cidr}")
+    net_local = Network(sim, cidr=cidr, bandwidth=constant(1 * GbPS), latency=normal(5 * MS, 1 * MS))
+    Endpoint("Router", net_local)
+    if num_endpoints is None:
+        num_endpoints = max(MIN_NUM_ENDPOINTS, int(0.2 * num_addresses))
+    num_endpoints = max(MIN_NUM_ENDPOINTS, num_endpoints)
+    num_workstations = num_endpoints - 1
+    num_mdns = int(0.9 * num_workstations)
+
+    _programs(sim, num_workstations)
+
+    dhcp_server = Endpoint("DHCPServer", net_local)
+    dhcp_server.install("dhcp_serve")
+    for n in range(num_workstations):
+        ws = Workstation(f"Workstation-{n + 1}", net_local, host_id=n + 1)
+        ws.install("blinking")
+        ws.install("client")
+        ws.install("mdns" if n <= num_mdns else "llmnr")   # sic, network_simple.py:380
+    sim.caps["trace_records"] = trace_records
+    sim.num_workstations = num_workstations
+    return sim

@@ -153,7 +153,7 @@ class Simulator(Named):
         self._is_running = False
         self._counter = 0
         self._processes_alive: "weakref.WeakSet[Process]" = weakref.WeakSet()
-        # Observation hooks used only by the oracle's tracer (oracle/trace.py); None in plain use.
+        # Observation hooks used only by the oracle's tracer (oracle/evtrace.py); None in plain use.
         self._on_pop: Optional[Callable[[_Event], None]] = None
         self.num_pops = 0
 
@@ -271,6 +271,7 @@ class Process(TaggedObject):
         # True for the helper processes this kernel spawns itself (select / balk); the oracle's tracer does not
         # count their hops as model events.
         self.hidden = False
+        self._blocked_in: Optional[str] = None  # "advance" | "wait" while parked (read by the tracer)
 
     # -- identity ----------------------------------------------------------------------------------
     @staticmethod
@@ -345,10 +346,11 @@ class Process(TaggedObject):
             self._inbox_args, self._inbox_kwargs = (), {}
             self._sim._processes_alive.discard(self)
 
-    def _yield_to_simulator(self) -> None:
+    def _yield_to_simulator(self, reason: str = "wait") -> None:
         """Called on the worker: give the baton back and wait for the next switch/throw."""
         worker = self._worker
         assert worker is not None
+        self._blocked_in = reason
         self._back.release()
         worker.go.acquire()
         _tls.process = self
@@ -380,7 +382,7 @@ local = _Local()
 
 
 def pause() -> None:
-    Process.current()._yield_to_simulator()
+    Process.current()._yield_to_simulator("wait")
 
 
 def advance(delay: float) -> None:
@@ -388,7 +390,7 @@ def advance(delay: float) -> None:
     sim = proc._sim
     id_wakeup = sim._schedule(delay, proc.switch)
     try:
-        proc._yield_to_simulator()
+        proc._yield_to_simulator("advance")
     except Interrupt:
         sim._cancel(id_wakeup)
         raise

@@ -1,0 +1,176 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- host emulation of the device interpreter.
+ *
+ * Compiles itsim_b200/csrc/itsb_core.cuh with ITSB_W == 1 (one "lane") as plain C++ so the unit tests that run
+ * without a GPU (pytest -m "not gpu") can check the interpreter's semantics against the oracle's golden traces.
+ * It exports the same itsb_* symbols as the product library so the same ctypes wrapper drives it, but it is built
+ * into tests/hostemu/ and only tests load it (explicitly, by path).  The product package never does: without the
+ * CUDA library it fails loudly (itsim_b200/_lib.py).
+ */
+#include <stdlib.h>
+#include <string>
+#include <vector>
+#include "../../itsim_b200/csrc/itsb_host_common.h"
+
+using namespace itsb;
+
+struct itsb_engine {
+    itsb_model_desc desc;
+    std::vector<uint64_t> code;
+    std::vector<itsb_entry> entries;
+    std::vector<itsb_dist> dists;
+    std::vector<double> consts;
+    std::vector<itsb_net> nets;
+    std::vector<itsb_node> nodes;
+    std::vector<itsb_initproc> init;
+    Model model;
+    Layout layout;
+    uint64_t n_replicas = 0, seed = 0, first = 0;
+    std::vector<unsigned char> hot;
+    std::vector<ArenaNode> arena;
+    std::vector<uint32_t> arena_free;
+    std::vector<itsb_trace_rec> trace;
+    uint64_t last_events = 0, launches = 0;
+    std::string err;
+    bool loaded = false;
+};
+
+extern "C" {
+
+int itsb_abi_version(void) { return ITSB_ABI_VERSION; }
+
+int itsb_create(int, itsb_engine** out) { *out = new itsb_engine(); return ITSB_OK; }
+
+int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const* blobs, const size_t* sizes) {
+    if (!validate_model(*d, blobs, sizes, e->err)) return ITSB_ERR_BAD_MODEL;
+    e->desc = *d;
+    e->code.assign((const uint64_t*)blobs[0], (const uint64_t*)blobs[0] + d->n_code);
+    e->entries.assign((const itsb_entry*)blobs[1], (const itsb_entry*)blobs[1] + d->n_entries);
+    e->dists.assign((const itsb_dist*)blobs[2], (const itsb_dist*)blobs[2] + d->n_dists);
+    e->consts.assign((const double*)blobs[3], (const double*)blobs[3] + d->n_consts);
+    e->nets.assign((const itsb_net*)blobs[4], (const itsb_net*)blobs[4] + d->n_nets);
+    e->nodes.assign((const itsb_node*)blobs[5], (const itsb_node*)blobs[5] + d->n_nodes);
+    e->init.assign((const itsb_initproc*)blobs[6], (const itsb_initproc*)blobs[6] + d->n_init);
+    Model& m = e->model;
+    m.code = e->code.data(); m.entries = e->entries.data(); m.dists = e->dists.data(); m.consts = e->consts.data();
+    m.nets = e->nets.data(); m.nodes = e->nodes.data(); m.init = e->init.data();
+    m.n_code = d->n_code; m.n_entries = d->n_entries; m.n_dists = d->n_dists; m.n_consts = d->n_consts;
+    m.n_nets = d->n_nets; m.n_nodes = d->n_nodes; m.n_init = d->n_init;
+    e->layout = compute_layout(*d);
+    e->loaded = true;
+    return ITSB_OK;
+}
+
+static void bind(itsb_engine* e, Rep& R, uint64_t r) {
+    bind_views(R, e->hot.data() + r * e->layout.hot_bytes, &e->layout);
+    R.m = &e->model;
+    R.arena = e->arena.data() + r * e->layout.arena_nodes;
+    R.arena_free = e->arena_free.data() + r * e->layout.arena_nodes;
+    R.trace = e->layout.trace_cap ? e->trace.data() + r * e->layout.trace_cap : nullptr;
+}
+
+int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first) {
+    if (!e->loaded) return ITSB_ERR_STATE;
+    e->n_replicas = n; e->seed = seed; e->first = first;
+    e->hot.assign(n * e->layout.hot_bytes, 0);
+    e->arena.assign(n * e->layout.arena_nodes, ArenaNode());
+    e->arena_free.resize(n * e->layout.arena_nodes);
+    e->trace.assign(n * e->layout.trace_cap, itsb_trace_rec());
+    for (uint64_t r = 0; r < n; ++r) {
+        Rep R; bind(e, R, r);
+        for (uint32_t i = 0; i < e->layout.arena_nodes; ++i) R.arena_free[i] = e->layout.arena_nodes - 1 - i;
+        init_replica(R, first + r);
+    }
+    return ITSB_OK;
+}
+
+int itsb_run_async(itsb_engine* e, double duration) {
+    if (!e->n_replicas) return ITSB_ERR_STATE;
+    Seed seed = {(uint32_t)e->seed, (uint32_t)(e->seed >> 32)};
+    e->last_events = 0;
+    for (uint64_t r = 0; r < e->n_replicas; ++r) {
+        Rep R; bind(e, R, r);
+        run_replica(R, seed, duration);
+        e->last_events += R.events;
+    }
+    e->launches += 1;
+    return ITSB_OK;
+}
+
+int64_t itsb_first_failed_replica(itsb_engine* e) {
+    for (uint64_t r = 0; r < e->n_replicas; ++r)
+        if (((Hdr*)(e->hot.data() + r * e->layout.hot_bytes))->status != 0) return (int64_t)r;
+    return -1;
+}
+
+int itsb_sync(itsb_engine* e, uint64_t* events_done) {
+    if (events_done) *events_done = e->last_events;
+    int64_t bad = itsb_first_failed_replica(e);
+    if (bad >= 0) return ((Hdr*)(e->hot.data() + bad * e->layout.hot_bytes))->status;
+    return ITSB_OK;
+}
+
+int itsb_run(itsb_engine* e, double duration, uint64_t* events_done) {
+    int rc = itsb_run_async(e, duration);
+    if (rc) return rc;
+    return itsb_sync(e, events_done);
+}
+
+int itsb_last_run_ms(itsb_engine*, float* ms) { *ms = 0.f; return ITSB_OK; }
+int itsb_launch_count(itsb_engine* e, uint64_t* n) { *n = e->launches; return ITSB_OK; }
+
+int itsb_read_now(itsb_engine* e, uint64_t first, uint64_t n, double* dst) {
+    if (first + n > e->n_replicas) return ITSB_ERR_STATE;
+    for (uint64_t i = 0; i < n; ++i) dst[i] = ((Hdr*)(e->hot.data() + (first + i) * e->layout.hot_bytes))->now;
+    return ITSB_OK;
+}
+
+int itsb_read_trace(itsb_engine* e, uint64_t replica, itsb_trace_rec* dst, size_t cap, size_t* n_total) {
+    if (replica >= e->n_replicas) return ITSB_ERR_STATE;
+    Hdr* H = (Hdr*)(e->hot.data() + replica * e->layout.hot_bytes);
+    if (n_total) *n_total = H->trace_count;
+    size_t n = H->trace_count < e->layout.trace_cap ? H->trace_count : e->layout.trace_cap;
+    if (n > cap) n = cap;
+    if (n) memcpy(dst, e->trace.data() + replica * e->layout.trace_cap, n * sizeof(itsb_trace_rec));
+    return ITSB_OK;
+}
+
+int itsb_read_replica_telemetry(itsb_engine* e, uint64_t replica, uint64_t* dst, size_t n) {
+    if (replica >= e->n_replicas || n < ITSB_TM_SIZE) return ITSB_ERR_STATE;
+    memcpy(dst, e->hot.data() + replica * e->layout.hot_bytes + e->layout.off_stats, 8 * ITSB_TM_SIZE);
+    return ITSB_OK;
+}
+
+int itsb_read_telemetry(itsb_engine* e, uint64_t* dst, size_t n) {
+    if (n < ITSB_TM_SIZE) return ITSB_ERR_STATE;
+    for (size_t i = 0; i < ITSB_TM_SIZE; ++i) dst[i] = 0;
+    for (uint64_t r = 0; r < e->n_replicas; ++r) {
+        const uint64_t* s = (const uint64_t*)(e->hot.data() + r * e->layout.hot_bytes + e->layout.off_stats);
+        for (size_t i = 0; i < ITSB_TM_SIZE; ++i) dst[i] += s[i];
+    }
+    return ITSB_OK;
+}
+
+int itsb_allreduce_telemetry(itsb_engine* e, void*, uint64_t* dst, size_t n) { return itsb_read_telemetry(e, dst, n); }
+int itsb_nccl_unique_id(void*, size_t) { return ITSB_ERR_NCCL; }
+int itsb_nccl_comm_init(itsb_engine*, int, int, const void*, void**) { return ITSB_ERR_NCCL; }
+int itsb_nccl_comm_destroy(void*) { return ITSB_ERR_NCCL; }
+
+int itsb_replica_status(itsb_engine* e, uint64_t replica, int32_t* status, uint64_t* detail) {
+    if (replica >= e->n_replicas) return ITSB_ERR_STATE;
+    Hdr* H = (Hdr*)(e->hot.data() + replica * e->layout.hot_bytes);
+    if (status) *status = H->status;
+    if (detail) *detail = H->detail;
+    return ITSB_OK;
+}
+
+int itsb_state_bytes(itsb_engine* e, uint64_t* hot, uint64_t* arena) {
+    if (hot) *hot = e->layout.hot_bytes;
+    if (arena) *arena = (uint64_t)e->layout.arena_nodes * (sizeof(ArenaNode) + 4);
+    return ITSB_OK;
+}
+
+const char* itsb_last_error(itsb_engine* e) { return e ? e->err.c_str() : ""; }
+void itsb_destroy(itsb_engine* e) { delete e; }
+
+}  // extern "C"
