@@ -1,0 +1,528 @@
+/*
+ * itsb_abi.cu -- libitsim_b200.so: the C ABI of include/itsb.h and the sm_100a kernels behind it.
+ *
+ * Kernels (all hand-written for B200; no tensor cores -- nothing here is a contraction):
+ *   k_run          persistent, one CTA per SM, one warp per resident replica.  A warp claims a replica from a
+ *                  global ticket, pulls its hot block HBM -> shared memory with one TMA bulk copy
+ *                  (cp.async.bulk + mbarrier), runs Simulator.run(duration) on it (itsb_core.cuh), pushes the block
+ *                  back with a bulk store, claims the next.  Static model tables are staged once per CTA.
+ *   k_make_template / k_fan_out   build the t = 0 state once, replicate it to every replica with 128-bit copies.
+ *   k_reduce_telemetry            column sums of the per-replica counters / histograms.
+ *
+ * Layout in HBM: replica r owns hot[r * hot_bytes] (event pool, process table, sockets, nodes, in-flight packets,
+ * counters: everything the warp touches per event), arena[r * arena_nodes] (32-byte queue nodes, one DRAM sector
+ * each) with its free stack, and optionally trace[r * trace_cap].
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "itsb_host_common.h"
+
+using namespace itsb;
+
+/* ---- TMA bulk copies (non-tensor form) --------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+/* ---- kernel parameters ---------------------------------------------------------------------------------------------- */
+struct RunParams {
+    Model model;            /* device pointers */
+    Layout layout;
+    unsigned char* hot;
+    ArenaNode* arena;
+    uint32_t* arena_free;
+    itsb_trace_rec* trace;
+    uint64_t n_replicas;
+    uint64_t seed;
+    double duration;
+    unsigned long long* ticket;       /* next replica to claim */
+    unsigned long long* events_done;  /* events processed by this launch */
+    long long* first_failed;          /* min index of a replica with non-zero status, or LLONG_MAX */
+    uint32_t static_bytes;            /* size of the CTA-shared copy of the model tables */
+    uint32_t warps_per_cta;
+};
+
+struct StaticOffsets { uint32_t code, entries, dists, consts, nets, nodes, total; };
+
+static inline StaticOffsets static_offsets(const itsb_model_desc& d) {
+    StaticOffsets o;
+    uint32_t off = 0;
+    o.code = off;    off = align_up(off + 8 * d.n_code, 16);
+    o.entries = off; off = align_up(off + (uint32_t)sizeof(itsb_entry) * d.n_entries, 16);
+    o.dists = off;   off = align_up(off + (uint32_t)sizeof(itsb_dist) * d.n_dists, 16);
+    o.consts = off;  off = align_up(off + 8 * d.n_consts, 16);
+    o.nets = off;    off = align_up(off + (uint32_t)sizeof(itsb_net) * d.n_nets, 16);
+    o.nodes = off;   off = align_up(off + (uint32_t)sizeof(itsb_node) * d.n_nodes, 16);
+    o.total = align_up(off, 128);
+    return o;
+}
+
+__device__ __forceinline__ void cta_copy(void* dst, const void* src, uint32_t bytes) {
+    const uint4* s = (const uint4*)src;
+    uint4* d = (uint4*)dst;
+    for (uint32_t i = threadIdx.x; i < (bytes + 15) / 16; i += blockDim.x) d[i] = s[i];
+}
+
+/* Stages the model tables into shared memory (they are padded to 16 bytes on the device) and returns a Model whose
+ * pointers address the shared copy. */
+__device__ __forceinline__ Model stage_model(const Model& g, unsigned char* sm) {
+    Model m = g;
+    uint32_t off = 0;
+    cta_copy(sm + off, g.code, 8 * g.n_code);                 m.code = (const u64*)(sm + off);          off = (off + 8 * g.n_code + 15) & ~15u;
+    cta_copy(sm + off, g.entries, 8 * g.n_entries);           m.entries = (const itsb_entry*)(sm + off); off = (off + 8 * g.n_entries + 15) & ~15u;
+    cta_copy(sm + off, g.dists, 56 * g.n_dists);              m.dists = (const itsb_dist*)(sm + off);    off = (off + 56 * g.n_dists + 15) & ~15u;
+    cta_copy(sm + off, g.consts, 8 * g.n_consts);             m.consts = (const double*)(sm + off);      off = (off + 8 * g.n_consts + 15) & ~15u;
+    cta_copy(sm + off, g.nets, 32 * g.n_nets);                m.nets = (const itsb_net*)(sm + off);      off = (off + 32 * g.n_nets + 15) & ~15u;
+    cta_copy(sm + off, g.nodes, 16 * g.n_nodes);              m.nodes = (const itsb_node*)(sm + off);
+    __syncthreads();
+    return m;
+}
+
+/* ---- the engine kernel ------------------------------------------------------------------------------------------------ */
+extern "C" __global__ void __launch_bounds__(512, 1) k_run(const RunParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const Model m = stage_model(p.model, smem);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* hot = smem + p.static_bytes + (size_t)warp * p.layout.hot_bytes;
+    uint64_t* bar = (uint64_t*)(smem + p.static_bytes + (size_t)p.warps_per_cta * p.layout.hot_bytes) + warp;
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const Seed seed = {(uint32_t)p.seed, (uint32_t)(p.seed >> 32)};
+    uint32_t phase = 0;
+    for (;;) {
+        unsigned long long r = 0;
+        if (lane == 0) r = atomicAdd(p.ticket, 1ull);
+        r = __shfl_sync(0xFFFFFFFFu, r, 0);
+        if (r >= p.n_replicas) break;
+        /* HBM -> shared: one bulk copy of the whole hot block, completion on the warp's mbarrier */
+        if (lane == 0) {
+            mbar_expect_tx(bar, p.layout.hot_bytes);
+            bulk_g2s(hot, p.hot + r * p.layout.hot_bytes, p.layout.hot_bytes, bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        Rep R;
+        bind_views(R, hot, &p.layout);
+        R.m = m;
+        R.arena = p.arena + r * p.layout.arena_nodes;
+        R.arena_free = p.arena_free + r * p.layout.arena_nodes;
+        R.trace = p.trace ? p.trace + r * p.layout.trace_cap : nullptr;
+        run_replica(R, seed, p.duration);
+        __syncwarp();
+        const int32_t status = R.hdr->status;
+        /* shared -> HBM */
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(p.hot + r * p.layout.hot_bytes, hot, p.layout.hot_bytes);
+            bulk_wait_all();
+            atomicAdd(p.events_done, (unsigned long long)R.events);
+            if (status != 0) atomicMin(p.first_failed, (long long)r);
+        }
+        __syncwarp();
+    }
+}
+
+/* Builds the t = 0 hot block once (replica id patched in by k_fan_out). */
+extern "C" __global__ void k_make_template(const RunParams p, unsigned char* tmpl, ArenaNode* arena0, uint32_t* free0) {
+    Rep R;
+    bind_views(R, tmpl, &p.layout);
+    R.m = p.model;
+    R.arena = arena0;
+    R.arena_free = free0;
+    R.trace = nullptr;
+    init_replica(R, 0);
+}
+
+/* Replicates the template into every replica's hot block and fills the arena free stacks. */
+extern "C" __global__ void k_fan_out(const RunParams p, const unsigned char* tmpl, uint64_t first_replica_id) {
+    const uint32_t vec = p.layout.hot_bytes / 16;
+    const uint4* src = (const uint4*)tmpl;
+    for (uint64_t r = blockIdx.x; r < p.n_replicas; r += gridDim.x) {
+        uint4* dst = (uint4*)(p.hot + r * p.layout.hot_bytes);
+        for (uint32_t i = threadIdx.x; i < vec; i += blockDim.x) dst[i] = src[i];
+        uint32_t* fr = p.arena_free + r * p.layout.arena_nodes;
+        for (uint32_t i = threadIdx.x; i < p.layout.arena_nodes; i += blockDim.x) fr[i] = p.layout.arena_nodes - 1 - i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Hdr* H = (Hdr*)dst;
+            uint64_t id = first_replica_id + r;
+            H->replica_lo = (uint32_t)id;
+            H->replica_hi = (uint32_t)(id >> 32);
+        }
+    }
+}
+
+extern "C" __global__ void k_reduce_telemetry(const unsigned char* hot, uint32_t hot_bytes, uint32_t off_stats,
+                                              uint64_t n, unsigned long long* out) {
+    const uint32_t c = threadIdx.x;
+    if (c >= ITSB_TM_SIZE) return;
+    unsigned long long acc = 0;
+    for (uint64_t r = blockIdx.x; r < n; r += gridDim.x)
+        acc += ((const unsigned long long*)(hot + r * hot_bytes + off_stats))[c];
+    if (acc) atomicAdd(out + c, acc);
+}
+
+/* ---- host side ---------------------------------------------------------------------------------------------------------- */
+struct itsb_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaDeviceProp prop;
+    itsb_model_desc desc;
+    bool loaded = false;
+    void* d_tables[ITSB_NUM_BLOBS] = {nullptr};
+    RunParams rp;
+    StaticOffsets so;
+    unsigned char* d_hot = nullptr;
+    ArenaNode* d_arena = nullptr;
+    uint32_t* d_arena_free = nullptr;
+    itsb_trace_rec* d_trace = nullptr;
+    unsigned long long* d_ticket = nullptr;       /* [0] ticket, [1] events_done */
+    long long* d_first_failed = nullptr;
+    unsigned long long* d_telemetry = nullptr;
+    uint64_t n_replicas = 0;
+    uint64_t launches = 0;
+    uint32_t warps_per_cta = 0, grid = 0;
+    size_t smem_bytes = 0;
+    bool run_pending = false;
+    float last_ms = 0.f;
+    long long first_failed = -1;
+    std::string err;
+};
+
+#define CU(e, call)                                                                            \
+    do {                                                                                       \
+        cudaError_t _rc = (call);                                                              \
+        if (_rc != cudaSuccess) {                                                              \
+            (e)->err = std::string(#call) + ": " + cudaGetErrorString(_rc);                    \
+            return ITSB_ERR_CUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+static void free_replicas(itsb_engine* e) {
+    cudaFree(e->d_hot); cudaFree(e->d_arena); cudaFree(e->d_arena_free); cudaFree(e->d_trace);
+    e->d_hot = nullptr; e->d_arena = nullptr; e->d_arena_free = nullptr; e->d_trace = nullptr;
+    e->n_replicas = 0;
+}
+
+extern "C" {
+
+int itsb_abi_version(void) { return ITSB_ABI_VERSION; }
+
+int itsb_create(int device, itsb_engine** out) {
+    if (!out) return ITSB_ERR_STATE;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return ITSB_ERR_NO_DEVICE;
+    }
+    itsb_engine* e = new itsb_engine();
+    e->device = device;
+    *out = e;
+    CU(e, cudaSetDevice(device));
+    CU(e, cudaGetDeviceProperties(&e->prop, device));
+    CU(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CU(e, cudaEventCreate(&e->ev_start));
+    CU(e, cudaEventCreate(&e->ev_stop));
+    CU(e, cudaMalloc(&e->d_ticket, 2 * sizeof(unsigned long long)));
+    CU(e, cudaMalloc(&e->d_first_failed, sizeof(long long)));
+    CU(e, cudaMalloc(&e->d_telemetry, ITSB_TM_SIZE * sizeof(unsigned long long)));
+    return ITSB_OK;
+}
+
+int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const* blobs, const size_t* sizes) {
+    if (!e || !d || !blobs || !sizes) return ITSB_ERR_STATE;
+    if (!validate_model(*d, blobs, sizes, e->err)) return ITSB_ERR_BAD_MODEL;
+    CU(e, cudaSetDevice(e->device));
+    free_replicas(e);
+    for (int i = 0; i < ITSB_NUM_BLOBS; ++i) { cudaFree(e->d_tables[i]); e->d_tables[i] = nullptr; }
+    e->desc = *d;
+    for (int i = 0; i < ITSB_NUM_BLOBS; ++i) {
+        size_t padded = (sizes[i] + 15) / 16 * 16 + 16;   /* staged with 128-bit loads */
+        CU(e, cudaMalloc(&e->d_tables[i], padded));
+        CU(e, cudaMemsetAsync(e->d_tables[i], 0, padded, e->stream));
+        if (sizes[i]) CU(e, cudaMemcpyAsync(e->d_tables[i], blobs[i], sizes[i], cudaMemcpyHostToDevice, e->stream));
+    }
+    CU(e, cudaStreamSynchronize(e->stream));
+    memset(&e->rp, 0, sizeof(e->rp));
+    Model& m = e->rp.model;
+    m.code = (const u64*)e->d_tables[ITSB_BLOB_CODE];
+    m.entries = (const itsb_entry*)e->d_tables[ITSB_BLOB_ENTRIES];
+    m.dists = (const itsb_dist*)e->d_tables[ITSB_BLOB_DISTS];
+    m.consts = (const double*)e->d_tables[ITSB_BLOB_CONSTS];
+    m.nets = (const itsb_net*)e->d_tables[ITSB_BLOB_NETS];
+    m.nodes = (const itsb_node*)e->d_tables[ITSB_BLOB_NODES];
+    m.init = (const itsb_initproc*)e->d_tables[ITSB_BLOB_INIT];
+    m.n_code = d->n_code; m.n_entries = d->n_entries; m.n_dists = d->n_dists; m.n_consts = d->n_consts;
+    m.n_nets = d->n_nets; m.n_nodes = d->n_nodes; m.n_init = d->n_init;
+    e->rp.layout = compute_layout(*d);
+    e->so = static_offsets(*d);
+    e->rp.static_bytes = e->so.total;
+
+    /* one CTA per SM; as many resident replicas (warps) as shared memory holds */
+    const size_t smem_max = e->prop.sharedMemPerBlockOptin;
+    const size_t per_warp = (size_t)e->rp.layout.hot_bytes + 8;
+    if (e->so.total + per_warp + 128 > smem_max) { e->err = "model does not fit one warp's shared memory"; return ITSB_ERR_BAD_MODEL; }
+    uint32_t w = (uint32_t)((smem_max - e->so.total - 128) / per_warp);
+    if (w > 16) w = 16;
+    e->warps_per_cta = w;
+    e->rp.warps_per_cta = w;
+    e->smem_bytes = e->so.total + (size_t)w * e->rp.layout.hot_bytes + (size_t)w * 8 + 64;
+    e->grid = (uint32_t)e->prop.multiProcessorCount;
+    CU(e, cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    e->loaded = true;
+    return ITSB_OK;
+}
+
+int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first_replica_id) {
+    if (!e || !e->loaded || n == 0) return ITSB_ERR_STATE;
+    CU(e, cudaSetDevice(e->device));
+    free_replicas(e);
+    const Layout& L = e->rp.layout;
+    CU(e, cudaMalloc(&e->d_hot, (size_t)n * L.hot_bytes));
+    CU(e, cudaMalloc(&e->d_arena, (size_t)n * L.arena_nodes * sizeof(ArenaNode)));
+    CU(e, cudaMalloc(&e->d_arena_free, (size_t)n * L.arena_nodes * sizeof(uint32_t)));
+    if (L.trace_cap) CU(e, cudaMalloc(&e->d_trace, (size_t)n * L.trace_cap * sizeof(itsb_trace_rec)));
+    e->rp.hot = e->d_hot; e->rp.arena = e->d_arena; e->rp.arena_free = e->d_arena_free; e->rp.trace = e->d_trace;
+    e->rp.n_replicas = n; e->rp.seed = seed;
+    e->rp.ticket = e->d_ticket; e->rp.events_done = e->d_ticket + 1; e->rp.first_failed = e->d_first_failed;
+    unsigned char* tmpl = nullptr;
+    CU(e, cudaMalloc(&tmpl, L.hot_bytes));
+    CU(e, cudaMemsetAsync(tmpl, 0, L.hot_bytes, e->stream));
+    k_make_template<<<1, 32, 0, e->stream>>>(e->rp, tmpl, e->d_arena, e->d_arena_free);
+    CU(e, cudaGetLastError());
+    uint32_t blocks = (uint32_t)(n < (uint64_t)e->prop.multiProcessorCount * 8 ? n : (uint64_t)e->prop.multiProcessorCount * 8);
+    k_fan_out<<<blocks, 256, 0, e->stream>>>(e->rp, tmpl, first_replica_id);
+    CU(e, cudaGetLastError());
+    CU(e, cudaStreamSynchronize(e->stream));
+    cudaFree(tmpl);
+    const long long none = 0x7FFFFFFFFFFFFFFFll;
+    CU(e, cudaMemcpy(e->d_first_failed, &none, sizeof(none), cudaMemcpyHostToDevice));
+    CU(e, cudaMemset(e->d_ticket, 0, 2 * sizeof(unsigned long long)));
+    e->launches += 2;
+    e->n_replicas = n;
+    e->first_failed = -1;
+    e->run_pending = false;
+    return ITSB_OK;
+}
+
+int itsb_run_async(itsb_engine* e, double duration) {
+    if (!e || !e->n_replicas) return ITSB_ERR_STATE;
+    CU(e, cudaSetDevice(e->device));
+    /* launches queue on the engine's stream: the ticket is reset per launch, events_done and first_failed
+       accumulate until itsb_sync collects them */
+    CU(e, cudaMemsetAsync(e->d_ticket, 0, sizeof(unsigned long long), e->stream));
+    e->rp.duration = duration;
+    if (!e->run_pending) CU(e, cudaEventRecord(e->ev_start, e->stream));
+    k_run<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
+    CU(e, cudaGetLastError());
+    CU(e, cudaEventRecord(e->ev_stop, e->stream));
+    e->launches += 1;
+    e->run_pending = true;
+    return ITSB_OK;
+}
+
+int itsb_sync(itsb_engine* e, uint64_t* events_done) {
+    if (!e) return ITSB_ERR_STATE;
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaStreamSynchronize(e->stream));
+    if (e->run_pending) {
+        e->run_pending = false;
+        CU(e, cudaEventElapsedTime(&e->last_ms, e->ev_start, e->ev_stop));
+    }
+    unsigned long long host[2] = {0, 0};
+    long long ff = 0;
+    const long long none = 0x7FFFFFFFFFFFFFFFll;
+    CU(e, cudaMemcpy(host, e->d_ticket, sizeof(host), cudaMemcpyDeviceToHost));
+    CU(e, cudaMemcpy(&ff, e->d_first_failed, sizeof(ff), cudaMemcpyDeviceToHost));
+    CU(e, cudaMemset(e->d_ticket + 1, 0, sizeof(unsigned long long)));
+    if (events_done) *events_done = host[1];
+    if (ff != none) {
+        e->first_failed = ff;
+        Hdr h;
+        CU(e, cudaMemcpy(&h, e->d_hot + (size_t)ff * e->rp.layout.hot_bytes, sizeof(Hdr), cudaMemcpyDeviceToHost));
+        return h.status;
+    }
+    return ITSB_OK;
+}
+
+int itsb_run(itsb_engine* e, double duration, uint64_t* events_done) {
+    int rc = itsb_run_async(e, duration);
+    if (rc) return rc;
+    return itsb_sync(e, events_done);
+}
+
+int itsb_last_run_ms(itsb_engine* e, float* ms) { if (!e || !ms) return ITSB_ERR_STATE; *ms = e->last_ms; return ITSB_OK; }
+int itsb_launch_count(itsb_engine* e, uint64_t* n) { if (!e || !n) return ITSB_ERR_STATE; *n = e->launches; return ITSB_OK; }
+
+int itsb_read_now(itsb_engine* e, uint64_t first, uint64_t n, double* dst) {
+    if (!e || first + n > e->n_replicas) return ITSB_ERR_STATE;
+    CU(e, cudaSetDevice(e->device));
+    /* now is the first field of each hot block: a strided 2-D copy */
+    CU(e, cudaMemcpy2D(dst, sizeof(double), e->d_hot + (size_t)first * e->rp.layout.hot_bytes, e->rp.layout.hot_bytes,
+                       sizeof(double), n, cudaMemcpyDeviceToHost));
+    return ITSB_OK;
+}
+
+int itsb_read_trace(itsb_engine* e, uint64_t replica, itsb_trace_rec* dst, size_t cap, size_t* n_total) {
+    if (!e || replica >= e->n_replicas) return ITSB_ERR_STATE;
+    CU(e, cudaSetDevice(e->device));
+    Hdr h;
+    CU(e, cudaMemcpy(&h, e->d_hot + (size_t)replica * e->rp.layout.hot_bytes, sizeof(Hdr), cudaMemcpyDeviceToHost));
+    if (n_total) *n_total = h.trace_count;
+    size_t n = h.trace_count < e->rp.layout.trace_cap ? h.trace_count : e->rp.layout.trace_cap;
+    if (n > cap) n = cap;
+    if (n && e->d_trace)
+        CU(e, cudaMemcpy(dst, e->d_trace + (size_t)replica * e->rp.layout.trace_cap, n * sizeof(itsb_trace_rec), cudaMemcpyDeviceToHost));
+    return ITSB_OK;
+}
+
+static int reduce_telemetry(itsb_engine* e) {
+    CU(e, cudaMemsetAsync(e->d_telemetry, 0, ITSB_TM_SIZE * sizeof(unsigned long long), e->stream));
+    uint32_t blocks = (uint32_t)(e->n_replicas < 1024 ? e->n_replicas : 1024);
+    k_reduce_telemetry<<<blocks, 96, 0, e->stream>>>(e->d_hot, e->rp.layout.hot_bytes, e->rp.layout.off_stats, e->n_replicas, e->d_telemetry);
+    CU(e, cudaGetLastError());
+    e->launches += 1;
+    return ITSB_OK;
+}
+
+int itsb_read_telemetry(itsb_engine* e, uint64_t* dst, size_t n) {
+    if (!e || !e->n_replicas || n < ITSB_TM_SIZE) return ITSB_ERR_STATE;
+    CU(e, cudaSetDevice(e->device));
+    int rc = reduce_telemetry(e);
+    if (rc) return rc;
+    CU(e, cudaMemcpyAsync(dst, e->d_telemetry, ITSB_TM_SIZE * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return ITSB_OK;
+}
+
+int itsb_read_replica_telemetry(itsb_engine* e, uint64_t replica, uint64_t* dst, size_t n) {
+    if (!e || replica >= e->n_replicas || n < ITSB_TM_SIZE) return ITSB_ERR_STATE;
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaMemcpy(dst, e->d_hot + (size_t)replica * e->rp.layout.hot_bytes + e->rp.layout.off_stats,
+                     ITSB_TM_SIZE * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return ITSB_OK;
+}
+
+/* ---- NCCL, resolved at run time so the library loads without it ------------------------------------------------------ */
+typedef int (*nccl_get_unique_id_t)(void*);
+struct nccl_uid { char internal[128]; };
+typedef int (*nccl_comm_init_rank_fn)(void**, int, nccl_uid, int);
+typedef int (*nccl_comm_destroy_fn)(void*);
+typedef int (*nccl_all_reduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+static void* g_nccl = nullptr;
+static void* nccl_sym(const char* name) {
+    if (!g_nccl) g_nccl = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!g_nccl) g_nccl = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    return g_nccl ? dlsym(g_nccl, name) : nullptr;
+}
+
+int itsb_nccl_unique_id(void* id128, size_t cap) {
+    if (cap < 128) return ITSB_ERR_STATE;
+    nccl_get_unique_id_t fn = (nccl_get_unique_id_t)nccl_sym("ncclGetUniqueId");
+    if (!fn) return ITSB_ERR_NCCL;
+    return fn(id128) == 0 ? ITSB_OK : ITSB_ERR_NCCL;
+}
+
+int itsb_nccl_comm_init(itsb_engine* e, int nranks, int rank, const void* id128, void** comm_out) {
+    if (!e || !id128 || !comm_out) return ITSB_ERR_STATE;
+    nccl_comm_init_rank_fn fn = (nccl_comm_init_rank_fn)nccl_sym("ncclCommInitRank");
+    if (!fn) { e->err = "libnccl.so.2 not found"; return ITSB_ERR_NCCL; }
+    CU(e, cudaSetDevice(e->device));
+    nccl_uid uid;
+    memcpy(&uid, id128, 128);
+    int rc = fn(comm_out, nranks, uid, rank);
+    if (rc != 0) { e->err = "ncclCommInitRank failed: " + std::to_string(rc); return ITSB_ERR_NCCL; }
+    return ITSB_OK;
+}
+
+int itsb_nccl_comm_destroy(void* comm) {
+    nccl_comm_destroy_fn fn = (nccl_comm_destroy_fn)nccl_sym("ncclCommDestroy");
+    if (!fn) return ITSB_ERR_NCCL;
+    return fn(comm) == 0 ? ITSB_OK : ITSB_ERR_NCCL;
+}
+
+int itsb_allreduce_telemetry(itsb_engine* e, void* comm, uint64_t* dst, size_t n) {
+    if (!e || !e->n_replicas || n < ITSB_TM_SIZE || !comm) return ITSB_ERR_STATE;
+    nccl_all_reduce_fn fn = (nccl_all_reduce_fn)nccl_sym("ncclAllReduce");
+    if (!fn) { e->err = "libnccl.so.2 not found"; return ITSB_ERR_NCCL; }
+    CU(e, cudaSetDevice(e->device));
+    int rc = reduce_telemetry(e);
+    if (rc) return rc;
+    /* ncclUint64 = 5, ncclSum = 0 (nccl.h) */
+    int nrc = fn(e->d_telemetry, e->d_telemetry, ITSB_TM_SIZE, 5, 0, comm, e->stream);
+    if (nrc != 0) { e->err = "ncclAllReduce failed: " + std::to_string(nrc); return ITSB_ERR_NCCL; }
+    CU(e, cudaMemcpyAsync(dst, e->d_telemetry, ITSB_TM_SIZE * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return ITSB_OK;
+}
+
+int itsb_replica_status(itsb_engine* e, uint64_t replica, int32_t* status, uint64_t* detail) {
+    if (!e || replica >= e->n_replicas) return ITSB_ERR_STATE;
+    CU(e, cudaSetDevice(e->device));
+    Hdr h;
+    CU(e, cudaMemcpy(&h, e->d_hot + (size_t)replica * e->rp.layout.hot_bytes, sizeof(Hdr), cudaMemcpyDeviceToHost));
+    if (status) *status = h.status;
+    if (detail) *detail = h.detail;
+    return ITSB_OK;
+}
+
+int64_t itsb_first_failed_replica(itsb_engine* e) { return e ? e->first_failed : -1; }
+
+int itsb_state_bytes(itsb_engine* e, uint64_t* hot, uint64_t* arena) {
+    if (!e || !e->loaded) return ITSB_ERR_STATE;
+    if (hot) *hot = e->rp.layout.hot_bytes;
+    if (arena) *arena = (uint64_t)e->rp.layout.arena_nodes * (sizeof(ArenaNode) + 4);
+    return ITSB_OK;
+}
+
+const char* itsb_last_error(itsb_engine* e) { return e ? e->err.c_str() : ""; }
+
+void itsb_destroy(itsb_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    free_replicas(e);
+    for (int i = 0; i < ITSB_NUM_BLOBS; ++i) cudaFree(e->d_tables[i]);
+    cudaFree(e->d_ticket); cudaFree(e->d_first_failed); cudaFree(e->d_telemetry);
+    if (e->ev_start) cudaEventDestroy(e->ev_start);
+    if (e->ev_stop) cudaEventDestroy(e->ev_stop);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+}  // extern "C"

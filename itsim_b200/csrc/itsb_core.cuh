@@ -194,8 +194,8 @@ struct Rep {                /* working view of one replica (pointers into the ho
     ArenaNode* arena;       /* HBM */
     u32* arena_free;        /* HBM */
     itsb_trace_rec* trace;  /* HBM or null */
-    const Model* m;
-    const Layout* L;
+    Model m;                /* by value: table pointers stay in registers */
+    Layout L;
     /* volatile interpreter registers: valid only inside one activation of a process */
     u32 pk_src_ip, pk_src_port, pk_size, pk_tag, pk_f0, pk_f1;
     u32 ent_ip, ent_port;
@@ -205,7 +205,7 @@ struct Rep {                /* working view of one replica (pointers into the ho
 };
 
 ITSB_FN void bind_views(Rep& R, unsigned char* hot, const Layout* L) {
-    R.L = L;
+    R.L = *L;
     R.hdr = (Hdr*)hot;
     R.ev_t = (u64*)(hot + L->off_ev_t);
     R.ev_seq = (u32*)(hot + L->off_ev_seq);
@@ -334,7 +334,7 @@ ITSB_FN void stat_add(Rep& R, u32 slot, u64 v) { R.stats[slot] += v; }
 ITSB_FN void trace_put(Rep& R, u32 kind, u32 prog, u32 node, u32 aux) {
     if (R.trace) {
         u32 n = R.hdr->trace_count;
-        if (n < R.L->trace_cap && lane_id() == 0) {
+        if (n < R.L.trace_cap && lane_id() == 0) {
             itsb_trace_rec rec;
             rec.t = R.hdr->now; rec.kind = (u8)kind; rec.prog = (u8)prog; rec.node = (u16)node; rec.aux = aux;
             R.trace[n] = rec;
@@ -383,7 +383,7 @@ ITSB_FN int ev_min(Rep& R, u64& tbits, u32& seq) {
     u64 bt = T_EMPTY;
     u32 bs = NIL32;
     u32 bi = NIL32;
-    const u32 n = R.L->max_ev;
+    const u32 n = R.L.max_ev;
     for (u32 i = (u32)lane_id(); i < n; i += ITSB_W) {
         u64 t = R.ev_t[i];
         u32 s = R.ev_seq[i];
@@ -436,7 +436,7 @@ ITSB_FN int proc_spawn(Rep& R, u32 entry, u32 node, const u32 regs[4], double de
     int p = pcb_alloc(R);
     if (p < 0) return -1;
     Pcb& P = R.pcb[p];
-    const itsb_entry E = R.m->entries[entry];
+    const itsb_entry E = R.m.entries[entry];
     P.pc = (u16)E.pc;
     P.state = PS_UNSTARTED;
     P.prog = (u8)E.prog;
@@ -501,8 +501,8 @@ ITSB_FN void waiters_resume_all(Rep& R, u16& head, u16& tail) {
 
 /* ---- sockets ------------------------------------------------------------------------------------------------------------ */
 ITSB_FN int sock_find(Rep& R, u32 node, u32 dst_ip, u32 dst_port) {
-    const itsb_node N = R.m->nodes[node];
-    if (dst_ip != N.addr && dst_ip != R.m->nets[N.net].bcast) return -1;
+    const itsb_node N = R.m.nodes[node];
+    if (dst_ip != N.addr && dst_ip != R.m.nets[N.net].bcast) return -1;
     u16 s = R.node[node].sock_head;
     while (s != NIL16) {
         if (R.sock[s].port == dst_port) return (int)s;
@@ -599,13 +599,13 @@ ITSB_FN void pkt_release(Rep& R, u32 k) {
 ITSB_FN void net_send(Rep& R, u32 p, u32 dst_ip, u32 dst_port, u32 size, u32 tag, u32 f0, u32 f1) {
     Pcb& P = R.pcb[p];
     if (P.sock == NIL16) { fail(R, ITSB_EXC_SOCKET_CLOSED, P.pc); return; }
-    const itsb_node N = R.m->nodes[P.node];
-    const itsb_net NET = R.m->nets[N.net];
+    const itsb_node N = R.m.nodes[P.node];
+    const itsb_net NET = R.m.nets[N.net];
     if (dst_ip != NET.bcast) {
         /* must be a member of the network: members have consecutive node indices; find by address */
         bool found = false;
         for (u32 i = (u32)lane_id(); i < NET.n_nodes; i += ITSB_W)
-            if (R.m->nodes[NET.first_node + i].addr == dst_ip) found = true;
+            if (R.m.nodes[NET.first_node + i].addr == dst_ip) found = true;
         if (w_ballot(found) == 0) { fail(R, ITSB_EXC_NO_SUCH_ADDRESS, dst_ip); return; }
     }
     int k = pkt_alloc(R);
@@ -623,10 +623,10 @@ ITSB_FN void net_send(Rep& R, u32 p, u32 dst_ip, u32 dst_port, u32 size, u32 tag
 /* transmission(): advance(next(latency) + len(packet) / next(bandwidth))  (overrides.py:287-288) */
 ITSB_FN void on_tx_begin(Rep& R, Seed seed, u32 k) {
     Pkt& K = R.pkt[k];
-    const itsb_net NET = R.m->nets[K.meta >> 16];
+    const itsb_net NET = R.m.nets[K.meta >> 16];
     count_event(R, ITSB_EV_TX_BEGIN, 9, K.meta & 0xFFFF, K.size);
-    double lat = draw_dist(R, seed, R.m->dists[NET.lat_dist]);
-    double bw = draw_dist(R, seed, R.m->dists[NET.bw_dist]);
+    double lat = draw_dist(R, seed, R.m.dists[NET.lat_dist]);
+    double bw = draw_dist(R, seed, R.m.dists[NET.bw_dist]);
     double delay = lat + (double)K.size / bw;
     if (delay < 0.0) { fail(R, ITSB_EXC_NEGATIVE_DELAY, k); return; }
     stat_add(R, ITSB_TM_LAT0 + latency_bin(delay), 1);
@@ -636,7 +636,7 @@ ITSB_FN void on_tx_begin(Rep& R, Seed seed, u32 k) {
 /* for node in receivers: sim.add(node._receive, packet)  -- one pool entry stands for the R consecutive pushes */
 ITSB_FN void on_tx_end(Rep& R, u32 k) {
     Pkt& K = R.pkt[k];
-    const itsb_net NET = R.m->nets[K.meta >> 16];
+    const itsb_net NET = R.m.nets[K.meta >> 16];
     u32 count = (K.dst_ip == NET.bcast) ? NET.n_nodes : 1u;
     count_event(R, ITSB_EV_TX_END, 9, K.meta & 0xFFFF, K.size);
     ev_push(R, R.hdr->now, ev_pack(ITSB_EV_DELIVER, k, 0, 0));
@@ -646,13 +646,13 @@ ITSB_FN void on_tx_end(Rep& R, u32 k) {
 /* Node._receive for every recipient, in link order (overrides.py:379-382), lane-parallel. */
 ITSB_FN void on_deliver(Rep& R, u32 k) {
     const Pkt K = R.pkt[k];
-    const itsb_net NET = R.m->nets[K.meta >> 16];
+    const itsb_net NET = R.m.nets[K.meta >> 16];
     const bool bcast = (K.dst_ip == NET.bcast);
     u32 first = NET.first_node, count = NET.n_nodes;
     if (!bcast) {
         u32 hit = NIL32;
         for (u32 i = (u32)lane_id(); i < NET.n_nodes; i += ITSB_W)
-            if (R.m->nodes[NET.first_node + i].addr == K.dst_ip) hit = i;
+            if (R.m.nodes[NET.first_node + i].addr == K.dst_ip) hit = i;
         u32 m = w_min(hit);
         first = NET.first_node + m;
         count = 1;
@@ -671,7 +671,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
         /* trace: one DELIVER record per recipient */
         if (R.trace && valid) {
             u32 n = R.hdr->trace_count + i - base;
-            if (n < R.L->trace_cap) {
+            if (n < R.L.trace_cap) {
                 itsb_trace_rec rec;
                 rec.t = now; rec.kind = ITSB_EV_DELIVER; rec.prog = 10; rec.node = (u16)node;
                 rec.aux = (K.size & 0x7FFFFFFFu) | (acc ? 0x80000000u : 0u);
@@ -744,11 +744,11 @@ ITSB_FN u32 src_val(Rep& R, u32 p, u32 s) {
     case SRC_PKT_F1: return R.pk_f1;
     case SRC_ENT_IP: return R.ent_ip;
     case SRC_ENT_PORT: return R.ent_port;
-    case SRC_NODE_ADDR: return R.m->nodes[P.node].addr;
+    case SRC_NODE_ADDR: return R.m.nodes[P.node].addr;
     case SRC_NODE_INDEX: return P.node;
-    case SRC_NODE_HOST: return R.m->nodes[P.node].host;
+    case SRC_NODE_HOST: return R.m.nodes[P.node].host;
     case SRC_NODE_EPOCH: return R.node[P.node].epoch;
-    case SRC_NODE_BCAST: return R.m->nets[R.m->nodes[P.node].net].bcast;
+    case SRC_NODE_BCAST: return R.m.nets[R.m.nodes[P.node].net].bcast;
     case SRC_SELF: return handle_of(R, p);
     case SRC_EXC: return P.exc;
     default: return 0;
@@ -761,7 +761,7 @@ ITSB_FN void run_process(Rep& R, Seed seed, u32 p) {
     P.state = PS_RUNNING;
     for (u32 steps = 0; ; ++steps) {
         if (R.hdr->status != 0) return;
-        const u64 ins = R.m->code[P.pc];
+        const u64 ins = R.m.code[P.pc];
         const u32 op = (u32)(ins & 0xFF), a = (u32)((ins >> 8) & 0xFF), b = (u32)((ins >> 16) & 0xFF),
                   c = (u32)((ins >> 24) & 0xFF), imm = (u32)(ins >> 32);
         switch (op) {
@@ -796,18 +796,18 @@ ITSB_FN void run_process(Rep& R, Seed seed, u32 p) {
             P.pc = (src_val(R, p, a) != (imm >> 16)) ? (u16)(imm & 0xFFFF) : (u16)(P.pc + 1);
             break;
         case OP_DRAWI:
-            P.r[a] = (u32)(int32_t)(long long)draw_dist(R, seed, R.m->dists[imm]);
+            P.r[a] = (u32)(int32_t)(long long)draw_dist(R, seed, R.m.dists[imm]);
             P.pc += 1;
             break;
         case OP_DRAW_ADDI: {
-            double v = (double)(int32_t)src_val(R, p, b) + draw_dist(R, seed, R.m->dists[imm]);
+            double v = (double)(int32_t)src_val(R, p, b) + draw_dist(R, seed, R.m.dists[imm]);
             P.r[a] = (u32)(int32_t)(long long)v;
             P.pc += 1;
             break;
         }
         case OP_ADVANCE:
         case OP_ADVANCE_C: {
-            double d = (op == OP_ADVANCE) ? draw_dist(R, seed, R.m->dists[imm & 0xFFFF]) : R.m->consts[imm & 0xFFFF];
+            double d = (op == OP_ADVANCE) ? draw_dist(R, seed, R.m.dists[imm & 0xFFFF]) : R.m.consts[imm & 0xFFFF];
             if (d < 0.0) { fail(R, ITSB_EXC_NEGATIVE_DELAY, P.pc); return; }
             int slot = ev_push(R, R.hdr->now + d, ev_pack(ITSB_EV_TIMER, p, P.gen, 0));
             P.timer_ev = (u16)slot;
@@ -961,7 +961,7 @@ ITSB_FN void deliver_exception(Rep& R, Seed seed, u32 p, u32 exc) {
         else if (P.wsig & WS_SOCK) { Sock& S = R.sock[P.wsig & 0x3FFF]; waiters_unlink(R, S.wait_head, S.wait_tail, p); }
     }
     P.exc = (u16)exc;
-    const u64 ins = R.m->code[P.pc];
+    const u64 ins = R.m.code[P.pc];
     u32 handler = (u32)(ins >> 48);
     if (handler == 0) {
         if (!(exc & EXC_INTERRUPT_CLASS)) { fail(R, ITSB_EXC_UNCAUGHT, ((u64)exc << 32) | P.pc); return; }
@@ -1032,7 +1032,7 @@ ITSB_FN void run_replica(Rep& R, Seed seed, double duration) {
 /* Builds the t = 0 state of a replica: empty tables, free lists, and the model's installed processes in
  * installation order (Endpoint.install -> sim.add, overrides.py:423-424; network_simple.py:366-385). */
 ITSB_FN void init_replica(Rep& R, u64 replica_id) {
-    const Layout* L = R.L;
+    const Layout* L = &R.L;
     Hdr* H = R.hdr;
     H->now = 0.0; H->draws = 0; H->seq = 0; H->status = 0; H->detail = 0;
     H->trace_count = 0;
@@ -1052,8 +1052,8 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
     }
     for (u32 i = 0; i < ITSB_TM_SIZE; ++i) R.stats[i] = 0;
     H->arena_free_top = L->arena_nodes;
-    for (u32 i = 0; i < R.m->n_init; ++i) {
-        const itsb_initproc I = R.m->init[i];
+    for (u32 i = 0; i < R.m.n_init; ++i) {
+        const itsb_initproc I = R.m.init[i];
         proc_spawn(R, I.entry, I.node, I.r, 0.0);
     }
 }

@@ -1,0 +1,67 @@
+"""
+ORACLE / TEST INFRASTRUCTURE ONLY.  Regenerates tests/golden/ from the oracle (run in the build container).
+
+The reference holds no seeded traces ("no test fixes an RNG seed"), so the stochastic golden
+vectors are the oracle's own output under the injected Philox stream:
+
+* netsimple_trace_s{seed}_r{replica}_{T}s.npz   full event trace (t, kind, prog, node, aux) of one replica
+* netsimple_summaries.json                      per (seed, replica, horizon): event counts per kind, model counters,
+                                                draws consumed, final clock, digest of the integer trace columns
+
+Usage: python oracle/make_golden.py [--full]     (--full adds the 43 200 s = 12 h horizon of config C1: ~7 min)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import evtrace  # noqa: E402
+import netsimple  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def summary_of(model, horizon):
+    arr = model.tracer.as_array()
+    out = model.tracer.summary()
+    out.update(model.stats)
+    out.update({"draws": model.rng.draws, "now": model.sim.now(), "horizon": horizon,
+                "connections": len(model.connections), "digest": evtrace.trace_digest(arr),
+                "t_sum": float(np.sum(arr["t"]))})
+    return out, arr
+
+
+def main() -> None:
+    os.makedirs(GOLDEN, exist_ok=True)
+    path = os.path.join(GOLDEN, "netsimple_summaries.json")
+    summaries = json.load(open(path)) if os.path.exists(path) else {}
+    # 1. full traces, short horizon
+    for seed, replica, horizon in ((0, 0, 1800.0), (7, 3, 900.0)):
+        model = netsimple.run_replica(seed, replica, horizon)
+        s, arr = summary_of(model, horizon)
+        np.savez_compressed(os.path.join(GOLDEN, f"netsimple_trace_s{seed}_r{replica}_{int(horizon)}s.npz"), trace=arr)
+        summaries[f"{seed}:{replica}:{int(horizon)}"] = s
+        model.close()
+        print("trace", seed, replica, horizon, s["events"], flush=True)
+    # 2. summaries, 1 h horizon, several streams
+    jobs = [(0, r, 3600.0) for r in (0, 1, 2, 3, 63, 99999)] + [(1, 0, 3600.0), (123456789012, 5, 3600.0)]
+    if "--full" in sys.argv:
+        jobs.append((0, 0, 43200.0))
+    for seed, replica, horizon in jobs:
+        key = f"{seed}:{replica}:{int(horizon)}"
+        if key in summaries:
+            continue
+        model = netsimple.run_replica(seed, replica, horizon)
+        s, _ = summary_of(model, horizon)
+        summaries[key] = s
+        model.close()
+        print("summary", key, s["events"], flush=True)
+        json.dump(summaries, open(path, "w"), indent=1, sort_keys=True)
+    json.dump(summaries, open(path, "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,7 +63,7 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
 
 static void bind(itsb_engine* e, Rep& R, uint64_t r) {
     bind_views(R, e->hot.data() + r * e->layout.hot_bytes, &e->layout);
-    R.m = &e->model;
+    R.m = e->model;
     R.arena = e->arena.data() + r * e->layout.arena_nodes;
     R.arena_free = e->arena_free.data() + r * e->layout.arena_nodes;
     R.trace = e->layout.trace_cap ? e->trace.data() + r * e->layout.trace_cap : nullptr;
@@ -87,7 +87,6 @@ int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first
 int itsb_run_async(itsb_engine* e, double duration) {
     if (!e->n_replicas) return ITSB_ERR_STATE;
     Seed seed = {(uint32_t)e->seed, (uint32_t)(e->seed >> 32)};
-    e->last_events = 0;
     for (uint64_t r = 0; r < e->n_replicas; ++r) {
         Rep R; bind(e, R, r);
         run_replica(R, seed, duration);
@@ -105,6 +104,7 @@ int64_t itsb_first_failed_replica(itsb_engine* e) {
 
 int itsb_sync(itsb_engine* e, uint64_t* events_done) {
     if (events_done) *events_done = e->last_events;
+    e->last_events = 0;
     int64_t bad = itsb_first_failed_replica(e);
     if (bad >= 0) return ((Hdr*)(e->hot.data() + bad * e->layout.hot_bytes))->status;
     return ITSB_OK;

@@ -1,0 +1,63 @@
+"""The drop-in boundary: the CUDA library loads, exports exactly what include/itsb.h declares, and has no CPU path."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "itsb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(itsb_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    from itsim_b200 import _lib
+    assert declared_functions() == sorted(_lib.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(built):
+    lib = ctypes.CDLL(built.LIB)
+    for name in declared_functions():
+        assert hasattr(lib, name), name
+    assert lib.itsb_abi_version() == 1
+
+
+def test_hostemu_exports_the_same_surface(built):
+    lib = ctypes.CDLL(built.HOSTEMU)
+    for name in declared_functions():
+        assert hasattr(lib, name), name
+
+
+def test_no_cpu_fallback_without_a_device(built):
+    """On a box without a GPU the product fails loudly instead of computing on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from itsim_b200 import _lib, netsimple
+    sim = netsimple.build()
+    with pytest.raises(_lib.EngineError) as err:
+        sim.run_replicas(1, seed=0, duration=1.0)
+    assert err.value.code == -1
+
+
+def test_missing_library_is_an_import_error(tmp_path):
+    from itsim_b200 import _lib
+    with pytest.raises(ImportError):
+        _lib.load(str(tmp_path / "nope.so"))
+
+
+def test_product_never_touches_the_oracle_or_hostemu():
+    """Nothing under itsim_b200/ may import or open oracle/ or the host emulation."""
+    for root, _, files in os.walk(os.path.join(ROOT, "itsim_b200")):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(root, name)).read()
+                code = re.sub(r'""".*?"""', "", text, flags=re.S)
+                code = re.sub(r"/\*.*?\*/", "", code, flags=re.S)
+                code = "\n".join(line.split("#")[0] for line in code.splitlines())
+                assert "hostemu" not in code, name
+                assert not re.search(r"^\s*(from|import)\s+(oracle|evtrace|philox|greensim)\b", code, flags=re.M), name

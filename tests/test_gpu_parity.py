@@ -1,0 +1,140 @@
+"""
+Parity tests proper: the CUDA engine, through the C ABI, against the oracle's golden vectors and against
+size-independent properties at batch sizes the oracle cannot reach.  Run with ``pytest -m gpu`` on a B200.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_trace_equal, load_golden_trace, telemetry_matches_summary
+
+pytestmark = pytest.mark.gpu
+
+
+def make(trace_records=0, **caps):
+    from itsim_b200 import netsimple
+    sim = netsimple.build(trace_records=trace_records)
+    sim.caps.update(caps)
+    return sim
+
+
+def test_trace_matches_golden_inside_a_batch():
+    """Replica 0 of seed 0, traced while 5 replicas run side by side in one launch."""
+    ref = load_golden_trace("netsimple_trace_s0_r0_1800s.npz")
+    eng = make(trace_records=len(ref) + 16).run_replicas(5, seed=0)
+    eng.run(1800.0)
+    assert_trace_equal(eng.trace(0), ref)
+    assert np.all(eng.now() == 1800.0)
+    eng.close()
+
+
+def test_other_stream_matches_golden():
+    ref = load_golden_trace("netsimple_trace_s7_r3_900s.npz")
+    eng = make(trace_records=len(ref) + 16).run_replicas(2, seed=7, first_replica_id=3)
+    eng.run(900.0)
+    assert_trace_equal(eng.trace(0), ref)
+    eng.close()
+
+
+def test_live_oracle_trace_short():
+    """The oracle itself, run here, on a stream no fixture covers."""
+    import netsimple as oracle_netsimple
+    model = oracle_netsimple.run_replica(42, 17, 400.0)
+    ref = model.tracer.as_array()
+    model.close()
+    eng = make(trace_records=len(ref) + 16).run_replicas(1, seed=42, first_replica_id=17)
+    eng.run(400.0)
+    assert_trace_equal(eng.trace(0), ref)
+    eng.close()
+
+
+def test_summaries_match_golden_in_one_batch(golden_summaries):
+    """Seed 0, replicas 0..99999 would be config C2; here the batch is the 64 first ids plus id 99999, and every
+    replica that has a golden summary must match it counter for counter after 3600 s."""
+    eng = make().run_replicas(64, seed=0)
+    events = eng.run(3600.0)
+    for r in (0, 1, 2, 3, 63):
+        s = golden_summaries[f"0:{r}:3600"]
+        telemetry_matches_summary(eng.replica_telemetry(r), s)
+    tm = eng.telemetry()
+    assert int(tm[:9].sum()) == events
+    assert np.array_equal(tm, sum(eng.replica_telemetry(r) for r in range(64)))
+    eng.close()
+    for key in ("0:99999:3600", "1:0:3600", "123456789012:5:3600"):
+        seed, replica, horizon = (int(x) for x in key.split(":"))
+        eng = make().run_replicas(1, seed=seed, first_replica_id=replica)
+        assert eng.run(float(horizon)) == golden_summaries[key]["events"]
+        telemetry_matches_summary(eng.replica_telemetry(0), golden_summaries[key])
+        eng.close()
+
+
+def test_full_horizon_c1(golden_summaries):
+    """Config C1: the reference example's own horizon, 12 h = 43 200 s, 3.8 M events, one replica."""
+    s = golden_summaries["0:0:43200"]
+    eng = make().run_replicas(1, seed=0)
+    assert eng.run(43200.0) == s["events"]
+    telemetry_matches_summary(eng.replica_telemetry(0), s)
+    eng.close()
+
+
+def test_rerun_continues(golden_summaries):
+    s = golden_summaries["0:1:3600"]
+    eng = make().run_replicas(1, seed=0, first_replica_id=1)
+    total = sum(eng.run(1200.0) for _ in range(3))
+    assert total == s["events"] + 2                      # two extra STOP events
+    assert int(eng.replica_telemetry(0)[10]) == s["bytes_sent"]
+    eng.close()
+
+
+def test_queued_async_launches(golden_summaries):
+    s = golden_summaries["0:2:3600"]
+    eng = make().run_replicas(1, seed=0, first_replica_id=2)
+    for _ in range(4):
+        eng.run_async(900.0)
+    assert eng.sync() == s["events"] + 3
+    assert eng.last_run_ms() > 0.0
+    eng.close()
+
+
+def test_gpu_equals_host_emulation_on_a_batch(hostemu):
+    """Warp width 32 against warp width 1 of the same source: every counter of every replica."""
+    gpu = make().run_replicas(96, seed=11, first_replica_id=1000)
+    gpu.run(1500.0)
+    sim = make()
+    sim._lib = hostemu
+    emu = sim.run_replicas(96, seed=11, first_replica_id=1000)
+    emu.run(1500.0)
+    for r in range(96):
+        assert np.array_equal(gpu.replica_telemetry(r), emu.replica_telemetry(r)), r
+    gpu.close()
+
+
+def test_partition_invariance_and_large_batch_properties():
+    """20 000 replicas x 120 s: no replica fails, conservation laws hold, and sampled replicas equal the same ids
+    run alone (a replica depends only on (seed, id))."""
+    from itsim_b200 import _lib as L
+    n = 20000
+    big = make().run_replicas(n, seed=5)
+    events = big.run(120.0)
+    tm = big.telemetry()
+    assert int(tm[:9].sum()) == events
+    assert int(tm[L.TM_KIND0 + L.EV_STOP]) == n
+    assert int(tm[L.TM_KIND0 + L.EV_PROC_START]) >= 148 * n
+    assert int(tm[L.TM_KIND0 + L.EV_TX_BEGIN]) == int(tm[L.TM_PACKETS_SENT])
+    assert int(tm[L.TM_KIND0 + L.EV_TX_END]) <= int(tm[L.TM_KIND0 + L.EV_TX_BEGIN])
+    assert int(tm[L.TM_DELIVERED]) + int(tm[L.TM_DROPPED]) == int(tm[L.TM_KIND0 + L.EV_DELIVER])
+    assert int(tm[L.TM_LAT0:L.TM_LAT0 + L.LAT_BINS].sum()) == int(tm[L.TM_KIND0 + L.EV_TX_BEGIN])
+    for r in (0, 7777, n - 1):
+        alone = make().run_replicas(1, seed=5, first_replica_id=r)
+        alone.run(120.0)
+        assert np.array_equal(alone.replica_telemetry(0), big.replica_telemetry(r)), r
+        alone.close()
+    big.close()
+
+
+def test_capacity_overflow_is_reported():
+    from itsim_b200 import _lib as L
+    eng = make(arena_nodes=64).run_replicas(3, seed=0)
+    with pytest.raises(L.EngineError) as err:
+        eng.run(3600.0)
+    assert err.value.code == -14
+    eng.close()

@@ -1,0 +1,91 @@
+"""
+Interpreter semantics without a GPU: the device source compiled at warp width 1 (tests/hostemu, test infrastructure)
+against the oracle's golden vectors.  The GPU parity tests proper are in test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+from conftest import assert_trace_equal, load_golden_trace, telemetry_matches_summary
+
+
+def make(hostemu, trace_records=0, **caps):
+    from itsim_b200 import netsimple
+    sim = netsimple.build(trace_records=trace_records)
+    sim.caps.update(caps)
+    sim._lib = hostemu
+    return sim
+
+
+def test_trace_matches_golden(hostemu):
+    ref = load_golden_trace("netsimple_trace_s0_r0_1800s.npz")
+    sim = make(hostemu, trace_records=len(ref) + 16)
+    eng = sim.run_replicas(1, seed=0)
+    eng.run(1800.0)
+    assert_trace_equal(eng.trace(0), ref)
+    assert eng.now()[0] == 1800.0
+
+
+def test_other_stream_matches_golden(hostemu):
+    ref = load_golden_trace("netsimple_trace_s7_r3_900s.npz")
+    sim = make(hostemu, trace_records=len(ref) + 16)
+    eng = sim.run_replicas(1, seed=7, first_replica_id=3)
+    eng.run(900.0)
+    assert_trace_equal(eng.trace(0), ref)
+
+
+def test_summaries_match_golden(hostemu, golden_summaries):
+    checked = 0
+    for key, s in golden_summaries.items():
+        seed, replica, horizon = (int(x) for x in key.split(":"))
+        if horizon > 3600:
+            continue
+        sim = make(hostemu)
+        eng = sim.run_replicas(1, seed=seed, first_replica_id=replica)
+        events = eng.run(float(horizon))
+        assert events == s["events"], key
+        telemetry_matches_summary(eng.replica_telemetry(0), s)
+        checked += 1
+    assert checked >= 5
+
+
+def test_rerun_continues(hostemu, golden_summaries):
+    """Repeated run() continues like the reference (test_thread.py:148-152): 3 x 1200 s == 3600 s, apart from the
+    extra STOP events and the seq numbers they take."""
+    s = golden_summaries["0:1:3600"]
+    sim = make(hostemu)
+    eng = sim.run_replicas(1, seed=0, first_replica_id=1)
+    total = sum(eng.run(1200.0) for _ in range(3))
+    assert total == s["events"] + 2
+    tm = eng.replica_telemetry(0)
+    from itsim_b200 import _lib as L
+    assert int(tm[L.TM_KIND0 + L.EV_STOP]) == 3
+    assert int(tm[L.TM_BYTES_SENT]) == s["bytes_sent"]
+    assert eng.now()[0] == 3600.0
+
+
+def test_batch_is_partition_invariant(hostemu):
+    """Replica r's trajectory depends only on (seed, r), not on which batch or position it runs in."""
+    sim = make(hostemu)
+    whole = sim.run_replicas(6, seed=3, first_replica_id=10)
+    whole.run(600.0)
+    part = make(hostemu).run_replicas(2, seed=3, first_replica_id=13)
+    part.run(600.0)
+    assert np.array_equal(whole.replica_telemetry(3), part.replica_telemetry(0))
+    assert np.array_equal(whole.replica_telemetry(4), part.replica_telemetry(1))
+    assert not np.array_equal(whole.replica_telemetry(0), whole.replica_telemetry(1))
+    total = whole.telemetry()
+    assert np.array_equal(total, sum(whole.replica_telemetry(i) for i in range(6)))
+
+
+def test_capacity_overflow_is_reported_not_hidden(hostemu):
+    from itsim_b200 import _lib as L
+    sim = make(hostemu, arena_nodes=64)
+    eng = sim.run_replicas(1, seed=0)
+    with pytest.raises(L.EngineError) as err:
+        eng.run(3600.0)
+    assert err.value.code == -14
+    sim = make(hostemu, max_events=160)
+    eng = sim.run_replicas(1, seed=0)
+    with pytest.raises(L.EngineError) as err:
+        eng.run(3600.0)
+    assert err.value.code == -10
