@@ -173,6 +173,9 @@ def main() -> None:
     ap.add_argument("--cpu-horizon", type=float, default=1800.0, help="simulated seconds per CPU-baseline replica")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--arena-nodes", type=int, default=12288)
+    ap.add_argument("--max-events", type=int, default=0, help="future-event pool slots per replica (0 = model default)")
+    ap.add_argument("--max-procs", type=int, default=0)
+    ap.add_argument("--max-sockets", type=int, default=0)
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -219,6 +222,9 @@ def main() -> None:
     t_cold0 = time.perf_counter()
     sim = netsimple.build()
     sim.caps["arena_nodes"] = args.arena_nodes
+    for key, val in (("max_events", args.max_events), ("max_procs", args.max_procs), ("max_sockets", args.max_sockets)):
+        if val:
+            sim.caps[key] = val
     engine = sim.run_replicas(args.replicas, seed=args.seed, first_replica_id=rank * args.replicas, device=local_rank)
     t_cold = time.perf_counter() - t_cold0
     state = engine.state_bytes()

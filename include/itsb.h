@@ -32,7 +32,7 @@ extern "C" {
 #define ITSB_ERR_CAP_EVENTS       -10  /* per-replica event pool exhausted                                    */
 #define ITSB_ERR_CAP_PROCS        -11  /* per-replica process slots exhausted                                 */
 #define ITSB_ERR_CAP_SOCKETS      -12  /* per-replica socket slots exhausted                                  */
-#define ITSB_ERR_CAP_PACKETS      -13  /* per-replica in-flight packet slots exhausted                        */
+#define ITSB_ERR_CAP_PACKETS      -13  /* reserved                                                            */
 #define ITSB_ERR_CAP_ARENA        -14  /* per-replica queue arena (HBM) exhausted                             */
 #define ITSB_ERR_BAD_OPCODE       -15
 #define ITSB_ERR_NCCL             -20
@@ -128,8 +128,9 @@ typedef struct itsb_initproc {    /* process installed at t=0, in installation o
 } itsb_initproc;
 
 typedef struct itsb_caps {        /* per-replica capacities; exceeding one flags the replica with ITSB_ERR_CAP_*  */
-    uint32_t max_events, max_procs, max_sockets, max_packets;
-    uint32_t arena_nodes;         /* 32-byte queue/list nodes in HBM                                              */
+    uint32_t max_events, max_procs, max_sockets;
+    uint32_t max_packets;         /* reserved: packets in flight are arena nodes                                  */
+    uint32_t arena_nodes;         /* 32-byte nodes in HBM: socket queues, remembered packets, packets in flight   */
     uint32_t trace_records;       /* per-replica trace capacity (0 = tracing off)                                 */
 } itsb_caps;
 

@@ -91,7 +91,7 @@ ITSB_FN u32 mulhi32(u32 a, u32 b) { return (u32)(((u64)a * (u64)b) >> 32); }
 
 /* ---- per-replica state ------------------------------------------------------------------------------------------ */
 
-struct Hdr {                /* 64 bytes */
+struct Hdr {                /* 128 bytes */
     double now;
     u64 draws;              /* Philox draw index (oracle/philox.py stream layout) */
     u32 seq;                /* greensim's insertion counter */
@@ -101,7 +101,15 @@ struct Hdr {                /* 64 bytes */
     u32 trace_count;
     u16 ev_free_top, pcb_free_top, sock_free_top, pkt_free_top;
     u32 replica_lo, replica_hi;
-    u32 pad[2];
+    /* now-queue: FIFO of the events scheduled with zero delay (they all carry t == now) */
+    u32 nq_head, nq_tail;   /* monotone cursors into the shared-memory ring */
+    u32 nq_spill_head, nq_spill_tail, nq_spill_count;   /* arena-backed continuation when the ring is full */
+    /* future pool: cached minimum, and the arena-backed overflow list used when the pool is full */
+    u32 pmin_valid, pmin_idx, pmin_seq;
+    u64 pmin_t;
+    u64 ovf_min_t;
+    u32 ovf_min_seq, ovf_head, ovf_count;
+    u32 pad[5];
 };
 
 struct Pcb {                /* 48 bytes: one greensim process */
@@ -117,7 +125,8 @@ struct Pcb {                /* 48 bytes: one greensim process */
     u16 exc;                /* last exception delivered */
     u32 list_head, list_tail; /* remembered-packet list (arena nodes) */
     u32 r[4];
-    u32 pad[1];
+    u16 timer_tok;          /* bumped by every advance(); a TIMER event is live only if it carries the current one */
+    u16 pad16;
 };
 
 enum { PS_FREE = 0, PS_UNSTARTED = 1, PS_RUNNING = 2, PS_TIMER = 3, PS_WAIT = 4, PS_RESUMING = 5 };
@@ -160,9 +169,9 @@ struct ArenaNode {          /* 32 bytes = one DRAM sector */
 
 struct Layout {             /* byte offsets inside one replica's hot block */
     u32 hot_bytes;
-    u32 off_ev_t, off_ev_seq, off_ev_data, off_ev_free;
-    u32 off_pcb, off_pcb_free, off_sock, off_sock_free, off_node, off_pkt, off_pkt_free, off_stats;
-    u32 max_ev, max_proc, max_sock, max_pkt, n_nodes;
+    u32 off_ev_t, off_ev_seq, off_ev_data, off_ev_free, off_nq;
+    u32 off_pcb, off_pcb_free, off_sock, off_sock_free, off_node, off_stats;
+    u32 max_ev, max_proc, max_sock, n_nodes;
     u32 arena_nodes, trace_cap;
 };
 
@@ -183,13 +192,12 @@ struct Rep {                /* working view of one replica (pointers into the ho
     u32* ev_seq;
     u32* ev_data;
     u16* ev_free;
+    u32* nq;                /* now-queue ring: (seq, data) pairs */
     Pcb* pcb;
     u16* pcb_free;
     Sock* sock;
     u16* sock_free;
     NodeDyn* node;
-    Pkt* pkt;
-    u16* pkt_free;
     u64* stats;
     ArenaNode* arena;       /* HBM */
     u32* arena_free;        /* HBM */
@@ -211,13 +219,12 @@ ITSB_FN void bind_views(Rep& R, unsigned char* hot, const Layout* L) {
     R.ev_seq = (u32*)(hot + L->off_ev_seq);
     R.ev_data = (u32*)(hot + L->off_ev_data);
     R.ev_free = (u16*)(hot + L->off_ev_free);
+    R.nq = (u32*)(hot + L->off_nq);
     R.pcb = (Pcb*)(hot + L->off_pcb);
     R.pcb_free = (u16*)(hot + L->off_pcb_free);
     R.sock = (Sock*)(hot + L->off_sock);
     R.sock_free = (u16*)(hot + L->off_sock_free);
     R.node = (NodeDyn*)(hot + L->off_node);
-    R.pkt = (Pkt*)(hot + L->off_pkt);
-    R.pkt_free = (u16*)(hot + L->off_pkt_free);
     R.stats = (u64*)(hot + L->off_stats);
     R.events = 0;
     R.rng_block = ~0ull;
@@ -238,6 +245,9 @@ ITSB_FN u32 ev_kind(u32 d) { return d & 0xF; }
 ITSB_FN u32 ev_exc(u32 d) { return (d >> 4) & 0xFF; }
 ITSB_FN u32 ev_idx(u32 d) { return (d >> 12) & 0x3FF; }
 ITSB_FN u32 ev_gen(u32 d) { return (d >> 22) & 0x3FF; }
+/* packet events (TX_BEGIN / TX_END / DELIVER): kind[0:4] arena-index[4:32] */
+ITSB_FN u32 ev_pack_pkt(u32 kind, u32 node_index) { return kind | (node_index << 4); }
+ITSB_FN u32 ev_pkt(u32 d) { return d >> 4; }
 
 /* ---- Philox4x32-10 stream (same definition as oracle/philox.py) --------------------------------------------------- */
 ITSB_FN void philox_block(u32 seed_lo, u32 seed_hi, u32 rep_lo, u32 rep_hi, u64 block, u32 out[4]) {
@@ -357,64 +367,6 @@ ITSB_FN u32 latency_bin(double delay) {
     return e > (ITSB_LAT_BINS - 1) ? (ITSB_LAT_BINS - 1) : e;
 }
 
-/* ---- event pool -------------------------------------------------------------------------------------------------------- */
-ITSB_FN int ev_push(Rep& R, double t, u32 data) {
-    u32 top = R.hdr->ev_free_top;
-    if (top == 0) { fail(R, ITSB_ERR_CAP_EVENTS, R.hdr->seq); return -1; }
-    top -= 1;
-    R.hdr->ev_free_top = (u16)top;
-    u32 slot = R.ev_free[top];
-    R.ev_t[slot] = dbits(t);
-    R.ev_seq[slot] = R.hdr->seq;
-    R.hdr->seq += 1;
-    R.ev_data[slot] = data;
-    return (int)slot;
-}
-
-ITSB_FN void ev_release(Rep& R, u32 slot) {
-    R.ev_t[slot] = T_EMPTY;
-    u32 top = R.hdr->ev_free_top;
-    R.ev_free[top] = (u16)slot;
-    R.hdr->ev_free_top = (u16)(top + 1);
-}
-
-/* Index of the minimum (t, seq) entry, or -1.  Each lane scans a strided slice, then three redux min-reductions. */
-ITSB_FN int ev_min(Rep& R, u64& tbits, u32& seq) {
-    u64 bt = T_EMPTY;
-    u32 bs = NIL32;
-    u32 bi = NIL32;
-    const u32 n = R.L.max_ev;
-    for (u32 i = (u32)lane_id(); i < n; i += ITSB_W) {
-        u64 t = R.ev_t[i];
-        u32 s = R.ev_seq[i];
-        if (t < bt || (t == bt && s < bs)) { bt = t; bs = s; bi = i; }
-    }
-    u32 hi = (u32)(bt >> 32);
-    u32 mhi = w_min(hi);
-    if (mhi >= 0x7FF00000u) return -1;
-    bool cand = (hi == mhi);
-    u32 lo = cand ? (u32)bt : NIL32;
-    u32 mlo = w_min(lo);
-    cand = cand && (lo == mlo);
-    u32 sq = cand ? bs : NIL32;
-    u32 msq = w_min(sq);
-    cand = cand && (sq == msq);
-    int winner = ffs32(w_ballot(cand)) - 1;
-    u32 idx = w_shfl(bi, winner);
-    tbits = ((u64)mhi << 32) | mlo;
-    seq = msq;
-    return (int)idx;
-}
-
-/* ---- slots ------------------------------------------------------------------------------------------------------------- */
-ITSB_FN int pcb_alloc(Rep& R) {
-    u32 top = R.hdr->pcb_free_top;
-    if (top == 0) { fail(R, ITSB_ERR_CAP_PROCS, 0); return -1; }
-    top -= 1;
-    R.hdr->pcb_free_top = (u16)top;
-    return (int)R.pcb_free[top];
-}
-
 ITSB_FN u32 arena_alloc(Rep& R) {
     u32 top = R.hdr->arena_free_top;
     if (top == 0) { fail(R, ITSB_ERR_CAP_ARENA, 0); return NIL32; }
@@ -427,6 +379,216 @@ ITSB_FN void arena_release(Rep& R, u32 idx) {
     u32 top = R.hdr->arena_free_top;
     R.arena_free[top] = idx;   /* every lane stores the same word: each lane stays self-consistent */
     R.hdr->arena_free_top = top + 1;
+}
+
+/* ---- events ---------------------------------------------------------------------------------------------------------
+ * greensim keeps one heap keyed (t, insertion counter).  The same total order is kept here by two structures:
+ *
+ *  now-queue   every event scheduled with zero delay (resume, throw, add, the delivery fan-out, TX_BEGIN) has
+ *              t == now and a counter larger than anything scheduled before it, so these events are already sorted:
+ *              a FIFO ring in shared memory, O(1) push and pop.  They are ~95 % of all pops in network_simple.
+ *  future pool events with t > now (advance wake-ups, TX_END): an unordered slot array whose minimum is found by a
+ *              lane-strided scan + three redux min-reductions, cached until the minimum itself is removed.
+ *
+ * Neither is bounded in the reference, so both continue into arena nodes in HBM when full (a workstation that wakes
+ * with a thousand queued packets emits its answers in one instant): the ring spills to a FIFO chain, the pool to an
+ * unordered overflow list with its own cached minimum.
+ */
+static const u32 NQ_CAP = 128;        /* ring entries (power of two) */
+
+struct EvNode {            /* arena node used by the spill chain and the overflow list (32 bytes) */
+    u32 next;
+    u32 seq;
+    u32 data;
+    u32 t_lo, t_hi;
+    u32 pad[3];
+};
+
+ITSB_FN void nq_push_seq(Rep& R, u32 seq, u32 data) {
+    Hdr* H = R.hdr;
+    if (H->nq_spill_count == 0 && H->nq_tail - H->nq_head < NQ_CAP) {
+        u32 i = H->nq_tail & (NQ_CAP - 1);
+        R.nq[2 * i] = seq;
+        R.nq[2 * i + 1] = data;
+        H->nq_tail += 1;
+        return;
+    }
+    u32 n = arena_alloc(R);
+    if (n == NIL32) return;
+    EvNode E;
+    E.next = NIL32; E.seq = seq; E.data = data; E.t_lo = 0; E.t_hi = 0; E.pad[0] = 0; E.pad[1] = 0; E.pad[2] = 0;
+    *(EvNode*)&R.arena[n] = E;
+    if (H->nq_spill_count == 0) H->nq_spill_head = n; else ((EvNode*)&R.arena[H->nq_spill_tail])->next = n;
+    H->nq_spill_tail = n;
+    H->nq_spill_count += 1;
+}
+
+/* Moves spilled entries back into the ring once it has drained. */
+ITSB_FN void nq_refill(Rep& R) {
+    Hdr* H = R.hdr;
+    while (H->nq_spill_count != 0 && H->nq_tail - H->nq_head < NQ_CAP) {
+        u32 n = H->nq_spill_head;
+        const EvNode E = *(const EvNode*)&R.arena[n];
+        u32 i = H->nq_tail & (NQ_CAP - 1);
+        R.nq[2 * i] = E.seq;
+        R.nq[2 * i + 1] = E.data;
+        H->nq_tail += 1;
+        H->nq_spill_head = E.next;
+        H->nq_spill_count -= 1;
+        arena_release(R, n);
+    }
+}
+
+ITSB_FN void ev_release(Rep& R, u32 slot) {
+    R.ev_t[slot] = T_EMPTY;
+    u32 top = R.hdr->ev_free_top;
+    R.ev_free[top] = (u16)slot;
+    R.hdr->ev_free_top = (u16)(top + 1);
+    if (R.hdr->pmin_valid && R.hdr->pmin_idx == slot) R.hdr->pmin_valid = 0;
+}
+
+/* Schedules (t, seq = counter++).  Returns the pool slot (so an advance() can be cancelled) or -1. */
+ITSB_FN int ev_push(Rep& R, double t, u32 data) {
+    Hdr* H = R.hdr;
+    const u32 seq = H->seq;
+    H->seq = seq + 1;
+    const u64 tb = dbits(t);
+    if (tb == dbits(H->now)) { nq_push_seq(R, seq, data); return -1; }
+    u32 top = H->ev_free_top;
+    if (top == 0) {
+        /* pool full: unordered overflow list in the arena */
+        u32 n = arena_alloc(R);
+        if (n == NIL32) return -1;
+        EvNode E;
+        E.next = H->ovf_count ? H->ovf_head : NIL32; E.seq = seq; E.data = data;
+        E.t_lo = (u32)tb; E.t_hi = (u32)(tb >> 32); E.pad[0] = 0; E.pad[1] = 0; E.pad[2] = 0;
+        *(EvNode*)&R.arena[n] = E;
+        H->ovf_head = n;
+        if (H->ovf_count == 0 || tb < H->ovf_min_t || (tb == H->ovf_min_t && seq < H->ovf_min_seq)) {
+            H->ovf_min_t = tb; H->ovf_min_seq = seq;
+        }
+        H->ovf_count += 1;
+        return -1;
+    }
+    top -= 1;
+    H->ev_free_top = (u16)top;
+    u32 slot = R.ev_free[top];
+    R.ev_t[slot] = tb;
+    R.ev_seq[slot] = seq;
+    R.ev_data[slot] = data;
+    if (H->pmin_valid && (tb < H->pmin_t || (tb == H->pmin_t && seq < H->pmin_seq))) {
+        H->pmin_t = tb; H->pmin_seq = seq; H->pmin_idx = slot;
+    }
+    return (int)slot;
+}
+
+/* Minimum (t, seq) of the future pool: each lane scans a strided slice, then three redux min-reductions. */
+ITSB_FN void pool_scan_min(Rep& R) {
+    u64 bt = T_EMPTY;
+    u32 bs = NIL32;
+    u32 bi = NIL32;
+    const u32 n = R.L.max_ev;
+    for (u32 i = (u32)lane_id(); i < n; i += ITSB_W) {
+        u64 t = R.ev_t[i];
+        u32 s = R.ev_seq[i];
+        if (t < bt || (t == bt && s < bs)) { bt = t; bs = s; bi = i; }
+    }
+    Hdr* H = R.hdr;
+    u32 hi = (u32)(bt >> 32);
+    u32 mhi = w_min(hi);
+    if (mhi >= 0x7FF00000u) {
+        H->pmin_t = T_EMPTY; H->pmin_seq = NIL32; H->pmin_idx = NIL32; H->pmin_valid = 1;
+        return;
+    }
+    bool cand = (hi == mhi);
+    u32 lo = cand ? (u32)bt : NIL32;
+    u32 mlo = w_min(lo);
+    cand = cand && (lo == mlo);
+    u32 sq = cand ? bs : NIL32;
+    u32 msq = w_min(sq);
+    cand = cand && (sq == msq);
+    int winner = ffs32(w_ballot(cand)) - 1;
+    H->pmin_idx = w_shfl(bi, winner);
+    H->pmin_t = ((u64)mhi << 32) | mlo;
+    H->pmin_seq = msq;
+    H->pmin_valid = 1;
+}
+
+/* Removes the minimum of the overflow list (rare: only after the pool filled up) and recomputes its cached minimum. */
+ITSB_FN u32 ovf_take_min(Rep& R) {
+    Hdr* H = R.hdr;
+    u32 prev = NIL32, n = H->ovf_head, data = 0;
+    const u64 want_t = H->ovf_min_t;
+    const u32 want_seq = H->ovf_min_seq;
+    u64 nt = T_EMPTY; u32 ns = NIL32;
+    bool taken = false;
+    u32 left = H->ovf_count;
+    while (left != 0) {
+        const EvNode E = *(const EvNode*)&R.arena[n];
+        const u64 tb = ((u64)E.t_hi << 32) | E.t_lo;
+        if (!taken && tb == want_t && E.seq == want_seq) {
+            data = E.data;
+            if (prev == NIL32) H->ovf_head = E.next; else ((EvNode*)&R.arena[prev])->next = E.next;
+            arena_release(R, n);
+            taken = true;
+        } else {
+            if (tb < nt || (tb == nt && E.seq < ns)) { nt = tb; ns = E.seq; }
+            prev = n;
+        }
+        n = E.next;
+        left -= 1;
+    }
+    H->ovf_count -= 1;
+    H->ovf_min_t = nt; H->ovf_min_seq = ns;
+    return data;
+}
+
+enum { SRC_NONE_LEFT = 0, SRC_NQ = 1, SRC_POOL = 2, SRC_OVF = 3 };
+
+/* Key of the next event in (t, seq) order and where it sits; nothing is removed yet. */
+ITSB_FN int ev_peek(Rep& R, u64& tbits, u32& seq) {
+    Hdr* H = R.hdr;
+    if (H->nq_head == H->nq_tail && H->nq_spill_count != 0) nq_refill(R);
+    if (!H->pmin_valid) pool_scan_min(R);
+    int src = SRC_NONE_LEFT;
+    tbits = T_EMPTY; seq = NIL32;
+    if (H->pmin_t != T_EMPTY) { src = SRC_POOL; tbits = H->pmin_t; seq = H->pmin_seq; }
+    if (H->ovf_count != 0 && (H->ovf_min_t < tbits || (H->ovf_min_t == tbits && H->ovf_min_seq < seq))) {
+        src = SRC_OVF; tbits = H->ovf_min_t; seq = H->ovf_min_seq;
+    }
+    if (H->nq_head != H->nq_tail) {
+        const u64 nb = dbits(H->now);
+        const u32 ns = R.nq[2 * (H->nq_head & (NQ_CAP - 1))];
+        if (nb < tbits || (nb == tbits && ns < seq)) { src = SRC_NQ; tbits = nb; seq = ns; }
+    }
+    return src;
+}
+
+/* Removes the event ev_peek chose; returns its data word and, for pool events, the slot it occupied. */
+ITSB_FN u32 ev_take(Rep& R, int src, u32& slot) {
+    Hdr* H = R.hdr;
+    slot = NIL32;
+    if (src == SRC_NQ) {
+        u32 d = R.nq[2 * (H->nq_head & (NQ_CAP - 1)) + 1];
+        H->nq_head += 1;
+        return d;
+    }
+    if (src == SRC_POOL) {
+        slot = H->pmin_idx;
+        u32 d = R.ev_data[slot];
+        ev_release(R, slot);
+        return d;
+    }
+    return ovf_take_min(R);
+}
+
+/* ---- slots ------------------------------------------------------------------------------------------------------------- */
+ITSB_FN int pcb_alloc(Rep& R) {
+    u32 top = R.hdr->pcb_free_top;
+    if (top == 0) { fail(R, ITSB_ERR_CAP_PROCS, 0); return -1; }
+    top -= 1;
+    R.hdr->pcb_free_top = (u16)top;
+    return (int)R.pcb_free[top];
 }
 
 ITSB_FN u32 handle_of(Rep& R, u32 p) { return p | ((u32)R.pcb[p].gen << 16); }
@@ -580,19 +742,9 @@ ITSB_FN void sock_close(Rep& R, u32 p) {
 }
 
 /* ---- transmission ---------------------------------------------------------------------------------------------------------- */
-ITSB_FN int pkt_alloc(Rep& R) {
-    u32 top = R.hdr->pkt_free_top;
-    if (top == 0) { fail(R, ITSB_ERR_CAP_PACKETS, 0); return -1; }
-    top -= 1;
-    R.hdr->pkt_free_top = (u16)top;
-    return (int)R.pkt_free[top];
-}
-
-ITSB_FN void pkt_release(Rep& R, u32 k) {
-    u32 top = R.hdr->pkt_free_top;
-    R.pkt_free[top] = (u16)k;
-    R.hdr->pkt_free_top = (u16)(top + 1);
-}
+/* Packets in flight live in arena nodes (HBM): a waking daemon can emit hundreds of sends in one instant, and a
+ * packet is touched only three times (send, TX_BEGIN, TX_END/DELIVER). */
+ITSB_FN Pkt* pkt_at(Rep& R, u32 k) { return (Pkt*)&R.arena[k]; }
 
 /* Socket.send -> Node._send_to_network -> Network.transmit (overrides.py:122-125,371-377,273-291): the packet
  * becomes a transmission process started with sim.add, i.e. one TX_BEGIN event at the current time. */
@@ -608,21 +760,22 @@ ITSB_FN void net_send(Rep& R, u32 p, u32 dst_ip, u32 dst_port, u32 size, u32 tag
             if (R.m.nodes[NET.first_node + i].addr == dst_ip) found = true;
         if (w_ballot(found) == 0) { fail(R, ITSB_EXC_NO_SUCH_ADDRESS, dst_ip); return; }
     }
-    int k = pkt_alloc(R);
-    if (k < 0) return;
-    Pkt& K = R.pkt[k];
+    u32 k = arena_alloc(R);
+    if (k == NIL32) return;
+    Pkt K;
     K.src_ip = N.addr; K.dst_ip = dst_ip;
     K.ports = (u32)R.sock[P.sock].port | (dst_port << 16);
     K.size = size; K.tag = tag; K.f0 = f0; K.f1 = f1;
     K.meta = (u32)P.node | (N.net << 16);
+    *pkt_at(R, k) = K;
     stat_add(R, ITSB_TM_PACKETS_SENT, 1);
     stat_add(R, ITSB_TM_BYTES_SENT, size);
-    ev_push(R, R.hdr->now, ev_pack(ITSB_EV_TX_BEGIN, (u32)k, 0, 0));
+    ev_push(R, R.hdr->now, ev_pack_pkt(ITSB_EV_TX_BEGIN, k));
 }
 
 /* transmission(): advance(next(latency) + len(packet) / next(bandwidth))  (overrides.py:287-288) */
 ITSB_FN void on_tx_begin(Rep& R, Seed seed, u32 k) {
-    Pkt& K = R.pkt[k];
+    const Pkt K = *pkt_at(R, k);
     const itsb_net NET = R.m.nets[K.meta >> 16];
     count_event(R, ITSB_EV_TX_BEGIN, 9, K.meta & 0xFFFF, K.size);
     double lat = draw_dist(R, seed, R.m.dists[NET.lat_dist]);
@@ -630,22 +783,22 @@ ITSB_FN void on_tx_begin(Rep& R, Seed seed, u32 k) {
     double delay = lat + (double)K.size / bw;
     if (delay < 0.0) { fail(R, ITSB_EXC_NEGATIVE_DELAY, k); return; }
     stat_add(R, ITSB_TM_LAT0 + latency_bin(delay), 1);
-    ev_push(R, R.hdr->now + delay, ev_pack(ITSB_EV_TX_END, k, 0, 0));
+    ev_push(R, R.hdr->now + delay, ev_pack_pkt(ITSB_EV_TX_END, k));
 }
 
 /* for node in receivers: sim.add(node._receive, packet)  -- one pool entry stands for the R consecutive pushes */
 ITSB_FN void on_tx_end(Rep& R, u32 k) {
-    Pkt& K = R.pkt[k];
+    const Pkt K = *pkt_at(R, k);
     const itsb_net NET = R.m.nets[K.meta >> 16];
     u32 count = (K.dst_ip == NET.bcast) ? NET.n_nodes : 1u;
     count_event(R, ITSB_EV_TX_END, 9, K.meta & 0xFFFF, K.size);
-    ev_push(R, R.hdr->now, ev_pack(ITSB_EV_DELIVER, k, 0, 0));
+    ev_push(R, R.hdr->now, ev_pack_pkt(ITSB_EV_DELIVER, k));
     R.hdr->seq += count - 1;
 }
 
 /* Node._receive for every recipient, in link order (overrides.py:379-382), lane-parallel. */
 ITSB_FN void on_deliver(Rep& R, u32 k) {
-    const Pkt K = R.pkt[k];
+    const Pkt K = *pkt_at(R, k);
     const itsb_net NET = R.m.nets[K.meta >> 16];
     const bool bcast = (K.dst_ip == NET.bcast);
     u32 first = NET.first_node, count = NET.n_nodes;
@@ -700,35 +853,45 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
         /* _enqueue -> packet signal turn_on: resume this socket's waiters (normally the one blocked in recv) */
         u32 total;
         u32 before = w_excl_scan(nwait, &total);
-        u32 etop = R.hdr->ev_free_top;
-        if (etop < total) { fail(R, ITSB_ERR_CAP_EVENTS, k); return; }
-        if (nwait) {
-            Sock& S = R.sock[s];
-            u32 j = 0;
-            u16 w = S.wait_head;
-            while (w != NIL16) {
-                Pcb& P = R.pcb[w];
-                u16 nx = P.wnext;
-                P.wnext = NIL16; P.wprev = NIL16; P.wsig = WS_NONE; P.state = PS_RESUMING;
-                u32 slot = R.ev_free[etop - 1 - (before + j)];
-                R.ev_t[slot] = dbits(now);
-                R.ev_seq[slot] = R.hdr->seq + before + j;
-                R.ev_data[slot] = ev_pack(ITSB_EV_WAKE, w, P.gen, 0);
-                j += 1;
-                w = nx;
+        Hdr* H = R.hdr;
+        const bool ring_ok = H->nq_spill_count == 0 && (NQ_CAP - (H->nq_tail - H->nq_head)) >= total;
+        if (ring_ok) {
+            /* every lane writes its socket's resumes straight into the ring slots its prefix rank assigns */
+            if (nwait) {
+                Sock& S = R.sock[s];
+                u32 j = 0;
+                u16 w = S.wait_head;
+                while (w != NIL16) {
+                    Pcb& P = R.pcb[w];
+                    u16 nx = P.wnext;
+                    P.wnext = NIL16; P.wprev = NIL16; P.wsig = WS_NONE; P.state = PS_RESUMING;
+                    u32 i = (H->nq_tail + before + j) & (NQ_CAP - 1);
+                    R.nq[2 * i] = H->seq + before + j;
+                    R.nq[2 * i + 1] = ev_pack(ITSB_EV_WAKE, w, P.gen, 0);
+                    j += 1;
+                    w = nx;
+                }
+                S.wait_head = NIL16; S.wait_tail = NIL16;
             }
-            S.wait_head = NIL16; S.wait_tail = NIL16;
+            w_sync();
+            H->nq_tail += total;
+            H->seq += total;
+        } else if (total) {
+            /* ring nearly full: same pushes, in recipient order, through the spilling path (warp-uniform) */
+            for (int l = 0; l < ITSB_W; ++l) {
+                u32 nl = w_shfl(nwait, l);
+                if (nl == 0) continue;
+                Sock& S = R.sock[w_shfl((u32)s, l)];
+                waiters_resume_all(R, S.wait_head, S.wait_tail);
+            }
         }
-        w_sync();
-        R.hdr->ev_free_top = (u16)(etop - total);
-        R.hdr->seq += total;
         R.stats[ITSB_TM_KIND0 + ITSB_EV_DELIVER] += n_valid;
         R.stats[ITSB_TM_DELIVERED] += n_acc;
         R.stats[ITSB_TM_DROPPED] += n_valid - n_acc;
         R.events += n_valid;
         w_sync();
     }
-    pkt_release(R, k);
+    arena_release(R, k);
 }
 
 /* ---- interpreter ------------------------------------------------------------------------------------------------------------- */
@@ -809,8 +972,9 @@ ITSB_FN void run_process(Rep& R, Seed seed, u32 p) {
         case OP_ADVANCE_C: {
             double d = (op == OP_ADVANCE) ? draw_dist(R, seed, R.m.dists[imm & 0xFFFF]) : R.m.consts[imm & 0xFFFF];
             if (d < 0.0) { fail(R, ITSB_EXC_NEGATIVE_DELAY, P.pc); return; }
-            int slot = ev_push(R, R.hdr->now + d, ev_pack(ITSB_EV_TIMER, p, P.gen, 0));
-            P.timer_ev = (u16)slot;
+            P.timer_tok = (u16)(P.timer_tok + 1);
+            int slot = ev_push(R, R.hdr->now + d, ev_pack(ITSB_EV_TIMER, p, P.gen, P.timer_tok));
+            P.timer_ev = slot < 0 ? NIL16 : (u16)slot;
             P.state = PS_TIMER;
             return;  /* pc stays on the ADVANCE; the TIMER event moves it on */
         }
@@ -953,9 +1117,11 @@ ITSB_FN void run_process(Rep& R, Seed seed, u32 p) {
  * engine removes them instead (same model-visible order). */
 ITSB_FN void deliver_exception(Rep& R, Seed seed, u32 p, u32 exc) {
     Pcb& P = R.pcb[p];
-    if (P.state == PS_TIMER && P.timer_ev != NIL16) {
-        ev_release(R, P.timer_ev);
+    if (P.state == PS_TIMER) {
+        /* advance() interrupted: its wake-up is cancelled (pool) or left to expire as a dead hop (queue / overflow) */
+        if (P.timer_ev != NIL16) ev_release(R, P.timer_ev);
         P.timer_ev = NIL16;
+        P.timer_tok = (u16)(P.timer_tok + 1);
     } else if (P.state == PS_WAIT) {
         if (P.wsig & WS_NODE) { NodeDyn& N = R.node[P.wsig & 0x3FFF]; waiters_unlink(R, N.wake_head, N.wake_tail, p); }
         else if (P.wsig & WS_SOCK) { Sock& S = R.sock[P.wsig & 0x3FFF]; waiters_unlink(R, S.wait_head, S.wait_tail, p); }
@@ -984,28 +1150,28 @@ ITSB_FN void run_replica(Rep& R, Seed seed, double duration) {
     for (;;) {
         if (H->status != 0) break;
         u64 tb; u32 seq;
-        int slot = ev_min(R, tb, seq);
-        if (slot < 0) break;                                  /* heap empty: the clock stays where it is */
+        const int src = ev_peek(R, tb, seq);
+        if (src == SRC_NONE_LEFT) break;                      /* heap empty: the clock stays where it is */
         if (tb > t_stop_bits || (tb == t_stop_bits && seq > stop_seq)) {
             H->now = t_stop;
             count_event(R, ITSB_EV_STOP, 0, 0, 0);
             break;
         }
-        const u32 data = R.ev_data[slot];
-        ev_release(R, (u32)slot);
+        u32 slot;
+        const u32 data = ev_take(R, src, slot);
         H->now = bitsd(tb);
         const u32 kind = ev_kind(data), idx = ev_idx(data);
         switch (kind) {
-        case ITSB_EV_TX_BEGIN: on_tx_begin(R, seed, idx); break;
-        case ITSB_EV_TX_END: on_tx_end(R, idx); break;
-        case ITSB_EV_DELIVER: on_deliver(R, idx); break;
+        case ITSB_EV_TX_BEGIN: on_tx_begin(R, seed, ev_pkt(data)); break;
+        case ITSB_EV_TX_END: on_tx_end(R, ev_pkt(data)); break;
+        case ITSB_EV_DELIVER: on_deliver(R, ev_pkt(data)); break;
         case ITSB_EV_PROC_START:
         case ITSB_EV_TIMER:
         case ITSB_EV_WAKE: {
             Pcb& P = R.pcb[idx];
             if (P.state == PS_FREE || P.gen != ev_gen(data)) break;   /* ghost hop: target finished */
             if (kind == ITSB_EV_TIMER) {
-                if (P.state != PS_TIMER || P.timer_ev != (u16)slot) break;
+                if (P.state != PS_TIMER || (u32)(P.timer_tok & 0xFF) != ev_exc(data)) break;
                 P.timer_ev = NIL16;
                 P.pc += 1;
             } else if (kind == ITSB_EV_WAKE) {
@@ -1037,15 +1203,18 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
     H->now = 0.0; H->draws = 0; H->seq = 0; H->status = 0; H->detail = 0;
     H->trace_count = 0;
     H->replica_lo = (u32)replica_id; H->replica_hi = (u32)(replica_id >> 32);
-    H->pad[0] = 0; H->pad[1] = 0;
+    H->nq_head = 0; H->nq_tail = 0; H->nq_spill_head = NIL32; H->nq_spill_tail = NIL32; H->nq_spill_count = 0;
+    H->pmin_valid = 0; H->pmin_idx = NIL32; H->pmin_seq = NIL32; H->pmin_t = T_EMPTY;
+    H->ovf_min_t = T_EMPTY; H->ovf_min_seq = NIL32; H->ovf_head = NIL32; H->ovf_count = 0;
+    for (u32 i = 0; i < 5; ++i) H->pad[i] = 0;
+    for (u32 i = 0; i < 2 * NQ_CAP; ++i) R.nq[i] = 0;
     for (u32 i = 0; i < L->max_ev; ++i) { R.ev_t[i] = T_EMPTY; R.ev_seq[i] = 0; R.ev_data[i] = 0; R.ev_free[i] = (u16)(L->max_ev - 1 - i); }
     H->ev_free_top = (u16)L->max_ev;
     for (u32 i = 0; i < L->max_proc; ++i) { memset(&R.pcb[i], 0, sizeof(Pcb)); R.pcb_free[i] = (u16)(L->max_proc - 1 - i); }
     H->pcb_free_top = (u16)L->max_proc;
     for (u32 i = 0; i < L->max_sock; ++i) { memset(&R.sock[i], 0, sizeof(Sock)); R.sock_free[i] = (u16)(L->max_sock - 1 - i); }
     H->sock_free_top = (u16)L->max_sock;
-    for (u32 i = 0; i < L->max_pkt; ++i) { memset(&R.pkt[i], 0, sizeof(Pkt)); R.pkt_free[i] = (u16)(L->max_pkt - 1 - i); }
-    H->pkt_free_top = (u16)L->max_pkt;
+    H->pkt_free_top = 0;
     for (u32 i = 0; i < L->n_nodes; ++i) {
         NodeDyn& N = R.node[i];
         N.sock_head = NIL16; N.port_cursor = 1024; N.wake_head = NIL16; N.wake_tail = NIL16; N.epoch = 0; N.awake = 0;

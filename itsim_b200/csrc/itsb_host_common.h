@@ -17,20 +17,19 @@ static inline Layout compute_layout(const itsb_model_desc& d) {
     Layout L;
     memset(&L, 0, sizeof(L));
     const itsb_caps& c = d.caps;
-    L.max_ev = c.max_events; L.max_proc = c.max_procs; L.max_sock = c.max_sockets; L.max_pkt = c.max_packets;
+    L.max_ev = c.max_events; L.max_proc = c.max_procs; L.max_sock = c.max_sockets;
     L.n_nodes = d.n_nodes; L.arena_nodes = c.arena_nodes; L.trace_cap = c.trace_records;
     uint32_t off = align_up((uint32_t)sizeof(Hdr), 16);
     L.off_ev_t = off;      off = align_up(off + 8 * L.max_ev, 16);
     L.off_ev_seq = off;    off = align_up(off + 4 * L.max_ev, 16);
     L.off_ev_data = off;   off = align_up(off + 4 * L.max_ev, 16);
     L.off_ev_free = off;   off = align_up(off + 2 * L.max_ev, 16);
+    L.off_nq = off;        off = align_up(off + 8 * NQ_CAP, 16);
     L.off_pcb = off;       off = align_up(off + (uint32_t)sizeof(Pcb) * L.max_proc, 16);
     L.off_pcb_free = off;  off = align_up(off + 2 * L.max_proc, 16);
     L.off_sock = off;      off = align_up(off + (uint32_t)sizeof(Sock) * L.max_sock, 16);
     L.off_sock_free = off; off = align_up(off + 2 * L.max_sock, 16);
     L.off_node = off;      off = align_up(off + (uint32_t)sizeof(NodeDyn) * L.n_nodes, 16);
-    L.off_pkt = off;       off = align_up(off + (uint32_t)sizeof(Pkt) * L.max_pkt, 16);
-    L.off_pkt_free = off;  off = align_up(off + 2 * L.max_pkt, 16);
     L.off_stats = off;     off = align_up(off + 8 * ITSB_TM_SIZE, 16);
     L.hot_bytes = align_up(off, 128);
     return L;
@@ -52,7 +51,7 @@ static inline bool validate_model(const itsb_model_desc& d, const void* const* b
     }
     const itsb_caps& c = d.caps;
     if (c.max_events < 8 || c.max_events > 65535 || c.max_procs < 1 || c.max_procs > 1024 || c.max_sockets < 1 ||
-        c.max_sockets > 0x3FFF || c.max_packets < 1 || c.max_packets > 1024 || c.arena_nodes < 1) {
+        c.max_sockets > 0x3FFF || c.arena_nodes < 1 || c.arena_nodes >= (1u << 28)) {
         why = "capacity out of range"; return false;
     }
     if (d.n_nodes == 0 || d.n_nodes > 0x3FFF || d.n_code == 0 || d.n_code > 65535) { why = "table size out of range"; return false; }
@@ -82,7 +81,7 @@ static inline bool validate_model(const itsb_model_desc& d, const void* const* b
     for (uint32_t i = 0; i < d.n_nodes; ++i) if (nodes[i].net >= d.n_nets) { why = "node.net out of range"; return false; }
     const itsb_initproc* ip = (const itsb_initproc*)blobs[ITSB_BLOB_INIT];
     for (uint32_t i = 0; i < d.n_init; ++i) if (ip[i].entry >= d.n_entries || ip[i].node >= d.n_nodes) { why = "init proc out of range"; return false; }
-    if (d.n_init > c.max_procs || d.n_init > c.max_events) { why = "more installed processes than slots"; return false; }
+    if (d.n_init > c.max_procs) { why = "more installed processes than slots"; return false; }
     return true;
 }
 

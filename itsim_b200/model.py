@@ -73,7 +73,7 @@ class Simulator:
         self.networks: List["Network"] = []
         self.nodes: List["Endpoint"] = []
         self._installed: List[Tuple[str, "Endpoint", Sequence[int]]] = []
-        self.caps = dict(max_events=256, max_procs=256, max_sockets=128, max_packets=64, arena_nodes=16384,
+        self.caps = dict(max_events=384, max_procs=256, max_sockets=128, max_packets=0, arena_nodes=16384,
                          trace_records=0)
         self._engine: Any = None
         self._lib: Any = None       # tests inject the host-emulation library here; None = the CUDA engine

@@ -138,3 +138,11 @@ def test_capacity_overflow_is_reported():
         eng.run(3600.0)
     assert err.value.code == -14
     eng.close()
+
+
+def test_tiny_pool_spills_to_the_arena_and_stays_exact(golden_summaries):
+    s = golden_summaries["0:3:3600"]
+    eng = make(max_events=16).run_replicas(1, seed=0, first_replica_id=3)
+    assert eng.run(3600.0) == s["events"]
+    telemetry_matches_summary(eng.replica_telemetry(0), s)
+    eng.close()

@@ -84,8 +84,12 @@ def test_capacity_overflow_is_reported_not_hidden(hostemu):
     with pytest.raises(L.EngineError) as err:
         eng.run(3600.0)
     assert err.value.code == -14
-    sim = make(hostemu, max_events=160)
-    eng = sim.run_replicas(1, seed=0)
-    with pytest.raises(L.EngineError) as err:
-        eng.run(3600.0)
-    assert err.value.code == -10
+
+
+def test_tiny_pool_spills_to_the_arena_and_stays_exact(hostemu, golden_summaries):
+    """The future-event pool is a cache: when it is full, events continue in the HBM arena and order is unchanged."""
+    s = golden_summaries["0:3:3600"]
+    sim = make(hostemu, max_events=16)
+    eng = sim.run_replicas(1, seed=0, first_replica_id=3)
+    assert eng.run(3600.0) == s["events"]
+    telemetry_matches_summary(eng.replica_telemetry(0), s)
