@@ -166,13 +166,19 @@ extern "C" __global__ void k_make_template(const RunParams p, unsigned char* tmp
     init_replica(R, 0);
 }
 
-/* Replicates the template into every replica's hot block and fills the arena free stacks. */
-extern "C" __global__ void k_fan_out(const RunParams p, const unsigned char* tmpl, uint64_t first_replica_id) {
+/* Replicates the template into every replica's hot block, fills the arena free stacks and copies the arena nodes
+ * the template already uses (installed processes beyond the now-queue ring start life in the spill chain; the free
+ * stack hands out node 0, 1, 2, ... so the used nodes are the prefix [0, used)). */
+extern "C" __global__ void k_fan_out(const RunParams p, const unsigned char* tmpl, const ArenaNode* tmpl_arena,
+                                     uint64_t first_replica_id) {
     const uint32_t vec = p.layout.hot_bytes / 16;
     const uint4* src = (const uint4*)tmpl;
+    const uint32_t used = p.layout.arena_nodes - ((const Hdr*)tmpl)->arena_free_top;
     for (uint64_t r = blockIdx.x; r < p.n_replicas; r += gridDim.x) {
         uint4* dst = (uint4*)(p.hot + r * p.layout.hot_bytes);
         for (uint32_t i = threadIdx.x; i < vec; i += blockDim.x) dst[i] = src[i];
+        uint4* adst = (uint4*)(p.arena + r * p.layout.arena_nodes);
+        for (uint32_t i = threadIdx.x; i < used * 2; i += blockDim.x) adst[i] = ((const uint4*)tmpl_arena)[i];
         uint32_t* fr = p.arena_free + r * p.layout.arena_nodes;
         for (uint32_t i = threadIdx.x; i < p.layout.arena_nodes; i += blockDim.x) fr[i] = p.layout.arena_nodes - 1 - i;
         __syncthreads();
@@ -321,15 +327,25 @@ int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first
     e->rp.n_replicas = n; e->rp.seed = seed;
     e->rp.ticket = e->d_ticket; e->rp.events_done = e->d_ticket + 1; e->rp.first_failed = e->d_first_failed;
     unsigned char* tmpl = nullptr;
+    ArenaNode* tmpl_arena = nullptr;
+    uint32_t* tmpl_free = nullptr;
     CU(e, cudaMalloc(&tmpl, L.hot_bytes));
+    CU(e, cudaMalloc(&tmpl_arena, (size_t)L.arena_nodes * sizeof(ArenaNode)));
+    CU(e, cudaMalloc(&tmpl_free, (size_t)L.arena_nodes * sizeof(uint32_t)));
     CU(e, cudaMemsetAsync(tmpl, 0, L.hot_bytes, e->stream));
-    k_make_template<<<1, 32, 0, e->stream>>>(e->rp, tmpl, e->d_arena, e->d_arena_free);
+    {
+        std::vector<uint32_t> ident(L.arena_nodes);
+        for (uint32_t i = 0; i < L.arena_nodes; ++i) ident[i] = L.arena_nodes - 1 - i;
+        CU(e, cudaMemcpyAsync(tmpl_free, ident.data(), ident.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+        CU(e, cudaStreamSynchronize(e->stream));
+    }
+    k_make_template<<<1, 32, 0, e->stream>>>(e->rp, tmpl, tmpl_arena, tmpl_free);
     CU(e, cudaGetLastError());
     uint32_t blocks = (uint32_t)(n < (uint64_t)e->prop.multiProcessorCount * 8 ? n : (uint64_t)e->prop.multiProcessorCount * 8);
-    k_fan_out<<<blocks, 256, 0, e->stream>>>(e->rp, tmpl, first_replica_id);
+    k_fan_out<<<blocks, 256, 0, e->stream>>>(e->rp, tmpl, tmpl_arena, first_replica_id);
     CU(e, cudaGetLastError());
     CU(e, cudaStreamSynchronize(e->stream));
-    cudaFree(tmpl);
+    cudaFree(tmpl); cudaFree(tmpl_arena); cudaFree(tmpl_free);
     const long long none = 0x7FFFFFFFFFFFFFFFll;
     CU(e, cudaMemcpy(e->d_first_failed, &none, sizeof(none), cudaMemcpyHostToDevice));
     CU(e, cudaMemset(e->d_ticket, 0, 2 * sizeof(unsigned long long)));

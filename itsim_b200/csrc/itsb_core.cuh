@@ -31,7 +31,7 @@
 #if defined(__CUDACC__)
 #define ITSB_W 32
 #define ITSB_FN __device__ __forceinline__
-#define ITSB_FN_NOINLINE __device__ __noinline__
+#define ITSB_FN_NOINLINE static __device__ __noinline__
 #else
 #define ITSB_W 1
 #define ITSB_FN static inline
@@ -208,8 +208,6 @@ struct Rep {                /* working view of one replica (pointers into the ho
     u32 pk_src_ip, pk_src_port, pk_size, pk_tag, pk_f0, pk_f1;
     u32 ent_ip, ent_port;
     u64 events;             /* simulated events processed by this call */
-    u32 rng_w[4];
-    u64 rng_block;
 };
 
 ITSB_FN void bind_views(Rep& R, unsigned char* hot, const Layout* L) {
@@ -227,7 +225,6 @@ ITSB_FN void bind_views(Rep& R, unsigned char* hot, const Layout* L) {
     R.node = (NodeDyn*)(hot + L->off_node);
     R.stats = (u64*)(hot + L->off_stats);
     R.events = 0;
-    R.rng_block = ~0ull;
 }
 
 ITSB_FN void fail(Rep& R, int status, u64 detail) {
@@ -266,43 +263,44 @@ ITSB_FN void philox_block(u32 seed_lo, u32 seed_hi, u32 rep_lo, u32 rep_hi, u64 
 
 struct Seed { u32 lo, hi; };
 
-ITSB_FN void rng_next(Rep& R, Seed seed, u32& a, u32& b) {
-    u64 d = R.hdr->draws;
-    R.hdr->draws = d + 1;
-    u64 block = d >> 1;
-    if (block != R.rng_block) {
-        R.rng_block = block;
-        philox_block(seed.lo, seed.hi, R.hdr->replica_lo, R.hdr->replica_hi, block, R.rng_w);
-    }
-    u32 half = (u32)(d & 1);
-    a = half ? R.rng_w[2] : R.rng_w[0];
-    b = half ? R.rng_w[3] : R.rng_w[1];
+/* Draw d of the replica's stream: the 64 bits (a, b) of its half of Philox block d >> 1. */
+ITSB_FN void rng_next(Hdr* H, Seed seed, u32& a, u32& b) {
+    const u64 d = H->draws;
+    H->draws = d + 1;
+    u32 w[4];
+    philox_block(seed.lo, seed.hi, H->replica_lo, H->replica_hi, d >> 1, w);
+    const bool half = (d & 1) != 0;
+    a = half ? w[2] : w[0];
+    b = half ? w[3] : w[1];
 }
 
-ITSB_FN double rng_random(Rep& R, Seed seed) {  /* CPython's 53-bit construction */
+ITSB_FN double rng_random(Hdr* H, Seed seed) {  /* CPython's 53-bit construction */
     u32 a, b;
-    rng_next(R, seed, a, b);
+    rng_next(H, seed, a, b);
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
 }
 
-/* One value of a generator chain: kind -> linear -> bounded -> project_int (itsim/random.py:29). */
-ITSB_FN double draw_dist(Rep& R, Seed seed, const itsb_dist& D) {
+/* One value of a generator chain: kind -> linear -> bounded -> project_int (itsim/random.py:29).  Kept out of line:
+ * it is reached from five places and holds two log() expansions and the Philox rounds; inlining it everywhere made
+ * the kernel 200 KB of SASS and instruction-fetch bound. */
+ITSB_FN_NOINLINE double draw_dist(Hdr* H, Seed seed, const itsb_dist* Dp) {
+    const itsb_dist D = *Dp;
     double x;
     switch (D.kind) {
     case ITSB_DIST_CONSTANT:
         x = D.p0;
         break;
     case ITSB_DIST_UNIFORM:  /* random.uniform: a + (b - a) * random() */
-        x = D.p0 + (D.p1 - D.p0) * rng_random(R, seed);
+        x = D.p0 + (D.p1 - D.p0) * rng_random(H, seed);
         break;
     case ITSB_DIST_EXPO:     /* random.expovariate(lambd): -log(1 - random()) / lambd */
-        x = -log(1.0 - rng_random(R, seed)) / D.p0;
+        x = -log(1.0 - rng_random(H, seed)) / D.p0;
         break;
     case ITSB_DIST_NORMAL: { /* random.normalvariate: Kinderman-Monahan ratio of uniforms */
         double z;
         for (;;) {
-            double u1 = rng_random(R, seed);
-            double u2 = 1.0 - rng_random(R, seed);
+            double u1 = rng_random(H, seed);
+            double u2 = 1.0 - rng_random(H, seed);
             z = 1.7155277699214135 * (u1 - 0.5) / u2;
             double zz = z * z / 4.0;
             if (zz <= -log(u2)) break;
@@ -321,7 +319,7 @@ ITSB_FN double draw_dist(Rep& R, Seed seed, const itsb_dist& D) {
         u32 r;
         for (;;) {
             u32 a, b;
-            rng_next(R, seed, a, b);
+            rng_next(H, seed, a, b);
             r = a >> (32 - k);
             if (r < n) break;
         }
@@ -404,6 +402,43 @@ struct EvNode {            /* arena node used by the spill chain and the overflo
     u32 pad[3];
 };
 
+/* slow paths, out of line: they run only when a burst outgrows the shared-memory structures */
+ITSB_FN_NOINLINE u32 arena_alloc_raw(Hdr* H, const u32* arena_free) {
+    u32 top = H->arena_free_top;
+    if (top == 0) {
+        if (H->status == 0) { H->status = ITSB_ERR_CAP_ARENA; H->detail = 0; }
+        return NIL32;
+    }
+    top -= 1;
+    H->arena_free_top = top;
+    return arena_free[top];
+}
+
+ITSB_FN_NOINLINE void nq_spill_push(Hdr* H, ArenaNode* arena, const u32* arena_free, u32 seq, u32 data) {
+    u32 n = arena_alloc_raw(H, arena_free);
+    if (n == NIL32) return;
+    EvNode E;
+    E.next = NIL32; E.seq = seq; E.data = data; E.t_lo = 0; E.t_hi = 0; E.pad[0] = 0; E.pad[1] = 0; E.pad[2] = 0;
+    *(EvNode*)&arena[n] = E;
+    if (H->nq_spill_count == 0) H->nq_spill_head = n; else ((EvNode*)&arena[H->nq_spill_tail])->next = n;
+    H->nq_spill_tail = n;
+    H->nq_spill_count += 1;
+}
+
+ITSB_FN_NOINLINE void ovf_push(Hdr* H, ArenaNode* arena, const u32* arena_free, u64 tb, u32 seq, u32 data) {
+    u32 n = arena_alloc_raw(H, arena_free);
+    if (n == NIL32) return;
+    EvNode E;
+    E.next = H->ovf_count ? H->ovf_head : NIL32; E.seq = seq; E.data = data;
+    E.t_lo = (u32)tb; E.t_hi = (u32)(tb >> 32); E.pad[0] = 0; E.pad[1] = 0; E.pad[2] = 0;
+    *(EvNode*)&arena[n] = E;
+    H->ovf_head = n;
+    if (H->ovf_count == 0 || tb < H->ovf_min_t || (tb == H->ovf_min_t && seq < H->ovf_min_seq)) {
+        H->ovf_min_t = tb; H->ovf_min_seq = seq;
+    }
+    H->ovf_count += 1;
+}
+
 ITSB_FN void nq_push_seq(Rep& R, u32 seq, u32 data) {
     Hdr* H = R.hdr;
     if (H->nq_spill_count == 0 && H->nq_tail - H->nq_head < NQ_CAP) {
@@ -413,14 +448,7 @@ ITSB_FN void nq_push_seq(Rep& R, u32 seq, u32 data) {
         H->nq_tail += 1;
         return;
     }
-    u32 n = arena_alloc(R);
-    if (n == NIL32) return;
-    EvNode E;
-    E.next = NIL32; E.seq = seq; E.data = data; E.t_lo = 0; E.t_hi = 0; E.pad[0] = 0; E.pad[1] = 0; E.pad[2] = 0;
-    *(EvNode*)&R.arena[n] = E;
-    if (H->nq_spill_count == 0) H->nq_spill_head = n; else ((EvNode*)&R.arena[H->nq_spill_tail])->next = n;
-    H->nq_spill_tail = n;
-    H->nq_spill_count += 1;
+    nq_spill_push(H, R.arena, R.arena_free, seq, data);
 }
 
 /* Moves spilled entries back into the ring once it has drained. */
@@ -455,19 +483,8 @@ ITSB_FN int ev_push(Rep& R, double t, u32 data) {
     const u64 tb = dbits(t);
     if (tb == dbits(H->now)) { nq_push_seq(R, seq, data); return -1; }
     u32 top = H->ev_free_top;
-    if (top == 0) {
-        /* pool full: unordered overflow list in the arena */
-        u32 n = arena_alloc(R);
-        if (n == NIL32) return -1;
-        EvNode E;
-        E.next = H->ovf_count ? H->ovf_head : NIL32; E.seq = seq; E.data = data;
-        E.t_lo = (u32)tb; E.t_hi = (u32)(tb >> 32); E.pad[0] = 0; E.pad[1] = 0; E.pad[2] = 0;
-        *(EvNode*)&R.arena[n] = E;
-        H->ovf_head = n;
-        if (H->ovf_count == 0 || tb < H->ovf_min_t || (tb == H->ovf_min_t && seq < H->ovf_min_seq)) {
-            H->ovf_min_t = tb; H->ovf_min_seq = seq;
-        }
-        H->ovf_count += 1;
+    if (top == 0) {   /* pool full: unordered overflow list in the arena */
+        ovf_push(H, R.arena, R.arena_free, tb, seq, data);
         return -1;
     }
     top -= 1;
@@ -778,8 +795,8 @@ ITSB_FN void on_tx_begin(Rep& R, Seed seed, u32 k) {
     const Pkt K = *pkt_at(R, k);
     const itsb_net NET = R.m.nets[K.meta >> 16];
     count_event(R, ITSB_EV_TX_BEGIN, 9, K.meta & 0xFFFF, K.size);
-    double lat = draw_dist(R, seed, R.m.dists[NET.lat_dist]);
-    double bw = draw_dist(R, seed, R.m.dists[NET.bw_dist]);
+    double lat = draw_dist(R.hdr, seed, &R.m.dists[NET.lat_dist]);
+    double bw = draw_dist(R.hdr, seed, &R.m.dists[NET.bw_dist]);
     double delay = lat + (double)K.size / bw;
     if (delay < 0.0) { fail(R, ITSB_EXC_NEGATIVE_DELAY, k); return; }
     stat_add(R, ITSB_TM_LAT0 + latency_bin(delay), 1);
@@ -959,18 +976,18 @@ ITSB_FN void run_process(Rep& R, Seed seed, u32 p) {
             P.pc = (src_val(R, p, a) != (imm >> 16)) ? (u16)(imm & 0xFFFF) : (u16)(P.pc + 1);
             break;
         case OP_DRAWI:
-            P.r[a] = (u32)(int32_t)(long long)draw_dist(R, seed, R.m.dists[imm]);
+            P.r[a] = (u32)(int32_t)(long long)draw_dist(R.hdr, seed, &R.m.dists[imm]);
             P.pc += 1;
             break;
         case OP_DRAW_ADDI: {
-            double v = (double)(int32_t)src_val(R, p, b) + draw_dist(R, seed, R.m.dists[imm]);
+            double v = (double)(int32_t)src_val(R, p, b) + draw_dist(R.hdr, seed, &R.m.dists[imm]);
             P.r[a] = (u32)(int32_t)(long long)v;
             P.pc += 1;
             break;
         }
         case OP_ADVANCE:
         case OP_ADVANCE_C: {
-            double d = (op == OP_ADVANCE) ? draw_dist(R, seed, R.m.dists[imm & 0xFFFF]) : R.m.consts[imm & 0xFFFF];
+            double d = (op == OP_ADVANCE) ? draw_dist(R.hdr, seed, &R.m.dists[imm & 0xFFFF]) : R.m.consts[imm & 0xFFFF];
             if (d < 0.0) { fail(R, ITSB_EXC_NEGATIVE_DELAY, P.pc); return; }
             P.timer_tok = (u16)(P.timer_tok + 1);
             int slot = ev_push(R, R.hdr->now + d, ev_pack(ITSB_EV_TIMER, p, P.gen, P.timer_tok));
@@ -1115,7 +1132,7 @@ ITSB_FN void run_process(Rep& R, Seed seed, u32 p) {
 /* An exception arrives at a blocked process (greenlet.throw): leave whatever it was parked in, then run its handler.
  * greensim would leave a "ghost" wake-up / queue entry for non-Interrupt exceptions; ghosts are no-ops, so the
  * engine removes them instead (same model-visible order). */
-ITSB_FN void deliver_exception(Rep& R, Seed seed, u32 p, u32 exc) {
+ITSB_FN u32 deliver_exception(Rep& R, u32 p, u32 exc) {
     Pcb& P = R.pcb[p];
     if (P.state == PS_TIMER) {
         /* advance() interrupted: its wake-up is cancelled (pool) or left to expire as a dead hop (queue / overflow) */
@@ -1130,13 +1147,11 @@ ITSB_FN void deliver_exception(Rep& R, Seed seed, u32 p, u32 exc) {
     const u64 ins = R.m.code[P.pc];
     u32 handler = (u32)(ins >> 48);
     if (handler == 0) {
-        if (!(exc & EXC_INTERRUPT_CLASS)) { fail(R, ITSB_EXC_UNCAUGHT, ((u64)exc << 32) | P.pc); return; }
-        sock_close(R, p);
-        proc_exit(R, p);
-        return;
+        if (!(exc & EXC_INTERRUPT_CLASS)) { fail(R, ITSB_EXC_UNCAUGHT, ((u64)exc << 32) | P.pc); return NIL32; }
+        handler = 0;    /* code[0..1] = CLOSE; EXIT -- an uncaught Interrupt ends the process silently */
     }
     P.pc = (u16)handler;
-    run_process(R, seed, p);
+    return p;
 }
 
 /* Simulator.run(duration): pops (t, seq)-ordered events until the stop event. */
@@ -1161,6 +1176,7 @@ ITSB_FN void run_replica(Rep& R, Seed seed, double duration) {
         const u32 data = ev_take(R, src, slot);
         H->now = bitsd(tb);
         const u32 kind = ev_kind(data), idx = ev_idx(data);
+        u32 runnable = NIL32;
         switch (kind) {
         case ITSB_EV_TX_BEGIN: on_tx_begin(R, seed, ev_pkt(data)); break;
         case ITSB_EV_TX_END: on_tx_end(R, ev_pkt(data)); break;
@@ -1178,7 +1194,7 @@ ITSB_FN void run_replica(Rep& R, Seed seed, double duration) {
                 if (P.state != PS_RESUMING) break;
             } else if (P.state != PS_UNSTARTED) break;
             count_event(R, kind, P.prog, P.node, 0);
-            run_process(R, seed, idx);
+            runnable = idx;
             break;
         }
         case ITSB_EV_THROW: {
@@ -1186,12 +1202,13 @@ ITSB_FN void run_replica(Rep& R, Seed seed, double duration) {
             if (P.state == PS_FREE || P.gen != ev_gen(data)) break;   /* ghost hop */
             count_event(R, ITSB_EV_THROW, P.prog, P.node, ev_exc(data));
             if (P.state == PS_UNSTARTED) { proc_exit(R, idx); break; }  /* never ran: dies on the spot */
-            deliver_exception(R, seed, idx, ev_exc(data));
+            runnable = deliver_exception(R, idx, ev_exc(data));
             break;
         }
         default:
             fail(R, ITSB_ERR_BAD_OPCODE, data);
         }
+        if (runnable != NIL32) run_process(R, seed, runnable);   /* the interpreter's only call site */
     }
 }
 

@@ -35,7 +35,8 @@ class Asm:
     """Two-pass assembler with symbolic labels; one code array holds every program of a model."""
 
     def __init__(self) -> None:
-        self._ins: List[Tuple[int, int, int, int, object]] = [(OP_EXIT, 0, 0, 0, 0)]  # pc 0 is never a handler
+        # pc 0..1 = CLOSE; EXIT: where a process lands when an Interrupt-class exception finds no handler
+        self._ins: List[Tuple[int, int, int, int, object]] = [(OP_CLOSE, 0, 0, 0, 0), (OP_EXIT, 0, 0, 0, 0)]
         self._labels: Dict[str, int] = {}
         self.entries: List[Tuple[str, int]] = []   # (label, program id)
         self._entry_index: Dict[str, int] = {}

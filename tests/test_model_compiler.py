@@ -16,13 +16,15 @@ def test_assembler_labels_and_encoding():
     a.label("h")
     a.exit()
     code, entries = a.assemble()
-    assert list(entries[0]) == [1, 9]
-    op, imm = int(code[1]) & 0xFF, int(code[1]) >> 32
-    assert op == ir.OP_RECV and imm >> 16 == 4
-    op, imm = int(code[2]) & 0xFF, int(code[2]) >> 32
-    assert op == ir.OP_JEQI and imm & 0xFFFF == 1 and imm >> 16 == 5
-    op, imm = int(code[3]) & 0xFF, int(code[3]) >> 32
-    assert op == ir.OP_ADVANCE and imm & 0xFFFF == 3 and imm >> 16 == 4
+    assert [int(code[0]) & 0xFF, int(code[1]) & 0xFF] == [ir.OP_CLOSE, ir.OP_EXIT]   # reserved: unhandled Interrupt
+    base = 2
+    assert list(entries[0]) == [base, 9]
+    op, imm = int(code[base]) & 0xFF, int(code[base]) >> 32
+    assert op == ir.OP_RECV and imm >> 16 == base + 3
+    op, imm = int(code[base + 1]) & 0xFF, int(code[base + 1]) >> 32
+    assert op == ir.OP_JEQI and imm & 0xFFFF == base and imm >> 16 == 5
+    op, imm = int(code[base + 2]) & 0xFF, int(code[base + 2]) >> 32
+    assert op == ir.OP_ADVANCE and imm & 0xFFFF == 3 and imm >> 16 == base + 3
     with pytest.raises(KeyError):
         b = ir.Asm()
         b.program("q", 1)
