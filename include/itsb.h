@@ -127,6 +127,15 @@ typedef struct itsb_initproc {    /* process installed at t=0, in installation o
     uint32_t r[4];
 } itsb_initproc;
 
+typedef struct itsb_filter {      /* which received packets a RECV_FILTER loop hands to its program; the rest it
+                                     consumes and loops (the daemon bodies' "not for me" branches,
+                                     network_simple.py:187-221,234-245).  Bit i of a mask = payload tag i.          */
+    uint32_t tags_always;         /* always handed over                                                           */
+    uint32_t tags_if_host;        /* handed over only if the packet's hostname field equals the node's             */
+    uint32_t tags_if_list;        /* handed over only if the process remembers at least one packet (LIST_*)        */
+    uint32_t reserved;
+} itsb_filter;
+
 typedef struct itsb_caps {        /* per-replica capacities; exceeding one flags the replica with ITSB_ERR_CAP_*  */
     uint32_t max_events, max_procs, max_sockets;
     uint32_t max_packets;         /* reserved: packets in flight are arena nodes                                  */
@@ -136,7 +145,7 @@ typedef struct itsb_caps {        /* per-replica capacities; exceeding one flags
 
 typedef struct itsb_model_desc {
     uint32_t abi_version;
-    uint32_t n_code, n_entries, n_dists, n_consts, n_nets, n_nodes, n_init;
+    uint32_t n_code, n_entries, n_dists, n_consts, n_nets, n_nodes, n_init, n_filters;
     itsb_caps caps;
 } itsb_model_desc;
 
@@ -148,7 +157,8 @@ typedef struct itsb_model_desc {
 #define ITSB_BLOB_NETS    4   /* itsb_net[n_nets]                                                                 */
 #define ITSB_BLOB_NODES   5   /* itsb_node[n_nodes]                                                               */
 #define ITSB_BLOB_INIT    6   /* itsb_initproc[n_init]                                                            */
-#define ITSB_NUM_BLOBS    7
+#define ITSB_BLOB_FILTERS 7   /* itsb_filter[n_filters]                                                           */
+#define ITSB_NUM_BLOBS    8
 
 typedef struct itsb_engine itsb_engine;
 

@@ -38,6 +38,7 @@ NET_DTYPE = np.dtype([("cidr_net", "<u4"), ("cidr_mask", "<u4"), ("bcast", "<u4"
 NODE_DTYPE = np.dtype([("addr", "<u4"), ("net", "<u4"), ("host", "<u4"), ("flags", "<u4")])
 ENTRY_DTYPE = np.dtype([("pc", "<u4"), ("prog", "<u4")])
 INIT_DTYPE = np.dtype([("entry", "<u4"), ("node", "<u4"), ("r", "<u4", (4,))])
+FILTER_DTYPE = np.dtype([("tags_always", "<u4"), ("tags_if_host", "<u4"), ("tags_if_list", "<u4"), ("reserved", "<u4")])
 assert TRACE_DTYPE.itemsize == 16 and DIST_DTYPE.itemsize == 56 and NET_DTYPE.itemsize == 32
 assert NODE_DTYPE.itemsize == 16 and ENTRY_DTYPE.itemsize == 8 and INIT_DTYPE.itemsize == 24
 
@@ -50,7 +51,7 @@ class Caps(C.Structure):
 class ModelDesc(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("n_code", C.c_uint32), ("n_entries", C.c_uint32),
                 ("n_dists", C.c_uint32), ("n_consts", C.c_uint32), ("n_nets", C.c_uint32), ("n_nodes", C.c_uint32),
-                ("n_init", C.c_uint32), ("caps", Caps)]
+                ("n_init", C.c_uint32), ("n_filters", C.c_uint32), ("caps", Caps)]
 
 
 class EngineError(RuntimeError):

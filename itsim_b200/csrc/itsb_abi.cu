@@ -73,7 +73,7 @@ struct RunParams {
     uint32_t warps_per_cta;
 };
 
-struct StaticOffsets { uint32_t code, entries, dists, consts, nets, nodes, total; };
+struct StaticOffsets { uint32_t code, entries, dists, consts, nets, nodes, filters, total; };
 
 static inline StaticOffsets static_offsets(const itsb_model_desc& d) {
     StaticOffsets o;
@@ -84,6 +84,7 @@ static inline StaticOffsets static_offsets(const itsb_model_desc& d) {
     o.consts = off;  off = align_up(off + 8 * d.n_consts, 16);
     o.nets = off;    off = align_up(off + (uint32_t)sizeof(itsb_net) * d.n_nets, 16);
     o.nodes = off;   off = align_up(off + (uint32_t)sizeof(itsb_node) * d.n_nodes, 16);
+    o.filters = off; off = align_up(off + (uint32_t)sizeof(itsb_filter) * d.n_filters, 16);
     o.total = align_up(off, 128);
     return o;
 }
@@ -104,7 +105,8 @@ __device__ __forceinline__ Model stage_model(const Model& g, unsigned char* sm) 
     cta_copy(sm + off, g.dists, 56 * g.n_dists);              m.dists = (const itsb_dist*)(sm + off);    off = (off + 56 * g.n_dists + 15) & ~15u;
     cta_copy(sm + off, g.consts, 8 * g.n_consts);             m.consts = (const double*)(sm + off);      off = (off + 8 * g.n_consts + 15) & ~15u;
     cta_copy(sm + off, g.nets, 32 * g.n_nets);                m.nets = (const itsb_net*)(sm + off);      off = (off + 32 * g.n_nets + 15) & ~15u;
-    cta_copy(sm + off, g.nodes, 16 * g.n_nodes);              m.nodes = (const itsb_node*)(sm + off);
+    cta_copy(sm + off, g.nodes, 16 * g.n_nodes);              m.nodes = (const itsb_node*)(sm + off);    off = (off + 16 * g.n_nodes + 15) & ~15u;
+    cta_copy(sm + off, g.filters, 16 * g.n_filters);          m.filters = (const itsb_filter*)(sm + off);
     __syncthreads();
     return m;
 }
@@ -293,8 +295,9 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     m.nets = (const itsb_net*)e->d_tables[ITSB_BLOB_NETS];
     m.nodes = (const itsb_node*)e->d_tables[ITSB_BLOB_NODES];
     m.init = (const itsb_initproc*)e->d_tables[ITSB_BLOB_INIT];
+    m.filters = (const itsb_filter*)e->d_tables[ITSB_BLOB_FILTERS];
     m.n_code = d->n_code; m.n_entries = d->n_entries; m.n_dists = d->n_dists; m.n_consts = d->n_consts;
-    m.n_nets = d->n_nets; m.n_nodes = d->n_nodes; m.n_init = d->n_init;
+    m.n_nets = d->n_nets; m.n_nodes = d->n_nodes; m.n_init = d->n_init; m.n_filters = d->n_filters;
     e->rp.layout = compute_layout(*d);
     e->so = static_offsets(*d);
     e->rp.static_bytes = e->so.total;

@@ -126,7 +126,7 @@ struct Pcb {                /* 48 bytes: one greensim process */
     u32 list_head, list_tail; /* remembered-packet list (arena nodes) */
     u32 r[4];
     u16 timer_tok;          /* bumped by every advance(); a TIMER event is live only if it carries the current one */
-    u16 pad16;
+    u16 phase;              /* RECV_FILTER: 0 = before the awake check, 1 = inside recv() */
 };
 
 enum { PS_FREE = 0, PS_UNSTARTED = 1, PS_RUNNING = 2, PS_TIMER = 3, PS_WAIT = 4, PS_RESUMING = 5 };
@@ -183,7 +183,8 @@ struct Model {              /* device pointers to the static tables */
     const itsb_net* nets;
     const itsb_node* nodes;
     const itsb_initproc* init;
-    u32 n_code, n_entries, n_dists, n_consts, n_nets, n_nodes, n_init;
+    const itsb_filter* filters;
+    u32 n_code, n_entries, n_dists, n_consts, n_nets, n_nodes, n_init, n_filters;
 };
 
 struct Rep {                /* working view of one replica (pointers into the hot block + HBM side buffers) */
@@ -621,7 +622,7 @@ ITSB_FN int proc_spawn(Rep& R, u32 entry, u32 node, const u32 regs[4], double de
     P.prog = (u8)E.prog;
     P.node = (u16)node;
     P.wnext = NIL16; P.wprev = NIL16; P.wsig = WS_NONE; P.timer_ev = NIL16; P.sock = NIL16; P.exc = 0;
-    P.list_head = NIL32; P.list_tail = NIL32;
+    P.list_head = NIL32; P.list_tail = NIL32; P.phase = 0;
     P.r[0] = regs[0]; P.r[1] = regs[1]; P.r[2] = regs[2]; P.r[3] = regs[3];
     ev_push(R, R.hdr->now + delay, ev_pack(ITSB_EV_PROC_START, (u32)p, P.gen, 0));
     return p;
@@ -813,7 +814,20 @@ ITSB_FN void on_tx_end(Rep& R, u32 k) {
     R.hdr->seq += count - 1;
 }
 
-/* Node._receive for every recipient, in link order (overrides.py:379-382), lane-parallel. */
+ITSB_FN bool filter_passes(const itsb_filter F, u32 tag, u32 f0, u32 host, bool list_nonempty) {
+    const u32 bit = 1u << (tag & 31);
+    return (F.tags_always & bit) != 0 || ((F.tags_if_host & bit) != 0 && f0 == host) ||
+           ((F.tags_if_list & bit) != 0 && list_nonempty);
+}
+
+/* Node._receive for every recipient, in link order (overrides.py:379-382), lane-parallel.
+ *
+ * Retiring filtered wake-ups in the delivery pass.  A recipient whose only waiter sits in a RECV_FILTER loop, awake,
+ * with an empty queue, and whose filter rejects this packet would be woken, pop the packet, reject it and block
+ * again on the same socket: no state changes but the counters.  When nothing else is pending at this instant
+ * (now-queue empty, no future event at t == now) that outcome cannot be influenced by anything in between, so the
+ * lane retires the wake-up on the spot: no queue node, no event, same counters, same counter values consumed.  Off
+ * while tracing, so a trace always shows the reference's interleaving event by event. */
 ITSB_FN void on_deliver(Rep& R, u32 k) {
     const Pkt K = *pkt_at(R, k);
     const itsb_net NET = R.m.nets[K.meta >> 16];
@@ -829,12 +843,38 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
     }
     const u32 dst_port = K.ports >> 16;
     const double now = R.hdr->now;
+    bool fast_ok = false;
+    if (R.trace == nullptr && R.m.n_filters != 0) {
+        Hdr* H0 = R.hdr;
+        if (H0->nq_head == H0->nq_tail && H0->nq_spill_count == 0) {
+            if (!H0->pmin_valid) pool_scan_min(R);
+            const u64 nb = dbits(now);
+            fast_ok = H0->pmin_t > nb && (H0->ovf_count == 0 || H0->ovf_min_t > nb);
+        }
+    }
     for (u32 base = 0; base < count; base += ITSB_W) {
         u32 i = base + (u32)lane_id();
         bool valid = i < count;
         u32 node = first + i;
         int s = valid ? sock_find(R, node, K.dst_ip, dst_port) : -1;
-        bool acc = s >= 0;
+        const bool found = s >= 0;
+        bool retire = false;
+        if (fast_ok && found) {
+            const Sock& S = R.sock[s];
+            const u16 w = S.wait_head;
+            if (w != NIL16 && S.q_len == 0 && R.pcb[w].wnext == NIL16) {
+                const Pcb& P = R.pcb[w];
+                const u64 ins = R.m.code[P.pc];
+                if ((u32)(ins & 0xFF) == OP_RECV_FILTER && P.phase == 1 &&
+                    R.node[node].epoch == P.r[(u32)(ins >> 8) & 3]) {
+                    const itsb_filter F = R.m.filters[(u32)(ins >> 16) & 0xFF];
+                    retire = !filter_passes(F, K.tag, K.f0, R.m.nodes[node].host, P.list_head != NIL32);
+                }
+            }
+        }
+        const u32 n_found = (u32)popc(w_ballot(found));
+        const u32 n_retired = (u32)popc(w_ballot(retire));
+        bool acc = found && !retire;      /* recipients that really enqueue */
         u32 amask = w_ballot(acc);
         u32 n_acc = (u32)popc(amask);
         u32 n_valid = (u32)popc(w_ballot(valid));
@@ -844,7 +884,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
             if (n < R.L.trace_cap) {
                 itsb_trace_rec rec;
                 rec.t = now; rec.kind = ITSB_EV_DELIVER; rec.prog = 10; rec.node = (u16)node;
-                rec.aux = (K.size & 0x7FFFFFFFu) | (acc ? 0x80000000u : 0u);
+                rec.aux = (K.size & 0x7FFFFFFFu) | (found ? 0x80000000u : 0u);
                 R.trace[n] = rec;
             }
         }
@@ -868,8 +908,9 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
         }
         R.hdr->arena_free_top = atop - n_acc;
         /* _enqueue -> packet signal turn_on: resume this socket's waiters (normally the one blocked in recv) */
-        u32 total;
-        u32 before = w_excl_scan(nwait, &total);
+        u32 total, total_seq;
+        u32 before = w_excl_scan(nwait, &total);                               /* ring position: real wake-ups */
+        u32 before_seq = w_excl_scan(nwait + (retire ? 1u : 0u), &total_seq);  /* counter value: every waiter  */
         Hdr* H = R.hdr;
         const bool ring_ok = H->nq_spill_count == 0 && (NQ_CAP - (H->nq_tail - H->nq_head)) >= total;
         if (ring_ok) {
@@ -883,7 +924,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
                     u16 nx = P.wnext;
                     P.wnext = NIL16; P.wprev = NIL16; P.wsig = WS_NONE; P.state = PS_RESUMING;
                     u32 i = (H->nq_tail + before + j) & (NQ_CAP - 1);
-                    R.nq[2 * i] = H->seq + before + j;
+                    R.nq[2 * i] = H->seq + before_seq + j;
                     R.nq[2 * i + 1] = ev_pack(ITSB_EV_WAKE, w, P.gen, 0);
                     j += 1;
                     w = nx;
@@ -892,7 +933,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
             }
             w_sync();
             H->nq_tail += total;
-            H->seq += total;
+            H->seq += total_seq;
         } else if (total) {
             /* ring nearly full: same pushes, in recipient order, through the spilling path (warp-uniform) */
             for (int l = 0; l < ITSB_W; ++l) {
@@ -901,11 +942,20 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
                 Sock& S = R.sock[w_shfl((u32)s, l)];
                 waiters_resume_all(R, S.wait_head, S.wait_tail);
             }
+            H->seq += n_retired;   /* (the retiring path is off whenever the ring is not empty; kept for symmetry) */
+        } else {
+            H->seq += total_seq;
         }
         R.stats[ITSB_TM_KIND0 + ITSB_EV_DELIVER] += n_valid;
-        R.stats[ITSB_TM_DELIVERED] += n_acc;
-        R.stats[ITSB_TM_DROPPED] += n_valid - n_acc;
+        R.stats[ITSB_TM_DELIVERED] += n_found;
+        R.stats[ITSB_TM_DROPPED] += n_valid - n_found;
         R.events += n_valid;
+        if (n_retired) {
+            R.stats[ITSB_TM_KIND0 + ITSB_EV_WAKE] += n_retired;
+            R.stats[ITSB_TM_PACKETS_RECEIVED] += n_retired;
+            R.stats[ITSB_TM_BYTES_RECEIVED] += (u64)n_retired * K.size;
+            R.events += n_retired;
+        }
         w_sync();
     }
     arena_release(R, k);
@@ -1038,6 +1088,47 @@ ITSB_FN void run_process(Rep& R, Seed seed, u32 p) {
             stat_add(R, ITSB_TM_PACKETS_RECEIVED, 1);
             stat_add(R, ITSB_TM_BYTES_RECEIVED, A.size);
             P.pc += 1;
+            break;
+        }
+        case OP_RECV_FILTER: {
+            if (P.sock == NIL16) { fail(R, ITSB_EXC_SOCKET_CLOSED, P.pc); return; }
+            NodeDyn& N = R.node[P.node];
+            Sock& S = R.sock[P.sock];
+            const itsb_filter F = R.m.filters[b];
+            bool handed = false;
+            for (;;) {
+                if (P.phase == 0) {               /* with ws.awake(): wait_until_awake, remember the wake epoch */
+                    if (!N.awake) {
+                        waiters_append(R, N.wake_head, N.wake_tail, p, (u16)(WS_NODE | P.node));
+                        P.state = PS_WAIT;
+                        return;
+                    }
+                    P.r[a] = N.epoch;
+                    P.phase = 1;
+                }
+                if (S.q_len == 0) {               /* socket.recv() */
+                    waiters_append(R, S.wait_head, S.wait_tail, p, (u16)(WS_SOCK | P.sock));
+                    P.state = PS_WAIT;
+                    return;
+                }
+                u32 n = S.q_head;
+                const ArenaNode A = R.arena[n];
+                S.q_head = A.next;
+                if (A.next == NIL32) S.q_tail = NIL32;
+                S.q_len -= 1;
+                arena_release(R, n);
+                stat_add(R, ITSB_TM_PACKETS_RECEIVED, 1);
+                stat_add(R, ITSB_TM_BYTES_RECEIVED, A.size);
+                P.phase = 0;
+                if (N.epoch != P.r[a]) { P.pc = (u16)(imm & 0xFFFF); break; }      /* FellAsleep */
+                if (filter_passes(F, A.tag, A.f0, R.m.nodes[P.node].host, P.list_head != NIL32)) {
+                    R.pk_src_ip = A.src_ip; R.pk_src_port = A.ports & 0xFFFF; R.pk_size = A.size;
+                    R.pk_tag = A.tag; R.pk_f0 = A.f0; R.pk_f1 = A.f1;
+                    handed = true;
+                    break;
+                }
+            }
+            if (handed) P.pc += 1;
             break;
         }
         case OP_WAIT_AWAKE: {

@@ -42,7 +42,7 @@ static inline bool validate_model(const itsb_model_desc& d, const void* const* b
     const size_t want[ITSB_NUM_BLOBS] = {
         (size_t)d.n_code * 8, (size_t)d.n_entries * sizeof(itsb_entry), (size_t)d.n_dists * sizeof(itsb_dist),
         (size_t)d.n_consts * 8, (size_t)d.n_nets * sizeof(itsb_net), (size_t)d.n_nodes * sizeof(itsb_node),
-        (size_t)d.n_init * sizeof(itsb_initproc)};
+        (size_t)d.n_init * sizeof(itsb_initproc), (size_t)d.n_filters * sizeof(itsb_filter)};
     for (int i = 0; i < ITSB_NUM_BLOBS; ++i) {
         if (sizes[i] != want[i] || (want[i] && !blobs[i])) {
             snprintf(buf, sizeof buf, "blob %d: %zu bytes given, %zu expected", i, sizes[i], want[i]);
@@ -64,6 +64,10 @@ static inline bool validate_model(const itsb_model_desc& d, const void* const* b
         if (op == OP_ADVANCE && (imm & 0xFFFF) >= d.n_dists) { why = "ADVANCE dist out of range"; return false; }
         if (op == OP_ADVANCE_C && (imm & 0xFFFF) >= d.n_consts) { why = "ADVANCE_C const out of range"; return false; }
         if (op == OP_SPAWN && imm >= d.n_entries) { why = "SPAWN entry out of range"; return false; }
+        if (op == OP_RECV_FILTER) {
+            uint32_t a = (uint32_t)((code[i] >> 8) & 0xFF), b = (uint32_t)((code[i] >> 16) & 0xFF);
+            if (a > 3 || b >= d.n_filters || (imm & 0xFFFF) >= d.n_code) { why = "RECV_FILTER operand out of range"; return false; }
+        }
         if ((op == OP_JMP || op == OP_JEQ || op == OP_JNE || op == OP_JASLEEP || op == OP_LIST_TAKE) && imm >= d.n_code) {
             snprintf(buf, sizeof buf, "code[%u]: jump out of range", i); why = buf; return false;
         }

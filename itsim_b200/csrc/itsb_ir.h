@@ -42,6 +42,9 @@ enum {
     OP_LIST_PUSH = 25,  /* queries.append(packet)                                        network_simple.py:193   */
     OP_LIST_TAKE = 26,  /* first entry with f0 == src(a): load ENT_*, delete it; else goto imm   :203-211        */
     OP_STAT = 27,       /* user counter imm += 1                                                                 */
+    OP_RECV_FILTER = 28,/* fused daemon loop head: "while True: with ws.awake(): packet = socket.recv(); if the
+                           packet is not for this program: continue".  r[a] = wake epoch, b = filter index,
+                           imm[0:16] = FellAsleep target, imm[16:32] = handler          network_simple.py:183-186 */
     OP_COUNT
 };
 

@@ -13,7 +13,7 @@ import numpy as np
 # opcodes (itsb_ir.h)
 (OP_NOP, OP_EXIT, OP_JMP, OP_LI, OP_MOV, OP_ADDI, OP_JEQ, OP_JNE, OP_JEQI, OP_JNEI, OP_DRAWI, OP_DRAW_ADDI,
  OP_ADVANCE, OP_ADVANCE_C, OP_OPEN, OP_CLOSE, OP_SEND, OP_RECV, OP_WAIT_AWAKE, OP_JASLEEP, OP_NODE_SLEEP,
- OP_NODE_WAKE, OP_SPAWN, OP_THROW, OP_LIST_CLEAR, OP_LIST_PUSH, OP_LIST_TAKE, OP_STAT) = range(28)
+ OP_NODE_WAKE, OP_SPAWN, OP_THROW, OP_LIST_CLEAR, OP_LIST_PUSH, OP_LIST_TAKE, OP_STAT, OP_RECV_FILTER) = range(29)
 
 # operand sources
 R0, R1, R2, R3 = 0, 1, 2, 3
@@ -97,6 +97,11 @@ class Asm:
 
     def recv(self, handler: Optional[Target] = None) -> None:
         self._emit(OP_RECV, imm=("hi16", self._t(handler), 0))
+
+    def recv_filter(self, rd: int, filter_index: int, asleep: Target, handler: Optional[Target] = None) -> None:
+        """Fused ``while True: with ws.awake(): packet = socket.recv()`` loop head that also consumes the packets
+        the program's own dispatch would ignore (see ``Simulator.packet_filter``)."""
+        self._emit(OP_RECV_FILTER, rd, filter_index, imm=("hi16", self._t(handler), self._t(asleep)))
 
     def wait_awake(self, rd: int = NONE, handler: Optional[Target] = None) -> None:
         self._emit(OP_WAIT_AWAKE, rd, imm=("hi16", self._t(handler), 0))

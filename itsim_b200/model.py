@@ -46,16 +46,16 @@ class NetworkFull(Exception):
 class Compiled:
     """The tables handed to ``itsb_load_model`` (blob order = ``ITSB_BLOB_*`` in include/itsb.h)."""
 
-    def __init__(self, code, entries, dists, consts, nets, nodes, init, caps: L.Caps) -> None:
+    def __init__(self, code, entries, dists, consts, nets, nodes, init, filters, caps: L.Caps) -> None:
         self.code, self.entries, self.dists, self.consts = code, entries, dists, consts
-        self.nets, self.nodes, self.init, self.caps = nets, nodes, init, caps
+        self.nets, self.nodes, self.init, self.filters, self.caps = nets, nodes, init, filters, caps
 
     def blobs(self) -> List[np.ndarray]:
-        return [self.code, self.entries, self.dists, self.consts, self.nets, self.nodes, self.init]
+        return [self.code, self.entries, self.dists, self.consts, self.nets, self.nodes, self.init, self.filters]
 
     def desc(self) -> L.ModelDesc:
         return L.ModelDesc(L.ABI_VERSION, len(self.code), len(self.entries), len(self.dists), len(self.consts),
-                           len(self.nets), len(self.nodes), len(self.init), self.caps)
+                           len(self.nets), len(self.nodes), len(self.init), len(self.filters), self.caps)
 
 
 class Simulator:
@@ -70,6 +70,7 @@ class Simulator:
         self._dists: List[Dist] = []
         self._dist_index: Dict[tuple, int] = {}
         self._consts: List[float] = []
+        self._filters: List[Tuple[int, int, int]] = []
         self.networks: List["Network"] = []
         self.nodes: List["Endpoint"] = []
         self._installed: List[Tuple[str, "Endpoint", Sequence[int]]] = []
@@ -91,6 +92,23 @@ class Simulator:
         if value not in self._consts:
             self._consts.append(value)
         return self._consts.index(value)
+
+    def packet_filter(self, always: Sequence[int] = (), if_host: Sequence[int] = (),
+                      if_list: Sequence[int] = ()) -> int:
+        """Declares which payload tags a ``recv_filter`` loop hands to its program: ``always``; ``if_host`` only when
+        the packet's hostname field is the node's own; ``if_list`` only while the process remembers a packet.  Every
+        other packet is consumed by the loop head, exactly as the body's own dispatch would have ignored it."""
+        def mask(tags: Sequence[int]) -> int:
+            m = 0
+            for t in tags:
+                if not 0 <= t < 32:
+                    raise ValueError("payload tags used in filters must be below 32")
+                m |= 1 << t
+            return m
+        entry = (mask(always), mask(if_host), mask(if_list))
+        if entry not in self._filters:
+            self._filters.append(entry)
+        return self._filters.index(entry)
 
     def compile(self) -> Compiled:
         code, entries_raw = self.asm.assemble()
@@ -122,7 +140,10 @@ class Simulator:
         for i, (program, node, regs) in enumerate(self._installed):
             r = list(regs) + [0] * (4 - len(regs))
             init[i] = (self.asm.entry(program), node.index, r)
-        return Compiled(code, entries, dists, consts, nets, nodes, init, L.Caps(**self.caps))
+        filters = np.zeros(len(self._filters), dtype=L.FILTER_DTYPE)
+        for i, (fa, fh, fl) in enumerate(self._filters):
+            filters[i] = (fa, fh, fl, 0)
+        return Compiled(code, entries, dists, consts, nets, nodes, init, filters, L.Caps(**self.caps))
 
     # -- running -------------------------------------------------------------------------------------------------
     def run_replicas(self, n: int, seed: int = 0, duration: Optional[float] = None, first_replica_id: int = 0,

@@ -28,7 +28,7 @@ NUM_ADDRESSES_RESERVED = 2
 MIN_NUM_ENDPOINTS = 3
 
 
-def _programs(sim: Simulator, num_workstations: int) -> None:
+def _programs(sim: Simulator, num_workstations: int, fused: bool) -> None:
     a = sim.asm
     d_awake = sim.dist(expo(2.0 * H))                                         # network_simple.py:101
     d_sleeping = sim.dist(expo(10.0 * MIN))                                   # :102
@@ -81,9 +81,13 @@ def _programs(sim: Simulator, num_workstations: int) -> None:
     a.list_clear()
     a.open(5353)
     a.label("loop")
-    a.wait_awake(R0)                 # with ws.awake(): wait, remember when we awoke
-    a.recv()
-    a.jasleep(R0, "asleep")          # leaving the with: FellAsleep if the machine slept meanwhile
+    if fused:
+        # the three lines below plus the "not for me" exits of the dispatch, as one instruction
+        a.recv_filter(R0, sim.packet_filter(always=[TAG_QUERY], if_host=[TAG_RESOLVE], if_list=[TAG_IAM]), "asleep")
+    else:
+        a.wait_awake(R0)             # with ws.awake(): wait, remember when we awoke
+        a.recv()
+        a.jasleep(R0, "asleep")      # leaving the with: FellAsleep if the machine slept meanwhile
     a.jeqi(PKT_TAG, TAG_QUERY, "query")
     a.jeqi(PKT_TAG, TAG_IAM, "iam")
     a.jeqi(PKT_TAG, TAG_RESOLVE, "resolve")
@@ -110,9 +114,12 @@ def _programs(sim: Simulator, num_workstations: int) -> None:
     a.label("top")
     a.open(5355)
     a.label("loop")
-    a.wait_awake(R0)
-    a.recv()
-    a.jasleep(R0, "asleep")
+    if fused:
+        a.recv_filter(R0, sim.packet_filter(if_host=[TAG_RESOLVE]), "asleep")
+    else:
+        a.wait_awake(R0)
+        a.recv()
+        a.jasleep(R0, "asleep")
     a.jnei(PKT_TAG, TAG_RESOLVE, "loop")
     a.jne(PKT_F0, NODE_HOST, "loop")
     a.drawi(R1, d_dns)
@@ -171,8 +178,11 @@ def _programs(sim: Simulator, num_workstations: int) -> None:
     a.exit()
 
 
-def build(cidr: str = "192.168.4.0/24", num_endpoints: Optional[int] = None, trace_records: int = 0) -> Simulator:
-    """``init()`` of network_simple.py:311-387 (argument defaults :315-316)."""
+def build(cidr: str = "192.168.4.0/24", num_endpoints: Optional[int] = None, trace_records: int = 0,
+          fused: bool = True) -> Simulator:
+    """``init()`` of network_simple.py:311-387 (argument defaults :315-316).  ``fused=False`` assembles the daemon
+    loops from the plain wait/recv/branch instructions instead of the fused loop head (same behaviour, used by the
+    tests to check one encoding against the other)."""
     sim = Simulator()
     num_addresses = ip_network(cidr).num_addresses - NUM_ADDRESSES_RESERVED
     if num_addresses < MIN_NUM_ENDPOINTS:
@@ -185,7 +195,7 @@ def build(cidr: str = "192.168.4.0/24", num_endpoints: Optional[int] = None, tra
     num_workstations = num_endpoints - 1
     num_mdns = int(0.9 * num_workstations)
 
-    _programs(sim, num_workstations)
+    _programs(sim, num_workstations, fused)
 
     dhcp_server = Endpoint("DHCPServer", net_local)
     dhcp_server.install("dhcp_serve")

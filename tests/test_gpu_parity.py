@@ -146,3 +146,18 @@ def test_tiny_pool_spills_to_the_arena_and_stays_exact(golden_summaries):
     assert eng.run(3600.0) == s["events"]
     telemetry_matches_summary(eng.replica_telemetry(0), s)
     eng.close()
+
+
+def test_fused_loop_head_and_retired_wakeups_change_nothing():
+    from itsim_b200 import netsimple
+    results = []
+    for fused, trace in ((False, 0), (True, 400000), (True, 0)):
+        eng = netsimple.build(trace_records=trace, fused=fused).run_replicas(3, seed=21, first_replica_id=40)
+        events = eng.run(3000.0)
+        results.append((events, [eng.replica_telemetry(r) for r in range(3)], eng.now()))
+        eng.close()
+    for other in results[1:]:
+        assert other[0] == results[0][0]
+        for r in range(3):
+            assert np.array_equal(other[1][r], results[0][1][r])
+        assert np.array_equal(other[2], results[0][2])

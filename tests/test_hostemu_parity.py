@@ -93,3 +93,22 @@ def test_tiny_pool_spills_to_the_arena_and_stays_exact(hostemu, golden_summaries
     eng = sim.run_replicas(1, seed=0, first_replica_id=3)
     assert eng.run(3600.0) == s["events"]
     telemetry_matches_summary(eng.replica_telemetry(0), s)
+
+
+def test_fused_loop_head_and_retired_wakeups_change_nothing(hostemu):
+    """Three encodings of the same model must agree counter for counter: plain instructions; the fused RECV_FILTER
+    loop head with tracing on (every wake-up is an event of its own); and tracing off, where filtered wake-ups are
+    retired inside the delivery pass."""
+    from itsim_b200 import netsimple
+    results = []
+    for fused, trace in ((False, 0), (True, 400000), (True, 0)):
+        sim = netsimple.build(trace_records=trace, fused=fused)
+        sim._lib = hostemu
+        eng = sim.run_replicas(3, seed=21, first_replica_id=40)
+        events = eng.run(3000.0)
+        results.append((events, [eng.replica_telemetry(r) for r in range(3)], eng.now()))
+    for other in results[1:]:
+        assert other[0] == results[0][0]
+        for r in range(3):
+            assert np.array_equal(other[1][r], results[0][1][r])
+        assert np.array_equal(other[2], results[0][2])
