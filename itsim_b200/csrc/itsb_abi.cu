@@ -77,7 +77,7 @@ struct StaticOffsets { uint32_t code, entries, dists, consts, nets, nodes, filte
 
 static inline StaticOffsets static_offsets(const itsb_model_desc& d) {
     StaticOffsets o;
-    uint32_t off = 0;
+    uint32_t off = align_up((uint32_t)sizeof(Model), 16);
     o.code = off;    off = align_up(off + 8 * d.n_code, 16);
     o.entries = off; off = align_up(off + (uint32_t)sizeof(itsb_entry) * d.n_entries, 16);
     o.dists = off;   off = align_up(off + (uint32_t)sizeof(itsb_dist) * d.n_dists, 16);
@@ -92,14 +92,16 @@ static inline StaticOffsets static_offsets(const itsb_model_desc& d) {
 __device__ __forceinline__ void cta_copy(void* dst, const void* src, uint32_t bytes) {
     const uint4* s = (const uint4*)src;
     uint4* d = (uint4*)dst;
+#pragma unroll 1
     for (uint32_t i = threadIdx.x; i < (bytes + 15) / 16; i += blockDim.x) d[i] = s[i];
 }
 
-/* Stages the model tables into shared memory (they are padded to 16 bytes on the device) and returns a Model whose
- * pointers address the shared copy. */
-__device__ __forceinline__ Model stage_model(const Model& g, unsigned char* sm) {
+/* Stages the model tables into shared memory (they are padded to 16 bytes on the device) behind a Model struct whose
+ * pointers address the shared copies; returns that struct's address (the out-of-line engine functions reach the
+ * tables through it). */
+__device__ __forceinline__ const Model* stage_model(const Model& g, unsigned char* sm) {
     Model m = g;
-    uint32_t off = 0;
+    uint32_t off = ((uint32_t)sizeof(Model) + 15) & ~15u;
     cta_copy(sm + off, g.code, 8 * g.n_code);                 m.code = (const u64*)(sm + off);          off = (off + 8 * g.n_code + 15) & ~15u;
     cta_copy(sm + off, g.entries, 8 * g.n_entries);           m.entries = (const itsb_entry*)(sm + off); off = (off + 8 * g.n_entries + 15) & ~15u;
     cta_copy(sm + off, g.dists, 56 * g.n_dists);              m.dists = (const itsb_dist*)(sm + off);    off = (off + 56 * g.n_dists + 15) & ~15u;
@@ -107,21 +109,21 @@ __device__ __forceinline__ Model stage_model(const Model& g, unsigned char* sm) 
     cta_copy(sm + off, g.nets, 32 * g.n_nets);                m.nets = (const itsb_net*)(sm + off);      off = (off + 32 * g.n_nets + 15) & ~15u;
     cta_copy(sm + off, g.nodes, 16 * g.n_nodes);              m.nodes = (const itsb_node*)(sm + off);    off = (off + 16 * g.n_nodes + 15) & ~15u;
     cta_copy(sm + off, g.filters, 16 * g.n_filters);          m.filters = (const itsb_filter*)(sm + off);
+    if (threadIdx.x == 0) *(Model*)sm = m;
     __syncthreads();
-    return m;
+    return (const Model*)sm;
 }
 
 /* ---- the engine kernel ------------------------------------------------------------------------------------------------ */
 extern "C" __global__ void __launch_bounds__(512, 1) k_run(const RunParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const Model m = stage_model(p.model, smem);
+    const Model* m = stage_model(p.model, smem);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* hot = smem + p.static_bytes + (size_t)warp * p.layout.hot_bytes;
     uint64_t* bar = (uint64_t*)(smem + p.static_bytes + (size_t)p.warps_per_cta * p.layout.hot_bytes) + warp;
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    const Seed seed = {(uint32_t)p.seed, (uint32_t)(p.seed >> 32)};
     uint32_t phase = 0;
     for (;;) {
         unsigned long long r = 0;
@@ -136,12 +138,9 @@ extern "C" __global__ void __launch_bounds__(512, 1) k_run(const RunParams p) {
         mbar_wait(bar, phase);
         phase ^= 1;
         Rep R;
-        bind_views(R, hot, &p.layout);
-        R.m = m;
-        R.arena = p.arena + r * p.layout.arena_nodes;
-        R.arena_free = p.arena_free + r * p.layout.arena_nodes;
-        R.trace = p.trace ? p.trace + r * p.layout.trace_cap : nullptr;
-        run_replica(R, seed, p.duration);
+        bind_views(R, hot, &p.layout, m, p.arena + r * p.layout.arena_nodes, p.arena_free + r * p.layout.arena_nodes,
+                   p.trace ? p.trace + r * p.layout.trace_cap : nullptr, p.seed);
+        const unsigned long long events = run_replica(R, p.duration);
         __syncwarp();
         const int32_t status = R.hdr->status;
         /* shared -> HBM */
@@ -150,7 +149,7 @@ extern "C" __global__ void __launch_bounds__(512, 1) k_run(const RunParams p) {
         if (lane == 0) {
             bulk_s2g(p.hot + r * p.layout.hot_bytes, hot, p.layout.hot_bytes);
             bulk_wait_all();
-            atomicAdd(p.events_done, (unsigned long long)R.events);
+            atomicAdd(p.events_done, events);
             if (status != 0) atomicMin(p.first_failed, (long long)r);
         }
         __syncwarp();
@@ -158,13 +157,10 @@ extern "C" __global__ void __launch_bounds__(512, 1) k_run(const RunParams p) {
 }
 
 /* Builds the t = 0 hot block once (replica id patched in by k_fan_out). */
-extern "C" __global__ void k_make_template(const RunParams p, unsigned char* tmpl, ArenaNode* arena0, uint32_t* free0) {
+extern "C" __global__ void k_make_template(const RunParams p, const Model* model, unsigned char* tmpl,
+                                           ArenaNode* arena0, uint32_t* free0) {
     Rep R;
-    bind_views(R, tmpl, &p.layout);
-    R.m = p.model;
-    R.arena = arena0;
-    R.arena_free = free0;
-    R.trace = nullptr;
+    bind_views(R, tmpl, &p.layout, model, arena0, free0, nullptr, p.seed);
     init_replica(R, 0);
 }
 
@@ -221,6 +217,7 @@ struct itsb_engine {
     unsigned long long* d_ticket = nullptr;       /* [0] ticket, [1] events_done */
     long long* d_first_failed = nullptr;
     unsigned long long* d_telemetry = nullptr;
+    Model* d_model = nullptr;                     /* the table pointers, in device memory (template build) */
     uint64_t n_replicas = 0;
     uint64_t launches = 0;
     uint32_t warps_per_cta = 0, grid = 0;
@@ -298,6 +295,8 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     m.filters = (const itsb_filter*)e->d_tables[ITSB_BLOB_FILTERS];
     m.n_code = d->n_code; m.n_entries = d->n_entries; m.n_dists = d->n_dists; m.n_consts = d->n_consts;
     m.n_nets = d->n_nets; m.n_nodes = d->n_nodes; m.n_init = d->n_init; m.n_filters = d->n_filters;
+    if (!e->d_model) CU(e, cudaMalloc(&e->d_model, sizeof(Model)));
+    CU(e, cudaMemcpy(e->d_model, &m, sizeof(Model), cudaMemcpyHostToDevice));
     e->rp.layout = compute_layout(*d);
     e->so = static_offsets(*d);
     e->rp.static_bytes = e->so.total;
@@ -342,7 +341,7 @@ int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first
         CU(e, cudaMemcpyAsync(tmpl_free, ident.data(), ident.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
         CU(e, cudaStreamSynchronize(e->stream));
     }
-    k_make_template<<<1, 32, 0, e->stream>>>(e->rp, tmpl, tmpl_arena, tmpl_free);
+    k_make_template<<<1, 32, 0, e->stream>>>(e->rp, e->d_model, tmpl, tmpl_arena, tmpl_free);
     CU(e, cudaGetLastError());
     uint32_t blocks = (uint32_t)(n < (uint64_t)e->prop.multiProcessorCount * 8 ? n : (uint64_t)e->prop.multiProcessorCount * 8);
     k_fan_out<<<blocks, 256, 0, e->stream>>>(e->rp, tmpl, tmpl_arena, first_replica_id);
@@ -537,7 +536,7 @@ void itsb_destroy(itsb_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     free_replicas(e);
     for (int i = 0; i < ITSB_NUM_BLOBS; ++i) cudaFree(e->d_tables[i]);
-    cudaFree(e->d_ticket); cudaFree(e->d_first_failed); cudaFree(e->d_telemetry);
+    cudaFree(e->d_ticket); cudaFree(e->d_first_failed); cudaFree(e->d_telemetry); cudaFree(e->d_model);
     if (e->ev_start) cudaEventDestroy(e->ev_start);
     if (e->ev_stop) cudaEventDestroy(e->ev_stop);
     if (e->stream) cudaStreamDestroy(e->stream);

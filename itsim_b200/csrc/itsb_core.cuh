@@ -14,9 +14,16 @@
  * Execution model.  All lanes of the warp run this code with warp-uniform control flow; replica state lives in the
  * warp's slice of shared memory.  Scalar bookkeeping is executed redundantly by every lane (same value, same
  * address), so each lane is self-consistent without fences; the lane-parallel phases -- the event-pool minimum
- * (strided scan + redux min-reduction), the delivery fan-out over a link's recipients (ballot / prefix ranks), slot
- * allocation -- end with a warp sync.  The socket packet queues and remembered-packet lists live in a per-replica
- * arena in HBM (they grow to thousands of packets while a workstation sleeps).
+ * (strided scan + redux min-reduction), the delivery fan-out over a link's recipients (ballot / prefix ranks) -- end
+ * with a warp sync.  Socket packet queues, remembered-packet lists and packets in flight live in a per-replica
+ * arena in HBM (queues grow to thousands of packets while a workstation sleeps).
+ *
+ * Code layout.  The first profile of this kernel was instruction-fetch bound (60 % of stall samples "no
+ * instruction": 100+ KB of SASS, a dozen warps per SM each somewhere else in it).  So the hot loop -- next event,
+ * delivery pass, the handful of instructions a daemon executes per packet -- is inlined into the kernel, and
+ * everything else (variates, socket open/close, spawn/exit, transmission bookkeeping, spill paths, tracing) is an
+ * out-of-line function that takes only the replica header: the header carries the offsets and pointers needed to
+ * rebuild a working view (Rep) of the replica on entry.
  *
  * The same source builds with ITSB_W == 1 (one "lane") as a plain C++ translation unit; that build exists only so
  * the unit tests can exercise the interpreter without a GPU (tests/hostemu).  The product library never contains it.
@@ -31,11 +38,11 @@
 #if defined(__CUDACC__)
 #define ITSB_W 32
 #define ITSB_FN __device__ __forceinline__
-#define ITSB_FN_NOINLINE static __device__ __noinline__
+#define ITSB_COLD static __device__ __noinline__
 #else
 #define ITSB_W 1
 #define ITSB_FN static inline
-#define ITSB_FN_NOINLINE static
+#define ITSB_COLD static __attribute__((noinline))
 #endif
 
 namespace itsb {
@@ -48,6 +55,7 @@ typedef uint64_t u64;
 static const u16 NIL16 = 0xFFFF;
 static const u32 NIL32 = 0xFFFFFFFFu;
 static const u64 T_EMPTY = 0x7FF0000000000000ull; /* +inf: empty event slot */
+static const u32 NQ_CAP = 128;                    /* now-queue ring entries (power of two) */
 
 /* ---- warp primitives (trivial when ITSB_W == 1) --------------------------------------------------------------- */
 #if defined(__CUDACC__)
@@ -55,7 +63,6 @@ ITSB_FN int lane_id() { return (int)(threadIdx.x & 31); }
 ITSB_FN u32 w_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
 ITSB_FN u32 w_shfl(u32 v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
 ITSB_FN u32 w_min(u32 v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
-ITSB_FN u32 w_add(u32 v) { return __reduce_add_sync(0xFFFFFFFFu, v); }
 ITSB_FN void w_sync() { __syncwarp(); }
 ITSB_FN u32 w_excl_scan(u32 v, u32* total) {
     u32 x = v;
@@ -73,12 +80,12 @@ ITSB_FN int ffs32(u32 v) { return __ffs(v); }
 ITSB_FN u64 dbits(double d) { return (u64)__double_as_longlong(d); }
 ITSB_FN double bitsd(u64 b) { return __longlong_as_double((long long)b); }
 ITSB_FN u32 mulhi32(u32 a, u32 b) { return __umulhi(a, b); }
+ITSB_FN u32 clz32(u32 v) { return (u32)__clz((int)v); }
 #else
 ITSB_FN int lane_id() { return 0; }
 ITSB_FN u32 w_ballot(bool p) { return p ? 1u : 0u; }
 ITSB_FN u32 w_shfl(u32 v, int) { return v; }
 ITSB_FN u32 w_min(u32 v) { return v; }
-ITSB_FN u32 w_add(u32 v) { return v; }
 ITSB_FN void w_sync() {}
 ITSB_FN u32 w_excl_scan(u32 v, u32* total) { *total = v; return 0; }
 ITSB_FN u32 lanemask_lt() { return 0; }
@@ -87,30 +94,10 @@ ITSB_FN int ffs32(u32 v) { return __builtin_ffs((int)v); }
 ITSB_FN u64 dbits(double d) { u64 b; memcpy(&b, &d, 8); return b; }
 ITSB_FN double bitsd(u64 b) { double d; memcpy(&d, &b, 8); return d; }
 ITSB_FN u32 mulhi32(u32 a, u32 b) { return (u32)(((u64)a * (u64)b) >> 32); }
+ITSB_FN u32 clz32(u32 v) { return (u32)__builtin_clz(v); }
 #endif
 
 /* ---- per-replica state ------------------------------------------------------------------------------------------ */
-
-struct Hdr {                /* 128 bytes */
-    double now;
-    u64 draws;              /* Philox draw index (oracle/philox.py stream layout) */
-    u32 seq;                /* greensim's insertion counter */
-    int32_t status;         /* 0, ITSB_ERR_CAP_* or ITSB_EXC_* */
-    u64 detail;
-    u32 arena_free_top;
-    u32 trace_count;
-    u16 ev_free_top, pcb_free_top, sock_free_top, pkt_free_top;
-    u32 replica_lo, replica_hi;
-    /* now-queue: FIFO of the events scheduled with zero delay (they all carry t == now) */
-    u32 nq_head, nq_tail;   /* monotone cursors into the shared-memory ring */
-    u32 nq_spill_head, nq_spill_tail, nq_spill_count;   /* arena-backed continuation when the ring is full */
-    /* future pool: cached minimum, and the arena-backed overflow list used when the pool is full */
-    u32 pmin_valid, pmin_idx, pmin_seq;
-    u64 pmin_t;
-    u64 ovf_min_t;
-    u32 ovf_min_seq, ovf_head, ovf_count;
-    u32 pad[5];
-};
 
 struct Pcb {                /* 48 bytes: one greensim process */
     u16 pc;
@@ -120,7 +107,7 @@ struct Pcb {                /* 48 bytes: one greensim process */
     u16 gen;
     u16 wnext, wprev;       /* waiter-list links */
     u16 wsig;               /* what it waits on: WS_* | index */
-    u16 timer_ev;           /* event slot of its pending advance() wake-up */
+    u16 timer_ev;           /* pool slot of its pending advance() wake-up */
     u16 sock;
     u16 exc;                /* last exception delivered */
     u32 list_head, list_tail; /* remembered-packet list (arena nodes) */
@@ -150,7 +137,7 @@ struct NodeDyn {            /* 16 bytes */
     u32 awake;
 };
 
-struct Pkt {                /* 32 bytes: a packet in flight */
+struct Pkt {                /* 32 bytes: a packet in flight (an arena node) */
     u32 src_ip, dst_ip;
     u32 ports;              /* src | dst << 16 */
     u32 size;
@@ -158,13 +145,21 @@ struct Pkt {                /* 32 bytes: a packet in flight */
     u32 meta;               /* src node | net << 16 */
 };
 
-struct ArenaNode {          /* 32 bytes = one DRAM sector */
+struct ArenaNode {          /* 32 bytes = one DRAM sector: a queued / remembered packet */
     u32 next;
     u32 src_ip;
     u32 ports;
     u32 size;
     u32 tag, f0, f1;
     u32 pad;
+};
+
+struct EvNode {             /* arena node used by the now-queue spill chain and the pool overflow list */
+    u32 next;
+    u32 seq;
+    u32 data;
+    u32 t_lo, t_hi;
+    u32 pad[3];
 };
 
 struct Layout {             /* byte offsets inside one replica's hot block */
@@ -175,7 +170,7 @@ struct Layout {             /* byte offsets inside one replica's hot block */
     u32 arena_nodes, trace_cap;
 };
 
-struct Model {              /* device pointers to the static tables */
+struct Model {              /* pointers to the static tables (shared-memory copies inside the kernel) */
     const u64* code;
     const itsb_entry* entries;
     const itsb_dist* dists;
@@ -187,7 +182,38 @@ struct Model {              /* device pointers to the static tables */
     u32 n_code, n_entries, n_dists, n_consts, n_nets, n_nodes, n_init, n_filters;
 };
 
-struct Rep {                /* working view of one replica (pointers into the hot block + HBM side buffers) */
+/* interpreter scratch registers, valid inside one activation of a process; index = operand source - 0x10 */
+enum { VOL_COUNT = 40 };
+
+struct Hdr {                /* first thing in the hot block */
+    /* -- persistent state -- */
+    double now;
+    u64 draws;              /* Philox draw index (oracle/philox.py stream layout) */
+    u32 seq;                /* greensim's insertion counter */
+    int32_t status;         /* 0, ITSB_ERR_CAP_* or ITSB_EXC_* */
+    u64 detail;
+    u32 arena_free_top;
+    u32 trace_count;
+    u16 ev_free_top, pcb_free_top, sock_free_top, spare16;
+    u32 replica_lo, replica_hi;
+    u32 nq_head, nq_tail;   /* now-queue ring cursors (monotone) */
+    u32 nq_spill_head, nq_spill_tail, nq_spill_count;
+    u32 pmin_valid, pmin_idx, pmin_seq;
+    u64 pmin_t;
+    u64 ovf_min_t;
+    u32 ovf_min_seq, ovf_head, ovf_count;
+    u32 spare32;
+    /* -- binding: rewritten every time the replica is staged (pointers of this launch, not state) -- */
+    ArenaNode* arena;
+    u32* arena_free;
+    itsb_trace_rec* trace;
+    const Model* model;
+    u32 seed_lo, seed_hi;
+    Layout L;
+    u32 vol[VOL_COUNT];
+};
+
+struct Rep {                /* register-resident working view of one replica */
     Hdr* hdr;
     u64* ev_t;
     u32* ev_seq;
@@ -200,42 +226,60 @@ struct Rep {                /* working view of one replica (pointers into the ho
     u16* sock_free;
     NodeDyn* node;
     u64* stats;
-    ArenaNode* arena;       /* HBM */
-    u32* arena_free;        /* HBM */
-    itsb_trace_rec* trace;  /* HBM or null */
-    Model m;                /* by value: table pointers stay in registers */
-    Layout L;
-    /* volatile interpreter registers: valid only inside one activation of a process */
-    u32 pk_src_ip, pk_src_port, pk_size, pk_tag, pk_f0, pk_f1;
-    u32 ent_ip, ent_port;
-    u64 events;             /* simulated events processed by this call */
+    ArenaNode* arena;
+    u32* arena_free;
+    itsb_trace_rec* trace;
+    Model m;
+    u32 max_ev, trace_cap;
 };
 
-ITSB_FN void bind_views(Rep& R, unsigned char* hot, const Layout* L) {
-    R.L = *L;
-    R.hdr = (Hdr*)hot;
-    R.ev_t = (u64*)(hot + L->off_ev_t);
-    R.ev_seq = (u32*)(hot + L->off_ev_seq);
-    R.ev_data = (u32*)(hot + L->off_ev_data);
-    R.ev_free = (u16*)(hot + L->off_ev_free);
-    R.nq = (u32*)(hot + L->off_nq);
-    R.pcb = (Pcb*)(hot + L->off_pcb);
-    R.pcb_free = (u16*)(hot + L->off_pcb_free);
-    R.sock = (Sock*)(hot + L->off_sock);
-    R.sock_free = (u16*)(hot + L->off_sock_free);
-    R.node = (NodeDyn*)(hot + L->off_node);
-    R.stats = (u64*)(hot + L->off_stats);
-    R.events = 0;
+/* Rebuilds the working view from the header alone (used on entry by every out-of-line function; unused fields are
+ * dead code there). */
+ITSB_FN void rebind(Rep& R, Hdr* H) {
+    unsigned char* hot = (unsigned char*)H;
+    R.hdr = H;
+    R.ev_t = (u64*)(hot + H->L.off_ev_t);
+    R.ev_seq = (u32*)(hot + H->L.off_ev_seq);
+    R.ev_data = (u32*)(hot + H->L.off_ev_data);
+    R.ev_free = (u16*)(hot + H->L.off_ev_free);
+    R.nq = (u32*)(hot + H->L.off_nq);
+    R.pcb = (Pcb*)(hot + H->L.off_pcb);
+    R.pcb_free = (u16*)(hot + H->L.off_pcb_free);
+    R.sock = (Sock*)(hot + H->L.off_sock);
+    R.sock_free = (u16*)(hot + H->L.off_sock_free);
+    R.node = (NodeDyn*)(hot + H->L.off_node);
+    R.stats = (u64*)(hot + H->L.off_stats);
+    R.arena = H->arena;
+    R.arena_free = H->arena_free;
+    R.trace = H->trace;
+    R.m = *H->model;
+    R.max_ev = H->L.max_ev;
+    R.trace_cap = H->L.trace_cap;
 }
 
-ITSB_FN void fail(Rep& R, int status, u64 detail) {
-    if (R.hdr->status == 0) {
-        R.hdr->status = status;
-        R.hdr->detail = detail;
+/* Stages the launch's pointers into the header, then builds the view. */
+ITSB_FN void bind_views(Rep& R, unsigned char* hot, const Layout* L, const Model* model, ArenaNode* arena,
+                        u32* arena_free, itsb_trace_rec* trace, u64 seed) {
+    Hdr* H = (Hdr*)hot;
+    H->L = *L;
+    H->model = model;
+    H->arena = arena;
+    H->arena_free = arena_free;
+    H->trace = trace;
+    H->seed_lo = (u32)seed;
+    H->seed_hi = (u32)(seed >> 32);
+    w_sync();
+    rebind(R, H);
+}
+
+ITSB_COLD void fail(Hdr* H, int status, u64 detail) {
+    if (H->status == 0) {
+        H->status = status;
+        H->detail = detail;
     }
 }
 
-/* ---- event data word: kind[0:4] exc[4:12] proc-or-packet[12:22] gen[22:32] ------------------------------------- */
+/* ---- event data word: kind[0:4] exc[4:12] proc[12:22] gen[22:32]; packet events: kind[0:4] arena-index[4:32] ---- */
 ITSB_FN u32 ev_pack(u32 kind, u32 idx, u32 gen, u32 exc) {
     return kind | ((exc & 0xFF) << 4) | ((idx & 0x3FF) << 12) | ((gen & 0x3FF) << 22);
 }
@@ -243,7 +287,6 @@ ITSB_FN u32 ev_kind(u32 d) { return d & 0xF; }
 ITSB_FN u32 ev_exc(u32 d) { return (d >> 4) & 0xFF; }
 ITSB_FN u32 ev_idx(u32 d) { return (d >> 12) & 0x3FF; }
 ITSB_FN u32 ev_gen(u32 d) { return (d >> 22) & 0x3FF; }
-/* packet events (TX_BEGIN / TX_END / DELIVER): kind[0:4] arena-index[4:32] */
 ITSB_FN u32 ev_pack_pkt(u32 kind, u32 node_index) { return kind | (node_index << 4); }
 ITSB_FN u32 ev_pkt(u32 d) { return d >> 4; }
 
@@ -251,7 +294,6 @@ ITSB_FN u32 ev_pkt(u32 d) { return d >> 4; }
 ITSB_FN void philox_block(u32 seed_lo, u32 seed_hi, u32 rep_lo, u32 rep_hi, u64 block, u32 out[4]) {
     u32 c0 = (u32)block, c1 = (u32)(block >> 32), c2 = seed_hi, c3 = rep_hi;
     u32 k0 = seed_lo, k1 = rep_lo;
-#pragma unroll
     for (int rnd = 0; rnd < 10; ++rnd) {
         if (rnd) { k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
         u32 hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -262,29 +304,26 @@ ITSB_FN void philox_block(u32 seed_lo, u32 seed_hi, u32 rep_lo, u32 rep_hi, u64 
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-struct Seed { u32 lo, hi; };
-
 /* Draw d of the replica's stream: the 64 bits (a, b) of its half of Philox block d >> 1. */
-ITSB_FN void rng_next(Hdr* H, Seed seed, u32& a, u32& b) {
+ITSB_COLD u64 rng_next(Hdr* H) {
     const u64 d = H->draws;
     H->draws = d + 1;
     u32 w[4];
-    philox_block(seed.lo, seed.hi, H->replica_lo, H->replica_hi, d >> 1, w);
+    philox_block(H->seed_lo, H->seed_hi, H->replica_lo, H->replica_hi, d >> 1, w);
     const bool half = (d & 1) != 0;
-    a = half ? w[2] : w[0];
-    b = half ? w[3] : w[1];
+    const u32 a = half ? w[2] : w[0];
+    const u32 b = half ? w[3] : w[1];
+    return ((u64)a << 32) | b;
 }
 
-ITSB_FN double rng_random(Hdr* H, Seed seed) {  /* CPython's 53-bit construction */
-    u32 a, b;
-    rng_next(H, seed, a, b);
+ITSB_FN double rng_random(Hdr* H) {  /* CPython's 53-bit construction */
+    const u64 ab = rng_next(H);
+    const u32 a = (u32)(ab >> 32), b = (u32)ab;
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
 }
 
-/* One value of a generator chain: kind -> linear -> bounded -> project_int (itsim/random.py:29).  Kept out of line:
- * it is reached from five places and holds two log() expansions and the Philox rounds; inlining it everywhere made
- * the kernel 200 KB of SASS and instruction-fetch bound. */
-ITSB_FN_NOINLINE double draw_dist(Hdr* H, Seed seed, const itsb_dist* Dp) {
+/* One value of a generator chain: kind -> linear -> bounded -> project_int (itsim/random.py:29). */
+ITSB_COLD double draw_dist(Hdr* H, const itsb_dist* Dp) {
     const itsb_dist D = *Dp;
     double x;
     switch (D.kind) {
@@ -292,16 +331,16 @@ ITSB_FN_NOINLINE double draw_dist(Hdr* H, Seed seed, const itsb_dist* Dp) {
         x = D.p0;
         break;
     case ITSB_DIST_UNIFORM:  /* random.uniform: a + (b - a) * random() */
-        x = D.p0 + (D.p1 - D.p0) * rng_random(H, seed);
+        x = D.p0 + (D.p1 - D.p0) * rng_random(H);
         break;
     case ITSB_DIST_EXPO:     /* random.expovariate(lambd): -log(1 - random()) / lambd */
-        x = -log(1.0 - rng_random(H, seed)) / D.p0;
+        x = -log(1.0 - rng_random(H)) / D.p0;
         break;
     case ITSB_DIST_NORMAL: { /* random.normalvariate: Kinderman-Monahan ratio of uniforms */
         double z;
         for (;;) {
-            double u1 = rng_random(H, seed);
-            double u2 = 1.0 - rng_random(H, seed);
+            double u1 = rng_random(H);
+            double u2 = 1.0 - rng_random(H);
             z = 1.7155277699214135 * (u1 - 0.5) / u2;
             double zz = z * z / 4.0;
             if (zz <= -log(u2)) break;
@@ -310,18 +349,11 @@ ITSB_FN_NOINLINE double draw_dist(Hdr* H, Seed seed, const itsb_dist* Dp) {
         break;
     }
     case ITSB_DIST_CHOICE: { /* random.choice -> _randbelow_with_getrandbits(n) */
-        u32 n = (u32)D.p0;
-        u32 k = 32 - (u32)
-#if defined(__CUDACC__)
-            __clz((int)n);
-#else
-            __builtin_clz(n);
-#endif
+        const u32 n = (u32)D.p0;
+        const u32 k = 32 - clz32(n);
         u32 r;
         for (;;) {
-            u32 a, b;
-            rng_next(H, seed, a, b);
-            r = a >> (32 - k);
+            r = (u32)(rng_next(H) >> 32) >> (32 - k);
             if (r < n) break;
         }
         x = (double)r;
@@ -340,22 +372,20 @@ ITSB_FN_NOINLINE double draw_dist(Hdr* H, Seed seed, const itsb_dist* Dp) {
 /* ---- telemetry ------------------------------------------------------------------------------------------------------ */
 ITSB_FN void stat_add(Rep& R, u32 slot, u64 v) { R.stats[slot] += v; }
 
-ITSB_FN void trace_put(Rep& R, u32 kind, u32 prog, u32 node, u32 aux) {
-    if (R.trace) {
-        u32 n = R.hdr->trace_count;
-        if (n < R.L.trace_cap && lane_id() == 0) {
-            itsb_trace_rec rec;
-            rec.t = R.hdr->now; rec.kind = (u8)kind; rec.prog = (u8)prog; rec.node = (u16)node; rec.aux = aux;
-            R.trace[n] = rec;
-        }
-        R.hdr->trace_count = n + 1;
+ITSB_COLD void trace_put(Hdr* H, u32 kind, u32 prog, u32 node, u32 aux) {
+    u32 n = H->trace_count;
+    if (n < H->L.trace_cap && lane_id() == 0) {
+        itsb_trace_rec rec;
+        rec.t = H->now; rec.kind = (u8)kind; rec.prog = (u8)prog; rec.node = (u16)node; rec.aux = aux;
+        H->trace[n] = rec;
     }
+    H->trace_count = n + 1;
 }
 
+/* one simulated event of the given kind (SURVEY.md section 8-d definition) */
 ITSB_FN void count_event(Rep& R, u32 kind, u32 prog, u32 node, u32 aux) {
     R.stats[ITSB_TM_KIND0 + kind] += 1;
-    R.events += 1;
-    trace_put(R, kind, prog, node, aux);
+    if (R.trace) trace_put(R.hdr, kind, prog, node, aux);
 }
 
 /* transit-delay histogram: bin = clamp(floor(log2(delay / 1us)), 0, 63) via the exponent field */
@@ -366,9 +396,10 @@ ITSB_FN u32 latency_bin(double delay) {
     return e > (ITSB_LAT_BINS - 1) ? (ITSB_LAT_BINS - 1) : e;
 }
 
+/* ---- arena (HBM) -------------------------------------------------------------------------------------------------- */
 ITSB_FN u32 arena_alloc(Rep& R) {
     u32 top = R.hdr->arena_free_top;
-    if (top == 0) { fail(R, ITSB_ERR_CAP_ARENA, 0); return NIL32; }
+    if (top == 0) { fail(R.hdr, ITSB_ERR_CAP_ARENA, 0); return NIL32; }
     top -= 1;
     R.hdr->arena_free_top = top;
     return R.arena_free[top];
@@ -393,46 +424,26 @@ ITSB_FN void arena_release(Rep& R, u32 idx) {
  * with a thousand queued packets emits its answers in one instant): the ring spills to a FIFO chain, the pool to an
  * unordered overflow list with its own cached minimum.
  */
-static const u32 NQ_CAP = 128;        /* ring entries (power of two) */
-
-struct EvNode {            /* arena node used by the spill chain and the overflow list (32 bytes) */
-    u32 next;
-    u32 seq;
-    u32 data;
-    u32 t_lo, t_hi;
-    u32 pad[3];
-};
-
-/* slow paths, out of line: they run only when a burst outgrows the shared-memory structures */
-ITSB_FN_NOINLINE u32 arena_alloc_raw(Hdr* H, const u32* arena_free) {
-    u32 top = H->arena_free_top;
-    if (top == 0) {
-        if (H->status == 0) { H->status = ITSB_ERR_CAP_ARENA; H->detail = 0; }
-        return NIL32;
-    }
-    top -= 1;
-    H->arena_free_top = top;
-    return arena_free[top];
-}
-
-ITSB_FN_NOINLINE void nq_spill_push(Hdr* H, ArenaNode* arena, const u32* arena_free, u32 seq, u32 data) {
-    u32 n = arena_alloc_raw(H, arena_free);
+ITSB_COLD void nq_spill_push(Hdr* H, u32 seq, u32 data) {
+    Rep R; rebind(R, H);
+    u32 n = arena_alloc(R);
     if (n == NIL32) return;
     EvNode E;
     E.next = NIL32; E.seq = seq; E.data = data; E.t_lo = 0; E.t_hi = 0; E.pad[0] = 0; E.pad[1] = 0; E.pad[2] = 0;
-    *(EvNode*)&arena[n] = E;
-    if (H->nq_spill_count == 0) H->nq_spill_head = n; else ((EvNode*)&arena[H->nq_spill_tail])->next = n;
+    *(EvNode*)&R.arena[n] = E;
+    if (H->nq_spill_count == 0) H->nq_spill_head = n; else ((EvNode*)&R.arena[H->nq_spill_tail])->next = n;
     H->nq_spill_tail = n;
     H->nq_spill_count += 1;
 }
 
-ITSB_FN_NOINLINE void ovf_push(Hdr* H, ArenaNode* arena, const u32* arena_free, u64 tb, u32 seq, u32 data) {
-    u32 n = arena_alloc_raw(H, arena_free);
+ITSB_COLD void ovf_push(Hdr* H, u64 tb, u32 seq, u32 data) {
+    Rep R; rebind(R, H);
+    u32 n = arena_alloc(R);
     if (n == NIL32) return;
     EvNode E;
     E.next = H->ovf_count ? H->ovf_head : NIL32; E.seq = seq; E.data = data;
     E.t_lo = (u32)tb; E.t_hi = (u32)(tb >> 32); E.pad[0] = 0; E.pad[1] = 0; E.pad[2] = 0;
-    *(EvNode*)&arena[n] = E;
+    *(EvNode*)&R.arena[n] = E;
     H->ovf_head = n;
     if (H->ovf_count == 0 || tb < H->ovf_min_t || (tb == H->ovf_min_t && seq < H->ovf_min_seq)) {
         H->ovf_min_t = tb; H->ovf_min_seq = seq;
@@ -440,21 +451,9 @@ ITSB_FN_NOINLINE void ovf_push(Hdr* H, ArenaNode* arena, const u32* arena_free, 
     H->ovf_count += 1;
 }
 
-ITSB_FN void nq_push_seq(Rep& R, u32 seq, u32 data) {
-    Hdr* H = R.hdr;
-    if (H->nq_spill_count == 0 && H->nq_tail - H->nq_head < NQ_CAP) {
-        u32 i = H->nq_tail & (NQ_CAP - 1);
-        R.nq[2 * i] = seq;
-        R.nq[2 * i + 1] = data;
-        H->nq_tail += 1;
-        return;
-    }
-    nq_spill_push(H, R.arena, R.arena_free, seq, data);
-}
-
 /* Moves spilled entries back into the ring once it has drained. */
-ITSB_FN void nq_refill(Rep& R) {
-    Hdr* H = R.hdr;
+ITSB_COLD void nq_refill(Hdr* H) {
+    Rep R; rebind(R, H);
     while (H->nq_spill_count != 0 && H->nq_tail - H->nq_head < NQ_CAP) {
         u32 n = H->nq_spill_head;
         const EvNode E = *(const EvNode*)&R.arena[n];
@@ -468,73 +467,9 @@ ITSB_FN void nq_refill(Rep& R) {
     }
 }
 
-ITSB_FN void ev_release(Rep& R, u32 slot) {
-    R.ev_t[slot] = T_EMPTY;
-    u32 top = R.hdr->ev_free_top;
-    R.ev_free[top] = (u16)slot;
-    R.hdr->ev_free_top = (u16)(top + 1);
-    if (R.hdr->pmin_valid && R.hdr->pmin_idx == slot) R.hdr->pmin_valid = 0;
-}
-
-/* Schedules (t, seq = counter++).  Returns the pool slot (so an advance() can be cancelled) or -1. */
-ITSB_FN int ev_push(Rep& R, double t, u32 data) {
-    Hdr* H = R.hdr;
-    const u32 seq = H->seq;
-    H->seq = seq + 1;
-    const u64 tb = dbits(t);
-    if (tb == dbits(H->now)) { nq_push_seq(R, seq, data); return -1; }
-    u32 top = H->ev_free_top;
-    if (top == 0) {   /* pool full: unordered overflow list in the arena */
-        ovf_push(H, R.arena, R.arena_free, tb, seq, data);
-        return -1;
-    }
-    top -= 1;
-    H->ev_free_top = (u16)top;
-    u32 slot = R.ev_free[top];
-    R.ev_t[slot] = tb;
-    R.ev_seq[slot] = seq;
-    R.ev_data[slot] = data;
-    if (H->pmin_valid && (tb < H->pmin_t || (tb == H->pmin_t && seq < H->pmin_seq))) {
-        H->pmin_t = tb; H->pmin_seq = seq; H->pmin_idx = slot;
-    }
-    return (int)slot;
-}
-
-/* Minimum (t, seq) of the future pool: each lane scans a strided slice, then three redux min-reductions. */
-ITSB_FN void pool_scan_min(Rep& R) {
-    u64 bt = T_EMPTY;
-    u32 bs = NIL32;
-    u32 bi = NIL32;
-    const u32 n = R.L.max_ev;
-    for (u32 i = (u32)lane_id(); i < n; i += ITSB_W) {
-        u64 t = R.ev_t[i];
-        u32 s = R.ev_seq[i];
-        if (t < bt || (t == bt && s < bs)) { bt = t; bs = s; bi = i; }
-    }
-    Hdr* H = R.hdr;
-    u32 hi = (u32)(bt >> 32);
-    u32 mhi = w_min(hi);
-    if (mhi >= 0x7FF00000u) {
-        H->pmin_t = T_EMPTY; H->pmin_seq = NIL32; H->pmin_idx = NIL32; H->pmin_valid = 1;
-        return;
-    }
-    bool cand = (hi == mhi);
-    u32 lo = cand ? (u32)bt : NIL32;
-    u32 mlo = w_min(lo);
-    cand = cand && (lo == mlo);
-    u32 sq = cand ? bs : NIL32;
-    u32 msq = w_min(sq);
-    cand = cand && (sq == msq);
-    int winner = ffs32(w_ballot(cand)) - 1;
-    H->pmin_idx = w_shfl(bi, winner);
-    H->pmin_t = ((u64)mhi << 32) | mlo;
-    H->pmin_seq = msq;
-    H->pmin_valid = 1;
-}
-
 /* Removes the minimum of the overflow list (rare: only after the pool filled up) and recomputes its cached minimum. */
-ITSB_FN u32 ovf_take_min(Rep& R) {
-    Hdr* H = R.hdr;
+ITSB_COLD u32 ovf_take_min(Hdr* H) {
+    Rep R; rebind(R, H);
     u32 prev = NIL32, n = H->ovf_head, data = 0;
     const u64 want_t = H->ovf_min_t;
     const u32 want_seq = H->ovf_min_seq;
@@ -561,13 +496,90 @@ ITSB_FN u32 ovf_take_min(Rep& R) {
     return data;
 }
 
+ITSB_FN void ev_release(Rep& R, u32 slot) {
+    R.ev_t[slot] = T_EMPTY;
+    u32 top = R.hdr->ev_free_top;
+    R.ev_free[top] = (u16)slot;
+    R.hdr->ev_free_top = (u16)(top + 1);
+    if (R.hdr->pmin_valid && R.hdr->pmin_idx == slot) R.hdr->pmin_valid = 0;
+}
+
+/* Schedules (t, seq = counter++).  Returns the pool slot (so an advance() can be cancelled) or -1. */
+ITSB_FN int ev_push_inl(Rep& R, double t, u32 data) {
+    Hdr* H = R.hdr;
+    const u32 seq = H->seq;
+    H->seq = seq + 1;
+    const u64 tb = dbits(t);
+    if (tb == dbits(H->now)) {
+        if (H->nq_spill_count == 0 && H->nq_tail - H->nq_head < NQ_CAP) {
+            u32 i = H->nq_tail & (NQ_CAP - 1);
+            R.nq[2 * i] = seq;
+            R.nq[2 * i + 1] = data;
+            H->nq_tail += 1;
+        } else {
+            nq_spill_push(H, seq, data);
+        }
+        return -1;
+    }
+    u32 top = H->ev_free_top;
+    if (top == 0) {   /* pool full: unordered overflow list in the arena */
+        ovf_push(H, tb, seq, data);
+        return -1;
+    }
+    top -= 1;
+    H->ev_free_top = (u16)top;
+    u32 slot = R.ev_free[top];
+    R.ev_t[slot] = tb;
+    R.ev_seq[slot] = seq;
+    R.ev_data[slot] = data;
+    if (H->pmin_valid && (tb < H->pmin_t || (tb == H->pmin_t && seq < H->pmin_seq))) {
+        H->pmin_t = tb; H->pmin_seq = seq; H->pmin_idx = slot;
+    }
+    return (int)slot;
+}
+
+/* Minimum (t, seq) of the future pool: each lane scans a strided slice, then three redux min-reductions. */
+ITSB_COLD void pool_scan_min(Hdr* H) {
+    Rep R; rebind(R, H);
+    u64 bt = T_EMPTY;
+    u32 bs = NIL32;
+    u32 bi = NIL32;
+    const u32 n = R.max_ev;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (u32 i = (u32)lane_id(); i < n; i += ITSB_W) {
+        u64 t = R.ev_t[i];
+        u32 s = R.ev_seq[i];
+        if (t < bt || (t == bt && s < bs)) { bt = t; bs = s; bi = i; }
+    }
+    u32 hi = (u32)(bt >> 32);
+    u32 mhi = w_min(hi);
+    if (mhi >= 0x7FF00000u) {
+        H->pmin_t = T_EMPTY; H->pmin_seq = NIL32; H->pmin_idx = NIL32; H->pmin_valid = 1;
+        return;
+    }
+    bool cand = (hi == mhi);
+    u32 lo = cand ? (u32)bt : NIL32;
+    u32 mlo = w_min(lo);
+    cand = cand && (lo == mlo);
+    u32 sq = cand ? bs : NIL32;
+    u32 msq = w_min(sq);
+    cand = cand && (sq == msq);
+    int winner = ffs32(w_ballot(cand)) - 1;
+    H->pmin_idx = w_shfl(bi, winner);
+    H->pmin_t = ((u64)mhi << 32) | mlo;
+    H->pmin_seq = msq;
+    H->pmin_valid = 1;
+}
+
 enum { SRC_NONE_LEFT = 0, SRC_NQ = 1, SRC_POOL = 2, SRC_OVF = 3 };
 
 /* Key of the next event in (t, seq) order and where it sits; nothing is removed yet. */
 ITSB_FN int ev_peek(Rep& R, u64& tbits, u32& seq) {
     Hdr* H = R.hdr;
-    if (H->nq_head == H->nq_tail && H->nq_spill_count != 0) nq_refill(R);
-    if (!H->pmin_valid) pool_scan_min(R);
+    if (H->nq_head == H->nq_tail && H->nq_spill_count != 0) nq_refill(H);
+    if (!H->pmin_valid) pool_scan_min(H);
     int src = SRC_NONE_LEFT;
     tbits = T_EMPTY; seq = NIL32;
     if (H->pmin_t != T_EMPTY) { src = SRC_POOL; tbits = H->pmin_t; seq = H->pmin_seq; }
@@ -582,50 +594,46 @@ ITSB_FN int ev_peek(Rep& R, u64& tbits, u32& seq) {
     return src;
 }
 
-/* Removes the event ev_peek chose; returns its data word and, for pool events, the slot it occupied. */
-ITSB_FN u32 ev_take(Rep& R, int src, u32& slot) {
+/* Removes the event ev_peek chose; returns its data word. */
+ITSB_FN u32 ev_take(Rep& R, int src) {
     Hdr* H = R.hdr;
-    slot = NIL32;
     if (src == SRC_NQ) {
         u32 d = R.nq[2 * (H->nq_head & (NQ_CAP - 1)) + 1];
         H->nq_head += 1;
         return d;
     }
     if (src == SRC_POOL) {
-        slot = H->pmin_idx;
+        u32 slot = H->pmin_idx;
         u32 d = R.ev_data[slot];
         ev_release(R, slot);
         return d;
     }
-    return ovf_take_min(R);
+    return ovf_take_min(H);
 }
 
-/* ---- slots ------------------------------------------------------------------------------------------------------------- */
-ITSB_FN int pcb_alloc(Rep& R) {
-    u32 top = R.hdr->pcb_free_top;
-    if (top == 0) { fail(R, ITSB_ERR_CAP_PROCS, 0); return -1; }
-    top -= 1;
-    R.hdr->pcb_free_top = (u16)top;
-    return (int)R.pcb_free[top];
-}
-
+/* ---- processes ----------------------------------------------------------------------------------------------------------- */
 ITSB_FN u32 handle_of(Rep& R, u32 p) { return p | ((u32)R.pcb[p].gen << 16); }
 
 /* Creates a process in PS_UNSTARTED and schedules its first switch (greensim add / add_in). */
-ITSB_FN int proc_spawn(Rep& R, u32 entry, u32 node, const u32 regs[4], double delay) {
-    int p = pcb_alloc(R);
-    if (p < 0) return -1;
+ITSB_COLD int proc_spawn(Hdr* H, u32 entry, u32 node, const u32* regs, double delay) {
+    Rep R; rebind(R, H);
+    u32 top = H->pcb_free_top;
+    if (top == 0) { fail(H, ITSB_ERR_CAP_PROCS, 0); return -1; }
+    top -= 1;
+    H->pcb_free_top = (u16)top;
+    const u32 p = R.pcb_free[top];
     Pcb& P = R.pcb[p];
     const itsb_entry E = R.m.entries[entry];
+    const u32 r0 = regs[0], r1 = regs[1], r2 = regs[2], r3 = regs[3];
     P.pc = (u16)E.pc;
     P.state = PS_UNSTARTED;
     P.prog = (u8)E.prog;
     P.node = (u16)node;
     P.wnext = NIL16; P.wprev = NIL16; P.wsig = WS_NONE; P.timer_ev = NIL16; P.sock = NIL16; P.exc = 0;
     P.list_head = NIL32; P.list_tail = NIL32; P.phase = 0;
-    P.r[0] = regs[0]; P.r[1] = regs[1]; P.r[2] = regs[2]; P.r[3] = regs[3];
-    ev_push(R, R.hdr->now + delay, ev_pack(ITSB_EV_PROC_START, (u32)p, P.gen, 0));
-    return p;
+    P.r[0] = r0; P.r[1] = r1; P.r[2] = r2; P.r[3] = r3;
+    ev_push_inl(R, H->now + delay, ev_pack(ITSB_EV_PROC_START, p, P.gen, 0));
+    return (int)p;
 }
 
 ITSB_FN void list_free_all(Rep& R, Pcb& P) {
@@ -638,14 +646,15 @@ ITSB_FN void list_free_all(Rep& R, Pcb& P) {
     P.list_head = NIL32; P.list_tail = NIL32;
 }
 
-ITSB_FN void proc_exit(Rep& R, u32 p) {
+ITSB_COLD void proc_exit(Hdr* H, u32 p) {
+    Rep R; rebind(R, H);
     Pcb& P = R.pcb[p];
     list_free_all(R, P);
     P.state = PS_FREE;
     P.gen = (u16)((P.gen + 1) & 0x3FF);
-    u32 top = R.hdr->pcb_free_top;
+    u32 top = H->pcb_free_top;
     R.pcb_free[top] = (u16)p;
-    R.hdr->pcb_free_top = (u16)(top + 1);
+    H->pcb_free_top = (u16)(top + 1);
 }
 
 /* ---- waiter lists (greensim Queue: FIFO by join order) --------------------------------------------------------------- */
@@ -673,10 +682,26 @@ ITSB_FN void waiters_resume_all(Rep& R, u16& head, u16& tail) {
         u16 nx = P.wnext;
         P.wnext = NIL16; P.wprev = NIL16; P.wsig = WS_NONE;
         P.state = PS_RESUMING;
-        ev_push(R, R.hdr->now, ev_pack(ITSB_EV_WAKE, p, P.gen, 0));
+        ev_push_inl(R, R.hdr->now, ev_pack(ITSB_EV_WAKE, p, P.gen, 0));
         p = nx;
     }
     head = NIL16; tail = NIL16;
+}
+
+/* ws.wake_up(): signal on, every waiter resumed in join order, then the wake time changes (network_simple.py:51-53) */
+ITSB_COLD void node_wake(Hdr* H, u32 node) {
+    Rep R; rebind(R, H);
+    NodeDyn& N = R.node[node];
+    N.awake = 1;
+    waiters_resume_all(R, N.wake_head, N.wake_tail);
+    N.epoch += 1;
+}
+
+/* the ordered fallback of the delivery pass: one socket's waiters through the spilling push */
+ITSB_COLD void sock_resume_waiters(Hdr* H, u32 s) {
+    Rep R; rebind(R, H);
+    Sock& S = R.sock[s];
+    waiters_resume_all(R, S.wait_head, S.wait_tail);
 }
 
 /* ---- sockets ------------------------------------------------------------------------------------------------------------ */
@@ -701,7 +726,8 @@ ITSB_FN bool port_in_use(Rep& R, u32 node, u32 port) {
 }
 
 /* open_socket (overrides.py:337-369): port 0 takes the next free port of the persistent 1024..65535 cycle. */
-ITSB_FN int sock_open(Rep& R, u32 p, u32 port) {
+ITSB_COLD int sock_open(Hdr* H, u32 p, u32 port) {
+    Rep R; rebind(R, H);
     Pcb& P = R.pcb[p];
     NodeDyn& N = R.node[P.node];
     if (port == 0) {
@@ -713,13 +739,13 @@ ITSB_FN int sock_open(Rep& R, u32 p, u32 port) {
         }
         N.port_cursor = (u16)c;
     } else if (port_in_use(R, P.node, port)) {
-        fail(R, ITSB_EXC_PORT_IN_USE, port);
+        fail(H, ITSB_EXC_PORT_IN_USE, port);
         return -1;
     }
-    u32 top = R.hdr->sock_free_top;
-    if (top == 0) { fail(R, ITSB_ERR_CAP_SOCKETS, port); return -1; }
+    u32 top = H->sock_free_top;
+    if (top == 0) { fail(H, ITSB_ERR_CAP_SOCKETS, port); return -1; }
     top -= 1;
-    R.hdr->sock_free_top = (u16)top;
+    H->sock_free_top = (u16)top;
     u32 s = R.sock_free[top];
     Sock& S = R.sock[s];
     S.port = (u16)port; S.node = P.node; S.owner = (u16)p;
@@ -731,21 +757,20 @@ ITSB_FN int sock_open(Rep& R, u32 p, u32 port) {
     return (int)s;
 }
 
-ITSB_FN void sock_close(Rep& R, u32 p) {
+ITSB_COLD void sock_close(Hdr* H, u32 p) {
+    Rep R; rebind(R, H);
     Pcb& P = R.pcb[p];
     u32 s = P.sock;
     if (s == NIL16) return;
     Sock& S = R.sock[s];
     NodeDyn& N = R.node[S.node];
-    /* unlink from the node's socket list */
     if (N.sock_head == s) N.sock_head = S.next;
     else {
         u16 q = N.sock_head;
         while (q != NIL16 && R.sock[q].next != s) q = R.sock[q].next;
         if (q != NIL16) R.sock[q].next = S.next;
     }
-    /* drop queued packets */
-    u32 n = S.q_head;
+    u32 n = S.q_head;      /* drop queued packets */
     while (n != NIL32) {
         u32 nx = R.arena[n].next;
         arena_release(R, n);
@@ -753,30 +778,28 @@ ITSB_FN void sock_close(Rep& R, u32 p) {
     }
     S.q_head = NIL32; S.q_tail = NIL32; S.q_len = 0;
     S.port = 0;
-    u32 top = R.hdr->sock_free_top;
+    u32 top = H->sock_free_top;
     R.sock_free[top] = (u16)s;
-    R.hdr->sock_free_top = (u16)(top + 1);
+    H->sock_free_top = (u16)(top + 1);
     P.sock = NIL16;
 }
 
 /* ---- transmission ---------------------------------------------------------------------------------------------------------- */
-/* Packets in flight live in arena nodes (HBM): a waking daemon can emit hundreds of sends in one instant, and a
- * packet is touched only three times (send, TX_BEGIN, TX_END/DELIVER). */
 ITSB_FN Pkt* pkt_at(Rep& R, u32 k) { return (Pkt*)&R.arena[k]; }
 
 /* Socket.send -> Node._send_to_network -> Network.transmit (overrides.py:122-125,371-377,273-291): the packet
  * becomes a transmission process started with sim.add, i.e. one TX_BEGIN event at the current time. */
-ITSB_FN void net_send(Rep& R, u32 p, u32 dst_ip, u32 dst_port, u32 size, u32 tag, u32 f0, u32 f1) {
+ITSB_COLD void net_send(Hdr* H, u32 p, u32 dst_ip, u32 dst_port, u32 size, u32 tag, u32 f0, u32 f1) {
+    Rep R; rebind(R, H);
     Pcb& P = R.pcb[p];
-    if (P.sock == NIL16) { fail(R, ITSB_EXC_SOCKET_CLOSED, P.pc); return; }
+    if (P.sock == NIL16) { fail(H, ITSB_EXC_SOCKET_CLOSED, P.pc); return; }
     const itsb_node N = R.m.nodes[P.node];
     const itsb_net NET = R.m.nets[N.net];
     if (dst_ip != NET.bcast) {
-        /* must be a member of the network: members have consecutive node indices; find by address */
-        bool found = false;
+        bool found = false;   /* must be a member of the network (CannotForward otherwise, overrides.py:293-297) */
         for (u32 i = (u32)lane_id(); i < NET.n_nodes; i += ITSB_W)
             if (R.m.nodes[NET.first_node + i].addr == dst_ip) found = true;
-        if (w_ballot(found) == 0) { fail(R, ITSB_EXC_NO_SUCH_ADDRESS, dst_ip); return; }
+        if (w_ballot(found) == 0) { fail(H, ITSB_EXC_NO_SUCH_ADDRESS, dst_ip); return; }
     }
     u32 k = arena_alloc(R);
     if (k == NIL32) return;
@@ -788,36 +811,52 @@ ITSB_FN void net_send(Rep& R, u32 p, u32 dst_ip, u32 dst_port, u32 size, u32 tag
     *pkt_at(R, k) = K;
     stat_add(R, ITSB_TM_PACKETS_SENT, 1);
     stat_add(R, ITSB_TM_BYTES_SENT, size);
-    ev_push(R, R.hdr->now, ev_pack_pkt(ITSB_EV_TX_BEGIN, k));
+    ev_push_inl(R, H->now, ev_pack_pkt(ITSB_EV_TX_BEGIN, k));
 }
 
 /* transmission(): advance(next(latency) + len(packet) / next(bandwidth))  (overrides.py:287-288) */
-ITSB_FN void on_tx_begin(Rep& R, Seed seed, u32 k) {
+ITSB_COLD void on_tx_begin(Hdr* H, u32 k) {
+    Rep R; rebind(R, H);
     const Pkt K = *pkt_at(R, k);
     const itsb_net NET = R.m.nets[K.meta >> 16];
     count_event(R, ITSB_EV_TX_BEGIN, 9, K.meta & 0xFFFF, K.size);
-    double lat = draw_dist(R.hdr, seed, &R.m.dists[NET.lat_dist]);
-    double bw = draw_dist(R.hdr, seed, &R.m.dists[NET.bw_dist]);
+    double lat = draw_dist(H, &R.m.dists[NET.lat_dist]);
+    double bw = draw_dist(H, &R.m.dists[NET.bw_dist]);
     double delay = lat + (double)K.size / bw;
-    if (delay < 0.0) { fail(R, ITSB_EXC_NEGATIVE_DELAY, k); return; }
+    if (delay < 0.0) { fail(H, ITSB_EXC_NEGATIVE_DELAY, k); return; }
     stat_add(R, ITSB_TM_LAT0 + latency_bin(delay), 1);
-    ev_push(R, R.hdr->now + delay, ev_pack_pkt(ITSB_EV_TX_END, k));
+    ev_push_inl(R, H->now + delay, ev_pack_pkt(ITSB_EV_TX_END, k));
 }
 
-/* for node in receivers: sim.add(node._receive, packet)  -- one pool entry stands for the R consecutive pushes */
-ITSB_FN void on_tx_end(Rep& R, u32 k) {
+/* for node in receivers: sim.add(node._receive, packet)  -- one queue entry stands for the R consecutive pushes */
+ITSB_COLD void on_tx_end(Hdr* H, u32 k) {
+    Rep R; rebind(R, H);
     const Pkt K = *pkt_at(R, k);
     const itsb_net NET = R.m.nets[K.meta >> 16];
     u32 count = (K.dst_ip == NET.bcast) ? NET.n_nodes : 1u;
     count_event(R, ITSB_EV_TX_END, 9, K.meta & 0xFFFF, K.size);
-    ev_push(R, R.hdr->now, ev_pack_pkt(ITSB_EV_DELIVER, k));
-    R.hdr->seq += count - 1;
+    ev_push_inl(R, H->now, ev_pack_pkt(ITSB_EV_DELIVER, k));
+    H->seq += count - 1;
 }
 
 ITSB_FN bool filter_passes(const itsb_filter F, u32 tag, u32 f0, u32 host, bool list_nonempty) {
     const u32 bit = 1u << (tag & 31);
     return (F.tags_always & bit) != 0 || ((F.tags_if_host & bit) != 0 && f0 == host) ||
            ((F.tags_if_list & bit) != 0 && list_nonempty);
+}
+
+/* trace records of one delivery pass: one DELIVER record per recipient, written by its lane */
+ITSB_COLD void trace_deliveries(Hdr* H, u32 first_slot, u32 node, bool valid, u32 aux, u32 n_valid) {
+    if (valid) {
+        u32 n = H->trace_count + first_slot;
+        if (n < H->L.trace_cap) {
+            itsb_trace_rec rec;
+            rec.t = H->now; rec.kind = ITSB_EV_DELIVER; rec.prog = 10; rec.node = (u16)node; rec.aux = aux;
+            H->trace[n] = rec;
+        }
+    }
+    w_sync();
+    H->trace_count += n_valid;
 }
 
 /* Node._receive for every recipient, in link order (overrides.py:379-382), lane-parallel.
@@ -829,6 +868,7 @@ ITSB_FN bool filter_passes(const itsb_filter F, u32 tag, u32 f0, u32 host, bool 
  * lane retires the wake-up on the spot: no queue node, no event, same counters, same counter values consumed.  Off
  * while tracing, so a trace always shows the reference's interleaving event by event. */
 ITSB_FN void on_deliver(Rep& R, u32 k) {
+    Hdr* H = R.hdr;
     const Pkt K = *pkt_at(R, k);
     const itsb_net NET = R.m.nets[K.meta >> 16];
     const bool bcast = (K.dst_ip == NET.bcast);
@@ -842,14 +882,13 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
         count = 1;
     }
     const u32 dst_port = K.ports >> 16;
-    const double now = R.hdr->now;
+    const double now = H->now;
     bool fast_ok = false;
     if (R.trace == nullptr && R.m.n_filters != 0) {
-        Hdr* H0 = R.hdr;
-        if (H0->nq_head == H0->nq_tail && H0->nq_spill_count == 0) {
-            if (!H0->pmin_valid) pool_scan_min(R);
+        if (H->nq_head == H->nq_tail && H->nq_spill_count == 0) {
+            if (!H->pmin_valid) pool_scan_min(H);
             const u64 nb = dbits(now);
-            fast_ok = H0->pmin_t > nb && (H0->ovf_count == 0 || H0->ovf_min_t > nb);
+            fast_ok = H->pmin_t > nb && (H->ovf_count == 0 || H->ovf_min_t > nb);
         }
     }
     for (u32 base = 0; base < count; base += ITSB_W) {
@@ -874,24 +913,15 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
         }
         const u32 n_found = (u32)popc(w_ballot(found));
         const u32 n_retired = (u32)popc(w_ballot(retire));
-        bool acc = found && !retire;      /* recipients that really enqueue */
-        u32 amask = w_ballot(acc);
-        u32 n_acc = (u32)popc(amask);
-        u32 n_valid = (u32)popc(w_ballot(valid));
-        /* trace: one DELIVER record per recipient */
-        if (R.trace && valid) {
-            u32 n = R.hdr->trace_count + i - base;
-            if (n < R.L.trace_cap) {
-                itsb_trace_rec rec;
-                rec.t = now; rec.kind = ITSB_EV_DELIVER; rec.prog = 10; rec.node = (u16)node;
-                rec.aux = (K.size & 0x7FFFFFFFu) | (found ? 0x80000000u : 0u);
-                R.trace[n] = rec;
-            }
-        }
-        if (R.trace) R.hdr->trace_count += n_valid;
+        const bool acc = found && !retire;      /* recipients that really enqueue */
+        const u32 amask = w_ballot(acc);
+        const u32 n_acc = (u32)popc(amask);
+        const u32 n_valid = (u32)popc(w_ballot(valid));
+        if (R.trace)
+            trace_deliveries(H, i - base, node, valid, (K.size & 0x7FFFFFFFu) | (found ? 0x80000000u : 0u), n_valid);
         /* enqueue a copy on each accepting socket */
-        u32 atop = R.hdr->arena_free_top;
-        if (atop < n_acc) { fail(R, ITSB_ERR_CAP_ARENA, k); return; }
+        u32 atop = H->arena_free_top;
+        if (atop < n_acc) { fail(H, ITSB_ERR_CAP_ARENA, k); return; }
         u32 nwait = 0;
         if (acc) {
             u32 rank = (u32)popc(amask & lanemask_lt());
@@ -906,12 +936,11 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
             S.q_len += 1;
             for (u16 w = S.wait_head; w != NIL16; w = R.pcb[w].wnext) nwait += 1;
         }
-        R.hdr->arena_free_top = atop - n_acc;
+        H->arena_free_top = atop - n_acc;
         /* _enqueue -> packet signal turn_on: resume this socket's waiters (normally the one blocked in recv) */
         u32 total, total_seq;
         u32 before = w_excl_scan(nwait, &total);                               /* ring position: real wake-ups */
         u32 before_seq = w_excl_scan(nwait + (retire ? 1u : 0u), &total_seq);  /* counter value: every waiter  */
-        Hdr* H = R.hdr;
         const bool ring_ok = H->nq_spill_count == 0 && (NQ_CAP - (H->nq_tail - H->nq_head)) >= total;
         if (ring_ok) {
             /* every lane writes its socket's resumes straight into the ring slots its prefix rank assigns */
@@ -923,9 +952,9 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
                     Pcb& P = R.pcb[w];
                     u16 nx = P.wnext;
                     P.wnext = NIL16; P.wprev = NIL16; P.wsig = WS_NONE; P.state = PS_RESUMING;
-                    u32 i = (H->nq_tail + before + j) & (NQ_CAP - 1);
-                    R.nq[2 * i] = H->seq + before_seq + j;
-                    R.nq[2 * i + 1] = ev_pack(ITSB_EV_WAKE, w, P.gen, 0);
+                    u32 q = (H->nq_tail + before + j) & (NQ_CAP - 1);
+                    R.nq[2 * q] = H->seq + before_seq + j;
+                    R.nq[2 * q + 1] = ev_pack(ITSB_EV_WAKE, w, P.gen, 0);
                     j += 1;
                     w = nx;
                 }
@@ -934,27 +963,22 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
             w_sync();
             H->nq_tail += total;
             H->seq += total_seq;
-        } else if (total) {
-            /* ring nearly full: same pushes, in recipient order, through the spilling path (warp-uniform) */
+        } else {
+            /* ring nearly full: same pushes, in recipient order, through the spilling path (warp-uniform);
+               the retiring path is off here because the ring was not empty */
             for (int l = 0; l < ITSB_W; ++l) {
                 u32 nl = w_shfl(nwait, l);
-                if (nl == 0) continue;
-                Sock& S = R.sock[w_shfl((u32)s, l)];
-                waiters_resume_all(R, S.wait_head, S.wait_tail);
+                u32 sl = w_shfl((u32)s, l);
+                if (nl != 0) sock_resume_waiters(H, sl);
             }
-            H->seq += n_retired;   /* (the retiring path is off whenever the ring is not empty; kept for symmetry) */
-        } else {
-            H->seq += total_seq;
         }
         R.stats[ITSB_TM_KIND0 + ITSB_EV_DELIVER] += n_valid;
         R.stats[ITSB_TM_DELIVERED] += n_found;
         R.stats[ITSB_TM_DROPPED] += n_valid - n_found;
-        R.events += n_valid;
         if (n_retired) {
             R.stats[ITSB_TM_KIND0 + ITSB_EV_WAKE] += n_retired;
             R.stats[ITSB_TM_PACKETS_RECEIVED] += n_retired;
             R.stats[ITSB_TM_BYTES_RECEIVED] += (u64)n_retired * K.size;
-            R.events += n_retired;
         }
         w_sync();
     }
@@ -962,136 +986,196 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
 }
 
 /* ---- interpreter ------------------------------------------------------------------------------------------------------------- */
-ITSB_FN u32 src_val(Rep& R, u32 p, u32 s) {
+ITSB_FN u32 vol_index(u32 s) {
+    u32 i = s - 0x10u;
+    return i < VOL_COUNT ? i : VOL_COUNT - 1;
+}
+
+/* operand value: r0..r3, or a scratch register (packet fields, list entry, node constants, ...) */
+ITSB_FN u32 src_val(Rep& R, const Pcb& P, u32 s) { return s < 4 ? P.r[s] : R.hdr->vol[vol_index(s)]; }
+
+ITSB_FN void set_pkt_regs(Rep& R, const ArenaNode& A) {
+    u32* v = R.hdr->vol;
+    v[SRC_PKT_SRC_IP - 0x10] = A.src_ip; v[SRC_PKT_SRC_PORT - 0x10] = A.ports & 0xFFFF;
+    v[SRC_PKT_SIZE - 0x10] = A.size; v[SRC_PKT_TAG - 0x10] = A.tag;
+    v[SRC_PKT_F0 - 0x10] = A.f0; v[SRC_PKT_F1 - 0x10] = A.f1;
+}
+
+enum { XR_CONTINUE = 0, XR_STOP = 1 };
+
+/* Every instruction that is not on the per-packet path of a daemon: out of line. */
+ITSB_COLD int exec_cold(Hdr* H, u32 p, u64 ins) {
+    Rep R; rebind(R, H);
     Pcb& P = R.pcb[p];
-    if (s < 4) return P.r[s];
-    switch (s) {
-    case SRC_PKT_SRC_IP: return R.pk_src_ip;
-    case SRC_PKT_SRC_PORT: return R.pk_src_port;
-    case SRC_PKT_SIZE: return R.pk_size;
-    case SRC_PKT_TAG: return R.pk_tag;
-    case SRC_PKT_F0: return R.pk_f0;
-    case SRC_PKT_F1: return R.pk_f1;
-    case SRC_ENT_IP: return R.ent_ip;
-    case SRC_ENT_PORT: return R.ent_port;
-    case SRC_NODE_ADDR: return R.m.nodes[P.node].addr;
-    case SRC_NODE_INDEX: return P.node;
-    case SRC_NODE_HOST: return R.m.nodes[P.node].host;
-    case SRC_NODE_EPOCH: return R.node[P.node].epoch;
-    case SRC_NODE_BCAST: return R.m.nets[R.m.nodes[P.node].net].bcast;
-    case SRC_SELF: return handle_of(R, p);
-    case SRC_EXC: return P.exc;
-    default: return 0;
+    const u32 op = (u32)(ins & 0xFF), a = (u32)((ins >> 8) & 0xFF), b = (u32)((ins >> 16) & 0xFF),
+              c = (u32)((ins >> 24) & 0xFF), imm = (u32)(ins >> 32);
+    switch (op) {
+    case OP_NOP:
+        P.pc += 1;
+        return XR_CONTINUE;
+    case OP_EXIT:
+        proc_exit(H, p);
+        return XR_STOP;
+    case OP_LI:
+        P.r[a & 3] = imm; P.pc += 1;
+        return XR_CONTINUE;
+    case OP_MOV:
+        P.r[a & 3] = src_val(R, P, b); P.pc += 1;
+        return XR_CONTINUE;
+    case OP_ADDI:
+        P.r[a & 3] = src_val(R, P, b) + imm; P.pc += 1;
+        return XR_CONTINUE;
+    case OP_DRAWI:
+        P.r[a & 3] = (u32)(int32_t)(long long)draw_dist(H, &R.m.dists[imm]);
+        P.pc += 1;
+        return XR_CONTINUE;
+    case OP_DRAW_ADDI: {
+        double v = (double)(int32_t)src_val(R, P, b) + draw_dist(H, &R.m.dists[imm]);
+        P.r[a & 3] = (u32)(int32_t)(long long)v;
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
+    case OP_ADVANCE:
+    case OP_ADVANCE_C: {
+        double d = (op == OP_ADVANCE) ? draw_dist(H, &R.m.dists[imm & 0xFFFF]) : R.m.consts[imm & 0xFFFF];
+        if (d < 0.0) { fail(H, ITSB_EXC_NEGATIVE_DELAY, P.pc); return XR_STOP; }
+        P.timer_tok = (u16)(P.timer_tok + 1);
+        int slot = ev_push_inl(R, H->now + d, ev_pack(ITSB_EV_TIMER, p, P.gen, P.timer_tok));
+        P.timer_ev = slot < 0 ? NIL16 : (u16)slot;
+        P.state = PS_TIMER;
+        return XR_STOP;  /* pc stays on the ADVANCE; the TIMER event moves it on */
+    }
+    case OP_OPEN:
+        if (sock_open(H, p, imm & 0xFFFF) < 0) return XR_STOP;
+        P.pc += 1;
+        return XR_CONTINUE;
+    case OP_CLOSE:
+        sock_close(H, p);
+        P.pc += 1;
+        return XR_CONTINUE;
+    case OP_SEND: {
+        const u32* v = H->vol;
+        u32 dst_ip, dst_port = imm & 0xFFFF;
+        switch (a) {
+        case DST_BCAST: dst_ip = v[SRC_NODE_BCAST - 0x10]; break;
+        case DST_PKT_SRC: dst_ip = v[SRC_PKT_SRC_IP - 0x10]; dst_port = v[SRC_PKT_SRC_PORT - 0x10]; break;
+        case DST_ENT: dst_ip = v[SRC_ENT_IP - 0x10]; dst_port = v[SRC_ENT_PORT - 0x10]; break;
+        case DST_SELF: dst_ip = v[SRC_NODE_ADDR - 0x10]; break;
+        default: dst_ip = P.r[2]; dst_port = P.r[3] & 0xFFFF; break;
+        }
+        u32 f0s = (imm >> 16) & 0xFF, f1s = (imm >> 24) & 0xFF;
+        net_send(H, p, dst_ip, dst_port, src_val(R, P, b), c,
+                 f0s == SRC_NONE ? 0 : src_val(R, P, f0s), f1s == SRC_NONE ? 0 : src_val(R, P, f1s));
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
+    case OP_NODE_SLEEP: {
+        NodeDyn& N = R.node[P.node];
+        N.awake = 0; N.epoch += 1;
+        H->vol[SRC_NODE_EPOCH - 0x10] = N.epoch;
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
+    case OP_NODE_WAKE:
+        node_wake(H, P.node);
+        H->vol[SRC_NODE_EPOCH - 0x10] = R.node[P.node].epoch;
+        P.pc += 1;
+        return XR_CONTINUE;
+    case OP_SPAWN: {
+        int child = proc_spawn(H, imm, P.node, P.r, 0.0);
+        if (child < 0) return XR_STOP;
+        if (a != SRC_NONE) P.r[a & 3] = handle_of(R, (u32)child);
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
+    case OP_THROW: {
+        u32 h = src_val(R, P, a);
+        ev_push_inl(R, H->now, ev_pack(ITSB_EV_THROW, h & 0x3FF, (h >> 16) & 0x3FF, imm));
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
+    case OP_LIST_CLEAR:
+        list_free_all(R, P);
+        P.pc += 1;
+        return XR_CONTINUE;
+    case OP_LIST_PUSH: {
+        u32 n = arena_alloc(R);
+        if (n == NIL32) return XR_STOP;
+        const u32* v = H->vol;
+        ArenaNode A;
+        A.next = NIL32; A.src_ip = v[SRC_PKT_SRC_IP - 0x10]; A.ports = v[SRC_PKT_SRC_PORT - 0x10];
+        A.size = v[SRC_PKT_SIZE - 0x10]; A.tag = v[SRC_PKT_TAG - 0x10];
+        A.f0 = v[SRC_PKT_F0 - 0x10]; A.f1 = v[SRC_PKT_F1 - 0x10]; A.pad = 0;
+        R.arena[n] = A;
+        if (P.list_tail != NIL32) R.arena[P.list_tail].next = n;
+        if (P.list_tail == NIL32) P.list_head = n;
+        P.list_tail = n;
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
+    case OP_LIST_TAKE: {
+        u32 key = src_val(R, P, a);
+        u32 prev = NIL32, n = P.list_head;
+        bool found = false;
+        while (n != NIL32) {
+            const ArenaNode A = R.arena[n];
+            if (A.f0 == key) {
+                H->vol[SRC_ENT_IP - 0x10] = A.src_ip; H->vol[SRC_ENT_PORT - 0x10] = A.ports & 0xFFFF;
+                if (prev == NIL32) P.list_head = A.next;
+                else R.arena[prev].next = A.next;
+                if (P.list_tail == n) P.list_tail = prev;
+                arena_release(R, n);
+                found = true;
+                break;
+            }
+            prev = n; n = A.next;
+        }
+        P.pc = found ? (u16)(P.pc + 1) : (u16)imm;
+        return XR_CONTINUE;
+    }
+    case OP_STAT:
+        stat_add(R, ITSB_TM_USER0 + (imm & 7), 1);
+        P.pc += 1;
+        return XR_CONTINUE;
+    default:
+        fail(H, ITSB_ERR_BAD_OPCODE, P.pc);
+        return XR_STOP;
     }
 }
 
-/* Runs process p from its pc until it blocks or ends. */
-ITSB_FN void run_process(Rep& R, Seed seed, u32 p) {
+/* Pops the head of the process's socket queue (caller checked q_len != 0). */
+ITSB_FN ArenaNode sock_pop(Rep& R, Sock& S) {
+    u32 n = S.q_head;
+    const ArenaNode A = R.arena[n];
+    S.q_head = A.next;
+    if (A.next == NIL32) S.q_tail = NIL32;
+    S.q_len -= 1;
+    arena_release(R, n);
+    stat_add(R, ITSB_TM_PACKETS_RECEIVED, 1);
+    stat_add(R, ITSB_TM_BYTES_RECEIVED, A.size);
+    return A;
+}
+
+/* Runs process p from its pc until it blocks or ends.  Inline: the receive loop heads, waits and branches a daemon
+ * or a query executes per packet; everything else goes through exec_cold. */
+ITSB_FN void run_process(Rep& R, u32 p) {
+    Hdr* H = R.hdr;
     Pcb& P = R.pcb[p];
     P.state = PS_RUNNING;
-    for (u32 steps = 0; ; ++steps) {
-        if (R.hdr->status != 0) return;
+    {   /* node constants of this activation */
+        const itsb_node N = R.m.nodes[P.node];
+        u32* v = H->vol;
+        v[SRC_NODE_ADDR - 0x10] = N.addr; v[SRC_NODE_INDEX - 0x10] = P.node; v[SRC_NODE_HOST - 0x10] = N.host;
+        v[SRC_NODE_EPOCH - 0x10] = R.node[P.node].epoch; v[SRC_NODE_BCAST - 0x10] = R.m.nets[N.net].bcast;
+        v[SRC_SELF - 0x10] = handle_of(R, p); v[SRC_EXC - 0x10] = P.exc; v[SRC_ZERO - 0x10] = 0;
+    }
+    for (;;) {
+        if (H->status != 0) return;
         const u64 ins = R.m.code[P.pc];
         const u32 op = (u32)(ins & 0xFF), a = (u32)((ins >> 8) & 0xFF), b = (u32)((ins >> 16) & 0xFF),
-                  c = (u32)((ins >> 24) & 0xFF), imm = (u32)(ins >> 32);
-        switch (op) {
-        case OP_NOP:
-            P.pc += 1;
-            break;
-        case OP_EXIT:
-            proc_exit(R, p);
-            return;
-        case OP_JMP:
-            P.pc = (u16)imm;
-            break;
-        case OP_LI:
-            P.r[a] = imm; P.pc += 1;
-            break;
-        case OP_MOV:
-            P.r[a] = src_val(R, p, b); P.pc += 1;
-            break;
-        case OP_ADDI:
-            P.r[a] = src_val(R, p, b) + imm; P.pc += 1;
-            break;
-        case OP_JEQ:
-            P.pc = (src_val(R, p, a) == src_val(R, p, b)) ? (u16)imm : (u16)(P.pc + 1);
-            break;
-        case OP_JNE:
-            P.pc = (src_val(R, p, a) != src_val(R, p, b)) ? (u16)imm : (u16)(P.pc + 1);
-            break;
-        case OP_JEQI:
-            P.pc = (src_val(R, p, a) == (imm >> 16)) ? (u16)(imm & 0xFFFF) : (u16)(P.pc + 1);
-            break;
-        case OP_JNEI:
-            P.pc = (src_val(R, p, a) != (imm >> 16)) ? (u16)(imm & 0xFFFF) : (u16)(P.pc + 1);
-            break;
-        case OP_DRAWI:
-            P.r[a] = (u32)(int32_t)(long long)draw_dist(R.hdr, seed, &R.m.dists[imm]);
-            P.pc += 1;
-            break;
-        case OP_DRAW_ADDI: {
-            double v = (double)(int32_t)src_val(R, p, b) + draw_dist(R.hdr, seed, &R.m.dists[imm]);
-            P.r[a] = (u32)(int32_t)(long long)v;
-            P.pc += 1;
-            break;
-        }
-        case OP_ADVANCE:
-        case OP_ADVANCE_C: {
-            double d = (op == OP_ADVANCE) ? draw_dist(R.hdr, seed, &R.m.dists[imm & 0xFFFF]) : R.m.consts[imm & 0xFFFF];
-            if (d < 0.0) { fail(R, ITSB_EXC_NEGATIVE_DELAY, P.pc); return; }
-            P.timer_tok = (u16)(P.timer_tok + 1);
-            int slot = ev_push(R, R.hdr->now + d, ev_pack(ITSB_EV_TIMER, p, P.gen, P.timer_tok));
-            P.timer_ev = slot < 0 ? NIL16 : (u16)slot;
-            P.state = PS_TIMER;
-            return;  /* pc stays on the ADVANCE; the TIMER event moves it on */
-        }
-        case OP_OPEN:
-            if (sock_open(R, p, imm & 0xFFFF) < 0) return;
-            P.pc += 1;
-            break;
-        case OP_CLOSE:
-            sock_close(R, p);
-            P.pc += 1;
-            break;
-        case OP_SEND: {
-            u32 dst_ip, dst_port = imm & 0xFFFF;
-            switch (a) {
-            case DST_BCAST: dst_ip = src_val(R, p, SRC_NODE_BCAST); break;
-            case DST_PKT_SRC: dst_ip = R.pk_src_ip; dst_port = R.pk_src_port; break;
-            case DST_ENT: dst_ip = R.ent_ip; dst_port = R.ent_port; break;
-            case DST_SELF: dst_ip = src_val(R, p, SRC_NODE_ADDR); break;
-            default: dst_ip = P.r[2]; dst_port = P.r[3] & 0xFFFF; break;
-            }
-            u32 f0s = (imm >> 16) & 0xFF, f1s = (imm >> 24) & 0xFF;
-            net_send(R, p, dst_ip, dst_port, src_val(R, p, b), c,
-                     f0s == SRC_NONE ? 0 : src_val(R, p, f0s), f1s == SRC_NONE ? 0 : src_val(R, p, f1s));
-            P.pc += 1;
-            break;
-        }
-        case OP_RECV: {
-            /* while queue.empty(): signal.wait()  (overrides.py:135-138) */
-            if (P.sock == NIL16) { fail(R, ITSB_EXC_SOCKET_CLOSED, P.pc); return; }
-            Sock& S = R.sock[P.sock];
-            if (S.q_len == 0) {
-                waiters_append(R, S.wait_head, S.wait_tail, p, (u16)(WS_SOCK | P.sock));
-                P.state = PS_WAIT;
-                return;
-            }
-            u32 n = S.q_head;
-            const ArenaNode A = R.arena[n];
-            S.q_head = A.next;
-            if (A.next == NIL32) S.q_tail = NIL32;
-            S.q_len -= 1;
-            arena_release(R, n);
-            R.pk_src_ip = A.src_ip; R.pk_src_port = A.ports & 0xFFFF; R.pk_size = A.size;
-            R.pk_tag = A.tag; R.pk_f0 = A.f0; R.pk_f1 = A.f1;
-            stat_add(R, ITSB_TM_PACKETS_RECEIVED, 1);
-            stat_add(R, ITSB_TM_BYTES_RECEIVED, A.size);
-            P.pc += 1;
-            break;
-        }
-        case OP_RECV_FILTER: {
-            if (P.sock == NIL16) { fail(R, ITSB_EXC_SOCKET_CLOSED, P.pc); return; }
+                  imm = (u32)(ins >> 32);
+        if (op == OP_RECV_FILTER) {
+            if (P.sock == NIL16) { fail(H, ITSB_EXC_SOCKET_CLOSED, P.pc); return; }
             NodeDyn& N = R.node[P.node];
             Sock& S = R.sock[P.sock];
             const itsb_filter F = R.m.filters[b];
@@ -1103,7 +1187,7 @@ ITSB_FN void run_process(Rep& R, Seed seed, u32 p) {
                         P.state = PS_WAIT;
                         return;
                     }
-                    P.r[a] = N.epoch;
+                    P.r[a & 3] = N.epoch;
                     P.phase = 1;
                 }
                 if (S.q_len == 0) {               /* socket.recv() */
@@ -1111,119 +1195,58 @@ ITSB_FN void run_process(Rep& R, Seed seed, u32 p) {
                     P.state = PS_WAIT;
                     return;
                 }
-                u32 n = S.q_head;
-                const ArenaNode A = R.arena[n];
-                S.q_head = A.next;
-                if (A.next == NIL32) S.q_tail = NIL32;
-                S.q_len -= 1;
-                arena_release(R, n);
-                stat_add(R, ITSB_TM_PACKETS_RECEIVED, 1);
-                stat_add(R, ITSB_TM_BYTES_RECEIVED, A.size);
+                const ArenaNode A = sock_pop(R, S);
                 P.phase = 0;
-                if (N.epoch != P.r[a]) { P.pc = (u16)(imm & 0xFFFF); break; }      /* FellAsleep */
+                if (N.epoch != P.r[a & 3]) { P.pc = (u16)(imm & 0xFFFF); break; }      /* FellAsleep */
                 if (filter_passes(F, A.tag, A.f0, R.m.nodes[P.node].host, P.list_head != NIL32)) {
-                    R.pk_src_ip = A.src_ip; R.pk_src_port = A.ports & 0xFFFF; R.pk_size = A.size;
-                    R.pk_tag = A.tag; R.pk_f0 = A.f0; R.pk_f1 = A.f1;
+                    set_pkt_regs(R, A);
                     handed = true;
                     break;
                 }
             }
             if (handed) P.pc += 1;
-            break;
-        }
-        case OP_WAIT_AWAKE: {
+        } else if (op == OP_RECV) {
+            /* while queue.empty(): signal.wait()  (overrides.py:135-138) */
+            if (P.sock == NIL16) { fail(H, ITSB_EXC_SOCKET_CLOSED, P.pc); return; }
+            Sock& S = R.sock[P.sock];
+            if (S.q_len == 0) {
+                waiters_append(R, S.wait_head, S.wait_tail, p, (u16)(WS_SOCK | P.sock));
+                P.state = PS_WAIT;
+                return;
+            }
+            const ArenaNode A = sock_pop(R, S);
+            set_pkt_regs(R, A);
+            P.pc += 1;
+        } else if (op == OP_WAIT_AWAKE) {
             NodeDyn& N = R.node[P.node];
             if (!N.awake) {
                 waiters_append(R, N.wake_head, N.wake_tail, p, (u16)(WS_NODE | P.node));
                 P.state = PS_WAIT;
                 return;
             }
-            if (a != SRC_NONE) P.r[a] = N.epoch;
+            if (a != SRC_NONE) P.r[a & 3] = N.epoch;
             P.pc += 1;
-            break;
-        }
-        case OP_JASLEEP:
-            P.pc = (R.node[P.node].epoch != src_val(R, p, a)) ? (u16)imm : (u16)(P.pc + 1);
-            break;
-        case OP_NODE_SLEEP: {
-            NodeDyn& N = R.node[P.node];
-            N.awake = 0; N.epoch += 1;
-            P.pc += 1;
-            break;
-        }
-        case OP_NODE_WAKE: {
-            NodeDyn& N = R.node[P.node];
-            N.awake = 1;
-            waiters_resume_all(R, N.wake_head, N.wake_tail);
-            N.epoch += 1;
-            P.pc += 1;
-            break;
-        }
-        case OP_SPAWN: {
-            int child = proc_spawn(R, imm, P.node, P.r, 0.0);
-            if (child < 0) return;
-            if (a != SRC_NONE) P.r[a] = handle_of(R, (u32)child);
-            P.pc += 1;
-            break;
-        }
-        case OP_THROW: {
-            u32 h = src_val(R, p, a);
-            ev_push(R, R.hdr->now, ev_pack(ITSB_EV_THROW, h & 0x3FF, (h >> 16) & 0x3FF, imm));
-            P.pc += 1;
-            break;
-        }
-        case OP_LIST_CLEAR:
-            list_free_all(R, P);
-            P.pc += 1;
-            break;
-        case OP_LIST_PUSH: {
-            u32 n = arena_alloc(R);
-            if (n == NIL32) return;
-            ArenaNode A;
-            A.next = NIL32; A.src_ip = R.pk_src_ip; A.ports = R.pk_src_port; A.size = R.pk_size;
-            A.tag = R.pk_tag; A.f0 = R.pk_f0; A.f1 = R.pk_f1; A.pad = 0;
-            R.arena[n] = A;
-            if (P.list_tail != NIL32) R.arena[P.list_tail].next = n;
-            if (P.list_tail == NIL32) P.list_head = n;
-            P.list_tail = n;
-            P.pc += 1;
-            break;
-        }
-        case OP_LIST_TAKE: {
-            u32 key = src_val(R, p, a);
-            u32 prev = NIL32, n = P.list_head;
-            bool found = false;
-            while (n != NIL32) {
-                const ArenaNode A = R.arena[n];
-                if (A.f0 == key) {
-                    R.ent_ip = A.src_ip; R.ent_port = A.ports & 0xFFFF;
-                    if (prev == NIL32) P.list_head = A.next;
-                    else R.arena[prev].next = A.next;
-                    if (P.list_tail == n) P.list_tail = prev;
-                    arena_release(R, n);
-                    found = true;
-                    break;
-                }
-                prev = n; n = A.next;
-            }
-            P.pc = found ? (u16)(P.pc + 1) : (u16)imm;
-            break;
-        }
-        case OP_STAT:
-            stat_add(R, ITSB_TM_USER0 + (imm & 7), 1);
-            P.pc += 1;
-            break;
-        default:
-            fail(R, ITSB_ERR_BAD_OPCODE, P.pc);
-            return;
+        } else if (op == OP_JMP) {
+            P.pc = (u16)imm;
+        } else if (op == OP_JEQI || op == OP_JNEI) {
+            const bool eq = src_val(R, P, a) == (imm >> 16);
+            P.pc = (eq == (op == OP_JEQI)) ? (u16)(imm & 0xFFFF) : (u16)(P.pc + 1);
+        } else if (op == OP_JEQ || op == OP_JNE) {
+            const bool eq = src_val(R, P, a) == src_val(R, P, b);
+            P.pc = (eq == (op == OP_JEQ)) ? (u16)imm : (u16)(P.pc + 1);
+        } else if (op == OP_JASLEEP) {
+            P.pc = (R.node[P.node].epoch != src_val(R, P, a)) ? (u16)imm : (u16)(P.pc + 1);
+        } else {
+            if (exec_cold(H, p, ins) != XR_CONTINUE) return;
         }
     }
 }
 
 /* An exception arrives at a blocked process (greenlet.throw): leave whatever it was parked in, then run its handler.
  * greensim would leave a "ghost" wake-up / queue entry for non-Interrupt exceptions; ghosts are no-ops, so the
- * engine removes them instead (same model-visible order). */
-ITSB_FN u32 deliver_exception(Rep& R, u32 p, u32 exc) {
+ * engine removes them instead (same model-visible order).  Returns the process to run, or NIL32. */
+ITSB_COLD u32 deliver_exception(Hdr* H, u32 p, u32 exc) {
+    Rep R; rebind(R, H);
     Pcb& P = R.pcb[p];
     if (P.state == PS_TIMER) {
         /* advance() interrupted: its wake-up is cancelled (pool) or left to expire as a dead hop (queue / overflow) */
@@ -1235,20 +1258,29 @@ ITSB_FN u32 deliver_exception(Rep& R, u32 p, u32 exc) {
         else if (P.wsig & WS_SOCK) { Sock& S = R.sock[P.wsig & 0x3FFF]; waiters_unlink(R, S.wait_head, S.wait_tail, p); }
     }
     P.exc = (u16)exc;
+    P.phase = 0;
     const u64 ins = R.m.code[P.pc];
     u32 handler = (u32)(ins >> 48);
     if (handler == 0) {
-        if (!(exc & EXC_INTERRUPT_CLASS)) { fail(R, ITSB_EXC_UNCAUGHT, ((u64)exc << 32) | P.pc); return NIL32; }
+        if (!(exc & EXC_INTERRUPT_CLASS)) { fail(H, ITSB_EXC_UNCAUGHT, ((u64)exc << 32) | P.pc); return NIL32; }
         handler = 0;    /* code[0..1] = CLOSE; EXIT -- an uncaught Interrupt ends the process silently */
     }
     P.pc = (u16)handler;
     return p;
 }
 
-/* Simulator.run(duration): pops (t, seq)-ordered events until the stop event. */
-ITSB_FN void run_replica(Rep& R, Seed seed, double duration) {
+ITSB_FN u64 events_counted(Rep& R) {
+    u64 n = 0;
+    for (u32 k = 0; k < ITSB_NUM_KINDS; ++k) n += R.stats[ITSB_TM_KIND0 + k];
+    return n;
+}
+
+/* Simulator.run(duration): pops (t, seq)-ordered events until the stop event.  Returns the number
+ * of simulated events this call processed. */
+ITSB_FN u64 run_replica(Rep& R, double duration) {
     Hdr* H = R.hdr;
-    if (H->status != 0) return;
+    if (H->status != 0) return 0;
+    const u64 events_before = events_counted(R);
     const double t_stop = H->now + duration;
     const u64 t_stop_bits = dbits(t_stop);
     const u32 stop_seq = H->seq;
@@ -1263,58 +1295,62 @@ ITSB_FN void run_replica(Rep& R, Seed seed, double duration) {
             count_event(R, ITSB_EV_STOP, 0, 0, 0);
             break;
         }
-        u32 slot;
-        const u32 data = ev_take(R, src, slot);
+        const u32 data = ev_take(R, src);
         H->now = bitsd(tb);
         const u32 kind = ev_kind(data), idx = ev_idx(data);
         u32 runnable = NIL32;
-        switch (kind) {
-        case ITSB_EV_TX_BEGIN: on_tx_begin(R, seed, ev_pkt(data)); break;
-        case ITSB_EV_TX_END: on_tx_end(R, ev_pkt(data)); break;
-        case ITSB_EV_DELIVER: on_deliver(R, ev_pkt(data)); break;
-        case ITSB_EV_PROC_START:
-        case ITSB_EV_TIMER:
-        case ITSB_EV_WAKE: {
+        if (kind == ITSB_EV_DELIVER) {
+            on_deliver(R, ev_pkt(data));
+        } else if (kind == ITSB_EV_WAKE || kind == ITSB_EV_TIMER || kind == ITSB_EV_PROC_START) {
             Pcb& P = R.pcb[idx];
-            if (P.state == PS_FREE || P.gen != ev_gen(data)) break;   /* ghost hop: target finished */
-            if (kind == ITSB_EV_TIMER) {
-                if (P.state != PS_TIMER || (u32)(P.timer_tok & 0xFF) != ev_exc(data)) break;
-                P.timer_ev = NIL16;
-                P.pc += 1;
-            } else if (kind == ITSB_EV_WAKE) {
-                if (P.state != PS_RESUMING) break;
-            } else if (P.state != PS_UNSTARTED) break;
-            count_event(R, kind, P.prog, P.node, 0);
-            runnable = idx;
-            break;
-        }
-        case ITSB_EV_THROW: {
+            bool live = P.state != PS_FREE && P.gen == ev_gen(data);   /* else a ghost hop: target finished */
+            if (live) {
+                if (kind == ITSB_EV_TIMER) {
+                    live = P.state == PS_TIMER && (u32)(P.timer_tok & 0xFF) == ev_exc(data);
+                    if (live) { P.timer_ev = NIL16; P.pc += 1; }
+                } else if (kind == ITSB_EV_WAKE) {
+                    live = P.state == PS_RESUMING;
+                } else {
+                    live = P.state == PS_UNSTARTED;
+                }
+            }
+            if (live) {
+                count_event(R, kind, P.prog, P.node, 0);
+                runnable = idx;
+            }
+        } else if (kind == ITSB_EV_TX_BEGIN) {
+            on_tx_begin(H, ev_pkt(data));
+        } else if (kind == ITSB_EV_TX_END) {
+            on_tx_end(H, ev_pkt(data));
+        } else if (kind == ITSB_EV_THROW) {
             Pcb& P = R.pcb[idx];
-            if (P.state == PS_FREE || P.gen != ev_gen(data)) break;   /* ghost hop */
-            count_event(R, ITSB_EV_THROW, P.prog, P.node, ev_exc(data));
-            if (P.state == PS_UNSTARTED) { proc_exit(R, idx); break; }  /* never ran: dies on the spot */
-            runnable = deliver_exception(R, idx, ev_exc(data));
-            break;
+            if (P.state != PS_FREE && P.gen == ev_gen(data)) {
+                count_event(R, ITSB_EV_THROW, P.prog, P.node, ev_exc(data));
+                if (P.state == PS_UNSTARTED) proc_exit(H, idx);   /* never ran: dies on the spot */
+                else runnable = deliver_exception(H, idx, ev_exc(data));
+            }
+        } else {
+            fail(H, ITSB_ERR_BAD_OPCODE, data);
         }
-        default:
-            fail(R, ITSB_ERR_BAD_OPCODE, data);
-        }
-        if (runnable != NIL32) run_process(R, seed, runnable);   /* the interpreter's only call site */
+        if (runnable != NIL32) run_process(R, runnable);   /* the interpreter's only call site */
     }
+    return events_counted(R) - events_before;
 }
 
 /* Builds the t = 0 state of a replica: empty tables, free lists, and the model's installed processes in
- * installation order (Endpoint.install -> sim.add, overrides.py:423-424; network_simple.py:366-385). */
+ * installation order (Endpoint.install -> sim.add, overrides.py:423-424; network_simple.py:366-385).  The header's
+ * binding fields must already be staged (bind_views). */
 ITSB_FN void init_replica(Rep& R, u64 replica_id) {
-    const Layout* L = &R.L;
     Hdr* H = R.hdr;
+    const Layout* L = &H->L;
     H->now = 0.0; H->draws = 0; H->seq = 0; H->status = 0; H->detail = 0;
     H->trace_count = 0;
     H->replica_lo = (u32)replica_id; H->replica_hi = (u32)(replica_id >> 32);
     H->nq_head = 0; H->nq_tail = 0; H->nq_spill_head = NIL32; H->nq_spill_tail = NIL32; H->nq_spill_count = 0;
     H->pmin_valid = 0; H->pmin_idx = NIL32; H->pmin_seq = NIL32; H->pmin_t = T_EMPTY;
     H->ovf_min_t = T_EMPTY; H->ovf_min_seq = NIL32; H->ovf_head = NIL32; H->ovf_count = 0;
-    for (u32 i = 0; i < 5; ++i) H->pad[i] = 0;
+    H->spare16 = 0; H->spare32 = 0;
+    for (u32 i = 0; i < VOL_COUNT; ++i) H->vol[i] = 0;
     for (u32 i = 0; i < 2 * NQ_CAP; ++i) R.nq[i] = 0;
     for (u32 i = 0; i < L->max_ev; ++i) { R.ev_t[i] = T_EMPTY; R.ev_seq[i] = 0; R.ev_data[i] = 0; R.ev_free[i] = (u16)(L->max_ev - 1 - i); }
     H->ev_free_top = (u16)L->max_ev;
@@ -1322,7 +1358,6 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
     H->pcb_free_top = (u16)L->max_proc;
     for (u32 i = 0; i < L->max_sock; ++i) { memset(&R.sock[i], 0, sizeof(Sock)); R.sock_free[i] = (u16)(L->max_sock - 1 - i); }
     H->sock_free_top = (u16)L->max_sock;
-    H->pkt_free_top = 0;
     for (u32 i = 0; i < L->n_nodes; ++i) {
         NodeDyn& N = R.node[i];
         N.sock_head = NIL16; N.port_cursor = 1024; N.wake_head = NIL16; N.wake_tail = NIL16; N.epoch = 0; N.awake = 0;
@@ -1331,7 +1366,7 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
     H->arena_free_top = L->arena_nodes;
     for (u32 i = 0; i < R.m.n_init; ++i) {
         const itsb_initproc I = R.m.init[i];
-        proc_spawn(R, I.entry, I.node, I.r, 0.0);
+        proc_spawn(H, I.entry, I.node, I.r, 0.0);
     }
 }
 

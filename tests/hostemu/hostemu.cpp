@@ -64,11 +64,9 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
 }
 
 static void bind(itsb_engine* e, Rep& R, uint64_t r) {
-    bind_views(R, e->hot.data() + r * e->layout.hot_bytes, &e->layout);
-    R.m = e->model;
-    R.arena = e->arena.data() + r * e->layout.arena_nodes;
-    R.arena_free = e->arena_free.data() + r * e->layout.arena_nodes;
-    R.trace = e->layout.trace_cap ? e->trace.data() + r * e->layout.trace_cap : nullptr;
+    bind_views(R, e->hot.data() + r * e->layout.hot_bytes, &e->layout, &e->model,
+               e->arena.data() + r * e->layout.arena_nodes, e->arena_free.data() + r * e->layout.arena_nodes,
+               e->layout.trace_cap ? e->trace.data() + r * e->layout.trace_cap : nullptr, e->seed);
 }
 
 int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first) {
@@ -88,11 +86,9 @@ int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first
 
 int itsb_run_async(itsb_engine* e, double duration) {
     if (!e->n_replicas) return ITSB_ERR_STATE;
-    Seed seed = {(uint32_t)e->seed, (uint32_t)(e->seed >> 32)};
     for (uint64_t r = 0; r < e->n_replicas; ++r) {
         Rep R; bind(e, R, r);
-        run_replica(R, seed, duration);
-        e->last_events += R.events;
+        e->last_events += run_replica(R, duration);
     }
     e->launches += 1;
     return ITSB_OK;
