@@ -31,6 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "simulated events/sec (batched network_simple replicas)"
+# ncu --set full capture committed under profiles/: (dram__bytes_read.sum + dram__bytes_write.sum) / replicas
+NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH = (333.9e6 + 168.9e6) / 6000.0
 UNIT = "events/s"
 
 
@@ -320,7 +322,9 @@ def main() -> None:
             "gpu_launches": launches_dev,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "k_run",
+                "traffic": NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH * args.replicas, "peak_source": peak_src, "kernel": "k_run",
+                "traffic_note": "dram__bytes_read+write of one k_run launch from profiles/r1_k_run_ncu_full.txt "
+                                "(6000 replicas x 60 simulated s: 5.03e8 B vs 2.30e8 B algorithmic), scaled per replica",
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "note": "algorithmic bytes = per-replica state staged HBM->smem->HBM once per run (S_in+S_out); the "
                         "kernel is bound by the serial pop->handle->push chain in shared memory, not by HBM",
