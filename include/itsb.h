@@ -35,6 +35,7 @@ extern "C" {
 #define ITSB_ERR_CAP_PACKETS      -13  /* reserved                                                            */
 #define ITSB_ERR_CAP_ARENA        -14  /* per-replica queue arena (HBM) exhausted                             */
 #define ITSB_ERR_BAD_OPCODE       -15
+#define ITSB_ERR_CAP_THREADS      -16  /* Thread / Process / Signal table exhausted                             */
 #define ITSB_ERR_NCCL             -20
 
 /* ---- model-level exceptions of the reference (positive) ------------------------------------------------------ */
@@ -56,6 +57,7 @@ extern "C" {
 #define ITSB_EV_THROW      7
 #define ITSB_EV_STOP       8
 #define ITSB_NUM_KINDS     9
+#define ITSB_TRACE_MARK    9   /* trace-only record (not an event): a model side effect declared with the MARK op */
 
 typedef struct itsb_trace_rec {   /* 16 bytes, little endian; same layout as oracle/evtrace.py TRACE_DTYPE */
     double   t;
@@ -102,7 +104,9 @@ typedef struct itsb_dist {        /* one variate generator chain (itsim/random.p
 typedef struct itsb_net {         /* one broadcast domain: override Network (overrides.py:189-291) or Link        */
     uint32_t cidr_net, cidr_mask; /* network address and netmask                                                 */
     uint32_t bcast;               /* broadcast address                                                           */
-    uint32_t first_node, n_nodes; /* members = node indices [first_node, first_node + n_nodes), in link order     */
+    uint32_t first_node, n_nodes; /* ITSB_NET_OVERRIDE: members = node indices [first_node, first_node + n_nodes), in
+                                     link order; ITSB_NET_LINK: members = members[first_node .. first_node + n_nodes),
+                                     in connection order                                                          */
     uint32_t lat_dist, bw_dist;   /* indices into the distribution table (already bounded as the reference does)  */
     uint32_t mode;                /* ITSB_NET_OVERRIDE: TX process, delay = lat + len/bw ; ITSB_NET_LINK: draw at
                                      send, delay = lat + 8*len/bw (itsim/network/link.py:82-86)                  */
@@ -114,18 +118,40 @@ typedef struct itsb_node {        /* static part of a node                      
     uint32_t addr;                /* IPv4 address on its network                                                  */
     uint32_t net;                 /* index into nets                                                              */
     uint32_t host;                /* hostname id (payload field f0 compares against it)                           */
-    uint32_t flags;
+    uint32_t flags;               /* shipped-itsim nodes: first interface | number of interfaces << 16            */
 } itsb_node;
+
+typedef struct itsb_iface {       /* Interface(link, address, routes) (itsim/network/interface.py:22-68); a node's
+                                     interfaces are consecutive, loopback first (itsim/machine/node.py:74-77)      */
+    uint32_t node, net;
+    uint32_t addr0;               /* address at t = 0 (DHCP may change it at run time)                            */
+    uint32_t first_route, n_routes; /* [Local(link.cidr)] + routes, in the order _solve_transfer scans them        */
+    uint32_t reserved[3];
+} itsb_iface;
+
+typedef struct itsb_route {       /* Local / Relay (itsim/network/route.py:8-59)                                  */
+    uint32_t net, mask, prefixlen;
+    uint32_t kind;                /* ITSB_ROUTE_LOCAL: hop = destination; ITSB_ROUTE_RELAY: hop = gateway          */
+    uint32_t gateway;
+    uint32_t reserved[3];
+} itsb_route;
+#define ITSB_ROUTE_LOCAL 0
+#define ITSB_ROUTE_RELAY 1
 
 typedef struct itsb_entry {       /* program entry point                                                          */
     uint32_t pc;                  /* first instruction                                                            */
     uint32_t prog;                /* program id reported in trace records                                         */
 } itsb_entry;
 
-typedef struct itsb_initproc {    /* process installed at t=0, in installation order (Endpoint.install)           */
+typedef struct itsb_initproc {    /* process started at t=0, in program order                                     */
     uint32_t entry, node;
     uint32_t r[4];
+    uint32_t mode;                /* ITSB_INIT_ADD: sim.add(body) (Endpoint.install, overrides.py:423-424);
+                                     ITSB_INIT_RUN_PROC: Node.run_proc_in(sim, delay, body) (node.py:279-283)      */
+    uint32_t delay_const;         /* index of the delay in consts (ITSB_INIT_RUN_PROC)                            */
 } itsb_initproc;
+#define ITSB_INIT_ADD      0
+#define ITSB_INIT_RUN_PROC 1
 
 typedef struct itsb_filter {      /* which received packets a RECV_FILTER loop hands to its program; the rest it
                                      consumes and loops (the daemon bodies' "not for me" branches,
@@ -141,11 +167,13 @@ typedef struct itsb_caps {        /* per-replica capacities; exceeding one flags
     uint32_t max_packets;         /* reserved: packets in flight are arena nodes                                  */
     uint32_t arena_nodes;         /* 32-byte nodes in HBM: socket queues, remembered packets, packets in flight   */
     uint32_t trace_records;       /* per-replica trace capacity (0 = tracing off)                                 */
+    uint32_t max_threads, max_tasks, max_signals;   /* shipped-itsim Thread / Process / Signal tables (0 = none)  */
 } itsb_caps;
 
 typedef struct itsb_model_desc {
     uint32_t abi_version;
     uint32_t n_code, n_entries, n_dists, n_consts, n_nets, n_nodes, n_init, n_filters;
+    uint32_t n_ifaces, n_routes, n_members;
     itsb_caps caps;
 } itsb_model_desc;
 
@@ -158,7 +186,10 @@ typedef struct itsb_model_desc {
 #define ITSB_BLOB_NODES   5   /* itsb_node[n_nodes]                                                               */
 #define ITSB_BLOB_INIT    6   /* itsb_initproc[n_init]                                                            */
 #define ITSB_BLOB_FILTERS 7   /* itsb_filter[n_filters]                                                           */
-#define ITSB_NUM_BLOBS    8
+#define ITSB_BLOB_IFACES  8   /* itsb_iface[n_ifaces]                                                             */
+#define ITSB_BLOB_ROUTES  9   /* itsb_route[n_routes]                                                             */
+#define ITSB_BLOB_MEMBERS 10  /* uint32[n_members] node indices of ITSB_NET_LINK networks                         */
+#define ITSB_NUM_BLOBS    11
 
 typedef struct itsb_engine itsb_engine;
 

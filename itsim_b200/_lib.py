@@ -20,12 +20,14 @@ TM_DELIVERED, TM_DROPPED, TM_USER0, TM_LAT0, LAT_BINS = 13, 14, 15, 23, 64
 TM_SIZE = TM_LAT0 + LAT_BINS
 NUM_KINDS = 9
 EV_PROC_START, EV_TIMER, EV_TX_BEGIN, EV_TX_END, EV_DELIVER, EV_WAKE, EV_THROW, EV_STOP = range(1, 9)
+TRACE_MARK = 9
 KIND_NAMES = {1: "PROC_START", 2: "TIMER", 3: "TX_BEGIN", 4: "TX_END", 5: "DELIVER", 6: "WAKE", 7: "THROW", 8: "STOP"}
 
 ERRORS = {
     -1: "no CUDA device (the engine has no CPU fallback)", -2: "bad model", -3: "CUDA error", -4: "bad call order",
     -10: "event pool exhausted", -11: "process slots exhausted", -12: "socket slots exhausted",
-    -13: "in-flight packet slots exhausted", -14: "queue arena exhausted", -15: "bad opcode", -20: "NCCL error",
+    -13: "in-flight packet slots exhausted", -14: "queue arena exhausted", -15: "bad opcode",
+    -16: "thread / process / signal table exhausted", -20: "NCCL error",
     1: "NoSuchAddress / CannotForward", 2: "NoRouteToHost", 3: "PortAlreadyInUse", 4: "EphemeralPortsAllInUse",
     5: "ValueError: Socket is closed", 6: "ValueError: negative delay", 7: "uncaught exception in a process body",
 }
@@ -37,21 +39,28 @@ NET_DTYPE = np.dtype([("cidr_net", "<u4"), ("cidr_mask", "<u4"), ("bcast", "<u4"
                       ("n_nodes", "<u4"), ("lat_dist", "<u4"), ("bw_dist", "<u4"), ("mode", "<u4")])
 NODE_DTYPE = np.dtype([("addr", "<u4"), ("net", "<u4"), ("host", "<u4"), ("flags", "<u4")])
 ENTRY_DTYPE = np.dtype([("pc", "<u4"), ("prog", "<u4")])
-INIT_DTYPE = np.dtype([("entry", "<u4"), ("node", "<u4"), ("r", "<u4", (4,))])
+INIT_DTYPE = np.dtype([("entry", "<u4"), ("node", "<u4"), ("r", "<u4", (4,)), ("mode", "<u4"), ("delay_const", "<u4")])
+IFACE_DTYPE = np.dtype([("node", "<u4"), ("net", "<u4"), ("addr0", "<u4"), ("first_route", "<u4"), ("n_routes", "<u4"),
+                        ("reserved", "<u4", (3,))])
+ROUTE_DTYPE = np.dtype([("net", "<u4"), ("mask", "<u4"), ("prefixlen", "<u4"), ("kind", "<u4"), ("gateway", "<u4"),
+                        ("reserved", "<u4", (3,))])
 FILTER_DTYPE = np.dtype([("tags_always", "<u4"), ("tags_if_host", "<u4"), ("tags_if_list", "<u4"), ("reserved", "<u4")])
 assert TRACE_DTYPE.itemsize == 16 and DIST_DTYPE.itemsize == 56 and NET_DTYPE.itemsize == 32
-assert NODE_DTYPE.itemsize == 16 and ENTRY_DTYPE.itemsize == 8 and INIT_DTYPE.itemsize == 24
+assert NODE_DTYPE.itemsize == 16 and ENTRY_DTYPE.itemsize == 8 and INIT_DTYPE.itemsize == 32
+assert IFACE_DTYPE.itemsize == 32 and ROUTE_DTYPE.itemsize == 32
 
 
 class Caps(C.Structure):
     _fields_ = [("max_events", C.c_uint32), ("max_procs", C.c_uint32), ("max_sockets", C.c_uint32),
-                ("max_packets", C.c_uint32), ("arena_nodes", C.c_uint32), ("trace_records", C.c_uint32)]
+                ("max_packets", C.c_uint32), ("arena_nodes", C.c_uint32), ("trace_records", C.c_uint32),
+                ("max_threads", C.c_uint32), ("max_tasks", C.c_uint32), ("max_signals", C.c_uint32)]
 
 
 class ModelDesc(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("n_code", C.c_uint32), ("n_entries", C.c_uint32),
                 ("n_dists", C.c_uint32), ("n_consts", C.c_uint32), ("n_nets", C.c_uint32), ("n_nodes", C.c_uint32),
-                ("n_init", C.c_uint32), ("n_filters", C.c_uint32), ("caps", Caps)]
+                ("n_init", C.c_uint32), ("n_filters", C.c_uint32), ("n_ifaces", C.c_uint32), ("n_routes", C.c_uint32),
+                ("n_members", C.c_uint32), ("caps", Caps)]
 
 
 class EngineError(RuntimeError):

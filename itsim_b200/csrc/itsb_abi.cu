@@ -73,18 +73,21 @@ struct RunParams {
     uint32_t warps_per_cta;
 };
 
-struct StaticOffsets { uint32_t code, entries, dists, consts, nets, nodes, filters, total; };
+struct StaticOffsets { uint32_t total; };
 
 static inline StaticOffsets static_offsets(const itsb_model_desc& d) {
     StaticOffsets o;
     uint32_t off = align_up((uint32_t)sizeof(Model), 16);
-    o.code = off;    off = align_up(off + 8 * d.n_code, 16);
-    o.entries = off; off = align_up(off + (uint32_t)sizeof(itsb_entry) * d.n_entries, 16);
-    o.dists = off;   off = align_up(off + (uint32_t)sizeof(itsb_dist) * d.n_dists, 16);
-    o.consts = off;  off = align_up(off + 8 * d.n_consts, 16);
-    o.nets = off;    off = align_up(off + (uint32_t)sizeof(itsb_net) * d.n_nets, 16);
-    o.nodes = off;   off = align_up(off + (uint32_t)sizeof(itsb_node) * d.n_nodes, 16);
-    o.filters = off; off = align_up(off + (uint32_t)sizeof(itsb_filter) * d.n_filters, 16);
+    off = align_up(off + 8 * d.n_code, 16);
+    off = align_up(off + (uint32_t)sizeof(itsb_entry) * d.n_entries, 16);
+    off = align_up(off + (uint32_t)sizeof(itsb_dist) * d.n_dists, 16);
+    off = align_up(off + 8 * d.n_consts, 16);
+    off = align_up(off + (uint32_t)sizeof(itsb_net) * d.n_nets, 16);
+    off = align_up(off + (uint32_t)sizeof(itsb_node) * d.n_nodes, 16);
+    off = align_up(off + (uint32_t)sizeof(itsb_filter) * d.n_filters, 16);
+    off = align_up(off + (uint32_t)sizeof(itsb_iface) * d.n_ifaces, 16);
+    off = align_up(off + (uint32_t)sizeof(itsb_route) * d.n_routes, 16);
+    off = align_up(off + 4 * d.n_members, 16);
     o.total = align_up(off, 128);
     return o;
 }
@@ -108,7 +111,10 @@ __device__ __forceinline__ const Model* stage_model(const Model& g, unsigned cha
     cta_copy(sm + off, g.consts, 8 * g.n_consts);             m.consts = (const double*)(sm + off);      off = (off + 8 * g.n_consts + 15) & ~15u;
     cta_copy(sm + off, g.nets, 32 * g.n_nets);                m.nets = (const itsb_net*)(sm + off);      off = (off + 32 * g.n_nets + 15) & ~15u;
     cta_copy(sm + off, g.nodes, 16 * g.n_nodes);              m.nodes = (const itsb_node*)(sm + off);    off = (off + 16 * g.n_nodes + 15) & ~15u;
-    cta_copy(sm + off, g.filters, 16 * g.n_filters);          m.filters = (const itsb_filter*)(sm + off);
+    cta_copy(sm + off, g.filters, 16 * g.n_filters);          m.filters = (const itsb_filter*)(sm + off); off = (off + 16 * g.n_filters + 15) & ~15u;
+    cta_copy(sm + off, g.ifaces, 32 * g.n_ifaces);            m.ifaces = (const itsb_iface*)(sm + off);   off = (off + 32 * g.n_ifaces + 15) & ~15u;
+    cta_copy(sm + off, g.routes, 32 * g.n_routes);            m.routes = (const itsb_route*)(sm + off);   off = (off + 32 * g.n_routes + 15) & ~15u;
+    cta_copy(sm + off, g.members, 4 * g.n_members);           m.members = (const u32*)(sm + off);
     if (threadIdx.x == 0) *(Model*)sm = m;
     __syncthreads();
     return (const Model*)sm;
@@ -293,6 +299,10 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     m.nodes = (const itsb_node*)e->d_tables[ITSB_BLOB_NODES];
     m.init = (const itsb_initproc*)e->d_tables[ITSB_BLOB_INIT];
     m.filters = (const itsb_filter*)e->d_tables[ITSB_BLOB_FILTERS];
+    m.ifaces = (const itsb_iface*)e->d_tables[ITSB_BLOB_IFACES];
+    m.routes = (const itsb_route*)e->d_tables[ITSB_BLOB_ROUTES];
+    m.members = (const u32*)e->d_tables[ITSB_BLOB_MEMBERS];
+    m.n_ifaces = d->n_ifaces; m.n_routes = d->n_routes; m.n_members = d->n_members;
     m.n_code = d->n_code; m.n_entries = d->n_entries; m.n_dists = d->n_dists; m.n_consts = d->n_consts;
     m.n_nets = d->n_nets; m.n_nodes = d->n_nodes; m.n_init = d->n_init; m.n_filters = d->n_filters;
     if (!e->d_model) CU(e, cudaMalloc(&e->d_model, sizeof(Model)));

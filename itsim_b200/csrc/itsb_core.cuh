@@ -117,7 +117,49 @@ struct Pcb {                /* 48 bytes: one greensim process */
 };
 
 enum { PS_FREE = 0, PS_UNSTARTED = 1, PS_RUNNING = 2, PS_TIMER = 3, PS_WAIT = 4, PS_RESUMING = 5 };
-enum { WS_NONE = 0, WS_SOCK = 0x4000, WS_NODE = 0x8000 };
+enum { WS_NONE = 0, WS_SOCK = 0x4000, WS_NODE = 0x8000, WS_SIG = 0xC000 };
+
+/* -- tables of the shipped-itsim primitives (present only when the model asks for them) -- */
+struct PcbX {               /* 40 bytes: extension of a process control block */
+    u16 thread;             /* the itsim Thread this computation belongs to (NIL16: a plain greensim process) */
+    u16 tnext;              /* next computation of the same thread */
+    u32 balker_h;           /* handle of the Queue.join timeout helper, while parked in a timed wait */
+    u32 sel_common;         /* select(): the private signal and the two helper processes */
+    u32 sel_h1, sel_h2;
+    u32 x[4];               /* x[0:2] = f64 delay the computation was started with, x[2:4] = f64 scratch */
+    u32 pad;
+};
+
+struct Sig {                /* 8 bytes: greensim.Signal */
+    u16 head, tail;         /* waiters, FIFO */
+    u16 on;
+    u16 gen;
+};
+
+struct Thr {                /* 20 bytes: itsim Thread */
+    u16 task;
+    u16 ncomp;
+    u16 comp_head, comp_tail;
+    u16 dead_sig;
+    u16 gen;
+    u16 next;               /* next thread of the same process */
+    u16 n;
+    u16 live;
+    u16 pad;
+};
+
+struct Task {               /* 24 bytes: itsim Process */
+    u16 pid;
+    u16 node;
+    u32 parent;
+    u16 nthreads;
+    u16 thread_counter;
+    u16 thr_head, thr_tail;
+    u16 dead_sig;
+    u16 gen;
+    u16 live;
+    u16 pad;
+};
 
 struct Sock {               /* 24 bytes */
     u16 port;
@@ -168,6 +210,9 @@ struct Layout {             /* byte offsets inside one replica's hot block */
     u32 off_pcb, off_pcb_free, off_sock, off_sock_free, off_node, off_stats;
     u32 max_ev, max_proc, max_sock, n_nodes;
     u32 arena_nodes, trace_cap;
+    /* shipped-itsim tables (all zero when the model does not use them) */
+    u32 off_iface, off_pcbx, off_sig, off_sig_free, off_thr, off_thr_free, off_task, off_task_free;
+    u32 n_ifaces, max_sig, max_thr, max_task;
 };
 
 struct Model {              /* pointers to the static tables (shared-memory copies inside the kernel) */
@@ -179,11 +224,14 @@ struct Model {              /* pointers to the static tables (shared-memory copi
     const itsb_node* nodes;
     const itsb_initproc* init;
     const itsb_filter* filters;
-    u32 n_code, n_entries, n_dists, n_consts, n_nets, n_nodes, n_init, n_filters;
+    const itsb_iface* ifaces;
+    const itsb_route* routes;
+    const u32* members;
+    u32 n_code, n_entries, n_dists, n_consts, n_nets, n_nodes, n_init, n_filters, n_ifaces, n_routes, n_members;
 };
 
 /* interpreter scratch registers, valid inside one activation of a process; index = operand source - 0x10 */
-enum { VOL_COUNT = 40 };
+enum { VOL_COUNT = 42 };
 
 struct Hdr {                /* first thing in the hot block */
     /* -- persistent state -- */
@@ -203,6 +251,8 @@ struct Hdr {                /* first thing in the hot block */
     u64 ovf_min_t;
     u32 ovf_min_seq, ovf_head, ovf_count;
     u32 spare32;
+    u16 sig_free_top, thr_free_top, task_free_top, spare16b;
+    u32 hidden_entry_balk, hidden_entry_wait_one;   /* entry indices of greensim's helper programs */
     /* -- binding: rewritten every time the replica is staged (pointers of this launch, not state) -- */
     ArenaNode* arena;
     u32* arena_free;
@@ -231,6 +281,14 @@ struct Rep {                /* register-resident working view of one replica */
     itsb_trace_rec* trace;
     Model m;
     u32 max_ev, trace_cap;
+    u32* iface_addr;        /* shipped-itsim tables */
+    PcbX* pcbx;
+    Sig* sig;
+    u16* sig_free;
+    Thr* thr;
+    u16* thr_free;
+    Task* task;
+    u16* task_free;
 };
 
 /* Rebuilds the working view from the header alone (used on entry by every out-of-line function; unused fields are
@@ -255,6 +313,14 @@ ITSB_FN void rebind(Rep& R, Hdr* H) {
     R.m = *H->model;
     R.max_ev = H->L.max_ev;
     R.trace_cap = H->L.trace_cap;
+    R.iface_addr = (u32*)(hot + H->L.off_iface);
+    R.pcbx = (PcbX*)(hot + H->L.off_pcbx);
+    R.sig = (Sig*)(hot + H->L.off_sig);
+    R.sig_free = (u16*)(hot + H->L.off_sig_free);
+    R.thr = (Thr*)(hot + H->L.off_thr);
+    R.thr_free = (u16*)(hot + H->L.off_thr_free);
+    R.task = (Task*)(hot + H->L.off_task);
+    R.task_free = (u16*)(hot + H->L.off_task_free);
 }
 
 /* Stages the launch's pointers into the header, then builds the view. */
@@ -632,6 +698,11 @@ ITSB_COLD int proc_spawn(Hdr* H, u32 entry, u32 node, const u32* regs, double de
     P.wnext = NIL16; P.wprev = NIL16; P.wsig = WS_NONE; P.timer_ev = NIL16; P.sock = NIL16; P.exc = 0;
     P.list_head = NIL32; P.list_tail = NIL32; P.phase = 0;
     P.r[0] = r0; P.r[1] = r1; P.r[2] = r2; P.r[3] = r3;
+    if (H->L.max_sig != 0) {
+        PcbX& X = R.pcbx[p];
+        X.thread = NIL16; X.tnext = NIL16; X.balker_h = NIL32; X.sel_common = NIL16; X.sel_h1 = NIL32; X.sel_h2 = NIL32;
+        X.x[0] = 0; X.x[1] = 0; X.x[2] = 0; X.x[3] = 0; X.pad = 0;
+    }
     ev_push_inl(R, H->now + delay, ev_pack(ITSB_EV_PROC_START, p, P.gen, 0));
     return (int)p;
 }
@@ -839,6 +910,8 @@ ITSB_COLD void on_tx_end(Hdr* H, u32 k) {
     H->seq += count - 1;
 }
 
+ITSB_COLD void m_deliver(Hdr* H, u32 k);   /* Link-mode delivery, itsb_machine.cuh */
+
 ITSB_FN bool filter_passes(const itsb_filter F, u32 tag, u32 f0, u32 host, bool list_nonempty) {
     const u32 bit = 1u << (tag & 31);
     return (F.tags_always & bit) != 0 || ((F.tags_if_host & bit) != 0 && f0 == host) ||
@@ -871,6 +944,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
     Hdr* H = R.hdr;
     const Pkt K = *pkt_at(R, k);
     const itsb_net NET = R.m.nets[K.meta >> 16];
+    if (NET.mode == ITSB_NET_LINK) { m_deliver(H, k); return; }
     const bool bcast = (K.dst_ip == NET.bcast);
     u32 first = NET.first_node, count = NET.n_nodes;
     if (!bcast) {
@@ -1002,6 +1076,23 @@ ITSB_FN void set_pkt_regs(Rep& R, const ArenaNode& A) {
 }
 
 enum { XR_CONTINUE = 0, XR_STOP = 1 };
+
+/* Pops the head of the process's socket queue (caller checked q_len != 0). */
+ITSB_FN ArenaNode sock_pop(Rep& R, Sock& S) {
+    u32 n = S.q_head;
+    const ArenaNode A = R.arena[n];
+    S.q_head = A.next;
+    if (A.next == NIL32) S.q_tail = NIL32;
+    S.q_len -= 1;
+    arena_release(R, n);
+    stat_add(R, ITSB_TM_PACKETS_RECEIVED, 1);
+    stat_add(R, ITSB_TM_BYTES_RECEIVED, A.size);
+    return A;
+}
+
+}  // namespace itsb
+#include "itsb_machine.cuh"
+namespace itsb {
 
 /* Every instruction that is not on the per-packet path of a daemon: out of line. */
 ITSB_COLD int exec_cold(Hdr* H, u32 p, u64 ins) {
@@ -1138,22 +1229,8 @@ ITSB_COLD int exec_cold(Hdr* H, u32 p, u64 ins) {
         P.pc += 1;
         return XR_CONTINUE;
     default:
-        fail(H, ITSB_ERR_BAD_OPCODE, P.pc);
-        return XR_STOP;
+        return exec_machine(H, p, ins);
     }
-}
-
-/* Pops the head of the process's socket queue (caller checked q_len != 0). */
-ITSB_FN ArenaNode sock_pop(Rep& R, Sock& S) {
-    u32 n = S.q_head;
-    const ArenaNode A = R.arena[n];
-    S.q_head = A.next;
-    if (A.next == NIL32) S.q_tail = NIL32;
-    S.q_len -= 1;
-    arena_release(R, n);
-    stat_add(R, ITSB_TM_PACKETS_RECEIVED, 1);
-    stat_add(R, ITSB_TM_BYTES_RECEIVED, A.size);
-    return A;
 }
 
 /* Runs process p from its pc until it blocks or ends.  Inline: the receive loop heads, waits and branches a daemon
@@ -1168,6 +1245,15 @@ ITSB_FN void run_process(Rep& R, u32 p) {
         v[SRC_NODE_ADDR - 0x10] = N.addr; v[SRC_NODE_INDEX - 0x10] = P.node; v[SRC_NODE_HOST - 0x10] = N.host;
         v[SRC_NODE_EPOCH - 0x10] = R.node[P.node].epoch; v[SRC_NODE_BCAST - 0x10] = R.m.nets[N.net].bcast;
         v[SRC_SELF - 0x10] = handle_of(R, p); v[SRC_EXC - 0x10] = P.exc; v[SRC_ZERO - 0x10] = 0;
+        if (H->L.max_sig != 0) {
+            const u32 th = R.pcbx[p].thread;
+            if (th != NIL16) {
+                const u32 tk = R.thr[th].task;
+                v[SRC_SELF_THREAD - 0x10] = th | ((u32)R.thr[th].gen << 16);
+                v[SRC_SELF_TASK - 0x10] = tk | ((u32)R.task[tk].gen << 16);
+                v[SRC_PID - 0x10] = R.task[tk].pid;
+            }
+        }
     }
     for (;;) {
         if (H->status != 0) return;
@@ -1253,10 +1339,11 @@ ITSB_COLD u32 deliver_exception(Hdr* H, u32 p, u32 exc) {
         if (P.timer_ev != NIL16) ev_release(R, P.timer_ev);
         P.timer_ev = NIL16;
         P.timer_tok = (u16)(P.timer_tok + 1);
-    } else if (P.state == PS_WAIT) {
+    } else if (P.state == PS_WAIT && (P.wsig & 0xC000) != WS_SIG) {
         if (P.wsig & WS_NODE) { NodeDyn& N = R.node[P.wsig & 0x3FFF]; waiters_unlink(R, N.wake_head, N.wake_tail, p); }
         else if (P.wsig & WS_SOCK) { Sock& S = R.sock[P.wsig & 0x3FFF]; waiters_unlink(R, S.wait_head, S.wait_tail, p); }
     }
+    exc = machine_unwind(R, p, exc);
     P.exc = (u16)exc;
     P.phase = 0;
     const u64 ins = R.m.code[P.pc];
@@ -1281,16 +1368,19 @@ ITSB_FN u64 run_replica(Rep& R, double duration) {
     Hdr* H = R.hdr;
     if (H->status != 0) return 0;
     const u64 events_before = events_counted(R);
+    /* run(duration): a finite duration schedules the stop event first (it takes a counter value); run() without
+       one ends when the heap is empty and leaves the clock where it is */
     const double t_stop = H->now + duration;
     const u64 t_stop_bits = dbits(t_stop);
-    const u32 stop_seq = H->seq;
-    H->seq += 1;
+    const bool finite = t_stop_bits < T_EMPTY;
+    const u32 stop_seq = finite ? H->seq : NIL32;
+    if (finite) H->seq += 1;
     for (;;) {
         if (H->status != 0) break;
         u64 tb; u32 seq;
         const int src = ev_peek(R, tb, seq);
-        if (src == SRC_NONE_LEFT) break;                      /* heap empty: the clock stays where it is */
-        if (tb > t_stop_bits || (tb == t_stop_bits && seq > stop_seq)) {
+        if (src == SRC_NONE_LEFT && !finite) break;
+        if (src == SRC_NONE_LEFT || tb > t_stop_bits || (tb == t_stop_bits && seq > stop_seq)) {
             H->now = t_stop;
             count_event(R, ITSB_EV_STOP, 0, 0, 0);
             break;
@@ -1315,7 +1405,7 @@ ITSB_FN u64 run_replica(Rep& R, double duration) {
                 }
             }
             if (live) {
-                count_event(R, kind, P.prog, P.node, 0);
+                if (!is_hidden_prog(P.prog)) count_event(R, kind, P.prog, P.node, 0);
                 runnable = idx;
             }
         } else if (kind == ITSB_EV_TX_BEGIN) {
@@ -1325,7 +1415,8 @@ ITSB_FN u64 run_replica(Rep& R, double duration) {
         } else if (kind == ITSB_EV_THROW) {
             Pcb& P = R.pcb[idx];
             if (P.state != PS_FREE && P.gen == ev_gen(data)) {
-                count_event(R, ITSB_EV_THROW, P.prog, P.node, ev_exc(data));
+                if (!is_hidden_prog(P.prog) && !(ev_exc(data) & EXC_HIDDEN))
+                    count_event(R, ITSB_EV_THROW, P.prog, P.node, ev_exc(data));
                 if (P.state == PS_UNSTARTED) proc_exit(H, idx);   /* never ran: dies on the spot */
                 else runnable = deliver_exception(H, idx, ev_exc(data));
             }
@@ -1364,9 +1455,27 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
     }
     for (u32 i = 0; i < ITSB_TM_SIZE; ++i) R.stats[i] = 0;
     H->arena_free_top = L->arena_nodes;
+    H->sig_free_top = (u16)L->max_sig; H->thr_free_top = (u16)L->max_thr; H->task_free_top = (u16)L->max_task;
+    H->spare16b = 0;
+    H->hidden_entry_balk = 0; H->hidden_entry_wait_one = 0;
+    for (u32 i = 0; i < R.m.n_entries; ++i) {
+        if (R.m.entries[i].prog == PROG_HIDDEN_BALK) H->hidden_entry_balk = i;
+        if (R.m.entries[i].prog == PROG_HIDDEN_WAIT_ONE) H->hidden_entry_wait_one = i;
+    }
+    for (u32 i = 0; i < L->n_ifaces; ++i) R.iface_addr[i] = R.m.ifaces[i].addr0;
+    for (u32 i = 0; i < L->max_sig; ++i) { memset(&R.sig[i], 0, sizeof(Sig)); R.sig_free[i] = (u16)(L->max_sig - 1 - i); }
+    for (u32 i = 0; i < L->max_thr; ++i) { memset(&R.thr[i], 0, sizeof(Thr)); R.thr_free[i] = (u16)(L->max_thr - 1 - i); }
+    for (u32 i = 0; i < L->max_task; ++i) { memset(&R.task[i], 0, sizeof(Task)); R.task_free[i] = (u16)(L->max_task - 1 - i); }
+    if (L->max_sig != 0) {
+        for (u32 i = 0; i < L->max_proc; ++i) memset(&R.pcbx[i], 0, sizeof(PcbX));
+        for (u32 i = 0; i < L->n_nodes; ++i) {
+            if ((R.m.nodes[i].flags >> 16) != 0) { R.node[i].port_cursor = 32768; R.node[i].awake = 0; }
+        }
+    }
     for (u32 i = 0; i < R.m.n_init; ++i) {
         const itsb_initproc I = R.m.init[i];
-        proc_spawn(H, I.entry, I.node, I.r, 0.0);
+        if (I.mode == ITSB_INIT_RUN_PROC) m_run_proc_in(H, I.node, NIL32, I.entry, I.delay_const, I.r);
+        else proc_spawn(H, I.entry, I.node, I.r, 0.0);
     }
 }
 

@@ -31,6 +31,16 @@ static inline Layout compute_layout(const itsb_model_desc& d) {
     L.off_sock_free = off; off = align_up(off + 2 * L.max_sock, 16);
     L.off_node = off;      off = align_up(off + (uint32_t)sizeof(NodeDyn) * L.n_nodes, 16);
     L.off_stats = off;     off = align_up(off + 8 * ITSB_TM_SIZE, 16);
+    /* shipped-itsim tables */
+    L.n_ifaces = d.n_ifaces; L.max_sig = c.max_signals; L.max_thr = c.max_threads; L.max_task = c.max_tasks;
+    L.off_iface = off;     off = align_up(off + 4 * L.n_ifaces, 16);
+    L.off_pcbx = off;      off = align_up(off + (L.max_sig ? (uint32_t)sizeof(PcbX) * L.max_proc : 0), 16);
+    L.off_sig = off;       off = align_up(off + (uint32_t)sizeof(Sig) * L.max_sig, 16);
+    L.off_sig_free = off;  off = align_up(off + 2 * L.max_sig, 16);
+    L.off_thr = off;       off = align_up(off + (uint32_t)sizeof(Thr) * L.max_thr, 16);
+    L.off_thr_free = off;  off = align_up(off + 2 * L.max_thr, 16);
+    L.off_task = off;      off = align_up(off + (uint32_t)sizeof(Task) * L.max_task, 16);
+    L.off_task_free = off; off = align_up(off + 2 * L.max_task, 16);
     L.hot_bytes = align_up(off, 128);
     return L;
 }
@@ -42,7 +52,8 @@ static inline bool validate_model(const itsb_model_desc& d, const void* const* b
     const size_t want[ITSB_NUM_BLOBS] = {
         (size_t)d.n_code * 8, (size_t)d.n_entries * sizeof(itsb_entry), (size_t)d.n_dists * sizeof(itsb_dist),
         (size_t)d.n_consts * 8, (size_t)d.n_nets * sizeof(itsb_net), (size_t)d.n_nodes * sizeof(itsb_node),
-        (size_t)d.n_init * sizeof(itsb_initproc), (size_t)d.n_filters * sizeof(itsb_filter)};
+        (size_t)d.n_init * sizeof(itsb_initproc), (size_t)d.n_filters * sizeof(itsb_filter),
+        (size_t)d.n_ifaces * sizeof(itsb_iface), (size_t)d.n_routes * sizeof(itsb_route), (size_t)d.n_members * 4};
     for (int i = 0; i < ITSB_NUM_BLOBS; ++i) {
         if (sizes[i] != want[i] || (want[i] && !blobs[i])) {
             snprintf(buf, sizeof buf, "blob %d: %zu bytes given, %zu expected", i, sizes[i], want[i]);
@@ -77,15 +88,38 @@ static inline bool validate_model(const itsb_model_desc& d, const void* const* b
     for (uint32_t i = 0; i < d.n_entries; ++i) if (en[i].pc >= d.n_code) { why = "entry pc out of range"; return false; }
     const itsb_net* nets = (const itsb_net*)blobs[ITSB_BLOB_NETS];
     for (uint32_t i = 0; i < d.n_nets; ++i) {
-        if (nets[i].first_node + nets[i].n_nodes > d.n_nodes || nets[i].lat_dist >= d.n_dists || nets[i].bw_dist >= d.n_dists) {
+        if (nets[i].lat_dist >= d.n_dists || nets[i].bw_dist >= d.n_dists || nets[i].mode > ITSB_NET_LINK) {
             why = "net table out of range"; return false;
         }
     }
     const itsb_node* nodes = (const itsb_node*)blobs[ITSB_BLOB_NODES];
     for (uint32_t i = 0; i < d.n_nodes; ++i) if (nodes[i].net >= d.n_nets) { why = "node.net out of range"; return false; }
+    if (d.n_nets == 0) { why = "no network"; return false; }
     const itsb_initproc* ip = (const itsb_initproc*)blobs[ITSB_BLOB_INIT];
     for (uint32_t i = 0; i < d.n_init; ++i) if (ip[i].entry >= d.n_entries || ip[i].node >= d.n_nodes) { why = "init proc out of range"; return false; }
     if (d.n_init > c.max_procs) { why = "more installed processes than slots"; return false; }
+    /* shipped-itsim tables */
+    const bool machine = d.n_ifaces != 0;
+    if (machine && (c.max_signals == 0 || c.max_threads == 0 || c.max_tasks == 0)) { why = "shipped-itsim model without thread/task/signal tables"; return false; }
+    if (c.max_signals > 0x3FFF || c.max_threads > 0xFFFE || c.max_tasks > 0xFFFE) { why = "table capacity out of range"; return false; }
+    const itsb_iface* ifs = (const itsb_iface*)blobs[ITSB_BLOB_IFACES];
+    for (uint32_t i = 0; i < d.n_ifaces; ++i)
+        if (ifs[i].node >= d.n_nodes || ifs[i].net >= d.n_nets || ifs[i].first_route + ifs[i].n_routes > d.n_routes) { why = "interface table out of range"; return false; }
+    const uint32_t* mem = (const uint32_t*)blobs[ITSB_BLOB_MEMBERS];
+    for (uint32_t i = 0; i < d.n_members; ++i) if (mem[i] >= d.n_nodes) { why = "member out of range"; return false; }
+    for (uint32_t i = 0; i < d.n_nets; ++i) {
+        if (nets[i].mode == ITSB_NET_LINK && nets[i].first_node + nets[i].n_nodes > d.n_members) { why = "link members out of range"; return false; }
+        if (nets[i].mode == ITSB_NET_OVERRIDE && nets[i].first_node + nets[i].n_nodes > d.n_nodes) { why = "net table out of range"; return false; }
+    }
+    for (uint32_t i = 0; i < d.n_nodes; ++i) {
+        uint32_t fi = nodes[i].flags & 0xFFFF, ni = nodes[i].flags >> 16;
+        if (fi + ni > d.n_ifaces) { why = "node interfaces out of range"; return false; }
+    }
+    for (uint32_t i = 0; i < d.n_init; ++i)
+        if (ip[i].mode == ITSB_INIT_RUN_PROC && (!machine || ip[i].delay_const >= d.n_consts)) { why = "run_proc init entry invalid"; return false; }
+    bool has_balk = false, has_wait_one = false;
+    for (uint32_t i = 0; i < d.n_entries; ++i) { has_balk |= en[i].prog == PROG_HIDDEN_BALK; has_wait_one |= en[i].prog == PROG_HIDDEN_WAIT_ONE; }
+    if (machine && !(has_balk && has_wait_one)) { why = "shipped-itsim model without the greensim helper programs"; return false; }
     return true;
 }
 

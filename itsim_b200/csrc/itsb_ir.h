@@ -45,8 +45,33 @@ enum {
     OP_RECV_FILTER = 28,/* fused daemon loop head: "while True: with ws.awake(): packet = socket.recv(); if the
                            packet is not for this program: continue".  r[a] = wake epoch, b = filter index,
                            imm[0:16] = FellAsleep target, imm[16:32] = handler          network_simple.py:183-186 */
+    /* ---- shipped-itsim primitives (itsim/machine, itsim/network/link.py) ---------------------------------------- */
+    OP_BIND = 29,       /* Node.bind(port imm[0:16]; 0 = next ephemeral port 32768..60999)       node.py:168-200    */
+    OP_SCLOSE = 30,     /* Socket.close(): free the port, turn the close signal on               socket.py:76-82    */
+    OP_SENDL = 31,      /* Socket.send through routes and Link._transfer_packet; operands as OP_SEND
+                                                                     socket.py:91-109; node.py:212-230; link.py:70-86 */
+    OP_RECVT = 32,      /* Socket.recv(timeout = consts[imm[0:16]], 0xFFFF = None): greensim.select on the packet
+                           and close signals with its helper processes                          socket.py:121-145   */
+    OP_ADVANCE_X = 33,  /* advance(delay the thread was started with)                            thread.py:47        */
+    OP_THREAD_EXIT = 34,/* exit_f bookkeeping; a = 1: then re-raise the pending exception        thread.py:49-50,62-70 */
+    OP_CLONE = 35,      /* r[a] = thread.clone_in(consts[imm[16:32]], entry imm[0:16])           thread.py:35-39     */
+    OP_FORK = 36,       /* r[a] = process.fork_exec_in(consts[imm[16:32]], entry imm[0:16])      process.py:87-96    */
+    OP_JOIN = 37,       /* Thread.join(timeout consts[imm[0:16]] | None) on src(a)               thread.py:100-106   */
+    OP_PWAIT = 38,      /* Process.wait(timeout) on src(a)                                       process.py:84-85    */
+    OP_TKILL = 39,      /* Thread.kill() on src(a)                                               thread.py:87-98     */
+    OP_PKILL = 40,      /* Process.kill() on src(a)                                              process.py:70-76    */
+    OP_MARK = 41,       /* trace-only record imm of a model side effect (the tests' cemetary.append(name))          */
+    OP_SIG_WAIT = 42,   /* Signal.wait(timeout) on signal src(a)   (used by the select / balk helper programs)      */
+    OP_SIG_ON = 43,     /* Signal.turn_on() on signal src(a)                                                         */
+    OP_GSET = 44,       /* model variable g[imm & 7] = src(a)    (state shared between bodies, e.g. a dict of children) */
+    OP_NOW_SUB = 45,    /* x[2:4] (f64) = consts[imm] - now      (advance(YEAR - now()))   then OP_ADVANCE_X2        */
+    OP_ADVANCE_X2 = 46, /* advance(f64 in x[2:4])                                                                    */
     OP_COUNT
 };
+
+/* hidden programs appended by the assembler: greensim's own helper processes */
+#define PROG_HIDDEN_BALK     0xF1   /* Queue.join timeout helper            */
+#define PROG_HIDDEN_WAIT_ONE 0xF2   /* select() helper, one per signal      */
 
 /* operand sources */
 enum {
@@ -56,7 +81,9 @@ enum {
     SRC_ENT_IP = 0x18, SRC_ENT_PORT = 0x19,
     SRC_NODE_ADDR = 0x20, SRC_NODE_INDEX = 0x21, SRC_NODE_HOST = 0x22, SRC_NODE_EPOCH = 0x23,
     SRC_NODE_BCAST = 0x24, SRC_SELF = 0x25, SRC_EXC = 0x26,
+    SRC_SELF_THREAD = 0x27, SRC_SELF_TASK = 0x28, SRC_PID = 0x29,
     SRC_ZERO = 0x30,
+    SRC_G0 = 0x31,      /* model variables g0..g7 = 0x31..0x38 */
     SRC_NONE = 0xFF
 };
 
@@ -69,7 +96,15 @@ enum {
     DST_REGS = 4        /* (r2, r3 & 0xFFFF)                                                                    */
 };
 
-/* exception codes carried by THROW events; bit 7 = Interrupt class (greensim.Interrupt subclasses)             */
+/* exception codes carried by THROW events; bit 7 = Interrupt class (greensim.Interrupt subclasses), bit 6 = hidden
+ * (interrupts greensim sends to its own helper processes: not simulated events)                                 */
 #define EXC_INTERRUPT_CLASS 0x80
+#define EXC_HIDDEN          0x40
+#define EXC_ITSIM_TIMEOUT   0x02   /* itsim.types.Timeout (itsim/types.py:220-224): a plain Exception             */
+#define EXC_SOCKET_CLOSED   0x03   /* ValueError("Socket is closed")                                              */
+#define EXC_THREAD_KILLED   0x81   /* ThreadKilled(Interrupt)            thread.py:10-11                          */
+#define EXC_GS_TIMEOUT      0x82   /* greensim.Timeout(Interrupt), sent by the balk helper                        */
+#define EXC_CLEANUP         0xC1   /* select()'s CleanUp                                                          */
+#define EXC_CANCEL_BALK     0xC2   /* Queue.join's CancelBalk                                                     */
 
 #endif

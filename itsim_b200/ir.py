@@ -13,20 +13,31 @@ import numpy as np
 # opcodes (itsb_ir.h)
 (OP_NOP, OP_EXIT, OP_JMP, OP_LI, OP_MOV, OP_ADDI, OP_JEQ, OP_JNE, OP_JEQI, OP_JNEI, OP_DRAWI, OP_DRAW_ADDI,
  OP_ADVANCE, OP_ADVANCE_C, OP_OPEN, OP_CLOSE, OP_SEND, OP_RECV, OP_WAIT_AWAKE, OP_JASLEEP, OP_NODE_SLEEP,
- OP_NODE_WAKE, OP_SPAWN, OP_THROW, OP_LIST_CLEAR, OP_LIST_PUSH, OP_LIST_TAKE, OP_STAT, OP_RECV_FILTER) = range(29)
+ OP_NODE_WAKE, OP_SPAWN, OP_THROW, OP_LIST_CLEAR, OP_LIST_PUSH, OP_LIST_TAKE, OP_STAT, OP_RECV_FILTER,
+ OP_BIND, OP_SCLOSE, OP_SENDL, OP_RECVT, OP_ADVANCE_X, OP_THREAD_EXIT, OP_CLONE, OP_FORK, OP_JOIN, OP_PWAIT, OP_TKILL,
+ OP_PKILL, OP_MARK, OP_SIG_WAIT, OP_SIG_ON, OP_GSET, OP_NOW_SUB, OP_ADVANCE_X2) = range(47)
+
+PROG_HIDDEN_BALK, PROG_HIDDEN_WAIT_ONE = 0xF1, 0xF2
 
 # operand sources
 R0, R1, R2, R3 = 0, 1, 2, 3
 PKT_SRC_IP, PKT_SRC_PORT, PKT_SIZE, PKT_TAG, PKT_F0, PKT_F1 = 0x10, 0x11, 0x12, 0x13, 0x14, 0x15
 ENT_IP, ENT_PORT = 0x18, 0x19
 NODE_ADDR, NODE_INDEX, NODE_HOST, NODE_EPOCH, NODE_BCAST, SELF, EXC = 0x20, 0x21, 0x22, 0x23, 0x24, 0x25, 0x26
+SELF_THREAD, SELF_TASK, PID = 0x27, 0x28, 0x29
 ZERO = 0x30
+G0, G1, G2, G3, G4, G5, G6, G7 = range(0x31, 0x39)
 NONE = 0xFF
 
 # OP_SEND destination modes
 DST_BCAST, DST_PKT_SRC, DST_ENT, DST_SELF, DST_REGS = 0, 1, 2, 3, 4
 
 EXC_INTERRUPT_CLASS = 0x80
+EXC_HIDDEN = 0x40
+EXC_ITSIM_TIMEOUT, EXC_SOCKET_CLOSED = 0x02, 0x03          # itsim.types.Timeout; ValueError("Socket is closed")
+EXC_THREAD_KILLED, EXC_GS_TIMEOUT = 0x81, 0x82             # ThreadKilled(Interrupt); greensim.Timeout(Interrupt)
+EXC_CLEANUP, EXC_CANCEL_BALK = 0xC1, 0xC2
+NO_TIMEOUT = 0xFFFF
 
 Target = Union[str, int]
 
@@ -41,6 +52,8 @@ class Asm:
         self.entries: List[Tuple[str, int]] = []   # (label, program id)
         self._entry_index: Dict[str, int] = {}
         self._scope = ""
+        self._default_handler: Optional[str] = None   # inside a thread program: where an unhandled exception goes
+        self.uses_machine = False
 
     # -- structure ---------------------------------------------------------------------------------------
     def program(self, name: str, prog_id: int) -> int:
@@ -53,6 +66,48 @@ class Asm:
 
     def entry(self, name: str) -> int:
         return self._entry_index[name]
+
+    # -- shipped-itsim thread bodies -------------------------------------------------------------------------
+    def thread_program(self, name: str, prog_id: int) -> int:
+        """Starts a body run through ``Thread.run_in`` (thread.py:41-57): ``try: advance(delay); body finally:
+        exit_f``.  Blocking instructions of the body default to the handler that runs ``exit_f`` and re-raises."""
+        self.uses_machine = True
+        idx = self.program(name, prog_id)
+        self._default_handler = "__exit_raise"
+        self._emit(OP_ADVANCE_X, imm=("hi16", self._t("__exit_raise"), 0))
+        return idx
+
+    def end_thread_program(self) -> None:
+        self._emit(OP_THREAD_EXIT, 0)
+        self.label("__exit_raise")
+        self._emit(OP_THREAD_EXIT, 1)
+        self._default_handler = None
+
+    def _h(self, handler: Optional[Target]) -> object:
+        if handler is None and self._default_handler is not None:
+            return self._t(self._default_handler)
+        return self._t(handler)
+
+    def reraise(self) -> None:
+        """``raise`` inside an except/finally block of a thread body: run exit_f, then propagate."""
+        self.jmp("__exit_raise")
+
+    def add_hidden_programs(self) -> None:
+        """greensim's own helper processes (SURVEY.md Appendix A): the Queue.join timeout helper and select()'s
+        per-signal helper.  Appended once to every model that uses the shipped-itsim primitives."""
+        if "__balk" in self._entry_index:
+            return
+        self._default_handler = None
+        self.program("__balk", PROG_HIDDEN_BALK)           # try: advance(timeout); proc.interrupt(Timeout())
+        self._emit(OP_ADVANCE_X, imm=("hi16", self._t("end"), 0))
+        self.throw(R0, EXC_GS_TIMEOUT)                     # except CancelBalk: pass
+        self.label("end")
+        self.exit()
+        self.program("__wait_one", PROG_HIDDEN_WAIT_ONE)   # try: signal.wait(); common.turn_on()
+        self._emit(OP_SIG_WAIT, R0, imm=("hi16", self._t("end"), NO_TIMEOUT))
+        self._emit(OP_SIG_ON, R1)                          # except CleanUp: pass
+        self.label("end")
+        self.exit()
 
     def label(self, name: str) -> None:
         key = self._scope + name
@@ -84,10 +139,41 @@ class Asm:
     def draw_addi(self, rd: int, src: int, dist: int) -> None: self._emit(OP_DRAW_ADDI, rd, src, imm=dist)
 
     def advance(self, dist: int, handler: Optional[Target] = None) -> None:
-        self._emit(OP_ADVANCE, imm=("hi16", self._t(handler), dist))
+        self._emit(OP_ADVANCE, imm=("hi16", self._h(handler), dist))
 
     def advance_const(self, const_index: int, handler: Optional[Target] = None) -> None:
-        self._emit(OP_ADVANCE_C, imm=("hi16", self._t(handler), const_index))
+        self._emit(OP_ADVANCE_C, imm=("hi16", self._h(handler), const_index))
+
+    # shipped-itsim primitives
+    def bind(self, port: int = 0) -> None: self._emit(OP_BIND, imm=port)
+    def sclose(self) -> None: self._emit(OP_SCLOSE)
+
+    def sendl(self, dst_mode: int, size_src: int, tag: int, port: int = 0, f0: int = NONE, f1: int = NONE,
+              handler: Optional[Target] = None) -> None:
+        self._emit(OP_SENDL, dst_mode, size_src, tag, (port & 0xFFFF) | (f0 << 16) | (f1 << 24))
+
+    def recvt(self, timeout_const: int = NO_TIMEOUT, handler: Optional[Target] = None) -> None:
+        self._emit(OP_RECVT, imm=("hi16", self._h(handler), timeout_const))
+
+    def clone(self, program: str, delay_const: int, rd: int = NONE) -> None:
+        self._emit(OP_CLONE, rd, imm=("hi16", delay_const, ("entry", program)))
+
+    def fork(self, program: str, delay_const: int, rd: int = NONE) -> None:
+        self._emit(OP_FORK, rd, imm=("hi16", delay_const, ("entry", program)))
+
+    def join(self, thread_src: int, timeout_const: int = NO_TIMEOUT, handler: Optional[Target] = None) -> None:
+        self._emit(OP_JOIN, thread_src, imm=("hi16", self._h(handler), timeout_const))
+
+    def pwait(self, task_src: int, timeout_const: int = NO_TIMEOUT, handler: Optional[Target] = None) -> None:
+        self._emit(OP_PWAIT, task_src, imm=("hi16", self._h(handler), timeout_const))
+
+    def tkill(self, thread_src: int) -> None: self._emit(OP_TKILL, thread_src)
+    def pkill(self, task_src: int) -> None: self._emit(OP_PKILL, task_src)
+    def mark(self, code: int) -> None: self._emit(OP_MARK, imm=code)
+    def gset(self, index: int, src: int) -> None: self._emit(OP_GSET, src, imm=index)
+    def now_sub(self, const_index: int) -> None: self._emit(OP_NOW_SUB, imm=const_index)
+    def advance_x2(self, handler: Optional[Target] = None) -> None:
+        self._emit(OP_ADVANCE_X2, imm=("hi16", self._h(handler), 0))
 
     def open(self, port: int = 0) -> None: self._emit(OP_OPEN, imm=port)
     def close(self) -> None: self._emit(OP_CLOSE)

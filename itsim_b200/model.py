@@ -46,16 +46,22 @@ class NetworkFull(Exception):
 class Compiled:
     """The tables handed to ``itsb_load_model`` (blob order = ``ITSB_BLOB_*`` in include/itsb.h)."""
 
-    def __init__(self, code, entries, dists, consts, nets, nodes, init, filters, caps: L.Caps) -> None:
+    def __init__(self, code, entries, dists, consts, nets, nodes, init, filters, caps: L.Caps, ifaces=None,
+                 routes=None, members=None) -> None:
         self.code, self.entries, self.dists, self.consts = code, entries, dists, consts
         self.nets, self.nodes, self.init, self.filters, self.caps = nets, nodes, init, filters, caps
+        self.ifaces = ifaces if ifaces is not None else np.zeros(0, dtype=L.IFACE_DTYPE)
+        self.routes = routes if routes is not None else np.zeros(0, dtype=L.ROUTE_DTYPE)
+        self.members = members if members is not None else np.zeros(0, dtype=np.uint32)
 
     def blobs(self) -> List[np.ndarray]:
-        return [self.code, self.entries, self.dists, self.consts, self.nets, self.nodes, self.init, self.filters]
+        return [self.code, self.entries, self.dists, self.consts, self.nets, self.nodes, self.init, self.filters,
+                self.ifaces, self.routes, self.members]
 
     def desc(self) -> L.ModelDesc:
         return L.ModelDesc(L.ABI_VERSION, len(self.code), len(self.entries), len(self.dists), len(self.consts),
-                           len(self.nets), len(self.nodes), len(self.init), len(self.filters), self.caps)
+                           len(self.nets), len(self.nodes), len(self.init), len(self.filters), len(self.ifaces),
+                           len(self.routes), len(self.members), self.caps)
 
 
 class Simulator:
@@ -75,7 +81,8 @@ class Simulator:
         self.nodes: List["Endpoint"] = []
         self._installed: List[Tuple[str, "Endpoint", Sequence[int]]] = []
         self.caps = dict(max_events=384, max_procs=256, max_sockets=128, max_packets=0, arena_nodes=16384,
-                         trace_records=0)
+                         trace_records=0, max_threads=0, max_tasks=0, max_signals=0)
+        self._machine_procs: List[Tuple[Any, float, str, Sequence[int]]] = []   # Node.run_proc_in calls, in order
         self._engine: Any = None
         self._lib: Any = None       # tests inject the host-emulation library here; None = the CUDA engine
 
@@ -111,6 +118,9 @@ class Simulator:
         return self._filters.index(entry)
 
     def compile(self) -> Compiled:
+        if self._machine_procs:
+            from .machine import compile_machine
+            return compile_machine(self)
         code, entries_raw = self.asm.assemble()
         entries = np.zeros(len(entries_raw), dtype=L.ENTRY_DTYPE)
         entries["pc"], entries["prog"] = entries_raw[:, 0], entries_raw[:, 1]
@@ -139,7 +149,7 @@ class Simulator:
         init = np.zeros(len(self._installed), dtype=L.INIT_DTYPE)
         for i, (program, node, regs) in enumerate(self._installed):
             r = list(regs) + [0] * (4 - len(regs))
-            init[i] = (self.asm.entry(program), node.index, r)
+            init[i] = (self.asm.entry(program), node.index, r, 0, 0)
         filters = np.zeros(len(self._filters), dtype=L.FILTER_DTYPE)
         for i, (fa, fh, fl) in enumerate(self._filters):
             filters[i] = (fa, fh, fl, 0)

@@ -62,6 +62,7 @@ class Tracer:
         self.ghost = 0
         self.exc_code: Callable[[BaseException], int] = lambda exc: 0
         self.deliver_aux: Callable[[Any, Any], int] = lambda proc, ev: 0
+        self.resolver: Optional[Callable[[Any], "Ident"]] = None   # labels processes the model code did not label
         sim._on_pop = self._on_pop
         self._stop_fn = sim.stop
 
@@ -96,7 +97,7 @@ class Tracer:
             return
         ident: Optional[Ident] = getattr(proc, "ident", None)
         if ident is None:
-            ident = Ident(ROLE_MODEL, 0, 0xFFFF)
+            ident = self.resolver(proc) if self.resolver is not None else Ident(ROLE_MODEL, 0, 0xFFFF)
             proc.ident = ident
         if name == "throw":
             exc = ev.args[0]

@@ -8,7 +8,11 @@ vectors are the oracle's own output under the injected Philox stream:
 * netsimple_summaries.json                      per (seed, replica, horizon): event counts per kind, model counters,
                                                 draws consumed, final clock, digest of the integer trace columns
 
+* machine_<scenario>*.npz / machine_summaries.json   (--machine) traces of the reference's own integration-test
+                                                bodies for the shipped-itsim primitives, oracle/machine_scenarios.py
+
 Usage: python oracle/make_golden.py [--full]     (--full adds the 43 200 s = 12 h horizon of config C1: ~7 min)
+       python oracle/make_golden.py --machine
 """
 import json
 import os
@@ -34,8 +38,28 @@ def summary_of(model, horizon):
     return out, arr
 
 
+def machine_golden() -> None:
+    """Golden traces of the shipped-itsim scenarios: the reference's own integration-test bodies (needs
+    /root/reference)."""
+    import machine_scenarios as ms
+    out = {}
+    jobs = [("thread_lifecycle", {}), ("process_lifecycle", {}),
+            ("packet_transfer", {"seed": 0, "replica": 0}), ("packet_transfer", {"seed": 5, "replica": 77}),
+            ("broadcast", {"seed": 0, "replica": 0}), ("broadcast", {"seed": 3, "replica": 11, "duration": 60.0})]
+    for name, kwargs in jobs:
+        arr, summary = ms.SCENARIOS[name](**kwargs)
+        tag = name + "".join(f"_{k[0]}{int(v)}" for k, v in kwargs.items())
+        np.savez_compressed(os.path.join(GOLDEN, f"machine_{tag}.npz"), trace=arr)
+        out[tag] = summary
+        print("machine", tag, summary["events"], flush=True)
+    json.dump(out, open(os.path.join(GOLDEN, "machine_summaries.json"), "w"), indent=1, sort_keys=True)
+
+
 def main() -> None:
     os.makedirs(GOLDEN, exist_ok=True)
+    if "--machine" in sys.argv:
+        machine_golden()
+        return
     path = os.path.join(GOLDEN, "netsimple_summaries.json")
     summaries = json.load(open(path)) if os.path.exists(path) else {}
     # 1. full traces, short horizon

@@ -24,6 +24,9 @@ struct itsb_engine {
     std::vector<itsb_node> nodes;
     std::vector<itsb_initproc> init;
     std::vector<itsb_filter> filters;
+    std::vector<itsb_iface> ifaces;
+    std::vector<itsb_route> routes;
+    std::vector<uint32_t> members;
     Model model;
     Layout layout;
     uint64_t n_replicas = 0, seed = 0, first = 0;
@@ -53,9 +56,14 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     e->nodes.assign((const itsb_node*)blobs[5], (const itsb_node*)blobs[5] + d->n_nodes);
     e->init.assign((const itsb_initproc*)blobs[6], (const itsb_initproc*)blobs[6] + d->n_init);
     e->filters.assign((const itsb_filter*)blobs[7], (const itsb_filter*)blobs[7] + d->n_filters);
+    e->ifaces.assign((const itsb_iface*)blobs[8], (const itsb_iface*)blobs[8] + d->n_ifaces);
+    e->routes.assign((const itsb_route*)blobs[9], (const itsb_route*)blobs[9] + d->n_routes);
+    e->members.assign((const uint32_t*)blobs[10], (const uint32_t*)blobs[10] + d->n_members);
     Model& m = e->model;
     m.code = e->code.data(); m.entries = e->entries.data(); m.dists = e->dists.data(); m.consts = e->consts.data();
     m.nets = e->nets.data(); m.nodes = e->nodes.data(); m.init = e->init.data(); m.filters = e->filters.data();
+    m.ifaces = e->ifaces.data(); m.routes = e->routes.data(); m.members = e->members.data();
+    m.n_ifaces = d->n_ifaces; m.n_routes = d->n_routes; m.n_members = d->n_members;
     m.n_code = d->n_code; m.n_entries = d->n_entries; m.n_dists = d->n_dists; m.n_consts = d->n_consts;
     m.n_nets = d->n_nets; m.n_nodes = d->n_nodes; m.n_init = d->n_init; m.n_filters = d->n_filters;
     e->layout = compute_layout(*d);

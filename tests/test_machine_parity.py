@@ -1,0 +1,83 @@
+"""
+Shipped-itsim primitives: the engine's restatement of the reference's integration-test models
+(itsim_b200/machine_models.py) against golden traces produced by the reference's OWN test bodies running unmodified on
+the reference's itsim package + the oracle's greensim shim (oracle/machine_scenarios.py).  The known answers the
+reference asserts -- cemetary order and final clock 120 of test_thread_lifecycle.py:83-84, the 2.0 s arrival of
+test_link.py:56-61 -- are checked directly as well.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_trace_equal, load_golden_trace
+
+INF = float("inf")
+CASES = [
+    ("thread_lifecycle", "machine_thread_lifecycle.npz", 0, 0, INF),
+    ("process_lifecycle", "machine_process_lifecycle.npz", 0, 0, 4000.0),
+    ("packet_transfer", "machine_packet_transfer_s0_r0.npz", 0, 0, 10.0),
+    ("packet_transfer", "machine_packet_transfer_s5_r77.npz", 5, 77, 10.0),
+    ("broadcast", "machine_broadcast_s0_r0.npz", 0, 0, 10.0),
+    ("broadcast", "machine_broadcast_s3_r11_d60.npz", 3, 11, 60.0),
+]
+
+
+def run_scenario(name, seed, replica, duration, lib=None, n=1):
+    from itsim_b200 import machine_models
+    sim = machine_models.SCENARIOS[name]()
+    sim._lib = lib
+    eng = sim.run_replicas(n, seed=seed, first_replica_id=replica)
+    eng.run(duration)
+    return eng
+
+
+@pytest.mark.parametrize("name,golden,seed,replica,duration", CASES)
+def test_hostemu_matches_reference_bodies(hostemu, name, golden, seed, replica, duration):
+    eng = run_scenario(name, seed, replica, duration, lib=hostemu)
+    assert_trace_equal(eng.trace(0), load_golden_trace(golden))
+
+
+def test_known_answers_of_the_reference(hostemu):
+    from itsim_b200 import _lib as L
+    eng = run_scenario("thread_lifecycle", 0, 0, INF, lib=hostemu)
+    tr = eng.trace(0)
+    marks = [int(r["aux"]) for r in tr if r["kind"] == L.TRACE_MARK]
+    assert marks == [1, 2, 3, 4, 5, 6]              # ["cadet", "grandchild", "elder", "parent", "super_long", "watcher"]
+    assert eng.now()[0] == 120.0                    # TIMEOUT_SUPERLONG + max(DELAY_GRANDCHILD, DELAY_CADET)
+    eng = run_scenario("link_delay", 0, 0, 5.0, lib=hostemu)
+    tr = eng.trace(0)
+    arrival = [r["t"] for r in tr if r["kind"] == L.EV_DELIVER]
+    assert arrival == [2.0]                         # DURATION_TRANSFER_TOTAL
+    assert int(tr[tr["kind"] == L.EV_DELIVER]["aux"][0]) == (1000 | 0x80000000)
+    eng = run_scenario("process_lifecycle", 0, 0, 4000.0, lib=hostemu)
+    tr = eng.trace(0)
+    marks = {int(r["aux"]): float(r["t"]) for r in tr if r["kind"] == L.TRACE_MARK}
+    assert marks == {2: 130.0, 1: 730.0, 3: 1042.0, 5: 3042.0}     # Abel, Cain, Seth die; adameve gives up on Humanity
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/itsim"), reason="reference tree not on this box")
+def test_golden_is_what_the_reference_bodies_produce_now():
+    import machine_scenarios as ms
+    arr, _ = ms.packet_transfer(seed=5, replica=77)
+    assert_trace_equal(arr, load_golden_trace("machine_packet_transfer_s5_r77.npz"), rtol=0.0)
+    arr, _ = ms.thread_lifecycle()
+    assert_trace_equal(arr, load_golden_trace("machine_thread_lifecycle.npz"), rtol=0.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,golden,seed,replica,duration", CASES)
+def test_gpu_matches_reference_bodies(name, golden, seed, replica, duration):
+    eng = run_scenario(name, seed, replica, duration, n=3)
+    assert_trace_equal(eng.trace(0), load_golden_trace(golden))
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_equals_hostemu_on_a_broadcast_batch(hostemu):
+    gpu = run_scenario("broadcast", 9, 100, 120.0, n=40)
+    emu = run_scenario("broadcast", 9, 100, 120.0, lib=hostemu, n=40)
+    for r in range(40):
+        assert np.array_equal(gpu.replica_telemetry(r), emu.replica_telemetry(r)), r
+    assert np.all(gpu.now() == 120.0)
+    gpu.close()
