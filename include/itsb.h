@@ -168,6 +168,7 @@ typedef struct itsb_caps {        /* per-replica capacities; exceeding one flags
     uint32_t arena_nodes;         /* 32-byte nodes in HBM: socket queues, remembered packets, packets in flight   */
     uint32_t trace_records;       /* per-replica trace capacity (0 = tracing off)                                 */
     uint32_t max_threads, max_tasks, max_signals;   /* shipped-itsim Thread / Process / Signal tables (0 = none)  */
+    uint32_t table_words;         /* per-replica uint32 model table (TLOAD / TSTORE), zero-initialised            */
 } itsb_caps;
 
 typedef struct itsb_model_desc {

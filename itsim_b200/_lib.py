@@ -53,7 +53,8 @@ assert IFACE_DTYPE.itemsize == 32 and ROUTE_DTYPE.itemsize == 32
 class Caps(C.Structure):
     _fields_ = [("max_events", C.c_uint32), ("max_procs", C.c_uint32), ("max_sockets", C.c_uint32),
                 ("max_packets", C.c_uint32), ("arena_nodes", C.c_uint32), ("trace_records", C.c_uint32),
-                ("max_threads", C.c_uint32), ("max_tasks", C.c_uint32), ("max_signals", C.c_uint32)]
+                ("max_threads", C.c_uint32), ("max_tasks", C.c_uint32), ("max_signals", C.c_uint32),
+                ("table_words", C.c_uint32)]
 
 
 class ModelDesc(C.Structure):

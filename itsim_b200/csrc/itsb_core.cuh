@@ -213,6 +213,7 @@ struct Layout {             /* byte offsets inside one replica's hot block */
     /* shipped-itsim tables (all zero when the model does not use them) */
     u32 off_iface, off_pcbx, off_sig, off_sig_free, off_thr, off_thr_free, off_task, off_task_free;
     u32 n_ifaces, max_sig, max_thr, max_task;
+    u32 off_tab, table_words;
 };
 
 struct Model {              /* pointers to the static tables (shared-memory copies inside the kernel) */
@@ -289,6 +290,7 @@ struct Rep {                /* register-resident working view of one replica */
     u16* thr_free;
     Task* task;
     u16* task_free;
+    u32* tab;               /* model table (TLOAD / TSTORE) */
 };
 
 /* Rebuilds the working view from the header alone (used on entry by every out-of-line function; unused fields are
@@ -321,6 +323,7 @@ ITSB_FN void rebind(Rep& R, Hdr* H) {
     R.thr_free = (u16*)(hot + H->L.off_thr_free);
     R.task = (Task*)(hot + H->L.off_task);
     R.task_free = (u16*)(hot + H->L.off_task_free);
+    R.tab = (u32*)(hot + H->L.off_tab);
 }
 
 /* Stages the launch's pointers into the header, then builds the view. */
@@ -1072,7 +1075,7 @@ ITSB_FN void set_pkt_regs(Rep& R, const ArenaNode& A) {
     u32* v = R.hdr->vol;
     v[SRC_PKT_SRC_IP - 0x10] = A.src_ip; v[SRC_PKT_SRC_PORT - 0x10] = A.ports & 0xFFFF;
     v[SRC_PKT_SIZE - 0x10] = A.size; v[SRC_PKT_TAG - 0x10] = A.tag;
-    v[SRC_PKT_F0 - 0x10] = A.f0; v[SRC_PKT_F1 - 0x10] = A.f1;
+    v[SRC_PKT_F0 - 0x10] = A.f0; v[SRC_PKT_F1 - 0x10] = A.f1; v[SRC_PKT_DST_IP - 0x10] = A.pad;
 }
 
 enum { XR_CONTINUE = 0, XR_STOP = 1 };
@@ -1463,6 +1466,7 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
         if (R.m.entries[i].prog == PROG_HIDDEN_WAIT_ONE) H->hidden_entry_wait_one = i;
     }
     for (u32 i = 0; i < L->n_ifaces; ++i) R.iface_addr[i] = R.m.ifaces[i].addr0;
+    for (u32 i = 0; i < L->table_words; ++i) R.tab[i] = 0;
     for (u32 i = 0; i < L->max_sig; ++i) { memset(&R.sig[i], 0, sizeof(Sig)); R.sig_free[i] = (u16)(L->max_sig - 1 - i); }
     for (u32 i = 0; i < L->max_thr; ++i) { memset(&R.thr[i], 0, sizeof(Thr)); R.thr_free[i] = (u16)(L->max_thr - 1 - i); }
     for (u32 i = 0; i < L->max_task; ++i) { memset(&R.task[i], 0, sizeof(Task)); R.task_free[i] = (u16)(L->max_task - 1 - i); }

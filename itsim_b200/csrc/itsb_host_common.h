@@ -41,6 +41,8 @@ static inline Layout compute_layout(const itsb_model_desc& d) {
     L.off_thr_free = off;  off = align_up(off + 2 * L.max_thr, 16);
     L.off_task = off;      off = align_up(off + (uint32_t)sizeof(Task) * L.max_task, 16);
     L.off_task_free = off; off = align_up(off + 2 * L.max_task, 16);
+    L.table_words = c.table_words;
+    L.off_tab = off;       off = align_up(off + 4 * L.table_words, 16);
     L.hot_bytes = align_up(off, 128);
     return L;
 }

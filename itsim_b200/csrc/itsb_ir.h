@@ -66,6 +66,20 @@ enum {
     OP_GSET = 44,       /* model variable g[imm & 7] = src(a)    (state shared between bodies, e.g. a dict of children) */
     OP_NOW_SUB = 45,    /* x[2:4] (f64) = consts[imm] - now      (advance(YEAR - now()))   then OP_ADVANCE_X2        */
     OP_ADVANCE_X2 = 46, /* advance(f64 in x[2:4])                                                                    */
+    /* ---- small generic helpers the protocol bodies need (DHCP: dhcp/client.py, dhcp/server.py) ------------------- */
+    OP_TLOAD = 47,      /* r[a] = table[imm + src(b)]        per-replica model table (dicts / sets of a daemon)       */
+    OP_TSTORE = 48,     /* table[imm + src(b)] = src(a)                                                               */
+    OP_ADD = 49,        /* r[a] = src(b) + src(c)                                                                     */
+    OP_SUB = 50,        /* r[a] = src(b) - src(c)                                                                     */
+    OP_JLTU = 51,       /* if src(a) < src(b) (unsigned) goto imm                                                     */
+    OP_XNOW = 52,       /* x[0:2] = now()                    time_before_recv = now()            client.py:89         */
+    OP_XSET = 53,       /* x[2:4] = consts[imm]              time_remaining = reservation_time   client.py:86         */
+    OP_XELAPSE = 54,    /* x[2:4] -= now() - x[0:2]          time_remaining -= now() - before    client.py:93         */
+    OP_JXLE0 = 55,      /* if x[2:4] <= 0.0 goto imm         while time_remaining > 0.0          client.py:87         */
+    OP_RECVT_X = 56,    /* Socket.recv(timeout = x[2:4])                                         client.py:90         */
+    OP_SETADDR = 57,    /* interface.address = src(a), re-rooted in the link's CIDR (first non-loopback interface)
+                                                                                  interface.py:50-57; client.py:147 */
+    OP_GETADDR = 58,    /* r[a] = interface.address                                              client.py:144        */
     OP_COUNT
 };
 
@@ -77,7 +91,7 @@ enum {
 enum {
     SRC_R0 = 0, SRC_R1 = 1, SRC_R2 = 2, SRC_R3 = 3,
     SRC_PKT_SRC_IP = 0x10, SRC_PKT_SRC_PORT = 0x11, SRC_PKT_SIZE = 0x12, SRC_PKT_TAG = 0x13,
-    SRC_PKT_F0 = 0x14, SRC_PKT_F1 = 0x15,
+    SRC_PKT_F0 = 0x14, SRC_PKT_F1 = 0x15, SRC_PKT_DST_IP = 0x16,
     SRC_ENT_IP = 0x18, SRC_ENT_PORT = 0x19,
     SRC_NODE_ADDR = 0x20, SRC_NODE_INDEX = 0x21, SRC_NODE_HOST = 0x22, SRC_NODE_EPOCH = 0x23,
     SRC_NODE_BCAST = 0x24, SRC_SELF = 0x25, SRC_EXC = 0x26,

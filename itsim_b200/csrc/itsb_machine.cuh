@@ -67,19 +67,19 @@ ITSB_FN void sig_on(Rep& R, u32 s) {
 }
 
 /* Queue.join(timeout) half: enqueue, start the balk helper if the wait is timed, park.  (greensim; Appendix A) */
-ITSB_FN void sig_join(Rep& R, u32 p, u32 s, u32 timeout_const) {
+ITSB_FN void sig_join(Rep& R, u32 p, u32 s, bool timed, double timeout) {
     Hdr* H = R.hdr;
     Sig& S = R.sig[s];
     Pcb& P = R.pcb[p];
     waiters_append(R, S.head, S.tail, p, (u16)(WS_SIG | s));
     PcbX& X = R.pcbx[p];
     X.balker_h = NIL32;
-    if (timeout_const != 0xFFFF) {
+    if (timed) {
         /* balker = add(balk, me): hidden process, r0 = my handle, its delay = the timeout */
         u32 regs[4] = {handle_of(R, p), 0, 0, 0};
         int b = proc_spawn(H, H->hidden_entry_balk, P.node, regs, 0.0);
         if (b >= 0) {
-            const u64 tbits = dbits(R.m.consts[timeout_const]);
+            const u64 tbits = dbits(timeout);
             R.pcbx[b].x[0] = (u32)tbits; R.pcbx[b].x[1] = (u32)(tbits >> 32);
             R.pcbx[b].thread = NIL16;
             X.balker_h = handle_of(R, (u32)b);
@@ -102,7 +102,7 @@ ITSB_FN bool sig_wait(Rep& R, u32 p, u32 s, u32 timeout_const) {
     Pcb& P = R.pcb[p];
     if (P.phase == 1) { cancel_balker(R, p); P.phase = 0; }
     if (s == NIL16 || R.sig[s].on) return false;
-    sig_join(R, p, s, timeout_const);
+    sig_join(R, p, s, timeout_const != 0xFFFF, timeout_const != 0xFFFF ? R.m.consts[timeout_const] : 0.0);
     P.phase = 1;
     return true;
 }
@@ -157,7 +157,7 @@ ITSB_FN int thr_new(Rep& R, u32 task) {
 
 /* Thread.run_in(time, f): sim.add(wrap_computation, sim_comp, time) -- the computation starts now, advances `time`,
  * then runs the body (thread.py:41-57) */
-ITSB_FN int thr_run_in(Rep& R, u32 thr, u32 entry, u32 delay_const, const u32* regs) {
+ITSB_FN int thr_run_in(Rep& R, u32 thr, u32 entry, u32 delay_const, const u32* regs, u32 inherit_sock = NIL16) {
     Hdr* H = R.hdr;
     Thr& T = R.thr[thr];
     const u32 node = R.task[T.task].node;
@@ -170,6 +170,7 @@ ITSB_FN int thr_run_in(Rep& R, u32 thr, u32 entry, u32 delay_const, const u32* r
     if (T.comp_tail == NIL16) T.comp_head = (u16)p; else R.pcbx[T.comp_tail].tnext = (u16)p;
     T.comp_tail = (u16)p;
     T.ncomp += 1;
+    R.pcb[p].sock = (u16)inherit_sock;      /* a body started with the caller's socket as argument (node.py:343-346) */
     return p;
 }
 
@@ -334,7 +335,7 @@ ITSB_COLD void m_deliver(Hdr* H, u32 k) {
             if (an == NIL32) return;
             ArenaNode A;
             A.next = NIL32; A.src_ip = K.src_ip; A.ports = K.ports; A.size = K.size;
-            A.tag = K.tag & 0xFFFF; A.f0 = K.f0; A.f1 = K.f1; A.pad = 0;
+            A.tag = K.tag & 0xFFFF; A.f0 = K.f0; A.f1 = K.f1; A.pad = K.dst_ip;
             R.arena[an] = A;
             Sock& S = R.sock[s];
             if (S.q_tail == NIL32) S.q_head = an; else R.arena[S.q_tail].next = an;
@@ -472,6 +473,7 @@ ITSB_COLD int exec_machine(Hdr* H, u32 p, u64 ins) {
     switch (op) {
     case OP_BIND:
         if (m_bind(H, p, imm & 0xFFFF) < 0) return XR_STOP;
+        if (a == 1) R.sock[P.sock].owner = NIL16;     /* detached: outlives the binder (networking daemon) */
         P.pc += 1;
         return XR_CONTINUE;
     case OP_SCLOSE:
@@ -497,9 +499,14 @@ ITSB_COLD int exec_machine(Hdr* H, u32 p, u64 ins) {
         P.pc += 1;
         return XR_CONTINUE;
     }
-    case OP_RECVT: {
+    case OP_RECVT:
+    case OP_RECVT_X: {
         if (P.sock == NIL16) { fail(H, ITSB_EXC_SOCKET_CLOSED, P.pc); return XR_STOP; }
         Sock& S = R.sock[P.sock];
+        bool timed;
+        double timeout;
+        if (op == OP_RECVT) { timed = (imm & 0xFFFF) != 0xFFFF; timeout = timed ? R.m.consts[imm & 0xFFFF] : 0.0; }
+        else { timed = true; timeout = bitsd(((u64)X.x[3] << 32) | X.x[2]); }
         if (P.phase == 0) {
             if (R.sig[S.wait_tail].on) return raise_here(R, p, EXC_SOCKET_CLOSED);
             /* greensim.select(packet_signal, close_signal, timeout=...) */
@@ -513,14 +520,14 @@ ITSB_COLD int exec_machine(Hdr* H, u32 p, u64 ins) {
             if (h1 < 0 || h2 < 0) return XR_STOP;
             R.pcbx[h1].thread = NIL16; R.pcbx[h2].thread = NIL16;
             X.sel_h1 = handle_of(R, (u32)h1); X.sel_h2 = handle_of(R, (u32)h2);
-            sig_join(R, p, common, imm & 0xFFFF);     /* common.wait(timeout): just created, so it is off */
+            sig_join(R, p, common, timed, timeout);   /* common.wait(timeout): just created, so it is off */
             P.phase = 1;
             return XR_STOP;
         }
         /* resumed: join()'s finally, then `while not common.is_on` */
         cancel_balker(R, p);
         if (!R.sig[X.sel_common].on) {
-            sig_join(R, p, X.sel_common, imm & 0xFFFF);
+            sig_join(R, p, X.sel_common, timed, timeout);
             return XR_STOP;
         }
         select_cleanup(R, p);
@@ -563,7 +570,7 @@ ITSB_COLD int exec_machine(Hdr* H, u32 p, u64 ins) {
         int t = thr_new(R, R.thr[X.thread].task);
         if (t < 0) return XR_STOP;
         const u32 gen = R.thr[t].gen;
-        if (thr_run_in(R, (u32)t, imm & 0xFFFF, imm >> 16, P.r) < 0) return XR_STOP;
+        if (thr_run_in(R, (u32)t, imm & 0xFFFF, imm >> 16, P.r, P.sock) < 0) return XR_STOP;
         if (a != SRC_NONE) P.r[a & 3] = mk_handle((u32)t, gen);
         P.pc += 1;
         return XR_CONTINUE;
@@ -619,6 +626,60 @@ ITSB_COLD int exec_machine(Hdr* H, u32 p, u64 ins) {
         H->vol[SRC_G0 - 0x10 + (imm & 7)] = src_val(R, P, a);
         P.pc += 1;
         return XR_CONTINUE;
+    case OP_TLOAD:
+    case OP_TSTORE: {
+        const u32 idx = imm + src_val(R, P, b);
+        if (idx >= H->L.table_words) { fail(H, ITSB_ERR_BAD_OPCODE, P.pc); return XR_STOP; }
+        if (op == OP_TLOAD) P.r[a & 3] = R.tab[idx]; else R.tab[idx] = src_val(R, P, a);
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
+    case OP_ADD:
+        P.r[a & 3] = src_val(R, P, b) + src_val(R, P, c); P.pc += 1;
+        return XR_CONTINUE;
+    case OP_SUB:
+        P.r[a & 3] = src_val(R, P, b) - src_val(R, P, c); P.pc += 1;
+        return XR_CONTINUE;
+    case OP_JLTU:
+        P.pc = (src_val(R, P, a) < src_val(R, P, b)) ? (u16)imm : (u16)(P.pc + 1);
+        return XR_CONTINUE;
+    case OP_XNOW: {
+        const u64 bits = dbits(H->now);
+        X.x[0] = (u32)bits; X.x[1] = (u32)(bits >> 32);
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
+    case OP_XSET: {
+        const u64 bits = dbits(R.m.consts[imm & 0xFFFF]);
+        X.x[2] = (u32)bits; X.x[3] = (u32)(bits >> 32);
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
+    case OP_XELAPSE: {
+        const double before = bitsd(((u64)X.x[1] << 32) | X.x[0]);
+        const double remaining = bitsd(((u64)X.x[3] << 32) | X.x[2]) - (H->now - before);
+        const u64 bits = dbits(remaining);
+        X.x[2] = (u32)bits; X.x[3] = (u32)(bits >> 32);
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
+    case OP_JXLE0: {
+        const double remaining = bitsd(((u64)X.x[3] << 32) | X.x[2]);
+        P.pc = !(remaining > 0.0) ? (u16)imm : (u16)(P.pc + 1);
+        return XR_CONTINUE;
+    }
+    case OP_SETADDR:
+    case OP_GETADDR: {
+        const u32 fl = R.m.nodes[P.node].flags;
+        const u32 ifx = (fl & 0xFFFF) + ((fl >> 16) > 1 ? 1 : 0);
+        if (op == OP_GETADDR) P.r[a & 3] = R.iface_addr[ifx];
+        else {
+            const itsb_net NET = R.m.nets[R.m.ifaces[ifx].net];
+            R.iface_addr[ifx] = NET.cidr_net + (src_val(R, P, a) & ~NET.cidr_mask);   /* as_address(ar, cidr) */
+        }
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
     default:
         fail(H, ITSB_ERR_BAD_OPCODE, P.pc);
         return XR_STOP;
@@ -636,9 +697,9 @@ ITSB_FN u32 machine_unwind(Rep& R, u32 p, u32 exc) {
         waiters_unlink(R, S.head, S.tail, p);
     }
     const u32 op = (u32)(R.m.code[P.pc] & 0xFF);
-    if (op == OP_RECVT || op == OP_JOIN || op == OP_PWAIT || op == OP_SIG_WAIT) {
+    if (op == OP_RECVT || op == OP_RECVT_X || op == OP_JOIN || op == OP_PWAIT || op == OP_SIG_WAIT) {
         cancel_balker(R, p);
-        if (op == OP_RECVT && P.phase == 1) select_cleanup(R, p);
+        if ((op == OP_RECVT || op == OP_RECVT_X) && P.phase == 1) select_cleanup(R, p);
         if (exc == EXC_GS_TIMEOUT && op != OP_SIG_WAIT) exc = EXC_ITSIM_TIMEOUT;
     }
     return exc;

@@ -15,13 +15,14 @@ import numpy as np
  OP_ADVANCE, OP_ADVANCE_C, OP_OPEN, OP_CLOSE, OP_SEND, OP_RECV, OP_WAIT_AWAKE, OP_JASLEEP, OP_NODE_SLEEP,
  OP_NODE_WAKE, OP_SPAWN, OP_THROW, OP_LIST_CLEAR, OP_LIST_PUSH, OP_LIST_TAKE, OP_STAT, OP_RECV_FILTER,
  OP_BIND, OP_SCLOSE, OP_SENDL, OP_RECVT, OP_ADVANCE_X, OP_THREAD_EXIT, OP_CLONE, OP_FORK, OP_JOIN, OP_PWAIT, OP_TKILL,
- OP_PKILL, OP_MARK, OP_SIG_WAIT, OP_SIG_ON, OP_GSET, OP_NOW_SUB, OP_ADVANCE_X2) = range(47)
+ OP_PKILL, OP_MARK, OP_SIG_WAIT, OP_SIG_ON, OP_GSET, OP_NOW_SUB, OP_ADVANCE_X2, OP_TLOAD, OP_TSTORE, OP_ADD, OP_SUB,
+ OP_JLTU, OP_XNOW, OP_XSET, OP_XELAPSE, OP_JXLE0, OP_RECVT_X, OP_SETADDR, OP_GETADDR) = range(59)
 
 PROG_HIDDEN_BALK, PROG_HIDDEN_WAIT_ONE = 0xF1, 0xF2
 
 # operand sources
 R0, R1, R2, R3 = 0, 1, 2, 3
-PKT_SRC_IP, PKT_SRC_PORT, PKT_SIZE, PKT_TAG, PKT_F0, PKT_F1 = 0x10, 0x11, 0x12, 0x13, 0x14, 0x15
+PKT_SRC_IP, PKT_SRC_PORT, PKT_SIZE, PKT_TAG, PKT_F0, PKT_F1, PKT_DST_IP = 0x10, 0x11, 0x12, 0x13, 0x14, 0x15, 0x16
 ENT_IP, ENT_PORT = 0x18, 0x19
 NODE_ADDR, NODE_INDEX, NODE_HOST, NODE_EPOCH, NODE_BCAST, SELF, EXC = 0x20, 0x21, 0x22, 0x23, 0x24, 0x25, 0x26
 SELF_THREAD, SELF_TASK, PID = 0x27, 0x28, 0x29
@@ -123,6 +124,8 @@ class Asm:
             return 0
         if isinstance(target, int):
             return target
+        if target.startswith("/"):
+            return ("label", target[1:])        # absolute: "/program.label"
         return ("label", self._scope + target)
 
     # -- instructions --------------------------------------------------------------------------------------
@@ -145,7 +148,10 @@ class Asm:
         self._emit(OP_ADVANCE_C, imm=("hi16", self._h(handler), const_index))
 
     # shipped-itsim primitives
-    def bind(self, port: int = 0) -> None: self._emit(OP_BIND, imm=port)
+    def bind(self, port: int = 0, detached: bool = False) -> None:
+        """``detached``: the socket outlives the binding process (``run_networking_daemon`` binds at set-up and
+        hands the socket to a chain of threads, node.py:340-348)."""
+        self._emit(OP_BIND, 1 if detached else 0, imm=port)
     def sclose(self) -> None: self._emit(OP_SCLOSE)
 
     def sendl(self, dst_mode: int, size_src: int, tag: int, port: int = 0, f0: int = NONE, f1: int = NONE,
@@ -174,6 +180,22 @@ class Asm:
     def now_sub(self, const_index: int) -> None: self._emit(OP_NOW_SUB, imm=const_index)
     def advance_x2(self, handler: Optional[Target] = None) -> None:
         self._emit(OP_ADVANCE_X2, imm=("hi16", self._h(handler), 0))
+
+    def tload(self, rd: int, index_src: int, base: int = 0) -> None: self._emit(OP_TLOAD, rd, index_src, imm=base)
+    def tstore(self, value_src: int, index_src: int, base: int = 0) -> None: self._emit(OP_TSTORE, value_src, index_src, imm=base)
+    def add(self, rd: int, a: int, b: int) -> None: self._emit(OP_ADD, rd, a, b)
+    def sub(self, rd: int, a: int, b: int) -> None: self._emit(OP_SUB, rd, a, b)
+    def jltu(self, a: int, b: int, target: Target) -> None: self._emit(OP_JLTU, a, b, imm=self._t(target))
+    def xnow(self) -> None: self._emit(OP_XNOW)
+    def xset(self, const_index: int) -> None: self._emit(OP_XSET, imm=const_index)
+    def xelapse(self) -> None: self._emit(OP_XELAPSE)
+    def jxle0(self, target: Target) -> None: self._emit(OP_JXLE0, imm=self._t(target))
+
+    def recvt_x(self, handler: Optional[Target] = None) -> None:
+        self._emit(OP_RECVT_X, imm=("hi16", self._h(handler), 0))
+
+    def setaddr(self, src: int) -> None: self._emit(OP_SETADDR, src)
+    def getaddr(self, rd: int) -> None: self._emit(OP_GETADDR, rd)
 
     def open(self, port: int = 0) -> None: self._emit(OP_OPEN, imm=port)
     def close(self) -> None: self._emit(OP_CLOSE)

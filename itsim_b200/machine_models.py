@@ -5,8 +5,10 @@ assembles the test's process bodies, citing the lines it follows.  ``oracle/mach
 reference's own bodies for the same scenarios; ``tests/`` compare the two event for event.
 """
 from . import ir
-from .ir import (DST_BCAST, DST_PKT_SRC, DST_REGS, EXC, EXC_ITSIM_TIMEOUT, G1, R0, R1, R2, R3, SELF_TASK)
-from .machine import Endpoint, Link, as_address
+from .ir import (DST_BCAST, DST_PKT_SRC, DST_REGS, EXC, EXC_ITSIM_TIMEOUT, G1, G6, NODE_INDEX, PKT_DST_IP, PKT_F0,
+                 PKT_F1, PKT_TAG, R0, R1, R2, R3, SELF_TASK, ZERO)
+from .machine import Endpoint, Link, Router, as_address
+from .random import normal, num_bytes
 from .model import Simulator
 from .random import constant, uniform
 from .units import MS, MbPS, S
@@ -227,5 +229,165 @@ def link_delay(trace_records: int = 64) -> Simulator:
     return sim
 
 
-SCENARIOS = {"packet_transfer": packet_transfer, "broadcast": broadcast, "thread_lifecycle": thread_lifecycle,
+# DHCP message types (itsim/network/service/dhcp/__init__.py:17-22) and the server's tables in the model table
+DHCP_DISCOVER, DHCP_OFFER, DHCP_REQUEST, DHCP_ACK = 1, 2, 3, 4
+T_CURSOR, T_UNIQUE, T_ALLOC_ADDR, T_ALLOC_UNIQ, T_ALLOC_CONF, T_RESERVED = 0, 1, 8, 72, 136, 200
+T_RESERVED_SLOTS = 256
+
+
+def dhcp_exchange(trace_records: int = 8192, clients: int = 3) -> Simulator:
+    """tests/integ/test_dhcp_exchange.py:17-38: DHCPServer(100, cidr, gateway) behind Router.networking_daemon(UDP, 67),
+    `clients` endpoints at address 0 running DHCPClient.  Bodies: itsim/network/service/dhcp/server.py:97-206,
+    client.py:58-174, itsim/machine/node.py:319-350 (forward_recv)."""
+    sim = Simulator()
+    a = sim.asm
+    link = Link("10.1.128.0/18", uniform(100 * MS, 200 * MS), constant(100 * MbPS))
+    num_host_first = 100
+    upper_num_host = int(link.cidr.hostmask)                      # server.py:67
+    num_hosts_max = upper_num_host - num_host_first               # server.py:73
+    first_address = int(link.cidr.network_address) + num_host_first
+    c0, c30 = sim.const(0.0), sim.const(30 * S)                   # RESERVATION_TIME
+    d_size = sim.dist(num_bytes(normal(100.0, 30.0), header=240))  # client.py:47-49, server.py:73-75
+    assert num_hosts_max < 65536 and clients < 60
+
+    # ---- Node.run_networking_daemon (node.py:340-348) + DHCPServer.on_packet -----------------------------------
+    a.thread_program("dhcp_listen_first", 1)
+    a.bind(67, detached=True)                                     # new_sock = self.bind(protocol, port)
+    a.jmp("/dhcp_listen.body")
+    a.end_thread_program()
+
+    a.thread_program("dhcp_listen", 1)
+    a.label("body")                                               # forward_recv:
+    a.recvt()                                                     #   packet = socket.recv()
+    a.clone("dhcp_listen", c0)                                    #   context.thread.clone(forward_recv, socket)
+    a.jeqi(PKT_TAG, DHCP_DISCOVER, "discover")                    #   daemon.trigger -> on_packet (server.py:97-132)
+    a.jeqi(PKT_TAG, DHCP_REQUEST, "request")
+    a.jmp("end")
+    # _handle_discover (server.py:134-176)
+    a.label("discover")
+    a.mov(R0, PKT_F0)                                             # node_id
+    a.jnei(PKT_F1, 0, "given")                                    # address_maybe (never sent by the reference client)
+    a.li(R3, 0)
+    a.label("scan")                                               # for _ in range(num_hosts_max):
+    a.tload(R2, ZERO, T_CURSOR)                                   #   suggestion = next(self._seq_num_hosts)
+    a.mov(R1, R2)
+    a.addi(R2, R2, 1)
+    a.jnei(R2, num_hosts_max, "nowrap")
+    a.li(R2, 0)
+    a.label("nowrap")
+    a.tstore(R2, ZERO, T_CURSOR)
+    a.jltu(R1, G6, "in_table")                                    #   (table holds T_RESERVED_SLOTS addresses)
+    a.jmp("found")
+    a.label("in_table")
+    a.tload(R2, R1, T_RESERVED)                                   #   if suggestion not in self._reserved: break
+    a.jeqi(R2, 0, "found")
+    a.addi(R3, R3, 1)
+    a.jnei(R3, num_hosts_max, "scan")
+    a.jmp("end")                                                  # else: decline
+    a.label("found")
+    a.addi(R1, R1, first_address)
+    a.label("have")
+    a.tload(R2, ZERO, T_UNIQUE)                                   # _AddressAllocation(suggestion): fresh unique
+    a.addi(R2, R2, 1)
+    a.tstore(R2, ZERO, T_UNIQUE)
+    a.tstore(R1, R0, T_ALLOC_ADDR)
+    a.tstore(R2, R0, T_ALLOC_UNIQ)
+    a.tstore(ZERO, R0, T_ALLOC_CONF)
+    a.addi(R3, R1, -first_address)
+    a.tstore(R2, R3, T_RESERVED)                                  # self._reserved[suggestion] = True
+    a.drawi(R3, d_size)
+    a.sendl(DST_BCAST, R3, DHCP_OFFER, port=68, f0=R0, f1=R1)     # OFFER to the broadcast address
+    a.advance_const(c30)                                          # advance(self._reservation_time)
+    a.tload(R3, R0, T_ALLOC_CONF)                                 # if not confirmed and unique unchanged: forget it
+    a.jnei(R3, 0, "end")
+    a.tload(R3, R0, T_ALLOC_UNIQ)
+    a.jne(R3, R2, "end")
+    a.tload(R1, R0, T_ALLOC_ADDR)
+    a.addi(R3, R1, -first_address)
+    a.tstore(ZERO, R3, T_RESERVED)
+    a.tstore(ZERO, R0, T_ALLOC_ADDR)
+    a.jmp("end")
+    a.label("given")
+    a.mov(R1, PKT_F1)
+    a.jmp("have")
+    # _handle_request (server.py:178-206)
+    a.label("request")
+    a.jeqi(PKT_F1, 0, "end")
+    a.mov(R0, PKT_F0)
+    a.mov(R1, PKT_F1)
+    a.tload(R2, R0, T_ALLOC_ADDR)
+    a.jeqi(R2, 0, "end")                                          # node_id not in self._address_allocation
+    a.jne(R2, R1, "end")                                          # spurious REQUEST
+    a.li(R3, 1)
+    a.tstore(R3, R0, T_ALLOC_CONF)
+    a.drawi(R3, d_size)
+    a.gset(5, R3)
+    a.mov(R2, R1)
+    a.li(R3, 68)
+    a.sendl(DST_REGS, ir.G0 + 5, DHCP_ACK, f0=R0, f1=R1)          # ACK, unicast to the address
+    a.label("end")
+    a.end_thread_program()
+
+    # ---- DHCPClient.run_client (client.py:58-174) -----------------------------------------------------------------
+    a.thread_program("dhcp_client", 2)
+    a.li(R0, T_RESERVED_SLOTS)
+    a.gset(6, R0)                                                 # (constant for the server's table bound)
+    a.addi(R0, NODE_INDEX, 1)                                     # node_id = context.process.node.uuid
+    for attempt in range(3):                                      # for _ in range(self._dhcp_client_retries):
+        t = f"a{attempt}_"
+        a.bind(68)                                                # with context.node.bind(UDP, client_port, pid):
+        a.drawi(R1, d_size)                                       # _dhcp_discover
+        a.sendl(DST_BCAST, R1, DHCP_DISCOVER, port=67, f0=R0)
+        a.xset(c30)                                               # _dhcp_iter_responses(OFFER)
+        a.label(t + "offers")
+        a.jxle0(t + "failed")
+        a.xnow()
+        a.recvt_x(handler=t + "offer_exc")
+        a.xelapse()
+        a.jnei(PKT_TAG, DHCP_OFFER, t + "offers")
+        a.jne(PKT_F0, R0, t + "offers")
+        a.jeqi(PKT_F1, 0, t + "offers")                           # if Field.ADDRESS in packet.payload
+        a.mov(R1, PKT_F1)                                         # _dhcp_request(address_proposed)
+        a.drawi(R2, d_size)
+        a.sendl(DST_BCAST, R2, DHCP_REQUEST, port=67, f0=R0, f1=R1)
+        a.getaddr(R3)                                             # address_orig
+        a.setaddr(R1)                                             # tentatively take the address
+        a.xset(c30)                                               # _dhcp_iter_responses(ACK)
+        a.label(t + "acks")
+        a.jxle0(t + "unconfirmed")
+        a.xnow()
+        a.recvt_x(handler=t + "ack_exc")
+        a.xelapse()
+        a.jnei(PKT_TAG, DHCP_ACK, t + "acks")
+        a.jne(PKT_F0, R0, t + "acks")
+        a.jne(PKT_DST_IP, R1, t + "acks")                         # packet.dest == address_proposed
+        a.sclose()
+        a.jmp("done")                                             # return True -> break
+        a.label(t + "ack_exc")
+        a.jnei(EXC, EXC_ITSIM_TIMEOUT, "cleanup_raise")           # except Timeout: return (generator ends)
+        a.label(t + "unconfirmed")
+        a.setaddr(R3)                                             # self._interface.address = address_orig
+        a.sclose()
+        a.jmp(t + "next")
+        a.label(t + "offer_exc")
+        a.jnei(EXC, EXC_ITSIM_TIMEOUT, "cleanup_raise")
+        a.label(t + "failed")
+        a.sclose()
+        a.label(t + "next")
+    a.label("done")
+    a.end_thread_program()
+    a.label("cleanup_raise")
+    a.sclose()
+    a.reraise()
+
+    router = Router().connected_to_static(link, "10.1.128.1")
+    router.run_proc(sim, "dhcp_listen_first")
+    for _ in range(clients):
+        Endpoint().connected_to_static(link, as_address(None)).run_proc_in(sim, 0.0, "dhcp_client")
+    _caps(sim, trace_records)
+    sim.caps["table_words"] = T_RESERVED + T_RESERVED_SLOTS
+    return sim
+
+
+SCENARIOS = {"dhcp_exchange": dhcp_exchange, "packet_transfer": packet_transfer, "broadcast": broadcast, "thread_lifecycle": thread_lifecycle,
              "process_lifecycle": process_lifecycle, "link_delay": link_delay}

@@ -206,7 +206,8 @@ def build(cidr: str = "192.168.4.0/24", num_endpoints: Optional[int] = None, tra
         ws.install("mdns" if n <= num_mdns else "llmnr")   # sic, network_simple.py:380
     sim.caps["trace_records"] = trace_records
     # per-replica shared-memory budget (every structure continues in the HBM arena when it fills, except the
-    # process and socket tables): 148 resident processes + 76 transient ones (19 query rounds in flight at once)
-    sim.caps.update(max_events=128, max_procs=224, max_sockets=104)
+    # process and socket tables): 148 resident processes + 72 transient ones (18 query rounds in flight at once);
+    # sized so that 12 replicas (warps) fit one SM's shared memory
+    sim.caps.update(max_events=128, max_procs=220, max_sockets=96)
     sim.num_workstations = num_workstations
     return sim

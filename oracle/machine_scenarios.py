@@ -276,9 +276,39 @@ def process_lifecycle():
     return sc.result()
 
 
+PROGS_DHCP = {"forward_recv": 1, "trigger": 2}
+
+
+def dhcp_exchange(seed: int = 0, replica: int = 0, duration: float = 10.0, clients: int = 3):
+    """tests/integ/test_dhcp_exchange.py:17-38 -- the reference's DHCPServer behind a networking daemon on a Router,
+    `clients` endpoints running the reference's DHCPClient; known answer: they end up with hosts 100, 101, 102."""
+    from greensim.random import uniform, constant
+    from itsim.machine.endpoint import Endpoint
+    from itsim.network.link import Link
+    from itsim.network.router import Router
+    from itsim.network.service.dhcp.client import DHCPClient
+    from itsim.network.service.dhcp.server import DHCPServer
+    from itsim.types import Protocol, as_address
+    from itsim.units import MS, MbPS
+    sc = Scenario(PROGS_DHCP, seed, replica)
+    link = Link("10.1.128.0/18", uniform(100 * MS, 200 * MS), constant(100 * MbPS))
+    router = sc.node(Router().connected_to_static(link, "10.1.128.1"))
+    router.networking_daemon(sc.sim, Protocol.UDP, 67)(DHCPServer(100, link.cidr, as_address("10.1.128.1")))
+    endpoints = [sc.node(Endpoint().connected_to_static(link, as_address(None))) for _ in range(clients)]
+    for endpoint in endpoints:
+        endpoint.schedule_daemon_in(sc.sim, 0.0, DHCPClient(endpoint._interfaces[link.cidr]))
+    sc.run(duration)
+    got = sorted(int(a) - int(link.cidr.network_address) for e in endpoints for a in e.addresses() if not a.is_loopback)
+    arr, out = sc.result()
+    out["hosts"] = got
+    if clients == 3 and duration >= 10.0:
+        assert got == [100, 101, 102], got
+    return arr, out
+
+
 SCENARIOS: Dict[str, Callable] = {
     "packet_transfer": packet_transfer, "broadcast": broadcast, "thread_lifecycle": thread_lifecycle,
-    "process_lifecycle": process_lifecycle,
+    "process_lifecycle": process_lifecycle, "dhcp_exchange": dhcp_exchange,
 }
 
 if __name__ == "__main__":

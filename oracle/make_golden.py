@@ -45,7 +45,8 @@ def machine_golden() -> None:
     out = {}
     jobs = [("thread_lifecycle", {}), ("process_lifecycle", {}),
             ("packet_transfer", {"seed": 0, "replica": 0}), ("packet_transfer", {"seed": 5, "replica": 77}),
-            ("broadcast", {"seed": 0, "replica": 0}), ("broadcast", {"seed": 3, "replica": 11, "duration": 60.0})]
+            ("broadcast", {"seed": 0, "replica": 0}), ("broadcast", {"seed": 3, "replica": 11, "duration": 60.0}),
+            ("dhcp_exchange", {"seed": 0, "replica": 0}), ("dhcp_exchange", {"seed": 4, "replica": 9, "duration": 100.0})]
     for name, kwargs in jobs:
         arr, summary = ms.SCENARIOS[name](**kwargs)
         tag = name + "".join(f"_{k[0]}{int(v)}" for k, v in kwargs.items())

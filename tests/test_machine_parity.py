@@ -20,6 +20,8 @@ CASES = [
     ("packet_transfer", "machine_packet_transfer_s5_r77.npz", 5, 77, 10.0),
     ("broadcast", "machine_broadcast_s0_r0.npz", 0, 0, 10.0),
     ("broadcast", "machine_broadcast_s3_r11_d60.npz", 3, 11, 60.0),
+    ("dhcp_exchange", "machine_dhcp_exchange_s0_r0.npz", 0, 0, 10.0),       # reference DHCPClient / DHCPServer classes
+    ("dhcp_exchange", "machine_dhcp_exchange_s4_r9_d100.npz", 4, 9, 100.0),
 ]
 
 
@@ -54,6 +56,17 @@ def test_known_answers_of_the_reference(hostemu):
     tr = eng.trace(0)
     marks = {int(r["aux"]): float(r["t"]) for r in tr if r["kind"] == L.TRACE_MARK}
     assert marks == {2: 130.0, 1: 730.0, 3: 1042.0, 5: 3042.0}     # Abel, Cain, Seth die; adameve gives up on Humanity
+    # tests/integ/test_dhcp_exchange.py:38: the three clients end up with hosts 100, 101, 102 -- each ACK is unicast to
+    # the address the client took, so an accepted unicast delivery per host proves it
+    eng = run_scenario("dhcp_exchange", 0, 0, 10.0, lib=hostemu)
+    tm = eng.replica_telemetry(0)
+    tr = eng.trace(0)
+    acks = [r for r in tr if r["kind"] == L.EV_DELIVER and r["node"] != 0 and r["aux"] & 0x80000000]
+    unicast_acks = [r for i, r in enumerate(tr) if r["kind"] == L.EV_DELIVER and r["aux"] & 0x80000000 and r["node"] != 0
+                    and not (i + 1 < len(tr) and tr[i + 1]["kind"] == L.EV_DELIVER and tr[i + 1]["t"] == r["t"])
+                    and not (i > 0 and tr[i - 1]["kind"] == L.EV_DELIVER and tr[i - 1]["t"] == r["t"])]
+    assert sorted(int(r["node"]) for r in unicast_acks) == [1, 2, 3]
+    assert int(tm[L.TM_PACKETS_SENT]) == 12 and len(acks) >= 3      # 3 x (DISCOVER, OFFER, REQUEST, ACK)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/itsim"), reason="reference tree not on this box")
