@@ -178,6 +178,8 @@ def main() -> None:
     ap.add_argument("--max-events", type=int, default=0, help="future-event pool slots per replica (0 = model default)")
     ap.add_argument("--max-procs", type=int, default=0)
     ap.add_argument("--max-sockets", type=int, default=0)
+    ap.add_argument("--workload", default="network_simple", choices=["network_simple", "malware"],
+                    help="malware = network_simple + the beaconing-malware overlay (BASELINE.json config 3)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -222,7 +224,7 @@ def main() -> None:
 
     # ---- cold job through the public API: compile, upload, allocate, initialise --------------------------------
     t_cold0 = time.perf_counter()
-    sim = netsimple.build()
+    sim = netsimple.build() if args.workload == "network_simple" else netsimple.build_malware()
     sim.caps["arena_nodes"] = args.arena_nodes
     for key, val in (("max_events", args.max_events), ("max_procs", args.max_procs), ("max_sockets", args.max_sockets)):
         if val:
@@ -305,7 +307,7 @@ def main() -> None:
             "warmup": args.warmup, "ms_per_step": ms_dev_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"network_simple (50 endpoints, /24) x {args.replicas} replicas per GPU, "
+                "workload": f"{args.workload} (50 endpoints, /24) x {args.replicas} replicas per GPU, "
                             f"step = run({args.slice:g} simulated s) on every replica after {args.spinup:g} s spin-up",
                 "replicas_per_gpu": args.replicas, "slice_s": args.slice, "spinup_s": args.spinup, "seed": args.seed,
                 "events_per_step_per_gpu": events_per_step_gpu,

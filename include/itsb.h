@@ -152,6 +152,9 @@ typedef struct itsb_initproc {    /* process started at t=0, in program order   
 } itsb_initproc;
 #define ITSB_INIT_ADD      0
 #define ITSB_INIT_RUN_PROC 1
+#define ITSB_INIT_ADD_DRAWN 2  /* sim.add on node `node + next(dists[delay_const])`, drawn per replica at set-up
+                                  (infected = next(distribution(workstations)), malware_simple.py:114)            */
+#define ITSB_INIT_ADD_SAME  3  /* sim.add on the node the previous ITSB_INIT_ADD_DRAWN entry drew                 */
 
 typedef struct itsb_filter {      /* which received packets a RECV_FILTER loop hands to its program; the rest it
                                      consumes and loops (the daemon bodies' "not for me" branches,

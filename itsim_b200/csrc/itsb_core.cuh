@@ -252,7 +252,8 @@ struct Hdr {                /* first thing in the hot block */
     u64 ovf_min_t;
     u32 ovf_min_seq, ovf_head, ovf_count;
     u32 spare32;
-    u16 sig_free_top, thr_free_top, task_free_top, spare16b;
+    u16 sig_free_top, thr_free_top, task_free_top;
+    u16 setup_done;         /* the per-replica set-up draws (ITSB_INIT_ADD_DRAWN) have been made */
     u32 hidden_entry_balk, hidden_entry_wait_one;   /* entry indices of greensim's helper programs */
     /* -- binding: rewritten every time the replica is staged (pointers of this launch, not state) -- */
     ArenaNode* arena;
@@ -863,11 +864,10 @@ ITSB_FN Pkt* pkt_at(Rep& R, u32 k) { return (Pkt*)&R.arena[k]; }
 
 /* Socket.send -> Node._send_to_network -> Network.transmit (overrides.py:122-125,371-377,273-291): the packet
  * becomes a transmission process started with sim.add, i.e. one TX_BEGIN event at the current time. */
-ITSB_COLD void net_send(Hdr* H, u32 p, u32 dst_ip, u32 dst_port, u32 size, u32 tag, u32 f0, u32 f1) {
+ITSB_COLD void net_send(Hdr* H, u32 src_node, u32 src_port, u32 dst_ip, u32 dst_port, u32 size, u32 tag, u32 f0,
+                        u32 f1) {
     Rep R; rebind(R, H);
-    Pcb& P = R.pcb[p];
-    if (P.sock == NIL16) { fail(H, ITSB_EXC_SOCKET_CLOSED, P.pc); return; }
-    const itsb_node N = R.m.nodes[P.node];
+    const itsb_node N = R.m.nodes[src_node];
     const itsb_net NET = R.m.nets[N.net];
     if (dst_ip != NET.bcast) {
         bool found = false;   /* must be a member of the network (CannotForward otherwise, overrides.py:293-297) */
@@ -879,9 +879,9 @@ ITSB_COLD void net_send(Hdr* H, u32 p, u32 dst_ip, u32 dst_port, u32 size, u32 t
     if (k == NIL32) return;
     Pkt K;
     K.src_ip = N.addr; K.dst_ip = dst_ip;
-    K.ports = (u32)R.sock[P.sock].port | (dst_port << 16);
+    K.ports = src_port | (dst_port << 16);
     K.size = size; K.tag = tag; K.f0 = f0; K.f1 = f1;
-    K.meta = (u32)P.node | (N.net << 16);
+    K.meta = src_node | (N.net << 16);
     *pkt_at(R, k) = K;
     stat_add(R, ITSB_TM_PACKETS_SENT, 1);
     stat_add(R, ITSB_TM_BYTES_SENT, size);
@@ -1158,8 +1158,18 @@ ITSB_COLD int exec_cold(Hdr* H, u32 p, u64 ins) {
         default: dst_ip = P.r[2]; dst_port = P.r[3] & 0xFFFF; break;
         }
         u32 f0s = (imm >> 16) & 0xFF, f1s = (imm >> 24) & 0xFF;
-        net_send(H, p, dst_ip, dst_port, src_val(R, P, b), c,
+        if (P.sock == NIL16) { fail(H, ITSB_EXC_SOCKET_CLOSED, P.pc); return XR_STOP; }
+        net_send(H, P.node, R.sock[P.sock].port, dst_ip, dst_port, src_val(R, P, b), c,
                  f0s == SRC_NONE ? 0 : src_val(R, P, f0s), f1s == SRC_NONE ? 0 : src_val(R, P, f1s));
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
+    case OP_FORWARD: {
+        /* world_socket.send(dest, msg.byte_size, msg.payload) from another attachment of this machine
+           (malware_simple.py:101-107): source = (address of node imm[0:16], port imm[16:32]), dest = (r2, r3) */
+        const u32* v = H->vol;
+        net_send(H, imm & 0xFFFF, imm >> 16, P.r[2], P.r[3] & 0xFFFF, v[SRC_PKT_SIZE - 0x10], v[SRC_PKT_TAG - 0x10],
+                 v[SRC_PKT_F0 - 0x10], v[SRC_PKT_F1 - 0x10]);
         P.pc += 1;
         return XR_CONTINUE;
     }
@@ -1359,6 +1369,23 @@ ITSB_COLD u32 deliver_exception(Hdr* H, u32 p, u32 exc) {
     return p;
 }
 
+/* Set-up time draws: `infected = next(distribution(workstation_list))` (malware_simple.py:114) happens before the
+ * run, from the replica's own stream; the installed process i sits in slot i of a fresh replica. */
+ITSB_COLD void replica_setup(Hdr* H) {
+    Rep R; rebind(R, H);
+    H->setup_done = 1;
+    u32 drawn = 0;
+    for (u32 i = 0; i < R.m.n_init; ++i) {
+        const itsb_initproc I = R.m.init[i];
+        if (I.mode == ITSB_INIT_ADD_DRAWN) {
+            drawn = I.node + (u32)(long long)draw_dist(H, &R.m.dists[I.delay_const]);
+            R.pcb[i].node = (u16)drawn;
+        } else if (I.mode == ITSB_INIT_ADD_SAME) {
+            R.pcb[i].node = (u16)drawn;
+        }
+    }
+}
+
 ITSB_FN u64 events_counted(Rep& R) {
     u64 n = 0;
     for (u32 k = 0; k < ITSB_NUM_KINDS; ++k) n += R.stats[ITSB_TM_KIND0 + k];
@@ -1370,6 +1397,7 @@ ITSB_FN u64 events_counted(Rep& R) {
 ITSB_FN u64 run_replica(Rep& R, double duration) {
     Hdr* H = R.hdr;
     if (H->status != 0) return 0;
+    if (!H->setup_done) replica_setup(H);
     const u64 events_before = events_counted(R);
     /* run(duration): a finite duration schedules the stop event first (it takes a counter value); run() without
        one ends when the heap is empty and leaves the clock where it is */
@@ -1459,7 +1487,7 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
     for (u32 i = 0; i < ITSB_TM_SIZE; ++i) R.stats[i] = 0;
     H->arena_free_top = L->arena_nodes;
     H->sig_free_top = (u16)L->max_sig; H->thr_free_top = (u16)L->max_thr; H->task_free_top = (u16)L->max_task;
-    H->spare16b = 0;
+    H->setup_done = 0;
     H->hidden_entry_balk = 0; H->hidden_entry_wait_one = 0;
     for (u32 i = 0; i < R.m.n_entries; ++i) {
         if (R.m.entries[i].prog == PROG_HIDDEN_BALK) H->hidden_entry_balk = i;

@@ -119,6 +119,11 @@ static inline bool validate_model(const itsb_model_desc& d, const void* const* b
     }
     for (uint32_t i = 0; i < d.n_init; ++i)
         if (ip[i].mode == ITSB_INIT_RUN_PROC && (!machine || ip[i].delay_const >= d.n_consts)) { why = "run_proc init entry invalid"; return false; }
+    for (uint32_t i = 0; i < d.n_init; ++i) {
+        if (ip[i].mode > ITSB_INIT_ADD_SAME) { why = "init mode out of range"; return false; }
+        if (ip[i].mode == ITSB_INIT_ADD_DRAWN && ip[i].delay_const >= d.n_dists) { why = "drawn init entry without a generator"; return false; }
+        if (ip[i].mode == ITSB_INIT_ADD_SAME && i == 0) { why = "ITSB_INIT_ADD_SAME without a drawn entry before it"; return false; }
+    }
     bool has_balk = false, has_wait_one = false;
     for (uint32_t i = 0; i < d.n_entries; ++i) { has_balk |= en[i].prog == PROG_HIDDEN_BALK; has_wait_one |= en[i].prog == PROG_HIDDEN_WAIT_ONE; }
     if (machine && !(has_balk && has_wait_one)) { why = "shipped-itsim model without the greensim helper programs"; return false; }

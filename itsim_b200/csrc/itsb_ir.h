@@ -80,6 +80,8 @@ enum {
     OP_SETADDR = 57,    /* interface.address = src(a), re-rooted in the link's CIDR (first non-loopback interface)
                                                                                   interface.py:50-57; client.py:147 */
     OP_GETADDR = 58,    /* r[a] = interface.address                                              client.py:144        */
+    OP_FORWARD = 59,    /* send the packet just received on, from (address of node imm[0:16], port imm[16:32]) to
+                           (r2, r3): the one-way router of malware_simple.py:96-107                                  */
     OP_COUNT
 };
 

@@ -469,7 +469,10 @@ ITSB_COLD int exec_machine(Hdr* H, u32 p, u64 ins) {
     PcbX& X = R.pcbx[p];
     const u32 op = (u32)(ins & 0xFF), a = (u32)((ins >> 8) & 0xFF), b = (u32)((ins >> 16) & 0xFF),
               c = (u32)((ins >> 24) & 0xFF), imm = (u32)(ins >> 32);
-    if (H->L.max_sig == 0) { fail(H, ITSB_ERR_BAD_OPCODE, P.pc); return XR_STOP; }
+    /* the thread / signal / link instructions need their tables; the small generic helpers do not */
+    const bool generic = op == OP_MARK || op == OP_GSET || op == OP_TLOAD || op == OP_TSTORE || op == OP_ADD ||
+                         op == OP_SUB || op == OP_JLTU;
+    if (H->L.max_sig == 0 && !generic) { fail(H, ITSB_ERR_BAD_OPCODE, P.pc); return XR_STOP; }
     switch (op) {
     case OP_BIND:
         if (m_bind(H, p, imm & 0xFFFF) < 0) return XR_STOP;

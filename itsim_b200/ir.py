@@ -16,7 +16,7 @@ import numpy as np
  OP_NODE_WAKE, OP_SPAWN, OP_THROW, OP_LIST_CLEAR, OP_LIST_PUSH, OP_LIST_TAKE, OP_STAT, OP_RECV_FILTER,
  OP_BIND, OP_SCLOSE, OP_SENDL, OP_RECVT, OP_ADVANCE_X, OP_THREAD_EXIT, OP_CLONE, OP_FORK, OP_JOIN, OP_PWAIT, OP_TKILL,
  OP_PKILL, OP_MARK, OP_SIG_WAIT, OP_SIG_ON, OP_GSET, OP_NOW_SUB, OP_ADVANCE_X2, OP_TLOAD, OP_TSTORE, OP_ADD, OP_SUB,
- OP_JLTU, OP_XNOW, OP_XSET, OP_XELAPSE, OP_JXLE0, OP_RECVT_X, OP_SETADDR, OP_GETADDR) = range(59)
+ OP_JLTU, OP_XNOW, OP_XSET, OP_XELAPSE, OP_JXLE0, OP_RECVT_X, OP_SETADDR, OP_GETADDR, OP_FORWARD) = range(60)
 
 PROG_HIDDEN_BALK, PROG_HIDDEN_WAIT_ONE = 0xF1, 0xF2
 
@@ -194,6 +194,11 @@ class Asm:
     def recvt_x(self, handler: Optional[Target] = None) -> None:
         self._emit(OP_RECVT_X, imm=("hi16", self._h(handler), 0))
 
+    def forward(self, from_node: object, from_port: int) -> None:
+        """Relay the packet just received from another attachment of the machine (node object resolved at
+        compile time) to (r2, r3)."""
+        self._emit(OP_FORWARD, imm=("node_port", from_node, from_port))
+
     def setaddr(self, src: int) -> None: self._emit(OP_SETADDR, src)
     def getaddr(self, rd: int) -> None: self._emit(OP_GETADDR, rd)
 
@@ -239,6 +244,8 @@ class Asm:
                 return (self._resolve(v[2]) & 0xFFFF) | (self._resolve(v[1]) << 16)
             if v[0] == "lo16":
                 return (self._resolve(v[1]) & 0xFFFF) | ((self._resolve(v[2]) & 0xFFFF) << 16)
+            if v[0] == "node_port":
+                return (v[1].index & 0xFFFF) | ((v[2] & 0xFFFF) << 16)
         raise TypeError(v)
 
     def assemble(self) -> Tuple[np.ndarray, np.ndarray]:

@@ -121,12 +121,6 @@ class Simulator:
         if self._machine_procs:
             from .machine import compile_machine
             return compile_machine(self)
-        code, entries_raw = self.asm.assemble()
-        entries = np.zeros(len(entries_raw), dtype=L.ENTRY_DTYPE)
-        entries["pc"], entries["prog"] = entries_raw[:, 0], entries_raw[:, 1]
-        dists = np.zeros(len(self._dists), dtype=L.DIST_DTYPE)
-        for i, d in enumerate(self._dists):
-            dists[i] = (d.kind, d.flags, d.p0, d.p1, d.slope, d.shift, d.lower, d.upper)
         consts = np.array(self._consts, dtype=np.float64)
         # nodes are numbered network by network, in link order, so a network's members are one index range
         order: List[Endpoint] = []
@@ -136,23 +130,29 @@ class Simulator:
             order.extend(net._members)
             nets[k] = (int(net.cidr.network_address), int(net.cidr.netmask), int(net.cidr.broadcast_address), first,
                        len(net._members), self.dist(net._latency), self.dist(net._bandwidth), net.mode)
-        dists = np.zeros(len(self._dists), dtype=L.DIST_DTYPE)   # networks may have added generators
-        for i, d in enumerate(self._dists):
-            dists[i] = (d.kind, d.flags, d.p0, d.p1, d.slope, d.shift, d.lower, d.upper)
         if len(order) != len(self.nodes):
             raise ValueError("every node must be linked to exactly one network")
         for idx, node in enumerate(order):
             node.index = idx
+        code, entries_raw = self.asm.assemble()     # after numbering: programs may name nodes
+        entries = np.zeros(len(entries_raw), dtype=L.ENTRY_DTYPE)
+        entries["pc"], entries["prog"] = entries_raw[:, 0], entries_raw[:, 1]
         nodes = np.zeros(len(order), dtype=L.NODE_DTYPE)
         for node in order:
             nodes[node.index] = (node.address, self.networks.index(node.network), node.host_id, 0)
         init = np.zeros(len(self._installed), dtype=L.INIT_DTYPE)
         for i, (program, node, regs) in enumerate(self._installed):
             r = list(regs) + [0] * (4 - len(regs))
-            init[i] = (self.asm.entry(program), node.index, r, 0, 0)
+            if isinstance(node, DrawnNode):
+                init[i] = (self.asm.entry(program), node.first.index, r, node.mode, self.dist(node.dist))
+            else:
+                init[i] = (self.asm.entry(program), node.index, r, 0, 0)
         filters = np.zeros(len(self._filters), dtype=L.FILTER_DTYPE)
         for i, (fa, fh, fl) in enumerate(self._filters):
             filters[i] = (fa, fh, fl, 0)
+        dists = np.zeros(len(self._dists), dtype=L.DIST_DTYPE)   # last: networks and drawn installs add generators
+        for i, d in enumerate(self._dists):
+            dists[i] = (d.kind, d.flags, d.p0, d.p1, d.slope, d.shift, d.lower, d.upper)
         return Compiled(code, entries, dists, consts, nets, nodes, init, filters, L.Caps(**self.caps))
 
     # -- running -------------------------------------------------------------------------------------------------
@@ -174,6 +174,26 @@ class Simulator:
 
     def now(self) -> float:
         return float(self._engine.now(0, 1)[0]) if self._engine is not None else 0.0
+
+
+class DrawnNode:
+    """A node chosen per replica at set-up with one draw from the replica's stream:
+    ``infected = next(distribution(workstation_list))`` (malware_simple.py:114).  ``install`` on it installs on
+    whichever node the replica drew; a second ``install`` lands on the same node."""
+
+    def __init__(self, sim: "Simulator", candidates: Sequence["Endpoint"]) -> None:
+        from .random import distribution_index
+        self.sim = sim
+        self.first = candidates[0]
+        self.dist = distribution_index(len(candidates))
+        self.mode = 2          # ITSB_INIT_ADD_DRAWN for the first install, ITSB_INIT_ADD_SAME afterwards
+        self._candidates = list(candidates)
+
+    def install(self, program: str, *regs: int) -> None:
+        drawn = DrawnNode.__new__(DrawnNode)
+        drawn.__dict__.update(self.__dict__)
+        self.sim._installed.append((program, drawn, regs))
+        self.mode = 3
 
 
 class Network:
@@ -232,6 +252,11 @@ class Endpoint:
 
     def install(self, program: str, *regs: int) -> None:
         self.sim._installed.append((program, self, regs))
+
+    def link_to(self, network: Network, ar: Optional[Any] = None) -> "Endpoint":
+        """``Node.link_to`` (overrides.py:307-312): a further address on another network.  The attachment is
+        numbered like a node of its own (a machine's attachments share nothing the engine needs to know about)."""
+        return Endpoint(f"{self.name}@{network.cidr}", network, ar, host_id=self.host_id)
 
 
 class Workstation(Endpoint):

@@ -10,19 +10,28 @@ from typing import Optional
 from . import ir
 from .ir import (DST_BCAST, DST_ENT, DST_PKT_SRC, DST_SELF, NODE_ADDR, NODE_HOST, PKT_F0, PKT_F1, PKT_SIZE, PKT_TAG,
                  R0, R1, R2, R3, SELF)
-from .model import Endpoint, Network, Simulator, Workstation
-from .random import constant, distribution_index, expo, normal, num_bytes
-from .units import B, GbPS, H, MIN, MS, US
+from .ir import G0, R0, R1, R2, R3  # noqa: F811
+from .ir import PKT_F0 as _PKT_F0, PKT_F1 as _PKT_F1, DST_REGS
+from .model import DrawnNode, Endpoint, Network, Simulator, Workstation
+from .random import bounded, constant, distribution_index, expo, normal, num_bytes
+from .units import B, GbPS, H, MIN, MS, MbPS, S, US
 
 # program ids reported in trace records (shared with oracle/netsimple.py)
 PROG_DHCP_SERVE, PROG_BLINKING, PROG_CLIENT, PROG_MDNS, PROG_LLMNR = 1, 2, 3, 4, 5
 PROG_QUERY_MDNS, PROG_QUERY_LLMNR, PROG_TIMEOUT_HELPER, PROG_TX, PROG_DELIVER = 6, 7, 8, 9, 10
+PROG_CALL_HOME, PROG_NO_GOOD, PROG_SUDO_TRANSMIT, PROG_EXFILTRATE, PROG_ROUTE, PROG_C2 = 11, 12, 13, 14, 15, 16
 
 # payload "content" values (network_simple.py:135-149,152-167,190-221)
 TAG_DISCOVER, TAG_OFFER, TAG_REQUEST, TAG_ACK, TAG_QUERY, TAG_RESOLVE, TAG_IAM = 1, 2, 3, 4, 5, 6, 7
+TAG_EXFIL = 8
 
 EXC_COMPLETE = 1          # Workstation._Complete (network_simple.py:78-79): a plain Exception, not an Interrupt
 STAT_QUERIES, STAT_RESOLVED, STAT_TIMEOUTS = 0, 1, 2
+STAT_BEACONS, STAT_ROUTED, STAT_C2_RECEIVED = 3, 4, 5
+
+BAD_NEWS_BEAR_ADDR = (1 << 24) | (2 << 16) | (3 << 8) | 4     # malware_simple.py:16-18
+BAD_NEWS_BEAR_PORT = 666
+LOCAL_ROUTER_PORT = 777
 
 NUM_ADDRESSES_RESERVED = 2
 MIN_NUM_ENDPOINTS = 3
@@ -188,7 +197,8 @@ def build(cidr: str = "192.168.4.0/24", num_endpoints: Optional[int] = None, tra
     if num_addresses < MIN_NUM_ENDPOINTS:
         raise ValueError(f"Unsuitable CIDR prefix for simulating a non-trivial network: {cidr}")
     net_local = Network(sim, cidr=cidr, bandwidth=constant(1 * GbPS), latency=normal(5 * MS, 1 * MS))
-    Endpoint("Router", net_local)
+    router = Endpoint("Router", net_local)
+    workstations = []
     if num_endpoints is None:
         num_endpoints = max(MIN_NUM_ENDPOINTS, int(0.2 * num_addresses))
     num_endpoints = max(MIN_NUM_ENDPOINTS, num_endpoints)
@@ -204,10 +214,80 @@ def build(cidr: str = "192.168.4.0/24", num_endpoints: Optional[int] = None, tra
         ws.install("blinking")
         ws.install("client")
         ws.install("mdns" if n <= num_mdns else "llmnr")   # sic, network_simple.py:380
+        workstations.append(ws)
+    sim.router, sim.workstations = router, workstations
     sim.caps["trace_records"] = trace_records
     # per-replica shared-memory budget (every structure continues in the HBM arena when it fills, except the
     # process and socket tables): 148 resident processes + 72 transient ones (18 query rounds in flight at once);
     # sized so that 12 replicas (warps) fit one SM's shared memory
     sim.caps.update(max_events=128, max_procs=220, max_sockets=96)
     sim.num_workstations = num_workstations
+    return sim
+
+
+def build_malware(trace_records: int = 0, fused: bool = True) -> Simulator:
+    """network_simple + the beaconing-malware overlay of ``examples/network_simple/malware_simple.py:53-125``
+    (BASELINE.json config 3).  One workstation drawn per replica at set-up runs ``call_home`` (beacon every expo(10) s)
+    and ``no_good`` (every expo(100) s); the router's ``route`` relays the 100-byte beacons over the ``Internet``
+    network (overrides.py:443-456) to the command-and-control host 1.2.3.4:666.  The overlay's own statistics are the
+    user counters STAT_BEACONS / STAT_ROUTED / STAT_C2_RECEIVED."""
+    sim = build(trace_records=trace_records, fused=fused)
+    a = sim.asm
+    www = Network(sim, "0.0.0.0/0", latency=bounded(expo(1 * S), lower=20 * MS), bandwidth=expo(10 * MbPS))
+    d_beacon, d_privileged = sim.dist(expo(10)), sim.dist(expo(100))
+    router_wan = sim.router.link_to(www)                          # malware_simple.py:117
+    bear = Endpoint("Mama Bear", www, BAD_NEWS_BEAR_ADDR)
+
+    a.program("call_home", PROG_CALL_HOME)                        # malware_simple.py:53-58
+    a.label("loop")
+    a.advance(d_beacon)
+    a.spawn("exfiltrate")
+    a.jmp("loop")
+
+    a.program("no_good", PROG_NO_GOOD)                            # :61-65
+    a.label("loop")
+    a.advance(d_privileged)
+    a.spawn("sudo_transmit")
+    a.jmp("loop")
+
+    a.program("sudo_transmit", PROG_SUDO_TRANSMIT)                # :68-72
+    a.spawn("exfiltrate")
+    a.exit()
+
+    a.program("exfiltrate", PROG_EXFILTRATE)                      # :75-82
+    a.stat(STAT_BEACONS)
+    a.open(BAD_NEWS_BEAR_PORT)
+    a.li(R1, BAD_NEWS_BEAR_PORT)
+    a.gset(1, R1)                                                 # payload["dest_addr"] = Location(1.2.3.4, 666)
+    a.li(R1, BAD_NEWS_BEAR_ADDR)
+    a.li(R2, sim.router.address)
+    a.li(R3, LOCAL_ROUTER_PORT)
+    a.li(R0, 100)
+    a.send(DST_REGS, R0, TAG_EXFIL, f0=R1, f1=G0 + 1)
+    a.close()
+    a.exit()
+
+    a.program("route", PROG_ROUTE)                                # :96-107 (the WAN-side socket only sends)
+    a.open(LOCAL_ROUTER_PORT)
+    a.label("loop")
+    a.recv()
+    a.stat(STAT_ROUTED)
+    a.mov(R2, _PKT_F0)
+    a.mov(R3, _PKT_F1)
+    a.forward(router_wan, LOCAL_ROUTER_PORT)
+    a.jmp("loop")
+
+    a.program("command_and_control", PROG_C2)                     # :85-92
+    a.open(BAD_NEWS_BEAR_PORT)
+    a.label("loop")
+    a.recv()
+    a.stat(STAT_C2_RECEIVED)
+    a.jmp("loop")
+
+    infected = DrawnNode(sim, sim.workstations)                   # :114 next(distribution(workstation_list))
+    infected.install("call_home")
+    infected.install("no_good")
+    sim.router.install("route")
+    bear.install("command_and_control")
+    sim.caps.update(max_procs=224, max_sockets=100)
     return sim

@@ -60,15 +60,19 @@ def linear(gen: Dist, slope: float, shift: float) -> Dist:
 
 
 def bounded(gen: Dist, lower: Optional[float] = None, upper: Optional[float] = None) -> Dist:
-    if gen.flags & (DF_LOWER | DF_UPPER | DF_INT):
-        raise ValueError("bounded() applied twice or after project_int()")
+    if gen.flags & DF_INT:
+        raise ValueError("bounded() after project_int()")
     d = gen._copy()
+    # nested clamps compose exactly (clamping is monotone): the Internet latency of overrides.py:443-456 is
+    # bounded(bounded(expo(1 s), lower=20 ms), lower=0)
     if lower is not None:
+        d.lower = max(d.lower, float(lower)) if d.flags & DF_LOWER else float(lower)
         d.flags |= DF_LOWER
-        d.lower = float(lower)
     if upper is not None:
+        d.upper = min(d.upper, float(upper)) if d.flags & DF_UPPER else float(upper)
         d.flags |= DF_UPPER
-        d.upper = float(upper)
+    if (d.flags & DF_LOWER) and (d.flags & DF_UPPER) and d.lower > d.upper:
+        raise ValueError("empty clamp interval")
     return d
 
 

@@ -56,10 +56,29 @@ def machine_golden() -> None:
     json.dump(out, open(os.path.join(GOLDEN, "machine_summaries.json"), "w"), indent=1, sort_keys=True)
 
 
+def malware_golden() -> None:
+    """network_simple + malware overlay (config C3): one full trace and two 1 h summaries."""
+    out = {}
+    for seed, replica, horizon, keep in ((0, 0, 900.0, True), (2, 41, 3600.0, False), (0, 7, 3600.0, False)):
+        model = netsimple.MalwareModel(seed, replica)
+        model.run(horizon)
+        s, arr = summary_of(model, horizon)
+        s["infected"] = model.infected.index
+        if keep:
+            np.savez_compressed(os.path.join(GOLDEN, f"malware_trace_s{seed}_r{replica}_{int(horizon)}s.npz"), trace=arr)
+        out[f"{seed}:{replica}:{int(horizon)}"] = s
+        model.close()
+        print("malware", seed, replica, horizon, s["events"], flush=True)
+    json.dump(out, open(os.path.join(GOLDEN, "malware_summaries.json"), "w"), indent=1, sort_keys=True)
+
+
 def main() -> None:
     os.makedirs(GOLDEN, exist_ok=True)
     if "--machine" in sys.argv:
         machine_golden()
+        return
+    if "--malware" in sys.argv:
+        malware_golden()
         return
     path = os.path.join(GOLDEN, "netsimple_summaries.json")
     summaries = json.load(open(path)) if os.path.exists(path) else {}

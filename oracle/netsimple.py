@@ -57,6 +57,7 @@ GbPS = 1024 * MbPS
 # ---- program ids shared with the engine (itsim_b200/netsimple.py) -----------------------------------------
 PROG_DHCP_SERVE, PROG_BLINKING, PROG_CLIENT, PROG_MDNS, PROG_LLMNR = 1, 2, 3, 4, 5
 PROG_QUERY_MDNS, PROG_QUERY_LLMNR, PROG_TIMEOUT_HELPER, PROG_TX, PROG_DELIVER = 6, 7, 8, 9, 10
+PROG_CALL_HOME, PROG_NO_GOOD, PROG_SUDO_TRANSMIT, PROG_EXFILTRATE, PROG_ROUTE, PROG_C2 = 11, 12, 13, 14, 15, 16
 EXC_COMPLETE = 1
 
 Location = Tuple[int, int]  # (IPv4 address as int, port); hashable like itsim.network.location.Location
@@ -103,6 +104,12 @@ class Network:
         self._nodes[address] = node
         return address
 
+    def _address_of(self, node: "Node") -> int:
+        for address, member in self._nodes.items():
+            if member is node:
+                return address
+        return -1
+
     def transmit(self, packet: Packet) -> None:
         """overrides.py:273-291."""
         dest_host = packet.dest[0]
@@ -116,8 +123,9 @@ class Network:
         def transmission() -> None:
             advance(next(self._latency) + len(packet) / next(self._bandwidth))
             for node in receivers:
+                index = self.model.node_of_address.get(self._address_of(node), node).index
                 proc = self.sim.add(node._receive, packet)
-                tr.Tracer.label(proc, tr.ROLE_DELIVER, PROG_DELIVER, node.index)
+                tr.Tracer.label(proc, tr.ROLE_DELIVER, PROG_DELIVER, index)
 
         proc = self.sim.add(transmission)
         tr.Tracer.label(proc, tr.ROLE_TX, PROG_TX, self.model.node_of_address[packet.source[0]].index,
@@ -220,7 +228,7 @@ class Socket:
 class Node:
     """overrides.py:300-388 plus Endpoint (overrides.py:403-433)."""
 
-    def __init__(self, model: "Model", name: str, network: Network) -> None:
+    def __init__(self, model: "Model", name: str, network: Network, address: Optional[int] = None) -> None:
         self.model = model
         self.name = name
         self.sim = model.sim
@@ -228,9 +236,19 @@ class Node:
         model.nodes.append(self)
         self._networks: "OrderedDict[int, _NetworkLink]" = OrderedDict()
         self._sockets: "OrderedDict[Location, Socket]" = OrderedDict()
-        address = network.link(self)
+        address = network.link(self, address)
         self._networks[address] = _NetworkLink(address, network)
         model.node_of_address[address] = self
+
+    def link_to(self, network: Network, address: Optional[int] = None) -> int:
+        """overrides.py:307-312: a further address on another network.  The trace numbers that attachment like a
+        node of its own (the engine models it as one), hence the placeholder in ``model.nodes``."""
+        address = network.link(self, address)
+        self._networks[address] = _NetworkLink(address, network)
+        alias = _Attachment(self, len(self.model.nodes))
+        self.model.nodes.append(alias)
+        self.model.node_of_address[address] = alias
+        return address
 
     @property
     def address_default(self) -> int:
@@ -240,8 +258,8 @@ class Node:
         return self._networks[src_addr].network.address_broadcast
 
     @contextmanager
-    def bind(self, port: Optional[int] = None) -> Iterator[Location]:
-        src: Location = (self.address_default, port or 0)
+    def bind(self, port: Any = None) -> Iterator[Location]:
+        src: Location = port if isinstance(port, tuple) else (self.address_default, port or 0)
         link = self._networks[src[0]]
         if src[1] == 0:
             src = (src[0], link.get_port_free())
@@ -254,7 +272,7 @@ class Node:
             del link.ports[src[1]]
 
     @contextmanager
-    def open_socket(self, port: Optional[int] = None) -> Iterator[Socket]:
+    def open_socket(self, port: Any = None) -> Iterator[Socket]:
         with self.bind(port) as src:
             sock = Socket(src, self)
             alias = (self._broadcast_address(src[0]), src[1])  # also listens on the broadcast address
@@ -280,6 +298,16 @@ class Node:
     def install(self, prog: int, fn_software: Any, *args: Any) -> None:
         proc = self.sim.add(fn_software, self, *args)
         tr.Tracer.label(proc, tr.ROLE_MODEL, prog, self.index)
+
+
+class _Attachment:
+    """A node's attachment to a further network, numbered like a node (see ``Node.link_to``)."""
+
+    def __init__(self, node: Node, index: int) -> None:
+        self.node, self.index = node, index
+
+    def _receive(self, packet: Packet) -> None:
+        self.node._receive(packet)
 
 
 class FellAsleep(Exception):
@@ -533,6 +561,81 @@ class Model:
                 tr.Tracer.label(proc, tr.ROLE_MODEL, PROG_QUERY_LLMNR, ws.index)
             except FellAsleep:
                 pass
+
+
+class MalwareModel(Model):
+    """network_simple + the beaconing-malware overlay of examples/network_simple/malware_simple.py:53-125 (config C3).
+
+    One workstation, chosen with ``next(distribution(workstation_list))`` at set-up (malware_simple.py:114: the
+    replica's first draw), runs ``call_home`` (beacon every expo(10) s) and ``no_good`` (privileged read every
+    expo(100) s); both end in ``exfiltrate``: 100 B to the router's port 777.  The router's ``route`` process relays
+    every such packet over the ``Internet`` network (latency max(expo(1 s), 20 ms), bandwidth max(expo(10 MbPS),
+    0.125): overrides.py:443-456) to the command-and-control host 1.2.3.4:666."""
+
+    BAD_NEWS_BEAR_ADDR = (1 << 24) | (2 << 16) | (3 << 8) | 4
+    BAD_NEWS_BEAR_PORT = 666
+    LOCAL_ROUTER_PORT = 777
+
+    def __init__(self, seed: int = 0, replica: int = 0, trace: bool = True, trace_limit: Optional[int] = None) -> None:
+        super().__init__(seed, replica, trace=trace, trace_limit=trace_limit)
+        self.stats.update({"beacons": 0, "routed": 0, "c2_received": 0})
+        gsrandom.set_default_rng(self.rng)
+        try:
+            self.www = Network(self, "0.0.0.0/0", latency=bounded(expo(1 * S), lower=20 * MS),
+                               bandwidth=expo(10 * MbPS))
+            infected = next(distribution(self.workstations))            # malware_simple.py:114
+        finally:
+            gsrandom.set_default_rng(None)
+        self.infected = infected
+        infected.install(PROG_CALL_HOME, self.call_home)
+        infected.install(PROG_NO_GOOD, self.no_good)
+        self.router_local_addr = self.router.address_default
+        self.router_inet_addr = self.router.link_to(self.www)
+        self.router.install(PROG_ROUTE, self.route)
+        self.bear = Node(self, "Mama Bear", self.www, self.BAD_NEWS_BEAR_ADDR)
+        self.bear.install(PROG_C2, self.command_and_control)
+
+    def call_home(self, ws: Node) -> None:
+        """malware_simple.py:53-58."""
+        while True:
+            advance(next(expo(10)))
+            proc = add(self.exfiltrate, ws)
+            tr.Tracer.label(proc, tr.ROLE_MODEL, PROG_EXFILTRATE, ws.index)
+
+    def no_good(self, ws: Node) -> None:
+        """malware_simple.py:61-65."""
+        while True:
+            advance(next(expo(100)))
+            proc = add(self.sudo_transmit, ws)
+            tr.Tracer.label(proc, tr.ROLE_MODEL, PROG_SUDO_TRANSMIT, ws.index)
+
+    def sudo_transmit(self, ws: Node) -> None:
+        """malware_simple.py:68-72."""
+        proc = add(self.exfiltrate, ws)
+        tr.Tracer.label(proc, tr.ROLE_MODEL, PROG_EXFILTRATE, ws.index)
+
+    def exfiltrate(self, ws: Node) -> None:
+        """malware_simple.py:75-82."""
+        self.stats["beacons"] += 1
+        with ws.open_socket(self.BAD_NEWS_BEAR_PORT) as socket:
+            socket.send((self.router_local_addr, self.LOCAL_ROUTER_PORT), 100,
+                        {"content": "exfil", "dest_addr": (self.BAD_NEWS_BEAR_ADDR, self.BAD_NEWS_BEAR_PORT)})
+
+    def route(self, router: Node) -> None:
+        """malware_simple.py:96-107: the one-way router."""
+        with router.open_socket((self.router_local_addr, self.LOCAL_ROUTER_PORT)) as i_socket:
+            with router.open_socket((self.router_inet_addr, self.LOCAL_ROUTER_PORT)) as world_socket:
+                while True:
+                    msg = i_socket.recv()
+                    self.stats["routed"] += 1
+                    world_socket.send(msg.payload["dest_addr"], msg.byte_size, msg.payload)
+
+    def command_and_control(self, bear: Node) -> None:
+        """malware_simple.py:85-92."""
+        with bear.open_socket(self.BAD_NEWS_BEAR_PORT) as socket:
+            while True:
+                socket.recv()
+                self.stats["c2_received"] += 1
 
 
 def run_replica(seed: int, replica: int, duration: float, trace: bool = True, trace_limit: Optional[int] = None,
