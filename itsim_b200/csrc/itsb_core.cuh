@@ -282,7 +282,7 @@ struct Rep {                /* register-resident working view of one replica */
     u32* arena_free;
     itsb_trace_rec* trace;
     Model m;
-    u32 max_ev, trace_cap;
+    u32 max_ev, trace_cap, max_sig;
     u32* iface_addr;        /* shipped-itsim tables */
     PcbX* pcbx;
     Sig* sig;
@@ -316,6 +316,7 @@ ITSB_FN void rebind(Rep& R, Hdr* H) {
     R.m = *H->model;
     R.max_ev = H->L.max_ev;
     R.trace_cap = H->L.trace_cap;
+    R.max_sig = H->L.max_sig;
     R.iface_addr = (u32*)(hot + H->L.off_iface);
     R.pcbx = (PcbX*)(hot + H->L.off_pcbx);
     R.sig = (Sig*)(hot + H->L.off_sig);
@@ -952,6 +953,9 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
     u32 first = NET.first_node, count = NET.n_nodes;
     if (!bcast) {
         u32 hit = NIL32;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
         for (u32 i = (u32)lane_id(); i < NET.n_nodes; i += ITSB_W)
             if (R.m.nodes[NET.first_node + i].addr == K.dst_ip) hit = i;
         u32 m = w_min(hit);
@@ -1043,6 +1047,9 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
         } else {
             /* ring nearly full: same pushes, in recipient order, through the spilling path (warp-uniform);
                the retiring path is off here because the ring was not empty */
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
             for (int l = 0; l < ITSB_W; ++l) {
                 u32 nl = w_shfl(nwait, l);
                 u32 sl = w_shfl((u32)s, l);
@@ -1151,10 +1158,10 @@ ITSB_COLD int exec_cold(Hdr* H, u32 p, u64 ins) {
         const u32* v = H->vol;
         u32 dst_ip, dst_port = imm & 0xFFFF;
         switch (a) {
-        case DST_BCAST: dst_ip = v[SRC_NODE_BCAST - 0x10]; break;
+        case DST_BCAST: dst_ip = R.m.nets[R.m.nodes[P.node].net].bcast; break;
         case DST_PKT_SRC: dst_ip = v[SRC_PKT_SRC_IP - 0x10]; dst_port = v[SRC_PKT_SRC_PORT - 0x10]; break;
         case DST_ENT: dst_ip = v[SRC_ENT_IP - 0x10]; dst_port = v[SRC_ENT_PORT - 0x10]; break;
-        case DST_SELF: dst_ip = v[SRC_NODE_ADDR - 0x10]; break;
+        case DST_SELF: dst_ip = R.m.nodes[P.node].addr; break;
         default: dst_ip = P.r[2]; dst_port = P.r[3] & 0xFFFF; break;
         }
         u32 f0s = (imm >> 16) & 0xFF, f1s = (imm >> 24) & 0xFF;
@@ -1246,6 +1253,18 @@ ITSB_COLD int exec_cold(Hdr* H, u32 p, u64 ins) {
     }
 }
 
+/* thread / process handles of an activation (shipped-itsim models) */
+ITSB_COLD void thread_regs(Hdr* H, u32 p) {
+    Rep R; rebind(R, H);
+    const u32 th = R.pcbx[p].thread;
+    if (th == NIL16) return;
+    const u32 tk = R.thr[th].task;
+    u32* v = H->vol;
+    v[SRC_SELF_THREAD - 0x10] = th | ((u32)R.thr[th].gen << 16);
+    v[SRC_SELF_TASK - 0x10] = tk | ((u32)R.task[tk].gen << 16);
+    v[SRC_PID - 0x10] = R.task[tk].pid;
+}
+
 /* Runs process p from its pc until it blocks or ends.  Inline: the receive loop heads, waits and branches a daemon
  * or a query executes per packet; everything else goes through exec_cold. */
 ITSB_FN void run_process(Rep& R, u32 p) {
@@ -1258,15 +1277,7 @@ ITSB_FN void run_process(Rep& R, u32 p) {
         v[SRC_NODE_ADDR - 0x10] = N.addr; v[SRC_NODE_INDEX - 0x10] = P.node; v[SRC_NODE_HOST - 0x10] = N.host;
         v[SRC_NODE_EPOCH - 0x10] = R.node[P.node].epoch; v[SRC_NODE_BCAST - 0x10] = R.m.nets[N.net].bcast;
         v[SRC_SELF - 0x10] = handle_of(R, p); v[SRC_EXC - 0x10] = P.exc; v[SRC_ZERO - 0x10] = 0;
-        if (H->L.max_sig != 0) {
-            const u32 th = R.pcbx[p].thread;
-            if (th != NIL16) {
-                const u32 tk = R.thr[th].task;
-                v[SRC_SELF_THREAD - 0x10] = th | ((u32)R.thr[th].gen << 16);
-                v[SRC_SELF_TASK - 0x10] = tk | ((u32)R.task[tk].gen << 16);
-                v[SRC_PID - 0x10] = R.task[tk].pid;
-            }
-        }
+        if (R.max_sig != 0) thread_regs(H, p);
     }
     for (;;) {
         if (H->status != 0) return;
@@ -1327,6 +1338,7 @@ ITSB_FN void run_process(Rep& R, u32 p) {
             P.pc += 1;
         } else if (op == OP_JMP) {
             P.pc = (u16)imm;
+
         } else if (op == OP_JEQI || op == OP_JNEI) {
             const bool eq = src_val(R, P, a) == (imm >> 16);
             P.pc = (eq == (op == OP_JEQI)) ? (u16)(imm & 0xFFFF) : (u16)(P.pc + 1);
