@@ -60,7 +60,8 @@ enum {
     OP_PWAIT = 38,      /* Process.wait(timeout) on src(a)                                       process.py:84-85    */
     OP_TKILL = 39,      /* Thread.kill() on src(a)                                               thread.py:87-98     */
     OP_PKILL = 40,      /* Process.kill() on src(a)                                              process.py:70-76    */
-    OP_MARK = 41,       /* trace-only record imm of a model side effect (the tests' cemetary.append(name))          */
+    OP_MARK = 41,       /* trace-only record of a model side effect (the tests' cemetary.append(name)): value imm, or
+                           src(a) when a != 0xFF                                                                     */
     OP_SIG_WAIT = 42,   /* Signal.wait(timeout) on signal src(a)   (used by the select / balk helper programs)      */
     OP_SIG_ON = 43,     /* Signal.turn_on() on signal src(a)                                                         */
     OP_GSET = 44,       /* model variable g[imm & 7] = src(a)    (state shared between bodies, e.g. a dict of children) */
@@ -82,6 +83,7 @@ enum {
     OP_GETADDR = 58,    /* r[a] = interface.address                                              client.py:144        */
     OP_FORWARD = 59,    /* send the packet just received on, from (address of node imm[0:16], port imm[16:32]) to
                            (r2, r3): the one-way router of malware_simple.py:96-107                                  */
+    OP_GETPORT = 60,    /* r[a] = socket.port                                                    socket.py:44-51      */
     OP_COUNT
 };
 

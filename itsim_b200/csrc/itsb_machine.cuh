@@ -352,10 +352,14 @@ ITSB_COLD void m_deliver(Hdr* H, u32 k) {
 
 /* Node.bind (node.py:178-200): explicit port or the next free port of the persistent 32768..60999 cycle; ports 0 and
  * 65535 are never free.  The socket's two signals start off (socket.py:35-36). */
+/* releases the socket slot of a finishing process (queued packets, both signals) */
+ITSB_FN void m_sock_release(Rep& R, u32 p);
+
 ITSB_COLD int m_bind(Hdr* H, u32 p, u32 port) {
     Rep R; rebind(R, H);
     Pcb& P = R.pcb[p];
     NodeDyn& N = R.node[P.node];
+    if (P.sock != NIL16) m_sock_release(R, p);   /* the name is rebound: the old Socket is finalised (socket.py:59-68) */
     if (port == 0) {
         u32 c = N.port_cursor, visited = 0;
         for (;;) {
@@ -470,7 +474,7 @@ ITSB_COLD int exec_machine(Hdr* H, u32 p, u64 ins) {
     const u32 op = (u32)(ins & 0xFF), a = (u32)((ins >> 8) & 0xFF), b = (u32)((ins >> 16) & 0xFF),
               c = (u32)((ins >> 24) & 0xFF), imm = (u32)(ins >> 32);
     /* the thread / signal / link instructions need their tables; the small generic helpers do not */
-    const bool generic = op == OP_MARK || op == OP_GSET || op == OP_TLOAD || op == OP_TSTORE || op == OP_ADD ||
+    const bool generic = op == OP_MARK || op == OP_GETPORT || op == OP_GSET || op == OP_TLOAD || op == OP_TSTORE || op == OP_ADD ||
                          op == OP_SUB || op == OP_JLTU;
     if (H->L.max_sig == 0 && !generic) { fail(H, ITSB_ERR_BAD_OPCODE, P.pc); return XR_STOP; }
     switch (op) {
@@ -614,7 +618,11 @@ ITSB_COLD int exec_machine(Hdr* H, u32 p, u64 ins) {
         return XR_CONTINUE;
     }
     case OP_MARK:
-        if (R.trace) trace_put(H, ITSB_TRACE_MARK, 0, 0, imm);
+        if (R.trace) trace_put(H, ITSB_TRACE_MARK, 0, 0, a == SRC_NONE ? imm : src_val(R, P, a));
+        P.pc += 1;
+        return XR_CONTINUE;
+    case OP_GETPORT:
+        P.r[a & 3] = P.sock == NIL16 ? 0 : R.sock[P.sock].port;
         P.pc += 1;
         return XR_CONTINUE;
     case OP_SIG_WAIT:

@@ -16,7 +16,7 @@ import numpy as np
  OP_NODE_WAKE, OP_SPAWN, OP_THROW, OP_LIST_CLEAR, OP_LIST_PUSH, OP_LIST_TAKE, OP_STAT, OP_RECV_FILTER,
  OP_BIND, OP_SCLOSE, OP_SENDL, OP_RECVT, OP_ADVANCE_X, OP_THREAD_EXIT, OP_CLONE, OP_FORK, OP_JOIN, OP_PWAIT, OP_TKILL,
  OP_PKILL, OP_MARK, OP_SIG_WAIT, OP_SIG_ON, OP_GSET, OP_NOW_SUB, OP_ADVANCE_X2, OP_TLOAD, OP_TSTORE, OP_ADD, OP_SUB,
- OP_JLTU, OP_XNOW, OP_XSET, OP_XELAPSE, OP_JXLE0, OP_RECVT_X, OP_SETADDR, OP_GETADDR, OP_FORWARD) = range(60)
+ OP_JLTU, OP_XNOW, OP_XSET, OP_XELAPSE, OP_JXLE0, OP_RECVT_X, OP_SETADDR, OP_GETADDR, OP_FORWARD, OP_GETPORT) = range(61)
 
 PROG_HIDDEN_BALK, PROG_HIDDEN_WAIT_ONE = 0xF1, 0xF2
 
@@ -175,7 +175,9 @@ class Asm:
 
     def tkill(self, thread_src: int) -> None: self._emit(OP_TKILL, thread_src)
     def pkill(self, task_src: int) -> None: self._emit(OP_PKILL, task_src)
-    def mark(self, code: int) -> None: self._emit(OP_MARK, imm=code)
+    def mark(self, code: int) -> None: self._emit(OP_MARK, NONE, imm=code)
+    def mark_value(self, src: int) -> None: self._emit(OP_MARK, src)
+    def getport(self, rd: int) -> None: self._emit(OP_GETPORT, rd)
     def gset(self, index: int, src: int) -> None: self._emit(OP_GSET, src, imm=index)
     def now_sub(self, const_index: int) -> None: self._emit(OP_NOW_SUB, imm=const_index)
     def advance_x2(self, handler: Optional[Target] = None) -> None:
