@@ -896,22 +896,36 @@ ITSB_COLD void on_tx_begin(Hdr* H, u32 k) {
     const itsb_net NET = R.m.nets[K.meta >> 16];
     count_event(R, ITSB_EV_TX_BEGIN, 9, K.meta & 0xFFFF, K.size);
     double lat = draw_dist(H, &R.m.dists[NET.lat_dist]);
-    double bw = draw_dist(H, &R.m.dists[NET.bw_dist]);
+    const itsb_dist* BW = &R.m.dists[NET.bw_dist];
+    double bw = (BW->kind == ITSB_DIST_CONSTANT && (BW->flags & (ITSB_DF_LINEAR | ITSB_DF_UPPER | ITSB_DF_INT)) == 0)
+                    ? ((BW->flags & ITSB_DF_LOWER) && BW->p0 < BW->lower ? BW->lower : BW->p0)   /* constant(c): no draw */
+                    : draw_dist(H, BW);
     double delay = lat + (double)K.size / bw;
     if (delay < 0.0) { fail(H, ITSB_EXC_NEGATIVE_DELAY, k); return; }
     stat_add(R, ITSB_TM_LAT0 + latency_bin(delay), 1);
     ev_push_inl(R, H->now + delay, ev_pack_pkt(ITSB_EV_TX_END, k));
 }
 
-/* for node in receivers: sim.add(node._receive, packet)  -- one queue entry stands for the R consecutive pushes */
-ITSB_COLD void on_tx_end(Hdr* H, u32 k) {
+/* for node in receivers: sim.add(node._receive, packet)  -- one queue entry stands for the R consecutive pushes.
+ * Returns true when that entry would be the very next event anyway (nothing queued at this instant, no future event
+ * at t == now): the caller then runs the delivery pass directly instead of pushing and popping it. */
+ITSB_COLD bool on_tx_end(Hdr* H, u32 k) {
     Rep R; rebind(R, H);
     const Pkt K = *pkt_at(R, k);
     const itsb_net NET = R.m.nets[K.meta >> 16];
     u32 count = (K.dst_ip == NET.bcast) ? NET.n_nodes : 1u;
     count_event(R, ITSB_EV_TX_END, 9, K.meta & 0xFFFF, K.size);
+    if (H->nq_head == H->nq_tail && H->nq_spill_count == 0) {
+        if (!H->pmin_valid) pool_scan_min(H);
+        const u64 nb = dbits(H->now);
+        if (H->pmin_t > nb && (H->ovf_count == 0 || H->ovf_min_t > nb)) {
+            H->seq += count;
+            return true;
+        }
+    }
     ev_push_inl(R, H->now, ev_pack_pkt(ITSB_EV_DELIVER, k));
     H->seq += count - 1;
+    return false;
 }
 
 ITSB_COLD void m_deliver(Hdr* H, u32 k);   /* Link-mode delivery, itsb_machine.cuh */
@@ -1431,9 +1445,9 @@ ITSB_FN u64 run_replica(Rep& R, double duration) {
         const u32 data = ev_take(R, src);
         H->now = bitsd(tb);
         const u32 kind = ev_kind(data), idx = ev_idx(data);
-        u32 runnable = NIL32;
+        u32 runnable = NIL32, deliver = NIL32;
         if (kind == ITSB_EV_DELIVER) {
-            on_deliver(R, ev_pkt(data));
+            deliver = ev_pkt(data);
         } else if (kind == ITSB_EV_WAKE || kind == ITSB_EV_TIMER || kind == ITSB_EV_PROC_START) {
             Pcb& P = R.pcb[idx];
             bool live = P.state != PS_FREE && P.gen == ev_gen(data);   /* else a ghost hop: target finished */
@@ -1454,7 +1468,7 @@ ITSB_FN u64 run_replica(Rep& R, double duration) {
         } else if (kind == ITSB_EV_TX_BEGIN) {
             on_tx_begin(H, ev_pkt(data));
         } else if (kind == ITSB_EV_TX_END) {
-            on_tx_end(H, ev_pkt(data));
+            if (on_tx_end(H, ev_pkt(data))) deliver = ev_pkt(data);
         } else if (kind == ITSB_EV_THROW) {
             Pcb& P = R.pcb[idx];
             if (P.state != PS_FREE && P.gen == ev_gen(data)) {
@@ -1466,6 +1480,7 @@ ITSB_FN u64 run_replica(Rep& R, double duration) {
         } else {
             fail(H, ITSB_ERR_BAD_OPCODE, data);
         }
+        if (deliver != NIL32) on_deliver(R, deliver);      /* the delivery pass's only call site */
         if (runnable != NIL32) run_process(R, runnable);   /* the interpreter's only call site */
     }
     return events_counted(R) - events_before;
