@@ -67,6 +67,21 @@ typedef struct itsb_trace_rec {   /* 16 bytes, little endian; same layout as ora
     uint32_t aux;
 } itsb_trace_rec;
 
+typedef struct itsb_net_event {   /* 32 bytes: one record of the datastore's `network_event` table
+                                     (itsim/schemas/items.py:83-131): a socket opened or closed                     */
+    double   t;                   /* simulated time                                                                */
+    uint16_t node;
+    uint16_t port;
+    uint8_t  type;                /* 1 = "open", 2 = "close"                                                       */
+    uint8_t  protocol;            /* 0 NONE, 1 UDP, 2 TCP                                                          */
+    int16_t  pid;
+    uint32_t src_ip;              /* local address the socket is bound on                                          */
+    uint32_t dst_ip;              /* 0: datagram sockets have no peer at open time                                 */
+    uint16_t dst_port;
+    uint16_t prog;                /* program id of the process that opened / closed it                             */
+    uint32_t reserved;
+} itsb_net_event;
+
 /* ---- telemetry: what the datastore would have been told, reduced on device ---------------------------------- */
 #define ITSB_LAT_BINS 64
 /* slots of the uint64 telemetry vector returned by itsb_read_telemetry / reduced by itsb_allreduce_telemetry */
@@ -172,6 +187,7 @@ typedef struct itsb_caps {        /* per-replica capacities; exceeding one flags
     uint32_t trace_records;       /* per-replica trace capacity (0 = tracing off)                                 */
     uint32_t max_threads, max_tasks, max_signals;   /* shipped-itsim Thread / Process / Signal tables (0 = none)  */
     uint32_t table_words;         /* per-replica uint32 model table (TLOAD / TSTORE), zero-initialised            */
+    uint32_t net_event_records;   /* per-replica capacity of the network_event log in HBM (0 = logging off)       */
 } itsb_caps;
 
 typedef struct itsb_model_desc {
@@ -227,6 +243,11 @@ int itsb_read_now(itsb_engine* e, uint64_t first, uint64_t n, double* dst);
 
 /* Replaces: reading the event log of one replica (the reference has none; the oracle's tracer defines it).       */
 int itsb_read_trace(itsb_engine* e, uint64_t replica, itsb_trace_rec* dst, size_t cap, size_t* n_total);
+
+/* Replaces: the `network_event` records the datastore stores (itsim/schemas/items.py:83-131; itsim/datastore/
+ * database.py:44-57).  dst receives up to cap records of one replica; n_total = records produced (may exceed the
+ * capacity the model asked for: later ones are counted but not kept).                                               */
+int itsb_read_net_events(itsb_engine* e, uint64_t replica, itsb_net_event* dst, size_t cap, size_t* n_total);
 
 /* Replaces: the records itsim/logging.py + itsim/datastore would receive (README.md:18-50), reduced on the device:
  * ITSB_TM_SIZE uint64 counters / histogram bins summed over this engine's replicas.                               */

@@ -32,6 +32,10 @@ ERRORS = {
     5: "ValueError: Socket is closed", 6: "ValueError: negative delay", 7: "uncaught exception in a process body",
 }
 
+NET_EVENT_DTYPE = np.dtype([("t", "<f8"), ("node", "<u2"), ("port", "<u2"), ("type", "u1"), ("protocol", "u1"),
+                            ("pid", "<i2"), ("src_ip", "<u4"), ("dst_ip", "<u4"), ("dst_port", "<u2"), ("prog", "<u2"),
+                            ("reserved", "<u4")])
+assert NET_EVENT_DTYPE.itemsize == 32
 TRACE_DTYPE = np.dtype([("t", "<f8"), ("kind", "u1"), ("prog", "u1"), ("node", "<u2"), ("aux", "<u4")])
 DIST_DTYPE = np.dtype([("kind", "<u4"), ("flags", "<u4"), ("p0", "<f8"), ("p1", "<f8"), ("slope", "<f8"),
                        ("shift", "<f8"), ("lower", "<f8"), ("upper", "<f8")])
@@ -54,7 +58,7 @@ class Caps(C.Structure):
     _fields_ = [("max_events", C.c_uint32), ("max_procs", C.c_uint32), ("max_sockets", C.c_uint32),
                 ("max_packets", C.c_uint32), ("arena_nodes", C.c_uint32), ("trace_records", C.c_uint32),
                 ("max_threads", C.c_uint32), ("max_tasks", C.c_uint32), ("max_signals", C.c_uint32),
-                ("table_words", C.c_uint32)]
+                ("table_words", C.c_uint32), ("net_event_records", C.c_uint32)]
 
 
 class ModelDesc(C.Structure):
@@ -82,6 +86,7 @@ _SIGNATURES = {
     "itsb_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "itsb_read_now": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "itsb_read_trace": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "itsb_read_net_events": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "itsb_read_telemetry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsb_read_replica_telemetry": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]),
     "itsb_allreduce_telemetry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),

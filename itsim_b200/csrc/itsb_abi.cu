@@ -63,6 +63,7 @@ struct RunParams {
     ArenaNode* arena;
     uint32_t* arena_free;
     itsb_trace_rec* trace;
+    itsb_net_event* netlog;
     uint64_t n_replicas;
     uint64_t seed;
     double duration;
@@ -145,7 +146,8 @@ extern "C" __global__ void __launch_bounds__(512, 1) k_run(const RunParams p) {
         phase ^= 1;
         Rep R;
         bind_views(R, hot, &p.layout, m, p.arena + r * p.layout.arena_nodes, p.arena_free + r * p.layout.arena_nodes,
-                   p.trace ? p.trace + r * p.layout.trace_cap : nullptr, p.seed);
+                   p.trace ? p.trace + r * p.layout.trace_cap : nullptr,
+                   p.netlog ? p.netlog + r * p.layout.log_cap : nullptr, p.seed);
         const unsigned long long events = run_replica(R, p.duration);
         __syncwarp();
         const int32_t status = R.hdr->status;
@@ -166,7 +168,7 @@ extern "C" __global__ void __launch_bounds__(512, 1) k_run(const RunParams p) {
 extern "C" __global__ void k_make_template(const RunParams p, const Model* model, unsigned char* tmpl,
                                            ArenaNode* arena0, uint32_t* free0) {
     Rep R;
-    bind_views(R, tmpl, &p.layout, model, arena0, free0, nullptr, p.seed);
+    bind_views(R, tmpl, &p.layout, model, arena0, free0, nullptr, nullptr, p.seed);
     init_replica(R, 0);
 }
 
@@ -220,6 +222,7 @@ struct itsb_engine {
     ArenaNode* d_arena = nullptr;
     uint32_t* d_arena_free = nullptr;
     itsb_trace_rec* d_trace = nullptr;
+    itsb_net_event* d_netlog = nullptr;
     unsigned long long* d_ticket = nullptr;       /* [0] ticket, [1] events_done */
     long long* d_first_failed = nullptr;
     unsigned long long* d_telemetry = nullptr;
@@ -244,8 +247,8 @@ struct itsb_engine {
     } while (0)
 
 static void free_replicas(itsb_engine* e) {
-    cudaFree(e->d_hot); cudaFree(e->d_arena); cudaFree(e->d_arena_free); cudaFree(e->d_trace);
-    e->d_hot = nullptr; e->d_arena = nullptr; e->d_arena_free = nullptr; e->d_trace = nullptr;
+    cudaFree(e->d_hot); cudaFree(e->d_arena); cudaFree(e->d_arena_free); cudaFree(e->d_trace); cudaFree(e->d_netlog);
+    e->d_hot = nullptr; e->d_arena = nullptr; e->d_arena_free = nullptr; e->d_trace = nullptr; e->d_netlog = nullptr;
     e->n_replicas = 0;
 }
 
@@ -335,7 +338,9 @@ int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first
     CU(e, cudaMalloc(&e->d_arena, (size_t)n * L.arena_nodes * sizeof(ArenaNode)));
     CU(e, cudaMalloc(&e->d_arena_free, (size_t)n * L.arena_nodes * sizeof(uint32_t)));
     if (L.trace_cap) CU(e, cudaMalloc(&e->d_trace, (size_t)n * L.trace_cap * sizeof(itsb_trace_rec)));
+    if (L.log_cap) CU(e, cudaMalloc(&e->d_netlog, (size_t)n * L.log_cap * sizeof(itsb_net_event)));
     e->rp.hot = e->d_hot; e->rp.arena = e->d_arena; e->rp.arena_free = e->d_arena_free; e->rp.trace = e->d_trace;
+    e->rp.netlog = e->d_netlog;
     e->rp.n_replicas = n; e->rp.seed = seed;
     e->rp.ticket = e->d_ticket; e->rp.events_done = e->d_ticket + 1; e->rp.first_failed = e->d_first_failed;
     unsigned char* tmpl = nullptr;
@@ -436,6 +441,19 @@ int itsb_read_trace(itsb_engine* e, uint64_t replica, itsb_trace_rec* dst, size_
     if (n > cap) n = cap;
     if (n && e->d_trace)
         CU(e, cudaMemcpy(dst, e->d_trace + (size_t)replica * e->rp.layout.trace_cap, n * sizeof(itsb_trace_rec), cudaMemcpyDeviceToHost));
+    return ITSB_OK;
+}
+
+int itsb_read_net_events(itsb_engine* e, uint64_t replica, itsb_net_event* dst, size_t cap, size_t* n_total) {
+    if (!e || replica >= e->n_replicas) return ITSB_ERR_STATE;
+    CU(e, cudaSetDevice(e->device));
+    Hdr h;
+    CU(e, cudaMemcpy(&h, e->d_hot + (size_t)replica * e->rp.layout.hot_bytes, sizeof(Hdr), cudaMemcpyDeviceToHost));
+    if (n_total) *n_total = h.log_count;
+    size_t n = h.log_count < e->rp.layout.log_cap ? h.log_count : e->rp.layout.log_cap;
+    if (n > cap) n = cap;
+    if (n && e->d_netlog)
+        CU(e, cudaMemcpy(dst, e->d_netlog + (size_t)replica * e->rp.layout.log_cap, n * sizeof(itsb_net_event), cudaMemcpyDeviceToHost));
     return ITSB_OK;
 }
 

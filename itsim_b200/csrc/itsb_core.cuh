@@ -214,6 +214,7 @@ struct Layout {             /* byte offsets inside one replica's hot block */
     u32 off_iface, off_pcbx, off_sig, off_sig_free, off_thr, off_thr_free, off_task, off_task_free;
     u32 n_ifaces, max_sig, max_thr, max_task;
     u32 off_tab, table_words;
+    u32 log_cap;            /* network_event records per replica (HBM) */
 };
 
 struct Model {              /* pointers to the static tables (shared-memory copies inside the kernel) */
@@ -243,6 +244,8 @@ struct Hdr {                /* first thing in the hot block */
     u64 detail;
     u32 arena_free_top;
     u32 trace_count;
+    u32 log_count;          /* network_event records produced */
+    u32 spare_a;
     u16 ev_free_top, pcb_free_top, sock_free_top, spare16;
     u32 replica_lo, replica_hi;
     u32 nq_head, nq_tail;   /* now-queue ring cursors (monotone) */
@@ -259,6 +262,7 @@ struct Hdr {                /* first thing in the hot block */
     ArenaNode* arena;
     u32* arena_free;
     itsb_trace_rec* trace;
+    itsb_net_event* netlog;
     const Model* model;
     u32 seed_lo, seed_hi;
     Layout L;
@@ -330,13 +334,14 @@ ITSB_FN void rebind(Rep& R, Hdr* H) {
 
 /* Stages the launch's pointers into the header, then builds the view. */
 ITSB_FN void bind_views(Rep& R, unsigned char* hot, const Layout* L, const Model* model, ArenaNode* arena,
-                        u32* arena_free, itsb_trace_rec* trace, u64 seed) {
+                        u32* arena_free, itsb_trace_rec* trace, itsb_net_event* netlog, u64 seed) {
     Hdr* H = (Hdr*)hot;
     H->L = *L;
     H->model = model;
     H->arena = arena;
     H->arena_free = arena_free;
     H->trace = trace;
+    H->netlog = netlog;
     H->seed_lo = (u32)seed;
     H->seed_hi = (u32)(seed >> 32);
     w_sync();
@@ -451,6 +456,19 @@ ITSB_COLD void trace_put(Hdr* H, u32 kind, u32 prog, u32 node, u32 aux) {
         H->trace[n] = rec;
     }
     H->trace_count = n + 1;
+}
+
+/* one `network_event` record (itsim/schemas/items.py:83-131): a socket opened (type 1) or closed (type 2) */
+ITSB_COLD void net_event_put(Hdr* H, u32 type, u32 node, u32 port, u32 src_ip, u32 prog, int pid, u32 protocol) {
+    if (H->netlog == nullptr) return;
+    const u32 n = H->log_count;
+    if (n < H->L.log_cap && lane_id() == 0) {
+        itsb_net_event E;
+        E.t = H->now; E.node = (u16)node; E.port = (u16)port; E.type = (u8)type; E.protocol = (u8)protocol;
+        E.pid = (int16_t)pid; E.src_ip = src_ip; E.dst_ip = 0; E.dst_port = 0; E.prog = (u16)prog; E.reserved = 0;
+        H->netlog[n] = E;
+    }
+    H->log_count = n + 1;
 }
 
 /* one simulated event of the given kind (SURVEY.md section 8-d definition) */
@@ -830,6 +848,7 @@ ITSB_COLD int sock_open(Hdr* H, u32 p, u32 port) {
     S.next = N.sock_head;
     N.sock_head = (u16)s;
     P.sock = (u16)s;
+    net_event_put(H, 1, P.node, port, R.m.nodes[P.node].addr, P.prog, 0, 1);
     return (int)s;
 }
 
@@ -840,6 +859,7 @@ ITSB_COLD void sock_close(Hdr* H, u32 p) {
     if (s == NIL16) return;
     Sock& S = R.sock[s];
     NodeDyn& N = R.node[S.node];
+    net_event_put(H, 2, S.node, S.port, R.m.nodes[S.node].addr, P.prog, 0, 1);
     if (N.sock_head == s) N.sock_head = S.next;
     else {
         u16 q = N.sock_head;
@@ -1493,7 +1513,7 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
     Hdr* H = R.hdr;
     const Layout* L = &H->L;
     H->now = 0.0; H->draws = 0; H->seq = 0; H->status = 0; H->detail = 0;
-    H->trace_count = 0;
+    H->trace_count = 0; H->log_count = 0; H->spare_a = 0;
     H->replica_lo = (u32)replica_id; H->replica_hi = (u32)(replica_id >> 32);
     H->nq_head = 0; H->nq_tail = 0; H->nq_spill_head = NIL32; H->nq_spill_tail = NIL32; H->nq_spill_count = 0;
     H->pmin_valid = 0; H->pmin_idx = NIL32; H->pmin_seq = NIL32; H->pmin_t = T_EMPTY;

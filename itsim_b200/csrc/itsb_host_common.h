@@ -19,6 +19,7 @@ static inline Layout compute_layout(const itsb_model_desc& d) {
     const itsb_caps& c = d.caps;
     L.max_ev = c.max_events; L.max_proc = c.max_procs; L.max_sock = c.max_sockets;
     L.n_nodes = d.n_nodes; L.arena_nodes = c.arena_nodes; L.trace_cap = c.trace_records;
+    L.log_cap = c.net_event_records;
     uint32_t off = align_up((uint32_t)sizeof(Hdr), 16);
     L.off_ev_t = off;      off = align_up(off + 8 * L.max_ev, 16);
     L.off_ev_seq = off;    off = align_up(off + 4 * L.max_ev, 16);

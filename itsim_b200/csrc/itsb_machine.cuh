@@ -385,6 +385,12 @@ ITSB_COLD int m_bind(Hdr* H, u32 p, u32 port) {
     S.next = N.sock_head;
     N.sock_head = (u16)s;
     P.sock = (u16)s;
+    {
+        const u32 fl = R.m.nodes[P.node].flags;
+        const u32 th = R.pcbx[p].thread;
+        net_event_put(H, 1, P.node, port, R.iface_addr[(fl & 0xFFFF) + ((fl >> 16) > 1 ? 1 : 0)], P.prog,
+                      th == NIL16 ? -1 : (int)R.task[R.thr[th].task].pid, 1);
+    }
     return (int)s;
 }
 
@@ -398,6 +404,12 @@ ITSB_COLD void m_close(Hdr* H, u32 p) {
     Sock& S = R.sock[s];
     if (R.sig[S.wait_tail].on) return;
     NodeDyn& N = R.node[S.node];
+    {
+        const u32 fl = R.m.nodes[S.node].flags;
+        const u32 th = R.pcbx[p].thread;
+        net_event_put(H, 2, S.node, S.port, R.iface_addr[(fl & 0xFFFF) + ((fl >> 16) > 1 ? 1 : 0)], P.prog,
+                      th == NIL16 ? -1 : (int)R.task[R.thr[th].task].pid, 1);
+    }
     if (N.sock_head == s) N.sock_head = S.next;
     else {
         u16 q = N.sock_head;

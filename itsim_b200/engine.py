@@ -94,6 +94,16 @@ class Engine:
         self.trace_total = total.value
         return out[:min(cap, total.value)]
 
+    def net_events(self, replica: int = 0) -> np.ndarray:
+        """The replica's ``network_event`` log (sockets opened / closed), as device records."""
+        cap = self.compiled.caps.net_event_records
+        out = np.zeros(cap, dtype=L.NET_EVENT_DTYPE)
+        total = C.c_size_t()
+        self._check(self._lib.itsb_read_net_events(self._h, replica, out.ctypes.data, cap, C.byref(total)),
+                    "itsb_read_net_events")
+        self.net_events_total = total.value
+        return out[:min(cap, total.value)]
+
     def telemetry(self) -> np.ndarray:
         out = np.zeros(L.TM_SIZE, dtype=np.uint64)
         self._check(self._lib.itsb_read_telemetry(self._h, out.ctypes.data, L.TM_SIZE), "itsb_read_telemetry")

@@ -81,7 +81,7 @@ class Simulator:
         self.nodes: List["Endpoint"] = []
         self._installed: List[Tuple[str, "Endpoint", Sequence[int]]] = []
         self.caps = dict(max_events=384, max_procs=256, max_sockets=128, max_packets=0, arena_nodes=16384,
-                         trace_records=0, max_threads=0, max_tasks=0, max_signals=0, table_words=0)
+                         trace_records=0, max_threads=0, max_tasks=0, max_signals=0, table_words=0, net_event_records=0)
         self._machine_procs: List[Tuple[Any, float, str, Sequence[int]]] = []   # Node.run_proc_in calls, in order
         self._engine: Any = None
         self._lib: Any = None       # tests inject the host-emulation library here; None = the CUDA engine

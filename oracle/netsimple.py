@@ -278,9 +278,11 @@ class Node:
             alias = (self._broadcast_address(src[0]), src[1])  # also listens on the broadcast address
             self._sockets[src] = sock
             self._sockets[alias] = sock
+            self.model.net_events.append((now(), self.index, src[1], 1))      # network_event "open"
             try:
                 yield sock
             finally:
+                self.model.net_events.append((now(), self.index, src[1], 2))  # network_event "close"
                 sock.flush_logs()
                 del self._sockets[src]
                 del self._sockets[alias]
@@ -382,6 +384,7 @@ class Model:
         self.nodes: List[Node] = []
         self.node_of_address: Dict[int, Node] = {}
         self.connections: List[tuple] = []
+        self.net_events: List[tuple] = []        # (t, node, port, 1 = open | 2 = close): itsim/schemas/items.py:83-131
         self.stats = {"packets_sent": 0, "bytes_sent": 0, "packets_received": 0, "bytes_received": 0,
                       "queries": 0, "resolved": 0, "timeouts": 0}
         self.tracer = tr.Tracer(self.sim, keep_records=trace, limit=trace_limit)

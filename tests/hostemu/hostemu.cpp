@@ -34,6 +34,7 @@ struct itsb_engine {
     std::vector<ArenaNode> arena;
     std::vector<uint32_t> arena_free;
     std::vector<itsb_trace_rec> trace;
+    std::vector<itsb_net_event> netlog;
     uint64_t last_events = 0, launches = 0;
     std::string err;
     bool loaded = false;
@@ -74,7 +75,8 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
 static void bind(itsb_engine* e, Rep& R, uint64_t r) {
     bind_views(R, e->hot.data() + r * e->layout.hot_bytes, &e->layout, &e->model,
                e->arena.data() + r * e->layout.arena_nodes, e->arena_free.data() + r * e->layout.arena_nodes,
-               e->layout.trace_cap ? e->trace.data() + r * e->layout.trace_cap : nullptr, e->seed);
+               e->layout.trace_cap ? e->trace.data() + r * e->layout.trace_cap : nullptr,
+               e->layout.log_cap ? e->netlog.data() + r * e->layout.log_cap : nullptr, e->seed);
 }
 
 int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first) {
@@ -84,6 +86,7 @@ int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first
     e->arena.assign(n * e->layout.arena_nodes, ArenaNode());
     e->arena_free.resize(n * e->layout.arena_nodes);
     e->trace.assign(n * e->layout.trace_cap, itsb_trace_rec());
+    e->netlog.assign(n * e->layout.log_cap, itsb_net_event());
     for (uint64_t r = 0; r < n; ++r) {
         Rep R; bind(e, R, r);
         for (uint32_t i = 0; i < e->layout.arena_nodes; ++i) R.arena_free[i] = e->layout.arena_nodes - 1 - i;
@@ -138,6 +141,16 @@ int itsb_read_trace(itsb_engine* e, uint64_t replica, itsb_trace_rec* dst, size_
     size_t n = H->trace_count < e->layout.trace_cap ? H->trace_count : e->layout.trace_cap;
     if (n > cap) n = cap;
     if (n) memcpy(dst, e->trace.data() + replica * e->layout.trace_cap, n * sizeof(itsb_trace_rec));
+    return ITSB_OK;
+}
+
+int itsb_read_net_events(itsb_engine* e, uint64_t replica, itsb_net_event* dst, size_t cap, size_t* n_total) {
+    if (replica >= e->n_replicas) return ITSB_ERR_STATE;
+    Hdr* H = (Hdr*)(e->hot.data() + replica * e->layout.hot_bytes);
+    if (n_total) *n_total = H->log_count;
+    size_t n = H->log_count < e->layout.log_cap ? H->log_count : e->layout.log_cap;
+    if (n > cap) n = cap;
+    if (n) memcpy(dst, e->netlog.data() + replica * e->layout.log_cap, n * sizeof(itsb_net_event));
     return ITSB_OK;
 }
 

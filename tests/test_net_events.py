@@ -1,0 +1,83 @@
+"""network_event records (sockets opened / closed): engine log in HBM against the oracle, and the conversion to the
+reference datastore's JSON schema (itsim/schemas/items.py:83-131)."""
+import json
+import os
+import sqlite3
+
+import numpy as np
+import pytest
+
+BACKENDS = [pytest.param("hostemu", id="hostemu"), pytest.param("gpu", id="gpu", marks=pytest.mark.gpu)]
+
+
+def engine_log(backend, hostemu, seed, replica, horizon, cap=20000):
+    from itsim_b200 import netsimple
+    sim = netsimple.build()
+    sim.caps["net_event_records"] = cap
+    sim._lib = hostemu if backend == "hostemu" else None
+    eng = sim.run_replicas(2, seed=seed, first_replica_id=replica)
+    eng.run(horizon)
+    return eng
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_log_matches_the_oracle(backend, hostemu):
+    import netsimple as oracle_netsimple
+    seed, replica, horizon = 4, 2, 1500.0
+    eng = engine_log(backend, hostemu, seed, replica, horizon)
+    got = eng.net_events(0)
+    model = oracle_netsimple.run_replica(seed, replica, horizon, trace=False)
+    ref = list(model.net_events)     # before close(): unwinding the parked bodies closes their sockets too
+    model.close()
+    assert eng.net_events_total == len(ref) == len(got)
+    assert [int(x) for x in got["node"]] == [r[1] for r in ref]
+    assert [int(x) for x in got["port"]] == [r[2] for r in ref]
+    assert [int(x) for x in got["type"]] == [r[3] for r in ref]
+    assert np.allclose(got["t"], [r[0] for r in ref], rtol=1e-9, atol=0.0)
+    # every socket that is opened and closed is closed after it was opened, on the same node and port
+    opened = {}
+    for rec in got:
+        key = (int(rec["node"]), int(rec["port"]))
+        if rec["type"] == 1:
+            assert key not in opened
+            opened[key] = float(rec["t"])
+        else:
+            assert float(rec["t"]) >= opened.pop(key)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_overflow_is_counted_not_written(backend, hostemu):
+    eng = engine_log(backend, hostemu, 0, 0, 1500.0, cap=16)
+    got = eng.net_events(0)
+    assert len(got) == 16 and eng.net_events_total > 16
+
+
+def test_conversion_to_the_datastore_schema(hostemu, tmp_path):
+    """The documents carry exactly the properties of NETWORK_EVENT_SCHEMA and load into the datastore's table layout
+    (uuid, timestamp, sim_uuid, json) with one executemany."""
+    from itsim_b200 import telemetry
+    eng = engine_log("hostemu", hostemu, 0, 0, 900.0)
+    docs = telemetry.network_event_documents(eng.net_events(0), sim_uuid="11111111-2222-3333-4444-555555555555")
+    assert docs
+    expected = {"sim_uuid", "timestamp", "type", "uuid", "uuid_node", "network_event_type", "pid", "protocol", "src", "dst"}
+    for d in docs:
+        assert set(d) == expected
+        assert d["network_event_type"] in ("open", "close") and d["protocol"] in ("TCP", "UDP", "NONE")
+        assert isinstance(d["src"][0], str) and isinstance(d["src"][1], int)
+    assert docs[0]["src"][0].startswith("192.168.4.")
+    reference_schema = "/root/reference/itsim/schemas/items.py"
+    if os.path.exists(reference_schema):
+        import jsonschema
+        scope = {}
+        source = open(reference_schema).read().split("def get_itsim_object_types")[0]
+        source = source.replace("import warlock", "")
+        exec(compile(source, reference_schema, "exec"), scope)          # the schema dicts only (warlock is not installed)
+        for d in docs[:50]:
+            jsonschema.validate(d, scope["NETWORK_EVENT_SCHEMA"])
+    rows = telemetry.datastore_rows(docs)
+    db = sqlite3.connect(str(tmp_path / "itsim.sqlite"))
+    db.execute("CREATE TABLE network_event (uuid TEXT PRIMARY KEY, timestamp TEXT, sim_uuid TEXT, json TEXT)")
+    db.executemany("INSERT INTO network_event VALUES (?, ?, ?, ?)", rows)
+    assert db.execute("SELECT COUNT(*) FROM network_event").fetchone()[0] == len(docs)
+    first = json.loads(db.execute("SELECT json FROM network_event ORDER BY timestamp LIMIT 1").fetchone()[0])
+    assert first["network_event_type"] == "open"
