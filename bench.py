@@ -178,6 +178,8 @@ def main() -> None:
     ap.add_argument("--max-events", type=int, default=0, help="future-event pool slots per replica (0 = model default)")
     ap.add_argument("--max-procs", type=int, default=0)
     ap.add_argument("--max-sockets", type=int, default=0)
+    ap.add_argument("--net-events", type=int, default=0,
+                    help="per-replica capacity of the network_event log in HBM (0 = off): the logging-on variant")
     ap.add_argument("--workload", default="network_simple", choices=["network_simple", "malware"],
                     help="malware = network_simple + the beaconing-malware overlay (BASELINE.json config 3)")
     args = ap.parse_args()
@@ -226,6 +228,7 @@ def main() -> None:
     t_cold0 = time.perf_counter()
     sim = netsimple.build() if args.workload == "network_simple" else netsimple.build_malware()
     sim.caps["arena_nodes"] = args.arena_nodes
+    sim.caps["net_event_records"] = args.net_events
     for key, val in (("max_events", args.max_events), ("max_procs", args.max_procs), ("max_sockets", args.max_sockets)):
         if val:
             sim.caps[key] = val
@@ -238,6 +241,7 @@ def main() -> None:
     spin_ms = engine.last_run_ms()
     for _ in range(args.warmup):
         engine.run(args.slice)
+    log_records_before = int(engine.telemetry()[L.TM_USER0 + 7])
 
     # ---- timed region 1: K steps queued back to back, device time ------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -296,7 +300,9 @@ def main() -> None:
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         events_per_step_gpu = events_dev / args.steps
-        algo_bytes = 2.0 * state["hot"] * args.replicas            # S_in + S_out per launch (B_log = 0 for C2)
+        log_records = (int(total[L.TM_USER0 + 7]) // max(1, world) - log_records_before) / (2.0 * args.steps)
+        # S_in + S_out per launch, plus B_log = 32 B per network_event record written in a step (0 when the log is off)
+        algo_bytes = 2.0 * state["hot"] * args.replicas + 32.0 * log_records
         launch_s = ms_dev * 1e-3 / args.steps
         achieved = algo_bytes / launch_s / 1e9
         cpu = None
@@ -314,6 +320,7 @@ def main() -> None:
                 "l2": "inputs larger than L2 (replica state %.2f GB per GPU vs 126 MB L2)" %
                       (args.replicas * (state["hot"] + state["arena"]) / 1e9),
                 "hot_bytes_per_replica": state["hot"], "arena_bytes_per_replica": state["arena"],
+                "net_event_records_per_step_per_gpu": log_records,
                 "cold_job_s": t_cold, "cold_job_h2d_bytes": h2d_model,
                 "spinup_events": spin_events, "spinup_ms": spin_ms,
                 "telemetry_allreduce_ms": allreduce_ms,

@@ -92,7 +92,8 @@ typedef struct itsb_net_event {   /* 32 bytes: one record of the datastore's `ne
 #define ITSB_TM_BYTES_RECEIVED   12
 #define ITSB_TM_DELIVERED        13                     /* deliveries that found a socket                      */
 #define ITSB_TM_DROPPED          14                     /* deliveries dropped at the node                      */
-#define ITSB_TM_USER0            15                     /* [15..22] model counters (STAT op)                   */
+#define ITSB_TM_USER0            15                     /* [15..22] model counters (STAT op); slot 22 counts the
+                                                           network_event records when that log is on           */
 #define ITSB_TM_LAT0             23                     /* [23..86] transit-delay histogram, log2-spaced bins  */
 #define ITSB_TM_SIZE             (ITSB_TM_LAT0 + ITSB_LAT_BINS)
 

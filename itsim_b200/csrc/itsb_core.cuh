@@ -461,6 +461,7 @@ ITSB_COLD void trace_put(Hdr* H, u32 kind, u32 prog, u32 node, u32 aux) {
 /* one `network_event` record (itsim/schemas/items.py:83-131): a socket opened (type 1) or closed (type 2) */
 ITSB_COLD void net_event_put(Hdr* H, u32 type, u32 node, u32 port, u32 src_ip, u32 prog, int pid, u32 protocol) {
     if (H->netlog == nullptr) return;
+    ((u64*)((unsigned char*)H + H->L.off_stats))[ITSB_TM_USER0 + 7] += 1;   /* records produced (user slot 7) */
     const u32 n = H->log_count;
     if (n < H->L.log_cap && lane_id() == 0) {
         itsb_net_event E;
