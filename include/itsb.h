@@ -133,9 +133,12 @@ typedef struct itsb_net {         /* one broadcast domain: override Network (ove
 typedef struct itsb_node {        /* static part of a node                                                        */
     uint32_t addr;                /* IPv4 address on its network                                                  */
     uint32_t net;                 /* index into nets                                                              */
-    uint32_t host;                /* hostname id (payload field f0 compares against it)                           */
+    uint32_t host;                /* override nodes: hostname id (payload field f0 compares against it);
+                                     shipped-itsim nodes: ITSB_NODE_* bits                                        */
     uint32_t flags;               /* shipped-itsim nodes: first interface | number of interfaces << 16            */
 } itsb_node;
+#define ITSB_NODE_FORWARDS 1u     /* a Router whose handle_packet_transit forwards:
+                                     interface, hop = _solve_transfer(dest); interface.link._transfer_packet(...)  */
 
 typedef struct itsb_iface {       /* Interface(link, address, routes) (itsim/network/interface.py:22-68); a node's
                                      interfaces are consecutive, loopback first (itsim/machine/node.py:74-77)      */

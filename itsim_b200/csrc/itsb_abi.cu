@@ -6,6 +6,9 @@
  *                  global ticket, pulls its hot block HBM -> shared memory with one TMA bulk copy
  *                  (cp.async.bulk + mbarrier), runs Simulator.run(duration) on it (itsb_core.cuh), pushes the block
  *                  back with a bulk store, claims the next.  Static model tables are staged once per CTA.
+ *                  A model whose replica does not fit one warp's share of shared memory (the 1 040-node LAN of
+ *                  config C4: ~650 KB per replica) is advanced in place instead: the same warp-per-replica code
+ *                  on the hot block in HBM, cached by L1/L2 (each replica is touched by one warp of one SM only).
  *   k_make_template / k_fan_out   build the t = 0 state once, replicate it to every replica with 128-bit copies.
  *   k_reduce_telemetry            column sums of the per-replica counters / histograms.
  *
@@ -16,152 +19,17 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
-#include "itsb_host_common.h"
+#include "itsb_kernel.cuh"
 
-using namespace itsb;
+extern "C" __global__ void k_run_in_place(const RunParams p);   /* itsb_inplace.cu */
 
-/* ---- TMA bulk copies (non-tensor form) --------------------------------------------------------------------------- */
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-/* ---- kernel parameters ---------------------------------------------------------------------------------------------- */
-struct RunParams {
-    Model model;            /* device pointers */
-    Layout layout;
-    unsigned char* hot;
-    ArenaNode* arena;
-    uint32_t* arena_free;
-    itsb_trace_rec* trace;
-    itsb_net_event* netlog;
-    uint64_t n_replicas;
-    uint64_t seed;
-    double duration;
-    unsigned long long* ticket;       /* next replica to claim */
-    unsigned long long* events_done;  /* events processed by this launch */
-    long long* first_failed;          /* min index of a replica with non-zero status, or LLONG_MAX */
-    uint32_t static_bytes;            /* size of the CTA-shared copy of the model tables */
-    uint32_t warps_per_cta;
-};
-
-struct StaticOffsets { uint32_t total; };
-
-static inline StaticOffsets static_offsets(const itsb_model_desc& d) {
-    StaticOffsets o;
-    uint32_t off = align_up((uint32_t)sizeof(Model), 16);
-    off = align_up(off + 8 * d.n_code, 16);
-    off = align_up(off + (uint32_t)sizeof(itsb_entry) * d.n_entries, 16);
-    off = align_up(off + (uint32_t)sizeof(itsb_dist) * d.n_dists, 16);
-    off = align_up(off + 8 * d.n_consts, 16);
-    off = align_up(off + (uint32_t)sizeof(itsb_net) * d.n_nets, 16);
-    off = align_up(off + (uint32_t)sizeof(itsb_node) * d.n_nodes, 16);
-    off = align_up(off + (uint32_t)sizeof(itsb_filter) * d.n_filters, 16);
-    off = align_up(off + (uint32_t)sizeof(itsb_iface) * d.n_ifaces, 16);
-    off = align_up(off + (uint32_t)sizeof(itsb_route) * d.n_routes, 16);
-    off = align_up(off + 4 * d.n_members, 16);
-    o.total = align_up(off, 128);
-    return o;
-}
-
-__device__ __forceinline__ void cta_copy(void* dst, const void* src, uint32_t bytes) {
-    const uint4* s = (const uint4*)src;
-    uint4* d = (uint4*)dst;
-#pragma unroll 1
-    for (uint32_t i = threadIdx.x; i < (bytes + 15) / 16; i += blockDim.x) d[i] = s[i];
-}
-
-/* Stages the model tables into shared memory (they are padded to 16 bytes on the device) behind a Model struct whose
- * pointers address the shared copies; returns that struct's address (the out-of-line engine functions reach the
- * tables through it). */
-__device__ __forceinline__ const Model* stage_model(const Model& g, unsigned char* sm) {
-    Model m = g;
-    uint32_t off = ((uint32_t)sizeof(Model) + 15) & ~15u;
-    cta_copy(sm + off, g.code, 8 * g.n_code);                 m.code = (const u64*)(sm + off);          off = (off + 8 * g.n_code + 15) & ~15u;
-    cta_copy(sm + off, g.entries, 8 * g.n_entries);           m.entries = (const itsb_entry*)(sm + off); off = (off + 8 * g.n_entries + 15) & ~15u;
-    cta_copy(sm + off, g.dists, 56 * g.n_dists);              m.dists = (const itsb_dist*)(sm + off);    off = (off + 56 * g.n_dists + 15) & ~15u;
-    cta_copy(sm + off, g.consts, 8 * g.n_consts);             m.consts = (const double*)(sm + off);      off = (off + 8 * g.n_consts + 15) & ~15u;
-    cta_copy(sm + off, g.nets, 32 * g.n_nets);                m.nets = (const itsb_net*)(sm + off);      off = (off + 32 * g.n_nets + 15) & ~15u;
-    cta_copy(sm + off, g.nodes, 16 * g.n_nodes);              m.nodes = (const itsb_node*)(sm + off);    off = (off + 16 * g.n_nodes + 15) & ~15u;
-    cta_copy(sm + off, g.filters, 16 * g.n_filters);          m.filters = (const itsb_filter*)(sm + off); off = (off + 16 * g.n_filters + 15) & ~15u;
-    cta_copy(sm + off, g.ifaces, 32 * g.n_ifaces);            m.ifaces = (const itsb_iface*)(sm + off);   off = (off + 32 * g.n_ifaces + 15) & ~15u;
-    cta_copy(sm + off, g.routes, 32 * g.n_routes);            m.routes = (const itsb_route*)(sm + off);   off = (off + 32 * g.n_routes + 15) & ~15u;
-    cta_copy(sm + off, g.members, 4 * g.n_members);           m.members = (const u32*)(sm + off);
-    if (threadIdx.x == 0) *(Model*)sm = m;
-    __syncthreads();
-    return (const Model*)sm;
-}
-
-/* ---- the engine kernel ------------------------------------------------------------------------------------------------ */
 extern "C" __global__ void __launch_bounds__(512, 1) k_run(const RunParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const Model* m = stage_model(p.model, smem);
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* hot = smem + p.static_bytes + (size_t)warp * p.layout.hot_bytes;
-    uint64_t* bar = (uint64_t*)(smem + p.static_bytes + (size_t)p.warps_per_cta * p.layout.hot_bytes) + warp;
-    if (lane == 0) mbar_init(bar, 1);
-    __syncwarp();
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    uint32_t phase = 0;
-    for (;;) {
-        unsigned long long r = 0;
-        if (lane == 0) r = atomicAdd(p.ticket, 1ull);
-        r = __shfl_sync(0xFFFFFFFFu, r, 0);
-        if (r >= p.n_replicas) break;
-        /* HBM -> shared: one bulk copy of the whole hot block, completion on the warp's mbarrier */
-        if (lane == 0) {
-            mbar_expect_tx(bar, p.layout.hot_bytes);
-            bulk_g2s(hot, p.hot + r * p.layout.hot_bytes, p.layout.hot_bytes, bar);
-        }
-        mbar_wait(bar, phase);
-        phase ^= 1;
-        Rep R;
-        bind_views(R, hot, &p.layout, m, p.arena + r * p.layout.arena_nodes, p.arena_free + r * p.layout.arena_nodes,
-                   p.trace ? p.trace + r * p.layout.trace_cap : nullptr,
-                   p.netlog ? p.netlog + r * p.layout.log_cap : nullptr, p.seed);
-        const unsigned long long events = run_replica(R, p.duration);
-        __syncwarp();
-        const int32_t status = R.hdr->status;
-        /* shared -> HBM */
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-            bulk_s2g(p.hot + r * p.layout.hot_bytes, hot, p.layout.hot_bytes);
-            bulk_wait_all();
-            atomicAdd(p.events_done, events);
-            if (status != 0) atomicMin(p.first_failed, (long long)r);
-        }
-        __syncwarp();
-    }
+    run_warps<false>(p, smem);
 }
 
 /* Builds the t = 0 hot block once (replica id patched in by k_fan_out). */
@@ -317,14 +185,25 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     /* one CTA per SM; as many resident replicas (warps) as shared memory holds */
     const size_t smem_max = e->prop.sharedMemPerBlockOptin;
     const size_t per_warp = (size_t)e->rp.layout.hot_bytes + 8;
-    if (e->so.total + per_warp + 128 > smem_max) { e->err = "model does not fit one warp's shared memory"; return ITSB_ERR_BAD_MODEL; }
-    uint32_t w = (uint32_t)((smem_max - e->so.total - 128) / per_warp);
-    if (w > 16) w = 16;
+    if (e->so.total + 1024 > smem_max) { e->err = "model tables do not fit shared memory"; return ITSB_ERR_BAD_MODEL; }
+    const char* force = getenv("ITSB_STATE_IN_HBM");
+    e->rp.state_in_hbm = (e->so.total + per_warp + 128 > smem_max) || (force && force[0] == '1') ? 1u : 0u;
+    uint32_t w;
+    if (e->rp.state_in_hbm) {
+        const char* nw = getenv("ITSB_IN_PLACE_WARPS");
+        w = nw ? (uint32_t)atoi(nw) : 16u;        /* no shared-memory limit: registers are (640 threads x 102) */
+        if (w < 1 || w > 20) w = 16;
+        e->smem_bytes = e->so.total + (size_t)w * 8 + 64;
+    } else {
+        w = (uint32_t)((smem_max - e->so.total - 128) / per_warp);
+        if (w > 16) w = 16;
+        e->smem_bytes = e->so.total + (size_t)w * e->rp.layout.hot_bytes + (size_t)w * 8 + 64;
+    }
     e->warps_per_cta = w;
     e->rp.warps_per_cta = w;
-    e->smem_bytes = e->so.total + (size_t)w * e->rp.layout.hot_bytes + (size_t)w * 8 + 64;
     e->grid = (uint32_t)e->prop.multiProcessorCount;
     CU(e, cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CU(e, cudaFuncSetAttribute(k_run_in_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     e->loaded = true;
     return ITSB_OK;
 }
@@ -381,7 +260,8 @@ int itsb_run_async(itsb_engine* e, double duration) {
     CU(e, cudaMemsetAsync(e->d_ticket, 0, sizeof(unsigned long long), e->stream));
     e->rp.duration = duration;
     if (!e->run_pending) CU(e, cudaEventRecord(e->ev_start, e->stream));
-    k_run<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
+    if (e->rp.state_in_hbm) k_run_in_place<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
+    else k_run<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
     CU(e, cudaGetLastError());
     CU(e, cudaEventRecord(e->ev_stop, e->stream));
     e->launches += 1;

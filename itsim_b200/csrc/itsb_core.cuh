@@ -355,14 +355,16 @@ ITSB_COLD void fail(Hdr* H, int status, u64 detail) {
     }
 }
 
-/* ---- event data word: kind[0:4] exc[4:12] proc[12:22] gen[22:32]; packet events: kind[0:4] arena-index[4:32] ---- */
+/* ---- event data word: kind[0:4] exc[4:12] proc[12:25] gen[25:32]; packet events: kind[0:4] arena-index[4:32] ---- */
+static const u32 PROC_MASK = 0x1FFF;   /* up to 8192 process slots per replica */
+static const u32 GEN_MASK = 0x7F;      /* slot generation: tells a finished process from the one that reuses its slot */
 ITSB_FN u32 ev_pack(u32 kind, u32 idx, u32 gen, u32 exc) {
-    return kind | ((exc & 0xFF) << 4) | ((idx & 0x3FF) << 12) | ((gen & 0x3FF) << 22);
+    return kind | ((exc & 0xFF) << 4) | ((idx & PROC_MASK) << 12) | ((gen & GEN_MASK) << 25);
 }
 ITSB_FN u32 ev_kind(u32 d) { return d & 0xF; }
 ITSB_FN u32 ev_exc(u32 d) { return (d >> 4) & 0xFF; }
-ITSB_FN u32 ev_idx(u32 d) { return (d >> 12) & 0x3FF; }
-ITSB_FN u32 ev_gen(u32 d) { return (d >> 22) & 0x3FF; }
+ITSB_FN u32 ev_idx(u32 d) { return (d >> 12) & PROC_MASK; }
+ITSB_FN u32 ev_gen(u32 d) { return (d >> 25) & GEN_MASK; }
 ITSB_FN u32 ev_pack_pkt(u32 kind, u32 node_index) { return kind | (node_index << 4); }
 ITSB_FN u32 ev_pkt(u32 d) { return d >> 4; }
 
@@ -746,7 +748,7 @@ ITSB_COLD void proc_exit(Hdr* H, u32 p) {
     Pcb& P = R.pcb[p];
     list_free_all(R, P);
     P.state = PS_FREE;
-    P.gen = (u16)((P.gen + 1) & 0x3FF);
+    P.gen = (u16)((P.gen + 1) & GEN_MASK);
     u32 top = H->pcb_free_top;
     R.pcb_free[top] = (u16)p;
     H->pcb_free_top = (u16)(top + 1);
@@ -1236,7 +1238,7 @@ ITSB_COLD int exec_cold(Hdr* H, u32 p, u64 ins) {
     }
     case OP_THROW: {
         u32 h = src_val(R, P, a);
-        ev_push_inl(R, H->now, ev_pack(ITSB_EV_THROW, h & 0x3FF, (h >> 16) & 0x3FF, imm));
+        ev_push_inl(R, H->now, ev_pack(ITSB_EV_THROW, h & PROC_MASK, (h >> 16) & GEN_MASK, imm));
         P.pc += 1;
         return XR_CONTINUE;
     }

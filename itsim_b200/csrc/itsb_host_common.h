@@ -64,7 +64,7 @@ static inline bool validate_model(const itsb_model_desc& d, const void* const* b
         }
     }
     const itsb_caps& c = d.caps;
-    if (c.max_events < 8 || c.max_events > 65535 || c.max_procs < 1 || c.max_procs > 1024 || c.max_sockets < 1 ||
+    if (c.max_events < 8 || c.max_events > 65535 || c.max_procs < 1 || c.max_procs > 8192 || c.max_sockets < 1 ||
         c.max_sockets > 0x3FFF || c.arena_nodes < 1 || c.arena_nodes >= (1u << 28)) {
         why = "capacity out of range"; return false;
     }

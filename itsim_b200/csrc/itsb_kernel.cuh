@@ -1,0 +1,166 @@
+/*
+ * itsb_kernel.cuh -- device side shared by the two translation units that instantiate the engine kernel
+ * (itsb_abi.cu: replicas staged in shared memory; itsb_inplace.cu: replicas advanced in place in HBM).  Two
+ * translation units so that each kernel's code is laid out on its own: the staged kernel is instruction-fetch
+ * bound and sensitive to what else sits around it.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include "itsb_host_common.h"
+
+using namespace itsb;
+
+/* ---- TMA bulk copies (non-tensor form) --------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+/* ---- kernel parameters ---------------------------------------------------------------------------------------------- */
+struct RunParams {
+    Model model;            /* device pointers */
+    Layout layout;
+    unsigned char* hot;
+    ArenaNode* arena;
+    uint32_t* arena_free;
+    itsb_trace_rec* trace;
+    itsb_net_event* netlog;
+    uint64_t n_replicas;
+    uint64_t seed;
+    double duration;
+    unsigned long long* ticket;       /* next replica to claim */
+    unsigned long long* events_done;  /* events processed by this launch */
+    long long* first_failed;          /* min index of a replica with non-zero status, or LLONG_MAX */
+    uint32_t static_bytes;            /* size of the CTA-shared copy of the model tables */
+    uint32_t warps_per_cta;
+    uint32_t state_in_hbm;            /* 1: replicas too large for shared memory are advanced in place (L1/L2-cached) */
+};
+
+struct StaticOffsets { uint32_t total; };
+
+static inline StaticOffsets static_offsets(const itsb_model_desc& d) {
+    StaticOffsets o;
+    uint32_t off = align_up((uint32_t)sizeof(Model), 16);
+    off = align_up(off + 8 * d.n_code, 16);
+    off = align_up(off + (uint32_t)sizeof(itsb_entry) * d.n_entries, 16);
+    off = align_up(off + (uint32_t)sizeof(itsb_dist) * d.n_dists, 16);
+    off = align_up(off + 8 * d.n_consts, 16);
+    off = align_up(off + (uint32_t)sizeof(itsb_net) * d.n_nets, 16);
+    off = align_up(off + (uint32_t)sizeof(itsb_node) * d.n_nodes, 16);
+    off = align_up(off + (uint32_t)sizeof(itsb_filter) * d.n_filters, 16);
+    off = align_up(off + (uint32_t)sizeof(itsb_iface) * d.n_ifaces, 16);
+    off = align_up(off + (uint32_t)sizeof(itsb_route) * d.n_routes, 16);
+    off = align_up(off + 4 * d.n_members, 16);
+    o.total = align_up(off, 128);
+    return o;
+}
+
+__device__ __forceinline__ void cta_copy(void* dst, const void* src, uint32_t bytes) {
+    const uint4* s = (const uint4*)src;
+    uint4* d = (uint4*)dst;
+#pragma unroll 1
+    for (uint32_t i = threadIdx.x; i < (bytes + 15) / 16; i += blockDim.x) d[i] = s[i];
+}
+
+/* Stages the model tables into shared memory (they are padded to 16 bytes on the device) behind a Model struct whose
+ * pointers address the shared copies; returns that struct's address (the out-of-line engine functions reach the
+ * tables through it). */
+__device__ __forceinline__ const Model* stage_model(const Model& g, unsigned char* sm) {
+    Model m = g;
+    uint32_t off = ((uint32_t)sizeof(Model) + 15) & ~15u;
+    cta_copy(sm + off, g.code, 8 * g.n_code);                 m.code = (const u64*)(sm + off);          off = (off + 8 * g.n_code + 15) & ~15u;
+    cta_copy(sm + off, g.entries, 8 * g.n_entries);           m.entries = (const itsb_entry*)(sm + off); off = (off + 8 * g.n_entries + 15) & ~15u;
+    cta_copy(sm + off, g.dists, 56 * g.n_dists);              m.dists = (const itsb_dist*)(sm + off);    off = (off + 56 * g.n_dists + 15) & ~15u;
+    cta_copy(sm + off, g.consts, 8 * g.n_consts);             m.consts = (const double*)(sm + off);      off = (off + 8 * g.n_consts + 15) & ~15u;
+    cta_copy(sm + off, g.nets, 32 * g.n_nets);                m.nets = (const itsb_net*)(sm + off);      off = (off + 32 * g.n_nets + 15) & ~15u;
+    cta_copy(sm + off, g.nodes, 16 * g.n_nodes);              m.nodes = (const itsb_node*)(sm + off);    off = (off + 16 * g.n_nodes + 15) & ~15u;
+    cta_copy(sm + off, g.filters, 16 * g.n_filters);          m.filters = (const itsb_filter*)(sm + off); off = (off + 16 * g.n_filters + 15) & ~15u;
+    cta_copy(sm + off, g.ifaces, 32 * g.n_ifaces);            m.ifaces = (const itsb_iface*)(sm + off);   off = (off + 32 * g.n_ifaces + 15) & ~15u;
+    cta_copy(sm + off, g.routes, 32 * g.n_routes);            m.routes = (const itsb_route*)(sm + off);   off = (off + 32 * g.n_routes + 15) & ~15u;
+    cta_copy(sm + off, g.members, 4 * g.n_members);           m.members = (const u32*)(sm + off);
+    if (threadIdx.x == 0) *(Model*)sm = m;
+    __syncthreads();
+    return (const Model*)sm;
+}
+
+/* ---- the engine kernel ------------------------------------------------------------------------------------------------
+ * Two instantiations: replicas staged in shared memory (the compiler then knows every state access is a shared-memory
+ * access), and replicas advanced in place in HBM for models too large for that.  One template, because letting a
+ * run-time flag pick the pointer made every access a generic-address access and cost 22 % on the staged path. */
+template <bool IN_PLACE>
+__device__ __forceinline__ void run_warps(const RunParams& p, unsigned char* smem) {
+    const Model* m = stage_model(p.model, smem);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* staged = smem + p.static_bytes + (size_t)warp * p.layout.hot_bytes;
+    uint64_t* bar = (uint64_t*)(smem + p.static_bytes + (IN_PLACE ? 0 : (size_t)p.warps_per_cta * p.layout.hot_bytes)) + warp;
+    if (!IN_PLACE) {
+        if (lane == 0) mbar_init(bar, 1);
+        __syncwarp();
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    uint32_t phase = 0;
+    for (;;) {
+        unsigned long long r = 0;
+        if (lane == 0) r = atomicAdd(p.ticket, 1ull);
+        r = __shfl_sync(0xFFFFFFFFu, r, 0);
+        if (r >= p.n_replicas) break;
+        unsigned char* hot;
+        if (IN_PLACE) {
+            hot = p.hot + r * p.layout.hot_bytes;
+        } else {
+            /* HBM -> shared: one bulk copy of the whole hot block, completion on the warp's mbarrier */
+            hot = staged;
+            if (lane == 0) {
+                mbar_expect_tx(bar, p.layout.hot_bytes);
+                bulk_g2s(hot, p.hot + r * p.layout.hot_bytes, p.layout.hot_bytes, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        }
+        Rep R;
+        bind_views(R, hot, &p.layout, m, p.arena + r * p.layout.arena_nodes, p.arena_free + r * p.layout.arena_nodes,
+                   p.trace ? p.trace + r * p.layout.trace_cap : nullptr,
+                   p.netlog ? p.netlog + r * p.layout.log_cap : nullptr, p.seed);
+        const unsigned long long events = run_replica(R, p.duration);
+        __syncwarp();
+        const int32_t status = R.hdr->status;
+        if (!IN_PLACE) fence_async_smem();      /* shared -> HBM */
+        __syncwarp();
+        if (lane == 0) {
+            if (!IN_PLACE) {
+                bulk_s2g(p.hot + r * p.layout.hot_bytes, hot, p.layout.hot_bytes);
+                bulk_wait_all();
+            }
+            atomicAdd(p.events_done, events);
+            if (status != 0) atomicMin(p.first_failed, (long long)r);
+        }
+        __syncwarp();
+    }
+}
+

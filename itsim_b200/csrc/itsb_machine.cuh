@@ -33,7 +33,7 @@ ITSB_FN bool proc_alive(Rep& R, u32 h) {
     const u32 p = h_idx(h);
     if (h == NIL32 || p >= R.hdr->L.max_proc) return false;
     const Pcb& P = R.pcb[p];
-    return P.state != PS_FREE && P.gen == (h_gen(h) & 0x3FF);
+    return P.state != PS_FREE && P.gen == (h_gen(h) & GEN_MASK);
 }
 
 /* ---- signals ---------------------------------------------------------------------------------------------------------- */
@@ -308,6 +308,43 @@ ITSB_COLD void m_send(Hdr* H, u32 p, u32 dst_ip, u32 dst_port, u32 size, u32 tag
     H->seq += count - 1;
 }
 
+/* Router forwarding: the packet (arena node k, left untouched) goes out again through the route to its destination;
+ * errors of the lookup are the forwarding node's (NoRouteToHost / NoSuchAddress abort the run like any exception
+ * raised inside _receive_packet). */
+ITSB_COLD void m_forward(Hdr* H, u32 node, u32 k) {
+    Rep R; rebind(R, H);
+    const Pkt K = *pkt_at(R, k);
+    u32 hop;
+    const int ifx = solve_transfer(R, node, K.dst_ip, &hop);
+    if (ifx < 0) { fail(H, ITSB_EXC_NO_ROUTE, K.dst_ip); return; }
+    const itsb_iface I = R.m.ifaces[ifx];
+    const itsb_net NET = R.m.nets[I.net];
+    u32 rcpt = 0;
+    if (hop != NET.bcast) {
+        bool found = false;
+        for (u32 m = 0; m < NET.n_nodes && !found; ++m) {
+            const u32 cand = R.m.members[NET.first_node + m];
+            const u32 fl = R.m.nodes[cand].flags;
+            for (u32 i = fl & 0xFFFF; i < (fl & 0xFFFF) + (fl >> 16); ++i)
+                if (R.iface_addr[i] == hop) { rcpt = cand + 1; found = true; break; }
+        }
+        if (!found) { fail(H, ITSB_EXC_NO_SUCH_ADDRESS, hop); return; }
+    }
+    const double lat = draw_dist(H, &R.m.dists[NET.lat_dist]);
+    const double bw = draw_dist(H, &R.m.dists[NET.bw_dist]);
+    const double duration = lat + (double)(8ull * (u64)K.size) / bw;
+    u32 k2 = arena_alloc(R);
+    if (k2 == NIL32) return;
+    Pkt F = K;
+    F.tag = (K.tag & 0xFFFF) | (rcpt << 16);
+    F.meta = node | (I.net << 16);
+    *pkt_at(R, k2) = F;
+    stat_add(R, ITSB_TM_LAT0 + latency_bin(duration), 1);
+    const u32 count = rcpt ? 1u : NET.n_nodes;
+    ev_push_inl(R, H->now + duration, ev_pack_pkt(ITSB_EV_DELIVER, k2));
+    H->seq += count - 1;
+}
+
 /* Node._receive_packet for every recipient (node.py:232-243), in connection order */
 ITSB_COLD void m_deliver(Hdr* H, u32 k) {
     Rep R; rebind(R, H);
@@ -316,6 +353,7 @@ ITSB_COLD void m_deliver(Hdr* H, u32 k) {
     const u32 rcpt = K.tag >> 16;
     const u32 count = rcpt ? 1u : NET.n_nodes;
     const u32 dst_port = K.ports >> 16;
+    u32 forward_from = NIL32;
     for (u32 m = 0; m < count; ++m) {
         const u32 node = rcpt ? rcpt - 1 : R.m.members[NET.first_node + m];
         const u32 fl = R.m.nodes[node].flags;
@@ -329,6 +367,15 @@ ITSB_COLD void m_deliver(Hdr* H, u32 k) {
             for (u16 q = R.node[node].sock_head; q != NIL16; q = R.sock[q].next)
                 if (R.sock[q].port == dst_port) { s = (int)q; break; }
         count_event(R, ITSB_EV_DELIVER, 10, node, (K.size & 0x7FFFFFFFu) | (s >= 0 ? 0x80000000u : 0u));
+        if (!mine && (R.m.nodes[node].host & ITSB_NODE_FORWARDS)) {
+            /* Node.handle_packet_transit overridden with the forwarding rule the reference documents as intent
+               (sphinx/source/networks.rst:275-280):
+               interface, hop = self._solve_transfer(dest); interface.link._transfer_packet(packet, hop).
+               Only a unicast hop can end at a node the packet is not for, so this is the pass's only recipient
+               and the forwarding itself runs after the loop. */
+            forward_from = node;
+            continue;
+        }
         if (s >= 0) {
             /* Socket._enqueue: queue.put(packet); packet_signal.turn_on() */
             u32 an = arena_alloc(R);
@@ -347,6 +394,7 @@ ITSB_COLD void m_deliver(Hdr* H, u32 k) {
             stat_add(R, ITSB_TM_DROPPED, 1);
         }
     }
+    if (forward_from != NIL32) m_forward(H, forward_from, k);
     arena_release(R, k);
 }
 
