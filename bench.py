@@ -180,8 +180,10 @@ def main() -> None:
     ap.add_argument("--max-sockets", type=int, default=0)
     ap.add_argument("--net-events", type=int, default=0,
                     help="per-replica capacity of the network_event log in HBM (0 = off): the logging-on variant")
-    ap.add_argument("--workload", default="network_simple", choices=["network_simple", "malware"],
-                    help="malware = network_simple + the beaconing-malware overlay (BASELINE.json config 3)")
+    ap.add_argument("--workload", default="network_simple", choices=["network_simple", "malware", "large_lan"],
+                    help="malware = network_simple + the beaconing-malware overlay (BASELINE.json config 3); "
+                         "large_lan = 1024 endpoints + 16 forwarding routers per replica (config 4; use "
+                         "--replicas 10000 --slice 2 --spinup 6)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -226,8 +228,12 @@ def main() -> None:
 
     # ---- cold job through the public API: compile, upload, allocate, initialise --------------------------------
     t_cold0 = time.perf_counter()
-    sim = netsimple.build() if args.workload == "network_simple" else netsimple.build_malware()
-    sim.caps["arena_nodes"] = args.arena_nodes
+    if args.workload == "large_lan":
+        from itsim_b200 import machine_models
+        sim = machine_models.large_lan()
+    else:
+        sim = netsimple.build() if args.workload == "network_simple" else netsimple.build_malware()
+        sim.caps["arena_nodes"] = args.arena_nodes
     sim.caps["net_event_records"] = args.net_events
     for key, val in (("max_events", args.max_events), ("max_procs", args.max_procs), ("max_sockets", args.max_sockets)):
         if val:
@@ -313,7 +319,9 @@ def main() -> None:
             "warmup": args.warmup, "ms_per_step": ms_dev_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"{args.workload} (50 endpoints, /24) x {args.replicas} replicas per GPU, "
+                "workload": f"{args.workload} "
+                            f"({'1024 endpoints + 16 routers' if args.workload == 'large_lan' else '50 endpoints, /24'})"
+                            f" x {args.replicas} replicas per GPU, "
                             f"step = run({args.slice:g} simulated s) on every replica after {args.spinup:g} s spin-up",
                 "replicas_per_gpu": args.replicas, "slice_s": args.slice, "spinup_s": args.spinup, "seed": args.seed,
                 "events_per_step_per_gpu": events_per_step_gpu,

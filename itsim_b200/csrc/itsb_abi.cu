@@ -185,7 +185,9 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     /* one CTA per SM; as many resident replicas (warps) as shared memory holds */
     const size_t smem_max = e->prop.sharedMemPerBlockOptin;
     const size_t per_warp = (size_t)e->rp.layout.hot_bytes + 8;
-    if (e->so.total + 1024 > smem_max) { e->err = "model tables do not fit shared memory"; return ITSB_ERR_BAD_MODEL; }
+    e->rp.model_dev = e->d_model;
+    e->rp.tables_in_hbm = (e->so.total + 4096 > smem_max) ? 1u : 0u;
+    if (e->rp.tables_in_hbm) { e->so.total = 128; e->rp.static_bytes = 128; }
     const char* force = getenv("ITSB_STATE_IN_HBM");
     e->rp.state_in_hbm = (e->so.total + per_warp + 128 > smem_max) || (force && force[0] == '1') ? 1u : 0u;
     uint32_t w;

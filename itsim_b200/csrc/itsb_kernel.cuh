@@ -60,6 +60,8 @@ struct RunParams {
     uint32_t static_bytes;            /* size of the CTA-shared copy of the model tables */
     uint32_t warps_per_cta;
     uint32_t state_in_hbm;            /* 1: replicas too large for shared memory are advanced in place (L1/L2-cached) */
+    uint32_t tables_in_hbm;           /* 1: the model tables themselves exceed shared memory: read in place (L1-cached) */
+    const Model* model_dev;           /* the Model struct in device memory (pointers to the tables in HBM)             */
 };
 
 struct StaticOffsets { uint32_t total; };
@@ -115,7 +117,7 @@ __device__ __forceinline__ const Model* stage_model(const Model& g, unsigned cha
  * run-time flag pick the pointer made every access a generic-address access and cost 22 % on the staged path. */
 template <bool IN_PLACE>
 __device__ __forceinline__ void run_warps(const RunParams& p, unsigned char* smem) {
-    const Model* m = stage_model(p.model, smem);
+    const Model* m = p.tables_in_hbm ? p.model_dev : stage_model(p.model, smem);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* staged = smem + p.static_bytes + (size_t)warp * p.layout.hot_bytes;
     uint64_t* bar = (uint64_t*)(smem + p.static_bytes + (IN_PLACE ? 0 : (size_t)p.warps_per_cta * p.layout.hot_bytes)) + warp;

@@ -157,7 +157,14 @@ class Endpoint(Node):
 
 
 class Router(Node):
-    """``itsim/network/router.py:4-15`` (no forwarding in the reference either)."""
+    """``itsim/network/router.py:4-15``.  The reference's Router is an empty Node (packets in transit are dropped,
+    node.py:245-250); ``forwarding=True`` installs the rule the reference documents as intent for
+    ``handle_packet_transit`` (sphinx/source/networks.rst:275-280): ``interface, hop = _solve_transfer(dest);
+    interface.link._transfer_packet(packet, hop)``."""
+
+    def __init__(self, forwarding: bool = False) -> None:
+        super().__init__()
+        self.forwarding = forwarding
 
 
 def compile_machine(sim: Simulator) -> Compiled:
@@ -210,7 +217,8 @@ def compile_machine(sim: Simulator) -> Compiled:
         n_if = len(ifaces) - first_iface
         visible = [i for i in node.interfaces() if not i.address.is_loopback]
         node_rows[node.index] = (int((visible or list(node.interfaces()))[0].address),
-                                 links.index(list(node.interfaces())[0].link), 0, first_iface | (n_if << 16))
+                                 links.index(list(node.interfaces())[0].link),
+                                 1 if getattr(node, "forwarding", False) else 0, first_iface | (n_if << 16))
 
     init = np.zeros(len(sim._machine_procs), dtype=L.INIT_DTYPE)
     for i, (node, delay, program, regs) in enumerate(sim._machine_procs):

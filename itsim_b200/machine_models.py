@@ -389,5 +389,65 @@ def dhcp_exchange(trace_records: int = 8192, clients: int = 3) -> Simulator:
     return sim
 
 
-SCENARIOS = {"dhcp_exchange": dhcp_exchange, "packet_transfer": packet_transfer, "broadcast": broadcast, "thread_lifecycle": thread_lifecycle,
+LAN_PORT, TAG_LAN_REQUEST, TAG_LAN_REPLY = 10000, 4, 5
+
+
+def large_lan(trace_records: int = 0, subnets: int = 16, per_subnet: int = 64) -> Simulator:
+    """Config C4: `subnets` /25 access links of `per_subnet` endpoints + one forwarding router each, routers joined by a
+    backbone /24, Relay default routes; same topology and bodies as ``oracle/machine_scenarios.large_lan`` (which
+    builds it from the reference's classes).  One replica is ~650 KB of state at 16 x 64: the engine advances it in
+    place in HBM (``k_run_in_place``)."""
+    from .machine import Relay
+    from .random import normal
+    from .units import GbPS
+    sim = Simulator()
+    a = sim.asm
+    d_interval = sim.dist(uniform(3.0, 6.0))
+
+    a.thread_program("server", 1)
+    a.bind(LAN_PORT)
+    a.label("loop")
+    a.recvt()
+    a.jnei(PKT_TAG, TAG_LAN_REQUEST, "loop")            # if packet.payload.get("content") == "request":
+    a.li(R0, 32)
+    a.sendl(DST_PKT_SRC, R0, TAG_LAN_REPLY)             #     socket.send(packet.source, 32, reply)
+    a.jmp("loop")
+    a.end_thread_program()
+
+    a.thread_program("client", 2)                       # r2 = peer address, r3 = port (run_proc arguments)
+    a.bind(0)
+    a.label("loop")
+    a.advance(d_interval)
+    a.li(R0, 128)
+    a.sendl(DST_BCAST, R0, TAG_CHATTER, port=LAN_PORT)  # every non-loopback interface (there is one)
+    a.li(R0, 64)
+    a.sendl(DST_REGS, R0, TAG_LAN_REQUEST)              # socket.send((peer, 10000), 64, request)
+    a.jmp("loop")
+    a.end_thread_program()
+
+    backbone = Link("10.30.0.0/24", normal(5 * MS, 1 * MS), constant(1 * GbPS))
+    access = [Link(f"10.20.{i}.0/25", normal(5 * MS, 1 * MS), constant(1 * GbPS)) for i in range(subnets)]
+    routers = []
+    for i in range(subnets):
+        router = Router(forwarding=True)
+        router.connected_to_static(access[i], 1)
+        router.connected_to_static(backbone, i + 1, [Relay(as_address(j + 1, backbone.cidr), f"10.20.{j}.0/25")
+                                                    for j in range(subnets) if j != i])
+        routers.append(router)
+    for i in range(subnets):
+        for h in range(per_subnet):
+            ep = Endpoint()
+            ep.connected_to_static(access[i], h + 2, [Relay(as_address(1, access[i].cidr))])
+            peer = int(as_address(h + 2, access[(i + 1) % subnets].cidr))
+            ep.run_proc(sim, "server")
+            ep.run_proc(sim, "client", 0, 0, peer, LAN_PORT)
+    n_ep = subnets * per_subnet
+    procs = 2 * n_ep + 2 * n_ep + 64                    # bodies + the two select helpers of every blocked recv
+    sim.caps.update(max_events=max(64, n_ep + 64), max_procs=procs, max_sockets=2 * n_ep + 16,
+                    arena_nodes=max(2048, 64 * n_ep), trace_records=trace_records, max_threads=2 * n_ep + 16,
+                    max_tasks=2 * n_ep + 16, max_signals=min(0x3FFF, 9 * n_ep + 64))
+    return sim
+
+
+SCENARIOS = {"large_lan": large_lan, "dhcp_exchange": dhcp_exchange, "packet_transfer": packet_transfer, "broadcast": broadcast, "thread_lifecycle": thread_lifecycle,
              "process_lifecycle": process_lifecycle, "link_delay": link_delay}

@@ -306,9 +306,74 @@ def dhcp_exchange(seed: int = 0, replica: int = 0, duration: float = 10.0, clien
     return arr, out
 
 
+PROGS_LAN = {"server": 1, "client": 2}
+LAN_PORT, TAG_CHATTER, TAG_REQUEST, TAG_REPLY = 10000, 3, 4, 5
+
+
+def large_lan(seed: int = 0, replica: int = 0, duration: float = 8.0, subnets: int = 16, per_subnet: int = 64):
+    """Config C4: `subnets` access links (/25) of `per_subnet` endpoints, one router per access
+    link, all routers on a backbone /24; endpoints reach other subnets through Relay default routes.  Built from the
+    reference's own Link / Endpoint / Router / Relay classes; the router's forwarding is the two-line rule the
+    reference documents as intent for ``Node.handle_packet_transit`` (sphinx/source/networks.rst:275-280, SURVEY
+    section 8-f row 1).  Traffic: every endpoint runs a server (recv loop on port 10000 answering requests) and a client
+    (every U(3, 6) s: a 128-byte broadcast on its link, then a 64-byte request to the same host number on the next
+    subnet) -- the bodies of tests/integ/test_broadcast.py:28-40 and test_packet_transfer.py:16-47 combined."""
+    from greensim.random import uniform, constant, normal
+    from itsim.machine.endpoint import Endpoint
+    from itsim.network.link import Link
+    from itsim.network.route import Relay
+    from itsim.network.router import Router
+    from itsim.simulator import advance
+    from itsim.types import Protocol, as_address
+    from itsim.units import MS, GbPS
+
+    class ForwardingRouter(Router):
+        def handle_packet_transit(self, packet):
+            interface, hop = self._solve_transfer(packet.dest.hostname_as_address())
+            interface.link._transfer_packet(packet, hop)
+
+    sc = Scenario(PROGS_LAN, seed, replica)
+    interval = uniform(3.0, 6.0)
+
+    def server(context):
+        with context.node.bind(Protocol.UDP, LAN_PORT) as socket:
+            while True:
+                packet = socket.recv()
+                if packet.payload.get("content") == "request":
+                    socket.send(packet.source, 32, {"content": "reply"})
+
+    def client(context, peer):
+        with context.node.bind(Protocol.UDP) as socket:
+            while True:
+                advance(next(interval))
+                for interface in context.node.interfaces():
+                    if not interface.address.is_loopback:
+                        socket.send((interface.cidr.broadcast_address, LAN_PORT), 128, {"content": "chatter"})
+                socket.send((peer, LAN_PORT), 64, {"content": "request"})
+
+    backbone = Link("10.30.0.0/24", normal(5 * MS, 1 * MS), constant(1 * GbPS))
+    access = [Link(f"10.20.{i}.0/25", normal(5 * MS, 1 * MS), constant(1 * GbPS)) for i in range(subnets)]
+    for i in range(subnets):
+        router = ForwardingRouter()
+        sc.node(router)
+        router.connected_to_static(access[i], 1)
+        router.connected_to_static(backbone, i + 1, [Relay(as_address(j + 1, backbone.cidr), f"10.20.{j}.0/25")
+                                                    for j in range(subnets) if j != i])
+    for i in range(subnets):
+        for h in range(per_subnet):
+            ep = Endpoint()
+            sc.node(ep)
+            ep.connected_to_static(access[i], h + 2, [Relay(as_address(1, access[i].cidr))])
+            peer = as_address(h + 2, access[(i + 1) % subnets].cidr)
+            ep.run_proc(sc.sim, server)
+            ep.run_proc(sc.sim, client, peer)
+    sc.run(duration)
+    return sc.result()
+
+
 SCENARIOS: Dict[str, Callable] = {
     "packet_transfer": packet_transfer, "broadcast": broadcast, "thread_lifecycle": thread_lifecycle,
-    "process_lifecycle": process_lifecycle, "dhcp_exchange": dhcp_exchange,
+    "process_lifecycle": process_lifecycle, "dhcp_exchange": dhcp_exchange, "large_lan": large_lan,
 }
 
 if __name__ == "__main__":

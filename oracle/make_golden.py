@@ -46,11 +46,17 @@ def machine_golden() -> None:
     jobs = [("thread_lifecycle", {}), ("process_lifecycle", {}),
             ("packet_transfer", {"seed": 0, "replica": 0}), ("packet_transfer", {"seed": 5, "replica": 77}),
             ("broadcast", {"seed": 0, "replica": 0}), ("broadcast", {"seed": 3, "replica": 11, "duration": 60.0}),
-            ("dhcp_exchange", {"seed": 0, "replica": 0}), ("dhcp_exchange", {"seed": 4, "replica": 9, "duration": 100.0})]
+            ("dhcp_exchange", {"seed": 0, "replica": 0}), ("dhcp_exchange", {"seed": 4, "replica": 9, "duration": 100.0}),
+            # config C4: small instance kept as a full trace, the 16 x 64 instance as counts + digest (~45 s of oracle)
+            ("large_lan", {"seed": 1, "replica": 2, "duration": 20.0, "subnets": 4, "per_subnet": 16}),
+            ("large_lan", {"seed": 0, "replica": 0, "duration": 8.0, "subnets": 16, "per_subnet": 64})]
     for name, kwargs in jobs:
         arr, summary = ms.SCENARIOS[name](**kwargs)
         tag = name + "".join(f"_{k[0]}{int(v)}" for k, v in kwargs.items())
-        np.savez_compressed(os.path.join(GOLDEN, f"machine_{tag}.npz"), trace=arr)
+        summary["t_digest"] = evtrace.trace_digest(arr)
+        summary["t_last"] = float(arr["t"][-1]) if len(arr) else 0.0
+        if len(arr) < 60000:
+            np.savez_compressed(os.path.join(GOLDEN, f"machine_{tag}.npz"), trace=arr)
         out[tag] = summary
         print("machine", tag, summary["events"], flush=True)
     json.dump(out, open(os.path.join(GOLDEN, "machine_summaries.json"), "w"), indent=1, sort_keys=True)
