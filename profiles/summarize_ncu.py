@@ -65,16 +65,21 @@ def main():
     if lib:
         with tempfile.TemporaryDirectory() as tmp:
             subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-            cubins = [f for f in os.listdir(tmp) if f.endswith(".cubin")]
-            text = subprocess.run(["nvdisasm", "-c", os.path.join(tmp, cubins[0])], capture_output=True, text=True).stdout
-        fn, seq = None, []
-        for line in text.splitlines():
-            m = re.match(r"^([_a-zA-Z$.][A-Za-z0-9_$.]*):", line)
-            if m and not m.group(1).startswith(".L"):
-                fn = m.group(1)
-            elif re.match(r"^ +/\*[0-9a-f]+\*/", line):
-                seq.append(fn)
-        seq = [f for f in seq if f == ".text.k_run" or f.startswith("$k_run$") or f.startswith("$__internal")]
+            cubins = sorted(f for f in os.listdir(tmp) if f.endswith(".cubin"))
+            texts = [subprocess.run(["nvdisasm", "-c", os.path.join(tmp, c)], capture_output=True, text=True).stdout
+                     for c in cubins]
+        seq = []
+        for text in texts:        # the cubin (translation unit) that holds the profiled kernel
+            fn, cand = None, []
+            for line in text.splitlines():
+                m = re.match(r"^([_a-zA-Z$.][A-Za-z0-9_$.]*):", line)
+                if m and not m.group(1).startswith(".L"):
+                    fn = m.group(1)
+                elif re.match(r"^ +/\*[0-9a-f]+\*/", line):
+                    cand.append(fn)
+            cand = [f for f in cand if f == ".text.k_run" or f.startswith("$k_run$") or f.startswith("$__internal")]
+            if len(cand) == len(data):
+                seq = cand
         if len(seq) == len(data):
             ex, sm, ni, size = (collections.Counter() for _ in range(4))
             for f, r in zip(seq, data):
