@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ITSB_ABI_VERSION 1
+#define ITSB_ABI_VERSION 2
 
 /* ---- engine errors (negative) ------------------------------------------------------------------------------ */
 #define ITSB_OK                    0
@@ -82,6 +82,20 @@ typedef struct itsb_net_event {   /* 32 bytes: one record of the datastore's `ne
     uint32_t reserved;
 } itsb_net_event;
 
+typedef struct itsb_connection {  /* 40 bytes: one connection record, the JSON `Socket.log_pair` prints
+                                     (examples/network_simple/network_simple_overrides.py:152-177)                  */
+    double   t_end;               /* End_Time: when the pair was logged                                            */
+    double   t_start;             /* Start_Time: when the first packet of the pair was sent / received             */
+    uint32_t local_ip;            /* Local_IP: destination of the inbound packet (0: none)                         */
+    uint32_t remote_ip;           /* Remote_IP: ADDRESS field of the outbound payload, else its destination (0)    */
+    uint32_t sent_bytes;          /* Sent_Bytes: size of the outbound packet (0: none)                             */
+    uint32_t received_bytes;      /* Received_Bytes: size of the inbound packet (0: none)                          */
+    uint16_t local_port, remote_port;
+    uint16_t node;
+    uint8_t  inbound;             /* Direction: 1 "Inbound", 0 "Outbound"                                          */
+    uint8_t  has;                 /* bit 0: an inbound packet is part of the pair, bit 1: an outbound one          */
+} itsb_connection;
+
 /* ---- telemetry: what the datastore would have been told, reduced on device ---------------------------------- */
 #define ITSB_LAT_BINS 64
 /* slots of the uint64 telemetry vector returned by itsb_read_telemetry / reduced by itsb_allreduce_telemetry */
@@ -93,7 +107,8 @@ typedef struct itsb_net_event {   /* 32 bytes: one record of the datastore's `ne
 #define ITSB_TM_DELIVERED        13                     /* deliveries that found a socket                      */
 #define ITSB_TM_DROPPED          14                     /* deliveries dropped at the node                      */
 #define ITSB_TM_USER0            15                     /* [15..22] model counters (STAT op); slot 22 counts the
-                                                           network_event records when that log is on           */
+                                                           network_event records, slot 21 the connection
+                                                           records, when those logs are on                     */
 #define ITSB_TM_LAT0             23                     /* [23..86] transit-delay histogram, log2-spaced bins  */
 #define ITSB_TM_SIZE             (ITSB_TM_LAT0 + ITSB_LAT_BINS)
 
@@ -192,12 +207,19 @@ typedef struct itsb_caps {        /* per-replica capacities; exceeding one flags
     uint32_t max_threads, max_tasks, max_signals;   /* shipped-itsim Thread / Process / Signal tables (0 = none)  */
     uint32_t table_words;         /* per-replica uint32 model table (TLOAD / TSTORE), zero-initialised            */
     uint32_t net_event_records;   /* per-replica capacity of the network_event log in HBM (0 = logging off)       */
+    uint32_t connection_records;  /* per-replica capacity of the connection log in HBM (0 = correlation off)      */
+    uint32_t connection_window;   /* packets a socket remembers per direction while waiting for the other half of
+                                     a pair (1..4096; the reference's dictionaries are unbounded, overrides.py:80-81;
+                                     a full window logs its oldest entry as unanswered, as flush_logs would at
+                                     close)                                                                       */
 } itsb_caps;
 
 typedef struct itsb_model_desc {
     uint32_t abi_version;
     uint32_t n_code, n_entries, n_dists, n_consts, n_nets, n_nodes, n_init, n_filters;
     uint32_t n_ifaces, n_routes, n_members;
+    uint32_t address_tags;        /* bit i: payloads tagged i carry an ADDRESS entry in field f1 (Remote_IP of the
+                                     connection records, overrides.py:158-162)                                    */
     itsb_caps caps;
 } itsb_model_desc;
 
@@ -252,6 +274,10 @@ int itsb_read_trace(itsb_engine* e, uint64_t replica, itsb_trace_rec* dst, size_
  * database.py:44-57).  dst receives up to cap records of one replica; n_total = records produced (may exceed the
  * capacity the model asked for: later ones are counted but not kept).                                               */
 int itsb_read_net_events(itsb_engine* e, uint64_t replica, itsb_net_event* dst, size_t cap, size_t* n_total);
+
+/* The connection records of one replica, in the order `Socket.log_pair` was called
+ * (network_simple_overrides.py:102-120,152-186).  *n_total = records produced (may exceed the capacity kept). */
+int itsb_read_connections(itsb_engine* e, uint64_t replica, itsb_connection* dst, size_t cap, size_t* n_total);
 
 /* Replaces: the records itsim/logging.py + itsim/datastore would receive (README.md:18-50), reduced on the device:
  * ITSB_TM_SIZE uint64 counters / histogram bins summed over this engine's replicas.                               */

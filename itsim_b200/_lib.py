@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libitsim_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 TM_KIND0, TM_PACKETS_SENT, TM_BYTES_SENT, TM_PACKETS_RECEIVED, TM_BYTES_RECEIVED = 0, 9, 10, 11, 12
 TM_DELIVERED, TM_DROPPED, TM_USER0, TM_LAT0, LAT_BINS = 13, 14, 15, 23, 64
 TM_SIZE = TM_LAT0 + LAT_BINS
@@ -49,6 +49,10 @@ IFACE_DTYPE = np.dtype([("node", "<u4"), ("net", "<u4"), ("addr0", "<u4"), ("fir
 ROUTE_DTYPE = np.dtype([("net", "<u4"), ("mask", "<u4"), ("prefixlen", "<u4"), ("kind", "<u4"), ("gateway", "<u4"),
                         ("reserved", "<u4", (3,))])
 FILTER_DTYPE = np.dtype([("tags_always", "<u4"), ("tags_if_host", "<u4"), ("tags_if_list", "<u4"), ("reserved", "<u4")])
+CONNECTION_DTYPE = np.dtype([("t_end", "<f8"), ("t_start", "<f8"), ("local_ip", "<u4"), ("remote_ip", "<u4"),
+                             ("sent_bytes", "<u4"), ("received_bytes", "<u4"), ("local_port", "<u2"),
+                             ("remote_port", "<u2"), ("node", "<u2"), ("inbound", "u1"), ("has", "u1")])
+assert CONNECTION_DTYPE.itemsize == 40
 assert TRACE_DTYPE.itemsize == 16 and DIST_DTYPE.itemsize == 56 and NET_DTYPE.itemsize == 32
 assert NODE_DTYPE.itemsize == 16 and ENTRY_DTYPE.itemsize == 8 and INIT_DTYPE.itemsize == 32
 assert IFACE_DTYPE.itemsize == 32 and ROUTE_DTYPE.itemsize == 32
@@ -58,14 +62,15 @@ class Caps(C.Structure):
     _fields_ = [("max_events", C.c_uint32), ("max_procs", C.c_uint32), ("max_sockets", C.c_uint32),
                 ("max_packets", C.c_uint32), ("arena_nodes", C.c_uint32), ("trace_records", C.c_uint32),
                 ("max_threads", C.c_uint32), ("max_tasks", C.c_uint32), ("max_signals", C.c_uint32),
-                ("table_words", C.c_uint32), ("net_event_records", C.c_uint32)]
+                ("table_words", C.c_uint32), ("net_event_records", C.c_uint32),
+                ("connection_records", C.c_uint32), ("connection_window", C.c_uint32)]
 
 
 class ModelDesc(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("n_code", C.c_uint32), ("n_entries", C.c_uint32),
                 ("n_dists", C.c_uint32), ("n_consts", C.c_uint32), ("n_nets", C.c_uint32), ("n_nodes", C.c_uint32),
                 ("n_init", C.c_uint32), ("n_filters", C.c_uint32), ("n_ifaces", C.c_uint32), ("n_routes", C.c_uint32),
-                ("n_members", C.c_uint32), ("caps", Caps)]
+                ("n_members", C.c_uint32), ("address_tags", C.c_uint32), ("caps", Caps)]
 
 
 class EngineError(RuntimeError):
@@ -87,6 +92,7 @@ _SIGNATURES = {
     "itsb_read_now": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "itsb_read_trace": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "itsb_read_net_events": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "itsb_read_connections": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "itsb_read_telemetry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsb_read_replica_telemetry": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]),
     "itsb_allreduce_telemetry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -26,8 +26,10 @@
 #include "itsb_kernel.cuh"
 
 extern "C" __global__ void k_run_in_place(const RunParams p);   /* itsb_inplace.cu */
+extern "C" __global__ void k_run_wide(const RunParams p);       /* itsb_wide.cu: 13..16 warps per CTA */
 
-extern "C" __global__ void __launch_bounds__(512, 1) k_run(const RunParams p) {
+/* up to 12 warps per CTA (what shared memory allows the flagship model): 168 registers per thread, no spills */
+extern "C" __global__ void __launch_bounds__(384, 1) k_run(const RunParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     run_warps<false>(p, smem);
 }
@@ -36,7 +38,9 @@ extern "C" __global__ void __launch_bounds__(512, 1) k_run(const RunParams p) {
 extern "C" __global__ void k_make_template(const RunParams p, const Model* model, unsigned char* tmpl,
                                            ArenaNode* arena0, uint32_t* free0) {
     Rep R;
-    bind_views(R, tmpl, &p.layout, model, arena0, free0, nullptr, nullptr, p.seed);
+    Binding B;
+    B.arena = arena0; B.arena_free = free0; B.trace = nullptr; B.netlog = nullptr; B.connlog = nullptr; B.conntab = nullptr;
+    bind_views(R, tmpl, &p.layout, model, B, p.seed);
     init_replica(R, 0);
 }
 
@@ -91,6 +95,8 @@ struct itsb_engine {
     uint32_t* d_arena_free = nullptr;
     itsb_trace_rec* d_trace = nullptr;
     itsb_net_event* d_netlog = nullptr;
+    itsb_connection* d_connlog = nullptr;
+    ConnEnt* d_conntab = nullptr;
     unsigned long long* d_ticket = nullptr;       /* [0] ticket, [1] events_done */
     long long* d_first_failed = nullptr;
     unsigned long long* d_telemetry = nullptr;
@@ -116,6 +122,8 @@ struct itsb_engine {
 
 static void free_replicas(itsb_engine* e) {
     cudaFree(e->d_hot); cudaFree(e->d_arena); cudaFree(e->d_arena_free); cudaFree(e->d_trace); cudaFree(e->d_netlog);
+    cudaFree(e->d_connlog); cudaFree(e->d_conntab);
+    e->d_connlog = nullptr; e->d_conntab = nullptr;
     e->d_hot = nullptr; e->d_arena = nullptr; e->d_arena_free = nullptr; e->d_trace = nullptr; e->d_netlog = nullptr;
     e->n_replicas = 0;
 }
@@ -205,6 +213,7 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     e->rp.warps_per_cta = w;
     e->grid = (uint32_t)e->prop.multiProcessorCount;
     CU(e, cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CU(e, cudaFuncSetAttribute(k_run_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     CU(e, cudaFuncSetAttribute(k_run_in_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     e->loaded = true;
     return ITSB_OK;
@@ -221,7 +230,11 @@ int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first
     if (L.trace_cap) CU(e, cudaMalloc(&e->d_trace, (size_t)n * L.trace_cap * sizeof(itsb_trace_rec)));
     if (L.log_cap) CU(e, cudaMalloc(&e->d_netlog, (size_t)n * L.log_cap * sizeof(itsb_net_event)));
     e->rp.hot = e->d_hot; e->rp.arena = e->d_arena; e->rp.arena_free = e->d_arena_free; e->rp.trace = e->d_trace;
-    e->rp.netlog = e->d_netlog;
+    if (L.conn_cap) {
+        CU(e, cudaMalloc(&e->d_connlog, (size_t)n * L.conn_cap * sizeof(itsb_connection)));
+        CU(e, cudaMalloc(&e->d_conntab, (size_t)n * L.max_sock * 2 * L.conn_window * sizeof(ConnEnt)));
+    }
+    e->rp.netlog = e->d_netlog; e->rp.connlog = e->d_connlog; e->rp.conntab = e->d_conntab;
     e->rp.n_replicas = n; e->rp.seed = seed;
     e->rp.ticket = e->d_ticket; e->rp.events_done = e->d_ticket + 1; e->rp.first_failed = e->d_first_failed;
     unsigned char* tmpl = nullptr;
@@ -263,6 +276,7 @@ int itsb_run_async(itsb_engine* e, double duration) {
     e->rp.duration = duration;
     if (!e->run_pending) CU(e, cudaEventRecord(e->ev_start, e->stream));
     if (e->rp.state_in_hbm) k_run_in_place<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
+    else if (e->warps_per_cta > 12) k_run_wide<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
     else k_run<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
     CU(e, cudaGetLastError());
     CU(e, cudaEventRecord(e->ev_stop, e->stream));
@@ -336,6 +350,19 @@ int itsb_read_net_events(itsb_engine* e, uint64_t replica, itsb_net_event* dst, 
     if (n > cap) n = cap;
     if (n && e->d_netlog)
         CU(e, cudaMemcpy(dst, e->d_netlog + (size_t)replica * e->rp.layout.log_cap, n * sizeof(itsb_net_event), cudaMemcpyDeviceToHost));
+    return ITSB_OK;
+}
+
+int itsb_read_connections(itsb_engine* e, uint64_t replica, itsb_connection* dst, size_t cap, size_t* n_total) {
+    if (!e || replica >= e->n_replicas) return ITSB_ERR_STATE;
+    CU(e, cudaSetDevice(e->device));
+    Hdr h;
+    CU(e, cudaMemcpy(&h, e->d_hot + (size_t)replica * e->rp.layout.hot_bytes, sizeof(Hdr), cudaMemcpyDeviceToHost));
+    if (n_total) *n_total = h.conn_count;
+    size_t n = h.conn_count < e->rp.layout.conn_cap ? h.conn_count : e->rp.layout.conn_cap;
+    if (n > cap) n = cap;
+    if (n && e->d_connlog)
+        CU(e, cudaMemcpy(dst, e->d_connlog + (size_t)replica * e->rp.layout.conn_cap, n * sizeof(itsb_connection), cudaMemcpyDeviceToHost));
     return ITSB_OK;
 }
 

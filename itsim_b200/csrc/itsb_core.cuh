@@ -39,6 +39,23 @@
 #define ITSB_W 32
 #define ITSB_FN __device__ __forceinline__
 #define ITSB_COLD static __device__ __noinline__
+/* Code placement.  ptxas lays the out-of-line functions of a kernel out behind its body in the order of their
+ * mangled names (<length><name>...), and the kernel is instruction-fetch bound (the hot code is larger than the
+ * 32 KB instruction cache level, profiles/).  The dozen functions that run per event are therefore given names
+ * that sort first, in call order, so the hot code is one contiguous range behind the event loop instead of being
+ * scattered over the 200 KB of the shipped-itsim primitives. */
+#define exec_cold         a0_execute
+#define draw_dist         a1_variate
+#define rng_next          a2_philox_
+#define on_tx_begin       a3_txbegin
+#define on_tx_end         a4_tx_end_
+#define pool_scan_min     a5_poolmin
+#define net_send          a6_netsend
+#define proc_spawn        a7_spawn__
+#define sock_open_on      a8_sk_open
+#define sock_close        a9_sk_clos
+#define proc_exit         aa_prcexit
+#define deliver_exception ab_deliv_x
 #else
 #define ITSB_W 1
 #define ITSB_FN static inline
@@ -196,6 +213,15 @@ struct ArenaNode {          /* 32 bytes = one DRAM sector: a queued / remembered
     u32 pad;
 };
 
+struct ConnEnt {            /* 32 bytes: a packet a socket remembers until the other half of its pair shows up */
+    u32 key_ip;             /* the peer Location the entry is filed under */
+    u32 a_ip;               /* outbound: Remote_IP; inbound: the address the packet was sent to */
+    u32 size;
+    u32 ports;              /* key port | (outbound: destination port; inbound: the port it was sent to) << 16 */
+    u32 t_lo, t_hi;         /* when it was filed */
+    u32 pad[2];
+};
+
 struct EvNode {             /* arena node used by the now-queue spill chain and the pool overflow list */
     u32 next;
     u32 seq;
@@ -215,6 +241,7 @@ struct Layout {             /* byte offsets inside one replica's hot block */
     u32 n_ifaces, max_sig, max_thr, max_task;
     u32 off_tab, table_words;
     u32 log_cap;            /* network_event records per replica (HBM) */
+    u32 conn_cap, conn_window, off_sockx, address_tags;   /* connection records (overrides.py:102-186) */
 };
 
 struct Model {              /* pointers to the static tables (shared-memory copies inside the kernel) */
@@ -245,7 +272,7 @@ struct Hdr {                /* first thing in the hot block */
     u32 arena_free_top;
     u32 trace_count;
     u32 log_count;          /* network_event records produced */
-    u32 spare_a;
+    u32 conn_count;         /* connection records produced */
     u16 ev_free_top, pcb_free_top, sock_free_top, spare16;
     u32 replica_lo, replica_hi;
     u32 nq_head, nq_tail;   /* now-queue ring cursors (monotone) */
@@ -263,6 +290,8 @@ struct Hdr {                /* first thing in the hot block */
     u32* arena_free;
     itsb_trace_rec* trace;
     itsb_net_event* netlog;
+    itsb_connection* connlog;
+    ConnEnt* conntab;       /* [socket][direction][window] */
     const Model* model;
     u32 seed_lo, seed_hi;
     Layout L;
@@ -333,15 +362,25 @@ ITSB_FN void rebind(Rep& R, Hdr* H) {
 }
 
 /* Stages the launch's pointers into the header, then builds the view. */
-ITSB_FN void bind_views(Rep& R, unsigned char* hot, const Layout* L, const Model* model, ArenaNode* arena,
-                        u32* arena_free, itsb_trace_rec* trace, itsb_net_event* netlog, u64 seed) {
+struct Binding {            /* one replica's regions outside the hot block, for this launch */
+    ArenaNode* arena;
+    u32* arena_free;
+    itsb_trace_rec* trace;
+    itsb_net_event* netlog;
+    itsb_connection* connlog;
+    ConnEnt* conntab;
+};
+
+ITSB_FN void bind_views(Rep& R, unsigned char* hot, const Layout* L, const Model* model, const Binding& B, u64 seed) {
     Hdr* H = (Hdr*)hot;
     H->L = *L;
     H->model = model;
-    H->arena = arena;
-    H->arena_free = arena_free;
-    H->trace = trace;
-    H->netlog = netlog;
+    H->arena = B.arena;
+    H->arena_free = B.arena_free;
+    H->trace = B.trace;
+    H->netlog = B.netlog;
+    H->connlog = B.connlog;
+    H->conntab = B.conntab;
     H->seed_lo = (u32)seed;
     H->seed_hi = (u32)(seed >> 32);
     w_sync();
@@ -823,19 +862,26 @@ ITSB_FN bool port_in_use(Rep& R, u32 node, u32 port) {
 }
 
 /* open_socket (overrides.py:337-369): port 0 takes the next free port of the persistent 1024..65535 cycle. */
-ITSB_COLD int sock_open(Hdr* H, u32 p, u32 port) {
+ITSB_COLD int sock_open_on(Hdr* H, u32 p, u32 node, u32 port, bool own);
+ITSB_FN int sock_open(Hdr* H, u32 p, u32 port) {
+    return sock_open_on(H, p, ((Pcb*)((unsigned char*)H + H->L.off_pcb))[p].node, port, true);
+}
+
+/* `own`: the socket becomes the process's current one (send / recv / close act on it).  A socket opened on another
+ * attachment of the machine (malware_simple.py:98-99) is only ever named by FORWARD. */
+ITSB_COLD int sock_open_on(Hdr* H, u32 p, u32 node, u32 port, bool own) {
     Rep R; rebind(R, H);
     Pcb& P = R.pcb[p];
-    NodeDyn& N = R.node[P.node];
+    NodeDyn& N = R.node[node];
     if (port == 0) {
         u32 c = N.port_cursor;
         for (;;) {
             u32 cand = c;
             c = (c == 65535u) ? 1024u : c + 1u;
-            if (!port_in_use(R, P.node, cand)) { port = cand; break; }
+            if (!port_in_use(R, node, cand)) { port = cand; break; }
         }
         N.port_cursor = (u16)c;
-    } else if (port_in_use(R, P.node, port)) {
+    } else if (port_in_use(R, node, port)) {
         fail(H, ITSB_EXC_PORT_IN_USE, port);
         return -1;
     }
@@ -845,13 +891,13 @@ ITSB_COLD int sock_open(Hdr* H, u32 p, u32 port) {
     H->sock_free_top = (u16)top;
     u32 s = R.sock_free[top];
     Sock& S = R.sock[s];
-    S.port = (u16)port; S.node = P.node; S.owner = (u16)p;
+    S.port = (u16)port; S.node = (u16)node; S.owner = (u16)p;
     S.wait_head = NIL16; S.wait_tail = NIL16;
     S.q_head = NIL32; S.q_tail = NIL32; S.q_len = 0;
     S.next = N.sock_head;
     N.sock_head = (u16)s;
-    P.sock = (u16)s;
-    net_event_put(H, 1, P.node, port, R.m.nodes[P.node].addr, P.prog, 0, 1);
+    if (own) P.sock = (u16)s;
+    net_event_put(H, 1, node, port, R.m.nodes[node].addr, P.prog, 0, 1);
     return (int)s;
 }
 
@@ -1002,7 +1048,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
     const u32 dst_port = K.ports >> 16;
     const double now = H->now;
     bool fast_ok = false;
-    if (R.trace == nullptr && R.m.n_filters != 0) {
+    if (R.trace == nullptr && R.m.n_filters != 0) {   /* (a model that keeps connection records has no RECV_FILTER) */
         if (H->nq_head == H->nq_tail && H->nq_spill_count == 0) {
             if (!H->pmin_valid) pool_scan_min(H);
             const u64 nb = dbits(now);
@@ -1046,7 +1092,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
             u32 an = R.arena_free[atop - 1 - rank];
             ArenaNode A;
             A.next = NIL32; A.src_ip = K.src_ip; A.ports = K.ports; A.size = K.size;
-            A.tag = K.tag; A.f0 = K.f0; A.f1 = K.f1; A.pad = 0;
+            A.tag = K.tag; A.f0 = K.f0; A.f1 = K.f1; A.pad = K.dst_ip;
             R.arena[an] = A;
             Sock& S = R.sock[s];
             if (S.q_tail == NIL32) S.q_head = an; else R.arena[S.q_tail].next = an;
@@ -1140,6 +1186,8 @@ ITSB_FN ArenaNode sock_pop(Rep& R, Sock& S) {
 }  // namespace itsb
 #include "itsb_machine.cuh"
 namespace itsb {
+
+ITSB_COLD int exec_logged(Hdr* H, u32 p, u64 ins);   /* instructions of models that keep connection records */
 
 /* Every instruction that is not on the per-packet path of a daemon: out of line. */
 ITSB_COLD int exec_cold(Hdr* H, u32 p, u64 ins) {
@@ -1286,7 +1334,7 @@ ITSB_COLD int exec_cold(Hdr* H, u32 p, u64 ins) {
         P.pc += 1;
         return XR_CONTINUE;
     default:
-        return exec_machine(H, p, ins);
+        return op >= OP_RECV_LOG ? exec_logged(H, p, ins) : exec_machine(H, p, ins);
     }
 }
 
@@ -1509,6 +1557,231 @@ ITSB_FN u64 run_replica(Rep& R, double duration) {
     return events_counted(R) - events_before;
 }
 
+/* ---- connection records (overrides.py:102-120,152-186) ------------------------------------------------------------------
+ * The override-path Socket files every packet it sends under its destination Location and every packet it receives
+ * under its source Location, and logs a record when the two halves of a pair meet, when an unanswered outbound
+ * packet is superseded, and for whatever is left when the socket closes.  The reference's two dictionaries never
+ * forget (a daemon socket's grows by one entry per broadcast it hears); here each is a window of the newest
+ * `connection_window` entries in insertion order, one 32-byte sector per entry in HBM, searched by the lanes in one
+ * coalesced read.  oracle/netsimple.py applies the same window. */
+ITSB_FN ConnEnt* conn_table(Hdr* H, u32 s, u32 dir) {
+    return H->conntab + ((size_t)s * 2 + dir) * H->L.conn_window;
+}
+ITSB_FN u16* conn_fill(Hdr* H, u32 s) { return (u16*)((u8*)H + H->L.off_sockx) + 2 * s; }
+
+ITSB_FN int conn_find(const ConnEnt* T, u32 n, u32 ip, u32 port) {
+    u32 hit = NIL32;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (u32 i = (u32)lane_id(); i < n; i += ITSB_W)
+        if (T[i].key_ip == ip && (T[i].ports & 0xFFFF) == port) hit = i;
+    const u32 m = w_min(hit);
+    return m == NIL32 ? -1 : (int)m;
+}
+
+ITSB_FN void conn_remove(ConnEnt* T, u16* fill, u32 idx) {
+    const u32 n = *fill;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (u32 base = idx + 1; base < n; base += ITSB_W) {
+        const u32 j = base + (u32)lane_id();
+        ConnEnt E;
+        if (j < n) E = T[j];
+        w_sync();
+        if (j < n) T[j - 1] = E;
+        w_sync();
+    }
+    w_sync();
+    *fill = (u16)(n - 1);
+}
+
+ITSB_COLD void conn_log(Hdr* H, u32 node, u32 has, u32 in_ip, u32 in_port, u32 in_size, u32 remote_ip, u32 out_port,
+                      u32 out_size, double start, bool inbound);
+ITSB_FN double conn_time(const ConnEnt& E) { return bitsd(((u64)E.t_hi << 32) | E.t_lo); }
+
+/* what flush_logs writes for an entry that never became a pair (overrides.py:181-186) */
+ITSB_FN void conn_log_single(Hdr* H, u32 node, const ConnEnt& E, u32 dir) {
+    if (dir == 0) conn_log(H, node, 2, 0, 0, 0, E.a_ip, E.ports >> 16, E.size, conn_time(E), false);
+    else conn_log(H, node, 1, E.a_ip, E.ports >> 16, E.size, 0, 0, 0, conn_time(E), true);
+}
+
+/* files an entry at position idx (>= 0: the key is already there and keeps its place, like a dict assignment) or
+ * appends it; a full window first gives up its oldest entry, logged as flush_logs would have logged it at close */
+ITSB_FN void conn_put(Hdr* H, u32 node, ConnEnt* T, u16* fill, u32 dir, int idx, u32 key_ip, u32 a_ip, u32 size,
+                      u32 ports) {
+    if (idx < 0) {
+        if (*fill >= H->L.conn_window) {
+            const ConnEnt Old = T[0];
+            conn_log_single(H, node, Old, dir);
+            conn_remove(T, fill, 0);
+        }
+        idx = *fill;
+        w_sync();
+        *fill = (u16)(idx + 1);
+    }
+    if (lane_id() == 0) {
+        ConnEnt E;
+        const u64 tb = dbits(H->now);
+        E.key_ip = key_ip; E.a_ip = a_ip; E.size = size; E.ports = ports;
+        E.t_lo = (u32)tb; E.t_hi = (u32)(tb >> 32); E.pad[0] = 0; E.pad[1] = 0;
+        T[idx] = E;
+    }
+    w_sync();
+}
+
+/* Socket.log_pair: in_* describe the inbound packet (has & 1), out_* the outbound one (has & 2) */
+ITSB_COLD void conn_log(Hdr* H, u32 node, u32 has, u32 in_ip, u32 in_port, u32 in_size, u32 remote_ip, u32 out_port,
+                      u32 out_size, double start, bool inbound) {
+    ((u64*)((unsigned char*)H + H->L.off_stats))[ITSB_TM_USER0 + 6] += 1;   /* records produced (user slot 6) */
+    const u32 n = H->conn_count;
+    if (n < H->L.conn_cap && lane_id() == 0) {
+        itsb_connection C;
+        C.t_end = H->now; C.t_start = start;
+        C.local_ip = (has & 1) ? in_ip : 0; C.local_port = (u16)((has & 1) ? in_port : 0);
+        C.received_bytes = (has & 1) ? in_size : 0;
+        C.remote_ip = (has & 2) ? remote_ip : 0; C.remote_port = (u16)((has & 2) ? out_port : 0);
+        C.sent_bytes = (has & 2) ? out_size : 0;
+        C.node = (u16)node; C.inbound = inbound ? 1 : 0; C.has = (u8)has;
+        H->connlog[n] = C;
+    }
+    H->conn_count = n + 1;
+}
+
+/* correlate_outbound_packet (overrides.py:102-109), called by send() after the packet went to the network */
+ITSB_COLD void conn_outbound(Hdr* H, u32 s, u32 node, u32 dst_ip, u32 dst_port, u32 size, u32 tag, u32 f1) {
+    const u32 remote = (tag < 32 && ((H->L.address_tags >> tag) & 1)) ? f1 : dst_ip;
+    u16* fill = conn_fill(H, s);
+    ConnEnt* TO = conn_table(H, s, 0);
+    ConnEnt* TI = conn_table(H, s, 1);
+    const int i = conn_find(TI, fill[1], dst_ip, dst_port);
+    if (i >= 0) {
+        const ConnEnt E = TI[i];
+        conn_log(H, node, 3, E.a_ip, E.ports >> 16, E.size, remote, dst_port, size, conn_time(E), true);
+        conn_remove(TI, fill + 1, (u32)i);
+        return;
+    }
+    const int j = conn_find(TO, fill[0], dst_ip, dst_port);
+    if (j >= 0) {
+        const ConnEnt E = TO[j];
+        conn_log(H, node, 2, 0, 0, 0, E.a_ip, E.ports >> 16, E.size, conn_time(E), false);
+    }
+    conn_put(H, node, TO, fill, 0, j, dst_ip, remote, size, dst_port | (dst_port << 16));
+}
+
+/* correlate_inbound_packet (overrides.py:115-120), called by recv() on the packet it returns */
+ITSB_COLD void conn_inbound(Hdr* H, u32 s, u32 queued) {
+    const ArenaNode A = H->arena[queued];
+    const u32 src_ip = A.src_ip, src_port = A.ports & 0xFFFF, dst_ip = A.pad, dst_port = A.ports >> 16, size = A.size;
+    u16* fill = conn_fill(H, s);
+    ConnEnt* TO = conn_table(H, s, 0);
+    ConnEnt* TI = conn_table(H, s, 1);
+    const u32 node = ((Sock*)((unsigned char*)H + H->L.off_sock))[s].node;
+    const int j = conn_find(TO, fill[0], src_ip, src_port);
+    if (j >= 0) {
+        const ConnEnt E = TO[j];
+        conn_log(H, node, 3, dst_ip, dst_port, size, E.a_ip, E.ports >> 16, E.size, conn_time(E), false);
+        conn_remove(TO, fill, (u32)j);
+        return;
+    }
+    const int i = conn_find(TI, fill[1], src_ip, src_port);
+    conn_put(H, node, TI, fill + 1, 1, i, src_ip, dst_ip, size, src_port | (dst_port << 16));
+}
+
+/* flush_logs (overrides.py:181-186): what never became a pair, when the socket closes */
+ITSB_COLD void conn_flush(Hdr* H, u32 s, u32 node) {
+    u16* fill = conn_fill(H, s);
+    ConnEnt* TO = conn_table(H, s, 0);
+    ConnEnt* TI = conn_table(H, s, 1);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (u32 i = 0; i < fill[0]; ++i) {
+        const ConnEnt E = TO[i];
+        conn_log_single(H, node, E, 0);
+    }
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (u32 i = 0; i < fill[1]; ++i) {
+        const ConnEnt E = TI[i];
+        conn_log_single(H, node, E, 1);
+    }
+    w_sync();
+    fill[0] = 0; fill[1] = 0;
+}
+
+/* The instructions a model that keeps connection records is assembled with (Asm.log_connections): the socket calls
+ * of the override path followed by the correlation the reference's Socket does inside them.  Kept apart from
+ * exec_cold so that the code every other model runs is the same with or without this feature. */
+ITSB_COLD int exec_logged(Hdr* H, u32 p, u64 ins) {
+    Rep R; rebind(R, H);
+    Pcb& P = R.pcb[p];
+    const u32 op = (u32)(ins & 0xFF), a = (u32)((ins >> 8) & 0xFF), b = (u32)((ins >> 16) & 0xFF),
+              c = (u32)((ins >> 24) & 0xFF), imm = (u32)(ins >> 32);
+    switch (op) {
+    case OP_RECV_LOG: {   /* OP_RECV (run_process), then correlate_inbound_packet on the packet returned */
+        if (P.sock == NIL16) { fail(H, ITSB_EXC_SOCKET_CLOSED, P.pc); return XR_STOP; }
+        Sock& S = R.sock[P.sock];
+        if (S.q_len == 0) {
+            waiters_append(R, S.wait_head, S.wait_tail, p, (u16)(WS_SOCK | P.sock));
+            P.state = PS_WAIT;
+            return XR_STOP;
+        }
+        if (H->conntab) conn_inbound(H, P.sock, S.q_head);
+        const ArenaNode A = sock_pop(R, S);
+        set_pkt_regs(R, A);
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
+    case OP_OPEN_AT:      /* a second socket, on another attachment of this machine: imm = node | port << 16 */
+        if (sock_open_on(H, p, imm & 0xFFFF, imm >> 16, false) < 0) return XR_STOP;
+        P.pc += 1;
+        return XR_CONTINUE;
+    case OP_SEND_LOG: {   /* OP_SEND, then correlate_outbound_packet */
+        const u32* v = H->vol;
+        u32 dst_ip, dst_port = imm & 0xFFFF;
+        switch (a) {
+        case DST_BCAST: dst_ip = R.m.nets[R.m.nodes[P.node].net].bcast; break;
+        case DST_PKT_SRC: dst_ip = v[SRC_PKT_SRC_IP - 0x10]; dst_port = v[SRC_PKT_SRC_PORT - 0x10]; break;
+        case DST_ENT: dst_ip = v[SRC_ENT_IP - 0x10]; dst_port = v[SRC_ENT_PORT - 0x10]; break;
+        case DST_SELF: dst_ip = R.m.nodes[P.node].addr; break;
+        default: dst_ip = P.r[2]; dst_port = P.r[3] & 0xFFFF; break;
+        }
+        u32 f0s = (imm >> 16) & 0xFF, f1s = (imm >> 24) & 0xFF;
+        if (P.sock == NIL16) { fail(H, ITSB_EXC_SOCKET_CLOSED, P.pc); return XR_STOP; }
+        const u32 size = src_val(R, P, b), f1 = f1s == SRC_NONE ? 0 : src_val(R, P, f1s);
+        net_send(H, P.node, R.sock[P.sock].port, dst_ip, dst_port, size, c, f0s == SRC_NONE ? 0 : src_val(R, P, f0s), f1);
+        if (H->conntab && H->status == 0) conn_outbound(H, P.sock, P.node, dst_ip, dst_port, size, c, f1);
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
+    case OP_FORWARD_LOG: {   /* OP_FORWARD, then the correlation on the socket of the other attachment */
+        const u32* v = H->vol;
+        net_send(H, imm & 0xFFFF, imm >> 16, P.r[2], P.r[3] & 0xFFFF, v[SRC_PKT_SIZE - 0x10], v[SRC_PKT_TAG - 0x10],
+                 v[SRC_PKT_F0 - 0x10], v[SRC_PKT_F1 - 0x10]);
+        if (H->conntab && H->status == 0) {
+            u16 ws = R.node[imm & 0xFFFF].sock_head;
+            while (ws != NIL16 && R.sock[ws].port != (imm >> 16)) ws = R.sock[ws].next;
+            if (ws != NIL16)
+                conn_outbound(H, ws, imm & 0xFFFF, P.r[2], P.r[3] & 0xFFFF, v[SRC_PKT_SIZE - 0x10],
+                              v[SRC_PKT_TAG - 0x10], v[SRC_PKT_F1 - 0x10]);
+        }
+        P.pc += 1;
+        return XR_CONTINUE;
+    }
+    case OP_CLOSE_LOG:    /* OP_CLOSE after flush_logs (overrides.py:366-367) */
+        if (P.sock != NIL16 && H->conntab) conn_flush(H, P.sock, R.sock[P.sock].node);
+        sock_close(H, p);
+        P.pc += 1;
+        return XR_CONTINUE;
+    default:
+        fail(H, ITSB_ERR_BAD_OPCODE, ins);
+        return XR_STOP;
+    }
+}
+
 /* Builds the t = 0 state of a replica: empty tables, free lists, and the model's installed processes in
  * installation order (Endpoint.install -> sim.add, overrides.py:423-424; network_simple.py:366-385).  The header's
  * binding fields must already be staged (bind_views). */
@@ -1516,7 +1789,7 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
     Hdr* H = R.hdr;
     const Layout* L = &H->L;
     H->now = 0.0; H->draws = 0; H->seq = 0; H->status = 0; H->detail = 0;
-    H->trace_count = 0; H->log_count = 0; H->spare_a = 0;
+    H->trace_count = 0; H->log_count = 0; H->conn_count = 0;
     H->replica_lo = (u32)replica_id; H->replica_hi = (u32)(replica_id >> 32);
     H->nq_head = 0; H->nq_tail = 0; H->nq_spill_head = NIL32; H->nq_spill_tail = NIL32; H->nq_spill_count = 0;
     H->pmin_valid = 0; H->pmin_idx = NIL32; H->pmin_seq = NIL32; H->pmin_t = T_EMPTY;

@@ -44,6 +44,10 @@ static inline Layout compute_layout(const itsb_model_desc& d) {
     L.off_task_free = off; off = align_up(off + 2 * L.max_task, 16);
     L.table_words = c.table_words;
     L.off_tab = off;       off = align_up(off + 4 * L.table_words, 16);
+    /* connection records: fill counts of the two correlation windows of every socket */
+    L.conn_cap = c.connection_records; L.conn_window = c.connection_records ? c.connection_window : 0;
+    L.address_tags = d.address_tags;
+    L.off_sockx = off;     off = align_up(off + (L.conn_cap ? 4 * L.max_sock : 0), 16);
     L.hot_bytes = align_up(off, 128);
     return L;
 }
@@ -68,6 +72,7 @@ static inline bool validate_model(const itsb_model_desc& d, const void* const* b
         c.max_sockets > 0x3FFF || c.arena_nodes < 1 || c.arena_nodes >= (1u << 28)) {
         why = "capacity out of range"; return false;
     }
+    if (c.connection_records && (c.connection_window < 1 || c.connection_window > 4096)) { why = "connection_window must be 1..4096"; return false; }
     if (d.n_nodes == 0 || d.n_nodes > 0x3FFF || d.n_code == 0 || d.n_code > 65535) { why = "table size out of range"; return false; }
     const uint64_t* code = (const uint64_t*)blobs[ITSB_BLOB_CODE];
     for (uint32_t i = 0; i < d.n_code; ++i) {
@@ -78,6 +83,9 @@ static inline bool validate_model(const itsb_model_desc& d, const void* const* b
         if (op == OP_ADVANCE && (imm & 0xFFFF) >= d.n_dists) { why = "ADVANCE dist out of range"; return false; }
         if (op == OP_ADVANCE_C && (imm & 0xFFFF) >= d.n_consts) { why = "ADVANCE_C const out of range"; return false; }
         if (op == OP_SPAWN && imm >= d.n_entries) { why = "SPAWN entry out of range"; return false; }
+        if (c.connection_records && (op == OP_RECV || op == OP_RECV_FILTER || op == OP_SEND || op == OP_FORWARD || op == OP_CLOSE)) {
+            why = "connection records need programs assembled with the logged socket instructions (OP_*_LOG)"; return false;
+        }
         if (op == OP_RECV_FILTER) {
             uint32_t a = (uint32_t)((code[i] >> 8) & 0xFF), b = (uint32_t)((code[i] >> 16) & 0xFF);
             if (a > 3 || b >= d.n_filters || (imm & 0xFFFF) >= d.n_code) { why = "RECV_FILTER operand out of range"; return false; }

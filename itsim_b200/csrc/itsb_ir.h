@@ -84,6 +84,13 @@ enum {
     OP_FORWARD = 59,    /* send the packet just received on, from (address of node imm[0:16], port imm[16:32]) to
                            (r2, r3): the one-way router of malware_simple.py:96-107                                  */
     OP_GETPORT = 60,    /* r[a] = socket.port                                                    socket.py:44-51      */
+    OP_RECV_LOG = 61,   /* socket.recv() of a model that keeps connection records: OP_RECV followed by
+                           correlate_inbound_packet                                              overrides.py:135-147   */
+    OP_OPEN_AT = 62,    /* open_socket((address of another attachment, port)): imm = node | port << 16; the
+                           process's current socket is unchanged                          malware_simple.py:98-99 */
+    OP_SEND_LOG = 63,   /* OP_SEND followed by correlate_outbound_packet                         overrides.py:122-125   */
+    OP_FORWARD_LOG = 64,/* OP_FORWARD followed by the same on the sending attachment's socket                           */
+    OP_CLOSE_LOG = 65,  /* flush_logs, then OP_CLOSE                                              overrides.py:366-367   */
     OP_COUNT
 };
 

@@ -51,6 +51,8 @@ struct RunParams {
     uint32_t* arena_free;
     itsb_trace_rec* trace;
     itsb_net_event* netlog;
+    itsb_connection* connlog;
+    ConnEnt* conntab;
     uint64_t n_replicas;
     uint64_t seed;
     double duration;
@@ -146,9 +148,14 @@ __device__ __forceinline__ void run_warps(const RunParams& p, unsigned char* sme
             phase ^= 1;
         }
         Rep R;
-        bind_views(R, hot, &p.layout, m, p.arena + r * p.layout.arena_nodes, p.arena_free + r * p.layout.arena_nodes,
-                   p.trace ? p.trace + r * p.layout.trace_cap : nullptr,
-                   p.netlog ? p.netlog + r * p.layout.log_cap : nullptr, p.seed);
+        Binding B;
+        B.arena = p.arena + r * p.layout.arena_nodes;
+        B.arena_free = p.arena_free + r * p.layout.arena_nodes;
+        B.trace = p.trace ? p.trace + r * p.layout.trace_cap : nullptr;
+        B.netlog = p.netlog ? p.netlog + r * p.layout.log_cap : nullptr;
+        B.connlog = p.connlog ? p.connlog + r * p.layout.conn_cap : nullptr;
+        B.conntab = p.conntab ? p.conntab + r * ((size_t)p.layout.max_sock * 2 * p.layout.conn_window) : nullptr;
+        bind_views(R, hot, &p.layout, m, B, p.seed);
         const unsigned long long events = run_replica(R, p.duration);
         __syncwarp();
         const int32_t status = R.hdr->status;

@@ -104,6 +104,16 @@ class Engine:
         self.net_events_total = total.value
         return out[:min(cap, total.value)]
 
+    def connections(self, replica: int = 0) -> np.ndarray:
+        """The replica's connection records (``Socket.log_pair``, network_simple_overrides.py:152-177)."""
+        cap = self.compiled.caps.connection_records
+        out = np.zeros(cap, dtype=L.CONNECTION_DTYPE)
+        total = C.c_size_t()
+        self._check(self._lib.itsb_read_connections(self._h, replica, out.ctypes.data, cap, C.byref(total)),
+                    "itsb_read_connections")
+        self.connections_total = total.value
+        return out[:min(cap, total.value)]
+
     def telemetry(self) -> np.ndarray:
         out = np.zeros(L.TM_SIZE, dtype=np.uint64)
         self._check(self._lib.itsb_read_telemetry(self._h, out.ctypes.data, L.TM_SIZE), "itsb_read_telemetry")

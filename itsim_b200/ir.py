@@ -16,7 +16,8 @@ import numpy as np
  OP_NODE_WAKE, OP_SPAWN, OP_THROW, OP_LIST_CLEAR, OP_LIST_PUSH, OP_LIST_TAKE, OP_STAT, OP_RECV_FILTER,
  OP_BIND, OP_SCLOSE, OP_SENDL, OP_RECVT, OP_ADVANCE_X, OP_THREAD_EXIT, OP_CLONE, OP_FORK, OP_JOIN, OP_PWAIT, OP_TKILL,
  OP_PKILL, OP_MARK, OP_SIG_WAIT, OP_SIG_ON, OP_GSET, OP_NOW_SUB, OP_ADVANCE_X2, OP_TLOAD, OP_TSTORE, OP_ADD, OP_SUB,
- OP_JLTU, OP_XNOW, OP_XSET, OP_XELAPSE, OP_JXLE0, OP_RECVT_X, OP_SETADDR, OP_GETADDR, OP_FORWARD, OP_GETPORT) = range(61)
+ OP_JLTU, OP_XNOW, OP_XSET, OP_XELAPSE, OP_JXLE0, OP_RECVT_X, OP_SETADDR, OP_GETADDR, OP_FORWARD, OP_GETPORT,
+ OP_RECV_LOG, OP_OPEN_AT, OP_SEND_LOG, OP_FORWARD_LOG, OP_CLOSE_LOG) = range(66)
 
 PROG_HIDDEN_BALK, PROG_HIDDEN_WAIT_ONE = 0xF1, 0xF2
 
@@ -55,6 +56,7 @@ class Asm:
         self._scope = ""
         self._default_handler: Optional[str] = None   # inside a thread program: where an unhandled exception goes
         self.uses_machine = False
+        self.log_connections = False   # socket calls assemble to their *_LOG forms (models that keep connection records)
 
     # -- structure ---------------------------------------------------------------------------------------
     def program(self, name: str, prog_id: int) -> int:
@@ -199,19 +201,24 @@ class Asm:
     def forward(self, from_node: object, from_port: int) -> None:
         """Relay the packet just received from another attachment of the machine (node object resolved at
         compile time) to (r2, r3)."""
-        self._emit(OP_FORWARD, imm=("node_port", from_node, from_port))
+        self._emit(OP_FORWARD_LOG if self.log_connections else OP_FORWARD, imm=("node_port", from_node, from_port))
+
+    def open_at(self, node: object, port: int) -> None:
+        """``open_socket((address of another attachment of this machine, port))``: a socket FORWARD sends from."""
+        self._emit(OP_OPEN_AT, imm=("node_port", node, port))
 
     def setaddr(self, src: int) -> None: self._emit(OP_SETADDR, src)
     def getaddr(self, rd: int) -> None: self._emit(OP_GETADDR, rd)
 
     def open(self, port: int = 0) -> None: self._emit(OP_OPEN, imm=port)
-    def close(self) -> None: self._emit(OP_CLOSE)
+    def close(self) -> None: self._emit(OP_CLOSE_LOG if self.log_connections else OP_CLOSE)
 
     def send(self, dst_mode: int, size_src: int, tag: int, port: int = 0, f0: int = NONE, f1: int = NONE) -> None:
-        self._emit(OP_SEND, dst_mode, size_src, tag, (port & 0xFFFF) | (f0 << 16) | (f1 << 24))
+        self._emit(OP_SEND_LOG if self.log_connections else OP_SEND, dst_mode, size_src, tag,
+                   (port & 0xFFFF) | (f0 << 16) | (f1 << 24))
 
     def recv(self, handler: Optional[Target] = None) -> None:
-        self._emit(OP_RECV, imm=("hi16", self._t(handler), 0))
+        self._emit(OP_RECV_LOG if self.log_connections else OP_RECV, imm=("hi16", self._t(handler), 0))
 
     def recv_filter(self, rd: int, filter_index: int, asleep: Target, handler: Optional[Target] = None) -> None:
         """Fused ``while True: with ws.awake(): packet = socket.recv()`` loop head that also consumes the packets
@@ -254,6 +261,8 @@ class Asm:
         """Returns (code uint64[n], entries (pc, prog) uint32[n_entries, 2])."""
         code = np.zeros(len(self._ins), dtype=np.uint64)
         for pc, (op, a, b, c, imm) in enumerate(self._ins):
+            if pc == 0 and self.log_connections:
+                op = OP_CLOSE_LOG      # the landing pad of an unhandled Interrupt closes the socket too
             word = (op & 0xFF) | ((a & 0xFF) << 8) | ((b & 0xFF) << 16) | ((c & 0xFF) << 24) \
                 | ((self._resolve(imm) & 0xFFFFFFFF) << 32)
             code[pc] = word

@@ -47,7 +47,8 @@ class Compiled:
     """The tables handed to ``itsb_load_model`` (blob order = ``ITSB_BLOB_*`` in include/itsb.h)."""
 
     def __init__(self, code, entries, dists, consts, nets, nodes, init, filters, caps: L.Caps, ifaces=None,
-                 routes=None, members=None) -> None:
+                 routes=None, members=None, address_tags: int = 0) -> None:
+        self.address_tags = address_tags
         self.code, self.entries, self.dists, self.consts = code, entries, dists, consts
         self.nets, self.nodes, self.init, self.filters, self.caps = nets, nodes, init, filters, caps
         self.ifaces = ifaces if ifaces is not None else np.zeros(0, dtype=L.IFACE_DTYPE)
@@ -61,7 +62,7 @@ class Compiled:
     def desc(self) -> L.ModelDesc:
         return L.ModelDesc(L.ABI_VERSION, len(self.code), len(self.entries), len(self.dists), len(self.consts),
                            len(self.nets), len(self.nodes), len(self.init), len(self.filters), len(self.ifaces),
-                           len(self.routes), len(self.members), self.caps)
+                           len(self.routes), len(self.members), self.address_tags, self.caps)
 
 
 class Simulator:
@@ -81,7 +82,9 @@ class Simulator:
         self.nodes: List["Endpoint"] = []
         self._installed: List[Tuple[str, "Endpoint", Sequence[int]]] = []
         self.caps = dict(max_events=384, max_procs=256, max_sockets=128, max_packets=0, arena_nodes=16384,
-                         trace_records=0, max_threads=0, max_tasks=0, max_signals=0, table_words=0, net_event_records=0)
+                         trace_records=0, max_threads=0, max_tasks=0, max_signals=0, table_words=0, net_event_records=0,
+                         connection_records=0, connection_window=8)
+        self.address_tags = 0       # payload tags whose f1 field is an ADDRESS entry (connection records)
         self._machine_procs: List[Tuple[Any, float, str, Sequence[int]]] = []   # Node.run_proc_in calls, in order
         self._engine: Any = None
         self._lib: Any = None       # tests inject the host-emulation library here; None = the CUDA engine
@@ -153,7 +156,8 @@ class Simulator:
         dists = np.zeros(len(self._dists), dtype=L.DIST_DTYPE)   # last: networks and drawn installs add generators
         for i, d in enumerate(self._dists):
             dists[i] = (d.kind, d.flags, d.p0, d.p1, d.slope, d.shift, d.lower, d.upper)
-        return Compiled(code, entries, dists, consts, nets, nodes, init, filters, L.Caps(**self.caps))
+        return Compiled(code, entries, dists, consts, nets, nodes, init, filters, L.Caps(**self.caps),
+                        address_tags=self.address_tags)
 
     # -- running -------------------------------------------------------------------------------------------------
     def run_replicas(self, n: int, seed: int = 0, duration: Optional[float] = None, first_replica_id: int = 0,

@@ -188,11 +188,17 @@ def _programs(sim: Simulator, num_workstations: int, fused: bool) -> None:
 
 
 def build(cidr: str = "192.168.4.0/24", num_endpoints: Optional[int] = None, trace_records: int = 0,
-          fused: bool = True) -> Simulator:
+          fused: bool = True, connection_records: int = 0, connection_window: int = 8) -> Simulator:
     """``init()`` of network_simple.py:311-387 (argument defaults :315-316).  ``fused=False`` assembles the daemon
     loops from the plain wait/recv/branch instructions instead of the fused loop head (same behaviour, used by the
-    tests to check one encoding against the other)."""
+    tests to check one encoding against the other).  ``connection_records`` > 0 keeps the per-socket packet
+    correlation of overrides.py:102-186 and logs its connection records (capacity per replica); the receive loops are
+    then assembled from plain instructions, since every received packet has to be correlated."""
     sim = Simulator()
+    if connection_records:
+        sim.asm.log_connections = True
+        sim.caps.update(connection_records=connection_records, connection_window=connection_window)
+        fused = False
     num_addresses = ip_network(cidr).num_addresses - NUM_ADDRESSES_RESERVED
     if num_addresses < MIN_NUM_ENDPOINTS:
         raise ValueError(f"Unsuitable CIDR prefix for simulating a non-trivial network: {cidr}")
@@ -221,17 +227,20 @@ def build(cidr: str = "192.168.4.0/24", num_endpoints: Optional[int] = None, tra
     # process and socket tables): 148 resident processes + 72 transient ones (18 query rounds in flight at once);
     # sized so that 12 replicas (warps) fit one SM's shared memory
     sim.caps.update(max_events=128, max_procs=220, max_sockets=96)
+    sim.address_tags = 1 << TAG_IAM      # the "iam" payloads carry PayloadDictionaryType.ADDRESS (network_simple.py:215,244)
     sim.num_workstations = num_workstations
     return sim
 
 
-def build_malware(trace_records: int = 0, fused: bool = True) -> Simulator:
+def build_malware(trace_records: int = 0, fused: bool = True, connection_records: int = 0,
+                  connection_window: int = 8) -> Simulator:
     """network_simple + the beaconing-malware overlay of ``examples/network_simple/malware_simple.py:53-125``
     (BASELINE.json config 3).  One workstation drawn per replica at set-up runs ``call_home`` (beacon every expo(10) s)
     and ``no_good`` (every expo(100) s); the router's ``route`` relays the 100-byte beacons over the ``Internet``
     network (overrides.py:443-456) to the command-and-control host 1.2.3.4:666.  The overlay's own statistics are the
     user counters STAT_BEACONS / STAT_ROUTED / STAT_C2_RECEIVED."""
-    sim = build(trace_records=trace_records, fused=fused)
+    sim = build(trace_records=trace_records, fused=fused, connection_records=connection_records,
+                connection_window=connection_window)
     a = sim.asm
     www = Network(sim, "0.0.0.0/0", latency=bounded(expo(1 * S), lower=20 * MS), bandwidth=expo(10 * MbPS))
     d_beacon, d_privileged = sim.dist(expo(10)), sim.dist(expo(100))
@@ -269,6 +278,7 @@ def build_malware(trace_records: int = 0, fused: bool = True) -> Simulator:
 
     a.program("route", PROG_ROUTE)                                # :96-107 (the WAN-side socket only sends)
     a.open(LOCAL_ROUTER_PORT)
+    a.open_at(router_wan, LOCAL_ROUTER_PORT)
     a.label("loop")
     a.recv()
     a.stat(STAT_ROUTED)
@@ -289,5 +299,6 @@ def build_malware(trace_records: int = 0, fused: bool = True) -> Simulator:
     infected.install("no_good")
     sim.router.install("route")
     bear.install("command_and_control")
+    sim.router_wan, sim.bear = router_wan, bear
     sim.caps.update(max_procs=224, max_sockets=100)
     return sim

@@ -44,3 +44,29 @@ def network_event_documents(records: np.ndarray, sim_uuid: Optional[str] = None,
 def datastore_rows(documents: Iterable[Dict[str, Any]]) -> List[Tuple[str, str, str, str]]:
     """``(uuid, timestamp, sim_uuid, json)`` rows of the datastore's ``network_event`` table."""
     return [(d["uuid"], d["timestamp"], d["sim_uuid"], json.dumps(d)) for d in documents]
+
+
+def connection_documents(records: np.ndarray) -> List[Dict[str, Any]]:
+    """The dictionaries ``Socket.log_pair`` dumps as JSON log lines (network_simple_overrides.py:163-177), value
+    conventions included: a missing half shows as integer 0 (``Remote_IP`` as the string "0"), a present one as
+    strings."""
+    docs = []
+    for rec in records:
+        has_in, has_out = bool(int(rec["has"]) & 1), bool(int(rec["has"]) & 2)
+        start = float(rec["t_start"])
+        docs.append({
+            "Connection_Type": "UDP",
+            "Local_IP": str(IPv4Address(int(rec["local_ip"]))) if has_in else 0,
+            "Local_Port": str(int(rec["local_port"])) if has_in else 0,
+            "Direction": "Inbound" if int(rec["inbound"]) else "Outbound",
+            "Remote_IP": str(IPv4Address(int(rec["remote_ip"]))) if has_out else "0",
+            "Remote_Port": str(int(rec["remote_port"])) if has_out else 0,
+            "Sent_Bytes": str(int(rec["sent_bytes"])) if has_out else 0,
+            "Received_Bytes": str(int(rec["received_bytes"])) if has_in else 0,
+            "PID": 0,
+            "Start_Time": start,
+            "End_Time": float(rec["t_end"]),
+            "Parent_Process_Path": "/home/town",
+            "Parent_Process_Start_Time": start,
+        })
+    return docs

@@ -173,6 +173,7 @@ class Socket:
             if dest in self._outbound:
                 self._log_pair(None, self._outbound[dest][0], self._outbound[dest][1], False)
             self._outbound[dest] = (packet, now())
+            self._forget_oldest(self._outbound)
 
     def _correlate_inbound(self, src: Location, packet: Packet) -> None:
         if src in self._outbound:
@@ -180,6 +181,21 @@ class Socket:
             del self._outbound[src]
         else:
             self._inbound[src] = (packet, now())
+            self._forget_oldest(self._inbound)
+
+    def _forget_oldest(self, filed: "OrderedDict[Location, Tuple[Packet, float]]") -> None:
+        """Not in the reference, whose dictionaries never forget (a daemon socket's inbound dictionary grows by one
+        entry per broadcast it hears until the workstation falls asleep and the socket closes).  ``Model.conn_window``
+        bounds each dictionary to its newest entries: the oldest one is logged the way ``flush_logs`` would log it at
+        close time, just earlier.  None keeps the reference's behaviour; a window the dictionaries never reach gives
+        the reference's records exactly (tests/test_connections.py)."""
+        window = self._node.model.conn_window
+        if window is not None and len(filed) > window:
+            _, (packet, start) = filed.popitem(last=False)
+            if filed is self._outbound:
+                self._log_pair(None, packet, start, False)
+            else:
+                self._log_pair(packet, None, start, True)
 
     def _log_pair(self, packet_in: Optional[Packet], packet_out: Optional[Packet], start: float,
                   is_inbound: bool) -> None:
@@ -378,7 +394,9 @@ class Model:
     """One replica of network_simple: ``init()`` of network_simple.py:311-387 with its module-level generators."""
 
     def __init__(self, seed: int = 0, replica: int = 0, cidr: str = "192.168.4.0/24",
-                 num_endpoints: Optional[int] = None, trace: bool = True, trace_limit: Optional[int] = None) -> None:
+                 num_endpoints: Optional[int] = None, trace: bool = True, trace_limit: Optional[int] = None,
+                 conn_window: Optional[int] = None) -> None:
+        self.conn_window = conn_window
         self.rng = PhiloxRandom(seed, replica)
         self.sim = Simulator()
         self.nodes: List[Node] = []
@@ -579,8 +597,9 @@ class MalwareModel(Model):
     BAD_NEWS_BEAR_PORT = 666
     LOCAL_ROUTER_PORT = 777
 
-    def __init__(self, seed: int = 0, replica: int = 0, trace: bool = True, trace_limit: Optional[int] = None) -> None:
-        super().__init__(seed, replica, trace=trace, trace_limit=trace_limit)
+    def __init__(self, seed: int = 0, replica: int = 0, trace: bool = True, trace_limit: Optional[int] = None,
+                 conn_window: Optional[int] = None) -> None:
+        super().__init__(seed, replica, trace=trace, trace_limit=trace_limit, conn_window=conn_window)
         self.stats.update({"beacons": 0, "routed": 0, "c2_received": 0})
         gsrandom.set_default_rng(self.rng)
         try:
@@ -642,9 +661,10 @@ class MalwareModel(Model):
 
 
 def run_replica(seed: int, replica: int, duration: float, trace: bool = True, trace_limit: Optional[int] = None,
-                num_endpoints: Optional[int] = None) -> Model:
+                num_endpoints: Optional[int] = None, conn_window: Optional[int] = None) -> Model:
     """Builds and runs one replica for ``duration`` simulated seconds; caller reads ``.tracer`` / ``.stats``."""
-    model = Model(seed, replica, num_endpoints=num_endpoints, trace=trace, trace_limit=trace_limit)
+    model = Model(seed, replica, num_endpoints=num_endpoints, trace=trace, trace_limit=trace_limit,
+                  conn_window=conn_window)
     model.run(duration)
     return model
 

@@ -35,6 +35,8 @@ struct itsb_engine {
     std::vector<uint32_t> arena_free;
     std::vector<itsb_trace_rec> trace;
     std::vector<itsb_net_event> netlog;
+    std::vector<itsb_connection> connlog;
+    std::vector<ConnEnt> conntab;
     uint64_t last_events = 0, launches = 0;
     std::string err;
     bool loaded = false;
@@ -73,10 +75,15 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
 }
 
 static void bind(itsb_engine* e, Rep& R, uint64_t r) {
-    bind_views(R, e->hot.data() + r * e->layout.hot_bytes, &e->layout, &e->model,
-               e->arena.data() + r * e->layout.arena_nodes, e->arena_free.data() + r * e->layout.arena_nodes,
-               e->layout.trace_cap ? e->trace.data() + r * e->layout.trace_cap : nullptr,
-               e->layout.log_cap ? e->netlog.data() + r * e->layout.log_cap : nullptr, e->seed);
+    const Layout& L = e->layout;
+    Binding B;
+    B.arena = e->arena.data() + r * L.arena_nodes;
+    B.arena_free = e->arena_free.data() + r * L.arena_nodes;
+    B.trace = L.trace_cap ? e->trace.data() + r * L.trace_cap : nullptr;
+    B.netlog = L.log_cap ? e->netlog.data() + r * L.log_cap : nullptr;
+    B.connlog = L.conn_cap ? e->connlog.data() + r * L.conn_cap : nullptr;
+    B.conntab = L.conn_cap ? e->conntab.data() + r * ((size_t)L.max_sock * 2 * L.conn_window) : nullptr;
+    bind_views(R, e->hot.data() + r * L.hot_bytes, &L, &e->model, B, e->seed);
 }
 
 int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first) {
@@ -87,6 +94,8 @@ int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first
     e->arena_free.resize(n * e->layout.arena_nodes);
     e->trace.assign(n * e->layout.trace_cap, itsb_trace_rec());
     e->netlog.assign(n * e->layout.log_cap, itsb_net_event());
+    e->connlog.assign(n * e->layout.conn_cap, itsb_connection());
+    e->conntab.assign(n * ((size_t)e->layout.max_sock * 2 * e->layout.conn_window), ConnEnt());
     for (uint64_t r = 0; r < n; ++r) {
         Rep R; bind(e, R, r);
         for (uint32_t i = 0; i < e->layout.arena_nodes; ++i) R.arena_free[i] = e->layout.arena_nodes - 1 - i;
@@ -151,6 +160,16 @@ int itsb_read_net_events(itsb_engine* e, uint64_t replica, itsb_net_event* dst, 
     size_t n = H->log_count < e->layout.log_cap ? H->log_count : e->layout.log_cap;
     if (n > cap) n = cap;
     if (n) memcpy(dst, e->netlog.data() + replica * e->layout.log_cap, n * sizeof(itsb_net_event));
+    return ITSB_OK;
+}
+
+int itsb_read_connections(itsb_engine* e, uint64_t replica, itsb_connection* dst, size_t cap, size_t* n_total) {
+    if (replica >= e->n_replicas) return ITSB_ERR_STATE;
+    Hdr* H = (Hdr*)(e->hot.data() + replica * e->layout.hot_bytes);
+    if (n_total) *n_total = H->conn_count;
+    size_t n = H->conn_count < e->layout.conn_cap ? H->conn_count : e->layout.conn_cap;
+    if (n > cap) n = cap;
+    if (n) memcpy(dst, e->connlog.data() + replica * e->layout.conn_cap, n * sizeof(itsb_connection));
     return ITSB_OK;
 }
 

@@ -23,7 +23,8 @@ def test_library_exports_every_declared_symbol(built):
     lib = ctypes.CDLL(built.LIB)
     for name in declared_functions():
         assert hasattr(lib, name), name
-    assert lib.itsb_abi_version() == 1
+    from itsim_b200 import _lib
+    assert lib.itsb_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_hostemu_exports_the_same_surface(built):
