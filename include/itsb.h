@@ -196,7 +196,8 @@ typedef struct itsb_filter {      /* which received packets a RECV_FILTER loop h
     uint32_t tags_always;         /* always handed over                                                           */
     uint32_t tags_if_host;        /* handed over only if the packet's hostname field equals the node's             */
     uint32_t tags_if_list;        /* handed over only if the process remembers at least one packet (LIST_*)        */
-    uint32_t reserved;
+    uint32_t tags_if_listed;      /* handed over only if the process remembers a packet with the same hostname
+                                     field (the entry a LIST_TAKE on that field would find)                        */
 } itsb_filter;
 
 typedef struct itsb_caps {        /* per-replica capacities; exceeding one flags the replica with ITSB_ERR_CAP_*  */

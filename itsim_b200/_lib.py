@@ -48,7 +48,7 @@ IFACE_DTYPE = np.dtype([("node", "<u4"), ("net", "<u4"), ("addr0", "<u4"), ("fir
                         ("reserved", "<u4", (3,))])
 ROUTE_DTYPE = np.dtype([("net", "<u4"), ("mask", "<u4"), ("prefixlen", "<u4"), ("kind", "<u4"), ("gateway", "<u4"),
                         ("reserved", "<u4", (3,))])
-FILTER_DTYPE = np.dtype([("tags_always", "<u4"), ("tags_if_host", "<u4"), ("tags_if_list", "<u4"), ("reserved", "<u4")])
+FILTER_DTYPE = np.dtype([("tags_always", "<u4"), ("tags_if_host", "<u4"), ("tags_if_list", "<u4"), ("tags_if_listed", "<u4")])
 CONNECTION_DTYPE = np.dtype([("t_end", "<f8"), ("t_start", "<f8"), ("local_ip", "<u4"), ("remote_ip", "<u4"),
                              ("sent_bytes", "<u4"), ("received_bytes", "<u4"), ("local_port", "<u2"),
                              ("remote_port", "<u2"), ("node", "<u2"), ("inbound", "u1"), ("has", "u1")])

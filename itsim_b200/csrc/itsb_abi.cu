@@ -207,6 +207,8 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     } else {
         w = (uint32_t)((smem_max - e->so.total - 128) / per_warp);
         if (w > 16) w = 16;
+        const char* cap = getenv("ITSB_MAX_WARPS");      /* experiments: fewer resident replicas per SM */
+        if (cap && atoi(cap) >= 1 && (uint32_t)atoi(cap) < w) w = (uint32_t)atoi(cap);
         e->smem_bytes = e->so.total + (size_t)w * e->rp.layout.hot_bytes + (size_t)w * 8 + 64;
     }
     e->warps_per_cta = w;

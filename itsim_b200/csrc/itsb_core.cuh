@@ -999,10 +999,25 @@ ITSB_COLD bool on_tx_end(Hdr* H, u32 k) {
 
 ITSB_COLD void m_deliver(Hdr* H, u32 k);   /* Link-mode delivery, itsb_machine.cuh */
 
-ITSB_FN bool filter_passes(const itsb_filter F, u32 tag, u32 f0, u32 host, bool list_nonempty) {
+/* does the process remember a packet whose hostname field is f0 (what LIST_TAKE would find)? */
+ITSB_FN bool list_holds(Rep& R, const Pcb& P, u32 f0) {
+    u32 n = P.list_head;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    while (n != NIL32) {
+        if (R.arena[n].f0 == f0) return true;
+        n = R.arena[n].next;
+    }
+    return false;
+}
+
+ITSB_FN bool filter_passes(Rep& R, const itsb_filter F, u32 tag, u32 f0, u32 host, const Pcb& P) {
     const u32 bit = 1u << (tag & 31);
-    return (F.tags_always & bit) != 0 || ((F.tags_if_host & bit) != 0 && f0 == host) ||
-           ((F.tags_if_list & bit) != 0 && list_nonempty);
+    if ((F.tags_always & bit) != 0 || ((F.tags_if_host & bit) != 0 && f0 == host) ||
+        ((F.tags_if_list & bit) != 0 && P.list_head != NIL32))
+        return true;
+    return (F.tags_if_listed & bit) != 0 && P.list_head != NIL32 && list_holds(R, P, f0);
 }
 
 /* trace records of one delivery pass: one DELIVER record per recipient, written by its lane */
@@ -1071,7 +1086,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
                 if ((u32)(ins & 0xFF) == OP_RECV_FILTER && P.phase == 1 &&
                     R.node[node].epoch == P.r[(u32)(ins >> 8) & 3]) {
                     const itsb_filter F = R.m.filters[(u32)(ins >> 16) & 0xFF];
-                    retire = !filter_passes(F, K.tag, K.f0, R.m.nodes[node].host, P.list_head != NIL32);
+                    retire = !filter_passes(R, F, K.tag, K.f0, R.m.nodes[node].host, P);
                 }
             }
         }
@@ -1393,7 +1408,7 @@ ITSB_FN void run_process(Rep& R, u32 p) {
                 const ArenaNode A = sock_pop(R, S);
                 P.phase = 0;
                 if (N.epoch != P.r[a & 3]) { P.pc = (u16)(imm & 0xFFFF); break; }      /* FellAsleep */
-                if (filter_passes(F, A.tag, A.f0, R.m.nodes[P.node].host, P.list_head != NIL32)) {
+                if (filter_passes(R, F, A.tag, A.f0, R.m.nodes[P.node].host, P)) {
                     set_pkt_regs(R, A);
                     handed = true;
                     break;

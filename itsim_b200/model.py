@@ -77,7 +77,7 @@ class Simulator:
         self._dists: List[Dist] = []
         self._dist_index: Dict[tuple, int] = {}
         self._consts: List[float] = []
-        self._filters: List[Tuple[int, int, int]] = []
+        self._filters: List[Tuple[int, int, int, int]] = []
         self.networks: List["Network"] = []
         self.nodes: List["Endpoint"] = []
         self._installed: List[Tuple[str, "Endpoint", Sequence[int]]] = []
@@ -104,10 +104,12 @@ class Simulator:
         return self._consts.index(value)
 
     def packet_filter(self, always: Sequence[int] = (), if_host: Sequence[int] = (),
-                      if_list: Sequence[int] = ()) -> int:
+                      if_list: Sequence[int] = (), if_listed: Sequence[int] = ()) -> int:
         """Declares which payload tags a ``recv_filter`` loop hands to its program: ``always``; ``if_host`` only when
-        the packet's hostname field is the node's own; ``if_list`` only while the process remembers a packet.  Every
-        other packet is consumed by the loop head, exactly as the body's own dispatch would have ignored it."""
+        the packet's hostname field is the node's own; ``if_list`` only while the process remembers a packet;
+        ``if_listed`` only while it remembers one with the packet's hostname field (the entry ``list_take`` on that
+        field would find).  Every other packet is consumed by the loop head, exactly as the body's own dispatch would
+        have ignored it."""
         def mask(tags: Sequence[int]) -> int:
             m = 0
             for t in tags:
@@ -115,7 +117,7 @@ class Simulator:
                     raise ValueError("payload tags used in filters must be below 32")
                 m |= 1 << t
             return m
-        entry = (mask(always), mask(if_host), mask(if_list))
+        entry = (mask(always), mask(if_host), mask(if_list), mask(if_listed))
         if entry not in self._filters:
             self._filters.append(entry)
         return self._filters.index(entry)
@@ -151,8 +153,8 @@ class Simulator:
             else:
                 init[i] = (self.asm.entry(program), node.index, r, 0, 0)
         filters = np.zeros(len(self._filters), dtype=L.FILTER_DTYPE)
-        for i, (fa, fh, fl) in enumerate(self._filters):
-            filters[i] = (fa, fh, fl, 0)
+        for i, (fa, fh, fl, fm) in enumerate(self._filters):
+            filters[i] = (fa, fh, fl, fm)
         dists = np.zeros(len(self._dists), dtype=L.DIST_DTYPE)   # last: networks and drawn installs add generators
         for i, d in enumerate(self._dists):
             dists[i] = (d.kind, d.flags, d.p0, d.p1, d.slope, d.shift, d.lower, d.upper)

@@ -92,7 +92,7 @@ def _programs(sim: Simulator, num_workstations: int, fused: bool) -> None:
     a.label("loop")
     if fused:
         # the three lines below plus the "not for me" exits of the dispatch, as one instruction
-        a.recv_filter(R0, sim.packet_filter(always=[TAG_QUERY], if_host=[TAG_RESOLVE], if_list=[TAG_IAM]), "asleep")
+        a.recv_filter(R0, sim.packet_filter(always=[TAG_QUERY], if_host=[TAG_RESOLVE], if_listed=[TAG_IAM]), "asleep")
     else:
         a.wait_awake(R0)             # with ws.awake(): wait, remember when we awoke
         a.recv()
