@@ -46,9 +46,11 @@
  * scattered over the 200 KB of the shipped-itsim primitives. */
 #define exec_cold         a0_execute
 #define draw_dist         a1_variate
+#define log_f64           a1z_ln_f64
 #define rng_next          a2_philox_
 #define on_tx_begin       a3_txbegin
 #define on_tx_end         a4_tx_end_
+#define ev_push           a4z_evpush
 #define pool_scan_min     a5_poolmin
 #define net_send          a6_netsend
 #define proc_spawn        a7_spawn__
@@ -282,6 +284,7 @@ struct Hdr {                /* first thing in the hot block */
     u64 ovf_min_t;
     u32 ovf_min_seq, ovf_head, ovf_count;
     u32 spare32;
+    u32 rng_c0, rng_c1;     /* the second half of the Philox block the last even draw computed (= the next draw) */
     u16 sig_free_top, thr_free_top, task_free_top;
     u16 setup_done;         /* the per-replica set-up draws (ITSB_INIT_ADD_DRAWN) have been made */
     u32 hidden_entry_balk, hidden_entry_wait_one;   /* entry indices of greensim's helper programs */
@@ -425,12 +428,11 @@ ITSB_FN void philox_block(u32 seed_lo, u32 seed_hi, u32 rep_lo, u32 rep_hi, u64 
 ITSB_COLD u64 rng_next(Hdr* H) {
     const u64 d = H->draws;
     H->draws = d + 1;
+    if (d & 1) return ((u64)H->rng_c0 << 32) | H->rng_c1;   /* draws are sequential: draw d - 1 computed this block */
     u32 w[4];
     philox_block(H->seed_lo, H->seed_hi, H->replica_lo, H->replica_hi, d >> 1, w);
-    const bool half = (d & 1) != 0;
-    const u32 a = half ? w[2] : w[0];
-    const u32 b = half ? w[3] : w[1];
-    return ((u64)a << 32) | b;
+    H->rng_c0 = w[2]; H->rng_c1 = w[3];
+    return ((u64)w[0] << 32) | w[1];
 }
 
 ITSB_FN double rng_random(Hdr* H) {  /* CPython's 53-bit construction */
@@ -438,6 +440,9 @@ ITSB_FN double rng_random(Hdr* H) {  /* CPython's 53-bit construction */
     const u32 a = (u32)(ab >> 32), b = (u32)ab;
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
 }
+
+/* math.log, one copy of its code for both variates that need it */
+ITSB_COLD double log_f64(double x) { return log(x); }
 
 /* One value of a generator chain: kind -> linear -> bounded -> project_int (itsim/random.py:29). */
 ITSB_COLD double draw_dist(Hdr* H, const itsb_dist* Dp) {
@@ -451,7 +456,7 @@ ITSB_COLD double draw_dist(Hdr* H, const itsb_dist* Dp) {
         x = D.p0 + (D.p1 - D.p0) * rng_random(H);
         break;
     case ITSB_DIST_EXPO:     /* random.expovariate(lambd): -log(1 - random()) / lambd */
-        x = -log(1.0 - rng_random(H)) / D.p0;
+        x = -log_f64(1.0 - rng_random(H)) / D.p0;
         break;
     case ITSB_DIST_NORMAL: { /* random.normalvariate: Kinderman-Monahan ratio of uniforms */
         double z;
@@ -460,7 +465,8 @@ ITSB_COLD double draw_dist(Hdr* H, const itsb_dist* Dp) {
             double u2 = 1.0 - rng_random(H);
             z = 1.7155277699214135 * (u1 - 0.5) / u2;
             double zz = z * z / 4.0;
-            if (zz <= -log(u2)) break;
+            if (zz <= 1.0 - u2) break;     /* -log(u2) >= 1 - u2 (exact: u2 = 1 - k 2^-53): accepted without the log */
+            if (zz <= -log_f64(u2)) break;
         }
         x = D.p0 + z * D.p1;
         break;
@@ -635,17 +641,18 @@ ITSB_FN void ev_release(Rep& R, u32 slot) {
     if (R.hdr->pmin_valid && R.hdr->pmin_idx == slot) R.hdr->pmin_valid = 0;
 }
 
-/* Schedules (t, seq = counter++).  Returns the pool slot (so an advance() can be cancelled) or -1. */
-ITSB_FN int ev_push_inl(Rep& R, double t, u32 data) {
-    Hdr* H = R.hdr;
+/* Schedules (t, seq = counter++).  Returns the pool slot (so an advance() can be cancelled) or -1.  One copy of the
+ * code for all callers: the kernel is bound by instruction fetch, not by instruction count. */
+ITSB_COLD int ev_push(Hdr* H, u64 tb, u32 data) {
     const u32 seq = H->seq;
     H->seq = seq + 1;
-    const u64 tb = dbits(t);
+    unsigned char* hot = (unsigned char*)H;
     if (tb == dbits(H->now)) {
         if (H->nq_spill_count == 0 && H->nq_tail - H->nq_head < NQ_CAP) {
+            u32* nq = (u32*)(hot + H->L.off_nq);
             u32 i = H->nq_tail & (NQ_CAP - 1);
-            R.nq[2 * i] = seq;
-            R.nq[2 * i + 1] = data;
+            nq[2 * i] = seq;
+            nq[2 * i + 1] = data;
             H->nq_tail += 1;
         } else {
             nq_spill_push(H, seq, data);
@@ -659,15 +666,16 @@ ITSB_FN int ev_push_inl(Rep& R, double t, u32 data) {
     }
     top -= 1;
     H->ev_free_top = (u16)top;
-    u32 slot = R.ev_free[top];
-    R.ev_t[slot] = tb;
-    R.ev_seq[slot] = seq;
-    R.ev_data[slot] = data;
+    u32 slot = ((u16*)(hot + H->L.off_ev_free))[top];
+    ((u64*)(hot + H->L.off_ev_t))[slot] = tb;
+    ((u32*)(hot + H->L.off_ev_seq))[slot] = seq;
+    ((u32*)(hot + H->L.off_ev_data))[slot] = data;
     if (H->pmin_valid && (tb < H->pmin_t || (tb == H->pmin_t && seq < H->pmin_seq))) {
         H->pmin_t = tb; H->pmin_seq = seq; H->pmin_idx = slot;
     }
     return (int)slot;
 }
+ITSB_FN int ev_push_inl(Rep& R, double t, u32 data) { return ev_push(R.hdr, dbits(t), data); }
 
 /* Minimum (t, seq) of the future pool: each lane scans a strided slice, then three redux min-reductions. */
 ITSB_COLD void pool_scan_min(Hdr* H) {
@@ -1379,12 +1387,17 @@ ITSB_FN void run_process(Rep& R, u32 p) {
         v[SRC_SELF - 0x10] = handle_of(R, p); v[SRC_EXC - 0x10] = P.exc; v[SRC_ZERO - 0x10] = 0;
         if (R.max_sig != 0) thread_regs(H, p);
     }
+    /* the instructions handled inline below (all numbered under 32); everything else is one test away from exec_cold */
+    const u32 INLINE_OPS = (1u << OP_RECV_FILTER) | (1u << OP_RECV) | (1u << OP_WAIT_AWAKE) | (1u << OP_JMP) |
+                           (1u << OP_JEQI) | (1u << OP_JNEI) | (1u << OP_JEQ) | (1u << OP_JNE) | (1u << OP_JASLEEP);
+    if (H->status != 0) return;
     for (;;) {
-        if (H->status != 0) return;
         const u64 ins = R.m.code[P.pc];
         const u32 op = (u32)(ins & 0xFF), a = (u32)((ins >> 8) & 0xFF), b = (u32)((ins >> 16) & 0xFF),
                   imm = (u32)(ins >> 32);
-        if (op == OP_RECV_FILTER) {
+        if (op >= 32 || ((INLINE_OPS >> op) & 1) == 0) {
+            if (exec_cold(H, p, ins) != XR_CONTINUE || H->status != 0) return;
+        } else if (op == OP_RECV_FILTER) {
             if (P.sock == NIL16) { fail(H, ITSB_EXC_SOCKET_CLOSED, P.pc); return; }
             NodeDyn& N = R.node[P.node];
             Sock& S = R.sock[P.sock];
@@ -1445,10 +1458,8 @@ ITSB_FN void run_process(Rep& R, u32 p) {
         } else if (op == OP_JEQ || op == OP_JNE) {
             const bool eq = src_val(R, P, a) == src_val(R, P, b);
             P.pc = (eq == (op == OP_JEQ)) ? (u16)imm : (u16)(P.pc + 1);
-        } else if (op == OP_JASLEEP) {
+        } else {   /* OP_JASLEEP */
             P.pc = (R.node[P.node].epoch != src_val(R, P, a)) ? (u16)imm : (u16)(P.pc + 1);
-        } else {
-            if (exec_cold(H, p, ins) != XR_CONTINUE) return;
         }
     }
 }
@@ -1809,7 +1820,7 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
     H->nq_head = 0; H->nq_tail = 0; H->nq_spill_head = NIL32; H->nq_spill_tail = NIL32; H->nq_spill_count = 0;
     H->pmin_valid = 0; H->pmin_idx = NIL32; H->pmin_seq = NIL32; H->pmin_t = T_EMPTY;
     H->ovf_min_t = T_EMPTY; H->ovf_min_seq = NIL32; H->ovf_head = NIL32; H->ovf_count = 0;
-    H->spare16 = 0; H->spare32 = 0;
+    H->spare16 = 0; H->spare32 = 0; H->rng_c0 = 0; H->rng_c1 = 0;
     for (u32 i = 0; i < VOL_COUNT; ++i) H->vol[i] = 0;
     for (u32 i = 0; i < 2 * NQ_CAP; ++i) R.nq[i] = 0;
     for (u32 i = 0; i < L->max_ev; ++i) { R.ev_t[i] = T_EMPTY; R.ev_seq[i] = 0; R.ev_data[i] = 0; R.ev_free[i] = (u16)(L->max_ev - 1 - i); }
