@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "simulated events/sec (batched network_simple replicas)"
 # ncu --set full capture committed under profiles/: (dram__bytes_read.sum + dram__bytes_write.sum) / replicas
-NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH = (333.9e6 + 168.9e6) / 6000.0
+NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH = (328.5e6 + 160.7e6) / 6000.0
 UNIT = "events/s"
 
 
@@ -180,6 +180,10 @@ def main() -> None:
     ap.add_argument("--max-sockets", type=int, default=0)
     ap.add_argument("--net-events", type=int, default=0,
                     help="per-replica capacity of the network_event log in HBM (0 = off): the logging-on variant")
+    ap.add_argument("--connections", type=int, default=0,
+                    help="per-replica capacity of the connection-record log (Socket.log_pair) in HBM (0 = off); with "
+                         "--net-events this is BASELINE.json config 5, full logging")
+    ap.add_argument("--connection-window", type=int, default=8)
     ap.add_argument("--workload", default="network_simple", choices=["network_simple", "malware", "large_lan"],
                     help="malware = network_simple + the beaconing-malware overlay (BASELINE.json config 3); "
                          "large_lan = 1024 endpoints + 16 forwarding routers per replica (config 4; use "
@@ -232,7 +236,8 @@ def main() -> None:
         from itsim_b200 import machine_models
         sim = machine_models.large_lan()
     else:
-        sim = netsimple.build() if args.workload == "network_simple" else netsimple.build_malware()
+        build = netsimple.build if args.workload == "network_simple" else netsimple.build_malware
+        sim = build(connection_records=args.connections, connection_window=args.connection_window)
         sim.caps["arena_nodes"] = args.arena_nodes
     sim.caps["net_event_records"] = args.net_events
     for key, val in (("max_events", args.max_events), ("max_procs", args.max_procs), ("max_sockets", args.max_sockets)):
@@ -248,6 +253,7 @@ def main() -> None:
     for _ in range(args.warmup):
         engine.run(args.slice)
     log_records_before = int(engine.telemetry()[L.TM_USER0 + 7])
+    conn_records_before = int(engine.telemetry()[L.TM_USER0 + 6]) if args.connections else 0
 
     # ---- timed region 1: K steps queued back to back, device time ------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -308,7 +314,9 @@ def main() -> None:
         events_per_step_gpu = events_dev / args.steps
         log_records = (int(total[L.TM_USER0 + 7]) // max(1, world) - log_records_before) / (2.0 * args.steps)
         # S_in + S_out per launch, plus B_log = 32 B per network_event record written in a step (0 when the log is off)
-        algo_bytes = 2.0 * state["hot"] * args.replicas + 32.0 * log_records
+        conn_records = ((int(total[L.TM_USER0 + 6]) // max(1, world) - conn_records_before) / (2.0 * args.steps)
+                        if args.connections else 0.0)
+        algo_bytes = 2.0 * state["hot"] * args.replicas + 32.0 * log_records + 40.0 * conn_records
         launch_s = ms_dev * 1e-3 / args.steps
         achieved = algo_bytes / launch_s / 1e9
         cpu = None
@@ -329,6 +337,7 @@ def main() -> None:
                       (args.replicas * (state["hot"] + state["arena"]) / 1e9),
                 "hot_bytes_per_replica": state["hot"], "arena_bytes_per_replica": state["arena"],
                 "net_event_records_per_step_per_gpu": log_records,
+                "connection_records_per_step_per_gpu": conn_records,
                 "cold_job_s": t_cold, "cold_job_h2d_bytes": h2d_model,
                 "spinup_events": spin_events, "spinup_ms": spin_ms,
                 "telemetry_allreduce_ms": allreduce_ms,
@@ -341,10 +350,12 @@ def main() -> None:
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH * args.replicas, "peak_source": peak_src, "kernel": "k_run",
                 "traffic_note": "dram__bytes_read+write of one k_run launch from profiles/r1_k_run_ncu_full.txt "
-                                "(6000 replicas x 60 simulated s: 5.03e8 B vs 2.30e8 B algorithmic), scaled per replica",
+                                "(6000 replicas x 60 simulated s: 4.89e8 B vs 2.27e8 B algorithmic), scaled per replica",
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "note": "algorithmic bytes = per-replica state staged HBM->smem->HBM once per run (S_in+S_out); the "
-                        "kernel is bound by the serial pop->handle->push chain in shared memory, not by HBM",
+                        "kernel is not HBM-bound: its measured limiter is instruction supply (ncu: GPC-level "
+                        "instruction-cache requests at 91% of peak in every configuration tried, launch time "
+                        "proportional to their count; profiles/README.md)",
             },
             "clocks": clocks,
         }

@@ -22,6 +22,10 @@ RAW_METRICS = [
     "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "launch__registers_per_thread",
     "launch__occupancy_limit_shared_mem", "launch__grid_size", "launch__block_size",
     "launch__shared_mem_per_block_dynamic", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    # instruction supply: per-SM instruction cache (icc) and the GPC-level cache behind it (gcc)
+    "sm__icc_requests.sum", "sm__icc_request_hit_rate.pct", "gcc__cache_requests_type_instruction.sum",
+    "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed", "gcc__average_cache_request_hit_rate.pct",
+    "smsp__inst_executed_op_branch.sum",
 ]
 
 
