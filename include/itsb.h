@@ -79,7 +79,8 @@ typedef struct itsb_net_event {   /* 32 bytes: one record of the datastore's `ne
     uint32_t dst_ip;              /* 0: datagram sockets have no peer at open time                                 */
     uint16_t dst_port;
     uint16_t prog;                /* program id of the process that opened / closed it                             */
-    uint32_t reserved;
+    uint16_t tags;                /* its tags (bit i = Tag value i: 0 MALWARE, 1 VULNERABLE)                      */
+    uint16_t reserved;
 } itsb_net_event;
 
 typedef struct itsb_connection {  /* 40 bytes: one connection record, the JSON `Socket.log_pair` prints
@@ -174,7 +175,10 @@ typedef struct itsb_route {       /* Local / Relay (itsim/network/route.py:8-59)
 
 typedef struct itsb_entry {       /* program entry point                                                          */
     uint32_t pc;                  /* first instruction                                                            */
-    uint32_t prog;                /* program id reported in trace records                                         */
+    uint16_t prog;                /* program id reported in trace records                                         */
+    uint16_t tags;                /* greensim tags of the body (`@tagged`, itsim/__init__.py:9-11,52-57): bit i =
+                                     Tag value i.  A process carries its body's tags and those of the process that
+                                     created it (greensim cascades them)                                          */
 } itsb_entry;
 
 typedef struct itsb_initproc {    /* process started at t=0, in program order                                     */

@@ -34,7 +34,7 @@ ERRORS = {
 
 NET_EVENT_DTYPE = np.dtype([("t", "<f8"), ("node", "<u2"), ("port", "<u2"), ("type", "u1"), ("protocol", "u1"),
                             ("pid", "<i2"), ("src_ip", "<u4"), ("dst_ip", "<u4"), ("dst_port", "<u2"), ("prog", "<u2"),
-                            ("reserved", "<u4")])
+                            ("tags", "<u2"), ("reserved", "<u2")])
 assert NET_EVENT_DTYPE.itemsize == 32
 TRACE_DTYPE = np.dtype([("t", "<f8"), ("kind", "u1"), ("prog", "u1"), ("node", "<u2"), ("aux", "<u4")])
 DIST_DTYPE = np.dtype([("kind", "<u4"), ("flags", "<u4"), ("p0", "<f8"), ("p1", "<f8"), ("slope", "<f8"),

@@ -132,7 +132,8 @@ struct Pcb {                /* 48 bytes: one greensim process */
     u32 list_head, list_tail; /* remembered-packet list (arena nodes) */
     u32 r[4];
     u16 timer_tok;          /* bumped by every advance(); a TIMER event is live only if it carries the current one */
-    u16 phase;              /* RECV_FILTER: 0 = before the awake check, 1 = inside recv() */
+    u8 phase;               /* RECV_FILTER: 0 = before the awake check, 1 = inside recv() */
+    u8 tags;                /* greensim tags: the body's and, cascaded, the creator's */
 };
 
 enum { PS_FREE = 0, PS_UNSTARTED = 1, PS_RUNNING = 2, PS_TIMER = 3, PS_WAIT = 4, PS_RESUMING = 5 };
@@ -513,7 +514,8 @@ ITSB_COLD void net_event_put(Hdr* H, u32 type, u32 node, u32 port, u32 src_ip, u
     if (n < H->L.log_cap && lane_id() == 0) {
         itsb_net_event E;
         E.t = H->now; E.node = (u16)node; E.port = (u16)port; E.type = (u8)type; E.protocol = (u8)protocol;
-        E.pid = (int16_t)pid; E.src_ip = src_ip; E.dst_ip = 0; E.dst_port = 0; E.prog = (u16)prog; E.reserved = 0;
+        E.pid = (int16_t)pid; E.src_ip = src_ip; E.dst_ip = 0; E.dst_port = 0; E.prog = (u16)(prog & 0xFFFF);
+        E.tags = (u16)(prog >> 16); E.reserved = 0;
         H->netlog[n] = E;
     }
     H->log_count = n + 1;
@@ -767,6 +769,7 @@ ITSB_COLD int proc_spawn(Hdr* H, u32 entry, u32 node, const u32* regs, double de
     P.pc = (u16)E.pc;
     P.state = PS_UNSTARTED;
     P.prog = (u8)E.prog;
+    P.tags = (u8)(E.tags | H->vol[SRC_TAGS - 0x10]);   /* the creator is the process running now (none at set-up) */
     P.node = (u16)node;
     P.wnext = NIL16; P.wprev = NIL16; P.wsig = WS_NONE; P.timer_ev = NIL16; P.sock = NIL16; P.exc = 0;
     P.list_head = NIL32; P.list_tail = NIL32; P.phase = 0;
@@ -905,7 +908,7 @@ ITSB_COLD int sock_open_on(Hdr* H, u32 p, u32 node, u32 port, bool own) {
     S.next = N.sock_head;
     N.sock_head = (u16)s;
     if (own) P.sock = (u16)s;
-    net_event_put(H, 1, node, port, R.m.nodes[node].addr, P.prog, 0, 1);
+    net_event_put(H, 1, node, port, R.m.nodes[node].addr, P.prog | ((u32)P.tags << 16), 0, 1);
     return (int)s;
 }
 
@@ -916,7 +919,7 @@ ITSB_COLD void sock_close(Hdr* H, u32 p) {
     if (s == NIL16) return;
     Sock& S = R.sock[s];
     NodeDyn& N = R.node[S.node];
-    net_event_put(H, 2, S.node, S.port, R.m.nodes[S.node].addr, P.prog, 0, 1);
+    net_event_put(H, 2, S.node, S.port, R.m.nodes[S.node].addr, P.prog | ((u32)P.tags << 16), 0, 1);
     if (N.sock_head == s) N.sock_head = S.next;
     else {
         u16 q = N.sock_head;
@@ -1385,6 +1388,7 @@ ITSB_FN void run_process(Rep& R, u32 p) {
         v[SRC_NODE_ADDR - 0x10] = N.addr; v[SRC_NODE_INDEX - 0x10] = P.node; v[SRC_NODE_HOST - 0x10] = N.host;
         v[SRC_NODE_EPOCH - 0x10] = R.node[P.node].epoch; v[SRC_NODE_BCAST - 0x10] = R.m.nets[N.net].bcast;
         v[SRC_SELF - 0x10] = handle_of(R, p); v[SRC_EXC - 0x10] = P.exc; v[SRC_ZERO - 0x10] = 0;
+        v[SRC_TAGS - 0x10] = P.tags;
         if (R.max_sig != 0) thread_regs(H, p);
     }
     /* the instructions handled inline below (all numbered under 32); everything else is one test away from exec_cold */

@@ -107,6 +107,7 @@ enum {
     SRC_NODE_ADDR = 0x20, SRC_NODE_INDEX = 0x21, SRC_NODE_HOST = 0x22, SRC_NODE_EPOCH = 0x23,
     SRC_NODE_BCAST = 0x24, SRC_SELF = 0x25, SRC_EXC = 0x26,
     SRC_SELF_THREAD = 0x27, SRC_SELF_TASK = 0x28, SRC_PID = 0x29,
+    SRC_TAGS = 0x2A,    /* tags of the running process: what a process it creates inherits */
     SRC_ZERO = 0x30,
     SRC_G0 = 0x31,      /* model variables g0..g7 = 0x31..0x38 */
     SRC_NONE = 0xFF

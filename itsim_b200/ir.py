@@ -6,7 +6,7 @@ process_management/thread.py:41-57``), which a GPU kernel cannot r
 once with this assembler as an explicit state machine over the reference's own primitives.  Opcodes and operand
 encodings mirror ``itsim_b200/csrc/itsb_ir.h`` one to one.
 """
-from typing import Dict, List, Optional, Tuple, Union
+from typing import Sequence, Dict, List, Optional, Tuple, Union
 
 import numpy as np
 
@@ -59,23 +59,27 @@ class Asm:
         self.log_connections = False   # socket calls assemble to their *_LOG forms (models that keep connection records)
 
     # -- structure ---------------------------------------------------------------------------------------
-    def program(self, name: str, prog_id: int) -> int:
-        """Starts a new program; returns its entry index."""
+    def program(self, name: str, prog_id: int, tags: Sequence[int] = ()) -> int:
+        """Starts a new program; returns its entry index.  ``tags`` are the body's greensim tags (``@tagged``,
+        ``@malware``: itsim/__init__.py:9-11,52-57); processes also inherit the tags of their creator."""
         self._scope = name + "."
         self._labels[name] = len(self._ins)
         self._entry_index[name] = len(self.entries)
-        self.entries.append((name, prog_id))
+        mask = 0
+        for t in tags:
+            mask |= 1 << int(t)
+        self.entries.append((name, prog_id | (mask << 16)))
         return self._entry_index[name]
 
     def entry(self, name: str) -> int:
         return self._entry_index[name]
 
     # -- shipped-itsim thread bodies -------------------------------------------------------------------------
-    def thread_program(self, name: str, prog_id: int) -> int:
+    def thread_program(self, name: str, prog_id: int, tags: Sequence[int] = ()) -> int:
         """Starts a body run through ``Thread.run_in`` (thread.py:41-57): ``try: advance(delay); body finally:
         exit_f``.  Blocking instructions of the body default to the handler that runs ``exit_f`` and re-raises."""
         self.uses_machine = True
-        idx = self.program(name, prog_id)
+        idx = self.program(name, prog_id, tags)
         self._default_handler = "__exit_raise"
         self._emit(OP_ADVANCE_X, imm=("hi16", self._t("__exit_raise"), 0))
         return idx

@@ -14,6 +14,7 @@ from .ir import G0, R0, R1, R2, R3  # noqa: F811
 from .ir import PKT_F0 as _PKT_F0, PKT_F1 as _PKT_F1, DST_REGS
 from .model import DrawnNode, Endpoint, Network, Simulator, Workstation
 from .random import bounded, constant, distribution_index, expo, normal, num_bytes
+from .tags import Tag
 from .units import B, GbPS, H, MIN, MS, MbPS, S, US
 
 # program ids reported in trace records (shared with oracle/netsimple.py)
@@ -247,19 +248,19 @@ def build_malware(trace_records: int = 0, fused: bool = True, connection_records
     router_wan = sim.router.link_to(www)                          # malware_simple.py:117
     bear = Endpoint("Mama Bear", www, BAD_NEWS_BEAR_ADDR)
 
-    a.program("call_home", PROG_CALL_HOME)                        # malware_simple.py:53-58
+    a.program("call_home", PROG_CALL_HOME, tags=[Tag.MALWARE])    # malware_simple.py:53-58 (@malware)
     a.label("loop")
     a.advance(d_beacon)
     a.spawn("exfiltrate")
     a.jmp("loop")
 
-    a.program("no_good", PROG_NO_GOOD)                            # :61-65
+    a.program("no_good", PROG_NO_GOOD, tags=[Tag.MALWARE])        # :61-65 (@malware)
     a.label("loop")
     a.advance(d_privileged)
     a.spawn("sudo_transmit")
     a.jmp("loop")
 
-    a.program("sudo_transmit", PROG_SUDO_TRANSMIT)                # :68-72
+    a.program("sudo_transmit", PROG_SUDO_TRANSMIT, tags=[Tag.VULNERABLE])   # :68-72 (@tagged(Tag.VULNERABLE))
     a.spawn("exfiltrate")
     a.exit()
 
@@ -287,7 +288,7 @@ def build_malware(trace_records: int = 0, fused: bool = True, connection_records
     a.forward(router_wan, LOCAL_ROUTER_PORT)
     a.jmp("loop")
 
-    a.program("command_and_control", PROG_C2)                     # :85-92
+    a.program("command_and_control", PROG_C2, tags=[Tag.MALWARE]) # :85-92 (@malware)
     a.open(BAD_NEWS_BEAR_PORT)
     a.label("loop")
     a.recv()

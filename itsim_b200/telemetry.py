@@ -41,6 +41,13 @@ def network_event_documents(records: np.ndarray, sim_uuid: Optional[str] = None,
     return docs
 
 
+def network_event_labels(records: np.ndarray) -> List[List[str]]:
+    """The tag names (``itsim.Tag``) of the process behind each record: the ground truth a detector trained on the
+    telemetry is scored against (``sphinx/source/overview.rst:46-56``: tags cascade from malware to what it causes)."""
+    from .tags import tag_names
+    return [tag_names(int(rec["tags"])) for rec in records]
+
+
 def datastore_rows(documents: Iterable[Dict[str, Any]]) -> List[Tuple[str, str, str, str]]:
     """``(uuid, timestamp, sim_uuid, json)`` rows of the datastore's ``network_event`` table."""
     return [(d["uuid"], d["timestamp"], d["sim_uuid"], json.dumps(d)) for d in documents]

@@ -35,7 +35,8 @@ if _HERE not in sys.path:
     sys.path.insert(0, _HERE)
 
 import greensim  # noqa: E402  (the shim in oracle/greensim)
-from greensim import Process, Signal, Simulator, add, advance, now  # noqa: E402
+from greensim import Process, Signal, Simulator, add, advance, now, tagged  # noqa: E402
+from greensim.tags import Tags  # noqa: E402
 from greensim.random import bounded, constant, distribution, expo, linear, normal, project_int  # noqa: E402
 import greensim.random as gsrandom  # noqa: E402
 
@@ -150,6 +151,20 @@ class _NetworkLink:
             if port not in self.ports:
                 return port
         raise AssertionError
+
+
+class Tag(Tags):
+    """itsim/__init__.py:9-11."""
+    MALWARE = 0
+    VULNERABLE = 1
+
+
+def current_tags() -> int:
+    """Bit mask (bit = tag value) of ``Process.current().iter_tags()``: what malware_simple.py:46 prints per log line."""
+    mask = 0
+    for t in Process.current().iter_tags():
+        mask |= 1 << t.value
+    return mask
 
 
 class Socket:
@@ -294,11 +309,11 @@ class Node:
             alias = (self._broadcast_address(src[0]), src[1])  # also listens on the broadcast address
             self._sockets[src] = sock
             self._sockets[alias] = sock
-            self.model.net_events.append((now(), self.index, src[1], 1))      # network_event "open"
+            self.model.net_events.append((now(), self.index, src[1], 1, current_tags()))   # network_event "open"
             try:
                 yield sock
             finally:
-                self.model.net_events.append((now(), self.index, src[1], 2))  # network_event "close"
+                self.model.net_events.append((now(), self.index, src[1], 2, current_tags()))   # "close"
                 sock.flush_logs()
                 del self._sockets[src]
                 del self._sockets[alias]
@@ -617,13 +632,15 @@ class MalwareModel(Model):
         self.bear = Node(self, "Mama Bear", self.www, self.BAD_NEWS_BEAR_ADDR)
         self.bear.install(PROG_C2, self.command_and_control)
 
+    @tagged(Tag.MALWARE)
     def call_home(self, ws: Node) -> None:
-        """malware_simple.py:53-58."""
+        """malware_simple.py:53-58 (``@malware`` = ``tagged(Tag.MALWARE)``, itsim/__init__.py:52-57)."""
         while True:
             advance(next(expo(10)))
             proc = add(self.exfiltrate, ws)
             tr.Tracer.label(proc, tr.ROLE_MODEL, PROG_EXFILTRATE, ws.index)
 
+    @tagged(Tag.MALWARE)
     def no_good(self, ws: Node) -> None:
         """malware_simple.py:61-65."""
         while True:
@@ -631,6 +648,7 @@ class MalwareModel(Model):
             proc = add(self.sudo_transmit, ws)
             tr.Tracer.label(proc, tr.ROLE_MODEL, PROG_SUDO_TRANSMIT, ws.index)
 
+    @tagged(Tag.VULNERABLE)
     def sudo_transmit(self, ws: Node) -> None:
         """malware_simple.py:68-72."""
         proc = add(self.exfiltrate, ws)
@@ -652,6 +670,7 @@ class MalwareModel(Model):
                     self.stats["routed"] += 1
                     world_socket.send(msg.payload["dest_addr"], msg.byte_size, msg.payload)
 
+    @tagged(Tag.MALWARE)
     def command_and_control(self, bear: Node) -> None:
         """malware_simple.py:85-92."""
         with bear.open_socket(self.BAD_NEWS_BEAR_PORT) as socket:

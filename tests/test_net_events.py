@@ -81,3 +81,34 @@ def test_conversion_to_the_datastore_schema(hostemu, tmp_path):
     assert db.execute("SELECT COUNT(*) FROM network_event").fetchone()[0] == len(docs)
     first = json.loads(db.execute("SELECT json FROM network_event ORDER BY timestamp LIMIT 1").fetchone()[0])
     assert first["network_event_type"] == "open"
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_records_carry_the_tags_greensim_cascades(backend, hostemu):
+    """malware_simple.py tags its bodies (`@malware`, `@tagged(Tag.VULNERABLE)`) and greensim hands a process the tags
+    of the process that created it (itsim/__init__.py:52-57): the sockets `exfiltrate` opens are labelled MALWARE
+    when `call_home` spawned it, MALWARE + VULNERABLE when it came through `sudo_transmit`, and nothing the
+    network_simple programs open is labelled."""
+    import netsimple as oracle_netsimple
+    from itsim_b200 import netsimple
+    from itsim_b200.tags import Tag, tag_mask, tag_names
+    seed, replica, horizon = 6, 3, 1200.0
+    sim = netsimple.build_malware()
+    sim.caps["net_event_records"] = 30000
+    sim._lib = hostemu if backend == "hostemu" else None
+    eng = sim.run_replicas(1, seed=seed, first_replica_id=replica)
+    eng.run(horizon)
+    got = eng.net_events(0)
+    model = oracle_netsimple.MalwareModel(seed, replica, trace=False)
+    model.run(horizon)
+    ref = list(model.net_events)
+    model.close()
+    assert len(got) == len(ref)
+    assert [int(x) for x in got["type"]] == [r[3] for r in ref]
+    assert [int(x) for x in got["port"]] == [r[2] for r in ref]
+    assert [int(x) for x in got["tags"]] == [r[4] for r in ref]
+    masks = {int(x) for x in got["tags"]}
+    assert masks == {0, tag_mask([Tag.MALWARE]), tag_mask([Tag.MALWARE, Tag.VULNERABLE])}
+    assert tag_names(3) == ["MALWARE", "VULNERABLE"]
+    # only the overlay's own sockets (port 666: exfiltrate and the command-and-control host) are labelled
+    assert {int(r["port"]) for r in got if r["tags"]} == {oracle_netsimple.MalwareModel.BAD_NEWS_BEAR_PORT}
