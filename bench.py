@@ -184,8 +184,9 @@ def main() -> None:
                     help="per-replica capacity of the connection-record log (Socket.log_pair) in HBM (0 = off); with "
                          "--net-events this is BASELINE.json config 5, full logging")
     ap.add_argument("--connection-window", type=int, default=8)
-    ap.add_argument("--workload", default="network_simple", choices=["network_simple", "malware", "large_lan"],
+    ap.add_argument("--workload", default="network_simple", choices=["network_simple", "malware", "backdoor", "large_lan"],
                     help="malware = network_simple + the beaconing-malware overlay (BASELINE.json config 3); "
+                         "backdoor = the overlay with the parameters of examples/backdoor/backdoor.py; "
                          "large_lan = 1024 endpoints + 16 forwarding routers per replica (config 4; use "
                          "--replicas 10000 --slice 2 --spinup 6)")
     args = ap.parse_args()
@@ -236,7 +237,8 @@ def main() -> None:
         from itsim_b200 import machine_models
         sim = machine_models.large_lan()
     else:
-        build = netsimple.build if args.workload == "network_simple" else netsimple.build_malware
+        build = {"network_simple": netsimple.build, "malware": netsimple.build_malware,
+                 "backdoor": netsimple.build_backdoor}[args.workload]
         sim = build(connection_records=args.connections, connection_window=args.connection_window)
         sim.caps["arena_nodes"] = args.arena_nodes
     sim.caps["net_event_records"] = args.net_events

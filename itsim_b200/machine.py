@@ -151,6 +151,16 @@ class Node:
     with_proc_in = run_proc_in
     with_proc = run_proc
 
+    def schedule_daemon_in(self, sim: Simulator, time: float, program: str, *regs: int) -> "Node":
+        """``node.py:352-357``: a daemon's trigger run as a new process after ``time``."""
+        return self.run_proc_in(sim, time, program, *regs)
+
+    def connected_to_dynamic(self, link: Link, sim: Simulator, program: str = "dhcp_client") -> "Node":
+        """``node.py:135-154``: connect at host number 0 of the link's CIDR and start a DHCP client on the new
+        interface (``program`` = the assembled ``DHCPClient`` body, ``machine_models.dhcp_exchange``)."""
+        self._connect_to(link, as_address(None), None)
+        return self.schedule_daemon_in(sim, 0.0, program)
+
 
 class Endpoint(Node):
     """``itsim/machine/endpoint.py:4-8``."""

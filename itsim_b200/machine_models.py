@@ -383,7 +383,7 @@ def dhcp_exchange(trace_records: int = 8192, clients: int = 3) -> Simulator:
     router = Router().connected_to_static(link, "10.1.128.1")
     router.run_proc(sim, "dhcp_listen_first")
     for _ in range(clients):
-        Endpoint().connected_to_static(link, as_address(None)).run_proc_in(sim, 0.0, "dhcp_client")
+        Endpoint().connected_to_dynamic(link, sim)                 # node.py:135-154 = test_dhcp_exchange.py:25-27
     _caps(sim, trace_records)
     sim.caps["table_words"] = T_RESERVED + T_RESERVED_SLOTS
     return sim

@@ -4,8 +4,8 @@ on the override classes of ``network_simple_overrides.py``), built on this packa
 the engine.  ``build()`` mirrors ``init()`` (network_simple.py:311-387); each ``_prog_*`` restates one process body
 as an IR program, citing the lines it follows.  RNG draw order per replica follows SURVEY.md Appendix B.
 """
-from ipaddress import ip_network
-from typing import Optional
+from ipaddress import ip_address, ip_network
+from typing import Optional, Sequence, Tuple
 
 from . import ir
 from .ir import (DST_BCAST, DST_ENT, DST_PKT_SRC, DST_SELF, NODE_ADDR, NODE_HOST, PKT_F0, PKT_F1, PKT_SIZE, PKT_TAG,
@@ -13,9 +13,9 @@ from .ir import (DST_BCAST, DST_ENT, DST_PKT_SRC, DST_SELF, NODE_ADDR, NODE_HOST
 from .ir import G0, R0, R1, R2, R3  # noqa: F811
 from .ir import PKT_F0 as _PKT_F0, PKT_F1 as _PKT_F1, DST_REGS
 from .model import DrawnNode, Endpoint, Network, Simulator, Workstation
-from .random import bounded, constant, distribution_index, expo, normal, num_bytes
+from .random import Dist, bounded, constant, distribution_index, expo, normal, num_bytes, uniform
 from .tags import Tag
-from .units import B, GbPS, H, MIN, MS, MbPS, S, US
+from .units import B, GbPS, H, MB, MIN, MS, MbPS, S, US
 
 # program ids reported in trace records (shared with oracle/netsimple.py)
 PROG_DHCP_SERVE, PROG_BLINKING, PROG_CLIENT, PROG_MDNS, PROG_LLMNR = 1, 2, 3, 4, 5
@@ -234,19 +234,31 @@ def build(cidr: str = "192.168.4.0/24", num_endpoints: Optional[int] = None, tra
 
 
 def build_malware(trace_records: int = 0, fused: bool = True, connection_records: int = 0,
-                  connection_window: int = 8) -> Simulator:
+                  connection_window: int = 8, beacon_gap: Optional[Dist] = None,
+                  privileged_gap: Optional[Dist] = None, c2_targets: Optional[Sequence[Tuple[int, int]]] = None,
+                  beacon_size: Optional[Dist] = None, infected_index: Optional[int] = None) -> Simulator:
     """network_simple + the beaconing-malware overlay of ``examples/network_simple/malware_simple.py:53-125``
     (BASELINE.json config 3).  One workstation drawn per replica at set-up runs ``call_home`` (beacon every expo(10) s)
     and ``no_good`` (every expo(100) s); the router's ``route`` relays the 100-byte beacons over the ``Internet``
     network (overrides.py:443-456) to the command-and-control host 1.2.3.4:666.  The overlay's own statistics are the
-    user counters STAT_BEACONS / STAT_ROUTED / STAT_C2_RECEIVED."""
+    user counters STAT_BEACONS / STAT_ROUTED / STAT_C2_RECEIVED.
+
+    The keyword parameters are those of ``examples/backdoor/backdoor.py`` (which itself cannot run: it calls
+    ``tcp_connect`` and ``random_network_activity``, absent from the reference): ``beacon_gap`` (:34, uniform(2.1 h,
+    4.9 h)), ``c2_targets`` (:11-20, a beacon goes to ``next(distribution(targets))``), ``beacon_size`` (:21),
+    ``infected_index`` (:69, workstations[23]); see ``build_backdoor``."""
     sim = build(trace_records=trace_records, fused=fused, connection_records=connection_records,
                 connection_window=connection_window)
     a = sim.asm
     www = Network(sim, "0.0.0.0/0", latency=bounded(expo(1 * S), lower=20 * MS), bandwidth=expo(10 * MbPS))
-    d_beacon, d_privileged = sim.dist(expo(10)), sim.dist(expo(100))
+    d_beacon = sim.dist(beacon_gap if beacon_gap is not None else expo(10))
+    d_privileged = sim.dist(privileged_gap if privileged_gap is not None else expo(100))
     router_wan = sim.router.link_to(www)                          # malware_simple.py:117
-    bear = Endpoint("Mama Bear", www, BAD_NEWS_BEAR_ADDR)
+    targets = list(c2_targets) if c2_targets else [(BAD_NEWS_BEAR_ADDR, BAD_NEWS_BEAR_PORT)]
+    if len(targets) > 16:
+        raise ValueError("at most 16 command-and-control targets")
+    bears = [Endpoint("Mama Bear" if k == 0 else f"Mama Bear {k + 1}", www, addr) for k, (addr, _) in enumerate(targets)]
+    bear = bears[0]
 
     a.program("call_home", PROG_CALL_HOME, tags=[Tag.MALWARE])    # malware_simple.py:53-58 (@malware)
     a.label("loop")
@@ -266,13 +278,26 @@ def build_malware(trace_records: int = 0, fused: bool = True, connection_records
 
     a.program("exfiltrate", PROG_EXFILTRATE)                      # :75-82
     a.stat(STAT_BEACONS)
+    if c2_targets:                                                # backdoor.py:36 next(location_c2)
+        a.drawi(R0, sim.dist(distribution_index(len(targets))))
+        for k in range(1, len(targets)):
+            a.jeqi(R0, k, f"target{k}")
+    for k, (addr, port) in enumerate(targets):
+        if k:
+            a.label(f"target{k}")
+        a.li(R1, port)
+        a.gset(1, R1)                                             # payload["dest_addr"] = Location(addr, port)
+        a.li(R1, addr)
+        if k + 1 < len(targets):
+            a.jmp("chosen")
+    a.label("chosen")
+    if beacon_size is not None:                                   # backdoor.py:37 next(len_beacon)
+        a.drawi(R0, sim.dist(beacon_size))
+    else:
+        a.li(R0, 100)
     a.open(BAD_NEWS_BEAR_PORT)
-    a.li(R1, BAD_NEWS_BEAR_PORT)
-    a.gset(1, R1)                                                 # payload["dest_addr"] = Location(1.2.3.4, 666)
-    a.li(R1, BAD_NEWS_BEAR_ADDR)
     a.li(R2, sim.router.address)
     a.li(R3, LOCAL_ROUTER_PORT)
-    a.li(R0, 100)
     a.send(DST_REGS, R0, TAG_EXFIL, f0=R1, f1=G0 + 1)
     a.close()
     a.exit()
@@ -288,18 +313,37 @@ def build_malware(trace_records: int = 0, fused: bool = True, connection_records
     a.forward(router_wan, LOCAL_ROUTER_PORT)
     a.jmp("loop")
 
-    a.program("command_and_control", PROG_C2, tags=[Tag.MALWARE]) # :85-92 (@malware)
-    a.open(BAD_NEWS_BEAR_PORT)
-    a.label("loop")
-    a.recv()
-    a.stat(STAT_C2_RECEIVED)
-    a.jmp("loop")
+    for port in sorted({port for _, port in targets}):
+        a.program(f"command_and_control_{port}", PROG_C2, tags=[Tag.MALWARE])   # :85-92 (@malware)
+        a.open(port)
+        a.label("loop")
+        a.recv()
+        a.stat(STAT_C2_RECEIVED)
+        a.jmp("loop")
 
-    infected = DrawnNode(sim, sim.workstations)                   # :114 next(distribution(workstation_list))
+    if infected_index is None:
+        infected = DrawnNode(sim, sim.workstations)               # :114 next(distribution(workstation_list))
+    else:
+        infected = sim.workstations[infected_index]               # backdoor.py:69
     infected.install("call_home")
     infected.install("no_good")
     sim.router.install("route")
-    bear.install("command_and_control")
-    sim.router_wan, sim.bear = router_wan, bear
-    sim.caps.update(max_procs=224, max_sockets=100)
+    for b, (_, port) in zip(bears, targets):
+        b.install(f"command_and_control_{port}")
+    sim.router_wan, sim.bear, sim.bears = router_wan, bear, bears
+    sim.caps.update(max_procs=224, max_sockets=100 + len(targets))
     return sim
+
+
+# examples/backdoor/backdoor.py:11-22,34,69
+BACKDOOR_C2 = [(int(ip_address("2.7.45.67")), 80), (int(ip_address("198.51.100.7")), 8080),      # "rom.com"
+               (int(ip_address("8.45.90.222")), 80), (int(ip_address("198.51.100.9")), 8081)]    # "intelligent.design"
+
+
+def build_backdoor(**kw) -> Simulator:
+    """The malware overlay with the parameters of ``examples/backdoor/backdoor.py``: 50 workstations, workstation 24
+    (index 23) infected, a beacon every uniform(2.1 h, 4.9 h) to one of four C2 locations, beacon length
+    ``num_bytes(expo(1024 B), header=128 B, upper=20 MB)``; meant to run 72 h (:70).  The two locations the example
+    names by host name get documentation addresses (the reference has no resolver to give them one)."""
+    return build_malware(beacon_gap=uniform(2.1 * H, 4.9 * H), c2_targets=BACKDOOR_C2,
+                         beacon_size=num_bytes(expo(1024 * B), header=128 * B, upper=20 * MB), infected_index=23, **kw)

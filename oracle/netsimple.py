@@ -613,14 +613,27 @@ class MalwareModel(Model):
     LOCAL_ROUTER_PORT = 777
 
     def __init__(self, seed: int = 0, replica: int = 0, trace: bool = True, trace_limit: Optional[int] = None,
-                 conn_window: Optional[int] = None) -> None:
+                 conn_window: Optional[int] = None, beacon_gap: Any = None, privileged_gap: Any = None,
+                 c2_targets: Optional[List[Location]] = None, beacon_size: Any = None,
+                 infected_index: Optional[int] = None) -> None:
+        """The keyword parameters are those of examples/backdoor/backdoor.py (itself not runnable: it calls
+        ``tcp_connect`` and ``random_network_activity``, which do not exist): ``beacon_gap`` :34 uniform(2.1 h, 4.9 h),
+        ``c2_targets`` :11-20 the C2 locations a beacon picks from with ``next(distribution(...))``, ``beacon_size``
+        :21 num_bytes(expo(1024 B), header=128 B, upper=20 MB), ``infected_index`` :69 workstations[23].  Left at None
+        they give malware_simple.py as written."""
         super().__init__(seed, replica, trace=trace, trace_limit=trace_limit, conn_window=conn_window)
+        self.beacon_gap, self.privileged_gap, self.beacon_size = beacon_gap, privileged_gap, beacon_size
+        self.c2_targets = c2_targets or [(self.BAD_NEWS_BEAR_ADDR, self.BAD_NEWS_BEAR_PORT)]
+        self.location_c2 = distribution(self.c2_targets) if c2_targets else None
         self.stats.update({"beacons": 0, "routed": 0, "c2_received": 0})
         gsrandom.set_default_rng(self.rng)
         try:
             self.www = Network(self, "0.0.0.0/0", latency=bounded(expo(1 * S), lower=20 * MS),
                                bandwidth=expo(10 * MbPS))
-            infected = next(distribution(self.workstations))            # malware_simple.py:114
+            if infected_index is None:
+                infected = next(distribution(self.workstations))        # malware_simple.py:114
+            else:
+                infected = self.workstations[infected_index]            # backdoor.py:69
         finally:
             gsrandom.set_default_rng(None)
         self.infected = infected
@@ -629,14 +642,18 @@ class MalwareModel(Model):
         self.router_local_addr = self.router.address_default
         self.router_inet_addr = self.router.link_to(self.www)
         self.router.install(PROG_ROUTE, self.route)
-        self.bear = Node(self, "Mama Bear", self.www, self.BAD_NEWS_BEAR_ADDR)
-        self.bear.install(PROG_C2, self.command_and_control)
+        self.bears = []
+        for k, (addr, port) in enumerate(self.c2_targets):
+            bear = Node(self, "Mama Bear" if k == 0 else f"Mama Bear {k + 1}", self.www, addr)
+            bear.install(PROG_C2, self.command_and_control, port)
+            self.bears.append(bear)
+        self.bear = self.bears[0]
 
     @tagged(Tag.MALWARE)
     def call_home(self, ws: Node) -> None:
         """malware_simple.py:53-58 (``@malware`` = ``tagged(Tag.MALWARE)``, itsim/__init__.py:52-57)."""
         while True:
-            advance(next(expo(10)))
+            advance(next(self.beacon_gap if self.beacon_gap is not None else expo(10)))
             proc = add(self.exfiltrate, ws)
             tr.Tracer.label(proc, tr.ROLE_MODEL, PROG_EXFILTRATE, ws.index)
 
@@ -644,7 +661,7 @@ class MalwareModel(Model):
     def no_good(self, ws: Node) -> None:
         """malware_simple.py:61-65."""
         while True:
-            advance(next(expo(100)))
+            advance(next(self.privileged_gap if self.privileged_gap is not None else expo(100)))
             proc = add(self.sudo_transmit, ws)
             tr.Tracer.label(proc, tr.ROLE_MODEL, PROG_SUDO_TRANSMIT, ws.index)
 
@@ -657,9 +674,11 @@ class MalwareModel(Model):
     def exfiltrate(self, ws: Node) -> None:
         """malware_simple.py:75-82."""
         self.stats["beacons"] += 1
+        target = next(self.location_c2) if self.location_c2 is not None else self.c2_targets[0]   # backdoor.py:36
+        size = next(self.beacon_size) if self.beacon_size is not None else 100                      # backdoor.py:37
         with ws.open_socket(self.BAD_NEWS_BEAR_PORT) as socket:
-            socket.send((self.router_local_addr, self.LOCAL_ROUTER_PORT), 100,
-                        {"content": "exfil", "dest_addr": (self.BAD_NEWS_BEAR_ADDR, self.BAD_NEWS_BEAR_PORT)})
+            socket.send((self.router_local_addr, self.LOCAL_ROUTER_PORT), size,
+                        {"content": "exfil", "dest_addr": target})
 
     def route(self, router: Node) -> None:
         """malware_simple.py:96-107: the one-way router."""
@@ -671,9 +690,9 @@ class MalwareModel(Model):
                     world_socket.send(msg.payload["dest_addr"], msg.byte_size, msg.payload)
 
     @tagged(Tag.MALWARE)
-    def command_and_control(self, bear: Node) -> None:
+    def command_and_control(self, bear: Node, port: int = BAD_NEWS_BEAR_PORT) -> None:
         """malware_simple.py:85-92."""
-        with bear.open_socket(self.BAD_NEWS_BEAR_PORT) as socket:
+        with bear.open_socket(port) as socket:
             while True:
                 socket.recv()
                 self.stats["c2_received"] += 1
