@@ -34,6 +34,7 @@ METRIC = "simulated events/sec (batched network_simple replicas)"
 # ncu --set full capture committed under profiles/: (dram__bytes_read.sum + dram__bytes_write.sum) / replicas
 NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH = (328.5e6 + 160.7e6) / 6000.0
 UNIT = "events/s"
+RESULT_OUT = sys.stdout
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -159,7 +160,7 @@ def run_reference_arm(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 def main() -> None:
@@ -190,6 +191,10 @@ def main() -> None:
                          "large_lan = 1024 endpoints + 16 forwarding routers per replica (config 4; use "
                          "--replicas 10000 --slice 2 --spinup 6)")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner) goes to stderr
+    global RESULT_OUT
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     if args.impl == "reference":
         run_reference_arm(args)
@@ -363,7 +368,7 @@ def main() -> None:
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     engine.close()
     if dist is not None:
         dist.destroy_process_group()
