@@ -163,6 +163,26 @@ def run_reference_arm(args) -> None:
     print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
+def replica_histograms(engine, args, L, netsimple, comm, world):
+    """Config 3's output: histograms over ALL replicas of the job of beacons per replica, bytes that left the local
+    network and the time of the first beacon (`itsb_histogram`: one privatised kernel per statistic, bins summed over
+    the ranks with ncclAllReduce when there is a communicator).  Returns (dict, milliseconds for the three)."""
+    if args.workload not in ("malware", "backdoor"):
+        return None, None
+    horizon_us = int((args.spinup + (2 * args.steps + args.warmup) * args.slice) * 1e6)
+    spec = {"beacons_per_replica": (L.tm_user(netsimple.STAT_BEACONS), 0, 8, 64, False),
+            "exfiltrated_bytes_per_replica": (L.tm_user(netsimple.STAT_EXFIL_BYTES), 0, 800, 64, False),
+            "first_beacon_us": (L.tm_user(netsimple.STAT_FIRST_BEACON_US), 0, max(1, horizon_us // 64), 64, True)}
+    out = {}
+    t0 = time.perf_counter()
+    for name, (slot, lo, width, nbins, nonzero) in spec.items():
+        bins = engine.histogram(slot, lo, width, nbins, only_nonzero=nonzero, comm=comm)
+        out[name] = {"lo": lo, "bin_width": width, "bins": [int(b) for b in bins]}
+    ms = 1e3 * (time.perf_counter() - t0)
+    assert sum(out["beacons_per_replica"]["bins"]) == args.replicas * world, "histogram does not cover every replica"
+    return out, ms
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -312,9 +332,11 @@ def main() -> None:
         gathered = [None] * world
         dist.all_gather_object(gathered, local.tolist())
         assert np.array_equal(total, np.sum(np.array(gathered, dtype=np.uint64), axis=0)), "allreduce mismatch"
+        hists, hist_ms = replica_histograms(engine, args, L, netsimple, comm, world)
         engine._lib.itsb_nccl_comm_destroy(comm)
     else:
         total = engine.telemetry()
+        hists, hist_ms = replica_histograms(engine, args, L, netsimple, None, 1)
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -349,6 +371,7 @@ def main() -> None:
                 "spinup_events": spin_events, "spinup_ms": spin_ms,
                 "telemetry_allreduce_ms": allreduce_ms,
                 "telemetry": {k: v for k, v in summarize(total).items() if k != "latency_hist"},
+                "replica_histograms": hists, "replica_histograms_ms": hist_ms,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 320, "d2h_bytes_per_step": 8 * L.TM_SIZE + 24,
                     "note": "per step: kernel arguments + ticket reset H2D; telemetry vector, event count and status D2H"},

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ITSB_ABI_VERSION 2
+#define ITSB_ABI_VERSION 3
 
 /* ---- engine errors (negative) ------------------------------------------------------------------------------ */
 #define ITSB_OK                    0
@@ -111,7 +111,10 @@ typedef struct itsb_connection {  /* 40 bytes: one connection record, the JSON `
                                                            network_event records, slot 21 the connection
                                                            records, when those logs are on                     */
 #define ITSB_TM_LAT0             23                     /* [23..86] transit-delay histogram, log2-spaced bins  */
-#define ITSB_TM_SIZE             (ITSB_TM_LAT0 + ITSB_LAT_BINS)
+#define ITSB_TM_USER8            (ITSB_TM_LAT0 + ITSB_LAT_BINS)   /* [87..90] model counters 8..11              */
+#define ITSB_TM_USER_SLOTS       12
+#define ITSB_TM_SIZE             (ITSB_TM_USER8 + 4)
+#define ITSB_TM_USER(s)          ((s) < 8 ? ITSB_TM_USER0 + (s) : ITSB_TM_USER8 + (s) - 8)
 
 /* ---- model description: flat struct-of-arrays tables produced by the host-side compiler ---------------------- */
 
@@ -279,6 +282,13 @@ int itsb_read_trace(itsb_engine* e, uint64_t replica, itsb_trace_rec* dst, size_
  * database.py:44-57).  dst receives up to cap records of one replica; n_total = records produced (may exceed the
  * capacity the model asked for: later ones are counted but not kept).                                               */
 int itsb_read_net_events(itsb_engine* e, uint64_t replica, itsb_net_event* dst, size_t cap, size_t* n_total);
+
+/* Histogram over the replicas of one telemetry slot (the per-replica statistics of BASELINE.json config 3: beacons
+ * per replica, bytes exfiltrated, time of the first beacon): dst[b] = number of replicas whose value v falls in bin
+ * b = min((v - lo) / width, nbins - 1), values below lo in bin 0; with `only_nonzero` replicas whose value is 0 are
+ * left out (a time that was never set).  comm (an ncclComm_t, may be NULL) sums the bins over the ranks first.  */
+int itsb_histogram(itsb_engine* e, uint32_t slot, uint64_t lo, uint64_t width, uint32_t nbins, int only_nonzero,
+                   void* comm, uint64_t* dst);
 
 /* The connection records of one replica, in the order `Socket.log_pair` was called
  * (network_simple_overrides.py:102-120,152-186).  *n_total = records produced (may exceed the capacity kept). */

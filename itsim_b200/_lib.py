@@ -14,10 +14,16 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libitsim_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 TM_KIND0, TM_PACKETS_SENT, TM_BYTES_SENT, TM_PACKETS_RECEIVED, TM_BYTES_RECEIVED = 0, 9, 10, 11, 12
 TM_DELIVERED, TM_DROPPED, TM_USER0, TM_LAT0, LAT_BINS = 13, 14, 15, 23, 64
-TM_SIZE = TM_LAT0 + LAT_BINS
+TM_USER8, TM_USER_SLOTS = TM_LAT0 + LAT_BINS, 12
+TM_SIZE = TM_USER8 + 4
+
+
+def tm_user(slot: int) -> int:
+    """Index of model counter ``slot`` in the telemetry vector (ITSB_TM_USER in include/itsb.h)."""
+    return TM_USER0 + slot if slot < 8 else TM_USER8 + slot - 8
 NUM_KINDS = 9
 EV_PROC_START, EV_TIMER, EV_TX_BEGIN, EV_TX_END, EV_DELIVER, EV_WAKE, EV_THROW, EV_STOP = range(1, 9)
 TRACE_MARK = 9
@@ -92,6 +98,8 @@ _SIGNATURES = {
     "itsb_read_now": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "itsb_read_trace": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "itsb_read_net_events": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "itsb_histogram": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p,
+                                 C.c_void_p]),
     "itsb_read_connections": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "itsb_read_telemetry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsb_read_replica_telemetry": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]),

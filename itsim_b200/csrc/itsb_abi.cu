@@ -368,6 +368,25 @@ int itsb_read_connections(itsb_engine* e, uint64_t replica, itsb_connection* dst
     return ITSB_OK;
 }
 
+/* histogram of one counter over the replicas: privatised in shared memory, then one atomic per bin and block */
+extern "C" __global__ void k_histogram(const unsigned char* hot, uint32_t hot_bytes, uint32_t off_stats, uint64_t n,
+                                       uint32_t slot, unsigned long long lo, unsigned long long width, uint32_t nbins,
+                                       int only_nonzero, unsigned long long* bins) {
+    extern __shared__ unsigned int local[];
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x) local[b] = 0;
+    __syncthreads();
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long v = ((const unsigned long long*)(hot + r * hot_bytes + off_stats))[slot];
+        if (only_nonzero && v == 0) continue;
+        unsigned long long b = v <= lo ? 0 : (v - lo) / width;
+        if (b >= nbins) b = nbins - 1;
+        atomicAdd(&local[(uint32_t)b], 1u);
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbins; b += blockDim.x)
+        if (local[b]) atomicAdd(&bins[b], (unsigned long long)local[b]);
+}
+
 static int reduce_telemetry(itsb_engine* e) {
     CU(e, cudaMemsetAsync(e->d_telemetry, 0, ITSB_TM_SIZE * sizeof(unsigned long long), e->stream));
     uint32_t blocks = (uint32_t)(e->n_replicas < 1024 ? e->n_replicas : 1024);
@@ -447,6 +466,35 @@ int itsb_allreduce_telemetry(itsb_engine* e, void* comm, uint64_t* dst, size_t n
     CU(e, cudaStreamSynchronize(e->stream));
     return ITSB_OK;
 }
+
+int itsb_histogram(itsb_engine* e, uint32_t slot, uint64_t lo, uint64_t width, uint32_t nbins, int only_nonzero,
+                   void* comm, uint64_t* dst) {
+    if (!e || !e->n_replicas || !dst || slot >= ITSB_TM_SIZE || width == 0 || nbins == 0 || nbins > 4096) return ITSB_ERR_STATE;
+    CU(e, cudaSetDevice(e->device));
+    unsigned long long* d_bins = nullptr;
+    CU(e, cudaMalloc(&d_bins, nbins * sizeof(unsigned long long)));
+    CU(e, cudaMemsetAsync(d_bins, 0, nbins * sizeof(unsigned long long), e->stream));
+    const uint32_t blocks = (uint32_t)((e->n_replicas + 255) / 256 < 592 ? (e->n_replicas + 255) / 256 : 592);
+    k_histogram<<<blocks, 256, nbins * sizeof(unsigned int), e->stream>>>(
+        e->d_hot, e->rp.layout.hot_bytes, e->rp.layout.off_stats, e->n_replicas, slot, lo, width, nbins, only_nonzero, d_bins);
+    e->launches += 1;
+    int rc = ITSB_OK;
+    if (comm) {
+        nccl_all_reduce_fn fn = (nccl_all_reduce_fn)nccl_sym("ncclAllReduce");
+        if (!fn) { cudaFree(d_bins); e->err = "libnccl.so.2 not found"; return ITSB_ERR_NCCL; }
+        if (fn(d_bins, d_bins, nbins, 5 /* ncclUint64 */, 0 /* ncclSum */, comm, e->stream) != 0) {
+            e->err = "ncclAllReduce failed"; rc = ITSB_ERR_NCCL;
+        }
+    }
+    if (rc == ITSB_OK) {
+        cudaError_t c1 = cudaMemcpyAsync(dst, d_bins, nbins * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream);
+        cudaError_t c2 = cudaStreamSynchronize(e->stream);
+        if (c1 != cudaSuccess || c2 != cudaSuccess) { e->err = "itsb_histogram: copy failed"; rc = ITSB_ERR_CUDA; }
+    }
+    cudaFree(d_bins);
+    return rc;
+}
+
 
 int itsb_replica_status(itsb_engine* e, uint64_t replica, int32_t* status, uint64_t* detail) {
     if (!e || replica >= e->n_replicas) return ITSB_ERR_STATE;

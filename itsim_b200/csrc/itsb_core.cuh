@@ -1356,7 +1356,7 @@ ITSB_COLD int exec_cold(Hdr* H, u32 p, u64 ins) {
         return XR_CONTINUE;
     }
     case OP_STAT:
-        stat_add(R, ITSB_TM_USER0 + (imm & 7), 1);
+        stat_add(R, ITSB_TM_USER(imm), 1);
         P.pc += 1;
         return XR_CONTINUE;
     default:
@@ -1801,6 +1801,14 @@ ITSB_COLD int exec_logged(Hdr* H, u32 p, u64 ins) {
         P.pc += 1;
         return XR_CONTINUE;
     }
+    case OP_STAT_ADD:
+        stat_add(R, ITSB_TM_USER(imm), src_val(R, P, a));
+        P.pc += 1;
+        return XR_CONTINUE;
+    case OP_STAT_FIRST:
+        if (R.stats[ITSB_TM_USER(imm)] == 0) R.stats[ITSB_TM_USER(imm)] = (u64)(H->now * 1.0e6);
+        P.pc += 1;
+        return XR_CONTINUE;
     case OP_CLOSE_LOG:    /* OP_CLOSE after flush_logs (overrides.py:366-367) */
         if (P.sock != NIL16 && H->conntab) conn_flush(H, P.sock, R.sock[P.sock].node);
         sock_close(H, p);

@@ -86,6 +86,9 @@ static inline bool validate_model(const itsb_model_desc& d, const void* const* b
         if (c.connection_records && (op == OP_RECV || op == OP_RECV_FILTER || op == OP_SEND || op == OP_FORWARD || op == OP_CLOSE)) {
             why = "connection records need programs assembled with the logged socket instructions (OP_*_LOG)"; return false;
         }
+        if ((op == OP_STAT || op == OP_STAT_ADD || op == OP_STAT_FIRST) && imm >= ITSB_TM_USER_SLOTS) {
+            why = "model counter out of range"; return false;
+        }
         if (op == OP_RECV_FILTER) {
             uint32_t a = (uint32_t)((code[i] >> 8) & 0xFF), b = (uint32_t)((code[i] >> 16) & 0xFF);
             if (a > 3 || b >= d.n_filters || (imm & 0xFFFF) >= d.n_code) { why = "RECV_FILTER operand out of range"; return false; }

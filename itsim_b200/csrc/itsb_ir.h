@@ -91,6 +91,8 @@ enum {
     OP_SEND_LOG = 63,   /* OP_SEND followed by correlate_outbound_packet                         overrides.py:122-125   */
     OP_FORWARD_LOG = 64,/* OP_FORWARD followed by the same on the sending attachment's socket                           */
     OP_CLOSE_LOG = 65,  /* flush_logs, then OP_CLOSE                                              overrides.py:366-367   */
+    OP_STAT_ADD = 66,   /* user counter imm += src(a)                                                              */
+    OP_STAT_FIRST = 67, /* user counter imm = now in microseconds, the first time only (a time-to-first statistic) */
     OP_COUNT
 };
 

@@ -114,6 +114,15 @@ class Engine:
         self.connections_total = total.value
         return out[:min(cap, total.value)]
 
+    def histogram(self, slot: int, lo: int, width: int, nbins: int, only_nonzero: bool = False,
+                  comm: Optional[C.c_void_p] = None) -> np.ndarray:
+        """Histogram over the replicas of telemetry slot ``slot`` (``_lib.tm_user(k)`` for model counter k); with a
+        communicator the bins are summed over the ranks (one ncclAllReduce of uint64 bins)."""
+        out = np.zeros(nbins, dtype=np.uint64)
+        self._check(self._lib.itsb_histogram(self._h, slot, lo, width, nbins, 1 if only_nonzero else 0, comm,
+                                             out.ctypes.data), "itsb_histogram")
+        return out
+
     def telemetry(self) -> np.ndarray:
         out = np.zeros(L.TM_SIZE, dtype=np.uint64)
         self._check(self._lib.itsb_read_telemetry(self._h, out.ctypes.data, L.TM_SIZE), "itsb_read_telemetry")
@@ -145,6 +154,6 @@ def summarize(tm: np.ndarray) -> Dict[str, Any]:
         "packets_sent": int(tm[L.TM_PACKETS_SENT]), "bytes_sent": int(tm[L.TM_BYTES_SENT]),
         "packets_received": int(tm[L.TM_PACKETS_RECEIVED]), "bytes_received": int(tm[L.TM_BYTES_RECEIVED]),
         "delivered": int(tm[L.TM_DELIVERED]), "dropped": int(tm[L.TM_DROPPED]),
-        "user": [int(v) for v in tm[L.TM_USER0:L.TM_USER0 + 8]],
+        "user": [int(tm[L.tm_user(k)]) for k in range(L.TM_USER_SLOTS)],
         "latency_hist": [int(v) for v in tm[L.TM_LAT0:L.TM_LAT0 + L.LAT_BINS]],
     }

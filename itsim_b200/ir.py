@@ -17,7 +17,7 @@ import numpy as np
  OP_BIND, OP_SCLOSE, OP_SENDL, OP_RECVT, OP_ADVANCE_X, OP_THREAD_EXIT, OP_CLONE, OP_FORK, OP_JOIN, OP_PWAIT, OP_TKILL,
  OP_PKILL, OP_MARK, OP_SIG_WAIT, OP_SIG_ON, OP_GSET, OP_NOW_SUB, OP_ADVANCE_X2, OP_TLOAD, OP_TSTORE, OP_ADD, OP_SUB,
  OP_JLTU, OP_XNOW, OP_XSET, OP_XELAPSE, OP_JXLE0, OP_RECVT_X, OP_SETADDR, OP_GETADDR, OP_FORWARD, OP_GETPORT,
- OP_RECV_LOG, OP_OPEN_AT, OP_SEND_LOG, OP_FORWARD_LOG, OP_CLOSE_LOG) = range(66)
+ OP_RECV_LOG, OP_OPEN_AT, OP_SEND_LOG, OP_FORWARD_LOG, OP_CLOSE_LOG, OP_STAT_ADD, OP_STAT_FIRST) = range(68)
 
 PROG_HIDDEN_BALK, PROG_HIDDEN_WAIT_ONE = 0xF1, 0xF2
 
@@ -241,6 +241,12 @@ class Asm:
     def list_push(self) -> None: self._emit(OP_LIST_PUSH)
     def list_take(self, key_src: int, not_found: Target) -> None: self._emit(OP_LIST_TAKE, key_src, imm=self._t(not_found))
     def stat(self, counter: int) -> None: self._emit(OP_STAT, imm=counter)
+    def stat_add(self, counter: int, src: int) -> None: self._emit(OP_STAT_ADD, src, imm=counter)
+
+    def stat_first(self, counter: int) -> None:
+        """counter = now() in microseconds, the first time this runs in a replica (never 0: a replica where it
+        never ran keeps 0)."""
+        self._emit(OP_STAT_FIRST, imm=counter)
 
     # -- output ----------------------------------------------------------------------------------------------
     def _resolve(self, v: object) -> int:

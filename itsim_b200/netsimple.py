@@ -29,6 +29,7 @@ TAG_EXFIL = 8
 EXC_COMPLETE = 1          # Workstation._Complete (network_simple.py:78-79): a plain Exception, not an Interrupt
 STAT_QUERIES, STAT_RESOLVED, STAT_TIMEOUTS = 0, 1, 2
 STAT_BEACONS, STAT_ROUTED, STAT_C2_RECEIVED = 3, 4, 5
+STAT_FIRST_BEACON_US, STAT_EXFIL_BYTES = 8, 9      # slots 6 and 7 count the connection / network_event records
 
 BAD_NEWS_BEAR_ADDR = (1 << 24) | (2 << 16) | (3 << 8) | 4     # malware_simple.py:16-18
 BAD_NEWS_BEAR_PORT = 666
@@ -278,6 +279,7 @@ def build_malware(trace_records: int = 0, fused: bool = True, connection_records
 
     a.program("exfiltrate", PROG_EXFILTRATE)                      # :75-82
     a.stat(STAT_BEACONS)
+    a.stat_first(STAT_FIRST_BEACON_US)                            # time to the first beacon (a config-3 statistic)
     if c2_targets:                                                # backdoor.py:36 next(location_c2)
         a.drawi(R0, sim.dist(distribution_index(len(targets))))
         for k in range(1, len(targets)):
@@ -308,6 +310,7 @@ def build_malware(trace_records: int = 0, fused: bool = True, connection_records
     a.label("loop")
     a.recv()
     a.stat(STAT_ROUTED)
+    a.stat_add(STAT_EXFIL_BYTES, PKT_SIZE)                        # bytes that left the local network
     a.mov(R2, _PKT_F0)
     a.mov(R3, _PKT_F1)
     a.forward(router_wan, LOCAL_ROUTER_PORT)

@@ -625,7 +625,7 @@ class MalwareModel(Model):
         self.beacon_gap, self.privileged_gap, self.beacon_size = beacon_gap, privileged_gap, beacon_size
         self.c2_targets = c2_targets or [(self.BAD_NEWS_BEAR_ADDR, self.BAD_NEWS_BEAR_PORT)]
         self.location_c2 = distribution(self.c2_targets) if c2_targets else None
-        self.stats.update({"beacons": 0, "routed": 0, "c2_received": 0})
+        self.stats.update({"beacons": 0, "routed": 0, "c2_received": 0, "first_beacon_us": 0, "exfil_bytes": 0})
         gsrandom.set_default_rng(self.rng)
         try:
             self.www = Network(self, "0.0.0.0/0", latency=bounded(expo(1 * S), lower=20 * MS),
@@ -674,6 +674,8 @@ class MalwareModel(Model):
     def exfiltrate(self, ws: Node) -> None:
         """malware_simple.py:75-82."""
         self.stats["beacons"] += 1
+        if self.stats["first_beacon_us"] == 0:
+            self.stats["first_beacon_us"] = int(now() * 1.0e6)
         target = next(self.location_c2) if self.location_c2 is not None else self.c2_targets[0]   # backdoor.py:36
         size = next(self.beacon_size) if self.beacon_size is not None else 100                      # backdoor.py:37
         with ws.open_socket(self.BAD_NEWS_BEAR_PORT) as socket:
@@ -687,6 +689,7 @@ class MalwareModel(Model):
                 while True:
                     msg = i_socket.recv()
                     self.stats["routed"] += 1
+                    self.stats["exfil_bytes"] += msg.byte_size
                     world_socket.send(msg.payload["dest_addr"], msg.byte_size, msg.payload)
 
     @tagged(Tag.MALWARE)

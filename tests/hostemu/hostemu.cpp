@@ -163,6 +163,19 @@ int itsb_read_net_events(itsb_engine* e, uint64_t replica, itsb_net_event* dst, 
     return ITSB_OK;
 }
 
+int itsb_histogram(itsb_engine* e, uint32_t slot, uint64_t lo, uint64_t width, uint32_t nbins, int only_nonzero,
+                   void* comm, uint64_t* dst) {
+    if (!e->n_replicas || !dst || slot >= ITSB_TM_SIZE || width == 0 || nbins == 0 || nbins > 4096 || comm) return ITSB_ERR_STATE;
+    for (uint32_t b = 0; b < nbins; ++b) dst[b] = 0;
+    for (uint64_t r = 0; r < e->n_replicas; ++r) {
+        const uint64_t v = ((const uint64_t*)(e->hot.data() + r * e->layout.hot_bytes + e->layout.off_stats))[slot];
+        if (only_nonzero && v == 0) continue;
+        uint64_t b = v <= lo ? 0 : (v - lo) / width;
+        dst[b >= nbins ? nbins - 1 : b] += 1;
+    }
+    return ITSB_OK;
+}
+
 int itsb_read_connections(itsb_engine* e, uint64_t replica, itsb_connection* dst, size_t cap, size_t* n_total) {
     if (replica >= e->n_replicas) return ITSB_ERR_STATE;
     Hdr* H = (Hdr*)(e->hot.data() + replica * e->layout.hot_bytes);
