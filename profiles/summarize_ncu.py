@@ -39,7 +39,8 @@ def main():
     lib = sys.argv[2] if len(sys.argv) > 2 else None
     raw = ncu_csv(rep, "raw")
     head, units, vals = raw[0], raw[1], raw[2]
-    print(f"# ncu summary of {os.path.basename(rep)} (kernel {vals[head.index('Kernel Name')]})")
+    kernel = vals[head.index('Kernel Name')].split("(")[0]
+    print(f"# ncu summary of {os.path.basename(rep)} (kernel {kernel})")
     print("\n## raw metrics")
     for name in RAW_METRICS:
         if name in head:
@@ -81,7 +82,8 @@ def main():
                     fn = m.group(1)
                 elif re.match(r"^ +/\*[0-9a-f]+\*/", line):
                     cand.append(fn)
-            cand = [f for f in cand if f == ".text.k_run" or f.startswith("$k_run$") or f.startswith("$__internal")]
+            cand = [f for f in cand if f == ".text." + kernel or f.startswith("$" + kernel + "$")
+                    or f.startswith("$__internal")]
             if len(cand) == len(data):
                 seq = cand
         if len(seq) == len(data):
