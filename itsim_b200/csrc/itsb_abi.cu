@@ -27,6 +27,7 @@
 
 extern "C" __global__ void k_run_in_place(const RunParams p);   /* itsb_inplace.cu */
 extern "C" __global__ void k_run_wide(const RunParams p);       /* itsb_wide.cu: 13..16 warps per CTA */
+extern "C" __global__ void k_run_phased(const RunParams p);     /* itsb_phased.cu: warps aligned on the loop's two halves */
 
 /* up to 12 warps per CTA (what shared memory allows the flagship model): 168 registers per thread, no spills */
 extern "C" __global__ void __launch_bounds__(384, 1) k_run(const RunParams p) {
@@ -106,6 +107,7 @@ struct itsb_engine {
     uint32_t warps_per_cta = 0, grid = 0;
     size_t smem_bytes = 0;
     bool run_pending = false;
+    bool phased = false;                          /* ITSB_PHASED=1: k_run_phased instead of k_run (A/B switch) */
     float last_ms = 0.f;
     long long first_failed = -1;
     std::string err;
@@ -213,9 +215,11 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     }
     e->warps_per_cta = w;
     e->rp.warps_per_cta = w;
+    { const char* ph = getenv("ITSB_PHASED"); e->phased = ph && ph[0] == '1'; }
     e->grid = (uint32_t)e->prop.multiProcessorCount;
     CU(e, cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     CU(e, cudaFuncSetAttribute(k_run_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CU(e, cudaFuncSetAttribute(k_run_phased, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     CU(e, cudaFuncSetAttribute(k_run_in_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     e->loaded = true;
     return ITSB_OK;
@@ -279,6 +283,7 @@ int itsb_run_async(itsb_engine* e, double duration) {
     if (!e->run_pending) CU(e, cudaEventRecord(e->ev_start, e->stream));
     if (e->rp.state_in_hbm) k_run_in_place<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
     else if (e->warps_per_cta > 12) k_run_wide<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
+    else if (e->phased) k_run_phased<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
     else k_run<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
     CU(e, cudaGetLastError());
     CU(e, cudaEventRecord(e->ev_stop, e->stream));

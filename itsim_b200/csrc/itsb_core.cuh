@@ -1587,6 +1587,84 @@ ITSB_FN u64 run_replica(Rep& R, double duration) {
     return events_counted(R) - events_before;
 }
 
+/* ---- the same loop, cut in two for the phase-aligned kernel (itsb_phased.cu) ------------------------------------------
+ * run_replica == run_begin; while (run_pop(runnable)) if (runnable) run_process(runnable); run_events.  The phased kernel
+ * lets every warp of the CTA do its pop (+ network work) first and its process activation second, with a CTA barrier
+ * in between, so that warps of one SM execute the same half of the code at the same time. */
+struct RunCtx { double t_stop; u64 t_stop_bits; u64 events_before; u32 stop_seq; bool finite; bool active; };
+
+ITSB_FN void run_begin(Rep& R, double duration, RunCtx& C) {
+    Hdr* H = R.hdr;
+    C.events_before = 0;
+    C.active = H->status == 0;
+    if (!C.active) return;
+    if (!H->setup_done) replica_setup(H);
+    C.events_before = events_counted(R);
+    C.t_stop = H->now + duration;
+    C.t_stop_bits = dbits(C.t_stop);
+    C.finite = C.t_stop_bits < T_EMPTY;
+    C.stop_seq = C.finite ? H->seq : NIL32;
+    if (C.finite) H->seq += 1;
+}
+
+/* One pop.  Returns false when this run() is over.  Network events (TX_BEGIN, TX_END, the delivery pass) are handled
+ * here; a process to activate is handed back in `runnable` (NIL32: none). */
+ITSB_FN bool run_pop(Rep& R, const RunCtx& C, u32& runnable) {
+    Hdr* H = R.hdr;
+    runnable = NIL32;
+    if (!C.active || H->status != 0) return false;
+    u64 tb; u32 seq;
+    const int src = ev_peek(R, tb, seq);
+    if (src == SRC_NONE_LEFT && !C.finite) return false;
+    if (src == SRC_NONE_LEFT || tb > C.t_stop_bits || (tb == C.t_stop_bits && seq > C.stop_seq)) {
+        H->now = C.t_stop;
+        count_event(R, ITSB_EV_STOP, 0, 0, 0);
+        return false;
+    }
+    const u32 data = ev_take(R, src);
+    H->now = bitsd(tb);
+    const u32 kind = ev_kind(data), idx = ev_idx(data);
+    u32 deliver = NIL32;
+    if (kind == ITSB_EV_DELIVER) {
+        deliver = ev_pkt(data);
+    } else if (kind == ITSB_EV_WAKE || kind == ITSB_EV_TIMER || kind == ITSB_EV_PROC_START) {
+        Pcb& P = R.pcb[idx];
+        bool live = P.state != PS_FREE && P.gen == ev_gen(data);
+        if (live) {
+            if (kind == ITSB_EV_TIMER) {
+                live = P.state == PS_TIMER && (u32)(P.timer_tok & 0xFF) == ev_exc(data);
+                if (live) { P.timer_ev = NIL16; P.pc += 1; }
+            } else if (kind == ITSB_EV_WAKE) {
+                live = P.state == PS_RESUMING;
+            } else {
+                live = P.state == PS_UNSTARTED;
+            }
+        }
+        if (live) {
+            if (!is_hidden_prog(P.prog)) count_event(R, kind, P.prog, P.node, 0);
+            runnable = idx;
+        }
+    } else if (kind == ITSB_EV_TX_BEGIN) {
+        on_tx_begin(H, ev_pkt(data));
+    } else if (kind == ITSB_EV_TX_END) {
+        if (on_tx_end(H, ev_pkt(data))) deliver = ev_pkt(data);
+    } else if (kind == ITSB_EV_THROW) {
+        Pcb& P = R.pcb[idx];
+        if (P.state != PS_FREE && P.gen == ev_gen(data)) {
+            if (!is_hidden_prog(P.prog) && !(ev_exc(data) & EXC_HIDDEN))
+                count_event(R, ITSB_EV_THROW, P.prog, P.node, ev_exc(data));
+            if (P.state == PS_UNSTARTED) proc_exit(H, idx);
+            else runnable = deliver_exception(H, idx, ev_exc(data));
+        }
+    } else {
+        fail(H, ITSB_ERR_BAD_OPCODE, data);
+    }
+    if (deliver != NIL32) on_deliver(R, deliver);
+    return true;
+}
+
+ITSB_FN u64 run_events(Rep& R, const RunCtx& C) { return C.active ? events_counted(R) - C.events_before : 0; }
+
 /* ---- connection records (overrides.py:102-120,152-186) ------------------------------------------------------------------
  * The override-path Socket files every packet it sends under its destination Location and every packet it receives
  * under its source Location, and logs a record when the two halves of a pair meet, when an unanswered outbound
