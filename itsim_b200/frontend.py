@@ -124,11 +124,13 @@ class Frontend:
         self.program_ids: Dict[str, int] = {}        # function name -> program id (what the trace reports); optional
         self.effects: List[Effect] = []
         self.content_tags: Dict[Any, int] = {}
+        self.payload_fields: Dict[Any, int] = {}     # payload key -> packet field 0 / 1
         self._programs: Dict[tuple, Tuple[str, int]] = {}
         self._queue: List[Tuple[str, Callable, tuple, int]] = []
         self._gslots: Dict[Tuple[int, Any], int] = {}
         self._keepalive: List[Any] = []
         self._next_prog = 1
+        self._gtemps = 0
         self.single_interface_programs: set = set()     # programs that use the "every non-loopback interface" idiom
 
     # -- public ----------------------------------------------------------------------------------------------------
@@ -154,6 +156,15 @@ class Frontend:
             if self.content_tags[content] > 255:
                 raise CompileError("more than 255 distinct payload contents")
         return self.content_tags[content]
+
+    def payload_field(self, key: Any, body: Any, node: ast.AST) -> int:
+        """Which of a packet's two 32-bit fields carries payload key ``key`` (assigned on first use, model-wide)."""
+        if key not in self.payload_fields:
+            if len(self.payload_fields) >= 2:
+                raise body.err(node, f"payload keys {sorted(map(str, list(self.payload_fields) + [key]))} are not carried "
+                                     f"by the engine's packets (a packet carries 'content' and two 32-bit fields)")
+            self.payload_fields[key] = len(self.payload_fields)
+        return self.payload_fields[key]
 
     def replay(self, trace: Any) -> int:
         """Re-executes the host-side statements of the bodies in the order (and at the simulated times) the replica
@@ -210,10 +221,16 @@ class Frontend:
             name, f, args, prog_id = self._queue.pop(0)
             _Body(self, name, f, args, prog_id).compile()
 
+    def gtemp(self, i: int) -> int:
+        self._gtemps = max(self._gtemps, i + 1)
+        if len(self._gslots) + self._gtemps > 8:
+            raise CompileError("more than 8 simulation values shared between bodies")
+        return 7 - i
+
     def gslot(self, container: Any, key: Any) -> int:
         k = (id(container), key)
         if k not in self._gslots:
-            if len(self._gslots) >= 8:
+            if len(self._gslots) + self._gtemps >= 8:
                 raise CompileError("more than 8 simulation values shared between bodies")
             self._gslots[k] = len(self._gslots)
             self._keepalive.append(container)
@@ -911,16 +928,34 @@ class _Body:
         payload_node = args[2] if len(args) > 2 else kw.get("payload")
         if dest_node is None or size_node is None:
             raise self.err(call, "socket.send(destination, size[, payload])")
-        tag = 0
+        tag, fields = 0, {}
         if payload_node is not None:
-            p = self.eval(payload_node, scope)
-            if not isinstance(p, Const) or not (p.v is None or isinstance(p.v, dict)):
-                raise self.err(call, "a payload is a compile-time dict")
-            if p.v:
-                extra = set(p.v) - {"content"}
-                if extra:
-                    raise self.err(call, f"payload keys {sorted(extra)} are not carried by the engine's packets")
-                tag = self.fe.tag_of(p.v["content"])
+            if isinstance(payload_node, ast.Dict):
+                items = {}
+                for k, v in zip(payload_node.keys, payload_node.values):
+                    kv = self.eval(k, scope) if k is not None else None
+                    if not isinstance(kv, Const):
+                        raise self.err(call, "payload keys are compile-time values")
+                    items[kv.v] = self.eval(v, scope)
+            else:
+                p = self.eval(payload_node, scope)
+                if not isinstance(p, Const) or not (p.v is None or isinstance(p.v, dict)):
+                    raise self.err(call, "a payload is a dict")
+                items = {k: Const(v) for k, v in (p.v or {}).items()}
+            for key, v in items.items():
+                if key == "content":
+                    if not isinstance(v, Const):
+                        raise self.err(call, "payload['content'] is a compile-time value")
+                    tag = self.fe.tag_of(v.v)
+                    continue
+                if not isinstance(v, (Const, Rt)) or (isinstance(v, Const) and not isinstance(v.v, (int, str, IPv4Address))):
+                    raise self.err(call, f"payload keys {[key]} are not carried by the engine's packets (a packet "
+                                         f"carries 'content' and two 32-bit fields)")
+                fields[self.fe.payload_field(key, self, call)] = v
+        fsrc = dict(fields)
+        f0 = self.field_src(call, fsrc.get(0))
+        f1 = self.field_src(call, fsrc.get(1), avoid=[f0])
+        fkw = dict(f0=f0, f1=f1)
         if isinstance(dest_node, ast.Tuple) and len(dest_node.elts) == 2:
             addr, port = self.eval(dest_node.elts[0], scope), self.eval(dest_node.elts[1], scope)
             if not isinstance(port, Const):
@@ -928,25 +963,42 @@ class _Body:
             size = self.eval(size_node, scope)
             if isinstance(addr, _Sym) and addr.what == "broadcast_address":
                 self.fe.single_interface_programs.add(self.name)
-                return self.a.sendl(ir.DST_BCAST, self.src_of(size_node, size), tag, port=int(port.v))
+                return self.a.sendl(ir.DST_BCAST, self.src_of(size_node, size, avoid=[f0, f1]), tag, port=int(port.v), **fkw)
             if isinstance(addr, Rt):
                 self.scratch_used.update(r for r in (2, 3) if r != addr.src)
                 if addr.src != ir.R2:
                     self.a.mov(ir.R2, addr.src)
                 self.a.li(ir.R3, int(port.v))
-                return self.a.sendl(ir.DST_REGS, self.src_of(size_node, size, avoid=[2, 3]), tag)
+                return self.a.sendl(ir.DST_REGS, self.src_of(size_node, size, avoid=[2, 3, f0, f1]), tag, **fkw)
         dest = self.eval(dest_node, scope)
         size = self.eval(size_node, scope)
         if isinstance(dest, _Sym) and dest.what == "packet_source":
             self.need_current(dest_node, dest)
-            return self.a.sendl(ir.DST_PKT_SRC, self.src_of(size_node, size), tag)
+            return self.a.sendl(ir.DST_PKT_SRC, self.src_of(size_node, size, avoid=[f0, f1]), tag, **fkw)
         if isinstance(dest, Const) and isinstance(dest.v, tuple) and len(dest.v) == 2:
             addr, port = dest.v
             self.scratch_used.update((2, 3))
             self.a.li(ir.R2, self.as_u32(dest_node, addr))
             self.a.li(ir.R3, int(port))
-            return self.a.sendl(ir.DST_REGS, self.src_of(size_node, size, avoid=[2, 3]), tag)
+            return self.a.sendl(ir.DST_REGS, self.src_of(size_node, size, avoid=[2, 3, f0, f1]), tag, **fkw)
         raise self.err(call, "destination must be packet.source or a compile-time (address, port)")
+
+    def field_src(self, node: ast.AST, v: Any, avoid: Sequence[int] = ()) -> int:
+        """Operand source of a payload field (NONE: the packet does not carry it -> 0)."""
+        if v is None:
+            return ir.NONE
+        if isinstance(v, Rt):
+            return v.src
+        val = self.as_u32(node, v.v)
+        if val == 0:
+            return ir.ZERO
+        # a constant field is parked in a model variable reserved for this (g7 / g6): the registers stay free for the
+        # destination and the size; nothing can run between the store and the send
+        slot = self.fe.gtemp(0 if not any(a == ir.G7 for a in avoid) else 1)
+        r = self.scratch(node)
+        self.a.li(r, val)
+        self.a.gset(slot, r)
+        return ir.G0 + slot
 
     def need_current(self, node: ast.AST, sym: _Sym) -> None:
         if sym.gen != self.packet_gen:
@@ -1009,7 +1061,9 @@ class _Body:
                 self.need_current(e, base)
                 if isinstance(key, Const) and key.v == "content":
                     return Rt(ir.PKT_TAG, "content")
-                raise self.err(e, "only payload['content'] is carried by the engine's packets")
+                if isinstance(key, Const):
+                    return Rt(ir.PKT_F0 if self.fe.payload_field(key.v, self, e) == 0 else ir.PKT_F1, "int")
+                raise self.err(e, "payload keys are compile-time values")
             if isinstance(base, Const) and isinstance(key, Const):
                 return self.wrap(base.v[key.v])
             raise self.err(e, "subscript on a simulation value")
@@ -1149,7 +1203,9 @@ class _Body:
                 key = self.eval(e.args[0], scope)
                 if isinstance(key, Const) and key.v == "content":
                     return Rt(ir.PKT_TAG, "content")
-                raise self.err(e, "only payload.get('content') is carried by the engine's packets")
+                if isinstance(key, Const):
+                    return Rt(ir.PKT_F0 if self.fe.payload_field(key.v, self, e) == 0 else ir.PKT_F1, "int")
+                raise self.err(e, "payload keys are compile-time values")
             if what == "socket" and fv.attr == "recv":
                 return self.sim_call(e, fv, scope, want_result=True)
             raise self.err(e, f"{what}.{fv.attr}(...) cannot be used as a value here")

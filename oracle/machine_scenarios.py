@@ -371,6 +371,65 @@ def large_lan(seed: int = 0, replica: int = 0, duration: float = 8.0, subnets: i
     return sc.result()
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# the front-end's test bodies (tests/frontend_bodies.py), run on the reference's itsim: the SAME source file that the
+# engine's front-end compiles is executed here as ordinary Python coroutines on the reference's classes
+# --------------------------------------------------------------------------------------------------------------------
+FRONTEND_PROGS = {
+    "ping_pong": {"pinger": 1, "ponger": 2},
+    "chatter": {"listen": 1, "shout": 2},
+    "threads": {"root": 1, "observer": 2, "first": 3, "second": 4, "sleeper": 5, "leaf": 6},
+    "family": {"ancestors": 1, "life": 2},
+    "lan": {"lan_server": 1, "lan_client": 2},
+    "echo": {"answerer": 1, "asker": 2},
+}
+
+
+def frontend_scenario(name: str, seed: int = 0, replica: int = 0, duration=10.0):
+    """Returns (trace, summary); summary["state"] holds the host-side containers the bodies filled."""
+    from itsim.network.router import Router
+    path = os.path.join(os.path.dirname(_HERE), "tests", "frontend_bodies.py")
+    spec = importlib.util.spec_from_file_location("frontend_bodies_on_reference", path)
+    B = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(B)
+
+    class ForwardingRouter(Router):
+        def handle_packet_transit(self, packet):
+            interface, hop = self._solve_transfer(packet.dest.hostname_as_address())
+            interface.link._transfer_packet(packet, hop)
+
+    sc = Scenario(FRONTEND_PROGS[name], seed, replica)
+    state: Dict[str, Any] = {}
+    if name == "ping_pong":
+        nodes = B.build_ping_pong(sc.sim)
+        state = {"seen": lambda: sorted(B.seen), "clock_at_timeout": lambda: list(B.clock_at_timeout)}
+    elif name == "chatter":
+        nodes = B.build_chatter(sc.sim)
+        state = {"heard_from": lambda: [sorted(int(a) for a in n.heard_from) for n in nodes]}
+    elif name == "threads":
+        log = []
+        nodes = B.build_threads(sc.sim, log)
+        state = {"log": lambda: list(log)}
+    elif name == "family":
+        graves = set()
+        nodes = B.build_family(sc.sim, graves)
+        state = {"graves": lambda: sorted(graves)}
+    elif name == "lan":
+        nodes = B.build_lan(sc.sim, 4, 16, lambda v: v, ForwardingRouter)
+    elif name == "echo":
+        nodes = B.build_echo(sc.sim)
+        state = {"echoed": lambda: list(B.echoed), "unanswered": lambda: list(B.unanswered)}
+    else:
+        raise KeyError(name)
+    for n in nodes:
+        sc.node(n)
+    sc.run(duration)
+    final = {k: f() for k, f in state.items()}      # before result(): clearing the simulator runs the bodies' finally blocks
+    arr, out = sc.result()
+    out["state"] = final
+    return arr, out
+
+
 SCENARIOS: Dict[str, Callable] = {
     "packet_transfer": packet_transfer, "broadcast": broadcast, "thread_lifecycle": thread_lifecycle,
     "process_lifecycle": process_lifecycle, "dhcp_exchange": dhcp_exchange, "large_lan": large_lan,

@@ -13,6 +13,7 @@ vectors are the oracle's own output under the injected Philox stream:
 
 Usage: python oracle/make_golden.py [--full]     (--full adds the 43 200 s = 12 h horizon of config C1: ~7 min)
        python oracle/make_golden.py --machine
+       python oracle/make_golden.py --frontend   (tests/frontend_bodies.py run on the reference's itsim)
 """
 import json
 import os
@@ -62,6 +63,23 @@ def machine_golden() -> None:
     json.dump(out, open(os.path.join(GOLDEN, "machine_summaries.json"), "w"), indent=1, sort_keys=True)
 
 
+def frontend_golden() -> None:
+    """tests/frontend_bodies.py executed on the reference's itsim (needs /root/reference): what the engine must
+    reproduce when the front-end compiles the same file."""
+    import machine_scenarios as ms
+    out = {}
+    jobs = [("ping_pong", 0, 0, 10.0), ("ping_pong", 9, 4, 10.0), ("chatter", 1, 5, 30.0), ("threads", 0, 0, None),
+            ("family", 0, 0, 4000.0), ("lan", 2, 3, 15.0), ("echo", 0, 0, 10.0), ("echo", 6, 21, 10.0)]
+    for name, seed, replica, duration in jobs:
+        arr, summary = ms.frontend_scenario(name, seed, replica, duration)
+        tag = f"{name}_s{seed}_r{replica}"
+        np.savez_compressed(os.path.join(GOLDEN, f"frontend_{tag}.npz"), trace=arr)
+        out[tag] = {"events": summary["events"], "now": summary["now"], "draws": summary["draws"],
+                    "state": summary["state"], "duration": duration}
+        print("frontend", tag, summary["events"], summary["state"] if name != "chatter" else "", flush=True)
+    json.dump(out, open(os.path.join(GOLDEN, "frontend_summaries.json"), "w"), indent=1, sort_keys=True)
+
+
 def malware_golden() -> None:
     """network_simple + malware overlay (config C3): one full trace and two 1 h summaries."""
     out = {}
@@ -82,6 +100,9 @@ def main() -> None:
     os.makedirs(GOLDEN, exist_ok=True)
     if "--machine" in sys.argv:
         machine_golden()
+        return
+    if "--frontend" in sys.argv:
+        frontend_golden()
         return
     if "--malware" in sys.argv:
         malware_golden()

@@ -52,9 +52,13 @@ def raise_failure(why):
 
 
 def build_ping_pong(sim):
+    """Every builder returns its nodes in creation order (the order the traces number them in)."""
     link = Link("10.11.12.0/24", latency=uniform(100 * MS, 200 * MS), bandwidth=constant(100 * MbPS))
-    Endpoint().connected_to_static(link, "10.11.12.10").run_proc_in(sim, 0.1, pinger)
-    Endpoint().connected_to_static(link, "10.11.12.20").run_proc(sim, ponger)
+    a = Endpoint().connected_to_static(link, "10.11.12.10")
+    a.run_proc_in(sim, 0.1, pinger)
+    b = Endpoint().connected_to_static(link, "10.11.12.20")
+    b.run_proc(sim, ponger)
+    return [a, b]
 
 
 # ---- twenty endpoints broadcasting (golden: machine_broadcast_*.npz) -------------------------------------------------
@@ -87,6 +91,14 @@ class Chatterbox(Endpoint):
 def build_chatter(sim, hosts=range(100, 120)):
     link = Link("10.11.0.0/16", uniform(100 * MS, 200 * MS), constant(100 * MbPS))
     return [Chatterbox(sim).connected_to_static(link, as_address(n, link.cidr)) for n in hosts]
+
+
+def build_threads(sim, log):
+    return [Endpoint().with_proc_in(sim, 0, root, log)]
+
+
+def build_family(sim, graves):
+    return [Endpoint().with_proc(sim, ancestors, graves)]
 
 
 # ---- threads of one process (golden: machine_thread_lifecycle.npz) ---------------------------------------------------
@@ -203,20 +215,72 @@ def lan_client(context, peer):
             sock.send((peer, LAN_PORT), 64, {"content": "request"})
 
 
-def build_lan(sim, subnets, per_subnet, per_process):
+def build_lan(sim, subnets, per_subnet, per_process, make_router):
     from greensim.random import normal
     from itsim.network.route import Relay
-    from itsim.network.router import Router
     from itsim.units import GbPS
     backbone = Link("10.30.0.0/24", normal(5 * MS, 1 * MS), constant(1 * GbPS))
     access = [Link(f"10.20.{i}.0/25", normal(5 * MS, 1 * MS), constant(1 * GbPS)) for i in range(subnets)]
+    nodes = []
     for i in range(subnets):
-        router = Router(forwarding=True)
+        router = make_router()
+        nodes.append(router)
         router.connected_to_static(access[i], 1)
         router.connected_to_static(backbone, i + 1, [Relay(as_address(j + 1, backbone.cidr), f"10.20.{j}.0/25")
                                                     for j in range(subnets) if j != i])
     for i in range(subnets):
         for h in range(per_subnet):
             ep = Endpoint().connected_to_static(access[i], h + 2, [Relay(as_address(1, access[i].cidr))])
+            nodes.append(ep)
             ep.run_proc(sim, lan_server)
             ep.run_proc(sim, lan_client, per_process(as_address(h + 2, access[(i + 1) % subnets].cidr)))
+    return nodes
+
+
+# ---- a request / response protocol with fields in the payload (golden: frontend_echo_*.npz, made by running THIS file
+# ---- on the reference's itsim: oracle/machine_scenarios.frontend_scenario) ----------------------------------------------
+ECHO_PORT = 4000
+echoed = []
+unanswered = []
+
+
+def asker(context, first_id):
+    with context.node.bind(Protocol.UDP) as sock:
+        for k in range(3):
+            advance(next(ask_gap))
+            sock.send(("10.5.0.2", ECHO_PORT), 40, {"content": "question", "id": first_id + k, "weight": 5 * k})
+            try:
+                reply = sock.recv(0.25 * S)
+            except Timeout:
+                unanswered.append(first_id + k)
+                continue
+            assert reply.payload["content"] == "answer"
+            if reply.payload["id"] != first_id + k:
+                unanswered.append(-1)
+            echoed.append(reply.payload["weight"])
+
+
+def answerer(context):
+    with context.node.bind(Protocol.UDP, ECHO_PORT) as sock:
+        while True:
+            q = sock.recv()
+            if q.payload["content"] != "question":
+                continue
+            if q.payload["weight"] >= 10:
+                continue                      # the third question of every asker goes unanswered
+            sock.send(q.source, 24, {"content": "answer", "id": q.payload["id"], "weight": q.payload["weight"]})
+
+
+ask_gap = uniform(0.5 * S, 1.5 * S)
+
+
+def build_echo(sim):
+    link = Link("10.5.0.0/24", latency=uniform(10 * MS, 60 * MS), bandwidth=constant(10 * MbPS))
+    server = Endpoint().connected_to_static(link, "10.5.0.2")
+    server.run_proc(sim, answerer)
+    nodes = [server]
+    for n in range(3):
+        ep = Endpoint().connected_to_static(link, as_address(10 + n, link.cidr))
+        ep.run_proc_in(sim, 0.05 * n, asker, 100 * (n + 1))
+        nodes.append(ep)
+    return nodes

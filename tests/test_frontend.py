@@ -68,7 +68,7 @@ def scenario(name, lib, seed=0, replica=0):
         sim.seed, sim.replica = seed, replica
         if name == "packet_transfer":
             sim.frontend.program_ids.update(pinger=1, ponger=2)
-            B.build_ping_pong(sim)
+            B.nodes = B.build_ping_pong(sim)
             marks = {"seen.add('pinger')": 1, "seen.add('ponger')": 2}
         elif name == "broadcast":
             sim.frontend.program_ids.update(listen=1, shout=2)
@@ -77,20 +77,24 @@ def scenario(name, lib, seed=0, replica=0):
         elif name == "thread_lifecycle":
             sim.frontend.program_ids.update(root=1, observer=2, first=3, second=4, sleeper=5, leaf=6)
             B.log = []
-            B.Endpoint().with_proc_in(sim, 0, B.root, B.log)
+            B.build_threads(sim, B.log)
             marks = {f"log.append('{n}')": c for n, c in (("second", 1), ("leaf", 2), ("first", 3), ("root", 4),
                                                           ("sleeper", 5), ("observer", 6))}
         elif name == "process_lifecycle":
             sim.frontend.program_ids.update(ancestors=1, life=2)
             B.graves = set()
-            B.Endpoint().with_proc(sim, B.ancestors, B.graves)
+            B.build_family(sim, B.graves)
             marks = {"graves.add(self.name)": None, "graves.add('ancestors')": 5}
         elif name == "large_lan":
             sim.frontend.program_ids.update(lan_server=1, lan_client=2)
-            B.build_lan(sim, 4, 16, compat.per_process)
+            B.build_lan(sim, 4, 16, compat.per_process, lambda: compat.Router(forwarding=True))
             n_ep = 64
             sim.caps.update(max_events=n_ep + 64, max_procs=4 * n_ep + 64, max_sockets=2 * n_ep + 16, arena_nodes=64 * n_ep,
                             max_threads=2 * n_ep + 16, max_tasks=2 * n_ep + 16, max_signals=9 * n_ep + 64)
+            marks = {}
+        elif name == "echo":
+            sim.frontend.program_ids.update(answerer=1, asker=2)
+            B.build_echo(sim)
             marks = {}
         else:
             raise KeyError(name)
@@ -144,6 +148,60 @@ def test_compiled_bodies_give_the_reference_traces(hostemu, name, golden, seed, 
 @pytest.mark.parametrize("name,golden,seed,replica,duration", CASES)
 def test_compiled_bodies_give_the_reference_traces_on_the_gpu(name, golden, seed, replica, duration):
     check_case(name, golden, seed, replica, duration, None)
+
+
+# The same source file executed on the reference's own itsim (oracle/machine_scenarios.frontend_scenario, goldens made by
+# `python oracle/make_golden.py --frontend`): trace and the host-side state the bodies leave behind.
+SAME_FILE = [("packet_transfer", "ping_pong_s0_r0"), ("packet_transfer", "ping_pong_s9_r4"), ("broadcast", "chatter_s1_r5"),
+             ("thread_lifecycle", "threads_s0_r0"), ("process_lifecycle", "family_s0_r0"), ("large_lan", "lan_s2_r3"),
+             ("echo", "echo_s0_r0"), ("echo", "echo_s6_r21")]
+
+
+def check_same_file(name, tag, lib):
+    import json
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "frontend_summaries.json")) as fh:
+        want = json.load(fh)[tag]
+    seed, replica = int(tag.split("_s")[1].split("_")[0]), int(tag.split("_r")[1])
+    sim, B, _ = scenario(name, lib, seed, replica)
+    sim.run(INF if want["duration"] is None else want["duration"])
+    assert_same_events(sim._engine.trace(0), load_golden_trace(f"frontend_{tag}.npz"))
+    assert sim.now() == pytest.approx(want["now"], rel=1e-9)
+    state = want["state"]
+    if name == "packet_transfer":
+        assert sorted(B.seen) == state["seen"]
+        assert B.clock_at_timeout == pytest.approx(state["clock_at_timeout"], rel=1e-9)
+    elif name == "broadcast":
+        assert [sorted(int(a) for a in n.heard_from) for n in B.nodes] == state["heard_from"]
+    elif name == "thread_lifecycle":
+        assert B.log == state["log"]
+    elif name == "process_lifecycle":
+        assert sorted(B.graves) == state["graves"]
+    elif name == "echo":
+        assert B.echoed == state["echoed"] and B.unanswered == state["unanswered"]
+    sim._engine.close()
+
+
+@pytest.mark.parametrize("name,tag", SAME_FILE)
+def test_same_source_file_on_the_reference_and_on_the_engine(hostemu, name, tag):
+    check_same_file(name, tag, hostemu)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,tag", SAME_FILE)
+def test_same_source_file_on_the_reference_and_on_the_gpu(name, tag):
+    check_same_file(name, tag, None)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/itsim"), reason="reference tree not on this box")
+def test_goldens_are_what_the_reference_produces_now():
+    import json
+    import machine_scenarios as ms
+    from conftest import GOLDEN, assert_trace_equal
+    arr, out = ms.frontend_scenario("echo", 6, 21, 10.0)
+    assert_trace_equal(arr, load_golden_trace("frontend_echo_s6_r21.npz"), rtol=0.0)
+    with open(os.path.join(GOLDEN, "frontend_summaries.json")) as fh:
+        assert json.load(fh)["echo_s6_r21"]["state"] == out["state"]
 
 
 @pytest.mark.gpu
