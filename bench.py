@@ -195,6 +195,7 @@ def main() -> None:
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-horizon", type=float, default=1800.0, help="simulated seconds per CPU-baseline replica")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the untimed full-size self-check after the timed steps")
     ap.add_argument("--arena-nodes", type=int, default=12288)
     ap.add_argument("--max-events", type=int, default=0, help="future-event pool slots per replica (0 = model default)")
     ap.add_argument("--max-procs", type=int, default=0)
@@ -338,6 +339,33 @@ def main() -> None:
         total = engine.telemetry()
         hists, hist_ms = replica_histograms(engine, args, L, netsimple, None, 1)
 
+    # ---- full-size self-check (untimed): conservation laws on the job's counters, and sampled replicas of the batch
+    # ---- equal the same replica ids advanced alone through the same sequence of run() calls -----------------------
+    checks = None
+    if rank == 0 and not args.no_verify:
+        tm_job = np.asarray(total, dtype=np.uint64)
+        k0 = L.TM_KIND0
+        checks = {"events_equal_sum_of_kinds": int(tm_job[:9].sum()) == int(summarize(tm_job)["events"]),
+                  "delivered_plus_dropped_equal_deliver_events":
+                      int(tm_job[L.TM_DELIVERED]) + int(tm_job[L.TM_DROPPED]) == int(tm_job[k0 + L.EV_DELIVER])}
+        if args.workload != "large_lan":
+            checks["tx_begin_equal_packets_sent"] = int(tm_job[k0 + L.EV_TX_BEGIN]) == int(tm_job[L.TM_PACKETS_SENT])
+            checks["latency_histogram_covers_every_transmission"] = \
+                int(tm_job[L.TM_LAT0:L.TM_LAT0 + L.LAT_BINS].sum()) == int(tm_job[k0 + L.EV_TX_BEGIN])
+        sample = sorted({0, args.replicas // 2, args.replicas - 1})
+        same = []
+        for r in sample:
+            alone = sim.run_replicas(1, seed=args.seed, first_replica_id=rank * args.replicas + r, device=local_rank)
+            if args.spinup > 0:
+                alone.run(args.spinup)
+            for _ in range(args.warmup + 2 * args.steps):
+                alone.run(args.slice)
+            same.append(bool(np.array_equal(alone.replica_telemetry(0), engine.replica_telemetry(r))))
+            alone.close()
+        checks["replicas_equal_themselves_run_alone"] = dict(zip(map(str, sample), same))
+        checks["all"] = all(v if isinstance(v, bool) else all(v.values()) for v in checks.values())
+        assert checks["all"], checks
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         events_per_step_gpu = events_dev / args.steps
@@ -388,6 +416,7 @@ def main() -> None:
                         "proportional to their count; profiles/README.md)",
             },
             "clocks": clocks,
+            "checks": checks,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
