@@ -1211,6 +1211,25 @@ ITSB_FN ArenaNode sock_pop(Rep& R, Sock& S) {
 
 }  // namespace itsb
 #include "itsb_machine.cuh"
+
+#if defined(ITSB_HIDDEN_FAST)
+namespace itsb {
+/* One activation (start or resume) of select()'s per-signal helper, without the interpreter: the program is
+ * `signal.wait(); common.turn_on()` (ir.py add_hidden_programs: SIG_WAIT r0 / SIG_ON r1 / EXIT), so an activation either
+ * parks on the signal again or turns the common signal on and ends.  Same calls, in the same order, as the interpreted
+ * program makes: every counter value and queue position is unchanged.  Compiled into the in-place kernel (five of the
+ * seven heap pops behind a received packet of a shipped-itsim model are such helper hops) and the host emulation. */
+ITSB_COLD void hidden_wait_one(Hdr* H, u32 p) {
+    Rep R; rebind(R, H);
+    Pcb& P = R.pcb[p];
+    P.state = PS_RUNNING;
+    if (H->status != 0) return;
+    if (sig_wait(R, p, P.r[0] & 0xFFFF, 0xFFFF)) return;
+    sig_on(R, P.r[1] & 0xFFFF);
+    proc_exit(H, p);
+}
+}  // namespace itsb
+#endif
 namespace itsb {
 
 ITSB_COLD int exec_logged(Hdr* H, u32 p, u64 ins);   /* instructions of models that keep connection records */
@@ -1563,8 +1582,13 @@ ITSB_FN u64 run_replica(Rep& R, double duration) {
                 }
             }
             if (live) {
+#if defined(ITSB_HIDDEN_FAST)
+                if (P.prog == PROG_HIDDEN_WAIT_ONE) hidden_wait_one(H, idx); else
+#endif
+                {
                 if (!is_hidden_prog(P.prog)) count_event(R, kind, P.prog, P.node, 0);
                 runnable = idx;
+                }
             }
         } else if (kind == ITSB_EV_TX_BEGIN) {
             on_tx_begin(H, ev_pkt(data));
@@ -1577,6 +1601,13 @@ ITSB_FN u64 run_replica(Rep& R, double duration) {
                     count_event(R, ITSB_EV_THROW, P.prog, P.node, ev_exc(data));
                 if (P.state == PS_UNSTARTED) proc_exit(H, idx);   /* never ran: dies on the spot */
                 else runnable = deliver_exception(H, idx, ev_exc(data));
+#if defined(ITSB_HIDDEN_FAST)
+                /* a helper whose handler is the program's EXIT (CleanUp / CancelBalk: `except ...: pass`) ends here */
+                if (runnable != NIL32 && is_hidden_prog(P.prog) && (u32)(R.m.code[P.pc] & 0xFF) == OP_EXIT) {
+                    proc_exit(H, idx);
+                    runnable = NIL32;
+                }
+#endif
             }
         } else {
             fail(H, ITSB_ERR_BAD_OPCODE, data);

@@ -33,6 +33,13 @@ def hostemu(built):
 
 
 @pytest.fixture(scope="session")
+def hostemu_fast(built):
+    """The host emulation compiled like the in-place kernel: select()'s helper hops without the interpreter."""
+    from itsim_b200 import _lib
+    return _lib.bind(ctypes.CDLL(built.HOSTEMU.replace(".so", "_fast.so")))
+
+
+@pytest.fixture(scope="session")
 def golden_summaries():
     with open(os.path.join(GOLDEN, "netsimple_summaries.json")) as fh:
         return json.load(fh)

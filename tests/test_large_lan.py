@@ -36,6 +36,12 @@ def test_small_instance_trace(backend, hostemu):
     assert_trace_equal(eng.trace(0), ref)
 
 
+def test_small_instance_trace_with_fast_helper_hops(hostemu_fast):
+    ref = load_golden_trace("machine_large_lan_s1_r2_d20_s4_p16.npz")
+    eng, _ = run("hostemu", hostemu_fast, 4, 16, 1, 2, 20.0, len(ref) + 16, n=2)
+    assert_trace_equal(eng.trace(0), ref)
+
+
 @pytest.mark.parametrize("backend", BACKENDS)
 def test_full_size_instance(backend, hostemu, summaries):
     """1 024 endpoints + 16 routers, 8 simulated seconds, 175 881 events: counts, final record time and the digest of

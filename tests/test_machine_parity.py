@@ -40,6 +40,14 @@ def test_hostemu_matches_reference_bodies(hostemu, name, golden, seed, replica, 
     assert_trace_equal(eng.trace(0), load_golden_trace(golden))
 
 
+@pytest.mark.parametrize("name,golden,seed,replica,duration", CASES)
+def test_helper_hops_without_the_interpreter_change_nothing(hostemu_fast, name, golden, seed, replica, duration):
+    """ITSB_HIDDEN_FAST (what k_run_in_place is compiled with): select()'s helper processes take their hops through
+    `hidden_wait_one` instead of the interpreter; the traces stay the reference's."""
+    eng = run_scenario(name, seed, replica, duration, lib=hostemu_fast)
+    assert_trace_equal(eng.trace(0), load_golden_trace(golden))
+
+
 def test_known_answers_of_the_reference(hostemu):
     from itsim_b200 import _lib as L
     eng = run_scenario("thread_lifecycle", 0, 0, INF, lib=hostemu)
