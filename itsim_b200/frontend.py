@@ -1065,7 +1065,7 @@ class _Body:
                     return Rt(ir.PKT_F0 if self.fe.payload_field(key.v, self, e) == 0 else ir.PKT_F1, "int")
                 raise self.err(e, "payload keys are compile-time values")
             if isinstance(base, Const) and isinstance(key, Const):
-                return self.wrap(base.v[key.v])
+                return Const(base.v[key.v])
             raise self.err(e, "subscript on a simulation value")
         if isinstance(e, ast.Call):
             return self.call(e, scope)
@@ -1093,9 +1093,6 @@ class _Body:
             raise self.err(e, "a dict of simulation values")
         # anything else: compile-time only
         return self.static(e, scope)
-
-    def wrap(self, v: Any) -> Any:
-        return Const(v)
 
     def static(self, e: ast.AST, scope: _Scope) -> Const:
         if not self.is_host_only(e, scope):
@@ -1237,9 +1234,6 @@ class _Body:
         conv = {"task_self": Rt(ir.SELF_TASK, "task"), "thread_self": Rt(ir.SELF_THREAD, "thread")}
         l = conv.get(l.what, l) if isinstance(l, _Sym) else l
         r = conv.get(r.what, r) if isinstance(r, _Sym) else r
-        for side in (l, r):
-            if isinstance(side, Const) and isinstance(side.v, GlobalRef):
-                pass
         if isinstance(l, Const) and isinstance(r, Const) and not isinstance(l.v, GlobalRef) \
                 and not isinstance(r.v, GlobalRef):
             return self.static(e, scope)
