@@ -237,7 +237,7 @@ int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first
     if (L.log_cap) CU(e, cudaMalloc(&e->d_netlog, (size_t)n * L.log_cap * sizeof(itsb_net_event)));
     e->rp.hot = e->d_hot; e->rp.arena = e->d_arena; e->rp.arena_free = e->d_arena_free; e->rp.trace = e->d_trace;
     if (L.conn_cap) {
-        CU(e, cudaMalloc(&e->d_connlog, (size_t)n * L.conn_cap * sizeof(itsb_connection)));
+        CU(e, cudaMalloc(&e->d_connlog, (size_t)n * conn_log_bytes(L.conn_cap)));
         CU(e, cudaMalloc(&e->d_conntab, (size_t)n * L.max_sock * 2 * L.conn_window * sizeof(ConnEnt)));
     }
     e->rp.netlog = e->d_netlog; e->rp.connlog = e->d_connlog; e->rp.conntab = e->d_conntab;
@@ -368,8 +368,19 @@ int itsb_read_connections(itsb_engine* e, uint64_t replica, itsb_connection* dst
     if (n_total) *n_total = h.conn_count;
     size_t n = h.conn_count < e->rp.layout.conn_cap ? h.conn_count : e->rp.layout.conn_cap;
     if (n > cap) n = cap;
-    if (n && e->d_connlog)
-        CU(e, cudaMemcpy(dst, e->d_connlog + (size_t)replica * e->rp.layout.conn_cap, n * sizeof(itsb_connection), cudaMemcpyDeviceToHost));
+    if (n && e->d_connlog) {
+        /* records, then their order keys (kept for everything the log holds: a record retired early may belong
+           before one that was cut off by `cap`, so order first, cut afterwards) */
+        const size_t held = h.conn_count < e->rp.layout.conn_cap ? h.conn_count : e->rp.layout.conn_cap;
+        const unsigned char* base = (const unsigned char*)e->d_connlog + (size_t)replica * conn_log_bytes(e->rp.layout.conn_cap);
+        std::vector<itsb_connection> recs(held);
+        std::vector<uint32_t> keys(held);
+        CU(e, cudaMemcpy(recs.data(), base, held * sizeof(itsb_connection), cudaMemcpyDeviceToHost));
+        CU(e, cudaMemcpy(keys.data(), base + (size_t)e->rp.layout.conn_cap * sizeof(itsb_connection), held * sizeof(uint32_t),
+                         cudaMemcpyDeviceToHost));
+        order_connections(recs.data(), keys.data(), held);
+        memcpy(dst, recs.data(), n * sizeof(itsb_connection));
+    }
     return ITSB_OK;
 }
 

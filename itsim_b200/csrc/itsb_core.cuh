@@ -284,7 +284,7 @@ struct Hdr {                /* first thing in the hot block */
     u64 pmin_t;
     u64 ovf_min_t;
     u32 ovf_min_seq, ovf_head, ovf_count;
-    u32 spare32;
+    u32 cur_seq;            /* counter value of the event being processed: the order key of the connection records */
     u32 rng_c0, rng_c1;     /* the second half of the Philox block the last even draw computed (= the next draw) */
     u16 sig_free_top, thr_free_top, task_free_top;
     u16 setup_done;         /* the per-replica set-up draws (ITSB_INIT_ADD_DRAWN) have been made */
@@ -1053,6 +1053,8 @@ ITSB_COLD void trace_deliveries(Hdr* H, u32 first_slot, u32 node, bool valid, u3
  * (now-queue empty, no future event at t == now) that outcome cannot be influenced by anything in between, so the
  * lane retires the wake-up on the spot: no queue node, no event, same counters, same counter values consumed.  Off
  * while tracing, so a trace always shows the reference's interleaving event by event. */
+ITSB_COLD void conn_retired(Hdr* H, u32 mask, u32 s_lane, u32 seq_lane, u32 k);
+
 ITSB_FN void on_deliver(Rep& R, u32 k) {
     Hdr* H = R.hdr;
     const Pkt K = *pkt_at(R, k);
@@ -1094,7 +1096,8 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
             if (w != NIL16 && S.q_len == 0 && R.pcb[w].wnext == NIL16) {
                 const Pcb& P = R.pcb[w];
                 const u64 ins = R.m.code[P.pc];
-                if ((u32)(ins & 0xFF) == OP_RECV_FILTER && P.phase == 1 &&
+                const u32 wop = (u32)(ins & 0xFF);
+                if ((wop == OP_RECV_FILTER || wop == OP_RECV_FILTER_LOG) && P.phase == 1 &&
                     R.node[node].epoch == P.r[(u32)(ins >> 8) & 3]) {
                     const itsb_filter F = R.m.filters[(u32)(ins >> 16) & 0xFF];
                     retire = !filter_passes(R, F, K.tag, K.f0, R.m.nodes[node].host, P);
@@ -1151,6 +1154,10 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
                 S.wait_head = NIL16; S.wait_tail = NIL16;
             }
             w_sync();
+            /* a model that keeps connection records: the retired recipients' recv() would have correlated the packet
+               (overrides.py:135-147); done here, one socket after the other in recipient order, each under the counter
+               value its wake-up would have had (the order key of the records it logs) */
+            if (n_retired && H->conntab) conn_retired(H, w_ballot(retire), (u32)s, H->seq + before_seq, k);
             H->nq_tail += total;
             H->seq += total_seq;
         } else {
@@ -1564,6 +1571,7 @@ ITSB_FN u64 run_replica(Rep& R, double duration) {
         }
         const u32 data = ev_take(R, src);
         H->now = bitsd(tb);
+        H->cur_seq = seq;
         const u32 kind = ev_kind(data), idx = ev_idx(data);
         u32 runnable = NIL32, deliver = NIL32;
         if (kind == ITSB_EV_DELIVER) {
@@ -1654,6 +1662,7 @@ ITSB_FN bool run_pop(Rep& R, const RunCtx& C, u32& runnable) {
     }
     const u32 data = ev_take(R, src);
     H->now = bitsd(tb);
+    H->cur_seq = seq;
     const u32 kind = ev_kind(data), idx = ev_idx(data);
     u32 deliver = NIL32;
     if (kind == ITSB_EV_DELIVER) {
@@ -1706,6 +1715,11 @@ ITSB_FN u64 run_events(Rep& R, const RunCtx& C) { return C.active ? events_count
 ITSB_FN ConnEnt* conn_table(Hdr* H, u32 s, u32 dir) {
     return H->conntab + ((size_t)s * 2 + dir) * H->L.conn_window;
 }
+/* the replica's record log is conn_cap records followed by conn_cap order keys (u32): a record's key is the counter
+ * value of the event whose processing logged it.  Records are appended in processing order except those of wake-ups
+ * retired in the delivery pass, which are logged early under the key their wake-up would have had;
+ * itsb_read_connections sorts by (End_Time, key), which is the order Socket.log_pair was called in. */
+ITSB_FN u32* conn_order(Hdr* H) { return (u32*)(H->connlog + H->L.conn_cap); }
 ITSB_FN u16* conn_fill(Hdr* H, u32 s) { return (u16*)((u8*)H + H->L.off_sockx) + 2 * s; }
 
 ITSB_FN int conn_find(const ConnEnt* T, u32 n, u32 ip, u32 port) {
@@ -1784,6 +1798,7 @@ ITSB_COLD void conn_log(Hdr* H, u32 node, u32 has, u32 in_ip, u32 in_port, u32 i
         C.sent_bytes = (has & 2) ? out_size : 0;
         C.node = (u16)node; C.inbound = inbound ? 1 : 0; C.has = (u8)has;
         H->connlog[n] = C;
+        conn_order(H)[n] = H->cur_seq;
     }
     H->conn_count = n + 1;
 }
@@ -1810,9 +1825,35 @@ ITSB_COLD void conn_outbound(Hdr* H, u32 s, u32 node, u32 dst_ip, u32 dst_port, 
 }
 
 /* correlate_inbound_packet (overrides.py:115-120), called by recv() on the packet it returns */
+ITSB_COLD void conn_inbound_fields(Hdr* H, u32 s, u32 src_ip, u32 ports, u32 dst_ip, u32 size);
 ITSB_COLD void conn_inbound(Hdr* H, u32 s, u32 queued) {
     const ArenaNode A = H->arena[queued];
-    const u32 src_ip = A.src_ip, src_port = A.ports & 0xFFFF, dst_ip = A.pad, dst_port = A.ports >> 16, size = A.size;
+    conn_inbound_fields(H, s, A.src_ip, A.ports, A.pad, A.size);
+}
+
+/* the correlations of the wake-ups retired in one delivery pass (see on_deliver) */
+ITSB_COLD void conn_retired(Hdr* H, u32 mask, u32 s_lane, u32 seq_lane, u32 k) {
+    Rep R; rebind(R, H);
+    const Pkt K = *pkt_at(R, k);
+    const u32 saved = H->cur_seq;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (int l = 0; l < ITSB_W; ++l) {
+        const u32 sl = w_shfl(s_lane, l), ql = w_shfl(seq_lane, l);
+        if (((mask >> l) & 1u) == 0) continue;
+        w_sync();
+        H->cur_seq = ql;
+        w_sync();
+        conn_inbound_fields(H, sl, K.src_ip, K.ports, K.dst_ip, K.size);
+    }
+    w_sync();
+    H->cur_seq = saved;
+    w_sync();
+}
+
+ITSB_COLD void conn_inbound_fields(Hdr* H, u32 s, u32 src_ip, u32 ports, u32 dst_ip, u32 size) {
+    const u32 src_port = ports & 0xFFFF, dst_port = ports >> 16;
     u16* fill = conn_fill(H, s);
     ConnEnt* TO = conn_table(H, s, 0);
     ConnEnt* TI = conn_table(H, s, 1);
@@ -1873,6 +1914,39 @@ ITSB_COLD int exec_logged(Hdr* H, u32 p, u64 ins) {
         set_pkt_regs(R, A);
         P.pc += 1;
         return XR_CONTINUE;
+    }
+    case OP_RECV_FILTER_LOG: {   /* OP_RECV_FILTER (run_process) of a model that keeps connection records: every packet
+                                    the loop head pops is correlated first, handed to the program or not; what a
+                                    filtered wake-up would do is then fixed, so the delivery pass can retire it */
+        if (P.sock == NIL16) { fail(H, ITSB_EXC_SOCKET_CLOSED, P.pc); return XR_STOP; }
+        NodeDyn& N = R.node[P.node];
+        Sock& S = R.sock[P.sock];
+        const itsb_filter F = R.m.filters[b];
+        for (;;) {
+            if (P.phase == 0) {               /* with ws.awake(): wait_until_awake, remember the wake epoch */
+                if (!N.awake) {
+                    waiters_append(R, N.wake_head, N.wake_tail, p, (u16)(WS_NODE | P.node));
+                    P.state = PS_WAIT;
+                    return XR_STOP;
+                }
+                P.r[a & 3] = N.epoch;
+                P.phase = 1;
+            }
+            if (S.q_len == 0) {               /* socket.recv() */
+                waiters_append(R, S.wait_head, S.wait_tail, p, (u16)(WS_SOCK | P.sock));
+                P.state = PS_WAIT;
+                return XR_STOP;
+            }
+            if (H->conntab) conn_inbound(H, P.sock, S.q_head);
+            const ArenaNode A = sock_pop(R, S);
+            P.phase = 0;
+            if (N.epoch != P.r[a & 3]) { P.pc = (u16)(imm & 0xFFFF); return XR_CONTINUE; }      /* FellAsleep */
+            if (filter_passes(R, F, A.tag, A.f0, R.m.nodes[P.node].host, P)) {
+                set_pkt_regs(R, A);
+                P.pc += 1;
+                return XR_CONTINUE;
+            }
+        }
     }
     case OP_OPEN_AT:      /* a second socket, on another attachment of this machine: imm = node | port << 16 */
         if (sock_open_on(H, p, imm & 0xFFFF, imm >> 16, false) < 0) return XR_STOP;
@@ -1941,7 +2015,7 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
     H->nq_head = 0; H->nq_tail = 0; H->nq_spill_head = NIL32; H->nq_spill_tail = NIL32; H->nq_spill_count = 0;
     H->pmin_valid = 0; H->pmin_idx = NIL32; H->pmin_seq = NIL32; H->pmin_t = T_EMPTY;
     H->ovf_min_t = T_EMPTY; H->ovf_min_seq = NIL32; H->ovf_head = NIL32; H->ovf_count = 0;
-    H->spare16 = 0; H->spare32 = 0; H->rng_c0 = 0; H->rng_c1 = 0;
+    H->spare16 = 0; H->cur_seq = 0; H->rng_c0 = 0; H->rng_c1 = 0;
     for (u32 i = 0; i < VOL_COUNT; ++i) H->vol[i] = 0;
     for (u32 i = 0; i < 2 * NQ_CAP; ++i) R.nq[i] = 0;
     for (u32 i = 0; i < L->max_ev; ++i) { R.ev_t[i] = T_EMPTY; R.ev_seq[i] = 0; R.ev_data[i] = 0; R.ev_free[i] = (u16)(L->max_ev - 1 - i); }

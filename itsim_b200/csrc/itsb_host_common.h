@@ -3,6 +3,9 @@
  * emulation build (tests/hostemu): model validation and the per-replica hot-block layout.
  */
 #pragma once
+#include <algorithm>
+#include <vector>
+#include <string.h>
 #include <stdio.h>
 #include <string>
 #include "itsb_core.cuh"
@@ -45,11 +48,36 @@ static inline Layout compute_layout(const itsb_model_desc& d) {
     L.table_words = c.table_words;
     L.off_tab = off;       off = align_up(off + 4 * L.table_words, 16);
     /* connection records: fill counts of the two correlation windows of every socket */
-    L.conn_cap = c.connection_records; L.conn_window = c.connection_records ? c.connection_window : 0;
+    L.conn_cap = (c.connection_records + 1u) & ~1u;      /* even: the order keys behind the records stay 8-byte aligned */
+    L.conn_window = c.connection_records ? c.connection_window : 0;
     L.address_tags = d.address_tags;
     L.off_sockx = off;     off = align_up(off + (L.conn_cap ? 4 * L.max_sock : 0), 16);
     L.hot_bytes = align_up(off, 128);
     return L;
+}
+
+/* bytes of one replica's connection log: conn_cap records followed by conn_cap u32 order keys (itsb_core.cuh conn_order) */
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline size_t conn_log_bytes(uint32_t conn_cap) { return (size_t)conn_cap * (sizeof(itsb_connection) + sizeof(uint32_t)); }
+
+/* Puts the first n records of a replica's log in the order Socket.log_pair was called in: by End_Time, then by the
+ * counter value of the event that logged them (records of wake-ups retired in the delivery pass are appended early,
+ * under the key their wake-up would have had).  Stable, so records of one event keep their order. */
+static inline void order_connections(itsb_connection* recs, const uint32_t* keys, size_t n) {
+    bool sorted = true;
+    for (size_t i = 1; i < n && sorted; ++i)
+        sorted = recs[i - 1].t_end < recs[i].t_end || (recs[i - 1].t_end == recs[i].t_end && keys[i - 1] <= keys[i]);
+    if (sorted) return;
+    std::vector<uint32_t> idx(n);
+    for (size_t i = 0; i < n; ++i) idx[i] = (uint32_t)i;
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
+        return recs[a].t_end < recs[b].t_end || (recs[a].t_end == recs[b].t_end && keys[a] < keys[b]);
+    });
+    std::vector<itsb_connection> out(n);
+    for (size_t i = 0; i < n; ++i) out[i] = recs[idx[i]];
+    memcpy(recs, out.data(), n * sizeof(itsb_connection));
 }
 
 static inline bool validate_model(const itsb_model_desc& d, const void* const* blobs, const size_t* sizes,
@@ -89,7 +117,7 @@ static inline bool validate_model(const itsb_model_desc& d, const void* const* b
         if ((op == OP_STAT || op == OP_STAT_ADD || op == OP_STAT_FIRST) && imm >= ITSB_TM_USER_SLOTS) {
             why = "model counter out of range"; return false;
         }
-        if (op == OP_RECV_FILTER) {
+        if (op == OP_RECV_FILTER || op == OP_RECV_FILTER_LOG) {
             uint32_t a = (uint32_t)((code[i] >> 8) & 0xFF), b = (uint32_t)((code[i] >> 16) & 0xFF);
             if (a > 3 || b >= d.n_filters || (imm & 0xFFFF) >= d.n_code) { why = "RECV_FILTER operand out of range"; return false; }
         }

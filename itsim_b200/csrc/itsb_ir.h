@@ -93,6 +93,7 @@ enum {
     OP_CLOSE_LOG = 65,  /* flush_logs, then OP_CLOSE                                              overrides.py:366-367   */
     OP_STAT_ADD = 66,   /* user counter imm += src(a)                                                              */
     OP_STAT_FIRST = 67, /* user counter imm = now in microseconds, the first time only (a time-to-first statistic) */
+    OP_RECV_FILTER_LOG = 68, /* OP_RECV_FILTER with correlate_inbound_packet on every packet the loop head pops            */
     OP_COUNT
 };
 

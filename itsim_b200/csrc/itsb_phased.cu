@@ -48,7 +48,7 @@ extern "C" __global__ void __launch_bounds__(384, 1) k_run_phased(const RunParam
                 B.arena_free = p.arena_free + r * p.layout.arena_nodes;
                 B.trace = p.trace ? p.trace + r * p.layout.trace_cap : nullptr;
                 B.netlog = p.netlog ? p.netlog + r * p.layout.log_cap : nullptr;
-                B.connlog = p.connlog ? p.connlog + r * p.layout.conn_cap : nullptr;
+                B.connlog = p.connlog ? (itsb_connection*)((unsigned char*)p.connlog + r * conn_log_bytes(p.layout.conn_cap)) : nullptr;
                 B.conntab = p.conntab ? p.conntab + r * ((size_t)p.layout.max_sock * 2 * p.layout.conn_window) : nullptr;
                 bind_views(R, hot, &p.layout, m, B, p.seed);
                 run_begin(R, p.duration, C);

@@ -17,7 +17,8 @@ import numpy as np
  OP_BIND, OP_SCLOSE, OP_SENDL, OP_RECVT, OP_ADVANCE_X, OP_THREAD_EXIT, OP_CLONE, OP_FORK, OP_JOIN, OP_PWAIT, OP_TKILL,
  OP_PKILL, OP_MARK, OP_SIG_WAIT, OP_SIG_ON, OP_GSET, OP_NOW_SUB, OP_ADVANCE_X2, OP_TLOAD, OP_TSTORE, OP_ADD, OP_SUB,
  OP_JLTU, OP_XNOW, OP_XSET, OP_XELAPSE, OP_JXLE0, OP_RECVT_X, OP_SETADDR, OP_GETADDR, OP_FORWARD, OP_GETPORT,
- OP_RECV_LOG, OP_OPEN_AT, OP_SEND_LOG, OP_FORWARD_LOG, OP_CLOSE_LOG, OP_STAT_ADD, OP_STAT_FIRST) = range(68)
+ OP_RECV_LOG, OP_OPEN_AT, OP_SEND_LOG, OP_FORWARD_LOG, OP_CLOSE_LOG, OP_STAT_ADD, OP_STAT_FIRST,
+ OP_RECV_FILTER_LOG) = range(69)
 
 PROG_HIDDEN_BALK, PROG_HIDDEN_WAIT_ONE = 0xF1, 0xF2
 
@@ -227,7 +228,8 @@ class Asm:
     def recv_filter(self, rd: int, filter_index: int, asleep: Target, handler: Optional[Target] = None) -> None:
         """Fused ``while True: with ws.awake(): packet = socket.recv()`` loop head that also consumes the packets
         the program's own dispatch would ignore (see ``Simulator.packet_filter``)."""
-        self._emit(OP_RECV_FILTER, rd, filter_index, imm=("hi16", self._t(handler), self._t(asleep)))
+        self._emit(OP_RECV_FILTER_LOG if self.log_connections else OP_RECV_FILTER, rd, filter_index,
+                   imm=("hi16", self._t(handler), self._t(asleep)))
 
     def wait_awake(self, rd: int = NONE, handler: Optional[Target] = None) -> None:
         self._emit(OP_WAIT_AWAKE, rd, imm=("hi16", self._t(handler), 0))

@@ -200,7 +200,6 @@ def build(cidr: str = "192.168.4.0/24", num_endpoints: Optional[int] = None, tra
     if connection_records:
         sim.asm.log_connections = True
         sim.caps.update(connection_records=connection_records, connection_window=connection_window)
-        fused = False
     num_addresses = ip_network(cidr).num_addresses - NUM_ADDRESSES_RESERVED
     if num_addresses < MIN_NUM_ENDPOINTS:
         raise ValueError(f"Unsuitable CIDR prefix for simulating a non-trivial network: {cidr}")

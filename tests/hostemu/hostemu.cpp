@@ -35,7 +35,7 @@ struct itsb_engine {
     std::vector<uint32_t> arena_free;
     std::vector<itsb_trace_rec> trace;
     std::vector<itsb_net_event> netlog;
-    std::vector<itsb_connection> connlog;
+    std::vector<unsigned char> connlog;      /* per replica: conn_cap records, then conn_cap order keys */
     std::vector<ConnEnt> conntab;
     uint64_t last_events = 0, launches = 0;
     std::string err;
@@ -81,7 +81,7 @@ static void bind(itsb_engine* e, Rep& R, uint64_t r) {
     B.arena_free = e->arena_free.data() + r * L.arena_nodes;
     B.trace = L.trace_cap ? e->trace.data() + r * L.trace_cap : nullptr;
     B.netlog = L.log_cap ? e->netlog.data() + r * L.log_cap : nullptr;
-    B.connlog = L.conn_cap ? e->connlog.data() + r * L.conn_cap : nullptr;
+    B.connlog = L.conn_cap ? (itsb_connection*)(e->connlog.data() + r * conn_log_bytes(L.conn_cap)) : nullptr;
     B.conntab = L.conn_cap ? e->conntab.data() + r * ((size_t)L.max_sock * 2 * L.conn_window) : nullptr;
     bind_views(R, e->hot.data() + r * L.hot_bytes, &L, &e->model, B, e->seed);
 }
@@ -94,7 +94,7 @@ int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first
     e->arena_free.resize(n * e->layout.arena_nodes);
     e->trace.assign(n * e->layout.trace_cap, itsb_trace_rec());
     e->netlog.assign(n * e->layout.log_cap, itsb_net_event());
-    e->connlog.assign(n * e->layout.conn_cap, itsb_connection());
+    e->connlog.assign(n * conn_log_bytes(e->layout.conn_cap), 0);
     e->conntab.assign(n * ((size_t)e->layout.max_sock * 2 * e->layout.conn_window), ConnEnt());
     for (uint64_t r = 0; r < n; ++r) {
         Rep R; bind(e, R, r);
@@ -182,7 +182,16 @@ int itsb_read_connections(itsb_engine* e, uint64_t replica, itsb_connection* dst
     if (n_total) *n_total = H->conn_count;
     size_t n = H->conn_count < e->layout.conn_cap ? H->conn_count : e->layout.conn_cap;
     if (n > cap) n = cap;
-    if (n) memcpy(dst, e->connlog.data() + replica * e->layout.conn_cap, n * sizeof(itsb_connection));
+    if (n) {
+        const size_t held = H->conn_count < e->layout.conn_cap ? H->conn_count : e->layout.conn_cap;
+        const unsigned char* base = e->connlog.data() + replica * conn_log_bytes(e->layout.conn_cap);
+        std::vector<itsb_connection> recs(held);
+        std::vector<uint32_t> keys(held);
+        memcpy(recs.data(), base, held * sizeof(itsb_connection));
+        memcpy(keys.data(), base + (size_t)e->layout.conn_cap * sizeof(itsb_connection), held * sizeof(uint32_t));
+        order_connections(recs.data(), keys.data(), held);
+        memcpy(dst, recs.data(), n * sizeof(itsb_connection));
+    }
     return ITSB_OK;
 }
 
