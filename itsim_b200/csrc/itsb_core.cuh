@@ -1831,24 +1831,75 @@ ITSB_COLD void conn_inbound(Hdr* H, u32 s, u32 queued) {
     conn_inbound_fields(H, s, A.src_ip, A.ports, A.pad, A.size);
 }
 
-/* the correlations of the wake-ups retired in one delivery pass (see on_deliver) */
+/* The correlations of the wake-ups retired in one delivery pass (see on_deliver): what conn_inbound does, with one
+ * lane per retired socket instead of the warp per socket -- the sockets are different, so are their tables, and the
+ * chains of dependent HBM accesses (find, log, remove, put) overlap instead of queueing up.  Each socket logs at most
+ * one record (the completed pair, or the entry its full window gives up); log slots go by lane rank = recipient order. */
 ITSB_COLD void conn_retired(Hdr* H, u32 mask, u32 s_lane, u32 seq_lane, u32 k) {
     Rep R; rebind(R, H);
     const Pkt K = *pkt_at(R, k);
-    const u32 saved = H->cur_seq;
-#if defined(__CUDACC__)
-#pragma unroll 1
-#endif
-    for (int l = 0; l < ITSB_W; ++l) {
-        const u32 sl = w_shfl(s_lane, l), ql = w_shfl(seq_lane, l);
-        if (((mask >> l) & 1u) == 0) continue;
-        w_sync();
-        H->cur_seq = ql;
-        w_sync();
-        conn_inbound_fields(H, sl, K.src_ip, K.ports, K.dst_ip, K.size);
+    const bool mine = ((mask >> lane_id()) & 1u) != 0;
+    const u32 src_ip = K.src_ip, src_port = K.ports & 0xFFFF, dst_ip = K.dst_ip, dst_port = K.ports >> 16, size = K.size;
+    const u32 window = H->L.conn_window;
+    const u64 nowb = dbits(H->now);
+    itsb_connection C;
+    bool emit = false;
+    if (mine) {
+        u16* fill = conn_fill(H, s_lane);
+        ConnEnt* TO = conn_table(H, s_lane, 0);
+        ConnEnt* TI = conn_table(H, s_lane, 1);
+        C.t_end = H->now; C.node = (u16)R.sock[s_lane].node;
+        int j = -1;
+        for (u32 i = 0; i < fill[0]; ++i)
+            if (TO[i].key_ip == src_ip && (TO[i].ports & 0xFFFF) == src_port) { j = (int)i; break; }
+        if (j >= 0) {                       /* the answer to something this socket sent: log the pair, forget the entry */
+            const ConnEnt E = TO[j];
+            C.t_start = conn_time(E);
+            C.local_ip = dst_ip; C.local_port = (u16)dst_port; C.received_bytes = size;
+            C.remote_ip = E.a_ip; C.remote_port = (u16)(E.ports >> 16); C.sent_bytes = E.size;
+            C.inbound = 0; C.has = 3;
+            emit = true;
+            const u32 n = fill[0];
+            for (u32 i = (u32)j + 1; i < n; ++i) TO[i - 1] = TO[i];
+            fill[0] = (u16)(n - 1);
+        } else {
+            int i = -1;
+            for (u32 q = 0; q < fill[1]; ++q)
+                if (TI[q].key_ip == src_ip && (TI[q].ports & 0xFFFF) == src_port) { i = (int)q; break; }
+            if (i < 0) {
+                u32 n = fill[1];
+                if (n >= window) {          /* full window: its oldest entry is logged as flush_logs would log it */
+                    const ConnEnt E = TI[0];
+                    C.t_start = conn_time(E);
+                    C.local_ip = E.a_ip; C.local_port = (u16)(E.ports >> 16); C.received_bytes = E.size;
+                    C.remote_ip = 0; C.remote_port = 0; C.sent_bytes = 0;
+                    C.inbound = 1; C.has = 1;
+                    emit = true;
+                    for (u32 q = 1; q < n; ++q) TI[q - 1] = TI[q];
+                    n -= 1;
+                }
+                i = (int)n;
+                fill[1] = (u16)(n + 1);
+            }
+            ConnEnt E;
+            E.key_ip = src_ip; E.a_ip = dst_ip; E.size = size; E.ports = src_port | (dst_port << 16);
+            E.t_lo = (u32)nowb; E.t_hi = (u32)(nowb >> 32); E.pad[0] = 0; E.pad[1] = 0;
+            TI[i] = E;
+        }
+    }
+    const u32 emask = w_ballot(emit);
+    const u32 total = (u32)popc(emask);
+    const u32 n0 = H->conn_count;
+    if (emit) {
+        const u32 slot = n0 + (u32)popc(emask & lanemask_lt());
+        if (slot < H->L.conn_cap) {
+            H->connlog[slot] = C;
+            conn_order(H)[slot] = seq_lane;
+        }
     }
     w_sync();
-    H->cur_seq = saved;
+    R.stats[ITSB_TM_USER0 + 6] += total;      /* records produced (user slot 6) */
+    H->conn_count = n0 + total;
     w_sync();
 }
 

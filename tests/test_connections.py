@@ -101,6 +101,22 @@ def test_malware_overlay_records_match_the_oracle(backend, hostemu):
 
 
 @pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("builder", ["build", "build_malware"])
+def test_retired_wakeups_are_correlated_in_the_delivery_pass(backend, builder, hostemu):
+    """With the log on, the daemons keep their fused receive loops (OP_RECV_FILTER_LOG): a wake-up the declared filter
+    would reject is retired in the delivery pass, which then does that recv()'s correlation itself and logs under the
+    counter value the wake-up would have had.  Records (after the read-side ordering) and every counter equal those of
+    the same model assembled from plain receive loops, where each of these packets wakes its daemon."""
+    fused = engine_run(backend, hostemu, 8, 40, 1800.0, builder=builder, n=3)
+    plain = engine_run(backend, hostemu, 8, 40, 1800.0, builder=builder, n=3, fused=False)
+    for r in range(3):
+        a, b = fused.connections(r), plain.connections(r)
+        assert fused.connections_total == plain.connections_total == len(a) > 1000
+        assert np.array_equal(a, b), r
+        assert np.array_equal(fused.replica_telemetry(r), plain.replica_telemetry(r)), r
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
 def test_overflow_is_counted_not_written(backend, hostemu):
     eng = engine_run(backend, hostemu, 0, 0, 1500.0, cap=16)
     got = eng.connections(0)
