@@ -84,6 +84,12 @@ def main():
                     cand.append(fn)
             cand = [f for f in cand if f == ".text." + kernel or f.startswith("$" + kernel + "$")
                     or f.startswith("$__internal")]
+            if len(cand) != len(data):      # an $__internal helper of another kernel of the cubin (a division routine)
+                for drop in sorted({f for f in cand if f.startswith("$__internal")}):
+                    trial = [f for f in cand if f != drop]
+                    if len(trial) == len(data):
+                        cand = trial
+                        break
             if len(cand) == len(data):
                 seq = cand
         if len(seq) == len(data):
