@@ -1722,7 +1722,7 @@ ITSB_FN ConnEnt* conn_table(Hdr* H, u32 s, u32 dir) {
 ITSB_FN u32* conn_order(Hdr* H) { return (u32*)(H->connlog + H->L.conn_cap); }
 ITSB_FN u16* conn_fill(Hdr* H, u32 s) { return (u16*)((u8*)H + H->L.off_sockx) + 2 * s; }
 
-ITSB_FN int conn_find(const ConnEnt* T, u32 n, u32 ip, u32 port) {
+ITSB_COLD int conn_find(const ConnEnt* T, u32 n, u32 ip, u32 port) {
     u32 hit = NIL32;
 #if defined(__CUDACC__)
 #pragma unroll 1
@@ -1733,7 +1733,7 @@ ITSB_FN int conn_find(const ConnEnt* T, u32 n, u32 ip, u32 port) {
     return m == NIL32 ? -1 : (int)m;
 }
 
-ITSB_FN void conn_remove(ConnEnt* T, u16* fill, u32 idx) {
+ITSB_COLD void conn_remove(ConnEnt* T, u16* fill, u32 idx) {
     const u32 n = *fill;
 #if defined(__CUDACC__)
 #pragma unroll 1
@@ -1762,7 +1762,7 @@ ITSB_FN void conn_log_single(Hdr* H, u32 node, const ConnEnt& E, u32 dir) {
 
 /* files an entry at position idx (>= 0: the key is already there and keeps its place, like a dict assignment) or
  * appends it; a full window first gives up its oldest entry, logged as flush_logs would have logged it at close */
-ITSB_FN void conn_put(Hdr* H, u32 node, ConnEnt* T, u16* fill, u32 dir, int idx, u32 key_ip, u32 a_ip, u32 size,
+ITSB_COLD void conn_put(Hdr* H, u32 node, ConnEnt* T, u16* fill, u32 dir, int idx, u32 key_ip, u32 a_ip, u32 size,
                       u32 ports) {
     if (idx < 0) {
         if (*fill >= H->L.conn_window) {
@@ -1850,6 +1850,9 @@ ITSB_COLD void conn_retired(Hdr* H, u32 mask, u32 s_lane, u32 seq_lane, u32 k) {
         ConnEnt* TI = conn_table(H, s_lane, 1);
         C.t_end = H->now; C.node = (u16)R.sock[s_lane].node;
         int j = -1;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
         for (u32 i = 0; i < fill[0]; ++i)
             if (TO[i].key_ip == src_ip && (TO[i].ports & 0xFFFF) == src_port) { j = (int)i; break; }
         if (j >= 0) {                       /* the answer to something this socket sent: log the pair, forget the entry */
@@ -1860,10 +1863,16 @@ ITSB_COLD void conn_retired(Hdr* H, u32 mask, u32 s_lane, u32 seq_lane, u32 k) {
             C.inbound = 0; C.has = 3;
             emit = true;
             const u32 n = fill[0];
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
             for (u32 i = (u32)j + 1; i < n; ++i) TO[i - 1] = TO[i];
             fill[0] = (u16)(n - 1);
         } else {
             int i = -1;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
             for (u32 q = 0; q < fill[1]; ++q)
                 if (TI[q].key_ip == src_ip && (TI[q].ports & 0xFFFF) == src_port) { i = (int)q; break; }
             if (i < 0) {
@@ -1875,6 +1884,9 @@ ITSB_COLD void conn_retired(Hdr* H, u32 mask, u32 s_lane, u32 seq_lane, u32 k) {
                     C.remote_ip = 0; C.remote_port = 0; C.sent_bytes = 0;
                     C.inbound = 1; C.has = 1;
                     emit = true;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
                     for (u32 q = 1; q < n; ++q) TI[q - 1] = TI[q];
                     n -= 1;
                 }
