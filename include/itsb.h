@@ -291,7 +291,10 @@ int itsb_histogram(itsb_engine* e, uint32_t slot, uint64_t lo, uint64_t width, u
                    void* comm, uint64_t* dst);
 
 /* The connection records of one replica, in the order `Socket.log_pair` was called
- * (network_simple_overrides.py:102-120,152-186).  *n_total = records produced (may exceed the capacity kept). */
+ * (network_simple_overrides.py:102-120,152-186).  *n_total = records produced (may exceed the capacity kept).
+ * The device appends a record when it is produced and keeps, next to it, the counter value of the event that
+ * produced it; records of wake-ups retired in the delivery pass are produced early, under the value their wake-up
+ * would have had, and this call orders what the log holds by (End_Time, that value) before copying it out.     */
 int itsb_read_connections(itsb_engine* e, uint64_t replica, itsb_connection* dst, size_t cap, size_t* n_total);
 
 /* Replaces: the records itsim/logging.py + itsim/datastore would receive (README.md:18-50), reduced on the device:
