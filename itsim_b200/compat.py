@@ -129,15 +129,67 @@ class _BodyMixin:
         return self
 
 
-class Node(_BodyMixin, machine.Node):
+class Daemon:
+    """``itsim.machine.process_management.daemon.Daemon`` (daemon.py:9-27): a container for the logic run when the daemon
+    is triggered."""
+
+    def __init__(self, trigger_event: Callable[..., None]) -> None:
+        self._trigger_event = trigger_event
+
+    def trigger(self, context: Any, packet: Any, socket: Any) -> None:
+        self._trigger_event(context, packet, socket)
+
+    trigger.__itsb_inline__ = True
+
+
+def _listener(daemon: Any, protocol: Any, port: int) -> Callable:
+    """The body ``run_networking_daemon`` starts for one port (node.py:340-348).  The reference binds on the host before
+    the run and starts ``forward_recv`` on the bound socket; here the first thread binds (outside a ``with``: a socket
+    that outlives the thread), then behaves as every later one."""
+
+    def forward_recv(context: Any, socket: Any) -> None:
+        packet = socket.recv()
+        context.thread.clone(forward_recv, socket)
+        daemon.trigger(context, packet, socket)
+
+    def first(context: Any) -> None:
+        socket = context.node.bind(protocol, port)
+        forward_recv(context, socket)
+
+    forward_recv.__itsb_inline__ = True
+    first.__name__ = "forward_recv"
+    return first
+
+
+class _DaemonMixin:
+    """``Node.run_networking_daemon`` / ``networking_daemon`` (node.py:319-392)."""
+
+    def run_networking_daemon(self, sim: Simulator, daemon: Any, protocol: Any, *ports: int) -> None:
+        for port in ports:
+            self.run_proc(sim, _listener(daemon, protocol, port))
+
+    def networking_daemon(self, sim: Simulator, protocol: Any, *ports: int) -> Callable:
+        def _decorator(server_behaviour: Any) -> Any:
+            if hasattr(server_behaviour, "trigger"):
+                daemon = server_behaviour if not isinstance(server_behaviour, type) else server_behaviour()
+            elif callable(server_behaviour):
+                daemon = Daemon(server_behaviour)
+            else:
+                raise TypeError("Daemon must have trigger() or be of type Callable")
+            self.run_networking_daemon(sim, daemon, protocol, *ports)
+            return server_behaviour
+        return _decorator
+
+
+class Node(_BodyMixin, _DaemonMixin, machine.Node):
     pass
 
 
-class Endpoint(_BodyMixin, machine.Endpoint):
+class Endpoint(_BodyMixin, _DaemonMixin, machine.Endpoint):
     pass
 
 
-class Router(_BodyMixin, machine.Router):
+class Router(_BodyMixin, _DaemonMixin, machine.Router):
     pass
 
 
@@ -167,6 +219,7 @@ def _modules() -> Dict[str, types.ModuleType]:
         "itsim.machine.process_management.process": _module("itsim.machine.process_management.process", Process=Process),
         "itsim.machine.process_management.thread": _module("itsim.machine.process_management.thread",
                                                            ThreadKilled=ThreadKilled),
+        "itsim.machine.process_management.daemon": _module("itsim.machine.process_management.daemon", Daemon=Daemon),
         "itsim.network": _module("itsim.network", __path__=[]),
         "itsim.network.link": _module("itsim.network.link", Link=machine.Link, Loopback=machine.Loopback),
         "itsim.network.router": _module("itsim.network.router", Router=Router),

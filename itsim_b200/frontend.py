@@ -198,7 +198,8 @@ class Frontend:
         """Registers (f, compile-time arguments) and returns (program name, positions of the run-time arguments)."""
         rt_positions = [i for i, a in enumerate(args) if isinstance(a, Rt)]
         key = (getattr(f, "__func__", f), id(getattr(f, "__self__", None)),
-               tuple(("rt", a.kind) if isinstance(a, Rt) else ("c", id(a.v)) for a in args))
+               tuple(("rt", a.kind) if isinstance(a, Rt) else (("sym", a.what) if isinstance(a, _Sym) else ("c", id(a.v)))
+                     for a in args))
         if key not in self._programs:
             base = f.__name__
             name, k = base, 1
@@ -278,6 +279,7 @@ class _Body:
         self.loops: List[Tuple[str, str, int]] = []   # (continue label, break label, handler depth)
         self.finalizers: List[Tuple[str, Any, int]] = []   # what `return` / `break` / `continue` must run on their way out
         self.packet_gen = 0
+        self.activation = 0                       # bumped by every blocking call: packet fields do not survive one
         self.low = 0                              # registers [0, low) hold parameters (and locals in send mode)
         self.high = 4                             # registers [high, 4) hold locals (default mode)
         self.scratch_used: set = set()
@@ -486,7 +488,11 @@ class _Body:
         if len(s.items) != 1:
             raise self.err(s, "one context manager per with statement")
         item = s.items[0]
-        v = self.eval(item.context_expr, scope)
+        self._bind_in_with = True
+        try:
+            v = self.eval(item.context_expr, scope)
+        finally:
+            self._bind_in_with = False
         if not (isinstance(v, _Sym) and v.what == "socket"):
             raise self.err(s, "only `with context.node.bind(...) as socket` is supported")
         if item.optional_vars is not None:
@@ -727,8 +733,10 @@ class _Body:
         fv = self.eval(call.func, scope)
         if isinstance(fv, Const) and _intrinsic_name(fv.v) == "advance":
             return self.advance(call, scope)
-        if isinstance(fv, Const) and self.inlinable(fv.v):
-            return self.inline_call(s, fv.v, [self.eval(x, scope) for x in call.args], scope)
+        if isinstance(fv, Const) and (inspect.isfunction(fv.v) or inspect.ismethod(fv.v)):
+            args = [self.eval(x, scope) for x in call.args]
+            if self.inlinable(fv.v, args):
+                return self.inline_call(s, fv.v, args, scope)
         if isinstance(fv, _Sym) and fv.what == "method":
             self.sim_call(call, fv, scope, want_result=False)
             return
@@ -740,15 +748,21 @@ class _Body:
                 return self.host_effect(s, scope, value=rts[0][1], value_node=rts[0][0])
         raise self.err(s, "this call mixes host objects and simulation values in a way the front-end cannot split")
 
-    def inlinable(self, f: Any) -> bool:
+    def inlinable(self, f: Any, args: Sequence[Any] = ()) -> bool:
+        """A Python function is compiled in place when it takes the context first (``self._live(context, child)``), or
+        when it is handed the context, a socket or a packet (``daemon.trigger(context, packet, socket)``)."""
         if not (inspect.isfunction(f) or inspect.ismethod(f)):
             return False
         func = getattr(f, "__func__", f)
         if _intrinsic_name(func) is not None:
             return False
         mod = (getattr(func, "__module__", "") or "").split(".")[0]
+        if getattr(func, "__itsb_inline__", False):
+            return True
         if mod in ("pytest", "_pytest", "builtins", "greensim", "itsim", "itsim_b200"):
             return False
+        if any(isinstance(a, _Sym) and a.what in ("context", "socket", "packet") for a in args):
+            return True
         try:
             params = list(inspect.signature(func).parameters)
         except (TypeError, ValueError):
@@ -787,9 +801,13 @@ class _Body:
         if len(targets) != 1:
             raise self.err(s, "chained assignment")
         tgt = targets[0]
+        def is_action(fv: Any) -> bool:      # a call that emits instructions (not a read of a packet field)
+            return isinstance(fv, _Sym) and fv.what == "method" and isinstance(fv.owner, _Sym) and \
+                fv.owner.what in ("socket", "thread_self", "task_self", "node")
+
         if isinstance(tgt, ast.Name) and isinstance(s.value, ast.Call):
             fv = self.eval(s.value.func, scope)
-            if isinstance(fv, _Sym) and fv.what == "method":
+            if is_action(fv):
                 existing = scope.names.get(tgt.id)
                 rd = existing.src if isinstance(existing, Rt) and existing.src < 4 else None
                 v = self.sim_call(s.value, fv, scope, want_result=True, name=tgt.id, rd=rd, node=s)
@@ -797,7 +815,7 @@ class _Body:
                 return
         if isinstance(tgt, ast.Subscript) and isinstance(s.value, ast.Call):
             fv = self.eval(s.value.func, scope)
-            if isinstance(fv, _Sym) and fv.what == "method":
+            if is_action(fv):
                 cont, key = self.eval(tgt.value, scope), self.eval(tgt.slice, scope)
                 if not (isinstance(cont, Const) and isinstance(key, Const)):
                     raise self.err(s, "container and key must be compile-time values")
@@ -864,6 +882,7 @@ class _Body:
     def advance(self, call: ast.Call, scope: _Scope) -> None:
         if len(call.args) != 1:
             raise self.err(call, "advance(delay)")
+        self.blocked()
         arg = call.args[0]
         # advance(next(generator))
         if isinstance(arg, ast.Call) and isinstance(arg.func, ast.Name) and arg.func.id == "next" and len(arg.args) == 1:
@@ -890,13 +909,16 @@ class _Body:
         owner, attr = m.owner, m.attr
         node = node or call
         what = owner.what if isinstance(owner, _Sym) else owner.kind
+        if what == "node" and attr == "bind":
+            return self.bind(call, scope)
         if what == "socket":
             if attr == "send":
                 return self.send(call, scope)
             if attr == "recv":
                 self.a.recvt(self.timeout_const(call, scope), handler=self.handler())
                 self.packet_gen += 1
-                return _Sym("packet", gen=self.packet_gen)
+                self.blocked()
+                return _Sym("packet", gen=self.packet_gen, act=self.activation)
             if attr == "close":
                 return self.a.sclose()
             raise self.err(call, f"Socket.{attr} is not supported")
@@ -913,8 +935,10 @@ class _Body:
             src = owner.src
         kind = "thread" if what.startswith("thread") else "task"
         if attr == "join" and kind == "thread":
+            self.blocked()
             return self.a.join(src, self.timeout_const(call, scope), handler=self.handler())
         if attr == "wait" and kind == "task":
+            self.blocked()
             return self.a.pwait(src, self.timeout_const(call, scope), handler=self.handler())
         if attr == "kill":
             return (self.a.tkill if kind == "thread" else self.a.pkill)(src)
@@ -958,30 +982,88 @@ class _Body:
         fkw = dict(f0=f0, f1=f1)
         if isinstance(dest_node, ast.Tuple) and len(dest_node.elts) == 2:
             addr, port = self.eval(dest_node.elts[0], scope), self.eval(dest_node.elts[1], scope)
-            if not isinstance(port, Const):
-                raise self.err(call, "the destination port must be a compile-time value")
             size = self.eval(size_node, scope)
             if isinstance(addr, _Sym) and addr.what == "broadcast_address":
+                if not isinstance(port, Const):
+                    raise self.err(call, "the port of a broadcast is a compile-time value")
                 self.fe.single_interface_programs.add(self.name)
                 return self.a.sendl(ir.DST_BCAST, self.src_of(size_node, size, avoid=[f0, f1]), tag, port=int(port.v), **fkw)
-            if isinstance(addr, Rt):
-                self.scratch_used.update(r for r in (2, 3) if r != addr.src)
-                if addr.src != ir.R2:
-                    self.a.mov(ir.R2, addr.src)
-                self.a.li(ir.R3, int(port.v))
-                return self.a.sendl(ir.DST_REGS, self.src_of(size_node, size, avoid=[2, 3, f0, f1]), tag, **fkw)
+            if isinstance(addr, (Rt, Const)) and isinstance(port, (Rt, Const)):
+                return self.send_regs(call, addr, port, size, tag, fkw)
         dest = self.eval(dest_node, scope)
         size = self.eval(size_node, scope)
         if isinstance(dest, _Sym) and dest.what == "packet_source":
             self.need_current(dest_node, dest)
             return self.a.sendl(ir.DST_PKT_SRC, self.src_of(size_node, size, avoid=[f0, f1]), tag, **fkw)
         if isinstance(dest, Const) and isinstance(dest.v, tuple) and len(dest.v) == 2:
-            addr, port = dest.v
-            self.scratch_used.update((2, 3))
-            self.a.li(ir.R2, self.as_u32(dest_node, addr))
-            self.a.li(ir.R3, int(port))
-            return self.a.sendl(ir.DST_REGS, self.src_of(size_node, size, avoid=[2, 3, f0, f1]), tag, **fkw)
-        raise self.err(call, "destination must be packet.source or a compile-time (address, port)")
+            return self.send_regs(call, Const(dest.v[0]), Const(dest.v[1]), size, tag, fkw)
+        raise self.err(call, "destination must be packet.source or an (address, port) pair")
+
+    def is_live(self, r: int) -> bool:
+        """Register r holds a parameter or a variable of this body."""
+        return r < self.low or r >= self.high
+
+    def send_regs(self, node: ast.AST, addr: Any, port: Any, size: Any, tag: int, fkw: Dict[str, int]) -> None:
+        """SENDL with the destination in (r2, r3).  Variables living in r2 / r3, and operands that would be overwritten
+        while the pair is loaded, are parked in model variables reserved for this (nothing runs in between) and put
+        back after the send."""
+        def park(i: int, src: int) -> int:
+            slot = self.fe.gtemp(2 + i)
+            self.a.gset(slot, src)
+            return ir.G0 + slot
+
+        want = {ir.R2: addr, ir.R3: port}
+        srcs: Dict[int, Any] = {}
+        for reg, v in want.items():
+            srcs[reg] = v.src if isinstance(v, Rt) else None
+        size_src = size.src if isinstance(size, Rt) else None
+        fsrc = {k: v for k, v in fkw.items()}
+        saved: Dict[int, int] = {}
+        for i, reg in enumerate((ir.R2, ir.R3)):
+            if srcs[reg] == reg:
+                continue                                  # already in place
+            if self.is_live(reg) or any(s_ == reg for s_ in (srcs[ir.R2], srcs[ir.R3], size_src, *fsrc.values())):
+                g = park(i, reg)
+                if self.is_live(reg):
+                    saved[reg] = g
+                # operands that were read from this register are read from the parked copy instead
+                for other in (ir.R2, ir.R3):
+                    if srcs[other] == reg:
+                        srcs[other] = g
+                if size_src == reg:
+                    size_src = g
+                for k in fsrc:
+                    if fsrc[k] == reg:
+                        fsrc[k] = g
+            else:
+                self.scratch_used.add(reg)
+        for reg, v in want.items():
+            if isinstance(v, Rt):
+                if srcs[reg] != reg:
+                    self.a.mov(reg, srcs[reg])
+            else:
+                self.a.li(reg, self.as_u32(node, v.v) if reg == ir.R2 else int(v.v))
+        if size_src is None:
+            val = self.as_u32(node, size.v)
+            if val == 0:
+                size_src = ir.ZERO
+            else:
+                free = [r for r in (0, 1) if not self.is_live(r) and r not in fsrc.values()]
+                if free:
+                    self.scratch_used.add(free[0])
+                    self.a.li(free[0], val)
+                    size_src = free[0]
+                else:                                     # every register is taken: through a parked constant
+                    r = ir.R3
+                    g_port = park(2, r)
+                    self.a.li(r, val)
+                    slot = self.fe.gtemp(5)
+                    self.a.gset(slot, r)
+                    self.a.mov(r, g_port)
+                    size_src = ir.G0 + slot
+        self.a.sendl(ir.DST_REGS, size_src, tag, **fsrc)
+        for reg, g in saved.items():
+            self.a.mov(reg, g)
 
     def field_src(self, node: ast.AST, v: Any, avoid: Sequence[int] = ()) -> int:
         """Operand source of a payload field (NONE: the packet does not carry it -> 0)."""
@@ -1003,6 +1085,12 @@ class _Body:
     def need_current(self, node: ast.AST, sym: _Sym) -> None:
         if sym.gen != self.packet_gen:
             raise self.err(node, "this packet is no longer the last one received (the engine keeps one per process)")
+        if getattr(sym, "act", self.activation) != self.activation:
+            raise self.err(node, "packet fields do not survive a blocking call (advance, recv, join, wait): copy what is "
+                                 "needed into variables first (size = packet.byte_size; port = packet.source.port; ...)")
+
+    def blocked(self) -> None:
+        self.activation += 1
 
     def spawn(self, call: ast.Call, scope: _Scope, timed: bool, emit: Callable, kind: str, rd: Optional[int],
               node: ast.AST) -> Any:
@@ -1026,6 +1114,9 @@ class _Body:
             if isinstance(v, _Sym):
                 if v.what in ("task_self", "thread_self"):
                     v = Rt(ir.SELF_TASK if v.what == "task_self" else ir.SELF_THREAD, v.what.split("_")[0])
+                elif v.what == "socket":
+                    if emit != self.a.clone:
+                        raise self.err(call, "a socket can be handed to a thread of the same process (clone) only")
                 elif v.what != "context":
                     raise self.err(call, f"cannot pass a {v.what} to another body")
             vals.append(v)
@@ -1159,11 +1250,11 @@ class _Body:
             if attr == "byte_size":
                 return Rt(ir.PKT_SIZE, "int")
             if attr == "source":
-                return _Sym("packet_source", gen=base.gen)
+                return _Sym("packet_source", gen=base.gen, act=base.act)
             if attr == "dest":
-                return _Sym("packet_dest", gen=base.gen)
+                return _Sym("packet_dest", gen=base.gen, act=base.act)
             if attr == "payload":
-                return _Sym("payload", gen=base.gen)
+                return _Sym("payload", gen=base.gen, act=base.act)
         elif what == "packet_source":
             self.need_current(e, base)
             if attr == "port":
@@ -1224,7 +1315,9 @@ class _Body:
             p = 0
         if isinstance(p, (tuple, list, range)):
             raise self.err(e, "port ranges are not supported")
-        self.a.bind(int(p))
+        # outside a `with`, the socket is not closed when this thread ends: Node.run_networking_daemon binds it once and
+        # hands it from thread to thread (node.py:340-348)
+        self.a.bind(int(p), detached=not getattr(self, "_bind_in_with", False))
         return _Sym("socket")
 
     def compare(self, e: ast.Compare, scope: _Scope) -> Any:

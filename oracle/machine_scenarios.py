@@ -382,6 +382,7 @@ FRONTEND_PROGS = {
     "family": {"ancestors": 1, "life": 2},
     "lan": {"lan_server": 1, "lan_client": 2},
     "echo": {"answerer": 1, "asker": 2},
+    "daemon": {"forward_recv": 1, "caller": 2},
 }
 
 
@@ -419,6 +420,9 @@ def frontend_scenario(name: str, seed: int = 0, replica: int = 0, duration=10.0)
     elif name == "echo":
         nodes = B.build_echo(sc.sim)
         state = {"echoed": lambda: list(B.echoed), "unanswered": lambda: list(B.unanswered)}
+    elif name == "daemon":
+        nodes = B.build_daemon(sc.sim)
+        state = {"served": lambda: list(B.served)}
     else:
         raise KeyError(name)
     for n in nodes:

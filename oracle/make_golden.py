@@ -69,7 +69,8 @@ def frontend_golden() -> None:
     import machine_scenarios as ms
     out = {}
     jobs = [("ping_pong", 0, 0, 10.0), ("ping_pong", 9, 4, 10.0), ("chatter", 1, 5, 30.0), ("threads", 0, 0, None),
-            ("family", 0, 0, 4000.0), ("lan", 2, 3, 15.0), ("echo", 0, 0, 10.0), ("echo", 6, 21, 10.0)]
+            ("family", 0, 0, 4000.0), ("lan", 2, 3, 15.0), ("echo", 0, 0, 10.0), ("echo", 6, 21, 10.0),
+            ("daemon", 0, 0, 10.0), ("daemon", 11, 2, 10.0)]
     for name, seed, replica, duration in jobs:
         arr, summary = ms.frontend_scenario(name, seed, replica, duration)
         tag = f"{name}_s{seed}_r{replica}"

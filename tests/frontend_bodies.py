@@ -284,3 +284,39 @@ def build_echo(sim):
         ep.run_proc_in(sim, 0.05 * n, asker, 100 * (n + 1))
         nodes.append(ep)
     return nodes
+
+
+# ---- a networking daemon (Node.networking_daemon, node.py:350-392) answering on two ports (golden: frontend_daemon_*.npz)
+served = []
+
+
+def build_daemon(sim):
+    link = Link("10.6.0.0/24", latency=uniform(20 * MS, 80 * MS), bandwidth=constant(10 * MbPS))
+    server = Endpoint().connected_to_static(link, "10.6.0.2")
+
+    @server.networking_daemon(sim, Protocol.UDP, 7, 9)
+    def echo(context, packet, socket):
+        size = packet.byte_size              # what is needed after the advance() is copied out of the packet first
+        addr = packet.source.hostname_as_address()
+        port = packet.source.port
+        served.append(size)
+        if packet.payload["content"] == "loud":
+            advance(0.5 * S)                 # requests overlap: every packet is served by a thread of its own
+        socket.send((addr, port), size, {"content": "echo"})
+
+    nodes = [server]
+    for n in range(2):
+        ep = Endpoint().connected_to_static(link, as_address(20 + n, link.cidr))
+        ep.run_proc_in(sim, 0.1 * (n + 1), caller, 7 + 2 * n, 32 * (n + 1))
+        nodes.append(ep)
+    return nodes
+
+
+def caller(context, port, size):
+    with context.node.bind(Protocol.UDP) as sock:
+        for content in ("loud", "quiet", "loud"):
+            sock.send(("10.6.0.2", port), size, {"content": content})
+            advance(0.2 * S)
+        for _ in range(3):
+            answer = sock.recv(3 * S)
+            assert answer.byte_size == size

@@ -42,6 +42,13 @@ def stale_packet(context):
         sock.send(one.source, 8)
 
 
+def packet_after_blocking(context):
+    with context.node.bind(Protocol.UDP, 99) as sock:
+        packet = sock.recv()
+        advance(1)
+        sock.send(packet.source, 8)
+
+
 def rich_payload(context):
     with context.node.bind(Protocol.UDP) as sock:
         sock.send(("10.0.0.1", 5), 8, {"content": "x", "blob": [1, 2, 3]})
@@ -61,6 +68,7 @@ REFUSED = [
     (clock_in_arithmetic, "now()"),
     (loop_over_packets, "mixes simulation values"),
     (stale_packet, "no longer the last one received"),
+    (packet_after_blocking, "do not survive a blocking call"),
     (rich_payload, "payload keys"),
     (new_exception, "raising a new exception"),
     (generator_body, "not supported"),

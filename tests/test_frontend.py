@@ -96,6 +96,10 @@ def scenario(name, lib, seed=0, replica=0):
             sim.frontend.program_ids.update(answerer=1, asker=2)
             B.build_echo(sim)
             marks = {}
+        elif name == "daemon":
+            sim.frontend.program_ids.update(forward_recv=1, caller=2)
+            B.build_daemon(sim)
+            marks = {}
         else:
             raise KeyError(name)
         return sim, B, marks
@@ -154,7 +158,7 @@ def test_compiled_bodies_give_the_reference_traces_on_the_gpu(name, golden, seed
 # `python oracle/make_golden.py --frontend`): trace and the host-side state the bodies leave behind.
 SAME_FILE = [("packet_transfer", "ping_pong_s0_r0"), ("packet_transfer", "ping_pong_s9_r4"), ("broadcast", "chatter_s1_r5"),
              ("thread_lifecycle", "threads_s0_r0"), ("process_lifecycle", "family_s0_r0"), ("large_lan", "lan_s2_r3"),
-             ("echo", "echo_s0_r0"), ("echo", "echo_s6_r21")]
+             ("echo", "echo_s0_r0"), ("echo", "echo_s6_r21"), ("daemon", "daemon_s0_r0"), ("daemon", "daemon_s11_r2")]
 
 
 def check_same_file(name, tag, lib):
@@ -179,6 +183,8 @@ def check_same_file(name, tag, lib):
         assert sorted(B.graves) == state["graves"]
     elif name == "echo":
         assert B.echoed == state["echoed"] and B.unanswered == state["unanswered"]
+    elif name == "daemon":
+        assert B.served == state["served"] and len(B.served) == 6
     sim._engine.close()
 
 
