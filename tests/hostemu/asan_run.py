@@ -27,6 +27,8 @@ run("network_simple traced", netsimple.build(trace_records=60000), 1, 600.0)
 run("network_simple tiny pool", netsimple.build(), 1, 900.0, max_events=16)
 run("network_simple plain loops", netsimple.build(fused=False), 1, 600.0)
 run("full logging", netsimple.build(connection_records=20000), 1, 900.0, net_event_records=4096)
+run("full logging, plain receive loops", netsimple.build(connection_records=20000, fused=False), 1, 900.0,
+    net_event_records=4096)
 run("full logging, window 1, logs overflowing", netsimple.build(connection_records=200, connection_window=1), 1, 900.0,
     net_event_records=16)
 run("malware", netsimple.build_malware(), 2, 600.0)
