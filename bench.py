@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "simulated events/sec (batched network_simple replicas)"
 # ncu --set full capture committed under profiles/: (dram__bytes_read.sum + dram__bytes_write.sum) / replicas
-NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH = (328.5e6 + 160.7e6) / 6000.0
+NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH = (328.9e6 + 160.1e6) / 6000.0
 UNIT = "events/s"
 RESULT_OUT = sys.stdout
 
