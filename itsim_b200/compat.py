@@ -83,6 +83,7 @@ class Simulator(model.Simulator):
         self._replayed = 0
         self.caps.update(max_events=64, max_procs=128, max_sockets=64, arena_nodes=2048, trace_records=1 << 16,
                          max_threads=64, max_tasks=64, max_signals=256)
+        self._default_caps = dict(self.caps)
 
     def compile(self) -> model.Compiled:
         procs = self._machine_procs
@@ -90,12 +91,24 @@ class Simulator(model.Simulator):
             if callable(program):
                 name, values = self.frontend.program(program, regs)
                 procs[i] = (node, delay, name, tuple(values))
+        self._size_capacities(len(procs))
         for node, _, name, _ in procs:
             if name in self.frontend.single_interface_programs and \
                     sum(1 for i in node.interfaces() if not i.address.is_loopback) != 1:
                 raise frontend.CompileError(f"{name}: `for interface in context.node.interfaces()` is compiled for "
                                             f"nodes with one non-loopback interface")
         return super().compile()
+
+    def _size_capacities(self, started: int) -> None:
+        """The per-replica tables are fixed-size; the reference's are Python containers.  Capacities a script did not
+        set itself grow with the number of processes the model starts (each may hold a socket, block in a ``recv`` with
+        its two ``select`` helpers, and have packets queued); exceeding one still fails loudly (``ITSB_ERR_CAP_*``)."""
+        wanted = dict(max_events=started + 64, max_procs=4 * started + 64, max_sockets=2 * started + 16,
+                      arena_nodes=64 * started, max_threads=2 * started + 16, max_tasks=2 * started + 16,
+                      max_signals=min(0x3FFF, 9 * started + 64))
+        for key, value in wanted.items():
+            if self.caps[key] == self._default_caps[key] and value > self.caps[key]:
+                self.caps[key] = value
 
     def run(self, duration: float = INF, seed: Optional[int] = None) -> None:
         if self._engine is None:

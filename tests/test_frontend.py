@@ -88,10 +88,7 @@ def scenario(name, lib, seed=0, replica=0):
         elif name == "large_lan":
             sim.frontend.program_ids.update(lan_server=1, lan_client=2)
             B.build_lan(sim, 4, 16, compat.per_process, lambda: compat.Router(forwarding=True))
-            n_ep = 64
-            sim.caps.update(max_events=n_ep + 64, max_procs=4 * n_ep + 64, max_sockets=2 * n_ep + 16, arena_nodes=64 * n_ep,
-                            max_threads=2 * n_ep + 16, max_tasks=2 * n_ep + 16, max_signals=9 * n_ep + 64)
-            marks = {}
+            marks = {}            # 128 processes: the capacities are sized by compat.Simulator itself
         elif name == "echo":
             sim.frontend.program_ids.update(answerer=1, asker=2)
             B.build_echo(sim)
