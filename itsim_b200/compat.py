@@ -103,9 +103,10 @@ class Simulator(model.Simulator):
         """The per-replica tables are fixed-size; the reference's are Python containers.  Capacities a script did not
         set itself grow with the number of processes the model starts (each may hold a socket, block in a ``recv`` with
         its two ``select`` helpers, and have packets queued); exceeding one still fails loudly (``ITSB_ERR_CAP_*``)."""
-        wanted = dict(max_events=started + 64, max_procs=4 * started + 64, max_sockets=2 * started + 16,
-                      arena_nodes=64 * started, max_threads=2 * started + 16, max_tasks=2 * started + 16,
-                      max_signals=min(0x3FFF, 9 * started + 64))
+        wanted = dict(max_events=min(65535, started + 64), max_procs=min(8192, 2 * started + 64),
+                      max_sockets=min(0x3FFF, started + 16), arena_nodes=32 * started,
+                      max_threads=min(0xFFFE, started + 16), max_tasks=min(0xFFFE, started + 16),
+                      max_signals=min(0x3FFF, 5 * started + 64))
         for key, value in wanted.items():
             if self.caps[key] == self._default_caps[key] and value > self.caps[key]:
                 self.caps[key] = value

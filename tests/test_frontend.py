@@ -207,6 +207,35 @@ def test_goldens_are_what_the_reference_produces_now():
         assert json.load(fh)["echo_s6_r21"]["state"] == out["state"]
 
 
+@pytest.mark.parametrize("backend", [pytest.param("hostemu", id="hostemu"),
+                                     pytest.param("gpu", id="gpu", marks=pytest.mark.gpu)])
+def test_config_c4_compiled_from_python_equals_the_assembled_model(backend, hostemu):
+    """The 1 024-endpoint LAN (BASELINE config 4) with its two bodies compiled from tests/frontend_bodies.py -- one
+    program for all 1 024 clients, the peer address a per-process argument -- against machine_models.large_lan, whose
+    bodies are written with the assembler: every counter of every replica."""
+    from itsim_b200 import compat, machine_models
+    lib = hostemu if backend == "hostemu" else None
+    n, horizon = (2, 5.0) if backend == "hostemu" else (12, 6.0)
+    with compat.installed(lib):
+        B = load_bodies()
+        sim = compat.Simulator()
+        sim.frontend.program_ids.update(lan_server=1, lan_client=2)
+        B.build_lan(sim, 16, 64, compat.per_process, lambda: compat.Router(forwarding=True))
+        sim.caps["trace_records"] = 0
+        compiled = sim.run_replicas(n, seed=4, first_replica_id=30)
+        events = compiled.run(horizon)
+    assert [name for name, _ in sim.asm.entries] == ["lan_server", "lan_client", "__balk", "__wait_one"]
+    ref = machine_models.large_lan()
+    ref._lib = lib
+    assembled = ref.run_replicas(n, seed=4, first_replica_id=30)
+    assert assembled.run(horizon) == events > 20000 * n
+    for r in range(n):
+        assert np.array_equal(compiled.replica_telemetry(r), assembled.replica_telemetry(r)), r
+    assert compiled.state_bytes()["hot"] > 232448          # the in-place kernel's territory
+    compiled.close()
+    assembled.close()
+
+
 @pytest.mark.gpu
 def test_compiled_bodies_batched_on_the_gpu_match_the_host_emulation(hostemu):
     """The batched entry on a compiled model: 64 replicas of the chatter scenario, every counter of every replica."""
