@@ -43,10 +43,13 @@ def _rank_main(rank, world, port, n_total, horizon, out):
     events = eng.run(horizon)
     tm = torch.from_numpy(eng.telemetry().astype(np.int64))
     dist.all_reduce(tm, op=dist.ReduceOp.SUM)
+    # the per-replica histogram of config 3 (itsb_histogram): each rank bins its shard, the bins are summed
+    hist = torch.from_numpy(eng.histogram(_lib.tm_user(netsimple.STAT_QUERIES), 0, 2, 32).astype(np.int64))
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM)
     ev = torch.tensor([events], dtype=torch.int64)
     dist.all_reduce(ev, op=dist.ReduceOp.SUM)
     if rank == 0:
-        out.put((tm.numpy().astype(np.uint64), int(ev.item())))
+        out.put((tm.numpy().astype(np.uint64), int(ev.item()), hist.numpy().astype(np.uint64)))
     dist.destroy_process_group()
 
 
@@ -62,7 +65,7 @@ def test_two_ranks_equal_one(built, hostemu):
     procs = [ctx.Process(target=_rank_main, args=(r, 2, port, n_total, horizon, out)) for r in range(2)]
     for p in procs:
         p.start()
-    total, events = out.get(timeout=180)
+    total, events, hist = out.get(timeout=180)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -71,3 +74,6 @@ def test_two_ranks_equal_one(built, hostemu):
     eng = sim.run_replicas(n_total, seed=9)
     assert eng.run(horizon) == events
     assert np.array_equal(eng.telemetry(), total)
+    from itsim_b200 import _lib as L
+    whole = eng.histogram(L.tm_user(netsimple.STAT_QUERIES), 0, 2, 32)
+    assert np.array_equal(whole, hist) and int(hist.sum()) == n_total
