@@ -131,6 +131,8 @@ class Frontend:
         self._keepalive: List[Any] = []
         self._next_prog = 1
         self._gtemps = 0
+        self._mutated: Dict[int, str] = {}           # id of a host object -> the statement of a body that modifies it
+        self._steering: Dict[int, Tuple[str, str]] = {}   # id of a host object read at compile time -> (where, text)
         self.single_interface_programs: set = set()     # programs that use the "every non-loopback interface" idiom
 
     # -- public ----------------------------------------------------------------------------------------------------
@@ -221,6 +223,16 @@ class Frontend:
         while self._queue:
             name, f, args, prog_id = self._queue.pop(0)
             _Body(self, name, f, args, prog_id).compile()
+        self.check_host_state()
+
+    def check_host_state(self) -> None:
+        """Host objects the bodies modify (``ledger.add(...)``, at replay) must not also steer the compilation
+        (``if len(ledger) > 3:`` would be decided once, here, on the object as it is now): that would be a silent
+        difference from the reference, where the body sees the live object."""
+        for obj_id, (where, text) in self._steering.items():
+            if obj_id in self._mutated:
+                raise CompileError(f"{where}: `{text}` reads a host object that {self._mutated[obj_id]} modifies while the "
+                                   f"simulation runs; host state changed by a body cannot steer the simulation")
 
     def gtemp(self, i: int) -> int:
         self._gtemps = max(self._gtemps, i + 1)
@@ -578,6 +590,7 @@ class _Body:
         self.a.label(top)
         cond = self.eval(s.test, scope)
         if isinstance(cond, Const):
+            self.note_steering(s.test, scope)
             if not cond.v:
                 return
         else:
@@ -592,6 +605,7 @@ class _Body:
         it = self.eval(s.iter, scope)
         if not isinstance(it, Const):
             raise self.err(s, "a for loop in a body iterates over compile-time values (it is unrolled)")
+        self.note_steering(s.iter, scope)
         if s.orelse:
             raise self.err(s, "for ... else")
         end = self.label("for_end")
@@ -607,6 +621,7 @@ class _Body:
     def if_(self, s: ast.If, scope: _Scope) -> None:
         cond = self.eval(s.test, scope)
         if isinstance(cond, Const):
+            self.note_steering(s.test, scope)
             return self.block(s.body if cond.v else s.orelse, scope)
         other, end = self.label("else"), self.label("endif")
         self.branch_unless(s.test, cond, other)
@@ -691,8 +706,45 @@ class _Body:
                 env[k] = v.v
         return env
 
+    @staticmethod
+    def _is_mutable(obj: Any) -> bool:
+        if isinstance(obj, (list, set, dict, bytearray)):
+            return True
+        return hasattr(obj, "__dict__") and not isinstance(obj, (type, type(ast), type(len))) and \
+            not inspect.isfunction(obj) and not inspect.ismethod(obj)
+
+    def note_mutation(self, s: ast.stmt, scope: _Scope) -> None:
+        """The receiver of a method call statement, and the mutable arguments of a plain call, are what the statement
+        may modify."""
+        call = s.value if isinstance(s, ast.Expr) and isinstance(s.value, ast.Call) else None
+        if call is None:
+            return
+        targets = [call.func.value] if isinstance(call.func, ast.Attribute) else list(call.args)
+        for t in targets:
+            try:
+                v = self.eval(t, scope)
+            except CompileError:
+                continue
+            if isinstance(v, Const) and self._is_mutable(v.v):
+                self.fe._mutated.setdefault(id(v.v), f"`{ast.unparse(s)}` ({self.f.__name__}, line {s.lineno})")
+                self.fe._keepalive.append(v.v)
+
+    def note_steering(self, e: ast.AST, scope: _Scope) -> None:
+        """Every host object a compile-time decision looks at."""
+        for n in ast.walk(e):
+            if isinstance(n, (ast.Name, ast.Attribute, ast.Subscript)):
+                try:
+                    v = self.eval(n, scope)
+                except Exception:
+                    continue
+                if isinstance(v, Const) and self._is_mutable(v.v):
+                    self.fe._steering.setdefault(id(v.v), (f"{self.f.__name__}, line {getattr(e, 'lineno', '?')}",
+                                                           ast.unparse(e)))
+                    self.fe._keepalive.append(v.v)
+
     def host_effect(self, s: ast.stmt, scope: _Scope, value: Optional[Rt] = None, value_node: Optional[ast.AST] = None) -> None:
         """Lifts statement ``s`` to the host: a MARK now, the statement itself at replay."""
+        self.note_mutation(s, scope)
 
         class Rewrite(ast.NodeTransformer):
             def visit(self_inner, n: ast.AST) -> ast.AST:      # noqa: N805

@@ -59,6 +59,18 @@ def new_exception(context):
     raise RuntimeError("boom")
 
 
+tally = []
+
+
+def host_state_steers(context):
+    with context.node.bind(Protocol.UDP, 99) as sock:
+        while True:
+            sock.recv()
+            tally.append(1)
+            if len(tally) > 3:          # the reference sees the live list; a compiled body would decide this once
+                break
+
+
 def generator_body(context):
     yield 1
 
@@ -71,5 +83,6 @@ REFUSED = [
     (packet_after_blocking, "do not survive a blocking call"),
     (rich_payload, "payload keys"),
     (new_exception, "raising a new exception"),
+    (host_state_steers, "cannot steer the simulation"),
     (generator_body, "not supported"),
 ]
