@@ -28,6 +28,7 @@
 extern "C" __global__ void k_run_in_place(const RunParams p);   /* itsb_inplace.cu */
 extern "C" __global__ void k_run_wide(const RunParams p);       /* itsb_wide.cu: 13..16 warps per CTA */
 extern "C" __global__ void k_run_phased(const RunParams p);     /* itsb_phased.cu: warps aligned on the loop's two halves */
+extern "C" __global__ void k_run_lanes(const RunParams p);      /* itsb_lanes.cu: experiment, a replica per lane */
 
 /* up to 12 warps per CTA (what shared memory allows the flagship model): 168 registers per thread, no spills */
 extern "C" __global__ void __launch_bounds__(384, 1) k_run(const RunParams p) {
@@ -108,6 +109,7 @@ struct itsb_engine {
     size_t smem_bytes = 0;
     bool run_pending = false;
     bool phased = false;                          /* ITSB_PHASED=1: k_run_phased instead of k_run (A/B switch) */
+    int lanes = 0;                                /* ITSB_LANES=n: k_run_lanes with n CTAs of 256 threads per SM (experiment) */
     float last_ms = 0.f;
     long long first_failed = -1;
     std::string err;
@@ -216,6 +218,7 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     e->warps_per_cta = w;
     e->rp.warps_per_cta = w;
     { const char* ph = getenv("ITSB_PHASED"); e->phased = ph && ph[0] == '1'; }
+    { const char* ln = getenv("ITSB_LANES"); e->lanes = ln ? atoi(ln) : 0; if (e->lanes < 0 || e->lanes > 8) e->lanes = 0; }
     e->grid = (uint32_t)e->prop.multiProcessorCount;
     CU(e, cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     CU(e, cudaFuncSetAttribute(k_run_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
@@ -281,7 +284,9 @@ int itsb_run_async(itsb_engine* e, double duration) {
     CU(e, cudaMemsetAsync(e->d_ticket, 0, sizeof(unsigned long long), e->stream));
     e->rp.duration = duration;
     if (!e->run_pending) CU(e, cudaEventRecord(e->ev_start, e->stream));
-    if (e->rp.state_in_hbm) k_run_in_place<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
+    if (e->lanes && !e->rp.tables_in_hbm)
+        k_run_lanes<<<e->grid * (uint32_t)e->lanes, 256, e->so.total, e->stream>>>(e->rp);
+    else if (e->rp.state_in_hbm) k_run_in_place<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
     else if (e->warps_per_cta > 12) k_run_wide<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
     else if (e->phased) k_run_phased<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
     else k_run<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);

@@ -35,7 +35,13 @@
 #include "../../include/itsb.h"
 #include "itsb_ir.h"
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && defined(ITSB_LANES)
+/* a replica per LANE (itsb_lanes.cu): the width-1 form of the engine -- what the host emulation compiles -- as device
+ * code.  Every "warp primitive" is the identity; 32 replicas share a warp's instruction stream and diverge freely. */
+#define ITSB_W 1
+#define ITSB_FN __device__ __forceinline__
+#define ITSB_COLD static __device__ __noinline__
+#elif defined(__CUDACC__)
 #define ITSB_W 32
 #define ITSB_FN __device__ __forceinline__
 #define ITSB_COLD static __device__ __noinline__
@@ -77,7 +83,21 @@ static const u64 T_EMPTY = 0x7FF0000000000000ull; /* +inf: empty event slot */
 static const u32 NQ_CAP = 128;                    /* now-queue ring entries (power of two) */
 
 /* ---- warp primitives (trivial when ITSB_W == 1) --------------------------------------------------------------- */
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && defined(ITSB_LANES)
+ITSB_FN int lane_id() { return 0; }
+ITSB_FN u32 w_ballot(bool p) { return p ? 1u : 0u; }
+ITSB_FN u32 w_shfl(u32 v, int) { return v; }
+ITSB_FN u32 w_min(u32 v) { return v; }
+ITSB_FN void w_sync() {}
+ITSB_FN u32 w_excl_scan(u32 v, u32* total) { *total = v; return 0; }
+ITSB_FN u32 lanemask_lt() { return 0; }
+ITSB_FN int popc(u32 v) { return __popc(v); }
+ITSB_FN int ffs32(u32 v) { return __ffs(v); }
+ITSB_FN u64 dbits(double d) { return (u64)__double_as_longlong(d); }
+ITSB_FN double bitsd(u64 b) { return __longlong_as_double((long long)b); }
+ITSB_FN u32 mulhi32(u32 a, u32 b) { return __umulhi(a, b); }
+ITSB_FN u32 clz32(u32 v) { return (u32)__clz((int)v); }
+#elif defined(__CUDACC__)
 ITSB_FN int lane_id() { return (int)(threadIdx.x & 31); }
 ITSB_FN u32 w_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
 ITSB_FN u32 w_shfl(u32 v, int src) { return __shfl_sync(0xFFFFFFFFu, v, src); }
