@@ -29,6 +29,7 @@ extern "C" __global__ void k_run_in_place(const RunParams p);   /* itsb_inplace.
 extern "C" __global__ void k_run_wide(const RunParams p);       /* itsb_wide.cu: 13..16 warps per CTA */
 extern "C" __global__ void k_run_phased(const RunParams p);     /* itsb_phased.cu: warps aligned on the loop's two halves */
 extern "C" __global__ void k_run_lanes(const RunParams p);      /* itsb_lanes.cu: experiment, a replica per lane */
+extern "C" __global__ void k_run_sorted(const RunParams p);     /* itsb_sorted.cu: experiment, lanes regrouped by next event */
 
 /* up to 12 warps per CTA (what shared memory allows the flagship model): 168 registers per thread, no spills */
 extern "C" __global__ void __launch_bounds__(384, 1) k_run(const RunParams p) {
@@ -110,6 +111,7 @@ struct itsb_engine {
     bool run_pending = false;
     bool phased = false;                          /* ITSB_PHASED=1: k_run_phased instead of k_run (A/B switch) */
     int lanes = 0;                                /* ITSB_LANES=n: k_run_lanes with n CTAs of 256 threads per SM (experiment) */
+    int sorted = 0;                               /* ITSB_SORTED=n: k_run_sorted with n CTAs of 256 threads per SM (experiment) */
     float last_ms = 0.f;
     long long first_failed = -1;
     std::string err;
@@ -219,6 +221,7 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     e->rp.warps_per_cta = w;
     { const char* ph = getenv("ITSB_PHASED"); e->phased = ph && ph[0] == '1'; }
     { const char* ln = getenv("ITSB_LANES"); e->lanes = ln ? atoi(ln) : 0; if (e->lanes < 0 || e->lanes > 8) e->lanes = 0; }
+    { const char* so = getenv("ITSB_SORTED"); e->sorted = so ? atoi(so) : 0; if (e->sorted < 0 || e->sorted > 8) e->sorted = 0; }
     e->grid = (uint32_t)e->prop.multiProcessorCount;
     CU(e, cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     CU(e, cudaFuncSetAttribute(k_run_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
@@ -284,7 +287,10 @@ int itsb_run_async(itsb_engine* e, double duration) {
     CU(e, cudaMemsetAsync(e->d_ticket, 0, sizeof(unsigned long long), e->stream));
     e->rp.duration = duration;
     if (!e->run_pending) CU(e, cudaEventRecord(e->ev_start, e->stream));
-    if (e->lanes && !e->rp.tables_in_hbm)
+    if (e->sorted && !e->rp.tables_in_hbm)
+        k_run_sorted<<<e->grid * (uint32_t)e->sorted, 256,
+                       e->so.total + 256 * (sizeof(PendingEvent) + sizeof(RunCtx) + 2 + 1 + 4) + 64, e->stream>>>(e->rp);
+    else if (e->lanes && !e->rp.tables_in_hbm)
         k_run_lanes<<<e->grid * (uint32_t)e->lanes, 256, e->so.total, e->stream>>>(e->rp);
     else if (e->rp.state_in_hbm) k_run_in_place<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
     else if (e->warps_per_cta > 12) k_run_wide<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);

@@ -1725,6 +1725,85 @@ ITSB_FN bool run_pop(Rep& R, const RunCtx& C, u32& runnable) {
 
 ITSB_FN u64 run_events(Rep& R, const RunCtx& C) { return C.active ? events_counted(R) - C.events_before : 0; }
 
+/* ---- the loop cut at the pop, for the kernel that sorts replicas by what they do next (itsb_sorted.cu) ---------------
+ * run_replica == run_begin; while (run_take(ev)) run_handle(ev).  The event is taken from the queue first and handled in
+ * a later step; nothing touches the replica in between, so the order of everything inside it is the original one. */
+struct PendingEvent { u64 tb; u32 seq; u32 data; };
+
+/* Takes the next event (or ends the run: stop event / empty heap).  Returns false when this run() is over. */
+ITSB_FN bool run_take(Rep& R, const RunCtx& C, PendingEvent& E) {
+    Hdr* H = R.hdr;
+    if (!C.active || H->status != 0) return false;
+    u64 tb; u32 seq;
+    const int src = ev_peek(R, tb, seq);
+    if (src == SRC_NONE_LEFT && !C.finite) return false;
+    if (src == SRC_NONE_LEFT || tb > C.t_stop_bits || (tb == C.t_stop_bits && seq > C.stop_seq)) {
+        H->now = C.t_stop;
+        count_event(R, ITSB_EV_STOP, 0, 0, 0);
+        return false;
+    }
+    E.data = ev_take(R, src);
+    E.tb = tb;
+    E.seq = seq;
+    return true;
+}
+
+/* What the pending event does (the body of run_pop after the pop), including the activation it leads to. */
+ITSB_FN void run_handle(Rep& R, const PendingEvent& E) {
+    Hdr* H = R.hdr;
+    const u32 data = E.data;
+    H->now = bitsd(E.tb);
+    H->cur_seq = E.seq;
+    const u32 kind = ev_kind(data), idx = ev_idx(data);
+    u32 runnable = NIL32, deliver = NIL32;
+    if (kind == ITSB_EV_DELIVER) {
+        deliver = ev_pkt(data);
+    } else if (kind == ITSB_EV_WAKE || kind == ITSB_EV_TIMER || kind == ITSB_EV_PROC_START) {
+        Pcb& P = R.pcb[idx];
+        bool live = P.state != PS_FREE && P.gen == ev_gen(data);
+        if (live) {
+            if (kind == ITSB_EV_TIMER) {
+                live = P.state == PS_TIMER && (u32)(P.timer_tok & 0xFF) == ev_exc(data);
+                if (live) { P.timer_ev = NIL16; P.pc += 1; }
+            } else if (kind == ITSB_EV_WAKE) {
+                live = P.state == PS_RESUMING;
+            } else {
+                live = P.state == PS_UNSTARTED;
+            }
+        }
+        if (live) {
+            if (!is_hidden_prog(P.prog)) count_event(R, kind, P.prog, P.node, 0);
+            runnable = idx;
+        }
+    } else if (kind == ITSB_EV_TX_BEGIN) {
+        on_tx_begin(H, ev_pkt(data));
+    } else if (kind == ITSB_EV_TX_END) {
+        if (on_tx_end(H, ev_pkt(data))) deliver = ev_pkt(data);
+    } else if (kind == ITSB_EV_THROW) {
+        Pcb& P = R.pcb[idx];
+        if (P.state != PS_FREE && P.gen == ev_gen(data)) {
+            if (!is_hidden_prog(P.prog) && !(ev_exc(data) & EXC_HIDDEN))
+                count_event(R, ITSB_EV_THROW, P.prog, P.node, ev_exc(data));
+            if (P.state == PS_UNSTARTED) proc_exit(H, idx);
+            else runnable = deliver_exception(H, idx, ev_exc(data));
+        }
+    } else {
+        fail(H, ITSB_ERR_BAD_OPCODE, data);
+    }
+    if (deliver != NIL32) on_deliver(R, deliver);
+    if (runnable != NIL32) run_process(R, runnable);
+}
+
+/* The key replicas are grouped by: the kind of the pending event, and for events that activate a process its program
+ * (the handler, then the interpreter, run the same code for equal keys most of the time). */
+ITSB_FN u32 pending_key(Rep& R, const PendingEvent& E) {
+    const u32 kind = ev_kind(E.data);
+    u32 prog = 0;
+    if (kind == ITSB_EV_WAKE || kind == ITSB_EV_TIMER || kind == ITSB_EV_PROC_START || kind == ITSB_EV_THROW)
+        prog = R.pcb[ev_idx(E.data)].prog & 15u;
+    return (kind << 4) | prog;      /* < 256 */
+}
+
 /* ---- connection records (overrides.py:102-120,152-186) ------------------------------------------------------------------
  * The override-path Socket files every packet it sends under its destination Location and every packet it receives
  * under its source Location, and logs a record when the two halves of a pair meet, when an unanswered outbound
