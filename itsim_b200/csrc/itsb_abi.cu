@@ -29,6 +29,7 @@ extern "C" __global__ void k_run_in_place(const RunParams p);   /* itsb_inplace.
 extern "C" __global__ void k_run_wide(const RunParams p);       /* itsb_wide.cu: 13..16 warps per CTA */
 extern "C" __global__ void k_run_phased(const RunParams p);     /* itsb_phased.cu: warps aligned on the loop's two halves */
 extern "C" __global__ void k_run_lanes(const RunParams p);      /* itsb_lanes.cu: experiment, a replica per lane */
+extern "C" __global__ void k_run_vote(const RunParams p);       /* itsb_lanes.cu: experiment, lanes + per-warp majority key */
 extern "C" __global__ void k_run_sorted(const RunParams p);     /* itsb_sorted.cu: experiment, lanes regrouped by next event */
 
 /* up to 12 warps per CTA (what shared memory allows the flagship model): 168 registers per thread, no spills */
@@ -220,7 +221,7 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     e->warps_per_cta = w;
     e->rp.warps_per_cta = w;
     { const char* ph = getenv("ITSB_PHASED"); e->phased = ph && ph[0] == '1'; }
-    { const char* ln = getenv("ITSB_LANES"); e->lanes = ln ? atoi(ln) : 0; if (e->lanes < 0 || e->lanes > 8) e->lanes = 0; }
+    { const char* ln = getenv("ITSB_LANES"); e->lanes = ln ? atoi(ln) : 0; if (e->lanes < -8 || e->lanes > 8) e->lanes = 0; }
     { const char* so = getenv("ITSB_SORTED"); e->sorted = so ? atoi(so) : 0; if (e->sorted < 0 || e->sorted > 8) e->sorted = 0; }
     e->grid = (uint32_t)e->prop.multiProcessorCount;
     CU(e, cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
@@ -290,8 +291,10 @@ int itsb_run_async(itsb_engine* e, double duration) {
     if (e->sorted && !e->rp.tables_in_hbm)
         k_run_sorted<<<e->grid * (uint32_t)e->sorted, 256,
                        e->so.total + 256 * (sizeof(PendingEvent) + sizeof(RunCtx) + 2 + 1 + 4) + 64, e->stream>>>(e->rp);
-    else if (e->lanes && !e->rp.tables_in_hbm)
+    else if (e->lanes > 0 && !e->rp.tables_in_hbm)
         k_run_lanes<<<e->grid * (uint32_t)e->lanes, 256, e->so.total, e->stream>>>(e->rp);
+    else if (e->lanes < 0 && !e->rp.tables_in_hbm)
+        k_run_vote<<<e->grid * (uint32_t)(-e->lanes), 256, e->so.total, e->stream>>>(e->rp);
     else if (e->rp.state_in_hbm) k_run_in_place<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
     else if (e->warps_per_cta > 12) k_run_wide<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
     else if (e->phased) k_run_phased<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
