@@ -31,8 +31,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "simulated events/sec (batched network_simple replicas)"
-# ncu --set full capture committed under profiles/: (dram__bytes_read.sum + dram__bytes_write.sum) / replicas
-NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH = (328.9e6 + 160.1e6) / 6000.0
+# ncu --set full captures committed under profiles/ (6000 replicas x 60 simulated s, one launch):
+# (dram__bytes_read.sum + dram__bytes_write.sum) / replicas, per engine kernel
+NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH = {"k_run": (328.9e6 + 160.1e6) / 6000.0, "k_run_vote": None}
 UNIT = "events/s"
 RESULT_OUT = sys.stdout
 
@@ -274,6 +275,7 @@ def main() -> None:
     engine = sim.run_replicas(args.replicas, seed=args.seed, first_replica_id=rank * args.replicas, device=local_rank)
     t_cold = time.perf_counter() - t_cold0
     state = engine.state_bytes()
+    kernel = engine.kernel_name()
     h2d_model = sum(b.nbytes for b in engine.compiled.blobs())
 
     spin_events = engine.run(args.spinup) if args.spinup > 0 else 0
@@ -416,14 +418,14 @@ def main() -> None:
             "gpu_launches": launches_dev,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH * args.replicas, "peak_source": peak_src, "kernel": "k_run",
-                "traffic_note": "dram__bytes_read+write of one k_run launch from profiles/r1_k_run_ncu_full.txt "
-                                "(6000 replicas x 60 simulated s: 4.89e8 B vs 2.27e8 B algorithmic), scaled per replica",
+                "traffic": (NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH.get(kernel) or 0) * args.replicas or None,
+                "peak_source": peak_src, "kernel": kernel,
+                "traffic_note": "dram__bytes_read+write of one launch of this kernel from the ncu --set full capture under "
+                                "profiles/ (6000 replicas x 60 simulated s), scaled per replica",
                 "algorithmic_bytes_per_launch": algo_bytes,
-                "note": "algorithmic bytes = per-replica state staged HBM->smem->HBM once per run (S_in+S_out); the "
-                        "kernel is not HBM-bound: its measured limiter is instruction supply (ncu: GPC-level "
-                        "instruction-cache requests at 91% of peak in every configuration tried, launch time "
-                        "proportional to their count; profiles/README.md)",
+                "note": "algorithmic bytes = per-replica state read and written once per run (S_in+S_out, SURVEY 8-d); "
+                        "neither engine kernel is HBM-bound: the measured limiter is instruction supply (ncu: "
+                        "GPC-level instruction-cache requests at 78-93% of peak; profiles/README.md)",
             },
             "clocks": clocks,
             "checks": checks,

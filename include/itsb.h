@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ITSB_ABI_VERSION 3
+#define ITSB_ABI_VERSION 4
 
 /* ---- engine errors (negative) ------------------------------------------------------------------------------ */
 #define ITSB_OK                    0
@@ -271,6 +271,10 @@ int itsb_sync(itsb_engine* e, uint64_t* events_done);
 int itsb_last_run_ms(itsb_engine* e, float* ms);
 /* Number of kernel launches issued by this engine so far.                                                        */
 int itsb_launch_count(itsb_engine* e, uint64_t* launches);
+
+/* Name of the engine kernel itsb_run launches for the loaded model ("k_run_vote", "k_run", "k_run_in_place", ...; ""
+ * before a model is loaded).  No reference counterpart: the reference has one interpreter loop.                  */
+const char* itsb_kernel_name(itsb_engine* e);
 
 /* Replaces: Simulator.now() per replica.  dst receives n doubles starting at replica `first`.                     */
 int itsb_read_now(itsb_engine* e, uint64_t first, uint64_t n, double* dst);

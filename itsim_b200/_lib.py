@@ -14,7 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libitsim_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 TM_KIND0, TM_PACKETS_SENT, TM_BYTES_SENT, TM_PACKETS_RECEIVED, TM_BYTES_RECEIVED = 0, 9, 10, 11, 12
 TM_DELIVERED, TM_DROPPED, TM_USER0, TM_LAT0, LAT_BINS = 13, 14, 15, 23, 64
 TM_USER8, TM_USER_SLOTS = TM_LAT0 + LAT_BINS, 12
@@ -95,6 +95,7 @@ _SIGNATURES = {
     "itsb_sync": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "itsb_last_run_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "itsb_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "itsb_kernel_name": (C.c_char_p, [C.c_void_p]),
     "itsb_read_now": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "itsb_read_trace": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "itsb_read_net_events": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -84,6 +84,18 @@ extern "C" __global__ void k_reduce_telemetry(const unsigned char* hot, uint32_t
 }
 
 /* ---- host side ---------------------------------------------------------------------------------------------------------- */
+/* Engine kernels.  Two designs:
+ *   a replica per WARP, state staged in shared memory (k_run; k_run_wide for 13-16 resident replicas per SM;
+ *   k_run_in_place with the state left in HBM for replicas larger than shared memory; k_run_phased: experiment);
+ *   a replica per LANE, state in place in HBM, the warp running the event kind most of its lanes wait on (k_run_vote;
+ *   k_run_lanes without the vote and k_run_sorted with a CTA-wide regrouping: experiments).
+ * Default: k_run_vote where it is the faster one -- models whose tables fit shared memory and that keep no connection
+ * records (their per-socket correlation is lane-parallel work in the warp-per-replica kernels).  ITSB_KERNEL=
+ * warp | vote | lanes | sorted | phased overrides, ITSB_KERNEL_CTAS=n sets the CTAs per SM of the lane kernels. */
+enum { K_WARP = 0, K_WIDE, K_IN_PLACE, K_PHASED, K_VOTE, K_LANES, K_SORTED };
+static const char* const KERNEL_NAMES[] = {"k_run", "k_run_wide", "k_run_in_place", "k_run_phased", "k_run_vote",
+                                           "k_run_lanes", "k_run_sorted"};
+
 struct itsb_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -110,13 +122,29 @@ struct itsb_engine {
     uint32_t warps_per_cta = 0, grid = 0;
     size_t smem_bytes = 0;
     bool run_pending = false;
-    bool phased = false;                          /* ITSB_PHASED=1: k_run_phased instead of k_run (A/B switch) */
-    int lanes = 0;                                /* ITSB_LANES=n: k_run_lanes with n CTAs of 256 threads per SM (experiment) */
-    int sorted = 0;                               /* ITSB_SORTED=n: k_run_sorted with n CTAs of 256 threads per SM (experiment) */
+    int kernel = 0;                               /* K_*: which engine kernel itsb_run launches (choose_kernel) */
+    int kernel_ctas = 3;                          /* CTAs of 256 threads per SM for the lane-per-replica kernels */
+    bool forced_in_place = false;
     float last_ms = 0.f;
     long long first_failed = -1;
     std::string err;
 };
+
+static void choose_kernel(itsb_engine* e) {
+    const char* k = getenv("ITSB_KERNEL");
+    const char* c = getenv("ITSB_KERNEL_CTAS");
+    e->kernel_ctas = c && atoi(c) >= 1 && atoi(c) <= 8 ? atoi(c) : 3;
+    const std::string want = k ? k : "";
+    const bool lane_ok = !e->rp.tables_in_hbm && !e->forced_in_place;
+    int warp_kernel = e->rp.state_in_hbm ? K_IN_PLACE : (e->warps_per_cta > 12 ? K_WIDE : K_WARP);
+    if (want == "phased" && warp_kernel == K_WARP) warp_kernel = K_PHASED;
+    if (lane_ok && want == "vote") e->kernel = K_VOTE;
+    else if (lane_ok && want == "lanes") e->kernel = K_LANES;
+    else if (lane_ok && want == "sorted") e->kernel = K_SORTED;
+    else if (want == "warp" || want == "phased" || !lane_ok) e->kernel = warp_kernel;
+    else e->kernel = e->rp.layout.conn_cap == 0 ? K_VOTE : warp_kernel;
+}
+
 
 #define CU(e, call)                                                                            \
     do {                                                                                       \
@@ -220,9 +248,8 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     }
     e->warps_per_cta = w;
     e->rp.warps_per_cta = w;
-    { const char* ph = getenv("ITSB_PHASED"); e->phased = ph && ph[0] == '1'; }
-    { const char* ln = getenv("ITSB_LANES"); e->lanes = ln ? atoi(ln) : 0; if (e->lanes < -8 || e->lanes > 8) e->lanes = 0; }
-    { const char* so = getenv("ITSB_SORTED"); e->sorted = so ? atoi(so) : 0; if (e->sorted < 0 || e->sorted > 8) e->sorted = 0; }
+    e->forced_in_place = force && force[0] == '1';
+    choose_kernel(e);
     e->grid = (uint32_t)e->prop.multiProcessorCount;
     CU(e, cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     CU(e, cudaFuncSetAttribute(k_run_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
@@ -288,17 +315,17 @@ int itsb_run_async(itsb_engine* e, double duration) {
     CU(e, cudaMemsetAsync(e->d_ticket, 0, sizeof(unsigned long long), e->stream));
     e->rp.duration = duration;
     if (!e->run_pending) CU(e, cudaEventRecord(e->ev_start, e->stream));
-    if (e->sorted && !e->rp.tables_in_hbm)
-        k_run_sorted<<<e->grid * (uint32_t)e->sorted, 256,
-                       e->so.total + 256 * (sizeof(PendingEvent) + sizeof(RunCtx) + 2 + 1 + 4) + 64, e->stream>>>(e->rp);
-    else if (e->lanes > 0 && !e->rp.tables_in_hbm)
-        k_run_lanes<<<e->grid * (uint32_t)e->lanes, 256, e->so.total, e->stream>>>(e->rp);
-    else if (e->lanes < 0 && !e->rp.tables_in_hbm)
-        k_run_vote<<<e->grid * (uint32_t)(-e->lanes), 256, e->so.total, e->stream>>>(e->rp);
-    else if (e->rp.state_in_hbm) k_run_in_place<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
-    else if (e->warps_per_cta > 12) k_run_wide<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
-    else if (e->phased) k_run_phased<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
-    else k_run<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp);
+    const uint32_t lane_grid = e->grid * (uint32_t)e->kernel_ctas;
+    switch (e->kernel) {
+    case K_VOTE:     k_run_vote<<<lane_grid, 256, e->so.total, e->stream>>>(e->rp); break;
+    case K_LANES:    k_run_lanes<<<lane_grid, 256, e->so.total, e->stream>>>(e->rp); break;
+    case K_SORTED:   k_run_sorted<<<lane_grid, 256, e->so.total + 256 * (sizeof(PendingEvent) + sizeof(RunCtx) + 2 + 1 + 4) + 64,
+                                    e->stream>>>(e->rp); break;
+    case K_IN_PLACE: k_run_in_place<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp); break;
+    case K_WIDE:     k_run_wide<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp); break;
+    case K_PHASED:   k_run_phased<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp); break;
+    default:         k_run<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp); break;
+    }
     CU(e, cudaGetLastError());
     CU(e, cudaEventRecord(e->ev_stop, e->stream));
     e->launches += 1;
@@ -337,6 +364,8 @@ int itsb_run(itsb_engine* e, double duration, uint64_t* events_done) {
 }
 
 int itsb_last_run_ms(itsb_engine* e, float* ms) { if (!e || !ms) return ITSB_ERR_STATE; *ms = e->last_ms; return ITSB_OK; }
+const char* itsb_kernel_name(itsb_engine* e) { return e && e->loaded ? KERNEL_NAMES[e->kernel] : ""; }
+
 int itsb_launch_count(itsb_engine* e, uint64_t* n) { if (!e || !n) return ITSB_ERR_STATE; *n = e->launches; return ITSB_OK; }
 
 int itsb_read_now(itsb_engine* e, uint64_t first, uint64_t n, double* dst) {

@@ -11,7 +11,7 @@
 #include "itsb_kernel.cuh"
 
 #ifndef ITSB_LANES_MIN_CTAS
-#define ITSB_LANES_MIN_CTAS 2
+#define ITSB_LANES_MIN_CTAS 3
 #endif
 extern "C" __global__ void __launch_bounds__(256, ITSB_LANES_MIN_CTAS) k_run_lanes(const RunParams p) {
     extern __shared__ __align__(128) unsigned char smem[];

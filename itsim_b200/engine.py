@@ -75,6 +75,11 @@ class Engine:
         self._check(self._lib.itsb_last_run_ms(self._h, C.byref(ms)), "itsb_last_run_ms")
         return ms.value
 
+    def kernel_name(self) -> str:
+        """The engine kernel ``run`` launches for this model (``itsb_kernel_name``)."""
+        name = self._lib.itsb_kernel_name(self._h)
+        return name.decode() if name else ""
+
     def launch_count(self) -> int:
         n = C.c_uint64()
         self._check(self._lib.itsb_launch_count(self._h, C.byref(n)), "itsb_launch_count")

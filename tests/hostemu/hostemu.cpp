@@ -136,6 +136,7 @@ int itsb_run(itsb_engine* e, double duration, uint64_t* events_done) {
 
 int itsb_last_run_ms(itsb_engine*, float* ms) { *ms = 0.f; return ITSB_OK; }
 int itsb_launch_count(itsb_engine* e, uint64_t* n) { *n = e->launches; return ITSB_OK; }
+const char* itsb_kernel_name(itsb_engine*) { return "host emulation (tests only)"; }
 
 int itsb_read_now(itsb_engine* e, uint64_t first, uint64_t n, double* dst) {
     if (first + n > e->n_replicas) return ITSB_ERR_STATE;
