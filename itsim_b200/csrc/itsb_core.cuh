@@ -706,6 +706,22 @@ ITSB_COLD void pool_scan_min(Hdr* H) {
     u32 bs = NIL32;
     u32 bi = NIL32;
     const u32 n = R.max_ev;
+#if defined(ITSB_LANES)
+    /* one lane scans the whole pool: eight independent 8-byte loads in flight per step instead of a chain of
+       dependent ones, and the counter values are read only where two times tie (the kernel waits on memory) */
+#pragma unroll 1
+    for (u32 i = 0; i < n; i += 8) {
+        u64 t[8];
+#pragma unroll
+        for (u32 k = 0; k < 8; ++k) t[k] = (i + k < n) ? R.ev_t[i + k] : T_EMPTY;
+#pragma unroll
+        for (u32 k = 0; k < 8; ++k) {
+            if (t[k] < bt) { bt = t[k]; bi = i + k; }
+            else if (t[k] == bt && bt != T_EMPTY && R.ev_seq[i + k] < R.ev_seq[bi]) bi = i + k;
+        }
+    }
+    if (bi != NIL32) bs = R.ev_seq[bi];
+#else
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
@@ -714,6 +730,7 @@ ITSB_COLD void pool_scan_min(Hdr* H) {
         u32 s = R.ev_seq[i];
         if (t < bt || (t == bt && s < bs)) { bt = t; bs = s; bi = i; }
     }
+#endif
     u32 hi = (u32)(bt >> 32);
     u32 mhi = w_min(hi);
     if (mhi >= 0x7FF00000u) {

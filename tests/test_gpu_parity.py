@@ -161,3 +161,36 @@ def test_fused_loop_head_and_retired_wakeups_change_nothing():
         for r in range(3):
             assert np.array_equal(other[1][r], results[0][1][r])
         assert np.array_equal(other[2], results[0][2])
+
+
+@pytest.mark.parametrize("kernel", ["vote", "lanes", "sorted", "phased"])
+def test_every_engine_kernel_gives_the_same_replicas(kernel, monkeypatch):
+    """The two designs (a replica per warp: k_run; a replica per lane: k_run_vote, the default from 50 000 replicas up)
+    and the experimental variants advance a replica through the same events: every counter of every replica, and the
+    clock, equal k_run's.  ITSB_KERNEL selects the kernel when the replicas are created."""
+    n, horizon = 1500, 400.0
+    engines = {}
+    for which in ("warp", kernel):
+        monkeypatch.setenv("ITSB_KERNEL", which)
+        eng = make().run_replicas(n, seed=21, first_replica_id=1000)
+        engines[which] = (eng, eng.run(horizon), eng.kernel_name())
+    ref, events, name = engines["warp"]
+    got, events_k, name_k = engines[kernel]
+    assert name == "k_run" and name_k == "k_run_" + kernel
+    assert events_k == events
+    for r in range(0, n, 7):
+        assert np.array_equal(got.replica_telemetry(r), ref.replica_telemetry(r)), r
+    assert np.array_equal(got.now(), ref.now())
+    assert np.array_equal(got.telemetry(), ref.telemetry())
+    for eng, _, _ in engines.values():
+        eng.close()
+
+
+def test_the_default_kernel_depends_on_the_batch(monkeypatch):
+    monkeypatch.delenv("ITSB_KERNEL", raising=False)
+    small = make().run_replicas(100, seed=0)
+    assert small.kernel_name() == "k_run"
+    small.close()
+    big = make(arena_nodes=2048).run_replicas(50000, seed=0)
+    assert big.kernel_name() == "k_run_vote"
+    big.close()
