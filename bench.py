@@ -33,7 +33,10 @@ sys.path.insert(0, ROOT)
 METRIC = "simulated events/sec (batched network_simple replicas)"
 # ncu --set full captures committed under profiles/ (6000 replicas x 60 simulated s, one launch):
 # (dram__bytes_read.sum + dram__bytes_write.sum) / replicas, per engine kernel
-NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH = {"k_run": (328.9e6 + 160.1e6) / 6000.0, "k_run_vote": None}
+# k_run stages a replica's state once per launch: its traffic goes per launch.  k_run_vote advances the state in place:
+# its traffic goes with the simulated time (100000 replicas x 60 simulated s: 97.36 GB read + 16.78 GB written).
+NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH = {"k_run": (328.9e6 + 160.1e6) / 6000.0}
+NCU_TRAFFIC_BYTES_PER_REPLICA_SECOND = {"k_run_vote": (97.36e9 + 16.78e9) / 100000.0 / 60.0}
 UNIT = "events/s"
 RESULT_OUT = sys.stdout
 
@@ -384,6 +387,11 @@ def main() -> None:
         algo_bytes = 2.0 * state["hot"] * args.replicas + 32.0 * log_records + 40.0 * conn_records
         launch_s = ms_dev * 1e-3 / args.steps
         achieved = algo_bytes / launch_s / 1e9
+        traffic = None
+        if kernel in NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH:
+            traffic = NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH[kernel] * args.replicas
+        elif kernel in NCU_TRAFFIC_BYTES_PER_REPLICA_SECOND:
+            traffic = NCU_TRAFFIC_BYTES_PER_REPLICA_SECOND[kernel] * args.replicas * args.slice
         cpu = None
         if not args.no_cpu_baseline:
             _, cpu = cpu_baseline(args.cpu_horizon, 1, 0, args.seed)
@@ -418,14 +426,16 @@ def main() -> None:
             "gpu_launches": launches_dev,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH.get(kernel) or 0) * args.replicas or None,
+                "traffic": traffic, "dram_gbs": (traffic / launch_s / 1e9) if traffic else None,
                 "peak_source": peak_src, "kernel": kernel,
-                "traffic_note": "dram__bytes_read+write of one launch of this kernel from the ncu --set full capture under "
-                                "profiles/ (6000 replicas x 60 simulated s), scaled per replica",
+                "traffic_note": "dram__bytes_read+write per launch, scaled from this kernel's ncu --set full capture under "
+                                "profiles/ (k_run: 6000 replicas x 60 s, per replica and launch; k_run_vote: 100000 "
+                                "replicas x 60 s, per replica and simulated second); dram_gbs = traffic / launch time",
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "note": "algorithmic bytes = per-replica state read and written once per run (S_in+S_out, SURVEY 8-d); "
-                        "neither engine kernel is HBM-bound: the measured limiter is instruction supply (ncu: "
-                        "GPC-level instruction-cache requests at 78-93% of peak; profiles/README.md)",
+                        "neither engine kernel moves bytes at the HBM rate: k_run is bound by instruction supply (GPC-level "
+                        "instruction-cache requests at 93% of peak), k_run_vote by memory latency (85% of stall samples "
+                        "wait on loads, DRAM at ~13% of peak); profiles/README.md",
             },
             "clocks": clocks,
             "checks": checks,
