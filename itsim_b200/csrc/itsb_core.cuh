@@ -309,13 +309,6 @@ struct Hdr {                /* first thing in the hot block */
     u16 sig_free_top, thr_free_top, task_free_top;
     u16 setup_done;         /* the per-replica set-up draws (ITSB_INIT_ADD_DRAWN) have been made */
     u32 hidden_entry_balk, hidden_entry_wait_one;   /* entry indices of greensim's helper programs */
-    /* width-1 builds only (a lane scans the whole pool by itself): the NEAR_K smallest pool entries, sorted, and a lower
-       bound for every entry not listed -- the minimum after a removal is then the next listed one, and the pool is
-       rescanned once per NEAR_K removals instead of once per removal.  Width-32 builds leave near_valid at 0. */
-    u64 near_bt;
-    u32 near_bs;
-    u16 near_idx[4];
-    u16 near_n, near_valid;
     /* -- binding: rewritten every time the replica is staged (pointers of this launch, not state) -- */
     ArenaNode* arena;
     u32* arena_free;
@@ -662,24 +655,7 @@ ITSB_COLD u32 ovf_take_min(Hdr* H) {
     return data;
 }
 
-static const u32 NEAR_K = 4;
-
 ITSB_FN void ev_release(Rep& R, u32 slot) {
-#if ITSB_W == 1
-    {   /* drop the slot from the sorted near list, if it is there */
-        Hdr* H = R.hdr;
-        if (H->near_valid) {
-            const u32 n = H->near_n;
-            for (u32 j = 0; j < n; ++j) {
-                if (H->near_idx[j] == slot) {
-                    for (u32 q = j + 1; q < n; ++q) H->near_idx[q - 1] = H->near_idx[q];
-                    H->near_n = (u16)(n - 1);
-                    break;
-                }
-            }
-        }
-    }
-#endif
     R.ev_t[slot] = T_EMPTY;
     u32 top = R.hdr->ev_free_top;
     R.ev_free[top] = (u16)slot;
@@ -719,80 +695,33 @@ ITSB_COLD int ev_push(Hdr* H, u64 tb, u32 data) {
     if (H->pmin_valid && (tb < H->pmin_t || (tb == H->pmin_t && seq < H->pmin_seq))) {
         H->pmin_t = tb; H->pmin_seq = seq; H->pmin_idx = slot;
     }
-#if ITSB_W == 1
-    if (H->near_valid && (tb < H->near_bt || (tb == H->near_bt && seq < H->near_bs))) {
-        /* below the bound of the unlisted entries: it belongs in the near list, at its sorted place */
-        const u64* ev_t = (const u64*)(hot + H->L.off_ev_t);
-        const u32* ev_seq = (const u32*)(hot + H->L.off_ev_seq);
-        u32 n = H->near_n;
-        if (n == NEAR_K) {                   /* full: the largest listed entry leaves, and becomes the new bound */
-            const u32 last = H->near_idx[NEAR_K - 1];
-            const u64 lt = ev_t[last]; const u32 ls = ev_seq[last];
-            if (tb < lt || (tb == lt && seq < ls)) { H->near_bt = lt; H->near_bs = ls; n = NEAR_K - 1; }
-            else { H->near_bt = tb; H->near_bs = seq; n = NEAR_K; }      /* larger than all listed: it is the bound */
-        }
-        if (n < NEAR_K) {
-            u32 j = n;
-            while (j > 0) {
-                const u32 prev = H->near_idx[j - 1];
-                const u64 pt = ev_t[prev]; const u32 ps = ev_seq[prev];
-                if (pt < tb || (pt == tb && ps < seq)) break;
-                H->near_idx[j] = (u16)prev;
-                j -= 1;
-            }
-            H->near_idx[j] = (u16)slot;
-            H->near_n = (u16)(n + 1);
-        }
-    }
-#endif
     return (int)slot;
 }
 ITSB_FN int ev_push_inl(Rep& R, double t, u32 data) { return ev_push(R.hdr, dbits(t), data); }
 
 /* Minimum (t, seq) of the future pool: each lane scans a strided slice, then three redux min-reductions. */
-#if ITSB_W == 1
-/* Width 1: the minimum comes from the near list; the pool is scanned (for its NEAR_K smallest entries) only when the
-   list has run empty while unlisted entries may remain. */
-ITSB_COLD void pool_scan_min(Hdr* H) {
-    Rep R; rebind(R, H);
-    if (!H->near_valid || (H->near_n == 0 && H->near_bt != T_EMPTY)) {
-        u64 kt[NEAR_K]; u32 ks[NEAR_K]; u32 ki[NEAR_K];
-        u32 n = 0;
-        const u32 cap = R.max_ev;
-        for (u32 i = 0; i < cap; ++i) {
-            const u64 t = R.ev_t[i];
-            if (t == T_EMPTY) continue;
-            if (n == NEAR_K && !(t < kt[NEAR_K - 1] || (t == kt[NEAR_K - 1] && R.ev_seq[i] < ks[NEAR_K - 1]))) continue;
-            const u32 sq = R.ev_seq[i];
-            u32 j = n < NEAR_K ? n : NEAR_K - 1;
-            while (j > 0 && (t < kt[j - 1] || (t == kt[j - 1] && sq < ks[j - 1]))) {
-                kt[j] = kt[j - 1]; ks[j] = ks[j - 1]; ki[j] = ki[j - 1];
-                j -= 1;
-            }
-            kt[j] = t; ks[j] = sq; ki[j] = i;
-            if (n < NEAR_K) n += 1;
-        }
-        for (u32 j = 0; j < n; ++j) H->near_idx[j] = (u16)ki[j];
-        H->near_n = (u16)n;
-        if (n == NEAR_K) { H->near_bt = kt[NEAR_K - 1]; H->near_bs = ks[NEAR_K - 1]; }
-        else { H->near_bt = T_EMPTY; H->near_bs = NIL32; }       /* everything is listed */
-        H->near_valid = 1;
-    }
-    if (H->near_n == 0) {
-        H->pmin_t = T_EMPTY; H->pmin_seq = NIL32; H->pmin_idx = NIL32;
-    } else {
-        const u32 i = H->near_idx[0];
-        H->pmin_idx = i; H->pmin_t = R.ev_t[i]; H->pmin_seq = R.ev_seq[i];
-    }
-    H->pmin_valid = 1;
-}
-#else
 ITSB_COLD void pool_scan_min(Hdr* H) {
     Rep R; rebind(R, H);
     u64 bt = T_EMPTY;
     u32 bs = NIL32;
     u32 bi = NIL32;
     const u32 n = R.max_ev;
+#if defined(ITSB_LANES)
+    /* one lane scans the whole pool: eight independent 8-byte loads in flight per step instead of a chain of
+       dependent ones, and the counter values are read only where two times tie (the kernel waits on memory) */
+#pragma unroll 1
+    for (u32 i = 0; i < n; i += 8) {
+        u64 t[8];
+#pragma unroll
+        for (u32 k = 0; k < 8; ++k) t[k] = (i + k < n) ? R.ev_t[i + k] : T_EMPTY;
+#pragma unroll
+        for (u32 k = 0; k < 8; ++k) {
+            if (t[k] < bt) { bt = t[k]; bi = i + k; }
+            else if (t[k] == bt && bt != T_EMPTY && R.ev_seq[i + k] < R.ev_seq[bi]) bi = i + k;
+        }
+    }
+    if (bi != NIL32) bs = R.ev_seq[bi];
+#else
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
@@ -801,6 +730,7 @@ ITSB_COLD void pool_scan_min(Hdr* H) {
         u32 s = R.ev_seq[i];
         if (t < bt || (t == bt && s < bs)) { bt = t; bs = s; bi = i; }
     }
+#endif
     u32 hi = (u32)(bt >> 32);
     u32 mhi = w_min(hi);
     if (mhi >= 0x7FF00000u) {
@@ -820,7 +750,6 @@ ITSB_COLD void pool_scan_min(Hdr* H) {
     H->pmin_seq = msq;
     H->pmin_valid = 1;
 }
-#endif
 
 enum { SRC_NONE_LEFT = 0, SRC_NQ = 1, SRC_POOL = 2, SRC_OVF = 3 };
 
@@ -2272,7 +2201,7 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
     H->nq_head = 0; H->nq_tail = 0; H->nq_spill_head = NIL32; H->nq_spill_tail = NIL32; H->nq_spill_count = 0;
     H->pmin_valid = 0; H->pmin_idx = NIL32; H->pmin_seq = NIL32; H->pmin_t = T_EMPTY;
     H->ovf_min_t = T_EMPTY; H->ovf_min_seq = NIL32; H->ovf_head = NIL32; H->ovf_count = 0;
-    H->spare16 = 0; H->cur_seq = 0; H->near_n = 0; H->near_valid = 0; H->near_bt = T_EMPTY; H->near_bs = NIL32; H->rng_c0 = 0; H->rng_c1 = 0;
+    H->spare16 = 0; H->cur_seq = 0; H->rng_c0 = 0; H->rng_c1 = 0;
     for (u32 i = 0; i < VOL_COUNT; ++i) H->vol[i] = 0;
     for (u32 i = 0; i < 2 * NQ_CAP; ++i) R.nq[i] = 0;
     for (u32 i = 0; i < L->max_ev; ++i) { R.ev_t[i] = T_EMPTY; R.ev_seq[i] = 0; R.ev_data[i] = 0; R.ev_free[i] = (u16)(L->max_ev - 1 - i); }
