@@ -30,7 +30,9 @@ extern "C" __global__ void k_run_wide(const RunParams p);       /* itsb_wide.cu:
 extern "C" __global__ void k_run_phased(const RunParams p);     /* itsb_phased.cu: warps aligned on the loop's two halves */
 extern "C" __global__ void k_run_lanes(const RunParams p);      /* itsb_lanes.cu: experiment, a replica per lane */
 extern "C" __global__ void k_run_vote(const RunParams p);       /* itsb_lanes.cu: experiment, lanes + per-warp majority key */
-extern "C" __global__ void k_run_sorted(const RunParams p);     /* itsb_sorted.cu: experiment, lanes regrouped by next event */
+extern "C" __global__ void k_run_sorted(const RunParams p);
+extern "C" __global__ void k_run_pool(const RunParams p);       /* itsb_pool.cu: experiment, replicas change warps via per-kind rings */
+extern "C" size_t itsb_pool_shared_bytes(void);     /* itsb_sorted.cu: experiment, lanes regrouped by next event */
 
 /* up to 12 warps per CTA (what shared memory allows the flagship model): 168 registers per thread, no spills */
 extern "C" __global__ void __launch_bounds__(384, 1) k_run(const RunParams p) {
@@ -92,9 +94,9 @@ extern "C" __global__ void k_reduce_telemetry(const unsigned char* hot, uint32_t
  * Default: k_run_vote where it is the faster one -- models whose tables fit shared memory and that keep no connection
  * records (their per-socket correlation is lane-parallel work in the warp-per-replica kernels).  ITSB_KERNEL=
  * warp | vote | lanes | sorted | phased overrides, ITSB_KERNEL_CTAS=n sets the CTAs per SM of the lane kernels. */
-enum { K_WARP = 0, K_WIDE, K_IN_PLACE, K_PHASED, K_VOTE, K_LANES, K_SORTED };
+enum { K_WARP = 0, K_WIDE, K_IN_PLACE, K_PHASED, K_VOTE, K_LANES, K_SORTED, K_POOL };
 static const char* const KERNEL_NAMES[] = {"k_run", "k_run_wide", "k_run_in_place", "k_run_phased", "k_run_vote",
-                                           "k_run_lanes", "k_run_sorted"};
+                                           "k_run_lanes", "k_run_sorted", "k_run_pool"};
 
 struct itsb_engine {
     int device = 0;
@@ -141,6 +143,7 @@ static void choose_kernel(itsb_engine* e) {
     if (lane_ok && want == "vote") e->kernel = K_VOTE;
     else if (lane_ok && want == "lanes") e->kernel = K_LANES;
     else if (lane_ok && want == "sorted") e->kernel = K_SORTED;
+    else if (lane_ok && want == "pool") e->kernel = K_POOL;
     else if (want == "warp" || want == "phased" || !lane_ok) e->kernel = warp_kernel;
     else {
         /* a lane per replica needs replicas to fill its threads (148 SMs x 768): measured on the default model, the two
@@ -260,6 +263,8 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     CU(e, cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     CU(e, cudaFuncSetAttribute(k_run_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     CU(e, cudaFuncSetAttribute(k_run_phased, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CU(e, cudaFuncSetAttribute(k_run_pool, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(e->so.total + itsb_pool_shared_bytes())));
     CU(e, cudaFuncSetAttribute(k_run_in_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     e->loaded = true;
     return ITSB_OK;
@@ -328,6 +333,7 @@ int itsb_run_async(itsb_engine* e, double duration) {
     case K_LANES:    k_run_lanes<<<lane_grid, 256, e->so.total, e->stream>>>(e->rp); break;
     case K_SORTED:   k_run_sorted<<<lane_grid, 256, e->so.total + 256 * (sizeof(PendingEvent) + sizeof(RunCtx) + 2 + 1 + 4) + 64,
                                     e->stream>>>(e->rp); break;
+    case K_POOL:     k_run_pool<<<lane_grid, 256, e->so.total + itsb_pool_shared_bytes(), e->stream>>>(e->rp); break;
     case K_IN_PLACE: k_run_in_place<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp); break;
     case K_WIDE:     k_run_wide<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp); break;
     case K_PHASED:   k_run_phased<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp); break;
