@@ -324,6 +324,12 @@ int64_t itsb_first_failed_replica(itsb_engine* e);
 /* bytes of per-replica state staged HBM<->shared memory per run (S_in + S_out of the roofline accounting).        */
 int itsb_state_bytes(itsb_engine* e, uint64_t* hot_bytes, uint64_t* arena_bytes);
 
+/* Replaces: math.log inside random.expovariate / random.normalvariate (CPython Lib/random.py; reached through
+ * greensim.random.expo / normal: itsim/random.py:4, itsim/network/service/dhcp/client.py:47-49).  Evaluates the
+ * engine's own logarithm -- the one its variates use -- on n doubles ON THE DEVICE (one thread per value), so a
+ * parity test can hold it bit for bit against the oracle's restatement of the same algorithm.                     */
+int itsb_eval_log(itsb_engine* e, const double* x, double* y, size_t n);
+
 const char* itsb_last_error(itsb_engine* e);
 void itsb_destroy(itsb_engine* e);
 int itsb_abi_version(void);

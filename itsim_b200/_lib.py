@@ -111,6 +111,7 @@ _SIGNATURES = {
     "itsb_replica_status": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]),
     "itsb_first_failed_replica": (C.c_int64, [C.c_void_p]),
     "itsb_state_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "itsb_eval_log": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsb_last_error": (C.c_char_p, [C.c_void_p]),
     "itsb_destroy": (None, [C.c_void_p]),
 }

@@ -85,6 +85,12 @@ extern "C" __global__ void k_reduce_telemetry(const unsigned char* hot, uint32_t
     if (acc) atomicAdd(out + c, acc);
 }
 
+/* the engine's logarithm on an array (itsb_eval_log): what the variates call, reachable from a parity test */
+extern "C" __global__ void k_eval_log(double* v, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = log_f64(v[i]);
+}
+
 /* ---- host side ---------------------------------------------------------------------------------------------------------- */
 /* Engine kernels.  Two designs:
  *   a replica per WARP, state staged in shared memory (k_run; k_run_wide for 13-16 resident replicas per SM;
@@ -584,6 +590,25 @@ int itsb_state_bytes(itsb_engine* e, uint64_t* hot, uint64_t* arena) {
     if (!e || !e->loaded) return ITSB_ERR_STATE;
     if (hot) *hot = e->rp.layout.hot_bytes;
     if (arena) *arena = (uint64_t)e->rp.layout.arena_nodes * (sizeof(ArenaNode) + 4);
+    return ITSB_OK;
+}
+
+int itsb_eval_log(itsb_engine* e, const double* x, double* y, size_t n) {
+    if (!e || !x || !y) return ITSB_ERR_STATE;
+    if (n == 0) return ITSB_OK;
+    CU(e, cudaSetDevice(e->device));
+    double* d = nullptr;
+    CU(e, cudaMalloc(&d, n * sizeof(double)));
+    cudaError_t rc = cudaMemcpyAsync(d, x, n * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+    if (rc == cudaSuccess) {
+        k_eval_log<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(d, n);
+        rc = cudaGetLastError();
+        e->launches += 1;
+    }
+    if (rc == cudaSuccess) rc = cudaMemcpyAsync(y, d, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+    if (rc == cudaSuccess) rc = cudaStreamSynchronize(e->stream);
+    cudaFree(d);
+    if (rc != cudaSuccess) { e->err = std::string("itsb_eval_log: ") + cudaGetErrorString(rc); return ITSB_ERR_CUDA; }
     return ITSB_OK;
 }
 

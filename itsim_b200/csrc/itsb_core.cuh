@@ -57,7 +57,7 @@
 #define on_tx_begin       a3_txbegin
 #define on_tx_end         a4_tx_end_
 #define ev_push           a4z_evpush
-#define pool_scan_min     a5_poolmin
+#define heap_pop          a5_heappop
 #define net_send          a6_netsend
 #define proc_spawn        a7_spawn__
 #define sock_open_on      a8_sk_open
@@ -253,9 +253,15 @@ struct EvNode {             /* arena node used by the now-queue spill chain and 
     u32 pad[3];
 };
 
+struct HeapEnt {            /* 16 bytes: one entry of the future-event heap, ordered by (t, seq) */
+    u64 t;                  /* timestamp, as its bit pattern (t >= 0: bit order is numeric order) */
+    u32 seq;                /* greensim's insertion counter: breaks ties */
+    u32 slot;               /* the event's stable slot: ev_data[slot] is its data word, ev_pos[slot] its heap position */
+};
+
 struct Layout {             /* byte offsets inside one replica's hot block */
     u32 hot_bytes;
-    u32 off_ev_t, off_ev_seq, off_ev_data, off_ev_free, off_nq;
+    u32 off_ev_heap, off_ev_pos, off_ev_data, off_ev_free, off_nq;
     u32 off_pcb, off_pcb_free, off_sock, off_sock_free, off_node, off_stats;
     u32 max_ev, max_proc, max_sock, n_nodes;
     u32 arena_nodes, trace_cap;
@@ -300,8 +306,8 @@ struct Hdr {                /* first thing in the hot block */
     u32 replica_lo, replica_hi;
     u32 nq_head, nq_tail;   /* now-queue ring cursors (monotone) */
     u32 nq_spill_head, nq_spill_tail, nq_spill_count;
-    u32 pmin_valid, pmin_idx, pmin_seq;
-    u64 pmin_t;
+    u32 ev_count;           /* entries in the future-event heap */
+    u32 spare32;
     u64 ovf_min_t;
     u32 ovf_min_seq, ovf_head, ovf_count;
     u32 cur_seq;            /* counter value of the event being processed: the order key of the connection records */
@@ -324,8 +330,8 @@ struct Hdr {                /* first thing in the hot block */
 
 struct Rep {                /* register-resident working view of one replica */
     Hdr* hdr;
-    u64* ev_t;
-    u32* ev_seq;
+    HeapEnt* ev_heap;
+    u16* ev_pos;
     u32* ev_data;
     u16* ev_free;
     u32* nq;                /* now-queue ring: (seq, data) pairs */
@@ -356,8 +362,8 @@ struct Rep {                /* register-resident working view of one replica */
 ITSB_FN void rebind(Rep& R, Hdr* H) {
     unsigned char* hot = (unsigned char*)H;
     R.hdr = H;
-    R.ev_t = (u64*)(hot + H->L.off_ev_t);
-    R.ev_seq = (u32*)(hot + H->L.off_ev_seq);
+    R.ev_heap = (HeapEnt*)(hot + H->L.off_ev_heap);
+    R.ev_pos = (u16*)(hot + H->L.off_ev_pos);
     R.ev_data = (u32*)(hot + H->L.off_ev_data);
     R.ev_free = (u16*)(hot + H->L.off_ev_free);
     R.nq = (u32*)(hot + H->L.off_nq);
@@ -462,8 +468,67 @@ ITSB_FN double rng_random(Hdr* H) {  /* CPython's 53-bit construction */
     return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
 }
 
-/* math.log, one copy of its code for both variates that need it */
-ITSB_COLD double log_f64(double x) { return log(x); }
+/* math.log, one copy of its code for both variates that need it -- and ONE ALGORITHM on every side of the parity
+ * check.  CPython's expovariate / normalvariate call the platform libm's log, whose last bit is not specified (glibc,
+ * CUDA: both <= 1 ulp, not the same ulp); a 1-ulp difference flips int(min(max(x + 68, 0), 576)) or the
+ * Kinderman-Monahan acceptance test once in ~1e13 draws and desynchronises the replica for good.  So the logarithm is
+ * written out here with IEEE +, -, *, / only (this file is compiled with -fmad=false / -ffp-contract=off, no table):
+ * the FreeBSD msun / fdlibm e_log.c algorithm (reduce x = 2^k (1 + f), sqrt(2)/2 <= 1 + f < sqrt(2); s = f / (2 + f);
+ * log(1 + f) = f - (f^2/2 - s (f^2/2 + R(s^2))) with a degree-14 minimax R; error < 1 ulp).  oracle/philox.py log_f64
+ * is the same sequence of operations in Python; tests/test_philox.py checks the two bit for bit. */
+ITSB_COLD double log_f64(double x) {
+    const double ln2_hi = bitsd(0x3FE62E42FEE00000ull), ln2_lo = bitsd(0x3DEA39EF35793C76ull);
+    const double Lg1 = bitsd(0x3FE5555555555593ull), Lg2 = bitsd(0x3FD999999997FA04ull),
+                 Lg3 = bitsd(0x3FD2492494229359ull), Lg4 = bitsd(0x3FCC71C51D8E78AFull),
+                 Lg5 = bitsd(0x3FC7466496CB03DEull), Lg6 = bitsd(0x3FC39A09D078C69Full),
+                 Lg7 = bitsd(0x3FC2F112DF3E5244ull);
+    u64 b = dbits(x);
+    int32_t hx = (int32_t)(b >> 32);
+    u32 lx = (u32)b;
+    int32_t k = 0;
+    if (hx < 0x00100000) {                          /* x < 2^-1022 */
+        if (((hx & 0x7FFFFFFF) | lx) == 0) return bitsd(0xFFF0000000000000ull);   /* log(+-0) = -inf */
+        if (hx < 0) return bitsd(0x7FF8000000000000ull);                           /* log(-#) = NaN */
+        k -= 54;
+        x *= 18014398509481984.0;                   /* subnormal: scale up by 2^54 */
+        b = dbits(x);
+        hx = (int32_t)(b >> 32);
+        lx = (u32)b;
+    }
+    if (hx >= 0x7FF00000) return x + x;
+    k += (hx >> 20) - 1023;
+    hx &= 0x000FFFFF;
+    int32_t i = (hx + 0x95F64) & 0x100000;
+    x = bitsd(((u64)(u32)(hx | (i ^ 0x3FF00000)) << 32) | lx);   /* x or x / 2, in [sqrt(2)/2, sqrt(2)) */
+    k += i >> 20;
+    const double f = x - 1.0;
+    const double dk = (double)k;
+    if ((0x000FFFFF & (2 + hx)) < 3) {              /* |f| < 2^-20 */
+        if (f == 0.0) {
+            if (k == 0) return 0.0;
+            return dk * ln2_hi + dk * ln2_lo;
+        }
+        const double r = f * f * (0.5 - 0.33333333333333333 * f);
+        if (k == 0) return f - r;
+        return dk * ln2_hi - ((r - dk * ln2_lo) - f);
+    }
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    i = hx - 0x6147A;
+    const double w = z * z;
+    const int32_t j = 0x6B851 - hx;
+    const double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+    const double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    i |= j;
+    const double r = t2 + t1;
+    if (i > 0) {
+        const double hfsq = 0.5 * f * f;
+        if (k == 0) return f - (hfsq - s * (hfsq + r));
+        return dk * ln2_hi - ((hfsq - (s * (hfsq + r) + dk * ln2_lo)) - f);
+    }
+    if (k == 0) return f - s * (f - r);
+    return dk * ln2_hi - ((s * (f - r) - dk * ln2_lo) - f);
+}
 
 /* One value of a generator chain: kind -> linear -> bounded -> project_int (itsim/random.py:29). */
 ITSB_COLD double draw_dist(Hdr* H, const itsb_dist* Dp) {
@@ -576,11 +641,10 @@ ITSB_FN void arena_release(Rep& R, u32 idx) {
  *  now-queue   every event scheduled with zero delay (resume, throw, add, the delivery fan-out, TX_BEGIN) has
  *              t == now and a counter larger than anything scheduled before it, so these events are already sorted:
  *              a FIFO ring in shared memory, O(1) push and pop.  They are ~95 % of all pops in network_simple.
- *  future pool events with t > now (advance wake-ups, TX_END): an unordered slot array whose minimum is found by a
- *              lane-strided scan + three redux min-reductions, cached until the minimum itself is removed.
+ *  future heap events with t > now (advance wake-ups, TX_END): a 4-ary min-heap on (t, seq), below.
  *
  * Neither is bounded in the reference, so both continue into arena nodes in HBM when full (a workstation that wakes
- * with a thousand queued packets emits its answers in one instant): the ring spills to a FIFO chain, the pool to an
+ * with a thousand queued packets emits its answers in one instant): the ring spills to a FIFO chain, the heap to an
  * unordered overflow list with its own cached minimum.
  */
 ITSB_COLD void nq_spill_push(Hdr* H, u32 seq, u32 data) {
@@ -655,15 +719,91 @@ ITSB_COLD u32 ovf_take_min(Hdr* H) {
     return data;
 }
 
-ITSB_FN void ev_release(Rep& R, u32 slot) {
-    R.ev_t[slot] = T_EMPTY;
-    u32 top = R.hdr->ev_free_top;
-    R.ev_free[top] = (u16)slot;
-    R.hdr->ev_free_top = (u16)(top + 1);
-    if (R.hdr->pmin_valid && R.hdr->pmin_idx == slot) R.hdr->pmin_valid = 0;
+/* ---- the future-event heap --------------------------------------------------------------------------------------------
+ * A 4-ary min-heap on (t, seq) of 16-byte entries; entry 0 sits at byte 48 of a 64-byte line, so the four children of
+ * any entry (4i + 1 .. 4i + 4) are one aligned 64-byte line: a pop costs one memory round per level (three or four for
+ * the ~100 sleepers of network_simple) where the unordered pool it replaces was scanned from end to end after every
+ * removal (round 1: 22 % of k_run_vote's instructions, 16 dependent rounds of loads per scan).  An event keeps a stable
+ * slot (ev_data / ev_pos / the free stack) so that an interrupted advance() can still cancel its wake-up exactly
+ * (greensim: "on Interrupt cancel the wake-up"): ev_pos[slot] is kept current by every move.  The peek is entry 0. */
+ITSB_FN bool key_less(u64 ta, u32 sa, u64 tb, u32 sb) { return ta < tb || (ta == tb && sa < sb); }
+
+ITSB_FN void heap_sift_up(Rep& R, u32 i, const HeapEnt E) {
+    HeapEnt* hp = R.ev_heap;
+#if ITSB_W == 1
+    /* a lane per replica waits on memory, not on instructions: the ancestors' addresses do not depend on their
+       contents, so the first four levels are loaded together (one round instead of up to four) */
+    if (i > 0) {
+        const u32 a0 = (i - 1) >> 2, a1 = a0 ? (a0 - 1) >> 2 : 0, a2 = a1 ? (a1 - 1) >> 2 : 0, a3 = a2 ? (a2 - 1) >> 2 : 0;
+        const HeapEnt A0 = hp[a0], A1 = hp[a1], A2 = hp[a2], A3 = hp[a3];
+        const HeapEnt anc[4] = {A0, A1, A2, A3};
+        const u32 idx[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i == 0 || !key_less(E.t, E.seq, anc[k].t, anc[k].seq)) break;
+            hp[i] = anc[k]; R.ev_pos[anc[k].slot] = (u16)i;
+            i = idx[k];
+        }
+    }
+#endif
+    while (i > 0) {
+        const u32 par = (i - 1) >> 2;
+        const HeapEnt A = hp[par];
+        if (!key_less(E.t, E.seq, A.t, A.seq)) break;
+        hp[i] = A; R.ev_pos[A.slot] = (u16)i;
+        i = par;
+    }
+    hp[i] = E; R.ev_pos[E.slot] = (u16)i;
 }
 
-/* Schedules (t, seq = counter++).  Returns the pool slot (so an advance() can be cancelled) or -1.  One copy of the
+/* places E at position i of a heap of n entries, moving it down while a child precedes it */
+ITSB_FN void heap_sift_down(Rep& R, u32 i, const HeapEnt E, u32 n) {
+    HeapEnt* hp = R.ev_heap;
+    for (;;) {
+        const u32 c = 4 * i + 1;
+        if (c >= n) break;
+        /* the four children: one aligned 64-byte line (absent ones read as +inf) */
+        HeapEnt C0 = hp[c], C1, C2, C3;
+        C1.t = T_EMPTY; C1.seq = NIL32; C1.slot = 0; C2 = C1; C3 = C1;
+        if (c + 1 < n) C1 = hp[c + 1];
+        if (c + 2 < n) C2 = hp[c + 2];
+        if (c + 3 < n) C3 = hp[c + 3];
+        u32 m = c; HeapEnt M = C0;
+        if (key_less(C1.t, C1.seq, M.t, M.seq)) { M = C1; m = c + 1; }
+        if (key_less(C2.t, C2.seq, M.t, M.seq)) { M = C2; m = c + 2; }
+        if (key_less(C3.t, C3.seq, M.t, M.seq)) { M = C3; m = c + 3; }
+        if (!key_less(M.t, M.seq, E.t, E.seq)) break;
+        hp[i] = M; R.ev_pos[M.slot] = (u16)i;
+        i = m;
+    }
+    hp[i] = E; R.ev_pos[E.slot] = (u16)i;
+}
+
+/* the time of the earliest future event (+inf when there is none) */
+ITSB_FN u64 heap_min_t(Hdr* H) {
+    return H->ev_count ? ((const HeapEnt*)((unsigned char*)H + H->L.off_ev_heap))[0].t : T_EMPTY;
+}
+
+/* Removes the event in `slot` wherever it sits in the heap (an interrupted advance() cancels its wake-up). */
+ITSB_COLD void ev_release_cold(Hdr* H, u32 slot) {
+    Rep R; rebind(R, H);
+    const u32 i = R.ev_pos[slot];
+    const u32 n = H->ev_count - 1;
+    H->ev_count = n;
+    u32 top = H->ev_free_top;
+    R.ev_free[top] = (u16)slot;
+    H->ev_free_top = (u16)(top + 1);
+    if (i == n) return;
+    const HeapEnt L = R.ev_heap[n];
+    if (i > 0) {
+        const HeapEnt A = R.ev_heap[(i - 1) >> 2];
+        if (key_less(L.t, L.seq, A.t, A.seq)) { heap_sift_up(R, i, L); return; }
+    }
+    heap_sift_down(R, i, L, n);
+}
+ITSB_FN void ev_release(Rep& R, u32 slot) { ev_release_cold(R.hdr, slot); }
+
+/* Schedules (t, seq = counter++).  Returns the event's slot (so an advance() can be cancelled) or -1.  One copy of the
  * code for all callers: the kernel is bound by instruction fetch, not by instruction count. */
 ITSB_COLD int ev_push(Hdr* H, u64 tb, u32 data) {
     const u32 seq = H->seq;
@@ -682,73 +822,38 @@ ITSB_COLD int ev_push(Hdr* H, u64 tb, u32 data) {
         return -1;
     }
     u32 top = H->ev_free_top;
-    if (top == 0) {   /* pool full: unordered overflow list in the arena */
+    if (top == 0) {   /* every slot taken: unordered overflow list in the arena */
         ovf_push(H, tb, seq, data);
         return -1;
     }
     top -= 1;
     H->ev_free_top = (u16)top;
-    u32 slot = ((u16*)(hot + H->L.off_ev_free))[top];
-    ((u64*)(hot + H->L.off_ev_t))[slot] = tb;
-    ((u32*)(hot + H->L.off_ev_seq))[slot] = seq;
+    const u32 slot = ((u16*)(hot + H->L.off_ev_free))[top];
     ((u32*)(hot + H->L.off_ev_data))[slot] = data;
-    if (H->pmin_valid && (tb < H->pmin_t || (tb == H->pmin_t && seq < H->pmin_seq))) {
-        H->pmin_t = tb; H->pmin_seq = seq; H->pmin_idx = slot;
-    }
+    Rep R; rebind(R, H);
+    HeapEnt E; E.t = tb; E.seq = seq; E.slot = slot;
+    const u32 n = H->ev_count;
+    H->ev_count = n + 1;
+    heap_sift_up(R, n, E);
     return (int)slot;
 }
 ITSB_FN int ev_push_inl(Rep& R, double t, u32 data) { return ev_push(R.hdr, dbits(t), data); }
 
-/* Minimum (t, seq) of the future pool: each lane scans a strided slice, then three redux min-reductions. */
-ITSB_COLD void pool_scan_min(Hdr* H) {
+/* Removes the heap's minimum; returns its data word. */
+ITSB_COLD u32 heap_pop(Hdr* H) {
     Rep R; rebind(R, H);
-    u64 bt = T_EMPTY;
-    u32 bs = NIL32;
-    u32 bi = NIL32;
-    const u32 n = R.max_ev;
-#if defined(ITSB_LANES)
-    /* one lane scans the whole pool: eight independent 8-byte loads in flight per step instead of a chain of
-       dependent ones, and the counter values are read only where two times tie (the kernel waits on memory) */
-#pragma unroll 1
-    for (u32 i = 0; i < n; i += 8) {
-        u64 t[8];
-#pragma unroll
-        for (u32 k = 0; k < 8; ++k) t[k] = (i + k < n) ? R.ev_t[i + k] : T_EMPTY;
-#pragma unroll
-        for (u32 k = 0; k < 8; ++k) {
-            if (t[k] < bt) { bt = t[k]; bi = i + k; }
-            else if (t[k] == bt && bt != T_EMPTY && R.ev_seq[i + k] < R.ev_seq[bi]) bi = i + k;
-        }
+    const u32 slot = R.ev_heap[0].slot;
+    const u32 d = R.ev_data[slot];
+    u32 top = H->ev_free_top;
+    R.ev_free[top] = (u16)slot;
+    H->ev_free_top = (u16)(top + 1);
+    const u32 n = H->ev_count - 1;
+    H->ev_count = n;
+    if (n != 0) {
+        const HeapEnt L = R.ev_heap[n];
+        heap_sift_down(R, 0, L, n);
     }
-    if (bi != NIL32) bs = R.ev_seq[bi];
-#else
-#if defined(__CUDACC__)
-#pragma unroll 1
-#endif
-    for (u32 i = (u32)lane_id(); i < n; i += ITSB_W) {
-        u64 t = R.ev_t[i];
-        u32 s = R.ev_seq[i];
-        if (t < bt || (t == bt && s < bs)) { bt = t; bs = s; bi = i; }
-    }
-#endif
-    u32 hi = (u32)(bt >> 32);
-    u32 mhi = w_min(hi);
-    if (mhi >= 0x7FF00000u) {
-        H->pmin_t = T_EMPTY; H->pmin_seq = NIL32; H->pmin_idx = NIL32; H->pmin_valid = 1;
-        return;
-    }
-    bool cand = (hi == mhi);
-    u32 lo = cand ? (u32)bt : NIL32;
-    u32 mlo = w_min(lo);
-    cand = cand && (lo == mlo);
-    u32 sq = cand ? bs : NIL32;
-    u32 msq = w_min(sq);
-    cand = cand && (sq == msq);
-    int winner = ffs32(w_ballot(cand)) - 1;
-    H->pmin_idx = w_shfl(bi, winner);
-    H->pmin_t = ((u64)mhi << 32) | mlo;
-    H->pmin_seq = msq;
-    H->pmin_valid = 1;
+    return d;
 }
 
 enum { SRC_NONE_LEFT = 0, SRC_NQ = 1, SRC_POOL = 2, SRC_OVF = 3 };
@@ -757,10 +862,9 @@ enum { SRC_NONE_LEFT = 0, SRC_NQ = 1, SRC_POOL = 2, SRC_OVF = 3 };
 ITSB_FN int ev_peek(Rep& R, u64& tbits, u32& seq) {
     Hdr* H = R.hdr;
     if (H->nq_head == H->nq_tail && H->nq_spill_count != 0) nq_refill(H);
-    if (!H->pmin_valid) pool_scan_min(H);
     int src = SRC_NONE_LEFT;
     tbits = T_EMPTY; seq = NIL32;
-    if (H->pmin_t != T_EMPTY) { src = SRC_POOL; tbits = H->pmin_t; seq = H->pmin_seq; }
+    if (H->ev_count != 0) { const HeapEnt E = R.ev_heap[0]; src = SRC_POOL; tbits = E.t; seq = E.seq; }
     if (H->ovf_count != 0 && (H->ovf_min_t < tbits || (H->ovf_min_t == tbits && H->ovf_min_seq < seq))) {
         src = SRC_OVF; tbits = H->ovf_min_t; seq = H->ovf_min_seq;
     }
@@ -780,12 +884,7 @@ ITSB_FN u32 ev_take(Rep& R, int src) {
         H->nq_head += 1;
         return d;
     }
-    if (src == SRC_POOL) {
-        u32 slot = H->pmin_idx;
-        u32 d = R.ev_data[slot];
-        ev_release(R, slot);
-        return d;
-    }
+    if (src == SRC_POOL) return heap_pop(H);
     return ovf_take_min(H);
 }
 
@@ -1033,9 +1132,8 @@ ITSB_COLD bool on_tx_end(Hdr* H, u32 k) {
     u32 count = (K.dst_ip == NET.bcast) ? NET.n_nodes : 1u;
     count_event(R, ITSB_EV_TX_END, 9, K.meta & 0xFFFF, K.size);
     if (H->nq_head == H->nq_tail && H->nq_spill_count == 0) {
-        if (!H->pmin_valid) pool_scan_min(H);
         const u64 nb = dbits(H->now);
-        if (H->pmin_t > nb && (H->ovf_count == 0 || H->ovf_min_t > nb)) {
+        if (heap_min_t(H) > nb && (H->ovf_count == 0 || H->ovf_min_t > nb)) {
             H->seq += count;
             return true;
         }
@@ -1115,9 +1213,8 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
     bool fast_ok = false;
     if (R.trace == nullptr && R.m.n_filters != 0) {   /* (a model that keeps connection records has no RECV_FILTER) */
         if (H->nq_head == H->nq_tail && H->nq_spill_count == 0) {
-            if (!H->pmin_valid) pool_scan_min(H);
             const u64 nb = dbits(now);
-            fast_ok = H->pmin_t > nb && (H->ovf_count == 0 || H->ovf_min_t > nb);
+            fast_ok = heap_min_t(H) > nb && (H->ovf_count == 0 || H->ovf_min_t > nb);
         }
     }
     for (u32 base = 0; base < count; base += ITSB_W) {
@@ -2199,12 +2296,15 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
     H->trace_count = 0; H->log_count = 0; H->conn_count = 0;
     H->replica_lo = (u32)replica_id; H->replica_hi = (u32)(replica_id >> 32);
     H->nq_head = 0; H->nq_tail = 0; H->nq_spill_head = NIL32; H->nq_spill_tail = NIL32; H->nq_spill_count = 0;
-    H->pmin_valid = 0; H->pmin_idx = NIL32; H->pmin_seq = NIL32; H->pmin_t = T_EMPTY;
+    H->ev_count = 0; H->spare32 = 0;
     H->ovf_min_t = T_EMPTY; H->ovf_min_seq = NIL32; H->ovf_head = NIL32; H->ovf_count = 0;
     H->spare16 = 0; H->cur_seq = 0; H->rng_c0 = 0; H->rng_c1 = 0;
     for (u32 i = 0; i < VOL_COUNT; ++i) H->vol[i] = 0;
     for (u32 i = 0; i < 2 * NQ_CAP; ++i) R.nq[i] = 0;
-    for (u32 i = 0; i < L->max_ev; ++i) { R.ev_t[i] = T_EMPTY; R.ev_seq[i] = 0; R.ev_data[i] = 0; R.ev_free[i] = (u16)(L->max_ev - 1 - i); }
+    for (u32 i = 0; i < L->max_ev; ++i) {
+        R.ev_heap[i].t = T_EMPTY; R.ev_heap[i].seq = 0; R.ev_heap[i].slot = 0;
+        R.ev_pos[i] = 0; R.ev_data[i] = 0; R.ev_free[i] = (u16)(L->max_ev - 1 - i);
+    }
     H->ev_free_top = (u16)L->max_ev;
     for (u32 i = 0; i < L->max_proc; ++i) { memset(&R.pcb[i], 0, sizeof(Pcb)); R.pcb_free[i] = (u16)(L->max_proc - 1 - i); }
     H->pcb_free_top = (u16)L->max_proc;

@@ -24,8 +24,9 @@ static inline Layout compute_layout(const itsb_model_desc& d) {
     L.n_nodes = d.n_nodes; L.arena_nodes = c.arena_nodes; L.trace_cap = c.trace_records;
     L.log_cap = c.net_event_records;
     uint32_t off = align_up((uint32_t)sizeof(Hdr), 16);
-    L.off_ev_t = off;      off = align_up(off + 8 * L.max_ev, 16);
-    L.off_ev_seq = off;    off = align_up(off + 4 * L.max_ev, 16);
+    /* the future-event heap: entry 0 at byte 48 of a 64-byte line, so children 4i + 1 .. 4i + 4 share one line */
+    L.off_ev_heap = align_up(off, 64) + 48; off = align_up(L.off_ev_heap + (uint32_t)sizeof(HeapEnt) * L.max_ev, 16);
+    L.off_ev_pos = off;    off = align_up(off + 2 * L.max_ev, 16);
     L.off_ev_data = off;   off = align_up(off + 4 * L.max_ev, 16);
     L.off_ev_free = off;   off = align_up(off + 2 * L.max_ev, 16);
     L.off_nq = off;        off = align_up(off + 8 * NQ_CAP, 16);

@@ -63,6 +63,7 @@ class Tracer:
         self.exc_code: Callable[[BaseException], int] = lambda exc: 0
         self.deliver_aux: Callable[[Any, Any], int] = lambda proc, ev: 0
         self.resolver: Optional[Callable[[Any], "Ident"]] = None   # labels processes the model code did not label
+        self.current_event: Any = None
         sim._on_pop = self._on_pop
         self._stop_fn = sim.stop
 
@@ -96,6 +97,7 @@ class Tracer:
             self.hidden += 1
             return
         ident: Optional[Ident] = getattr(proc, "ident", None)
+        self.current_event = ev         # what is being popped (a resolver reads a new process's arguments off it)
         if ident is None:
             ident = self.resolver(proc) if self.resolver is not None else Ident(ROLE_MODEL, 0, 0xFFFF)
             proc.ident = ident

@@ -111,7 +111,7 @@ def main() -> None:
     path = os.path.join(GOLDEN, "netsimple_summaries.json")
     summaries = json.load(open(path)) if os.path.exists(path) else {}
     # 1. full traces, short horizon
-    for seed, replica, horizon in ((0, 0, 1800.0), (7, 3, 900.0)):
+    for seed, replica, horizon in ((0, 0, 1800.0), (7, 3, 900.0), (0, 0, 600.0), (0, 49999, 600.0)):
         model = netsimple.run_replica(seed, replica, horizon)
         s, arr = summary_of(model, horizon)
         np.savez_compressed(os.path.join(GOLDEN, f"netsimple_trace_s{seed}_r{replica}_{int(horizon)}s.npz"), trace=arr)
@@ -119,7 +119,7 @@ def main() -> None:
         model.close()
         print("trace", seed, replica, horizon, s["events"], flush=True)
     # 2. summaries, 1 h horizon, several streams
-    jobs = [(0, r, 3600.0) for r in (0, 1, 2, 3, 63, 99999)] + [(1, 0, 3600.0), (123456789012, 5, 3600.0)]
+    jobs = [(0, r, 3600.0) for r in (0, 1, 2, 3, 63, 49999, 99999)] + [(1, 0, 3600.0), (123456789012, 5, 3600.0)]
     if "--full" in sys.argv:
         jobs.append((0, 0, 43200.0))
     for seed, replica, horizon in jobs:

@@ -49,14 +49,20 @@ def load_golden_trace(name):
     return np.load(os.path.join(GOLDEN, name))["trace"]
 
 
-def assert_trace_equal(got, ref, rtol=1e-9):
-    """Bit-exact on event order / kinds / programs / nodes / packet sizes; timestamps within rtol (north_star:
-    1e-9 relative, float64 FP-order note)."""
+def assert_trace_equal(got, ref, rtol=0.0):
+    """Bit-exact on event order / kinds / programs / nodes / packet sizes AND on the timestamps (rtol = 0): every side
+    computes them with the same IEEE operations in the same order -- no FMA contraction (-fmad=false /
+    -ffp-contract=off), one shared logarithm (log_f64 in itsb_core.cuh == oracle/philox.py).  north_star allows 1e-9
+    relative; the engine does not need the allowance."""
     assert len(got) == len(ref), f"trace length {len(got)} != {len(ref)}"
     for field in ("kind", "prog", "node", "aux"):
         neq = np.nonzero(got[field] != ref[field])[0]
         assert len(neq) == 0, f"first {field} mismatch at event {neq[0]}: got {got[neq[0]]}, ref {ref[neq[0]]}"
-    assert np.allclose(got["t"], ref["t"], rtol=rtol, atol=0.0)
+    if rtol == 0.0:
+        neq = np.nonzero(got["t"] != ref["t"])[0]
+        assert len(neq) == 0, f"first timestamp mismatch at event {neq[0]}: got {got['t'][neq[0]]!r}, ref {ref['t'][neq[0]]!r}"
+    else:
+        assert np.allclose(got["t"], ref["t"], rtol=rtol, atol=0.0)
 
 
 def telemetry_matches_summary(tm, s):

@@ -231,6 +231,11 @@ int itsb_state_bytes(itsb_engine* e, uint64_t* hot, uint64_t* arena) {
     return ITSB_OK;
 }
 
+int itsb_eval_log(itsb_engine*, const double* x, double* y, size_t n) {
+    for (size_t i = 0; i < n; ++i) y[i] = log_f64(x[i]);
+    return ITSB_OK;
+}
+
 const char* itsb_last_error(itsb_engine* e) { return e ? e->err.c_str() : ""; }
 void itsb_destroy(itsb_engine* e) { delete e; }
 

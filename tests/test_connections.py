@@ -30,8 +30,8 @@ def assert_same(got, ref):
     for name, col in (("node", 1), ("local_ip", 2), ("local_port", 3), ("inbound", 4), ("remote_ip", 5),
                       ("remote_port", 6), ("sent_bytes", 7), ("received_bytes", 8)):
         assert [int(x) for x in got[name]] == [int(r[col]) for r in ref], name
-    assert np.allclose(got["t_end"], [r[0] for r in ref], rtol=1e-9, atol=0.0)
-    assert np.allclose(got["t_start"], [r[9] for r in ref], rtol=1e-9, atol=0.0)
+    assert np.array_equal(got["t_end"], np.array([r[0] for r in ref], dtype=np.float64))
+    assert np.array_equal(got["t_start"], np.array([r[9] for r in ref], dtype=np.float64))
 
 
 @pytest.mark.parametrize("backend", BACKENDS)

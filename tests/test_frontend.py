@@ -34,13 +34,13 @@ def non_marks(trace):
     return trace[trace["kind"] != L.TRACE_MARK]
 
 
-def assert_same_events(got, ref, rtol=1e-9):
+def assert_same_events(got, ref, rtol=0.0):
     got, ref = non_marks(got), non_marks(ref)
     assert len(got) == len(ref), (len(got), len(ref))
     for field in ("kind", "prog", "node", "aux"):
         neq = np.nonzero(got[field] != ref[field])[0]
         assert len(neq) == 0, f"first {field} mismatch at event {neq[0]}: got {got[neq[0]]}, ref {ref[neq[0]]}"
-    assert np.allclose(got["t"], ref["t"], rtol=rtol, atol=0.0)
+    assert np.array_equal(got["t"], ref["t"]) if rtol == 0.0 else np.allclose(got["t"], ref["t"], rtol=rtol, atol=0.0)
 
 
 def named_marks(sim, trace, names):

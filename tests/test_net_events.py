@@ -20,10 +20,16 @@ def engine_log(backend, hostemu, seed, replica, horizon, cap=20000):
     return eng
 
 
-@pytest.mark.parametrize("backend", BACKENDS)
-def test_log_matches_the_oracle(backend, hostemu):
+KERNEL_BACKENDS = BACKENDS + [pytest.param("gpu:vote", id="gpu-k_run_vote", marks=pytest.mark.gpu)]
+
+
+@pytest.mark.parametrize("backend", KERNEL_BACKENDS)
+def test_log_matches_the_oracle(backend, hostemu, monkeypatch):
     import netsimple as oracle_netsimple
     seed, replica, horizon = 4, 2, 1500.0
+    if backend.startswith("gpu"):
+        monkeypatch.setenv("ITSB_KERNEL", "vote" if backend.endswith("vote") else "warp")
+        backend = "gpu"
     eng = engine_log(backend, hostemu, seed, replica, horizon)
     got = eng.net_events(0)
     model = oracle_netsimple.run_replica(seed, replica, horizon, trace=False)
@@ -33,7 +39,7 @@ def test_log_matches_the_oracle(backend, hostemu):
     assert [int(x) for x in got["node"]] == [r[1] for r in ref]
     assert [int(x) for x in got["port"]] == [r[2] for r in ref]
     assert [int(x) for x in got["type"]] == [r[3] for r in ref]
-    assert np.allclose(got["t"], [r[0] for r in ref], rtol=1e-9, atol=0.0)
+    assert np.array_equal(got["t"], np.array([r[0] for r in ref], dtype=np.float64))
     # every socket that is opened and closed is closed after it was opened, on the same node and port
     opened = {}
     for rec in got:

@@ -62,3 +62,53 @@ def test_event_definition_excludes_helper_hops():
     kinds = [r[1] for r in tracer.records]
     assert kinds == [evtrace.PROC_START, evtrace.THROW, evtrace.STOP]
     assert tracer.hidden > 0
+
+
+# ---- the reference's own example files, executed unmodified (oracle/ref_example.py) --------------------------------
+needs_example = pytest.mark.skipif(
+    not os.path.isfile(os.path.join(REFERENCE, "examples", "network_simple", "network_simple.py")),
+    reason="reference tree not on this box")
+
+
+def _assert_same_run(ref, ours):
+    """Bit for bit: every column of the trace (timestamps included: the same float operations on the same draws),
+    the connection records the override Socket logs, the draws consumed, the final clock."""
+    assert ref["summary"]["events"] == ours["summary"]["events"]
+    assert ref["summary"]["counts"] == ours["summary"]["counts"]
+    assert_trace_equal(ref["trace"], ours["trace"], rtol=0.0)
+    assert ref["connections"] == ours["connections"]
+    assert ref["draws"] == ours["draws"] and ref["now"] == ours["now"]
+
+
+@needs_example
+@pytest.mark.parametrize("seed,replica,duration", [(0, 0, 900.0), (7, 3, 700.0), (42, 17, 650.0), (123456789012, 5, 650.0)])
+def test_restatement_equals_the_reference_example_run_unmodified(seed, replica, duration):
+    """examples/network_simple/network_simple.py + network_simple_overrides.py, run as __main__ where they lie, against
+    oracle/netsimple.py on the same Philox stream: this is what pins the flagship workload's oracle (SURVEY rows
+    a16-a17) to the reference's own code instead of to a restatement of it."""
+    import ref_example
+    both = ref_example.compare_with_restatement("network_simple.py", seed, replica, duration)
+    _assert_same_run(both["reference"], both["restatement"])
+    assert len(both["reference"]["connections"]) > 0
+
+
+@needs_example
+@pytest.mark.parametrize("seed,replica,duration", [(0, 0, 500.0), (2, 41, 450.0), (9, 1000000, 400.0)])
+def test_malware_restatement_equals_the_reference_script_run_unmodified(seed, replica, duration):
+    """examples/network_simple/malware_simple.py (module-level script: init, Internet, infected = next(distribution(..)),
+    route, command_and_control, sim.run) against oracle/netsimple.MalwareModel (row a18)."""
+    import ref_example
+    both = ref_example.compare_with_restatement("malware_simple.py", seed, replica, duration)
+    _assert_same_run(both["reference"], both["restatement"])
+    kinds = both["reference"]["trace"]["prog"]
+    assert (kinds == 14).sum() > 0 and (kinds == 15).sum() > 0     # exfiltrate and route really ran
+
+
+@needs_example
+def test_golden_traces_are_what_the_reference_example_produces_now():
+    """The committed golden vectors the GPU tests compare against, regenerated from the reference's files here."""
+    import ref_example
+    out = ref_example.run_network_simple(7, 3, 900.0)
+    assert_trace_equal(out["trace"], load_golden_trace("netsimple_trace_s7_r3_900s.npz"), rtol=0.0)
+    out = ref_example.run_malware_simple(0, 0, 900.0)
+    assert_trace_equal(out["trace"], load_golden_trace("malware_trace_s0_r0_900s.npz"), rtol=0.0)
