@@ -311,6 +311,10 @@ int itsb_read_replica_telemetry(itsb_engine* e, uint64_t replica, uint64_t* dst,
 /* Sums the telemetry vector over all ranks (ncclAllReduce, SUM, uint64) -- the only collective on this path.
  * nccl_comm is an ncclComm_t created by the caller; the reduced vector is left on the device and in dst.          */
 int itsb_allreduce_telemetry(itsb_engine* e, void* nccl_comm, uint64_t* dst, size_t n);
+/* uint64 all-reduce of a small host vector over the ranks (op: 0 = sum, 2 = max, ncclRedOp_t): what a one-process-per-
+ * GPU host needs besides the telemetry sum -- a barrier, the slowest rank's time, the job's event count -- without
+ * a second communication library.  buf (n <= 4096) is read, reduced on the device through NCCL, and written back. */
+int itsb_allreduce_u64(itsb_engine* e, void* nccl_comm, uint64_t* buf, size_t n, int op);
 /* Helpers so a ctypes host can build the communicator without an NCCL binding of its own.                         */
 int itsb_nccl_unique_id(void* id128, size_t cap);
 int itsb_nccl_comm_init(itsb_engine* e, int nranks, int rank, const void* id128, void** comm_out);

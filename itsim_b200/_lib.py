@@ -105,6 +105,7 @@ _SIGNATURES = {
     "itsb_read_telemetry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsb_read_replica_telemetry": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]),
     "itsb_allreduce_telemetry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "itsb_allreduce_u64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "itsb_nccl_unique_id": (C.c_int, [C.c_void_p, C.c_size_t]),
     "itsb_nccl_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
     "itsb_nccl_comm_destroy": (C.c_int, [C.c_void_p]),

@@ -27,12 +27,16 @@
 
 extern "C" __global__ void k_run_in_place(const RunParams p);   /* itsb_inplace.cu */
 extern "C" __global__ void k_run_wide(const RunParams p);       /* itsb_wide.cu: 13..16 warps per CTA */
+extern "C" __global__ void k_run_vote(const RunParams p);       /* itsb_lanes.cu: a replica per lane + per-warp majority key */
+#if defined(ITSB_EXPERIMENTS)
+/* Variants measured slower in round 1 (profiles/README.md holds the tables); built only with -DITSB_EXPERIMENTS
+ * (python __graft_entry__.py --experiments), never part of the product library. */
 extern "C" __global__ void k_run_phased(const RunParams p);     /* itsb_phased.cu: warps aligned on the loop's two halves */
-extern "C" __global__ void k_run_lanes(const RunParams p);      /* itsb_lanes.cu: experiment, a replica per lane */
-extern "C" __global__ void k_run_vote(const RunParams p);       /* itsb_lanes.cu: experiment, lanes + per-warp majority key */
-extern "C" __global__ void k_run_sorted(const RunParams p);
-extern "C" __global__ void k_run_pool(const RunParams p);       /* itsb_pool.cu: experiment, replicas change warps via per-kind rings */
-extern "C" size_t itsb_pool_shared_bytes(void);     /* itsb_sorted.cu: experiment, lanes regrouped by next event */
+extern "C" __global__ void k_run_lanes(const RunParams p);      /* itsb_lanes.cu: a replica per lane, no vote */
+extern "C" __global__ void k_run_sorted(const RunParams p);     /* itsb_sorted.cu: lanes regrouped by next event, CTA-wide */
+extern "C" __global__ void k_run_pool(const RunParams p);       /* itsb_pool.cu: replicas change warps via per-kind rings */
+extern "C" size_t itsb_pool_shared_bytes(void);
+#endif
 
 /* up to 12 warps per CTA (what shared memory allows the flagship model): 168 registers per thread, no spills */
 extern "C" __global__ void __launch_bounds__(384, 1) k_run(const RunParams p) {
@@ -99,7 +103,8 @@ extern "C" __global__ void k_eval_log(double* v, size_t n) {
  *   k_run_lanes without the vote and k_run_sorted with a CTA-wide regrouping: experiments).
  * Default: k_run_vote where it is the faster one -- models whose tables fit shared memory and that keep no connection
  * records (their per-socket correlation is lane-parallel work in the warp-per-replica kernels).  ITSB_KERNEL=
- * warp | vote | lanes | sorted | phased overrides, ITSB_KERNEL_CTAS=n sets the CTAs per SM of the lane kernels. */
+ * warp | vote overrides (lanes | sorted | pool | phased too in a -DITSB_EXPERIMENTS build), ITSB_KERNEL_CTAS=n sets
+ * the CTAs per SM of the lane kernels. */
 enum { K_WARP = 0, K_WIDE, K_IN_PLACE, K_PHASED, K_VOTE, K_LANES, K_SORTED, K_POOL };
 static const char* const KERNEL_NAMES[] = {"k_run", "k_run_wide", "k_run_in_place", "k_run_phased", "k_run_vote",
                                            "k_run_lanes", "k_run_sorted", "k_run_pool"};
@@ -125,6 +130,7 @@ struct itsb_engine {
     long long* d_first_failed = nullptr;
     unsigned long long* d_telemetry = nullptr;
     Model* d_model = nullptr;                     /* the table pointers, in device memory (template build) */
+    unsigned long long* d_scratch = nullptr;      /* itsb_allreduce_u64 */
     uint64_t n_replicas = 0;
     uint64_t launches = 0;
     uint32_t warps_per_cta = 0, grid = 0;
@@ -133,6 +139,7 @@ struct itsb_engine {
     int kernel = 0;                               /* K_*: which engine kernel itsb_run launches (choose_kernel) */
     int kernel_ctas = 3;                          /* CTAs of 256 threads per SM for the lane-per-replica kernels */
     bool forced_in_place = false;
+    bool lane_smem_ok = false;                    /* the lane kernels' dynamic shared memory (model tables) was granted */
     float last_ms = 0.f;
     long long first_failed = -1;
     std::string err;
@@ -143,13 +150,18 @@ static void choose_kernel(itsb_engine* e) {
     const char* c = getenv("ITSB_KERNEL_CTAS");
     e->kernel_ctas = c && atoi(c) >= 1 && atoi(c) <= 8 ? atoi(c) : 3;
     const std::string want = k ? k : "";
-    const bool lane_ok = !e->rp.tables_in_hbm && !e->forced_in_place;
+    /* a lane per replica: the model tables must fit beside three CTAs per SM (cudaFuncSetAttribute in itsb_load_model) */
+    const bool lane_ok = !e->rp.tables_in_hbm && !e->forced_in_place && e->lane_smem_ok;
     int warp_kernel = e->rp.state_in_hbm ? K_IN_PLACE : (e->warps_per_cta > 12 ? K_WIDE : K_WARP);
+#if defined(ITSB_EXPERIMENTS)
     if (want == "phased" && warp_kernel == K_WARP) warp_kernel = K_PHASED;
+#endif
     if (lane_ok && want == "vote") e->kernel = K_VOTE;
+#if defined(ITSB_EXPERIMENTS)
     else if (lane_ok && want == "lanes") e->kernel = K_LANES;
     else if (lane_ok && want == "sorted") e->kernel = K_SORTED;
     else if (lane_ok && want == "pool") e->kernel = K_POOL;
+#endif
     else if (want == "warp" || want == "phased" || !lane_ok) e->kernel = warp_kernel;
     else {
         /* a lane per replica needs replicas to fill its threads (148 SMs x 768): measured on the default model, the two
@@ -264,14 +276,26 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     e->warps_per_cta = w;
     e->rp.warps_per_cta = w;
     e->forced_in_place = force && force[0] == '1';
-    choose_kernel(e);
     e->grid = (uint32_t)e->prop.multiProcessorCount;
     CU(e, cudaFuncSetAttribute(k_run, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     CU(e, cudaFuncSetAttribute(k_run_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    CU(e, cudaFuncSetAttribute(k_run_in_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    /* the lane-per-replica kernel stages only the model tables: more than 48 KB of them (a 4- or 8-subnet LAN: 57 KB,
+       115 KB) needs the opt-in too; tables that leave no room for its CTAs send the model to the warp kernels */
+    e->lane_smem_ok = !e->rp.tables_in_hbm &&
+                      cudaFuncSetAttribute(k_run_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->so.total) == cudaSuccess;
+    cudaGetLastError();
+#if defined(ITSB_EXPERIMENTS)
     CU(e, cudaFuncSetAttribute(k_run_phased, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
     CU(e, cudaFuncSetAttribute(k_run_pool, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)(e->so.total + itsb_pool_shared_bytes())));
-    CU(e, cudaFuncSetAttribute(k_run_in_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+    if (e->lane_smem_ok) {
+        CU(e, cudaFuncSetAttribute(k_run_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->so.total));
+        CU(e, cudaFuncSetAttribute(k_run_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(e->so.total + 256 * (sizeof(PendingEvent) + sizeof(RunCtx) + 2 + 1 + 4) + 64)));
+    }
+#endif
+    choose_kernel(e);
     e->loaded = true;
     return ITSB_OK;
 }
@@ -294,12 +318,17 @@ int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first
     e->rp.netlog = e->d_netlog; e->rp.connlog = e->d_connlog; e->rp.conntab = e->d_conntab;
     e->rp.n_replicas = n; e->rp.seed = seed;
     e->rp.ticket = e->d_ticket; e->rp.events_done = e->d_ticket + 1; e->rp.first_failed = e->d_first_failed;
-    unsigned char* tmpl = nullptr;
-    ArenaNode* tmpl_arena = nullptr;
-    uint32_t* tmpl_free = nullptr;
-    CU(e, cudaMalloc(&tmpl, L.hot_bytes));
-    CU(e, cudaMalloc(&tmpl_arena, (size_t)L.arena_nodes * sizeof(ArenaNode)));
-    CU(e, cudaMalloc(&tmpl_free, (size_t)L.arena_nodes * sizeof(uint32_t)));
+    /* the t = 0 template: temporaries released on every way out */
+    struct Temp {
+        void* p[3] = {nullptr, nullptr, nullptr};
+        ~Temp() { for (void* q : p) cudaFree(q); }
+    } tmp;
+    CU(e, cudaMalloc(&tmp.p[0], L.hot_bytes));
+    CU(e, cudaMalloc(&tmp.p[1], (size_t)L.arena_nodes * sizeof(ArenaNode)));
+    CU(e, cudaMalloc(&tmp.p[2], (size_t)L.arena_nodes * sizeof(uint32_t)));
+    unsigned char* tmpl = (unsigned char*)tmp.p[0];
+    ArenaNode* tmpl_arena = (ArenaNode*)tmp.p[1];
+    uint32_t* tmpl_free = (uint32_t*)tmp.p[2];
     CU(e, cudaMemsetAsync(tmpl, 0, L.hot_bytes, e->stream));
     {
         std::vector<uint32_t> ident(L.arena_nodes);
@@ -313,7 +342,6 @@ int itsb_init_replicas(itsb_engine* e, uint64_t n, uint64_t seed, uint64_t first
     k_fan_out<<<blocks, 256, 0, e->stream>>>(e->rp, tmpl, tmpl_arena, first_replica_id);
     CU(e, cudaGetLastError());
     CU(e, cudaStreamSynchronize(e->stream));
-    cudaFree(tmpl); cudaFree(tmpl_arena); cudaFree(tmpl_free);
     const long long none = 0x7FFFFFFFFFFFFFFFll;
     CU(e, cudaMemcpy(e->d_first_failed, &none, sizeof(none), cudaMemcpyHostToDevice));
     CU(e, cudaMemset(e->d_ticket, 0, 2 * sizeof(unsigned long long)));
@@ -336,13 +364,15 @@ int itsb_run_async(itsb_engine* e, double duration) {
     const uint32_t lane_grid = e->grid * (uint32_t)e->kernel_ctas;
     switch (e->kernel) {
     case K_VOTE:     k_run_vote<<<lane_grid, 256, e->so.total, e->stream>>>(e->rp); break;
+#if defined(ITSB_EXPERIMENTS)
     case K_LANES:    k_run_lanes<<<lane_grid, 256, e->so.total, e->stream>>>(e->rp); break;
     case K_SORTED:   k_run_sorted<<<lane_grid, 256, e->so.total + 256 * (sizeof(PendingEvent) + sizeof(RunCtx) + 2 + 1 + 4) + 64,
                                     e->stream>>>(e->rp); break;
     case K_POOL:     k_run_pool<<<lane_grid, 256, e->so.total + itsb_pool_shared_bytes(), e->stream>>>(e->rp); break;
+    case K_PHASED:   k_run_phased<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp); break;
+#endif
     case K_IN_PLACE: k_run_in_place<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp); break;
     case K_WIDE:     k_run_wide<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp); break;
-    case K_PHASED:   k_run_phased<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp); break;
     default:         k_run<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp); break;
     }
     CU(e, cudaGetLastError());
@@ -468,7 +498,8 @@ extern "C" __global__ void k_histogram(const unsigned char* hot, uint32_t hot_by
 static int reduce_telemetry(itsb_engine* e) {
     CU(e, cudaMemsetAsync(e->d_telemetry, 0, ITSB_TM_SIZE * sizeof(unsigned long long), e->stream));
     uint32_t blocks = (uint32_t)(e->n_replicas < 1024 ? e->n_replicas : 1024);
-    k_reduce_telemetry<<<blocks, 96, 0, e->stream>>>(e->d_hot, e->rp.layout.hot_bytes, e->rp.layout.off_stats, e->n_replicas, e->d_telemetry);
+    static_assert(ITSB_TM_SIZE <= 128, "k_reduce_telemetry: one thread per telemetry slot");
+    k_reduce_telemetry<<<blocks, 128, 0, e->stream>>>(e->d_hot, e->rp.layout.hot_bytes, e->rp.layout.off_stats, e->n_replicas, e->d_telemetry);
     CU(e, cudaGetLastError());
     e->launches += 1;
     return ITSB_OK;
@@ -545,17 +576,40 @@ int itsb_allreduce_telemetry(itsb_engine* e, void* comm, uint64_t* dst, size_t n
     return ITSB_OK;
 }
 
+int itsb_allreduce_u64(itsb_engine* e, void* comm, uint64_t* buf, size_t n, int op) {
+    if (!e || !comm || !buf || n == 0 || n > 4096 || (op != 0 && op != 2)) return ITSB_ERR_STATE;
+    nccl_all_reduce_fn fn = (nccl_all_reduce_fn)nccl_sym("ncclAllReduce");
+    if (!fn) { e->err = "libnccl.so.2 not found"; return ITSB_ERR_NCCL; }
+    CU(e, cudaSetDevice(e->device));
+    if (!e->d_scratch) CU(e, cudaMalloc(&e->d_scratch, 4096 * sizeof(uint64_t)));
+    CU(e, cudaMemcpyAsync(e->d_scratch, buf, n * sizeof(uint64_t), cudaMemcpyHostToDevice, e->stream));
+    if (fn(e->d_scratch, e->d_scratch, n, 5 /* ncclUint64 */, op, comm, e->stream) != 0) {
+        e->err = "ncclAllReduce failed"; return ITSB_ERR_NCCL;
+    }
+    CU(e, cudaMemcpyAsync(buf, e->d_scratch, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    return ITSB_OK;
+}
+
 int itsb_histogram(itsb_engine* e, uint32_t slot, uint64_t lo, uint64_t width, uint32_t nbins, int only_nonzero,
                    void* comm, uint64_t* dst) {
     if (!e || !e->n_replicas || !dst || slot >= ITSB_TM_SIZE || width == 0 || nbins == 0 || nbins > 4096) return ITSB_ERR_STATE;
     CU(e, cudaSetDevice(e->device));
     unsigned long long* d_bins = nullptr;
     CU(e, cudaMalloc(&d_bins, nbins * sizeof(unsigned long long)));
-    CU(e, cudaMemsetAsync(d_bins, 0, nbins * sizeof(unsigned long long), e->stream));
-    const uint32_t blocks = (uint32_t)((e->n_replicas + 255) / 256 < 592 ? (e->n_replicas + 255) / 256 : 592);
-    k_histogram<<<blocks, 256, nbins * sizeof(unsigned int), e->stream>>>(
-        e->d_hot, e->rp.layout.hot_bytes, e->rp.layout.off_stats, e->n_replicas, slot, lo, width, nbins, only_nonzero, d_bins);
-    e->launches += 1;
+    cudaError_t c0 = cudaMemsetAsync(d_bins, 0, nbins * sizeof(unsigned long long), e->stream);
+    if (c0 == cudaSuccess) {
+        const uint32_t blocks = (uint32_t)((e->n_replicas + 255) / 256 < 592 ? (e->n_replicas + 255) / 256 : 592);
+        k_histogram<<<blocks, 256, nbins * sizeof(unsigned int), e->stream>>>(
+            e->d_hot, e->rp.layout.hot_bytes, e->rp.layout.off_stats, e->n_replicas, slot, lo, width, nbins, only_nonzero, d_bins);
+        c0 = cudaGetLastError();
+        e->launches += 1;
+    }
+    if (c0 != cudaSuccess) {
+        cudaFree(d_bins);
+        e->err = std::string("itsb_histogram: ") + cudaGetErrorString(c0);
+        return ITSB_ERR_CUDA;
+    }
     int rc = ITSB_OK;
     if (comm) {
         nccl_all_reduce_fn fn = (nccl_all_reduce_fn)nccl_sym("ncclAllReduce");
@@ -620,7 +674,7 @@ void itsb_destroy(itsb_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     free_replicas(e);
     for (int i = 0; i < ITSB_NUM_BLOBS; ++i) cudaFree(e->d_tables[i]);
-    cudaFree(e->d_ticket); cudaFree(e->d_first_failed); cudaFree(e->d_telemetry); cudaFree(e->d_model);
+    cudaFree(e->d_ticket); cudaFree(e->d_first_failed); cudaFree(e->d_telemetry); cudaFree(e->d_model); cudaFree(e->d_scratch);
     if (e->ev_start) cudaEventDestroy(e->ev_start);
     if (e->ev_stop) cudaEventDestroy(e->ev_stop);
     if (e->stream) cudaStreamDestroy(e->stream);

@@ -271,6 +271,8 @@ struct Layout {             /* byte offsets inside one replica's hot block */
     u32 off_tab, table_words;
     u32 log_cap;            /* network_event records per replica (HBM) */
     u32 conn_cap, conn_window, off_sockx, address_tags;   /* connection records (overrides.py:102-186) */
+    u32 off_ndig;           /* delivery digests: one u32 per node (see node_digest_compute) */
+    u32 off_nmask, off_pmask;   /* per node / per process: which hostname fields the remembered packets carry (64-bit Bloom) */
 };
 
 struct Model {              /* pointers to the static tables (shared-memory copies inside the kernel) */
@@ -340,6 +342,9 @@ struct Rep {                /* register-resident working view of one replica */
     Sock* sock;
     u16* sock_free;
     NodeDyn* node;
+    u32* ndig;
+    u64* nmask;
+    u64* pmask;
     u64* stats;
     ArenaNode* arena;
     u32* arena_free;
@@ -372,6 +377,9 @@ ITSB_FN void rebind(Rep& R, Hdr* H) {
     R.sock = (Sock*)(hot + H->L.off_sock);
     R.sock_free = (u16*)(hot + H->L.off_sock_free);
     R.node = (NodeDyn*)(hot + H->L.off_node);
+    R.ndig = (u32*)(hot + H->L.off_ndig);
+    R.nmask = (u64*)(hot + H->L.off_nmask);
+    R.pmask = (u64*)(hot + H->L.off_pmask);
     R.stats = (u64*)(hot + H->L.off_stats);
     R.arena = H->arena;
     R.arena_free = H->arena_free;
@@ -423,6 +431,9 @@ ITSB_COLD void fail(Hdr* H, int status, u64 detail) {
         H->detail = detail;
     }
 }
+
+/* delivery digests (defined with the sockets, below) */
+ITSB_COLD void node_digest_refresh(Hdr* H, u32 node);
 
 /* ---- event data word: kind[0:4] exc[4:12] proc[12:25] gen[25:32]; packet events: kind[0:4] arena-index[4:32] ---- */
 static const u32 PROC_MASK = 0x1FFF;   /* up to 8192 process slots per replica */
@@ -579,7 +590,17 @@ ITSB_COLD double draw_dist(Hdr* H, const itsb_dist* Dp) {
 }
 
 /* ---- telemetry ------------------------------------------------------------------------------------------------------ */
+/* A counter update.  In the lane-per-replica kernel the counters live in HBM and a read-modify-write makes the lane wait
+ * for the load (round 2 profile: ~5 % of all stall samples on these lines); a replica's counters are touched by its own
+ * lane only, so the update goes out as a reduction (RED.ADD at the L2, nothing to wait for) and the few reads (the
+ * run's event count, STAT_FIRST) bypass the L1, which a reduction does not update. */
+#if defined(__CUDACC__) && defined(ITSB_LANES)
+ITSB_FN void stat_add(Rep& R, u32 slot, u64 v) { atomicAdd((unsigned long long*)&R.stats[slot], (unsigned long long)v); }
+ITSB_FN u64 stat_get(Rep& R, u32 slot) { return __ldcg((const unsigned long long*)&R.stats[slot]); }
+#else
 ITSB_FN void stat_add(Rep& R, u32 slot, u64 v) { R.stats[slot] += v; }
+ITSB_FN u64 stat_get(Rep& R, u32 slot) { return R.stats[slot]; }
+#endif
 
 ITSB_COLD void trace_put(Hdr* H, u32 kind, u32 prog, u32 node, u32 aux) {
     u32 n = H->trace_count;
@@ -594,7 +615,7 @@ ITSB_COLD void trace_put(Hdr* H, u32 kind, u32 prog, u32 node, u32 aux) {
 /* one `network_event` record (itsim/schemas/items.py:83-131): a socket opened (type 1) or closed (type 2) */
 ITSB_COLD void net_event_put(Hdr* H, u32 type, u32 node, u32 port, u32 src_ip, u32 prog, int pid, u32 protocol) {
     if (H->netlog == nullptr) return;
-    ((u64*)((unsigned char*)H + H->L.off_stats))[ITSB_TM_USER0 + 7] += 1;   /* records produced (user slot 7) */
+    { Rep Rs; Rs.stats = (u64*)((unsigned char*)H + H->L.off_stats); stat_add(Rs, ITSB_TM_USER0 + 7, 1); }   /* records produced (user slot 7) */
     const u32 n = H->log_count;
     if (n < H->L.log_cap && lane_id() == 0) {
         itsb_net_event E;
@@ -608,7 +629,7 @@ ITSB_COLD void net_event_put(Hdr* H, u32 type, u32 node, u32 port, u32 src_ip, u
 
 /* one simulated event of the given kind (SURVEY.md section 8-d definition) */
 ITSB_FN void count_event(Rep& R, u32 kind, u32 prog, u32 node, u32 aux) {
-    R.stats[ITSB_TM_KIND0 + kind] += 1;
+    stat_add(R, ITSB_TM_KIND0 + kind, 1);
     if (R.trace) trace_put(R.hdr, kind, prog, node, aux);
 }
 
@@ -888,6 +909,137 @@ ITSB_FN u32 ev_take(Rep& R, int src) {
     return ovf_take_min(H);
 }
 
+/* ---- delivery digests ----------------------------------------------------------------------------------------------
+ * What the delivery pass (on_deliver) wants to know about a recipient, in one word per node, kept beside the tables it
+ * summarises: a broadcast reaches all 51 nodes of network_simple, and finding out what each does with it by walking
+ * node -> socket list -> waiting process -> its instruction -> its filter (-> the packets it remembers) is four or more
+ * dependent loads per recipient on state that lives in HBM for the lane-per-replica kernel (round 1: 6.6 DRAM sectors
+ * per counted event, 85 % of stall samples waiting on those loads).  The digests of a network's nodes are contiguous:
+ * 51 x 4 bytes = 7 sectors.
+ *
+ *   port[0:16]  filter[16:24]  flags[24:32]
+ *   ND_SINGLE   the node has exactly one socket, bound to `port` (no socket at all: ND_SINGLE with port 0, which is
+ *               never bound) -- a packet for any other port finds nothing: dropped without looking further
+ *   ND_RETIRE   the socket bound to `port` has exactly one waiter, parked inside recv() of a RECV_FILTER loop head
+ *               (phase 1) using filter `filter`, with the node still in the wake epoch the loop remembered, the queue
+ *               empty.  A packet its filter rejects can then be retired on the spot (see on_deliver) from this word
+ *               and the static tables alone.  ND_LISTED: that process remembers at least one packet; nmask[node] then
+ *               holds a 64-bit Bloom filter (bit = hostname field & 63) of the packets it remembers, a copy of the
+ *               process's pmask: a packet whose bit is clear is certainly not "listed"
+ *
+ * A digest is a set of STATEMENTS, each of which must be true whenever it is present; an absent statement (flags 0) only
+ * sends the pass back to the tables.  The points that can falsify a statement update the word: a socket opened /
+ * closed, a process parking on or leaving a socket's wait list, a delivery waking a socket's waiters, the node
+ * sleeping or waking (epoch), and -- for pmask -- the three list instructions.  tests/hostemu builds with
+ * ITSB_CHECK_DIGEST verify every statement against the tables before every use and fail the replica otherwise. */
+enum { ND_RETIRE = 1u << 24, ND_LISTED = 1u << 25, ND_SINGLE = 1u << 26 };
+
+/* the statements recomputed from the tables (socket closed, exception delivered: the rare points) */
+ITSB_COLD void node_digest_refresh(Hdr* H, u32 node) {
+    Rep R; rebind(R, H);
+    if (H->L.max_sig != 0) { R.ndig[node] = 0; return; }   /* shipped-itsim sockets wait on signals: m_deliver */
+    const NodeDyn& N = R.node[node];
+    u32 n_socks = 0, d = 0, first_port = 0;
+    bool have = false;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (u16 s = N.sock_head; s != NIL16; s = R.sock[s].next) {
+        const Sock& S = R.sock[s];
+        if (n_socks == 0) first_port = S.port;
+        n_socks += 1;
+        const u16 w = S.wait_head;
+        if (have || w == NIL16 || S.q_len != 0) continue;
+        const Pcb& P = R.pcb[w];
+        if (P.wnext != NIL16 || P.phase != 1) continue;
+        const u64 ins = R.m.code[P.pc];
+        const u32 wop = (u32)(ins & 0xFF);
+        if (wop != OP_RECV_FILTER && wop != OP_RECV_FILTER_LOG) continue;
+        if (N.epoch != P.r[(u32)(ins >> 8) & 3]) continue;
+        have = true;
+        d = S.port | (((u32)(ins >> 16) & 0xFF) << 16) | ND_RETIRE | (P.list_head != NIL32 ? ND_LISTED : 0u);
+        R.nmask[node] = R.pmask[w];
+    }
+    if (n_socks == 0) d = ND_SINGLE;                    /* port 0: matches nothing */
+    else if (n_socks == 1) d = have ? (d | ND_SINGLE) : (first_port | ND_SINGLE);
+    R.ndig[node] = d;
+}
+
+/* a process parked inside recv() of a RECV_FILTER loop head on socket s (queue empty): everything is at hand */
+ITSB_FN void node_digest_parked(Rep& R, u32 node, u32 s, u32 p, u32 filter, u32 epoch_reg) {
+    if (R.hdr->L.max_sig != 0) return;
+    const NodeDyn& N = R.node[node];
+    const Sock& S = R.sock[s];
+    const Pcb& P = R.pcb[p];
+    const u32 old = R.ndig[node];
+    const u32 single = (N.sock_head == s && S.next == NIL16) ? (u32)ND_SINGLE : 0u;
+    if (S.wait_head == p && P.wnext == NIL16 && N.epoch == P.r[epoch_reg & 3]) {
+        R.ndig[node] = S.port | (filter << 16) | ND_RETIRE | (P.list_head != NIL32 ? ND_LISTED : 0u) | single;
+        if (P.list_head != NIL32) R.nmask[node] = R.pmask[p];
+    } else if ((old & 0xFFFF) == S.port) {
+        R.ndig[node] = single ? (S.port | single) : 0u;      /* a second waiter, or a stale epoch: nothing to retire */
+    }
+}
+
+/* a process parked on socket s by a plain recv(): whatever was said about retiring on that socket no longer holds */
+ITSB_FN void node_digest_waits(Rep& R, u32 node, u32 s) {
+    if (R.hdr->L.max_sig != 0) return;
+    const u32 old = R.ndig[node];
+    if ((old & ND_RETIRE) && (old & 0xFFFF) == R.sock[s].port) R.ndig[node] = (old & ND_SINGLE) ? (old & (0xFFFFu | ND_SINGLE)) : 0u;
+}
+
+/* a delivery woke every waiter of the socket bound to `port` */
+ITSB_FN void node_digest_woken(Rep& R, u32 node, u32 port) {
+    const u32 old = R.ndig[node];
+    if ((old & ND_RETIRE) && (old & 0xFFFF) == port) R.ndig[node] = (old & ND_SINGLE) ? (old & (0xFFFFu | ND_SINGLE)) : 0u;
+}
+
+/* the node slept or woke: its epoch moved on, so a loop head parked in recv() remembers a stale one */
+ITSB_FN void node_digest_epoch(Rep& R, u32 node) {
+    const u32 old = R.ndig[node];
+    if (old & ND_RETIRE) R.ndig[node] = (old & ND_SINGLE) ? (old & (0xFFFFu | ND_SINGLE)) : 0u;
+}
+
+/* socket s was just put at the head of the node's socket list */
+ITSB_FN void node_digest_opened(Rep& R, u32 node, u32 s) {
+    if (R.hdr->L.max_sig != 0) return;
+    const Sock& S = R.sock[s];
+    const u32 old = R.ndig[node];
+    if (S.next == NIL16) R.ndig[node] = S.port | ND_SINGLE;                 /* the node's only socket */
+    else R.ndig[node] = (old & ND_RETIRE) ? (old & ~(u32)ND_SINGLE) : 0u;   /* what was said about another socket stands */
+}
+
+#if defined(ITSB_CHECK_DIGEST)
+/* every statement of the stored digest, verified against the tables (test builds only) */
+static bool node_digest_valid(Rep& R, u32 node) {
+    const u32 d = R.ndig[node];
+    const NodeDyn& N = R.node[node];
+    if (R.hdr->L.max_sig != 0) return d == 0;
+    if (d & ND_SINGLE) {
+        if ((d & 0xFFFF) == 0) { if (N.sock_head != NIL16) return false; }
+        else if (N.sock_head == NIL16 || R.sock[N.sock_head].next != NIL16 || R.sock[N.sock_head].port != (d & 0xFFFF)) return false;
+    }
+    if (d & ND_RETIRE) {
+        u16 s = N.sock_head;
+        while (s != NIL16 && R.sock[s].port != (d & 0xFFFF)) s = R.sock[s].next;
+        if (s == NIL16) return false;
+        const Sock& S = R.sock[s];
+        if (S.wait_head == NIL16 || S.q_len != 0) return false;
+        const Pcb& P = R.pcb[S.wait_head];
+        const u64 ins = R.m.code[P.pc];
+        const u32 wop = (u32)(ins & 0xFF);
+        if (P.wnext != NIL16 || P.phase != 1 || (wop != OP_RECV_FILTER && wop != OP_RECV_FILTER_LOG)) return false;
+        if (((u32)(ins >> 16) & 0xFF) != ((d >> 16) & 0xFF) || N.epoch != P.r[(u32)(ins >> 8) & 3]) return false;
+        if (((d & ND_LISTED) != 0) != (P.list_head != NIL32)) return false;
+        u64 want = 0;
+        for (u32 n = P.list_head; n != NIL32; n = R.arena[n].next) want |= 1ull << (R.arena[n].f0 & 63);
+        if (R.pmask[S.wait_head] != want) return false;
+        if ((d & ND_LISTED) && R.nmask[node] != want) return false;
+    } else if (d & ND_LISTED) return false;
+    return true;
+}
+#endif
+
 /* ---- processes ----------------------------------------------------------------------------------------------------------- */
 ITSB_FN u32 handle_of(Rep& R, u32 p) { return p | ((u32)R.pcb[p].gen << 16); }
 
@@ -932,7 +1084,7 @@ ITSB_FN void list_free_all(Rep& R, Pcb& P) {
 ITSB_COLD void proc_exit(Hdr* H, u32 p) {
     Rep R; rebind(R, H);
     Pcb& P = R.pcb[p];
-    list_free_all(R, P);
+    if (P.list_head != NIL32) { list_free_all(R, P); R.pmask[p] = 0; }
     P.state = PS_FREE;
     P.gen = (u16)((P.gen + 1) & GEN_MASK);
     u32 top = H->pcb_free_top;
@@ -978,6 +1130,7 @@ ITSB_COLD void node_wake(Hdr* H, u32 node) {
     N.awake = 1;
     waiters_resume_all(R, N.wake_head, N.wake_tail);
     N.epoch += 1;
+    node_digest_epoch(R, node);
 }
 
 /* the ordered fallback of the delivery pass: one socket's waiters through the spilling push */
@@ -985,6 +1138,7 @@ ITSB_COLD void sock_resume_waiters(Hdr* H, u32 s) {
     Rep R; rebind(R, H);
     Sock& S = R.sock[s];
     waiters_resume_all(R, S.wait_head, S.wait_tail);
+    node_digest_woken(R, S.node, S.port);
 }
 
 /* ---- sockets ------------------------------------------------------------------------------------------------------------ */
@@ -1044,6 +1198,7 @@ ITSB_COLD int sock_open_on(Hdr* H, u32 p, u32 node, u32 port, bool own) {
     S.next = N.sock_head;
     N.sock_head = (u16)s;
     if (own) P.sock = (u16)s;
+    node_digest_opened(R, node, s);
     net_event_put(H, 1, node, port, R.m.nodes[node].addr, P.prog | ((u32)P.tags << 16), 0, 1);
     return (int)s;
 }
@@ -1074,10 +1229,30 @@ ITSB_COLD void sock_close(Hdr* H, u32 p) {
     R.sock_free[top] = (u16)s;
     H->sock_free_top = (u16)(top + 1);
     P.sock = NIL16;
+    node_digest_refresh(H, S.node);
 }
 
 /* ---- transmission ---------------------------------------------------------------------------------------------------------- */
 ITSB_FN Pkt* pkt_at(Rep& R, u32 k) { return (Pkt*)&R.arena[k]; }
+
+/* index of the node of network NET that owns address ip, or NIL32 (first match in link order).  Addresses handed out by
+ * Network.link are consecutive (cidr.hosts(), overrides.py:207-213), so the guess ip - addr(first) is checked first. */
+ITSB_FN u32 net_member(Rep& R, const itsb_net& NET, u32 ip) {
+    const u32 guess = ip - R.m.nodes[NET.first_node].addr;
+    u32 hit = NIL32;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+    for (u32 i = (u32)lane_id(); i < NET.n_nodes; i += ITSB_W) {
+        if (R.m.nodes[NET.first_node + i].addr == ip) { hit = i; if (ITSB_W == 1) break; }
+        if (ITSB_W == 1 && i == 0 && guess < NET.n_nodes && guess != 0 && R.m.nodes[NET.first_node + guess].addr == ip) {
+            /* only a shortcut when no earlier node has the same address: addresses on a network are unique
+               (AddressInUse, overrides.py:236-237), so the guess is the first match */
+            hit = guess; break;
+        }
+    }
+    return w_min(hit);
+}
 
 /* Socket.send -> Node._send_to_network -> Network.transmit (overrides.py:122-125,371-377,273-291): the packet
  * becomes a transmission process started with sim.add, i.e. one TX_BEGIN event at the current time. */
@@ -1086,11 +1261,8 @@ ITSB_COLD void net_send(Hdr* H, u32 src_node, u32 src_port, u32 dst_ip, u32 dst_
     Rep R; rebind(R, H);
     const itsb_node N = R.m.nodes[src_node];
     const itsb_net NET = R.m.nets[N.net];
-    if (dst_ip != NET.bcast) {
-        bool found = false;   /* must be a member of the network (CannotForward otherwise, overrides.py:293-297) */
-        for (u32 i = (u32)lane_id(); i < NET.n_nodes; i += ITSB_W)
-            if (R.m.nodes[NET.first_node + i].addr == dst_ip) found = true;
-        if (w_ballot(found) == 0) { fail(H, ITSB_EXC_NO_SUCH_ADDRESS, dst_ip); return; }
+    if (dst_ip != NET.bcast) {   /* must be a member of the network (CannotForward otherwise, overrides.py:293-297) */
+        if (net_member(R, NET, dst_ip) == NIL32) { fail(H, ITSB_EXC_NO_SUCH_ADDRESS, dst_ip); return; }
     }
     u32 k = arena_alloc(R);
     if (k == NIL32) return;
@@ -1198,14 +1370,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
     const bool bcast = (K.dst_ip == NET.bcast);
     u32 first = NET.first_node, count = NET.n_nodes;
     if (!bcast) {
-        u32 hit = NIL32;
-#if defined(__CUDACC__)
-#pragma unroll 1
-#endif
-        for (u32 i = (u32)lane_id(); i < NET.n_nodes; i += ITSB_W)
-            if (R.m.nodes[NET.first_node + i].addr == K.dst_ip) hit = i;
-        u32 m = w_min(hit);
-        first = NET.first_node + m;
+        first = NET.first_node + net_member(R, NET, K.dst_ip);
         count = 1;
     }
     const u32 dst_port = K.ports >> 16;
@@ -1217,27 +1382,73 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
             fast_ok = heap_min_t(H) > nb && (H->ovf_count == 0 || H->ovf_min_t > nb);
         }
     }
+    /* what a recipient's digest may decide on its own: "no socket on that port" always; "retired" when retiring is on
+       and the retired recv()'s correlation is not wanted (a model that keeps connection records does it per socket) */
+    const bool digest_retires = fast_ok && H->conntab == nullptr;
+    const u32 tag_bit = 1u << (K.tag & 31);
+#if ITSB_W == 1
+    /* a lane per replica: the whole pass usually needs nothing but the digests -- fetch their sectors together, and
+       keep the pass's counters in registers until it ends */
+    u32 q_valid = 0, q_found = 0, q_retired = 0;
+#if defined(__CUDACC__)
+    if (count > 8)
+        for (u32 o = 0; o < count; o += 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(R.ndig + first + o));
+#endif
+#endif
     for (u32 base = 0; base < count; base += ITSB_W) {
         u32 i = base + (u32)lane_id();
         bool valid = i < count;
         u32 node = first + i;
-        int s = valid ? sock_find(R, node, K.dst_ip, dst_port) : -1;
-        const bool found = s >= 0;
-        bool retire = false;
-        if (fast_ok && found) {
-            const Sock& S = R.sock[s];
-            const u16 w = S.wait_head;
-            if (w != NIL16 && S.q_len == 0 && R.pcb[w].wnext == NIL16) {
-                const Pcb& P = R.pcb[w];
-                const u64 ins = R.m.code[P.pc];
-                const u32 wop = (u32)(ins & 0xFF);
-                if ((wop == OP_RECV_FILTER || wop == OP_RECV_FILTER_LOG) && P.phase == 1 &&
-                    R.node[node].epoch == P.r[(u32)(ins >> 8) & 3]) {
-                    const itsb_filter F = R.m.filters[(u32)(ins >> 16) & 0xFF];
-                    retire = !filter_passes(R, F, K.tag, K.f0, R.m.nodes[node].host, P);
+        int s = -1;
+        bool found = false, retire = false;
+        if (valid) {
+            const u32 dg = R.ndig[node];
+#if defined(ITSB_CHECK_DIGEST)
+            if (!node_digest_valid(R, node)) { fail(H, ITSB_ERR_BAD_OPCODE, 0xD16E57ull << 32 | node); return; }
+#endif
+            bool look = true;
+            if ((dg & 0xFFFF) != dst_port) {
+                look = (dg & ND_SINGLE) == 0;          /* the node's only socket is on another port: nobody listens */
+            } else if (digest_retires && (dg & ND_RETIRE)) {
+                const itsb_filter F = R.m.filters[(dg >> 16) & 0xFF];
+                const bool pass = (F.tags_always & tag_bit) != 0 ||
+                                  ((F.tags_if_host & tag_bit) != 0 && K.f0 == R.m.nodes[node].host);
+                /* handed over while it remembers a packet (if_list), or one with this hostname field (if_listed):
+                   the Bloom bit says "certainly not" for the second; anything else is for the tables to decide */
+                bool depends = false;
+                if (dg & ND_LISTED) {
+                    if (F.tags_if_list & tag_bit) depends = true;
+                    else if (F.tags_if_listed & tag_bit) depends = ((R.nmask[node] >> (K.f0 & 63)) & 1ull) != 0;
+                }
+                if (!pass && !depends) { look = false; found = true; retire = true; }
+            }
+            if (look) {
+                s = sock_find(R, node, K.dst_ip, dst_port);
+                found = s >= 0;
+                if (fast_ok && found) {
+                    const Sock& S = R.sock[s];
+                    const u16 w = S.wait_head;
+                    if (w != NIL16 && S.q_len == 0 && R.pcb[w].wnext == NIL16) {
+                        const Pcb& P = R.pcb[w];
+                        const u64 ins = R.m.code[P.pc];
+                        const u32 wop = (u32)(ins & 0xFF);
+                        if ((wop == OP_RECV_FILTER || wop == OP_RECV_FILTER_LOG) && P.phase == 1 &&
+                            R.node[node].epoch == P.r[(u32)(ins >> 8) & 3]) {
+                            const itsb_filter F = R.m.filters[(u32)(ins >> 16) & 0xFF];
+                            retire = !filter_passes(R, F, K.tag, K.f0, R.m.nodes[node].host, P);
+                        }
+                    }
                 }
             }
         }
+#if ITSB_W == 1
+        if (R.trace == nullptr && (!found || (retire && s < 0))) {
+            /* dropped, or retired from the digest alone: counters only (flushed after the pass), one counter value */
+            q_valid += 1;
+            if (found) { q_found += 1; q_retired += 1; H->seq += 1; }
+            continue;
+        }
+#endif
         const u32 n_found = (u32)popc(w_ballot(found));
         const u32 n_retired = (u32)popc(w_ballot(retire));
         const bool acc = found && !retire;      /* recipients that really enqueue */
@@ -1268,6 +1479,9 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
         u32 total, total_seq;
         u32 before = w_excl_scan(nwait, &total);                               /* ring position: real wake-ups */
         u32 before_seq = w_excl_scan(nwait + (retire ? 1u : 0u), &total_seq);  /* counter value: every waiter  */
+        /* retired recipients take their counter values in recipient order whichever way the wake-ups are pushed; when
+           any lane retires, the ring was empty when the pass began (fast_ok), and a pass that fills it falls back to
+           the ordered pushes only for the wake-ups that are real -- so retiring is switched off for that case below */
         const bool ring_ok = H->nq_spill_count == 0 && (NQ_CAP - (H->nq_tail - H->nq_head)) >= total;
         if (ring_ok) {
             /* every lane writes its socket's resumes straight into the ring slots its prefix rank assigns */
@@ -1286,6 +1500,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
                     w = nx;
                 }
                 S.wait_head = NIL16; S.wait_tail = NIL16;
+                node_digest_woken(R, node, S.port);
             }
             w_sync();
             /* a model that keeps connection records: the retired recipients' recv() would have correlated the packet
@@ -1295,17 +1510,25 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
             H->nq_tail += total;
             H->seq += total_seq;
         } else {
-            /* ring nearly full: same pushes, in recipient order, through the spilling path (warp-uniform);
-               the retiring path is off here because the ring was not empty */
+            /* ring nearly full: the same pushes, in recipient order, through the spilling path (warp-uniform), each
+               recipient's counter values -- a retired wake-up's or its waiters' -- taken in that order */
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
             for (int l = 0; l < ITSB_W; ++l) {
                 u32 nl = w_shfl(nwait, l);
                 u32 sl = w_shfl((u32)s, l);
+                const bool rl = w_shfl(retire ? 1u : 0u, l) != 0;
+                if (rl) {
+                    if (H->conntab) conn_retired(H, 1u << l, (u32)s, H->seq, k);
+                    H->seq += 1;
+                }
                 if (nl != 0) sock_resume_waiters(H, sl);
             }
         }
+#if ITSB_W == 1
+        q_valid += n_valid; q_found += n_found; q_retired += n_retired;     /* flushed after the pass */
+#else
         R.stats[ITSB_TM_KIND0 + ITSB_EV_DELIVER] += n_valid;
         R.stats[ITSB_TM_DELIVERED] += n_found;
         R.stats[ITSB_TM_DROPPED] += n_valid - n_found;
@@ -1314,8 +1537,21 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
             R.stats[ITSB_TM_PACKETS_RECEIVED] += n_retired;
             R.stats[ITSB_TM_BYTES_RECEIVED] += (u64)n_retired * K.size;
         }
+#endif
         w_sync();
     }
+#if ITSB_W == 1
+    if (q_valid) {
+        stat_add(R, ITSB_TM_KIND0 + ITSB_EV_DELIVER, q_valid);
+        if (q_found) stat_add(R, ITSB_TM_DELIVERED, q_found);
+        if (q_valid != q_found) stat_add(R, ITSB_TM_DROPPED, q_valid - q_found);
+        if (q_retired) {
+            stat_add(R, ITSB_TM_KIND0 + ITSB_EV_WAKE, q_retired);
+            stat_add(R, ITSB_TM_PACKETS_RECEIVED, q_retired);
+            stat_add(R, ITSB_TM_BYTES_RECEIVED, (u64)q_retired * K.size);
+        }
+    }
+#endif
     arena_release(R, k);
 }
 
@@ -1454,6 +1690,7 @@ ITSB_COLD int exec_cold(Hdr* H, u32 p, u64 ins) {
     case OP_NODE_SLEEP: {
         NodeDyn& N = R.node[P.node];
         N.awake = 0; N.epoch += 1;
+        node_digest_epoch(R, P.node);
         H->vol[SRC_NODE_EPOCH - 0x10] = N.epoch;
         P.pc += 1;
         return XR_CONTINUE;
@@ -1478,6 +1715,7 @@ ITSB_COLD int exec_cold(Hdr* H, u32 p, u64 ins) {
     }
     case OP_LIST_CLEAR:
         list_free_all(R, P);
+        R.pmask[p] = 0;
         P.pc += 1;
         return XR_CONTINUE;
     case OP_LIST_PUSH: {
@@ -1492,6 +1730,7 @@ ITSB_COLD int exec_cold(Hdr* H, u32 p, u64 ins) {
         if (P.list_tail != NIL32) R.arena[P.list_tail].next = n;
         if (P.list_tail == NIL32) P.list_head = n;
         P.list_tail = n;
+        R.pmask[p] |= 1ull << (A.f0 & 63);
         P.pc += 1;
         return XR_CONTINUE;
     }
@@ -1511,6 +1750,11 @@ ITSB_COLD int exec_cold(Hdr* H, u32 p, u64 ins) {
                 break;
             }
             prev = n; n = A.next;
+        }
+        if (found) {     /* the Bloom filter of what is left (two remembered packets may share a bit) */
+            u64 mk = 0;
+            for (u32 q = P.list_head; q != NIL32; q = R.arena[q].next) mk |= 1ull << (R.arena[q].f0 & 63);
+            R.pmask[p] = mk;
         }
         P.pc = found ? (u16)(P.pc + 1) : (u16)imm;
         return XR_CONTINUE;
@@ -1580,6 +1824,7 @@ ITSB_FN void run_process(Rep& R, u32 p) {
                 if (S.q_len == 0) {               /* socket.recv() */
                     waiters_append(R, S.wait_head, S.wait_tail, p, (u16)(WS_SOCK | P.sock));
                     P.state = PS_WAIT;
+                    node_digest_parked(R, S.node, P.sock, p, b, a);
                     return;
                 }
                 const ArenaNode A = sock_pop(R, S);
@@ -1599,6 +1844,7 @@ ITSB_FN void run_process(Rep& R, u32 p) {
             if (S.q_len == 0) {
                 waiters_append(R, S.wait_head, S.wait_tail, p, (u16)(WS_SOCK | P.sock));
                 P.state = PS_WAIT;
+                node_digest_waits(R, S.node, P.sock);
                 return;
             }
             const ArenaNode A = sock_pop(R, S);
@@ -1641,7 +1887,11 @@ ITSB_COLD u32 deliver_exception(Hdr* H, u32 p, u32 exc) {
         P.timer_tok = (u16)(P.timer_tok + 1);
     } else if (P.state == PS_WAIT && (P.wsig & 0xC000) != WS_SIG) {
         if (P.wsig & WS_NODE) { NodeDyn& N = R.node[P.wsig & 0x3FFF]; waiters_unlink(R, N.wake_head, N.wake_tail, p); }
-        else if (P.wsig & WS_SOCK) { Sock& S = R.sock[P.wsig & 0x3FFF]; waiters_unlink(R, S.wait_head, S.wait_tail, p); }
+        else if (P.wsig & WS_SOCK) {
+            Sock& S = R.sock[P.wsig & 0x3FFF];
+            waiters_unlink(R, S.wait_head, S.wait_tail, p);
+            node_digest_refresh(H, S.node);
+        }
     }
     exc = machine_unwind(R, p, exc);
     P.exc = (u16)exc;
@@ -1675,7 +1925,7 @@ ITSB_COLD void replica_setup(Hdr* H) {
 
 ITSB_FN u64 events_counted(Rep& R) {
     u64 n = 0;
-    for (u32 k = 0; k < ITSB_NUM_KINDS; ++k) n += R.stats[ITSB_TM_KIND0 + k];
+    for (u32 k = 0; k < ITSB_NUM_KINDS; ++k) n += stat_get(R, ITSB_TM_KIND0 + k);
     return n;
 }
 
@@ -2007,7 +2257,7 @@ ITSB_COLD void conn_put(Hdr* H, u32 node, ConnEnt* T, u16* fill, u32 dir, int id
 /* Socket.log_pair: in_* describe the inbound packet (has & 1), out_* the outbound one (has & 2) */
 ITSB_COLD void conn_log(Hdr* H, u32 node, u32 has, u32 in_ip, u32 in_port, u32 in_size, u32 remote_ip, u32 out_port,
                       u32 out_size, double start, bool inbound) {
-    ((u64*)((unsigned char*)H + H->L.off_stats))[ITSB_TM_USER0 + 6] += 1;   /* records produced (user slot 6) */
+    { Rep Rs; Rs.stats = (u64*)((unsigned char*)H + H->L.off_stats); stat_add(Rs, ITSB_TM_USER0 + 6, 1); }   /* records produced (user slot 6) */
     const u32 n = H->conn_count;
     if (n < H->L.conn_cap && lane_id() == 0) {
         itsb_connection C;
@@ -2130,7 +2380,7 @@ ITSB_COLD void conn_retired(Hdr* H, u32 mask, u32 s_lane, u32 seq_lane, u32 k) {
         }
     }
     w_sync();
-    R.stats[ITSB_TM_USER0 + 6] += total;      /* records produced (user slot 6) */
+    if (total) stat_add(R, ITSB_TM_USER0 + 6, total);      /* records produced (user slot 6) */
     H->conn_count = n0 + total;
     w_sync();
 }
@@ -2190,6 +2440,7 @@ ITSB_COLD int exec_logged(Hdr* H, u32 p, u64 ins) {
         if (S.q_len == 0) {
             waiters_append(R, S.wait_head, S.wait_tail, p, (u16)(WS_SOCK | P.sock));
             P.state = PS_WAIT;
+            node_digest_waits(R, S.node, P.sock);
             return XR_STOP;
         }
         if (H->conntab) conn_inbound(H, P.sock, S.q_head);
@@ -2218,6 +2469,7 @@ ITSB_COLD int exec_logged(Hdr* H, u32 p, u64 ins) {
             if (S.q_len == 0) {               /* socket.recv() */
                 waiters_append(R, S.wait_head, S.wait_tail, p, (u16)(WS_SOCK | P.sock));
                 P.state = PS_WAIT;
+                node_digest_parked(R, S.node, P.sock, p, b, a);
                 return XR_STOP;
             }
             if (H->conntab) conn_inbound(H, P.sock, S.q_head);
@@ -2272,7 +2524,7 @@ ITSB_COLD int exec_logged(Hdr* H, u32 p, u64 ins) {
         P.pc += 1;
         return XR_CONTINUE;
     case OP_STAT_FIRST:
-        if (R.stats[ITSB_TM_USER(imm)] == 0) R.stats[ITSB_TM_USER(imm)] = (u64)(H->now * 1.0e6);
+        if (stat_get(R, ITSB_TM_USER(imm)) == 0) stat_add(R, ITSB_TM_USER(imm), (u64)(H->now * 1.0e6));
         P.pc += 1;
         return XR_CONTINUE;
     case OP_CLOSE_LOG:    /* OP_CLOSE after flush_logs (overrides.py:366-367) */
@@ -2314,6 +2566,8 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
         NodeDyn& N = R.node[i];
         N.sock_head = NIL16; N.port_cursor = 1024; N.wake_head = NIL16; N.wake_tail = NIL16; N.epoch = 0; N.awake = 0;
     }
+    for (u32 i = 0; i < L->n_nodes; ++i) { R.ndig[i] = L->max_sig != 0 ? 0u : (u32)ND_SINGLE; R.nmask[i] = 0; }   /* no socket yet */
+    for (u32 i = 0; i < L->max_proc; ++i) R.pmask[i] = 0;
     for (u32 i = 0; i < ITSB_TM_SIZE; ++i) R.stats[i] = 0;
     H->arena_free_top = L->arena_nodes;
     H->sig_free_top = (u16)L->max_sig; H->thr_free_top = (u16)L->max_thr; H->task_free_top = (u16)L->max_task;

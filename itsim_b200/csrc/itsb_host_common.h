@@ -35,6 +35,9 @@ static inline Layout compute_layout(const itsb_model_desc& d) {
     L.off_sock = off;      off = align_up(off + (uint32_t)sizeof(Sock) * L.max_sock, 16);
     L.off_sock_free = off; off = align_up(off + 2 * L.max_sock, 16);
     L.off_node = off;      off = align_up(off + (uint32_t)sizeof(NodeDyn) * L.n_nodes, 16);
+    L.off_ndig = align_up(off, 32); off = align_up(L.off_ndig + 4 * L.n_nodes, 16);   /* sector-aligned: 8 nodes per sector */
+    L.off_nmask = align_up(off, 32); off = align_up(L.off_nmask + 8 * L.n_nodes, 16);
+    L.off_pmask = off;     off = align_up(off + 8 * L.max_proc, 16);
     L.off_stats = off;     off = align_up(off + 8 * ITSB_TM_SIZE, 16);
     /* shipped-itsim tables */
     L.n_ifaces = d.n_ifaces; L.max_sig = c.max_signals; L.max_thr = c.max_threads; L.max_task = c.max_tasks;
@@ -127,6 +130,17 @@ static inline bool validate_model(const itsb_model_desc& d, const void* const* b
         }
         if ((op == OP_JEQI || op == OP_JNEI) && (imm & 0xFFFF) >= d.n_code) { why = "jump out of range"; return false; }
     }
+    /* generator parameters the device trusts: a CHOICE over nothing never terminates its rejection loop, an
+       exponential with a non-positive or non-finite rate divides by zero */
+    const itsb_dist* ds = (const itsb_dist*)blobs[ITSB_BLOB_DISTS];
+    for (uint32_t i = 0; i < d.n_dists; ++i) {
+        const itsb_dist& D = ds[i];
+        const double ps[6] = {D.p0, D.p1, D.slope, D.shift, D.lower, D.upper};
+        for (double v : ps) if (!(v == v) || v > 1.7e308 || v < -1.7e308) { snprintf(buf, sizeof buf, "dist[%u]: non-finite parameter", i); why = buf; return false; }
+        if (D.kind > ITSB_DIST_CHOICE) { snprintf(buf, sizeof buf, "dist[%u]: unknown kind", i); why = buf; return false; }
+        if (D.kind == ITSB_DIST_CHOICE && !(D.p0 >= 1.0 && D.p0 <= 2147483648.0)) { snprintf(buf, sizeof buf, "dist[%u]: CHOICE over %g values", i, D.p0); why = buf; return false; }
+        if (D.kind == ITSB_DIST_EXPO && !(D.p0 > 0.0)) { snprintf(buf, sizeof buf, "dist[%u]: exponential rate must be positive", i); why = buf; return false; }
+    }
     const itsb_entry* en = (const itsb_entry*)blobs[ITSB_BLOB_ENTRIES];
     for (uint32_t i = 0; i < d.n_entries; ++i) if (en[i].pc >= d.n_code) { why = "entry pc out of range"; return false; }
     const itsb_net* nets = (const itsb_net*)blobs[ITSB_BLOB_NETS];
@@ -163,6 +177,12 @@ static inline bool validate_model(const itsb_model_desc& d, const void* const* b
     for (uint32_t i = 0; i < d.n_init; ++i) {
         if (ip[i].mode > ITSB_INIT_ADD_SAME) { why = "init mode out of range"; return false; }
         if (ip[i].mode == ITSB_INIT_ADD_DRAWN && ip[i].delay_const >= d.n_dists) { why = "drawn init entry without a generator"; return false; }
+        if (ip[i].mode == ITSB_INIT_ADD_DRAWN) {     /* node + draw indexes the node tables: the candidates are node .. node + n - 1 */
+            const itsb_dist& D = ds[ip[i].delay_const];
+            if (D.kind != ITSB_DIST_CHOICE || D.flags != 0 || (double)ip[i].node + D.p0 > (double)d.n_nodes) {
+                why = "drawn init entry: the generator must be a plain CHOICE over consecutive nodes inside the node table"; return false;
+            }
+        }
         if (ip[i].mode == ITSB_INIT_ADD_SAME && i == 0) { why = "ITSB_INIT_ADD_SAME without a drawn entry before it"; return false; }
     }
     bool has_balk = false, has_wait_one = false;

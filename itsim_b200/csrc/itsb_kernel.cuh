@@ -98,16 +98,21 @@ __device__ __forceinline__ void cta_copy(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ const Model* stage_model(const Model& g, unsigned char* sm) {
     Model m = g;
     uint32_t off = ((uint32_t)sizeof(Model) + 15) & ~15u;
-    cta_copy(sm + off, g.code, 8 * g.n_code);                 m.code = (const u64*)(sm + off);          off = (off + 8 * g.n_code + 15) & ~15u;
-    cta_copy(sm + off, g.entries, 8 * g.n_entries);           m.entries = (const itsb_entry*)(sm + off); off = (off + 8 * g.n_entries + 15) & ~15u;
-    cta_copy(sm + off, g.dists, 56 * g.n_dists);              m.dists = (const itsb_dist*)(sm + off);    off = (off + 56 * g.n_dists + 15) & ~15u;
-    cta_copy(sm + off, g.consts, 8 * g.n_consts);             m.consts = (const double*)(sm + off);      off = (off + 8 * g.n_consts + 15) & ~15u;
-    cta_copy(sm + off, g.nets, 32 * g.n_nets);                m.nets = (const itsb_net*)(sm + off);      off = (off + 32 * g.n_nets + 15) & ~15u;
-    cta_copy(sm + off, g.nodes, 16 * g.n_nodes);              m.nodes = (const itsb_node*)(sm + off);    off = (off + 16 * g.n_nodes + 15) & ~15u;
-    cta_copy(sm + off, g.filters, 16 * g.n_filters);          m.filters = (const itsb_filter*)(sm + off); off = (off + 16 * g.n_filters + 15) & ~15u;
-    cta_copy(sm + off, g.ifaces, 32 * g.n_ifaces);            m.ifaces = (const itsb_iface*)(sm + off);   off = (off + 32 * g.n_ifaces + 15) & ~15u;
-    cta_copy(sm + off, g.routes, 32 * g.n_routes);            m.routes = (const itsb_route*)(sm + off);   off = (off + 32 * g.n_routes + 15) & ~15u;
-    cta_copy(sm + off, g.members, 4 * g.n_members);           m.members = (const u32*)(sm + off);
+    /* same order and element sizes as static_offsets() above */
+#define ITSB_STAGE(field, type, count)                                                               \
+    cta_copy(sm + off, g.field, (uint32_t)sizeof(type) * (count)); m.field = (const type*)(sm + off); \
+    off = (off + (uint32_t)sizeof(type) * (count) + 15) & ~15u;
+    ITSB_STAGE(code, u64, g.n_code)
+    ITSB_STAGE(entries, itsb_entry, g.n_entries)
+    ITSB_STAGE(dists, itsb_dist, g.n_dists)
+    ITSB_STAGE(consts, double, g.n_consts)
+    ITSB_STAGE(nets, itsb_net, g.n_nets)
+    ITSB_STAGE(nodes, itsb_node, g.n_nodes)
+    ITSB_STAGE(filters, itsb_filter, g.n_filters)
+    ITSB_STAGE(ifaces, itsb_iface, g.n_ifaces)
+    ITSB_STAGE(routes, itsb_route, g.n_routes)
+    ITSB_STAGE(members, u32, g.n_members)
+#undef ITSB_STAGE
     if (threadIdx.x == 0) *(Model*)sm = m;
     __syncthreads();
     return (const Model*)sm;

@@ -1,5 +1,6 @@
 /*
- * itsb_lanes.cu -- EXPERIMENT (ITSB_LANES=1): a replica per lane instead of a replica per warp.
+ * itsb_lanes.cu -- a replica per LANE instead of a replica per warp: k_run_vote (the default engine kernel for large
+ * batches), and k_run_lanes (the same without the vote: an experiment, built only with -DITSB_EXPERIMENTS).
  *
  * The same engine source at width 1 (what tests/hostemu compiles for the CPU), as device code: every thread advances
  * its own replica in place in HBM, 32 replicas share a warp's instruction stream and diverge wherever their next events
@@ -13,6 +14,7 @@
 #ifndef ITSB_LANES_MIN_CTAS
 #define ITSB_LANES_MIN_CTAS 3
 #endif
+#if defined(ITSB_EXPERIMENTS)
 extern "C" __global__ void __launch_bounds__(256, ITSB_LANES_MIN_CTAS) k_run_lanes(const RunParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const Model* m = p.tables_in_hbm ? p.model_dev : stage_model(p.model, smem);
@@ -34,6 +36,8 @@ extern "C" __global__ void __launch_bounds__(256, ITSB_LANES_MIN_CTAS) k_run_lan
         if (R.hdr->status != 0) atomicMin(p.first_failed, (long long)r);
     }
 }
+
+#endif
 
 /* k_run_vote (ITSB_LANES=-n): the same replica per lane, with the warp deciding what to run.  Every lane holds its
  * replica's next event, already taken from the queue; each round the warp picks the key (event kind, program) that most

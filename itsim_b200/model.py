@@ -149,6 +149,10 @@ class Simulator:
         for i, (program, node, regs) in enumerate(self._installed):
             r = list(regs) + [0] * (4 - len(regs))
             if isinstance(node, DrawnNode):
+                # the engine adds the drawn index to the first candidate's node index (replica_setup, itsb_core.cuh)
+                if [c.index for c in node.candidates] != list(range(node.first.index, node.first.index + len(node.candidates))):
+                    raise ValueError("the candidates of a drawn node must be numbered consecutively (link them to "
+                                     "their network one after the other)")
                 init[i] = (self.asm.entry(program), node.first.index, r, node.mode, self.dist(node.dist))
             else:
                 init[i] = (self.asm.entry(program), node.index, r, 0, 0)
@@ -191,6 +195,7 @@ class DrawnNode:
         from .random import distribution_index
         self.sim = sim
         self.first = candidates[0]
+        self.candidates = list(candidates)
         self.dist = distribution_index(len(candidates))
         self.mode = 2          # ITSB_INIT_ADD_DRAWN for the first install, ITSB_INIT_ADD_SAME afterwards
         self._candidates = list(candidates)

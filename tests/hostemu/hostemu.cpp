@@ -213,6 +213,7 @@ int itsb_read_telemetry(itsb_engine* e, uint64_t* dst, size_t n) {
 }
 
 int itsb_allreduce_telemetry(itsb_engine* e, void*, uint64_t* dst, size_t n) { return itsb_read_telemetry(e, dst, n); }
+int itsb_allreduce_u64(itsb_engine*, void*, uint64_t*, size_t, int) { return ITSB_ERR_NCCL; }
 int itsb_nccl_unique_id(void*, size_t) { return ITSB_ERR_NCCL; }
 int itsb_nccl_comm_init(itsb_engine*, int, int, const void*, void**) { return ITSB_ERR_NCCL; }
 int itsb_nccl_comm_destroy(void*) { return ITSB_ERR_NCCL; }

@@ -1,0 +1,26 @@
+#!/bin/bash
+# One GPU-box visit: parity suite, the default bench, the ncu launch list and one full capture of the top kernel.
+# Usage (from the repo root, through gpurun): bash tools/gpu_check.sh [tests|bench|ncu]...   (default: all three)
+set -u
+mkdir -p gpurun_out
+what="${*:-tests bench ncu}"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > gpurun_out/gpu.txt 2>&1
+for w in $what; do
+case $w in
+tests)
+  timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+  tail -5 gpurun_out/pytest_gpu.log;;
+smoke)
+  timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log; tail -3 gpurun_out/smoke.log;;
+bench)
+  timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json | head -c 1500; echo;;
+benchwarp)
+  ITSB_KERNEL=warp timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_warp.json 2> gpurun_out/bench_warp.err; echo "bench warp rc=$?"; head -c 600 gpurun_out/bench_warp.json; echo;;
+ncu)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-verify > gpurun_out/ncu_list.log 2>&1; echo "ncu list rc=$?"
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_run -s 5 -c 1 -f -o gpurun_out/k_run_vote \
+     python bench.py --replicas 100000 --steps 2 --warmup 3 --spinup 600 --slice 60 --no-cpu-baseline --no-verify > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
+  ls -la gpurun_out/*.ncu-rep;;
+esac
+done
