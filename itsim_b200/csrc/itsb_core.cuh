@@ -97,6 +97,8 @@ ITSB_FN u64 dbits(double d) { return (u64)__double_as_longlong(d); }
 ITSB_FN double bitsd(u64 b) { return __longlong_as_double((long long)b); }
 ITSB_FN u32 mulhi32(u32 a, u32 b) { return __umulhi(a, b); }
 ITSB_FN u32 clz32(u32 v) { return (u32)__clz((int)v); }
+ITSB_FN u32 popc64(u64 v) { return (u32)__popcll((unsigned long long)v); }
+ITSB_FN u32 ctz64(u64 v) { return (u32)(__ffsll((long long)v) - 1); }
 #elif defined(__CUDACC__)
 ITSB_FN int lane_id() { return (int)(threadIdx.x & 31); }
 ITSB_FN u32 w_ballot(bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
@@ -120,6 +122,8 @@ ITSB_FN u64 dbits(double d) { return (u64)__double_as_longlong(d); }
 ITSB_FN double bitsd(u64 b) { return __longlong_as_double((long long)b); }
 ITSB_FN u32 mulhi32(u32 a, u32 b) { return __umulhi(a, b); }
 ITSB_FN u32 clz32(u32 v) { return (u32)__clz((int)v); }
+ITSB_FN u32 popc64(u64 v) { return (u32)__popcll((unsigned long long)v); }
+ITSB_FN u32 ctz64(u64 v) { return (u32)(__ffsll((long long)v) - 1); }
 #else
 ITSB_FN int lane_id() { return 0; }
 ITSB_FN u32 w_ballot(bool p) { return p ? 1u : 0u; }
@@ -134,6 +138,8 @@ ITSB_FN u64 dbits(double d) { u64 b; memcpy(&b, &d, 8); return b; }
 ITSB_FN double bitsd(u64 b) { double d; memcpy(&d, &b, 8); return d; }
 ITSB_FN u32 mulhi32(u32 a, u32 b) { return (u32)(((u64)a * (u64)b) >> 32); }
 ITSB_FN u32 clz32(u32 v) { return (u32)__builtin_clz(v); }
+ITSB_FN u32 popc64(u64 v) { return (u32)__builtin_popcountll(v); }
+ITSB_FN u32 ctz64(u64 v) { return (u32)__builtin_ctzll(v); }
 #endif
 
 /* ---- per-replica state ------------------------------------------------------------------------------------------ */
@@ -273,6 +279,7 @@ struct Layout {             /* byte offsets inside one replica's hot block */
     u32 conn_cap, conn_window, off_sockx, address_tags;   /* connection records (overrides.py:102-186) */
     u32 off_ndig;           /* delivery digests: one u32 per node (see node_digest_compute) */
     u32 off_nmask, off_pmask;   /* per node / per process: which hostname fields the remembered packets carry (64-bit Bloom) */
+    u32 off_sockpkt;        /* per socket: the packet at the head of its queue, inline (override-path models) */
 };
 
 struct Model {              /* pointers to the static tables (shared-memory copies inside the kernel) */
@@ -340,6 +347,7 @@ struct Rep {                /* register-resident working view of one replica */
     Pcb* pcb;
     u16* pcb_free;
     Sock* sock;
+    ArenaNode* sockpkt;
     u16* sock_free;
     NodeDyn* node;
     u32* ndig;
@@ -375,6 +383,7 @@ ITSB_FN void rebind(Rep& R, Hdr* H) {
     R.pcb = (Pcb*)(hot + H->L.off_pcb);
     R.pcb_free = (u16*)(hot + H->L.off_pcb_free);
     R.sock = (Sock*)(hot + H->L.off_sock);
+    R.sockpkt = (ArenaNode*)(hot + H->L.off_sockpkt);
     R.sock_free = (u16*)(hot + H->L.off_sock_free);
     R.node = (NodeDyn*)(hot + H->L.off_node);
     R.ndig = (u32*)(hot + H->L.off_ndig);
@@ -917,7 +926,7 @@ ITSB_FN u32 ev_take(Rep& R, int src) {
  * per counted event, 85 % of stall samples waiting on those loads).  The digests of a network's nodes are contiguous:
  * 51 x 4 bytes = 7 sectors.
  *
- *   port[0:16]  filter[16:24]  flags[24:32]
+ *   port[0:16]  filter[16:21]  flags[21:24]  socket[24:32]
  *   ND_SINGLE   the node has exactly one socket, bound to `port` (no socket at all: ND_SINGLE with port 0, which is
  *               never bound) -- a packet for any other port finds nothing: dropped without looking further
  *   ND_RETIRE   the socket bound to `port` has exactly one waiter, parked inside recv() of a RECV_FILTER loop head
@@ -926,42 +935,50 @@ ITSB_FN u32 ev_take(Rep& R, int src) {
  *               and the static tables alone.  ND_LISTED: that process remembers at least one packet; nmask[node] then
  *               holds a 64-bit Bloom filter (bit = hostname field & 63) of the packets it remembers, a copy of the
  *               process's pmask: a packet whose bit is clear is certainly not "listed"
+ *   socket      with either flag: the index of the socket bound to `port` (ND_NOSOCK: not stated), so a packet that
+ *               is accepted finds its socket without walking the node's list
  *
  * A digest is a set of STATEMENTS, each of which must be true whenever it is present; an absent statement (flags 0) only
  * sends the pass back to the tables.  The points that can falsify a statement update the word: a socket opened /
  * closed, a process parking on or leaving a socket's wait list, a delivery waking a socket's waiters, the node
  * sleeping or waking (epoch), and -- for pmask -- the three list instructions.  tests/hostemu builds with
  * ITSB_CHECK_DIGEST verify every statement against the tables before every use and fail the replica otherwise. */
-enum { ND_RETIRE = 1u << 24, ND_LISTED = 1u << 25, ND_SINGLE = 1u << 26 };
+enum { ND_RETIRE = 1u << 21, ND_LISTED = 1u << 22, ND_SINGLE = 1u << 23, ND_NOSOCK = 0xFFu, ND_MAX_FILTER = 31u };
+ITSB_FN u32 nd_port(u32 d) { return d & 0xFFFFu; }
+ITSB_FN u32 nd_filter(u32 d) { return (d >> 16) & 31u; }
+ITSB_FN u32 nd_sock(u32 d) { return d >> 24; }
+ITSB_FN u32 nd_sock_field(u32 s) { return (s < ND_NOSOCK ? s : (u32)ND_NOSOCK) << 24; }
+/* what is left of a digest when nothing can be retired on its socket any more */
+ITSB_FN u32 nd_without_retire(u32 d) { return (d & ND_SINGLE) ? (d & (0xFFFFu | ND_SINGLE | 0xFF000000u)) : 0u; }
 
 /* the statements recomputed from the tables (socket closed, exception delivered: the rare points) */
 ITSB_COLD void node_digest_refresh(Hdr* H, u32 node) {
     Rep R; rebind(R, H);
     if (H->L.max_sig != 0) { R.ndig[node] = 0; return; }   /* shipped-itsim sockets wait on signals: m_deliver */
     const NodeDyn& N = R.node[node];
-    u32 n_socks = 0, d = 0, first_port = 0;
+    u32 n_socks = 0, d = 0, first_port = 0, first_sock = 0;
     bool have = false;
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
     for (u16 s = N.sock_head; s != NIL16; s = R.sock[s].next) {
         const Sock& S = R.sock[s];
-        if (n_socks == 0) first_port = S.port;
+        if (n_socks == 0) { first_port = S.port; first_sock = s; }
         n_socks += 1;
         const u16 w = S.wait_head;
         if (have || w == NIL16 || S.q_len != 0) continue;
         const Pcb& P = R.pcb[w];
         if (P.wnext != NIL16 || P.phase != 1) continue;
         const u64 ins = R.m.code[P.pc];
-        const u32 wop = (u32)(ins & 0xFF);
-        if (wop != OP_RECV_FILTER && wop != OP_RECV_FILTER_LOG) continue;
+        const u32 wop = (u32)(ins & 0xFF), filter = (u32)(ins >> 16) & 0xFF;
+        if ((wop != OP_RECV_FILTER && wop != OP_RECV_FILTER_LOG) || filter > ND_MAX_FILTER) continue;
         if (N.epoch != P.r[(u32)(ins >> 8) & 3]) continue;
         have = true;
-        d = S.port | (((u32)(ins >> 16) & 0xFF) << 16) | ND_RETIRE | (P.list_head != NIL32 ? ND_LISTED : 0u);
+        d = S.port | (filter << 16) | ND_RETIRE | (P.list_head != NIL32 ? ND_LISTED : 0u) | nd_sock_field(s);
         R.nmask[node] = R.pmask[w];
     }
-    if (n_socks == 0) d = ND_SINGLE;                    /* port 0: matches nothing */
-    else if (n_socks == 1) d = have ? (d | ND_SINGLE) : (first_port | ND_SINGLE);
+    if (n_socks == 0) d = ND_SINGLE | nd_sock_field(ND_NOSOCK);                    /* port 0: matches nothing */
+    else if (n_socks == 1) d = have ? (d | ND_SINGLE) : (first_port | ND_SINGLE | nd_sock_field(first_sock));
     R.ndig[node] = d;
 }
 
@@ -973,11 +990,11 @@ ITSB_FN void node_digest_parked(Rep& R, u32 node, u32 s, u32 p, u32 filter, u32 
     const Pcb& P = R.pcb[p];
     const u32 old = R.ndig[node];
     const u32 single = (N.sock_head == s && S.next == NIL16) ? (u32)ND_SINGLE : 0u;
-    if (S.wait_head == p && P.wnext == NIL16 && N.epoch == P.r[epoch_reg & 3]) {
-        R.ndig[node] = S.port | (filter << 16) | ND_RETIRE | (P.list_head != NIL32 ? ND_LISTED : 0u) | single;
+    if (S.wait_head == p && P.wnext == NIL16 && N.epoch == P.r[epoch_reg & 3] && filter <= ND_MAX_FILTER) {
+        R.ndig[node] = S.port | (filter << 16) | ND_RETIRE | (P.list_head != NIL32 ? ND_LISTED : 0u) | single | nd_sock_field(s);
         if (P.list_head != NIL32) R.nmask[node] = R.pmask[p];
-    } else if ((old & 0xFFFF) == S.port) {
-        R.ndig[node] = single ? (S.port | single) : 0u;      /* a second waiter, or a stale epoch: nothing to retire */
+    } else if (nd_port(old) == S.port) {
+        R.ndig[node] = single ? (S.port | single | nd_sock_field(s)) : 0u;   /* a second waiter, or a stale epoch */
     }
 }
 
@@ -985,19 +1002,19 @@ ITSB_FN void node_digest_parked(Rep& R, u32 node, u32 s, u32 p, u32 filter, u32 
 ITSB_FN void node_digest_waits(Rep& R, u32 node, u32 s) {
     if (R.hdr->L.max_sig != 0) return;
     const u32 old = R.ndig[node];
-    if ((old & ND_RETIRE) && (old & 0xFFFF) == R.sock[s].port) R.ndig[node] = (old & ND_SINGLE) ? (old & (0xFFFFu | ND_SINGLE)) : 0u;
+    if ((old & ND_RETIRE) && nd_port(old) == R.sock[s].port) R.ndig[node] = nd_without_retire(old);
 }
 
 /* a delivery woke every waiter of the socket bound to `port` */
 ITSB_FN void node_digest_woken(Rep& R, u32 node, u32 port) {
     const u32 old = R.ndig[node];
-    if ((old & ND_RETIRE) && (old & 0xFFFF) == port) R.ndig[node] = (old & ND_SINGLE) ? (old & (0xFFFFu | ND_SINGLE)) : 0u;
+    if ((old & ND_RETIRE) && nd_port(old) == port) R.ndig[node] = nd_without_retire(old);
 }
 
 /* the node slept or woke: its epoch moved on, so a loop head parked in recv() remembers a stale one */
 ITSB_FN void node_digest_epoch(Rep& R, u32 node) {
     const u32 old = R.ndig[node];
-    if (old & ND_RETIRE) R.ndig[node] = (old & ND_SINGLE) ? (old & (0xFFFFu | ND_SINGLE)) : 0u;
+    if (old & ND_RETIRE) R.ndig[node] = nd_without_retire(old);
 }
 
 /* socket s was just put at the head of the node's socket list */
@@ -1005,7 +1022,7 @@ ITSB_FN void node_digest_opened(Rep& R, u32 node, u32 s) {
     if (R.hdr->L.max_sig != 0) return;
     const Sock& S = R.sock[s];
     const u32 old = R.ndig[node];
-    if (S.next == NIL16) R.ndig[node] = S.port | ND_SINGLE;                 /* the node's only socket */
+    if (S.next == NIL16) R.ndig[node] = S.port | ND_SINGLE | nd_sock_field(s);     /* the node's only socket */
     else R.ndig[node] = (old & ND_RETIRE) ? (old & ~(u32)ND_SINGLE) : 0u;   /* what was said about another socket stands */
 }
 
@@ -1016,12 +1033,19 @@ static bool node_digest_valid(Rep& R, u32 node) {
     const NodeDyn& N = R.node[node];
     if (R.hdr->L.max_sig != 0) return d == 0;
     if (d & ND_SINGLE) {
-        if ((d & 0xFFFF) == 0) { if (N.sock_head != NIL16) return false; }
-        else if (N.sock_head == NIL16 || R.sock[N.sock_head].next != NIL16 || R.sock[N.sock_head].port != (d & 0xFFFF)) return false;
+        if (nd_port(d) == 0) { if (N.sock_head != NIL16) return false; }
+        else if (N.sock_head == NIL16 || R.sock[N.sock_head].next != NIL16 || R.sock[N.sock_head].port != nd_port(d)) return false;
+    }
+    if ((d & (ND_SINGLE | ND_RETIRE)) && nd_port(d) != 0 && nd_sock(d) != ND_NOSOCK) {
+        const Sock& S = R.sock[nd_sock(d)];
+        if (S.port != nd_port(d) || S.node != node) return false;
+        bool linked = false;
+        for (u16 s = N.sock_head; s != NIL16; s = R.sock[s].next) linked |= (s == nd_sock(d));
+        if (!linked) return false;
     }
     if (d & ND_RETIRE) {
         u16 s = N.sock_head;
-        while (s != NIL16 && R.sock[s].port != (d & 0xFFFF)) s = R.sock[s].next;
+        while (s != NIL16 && R.sock[s].port != nd_port(d)) s = R.sock[s].next;
         if (s == NIL16) return false;
         const Sock& S = R.sock[s];
         if (S.wait_head == NIL16 || S.q_len != 0) return false;
@@ -1029,7 +1053,7 @@ static bool node_digest_valid(Rep& R, u32 node) {
         const u64 ins = R.m.code[P.pc];
         const u32 wop = (u32)(ins & 0xFF);
         if (P.wnext != NIL16 || P.phase != 1 || (wop != OP_RECV_FILTER && wop != OP_RECV_FILTER_LOG)) return false;
-        if (((u32)(ins >> 16) & 0xFF) != ((d >> 16) & 0xFF) || N.epoch != P.r[(u32)(ins >> 8) & 3]) return false;
+        if (((u32)(ins >> 16) & 0xFF) != nd_filter(d) || N.epoch != P.r[(u32)(ins >> 8) & 3]) return false;
         if (((d & ND_LISTED) != 0) != (P.list_head != NIL32)) return false;
         u64 want = 0;
         for (u32 n = P.list_head; n != NIL32; n = R.arena[n].next) want |= 1ull << (R.arena[n].f0 & 63);
@@ -1232,6 +1256,48 @@ ITSB_COLD void sock_close(Hdr* H, u32 p) {
     node_digest_refresh(H, S.node);
 }
 
+/* A socket's packet queue (Socket._packet_queue, a FIFO).  In override-path models the packet at the HEAD sits inline,
+ * in the socket's own 32-byte slot of the hot block (sockpkt), and only the packets behind it are arena nodes: a daemon
+ * that is awake and waiting has an empty queue, so a packet it accepts goes into the slot and comes out of it again
+ * without an arena node being allocated, written, read back and released (round 2 profile of k_run_vote: those four
+ * steps were two of the four dependent DRAM round trips of an accepted packet).  q_len counts the slot and the nodes.
+ * Shipped-itsim models (Link mode, itsb_machine.cuh) keep every queued packet in arena nodes. */
+ITSB_FN bool sock_head_inline(Rep& R) { return R.max_sig == 0; }
+
+/* the packet recv() would return next (caller checked q_len != 0) */
+ITSB_FN ArenaNode sock_front(Rep& R, Sock& S) {
+    return sock_head_inline(R) ? R.sockpkt[(u32)(&S - R.sock)] : R.arena[S.q_head];
+}
+
+/* Pops the head of the process's socket queue (caller checked q_len != 0). */
+ITSB_FN ArenaNode sock_pop(Rep& R, Sock& S) {
+    ArenaNode A;
+    if (sock_head_inline(R)) {
+        const u32 s = (u32)(&S - R.sock);
+        A = R.sockpkt[s];
+        S.q_len -= 1;
+        if (S.q_len != 0) {                       /* the next one moves up into the slot */
+            const u32 n = S.q_head;
+            ArenaNode B = R.arena[n];
+            S.q_head = B.next;
+            if (B.next == NIL32) S.q_tail = NIL32;
+            B.next = NIL32;
+            R.sockpkt[s] = B;
+            arena_release(R, n);
+        }
+    } else {
+        const u32 n = S.q_head;
+        A = R.arena[n];
+        S.q_head = A.next;
+        if (A.next == NIL32) S.q_tail = NIL32;
+        S.q_len -= 1;
+        arena_release(R, n);
+    }
+    stat_add(R, ITSB_TM_PACKETS_RECEIVED, 1);
+    stat_add(R, ITSB_TM_BYTES_RECEIVED, A.size);
+    return A;
+}
+
 /* ---- transmission ---------------------------------------------------------------------------------------------------------- */
 ITSB_FN Pkt* pkt_at(Rep& R, u32 k) { return (Pkt*)&R.arena[k]; }
 
@@ -1386,44 +1452,54 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
        and the retired recv()'s correlation is not wanted (a model that keeps connection records does it per socket) */
     const bool digest_retires = fast_ok && H->conntab == nullptr;
     const u32 tag_bit = 1u << (K.tag & 31);
+    const bool inl = sock_head_inline(R);
+    enum { RC_TABLES = 0, RC_DROPPED = 1, RC_RETIRED = 2 };
+
+    /* a recipient's digest: nobody listens / retired on the spot / look at the tables (s = its socket when stated) */
+    auto classify = [&](u32 node, int& s) -> u32 {
+        const u32 dg = R.ndig[node];
+#if defined(ITSB_CHECK_DIGEST)
+        if (!node_digest_valid(R, node)) { fail(H, ITSB_ERR_BAD_OPCODE, 0xD16E57ull << 32 | node); return RC_DROPPED; }
+#endif
+        if (nd_port(dg) != dst_port) return (dg & ND_SINGLE) ? (u32)RC_DROPPED : (u32)RC_TABLES;   /* its only socket is elsewhere */
+        if ((dg & (ND_SINGLE | ND_RETIRE)) && nd_sock(dg) != ND_NOSOCK) s = (int)nd_sock(dg);
+        if (digest_retires && (dg & ND_RETIRE)) {
+            const itsb_filter F = R.m.filters[nd_filter(dg)];
+            if ((F.tags_always & tag_bit) != 0 || ((F.tags_if_host & tag_bit) != 0 && K.f0 == R.m.nodes[node].host))
+                return RC_TABLES;
+            /* handed over while it remembers a packet (if_list), or one with this hostname field (if_listed): the
+               Bloom bit says "certainly not" for the second; anything else is for the tables to decide */
+            if (dg & ND_LISTED) {
+                if (F.tags_if_list & tag_bit) return RC_TABLES;
+                if ((F.tags_if_listed & tag_bit) && ((R.nmask[node] >> (K.f0 & 63)) & 1ull) != 0) return RC_TABLES;
+            }
+            return RC_RETIRED;
+        }
+        return RC_TABLES;
+    };
+
 #if ITSB_W == 1
-    /* a lane per replica: the whole pass usually needs nothing but the digests -- fetch their sectors together, and
-       keep the pass's counters in registers until it ends */
-    u32 q_valid = 0, q_found = 0, q_retired = 0;
-#if defined(__CUDACC__)
-    if (count > 8)
-        for (u32 o = 0; o < count; o += 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(R.ndig + first + o));
+    u32 q_valid = 0, q_found = 0, q_retired = 0;       /* the pass's counters, flushed once */
 #endif
-#endif
-    for (u32 base = 0; base < count; base += ITSB_W) {
+    /* One pass through the tables: the recipients first + base + lane (one per lane; one in all at width 1).  `known`:
+       the caller classified them already and these are the ones left for the tables. */
+    auto pass = [&](u32 base, bool known) -> bool {
         u32 i = base + (u32)lane_id();
         bool valid = i < count;
         u32 node = first + i;
         int s = -1;
         bool found = false, retire = false;
         if (valid) {
-            const u32 dg = R.ndig[node];
-#if defined(ITSB_CHECK_DIGEST)
-            if (!node_digest_valid(R, node)) { fail(H, ITSB_ERR_BAD_OPCODE, 0xD16E57ull << 32 | node); return; }
-#endif
-            bool look = true;
-            if ((dg & 0xFFFF) != dst_port) {
-                look = (dg & ND_SINGLE) == 0;          /* the node's only socket is on another port: nobody listens */
-            } else if (digest_retires && (dg & ND_RETIRE)) {
-                const itsb_filter F = R.m.filters[(dg >> 16) & 0xFF];
-                const bool pass = (F.tags_always & tag_bit) != 0 ||
-                                  ((F.tags_if_host & tag_bit) != 0 && K.f0 == R.m.nodes[node].host);
-                /* handed over while it remembers a packet (if_list), or one with this hostname field (if_listed):
-                   the Bloom bit says "certainly not" for the second; anything else is for the tables to decide */
-                bool depends = false;
-                if (dg & ND_LISTED) {
-                    if (F.tags_if_list & tag_bit) depends = true;
-                    else if (F.tags_if_listed & tag_bit) depends = ((R.nmask[node] >> (K.f0 & 63)) & 1ull) != 0;
-                }
-                if (!pass && !depends) { look = false; found = true; retire = true; }
+            u32 rc = RC_TABLES;
+            if (known) {     /* classified by the caller and left for the tables: only the socket hint is read again */
+                const u32 dg = R.ndig[node];
+                if (nd_port(dg) == dst_port && (dg & (ND_SINGLE | ND_RETIRE)) && nd_sock(dg) != ND_NOSOCK) s = (int)nd_sock(dg);
+            } else {
+                rc = classify(node, s);
             }
-            if (look) {
-                s = sock_find(R, node, K.dst_ip, dst_port);
+            if (rc == RC_RETIRED) { found = true; retire = true; }
+            else if (rc == RC_TABLES) {
+                if (s < 0) s = sock_find(R, node, K.dst_ip, dst_port);
                 found = s >= 0;
                 if (fast_ok && found) {
                     const Sock& S = R.sock[s];
@@ -1441,48 +1517,42 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
                 }
             }
         }
-#if ITSB_W == 1
-        if (R.trace == nullptr && (!found || (retire && s < 0))) {
-            /* dropped, or retired from the digest alone: counters only (flushed after the pass), one counter value */
-            q_valid += 1;
-            if (found) { q_found += 1; q_retired += 1; H->seq += 1; }
-            continue;
-        }
-#endif
         const u32 n_found = (u32)popc(w_ballot(found));
         const u32 n_retired = (u32)popc(w_ballot(retire));
         const bool acc = found && !retire;      /* recipients that really enqueue */
-        const u32 amask = w_ballot(acc);
+        /* a copy goes onto each accepting socket: into its inline head slot when its queue is empty, else an arena node */
+        const bool need_node = acc && (!inl || R.sock[s].q_len != 0);
+        const u32 amask = w_ballot(need_node);
         const u32 n_acc = (u32)popc(amask);
         const u32 n_valid = (u32)popc(w_ballot(valid));
         if (R.trace)
             trace_deliveries(H, i - base, node, valid, (K.size & 0x7FFFFFFFu) | (found ? 0x80000000u : 0u), n_valid);
-        /* enqueue a copy on each accepting socket */
         u32 atop = H->arena_free_top;
-        if (atop < n_acc) { fail(H, ITSB_ERR_CAP_ARENA, k); return; }
+        if (atop < n_acc) { fail(H, ITSB_ERR_CAP_ARENA, k); return false; }
         u32 nwait = 0;
         if (acc) {
-            u32 rank = (u32)popc(amask & lanemask_lt());
-            u32 an = R.arena_free[atop - 1 - rank];
             ArenaNode A;
             A.next = NIL32; A.src_ip = K.src_ip; A.ports = K.ports; A.size = K.size;
             A.tag = K.tag; A.f0 = K.f0; A.f1 = K.f1; A.pad = K.dst_ip;
-            R.arena[an] = A;
             Sock& S = R.sock[s];
-            if (S.q_tail == NIL32) S.q_head = an; else R.arena[S.q_tail].next = an;
-            S.q_tail = an;
+            if (need_node) {
+                u32 rank = (u32)popc(amask & lanemask_lt());
+                u32 an = R.arena_free[atop - 1 - rank];
+                R.arena[an] = A;
+                if (S.q_tail == NIL32) S.q_head = an; else R.arena[S.q_tail].next = an;
+                S.q_tail = an;
+            } else {
+                R.sockpkt[s] = A;
+            }
             S.q_len += 1;
             for (u16 w = S.wait_head; w != NIL16; w = R.pcb[w].wnext) nwait += 1;
         }
-        H->arena_free_top = atop - n_acc;
+        if (n_acc) H->arena_free_top = atop - n_acc;
         /* _enqueue -> packet signal turn_on: resume this socket's waiters (normally the one blocked in recv) */
         u32 total, total_seq;
         u32 before = w_excl_scan(nwait, &total);                               /* ring position: real wake-ups */
         u32 before_seq = w_excl_scan(nwait + (retire ? 1u : 0u), &total_seq);  /* counter value: every waiter  */
-        /* retired recipients take their counter values in recipient order whichever way the wake-ups are pushed; when
-           any lane retires, the ring was empty when the pass began (fast_ok), and a pass that fills it falls back to
-           the ordered pushes only for the wake-ups that are real -- so retiring is switched off for that case below */
-        const bool ring_ok = H->nq_spill_count == 0 && (NQ_CAP - (H->nq_tail - H->nq_head)) >= total;
+        const bool ring_ok = total == 0 || (H->nq_spill_count == 0 && (NQ_CAP - (H->nq_tail - H->nq_head)) >= total);
         if (ring_ok) {
             /* every lane writes its socket's resumes straight into the ring slots its prefix rank assigns */
             if (nwait) {
@@ -1507,8 +1577,8 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
                (overrides.py:135-147); done here, one socket after the other in recipient order, each under the counter
                value its wake-up would have had (the order key of the records it logs) */
             if (n_retired && H->conntab) conn_retired(H, w_ballot(retire), (u32)s, H->seq + before_seq, k);
-            H->nq_tail += total;
-            H->seq += total_seq;
+            if (total) H->nq_tail += total;
+            if (total_seq) H->seq += total_seq;
         } else {
             /* ring nearly full: the same pushes, in recipient order, through the spilling path (warp-uniform), each
                recipient's counter values -- a retired wake-up's or its waiters' -- taken in that order */
@@ -1539,8 +1609,52 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
         }
 #endif
         w_sync();
-    }
+        return true;
+    };
+
 #if ITSB_W == 1
+    if (R.trace == nullptr) {
+        /* A lane per replica, two phases per 64 recipients.  (1) every recipient is classified from its digest alone:
+           a tight loop over 4-byte words whose sectors are fetched together, in which the lanes of a warp that are
+           delivering stay in step.  (2) the recipients left for the tables -- typically the one socket that accepts
+           and the daemons of sleeping workstations -- are taken in recipient order; the counter values the retired
+           ones in between consume are accounted for as the pass reaches them, so every wake-up gets the value it
+           would have got with the recipients taken strictly one after the other. */
+#if defined(__CUDACC__)
+        if (count > 8)
+            for (u32 o = 0; o < count; o += 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(R.ndig + first + o));
+#endif
+        for (u32 c0 = 0; c0 < count; c0 += 64) {
+            const u32 cn = count - c0 < 64 ? count - c0 : 64;
+            u64 slow = 0, retired = 0;
+            u32 dropped = 0;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+            for (u32 j = 0; j < cn; ++j) {
+                int s_unused = -1;
+                const u32 rc = classify(first + c0 + j, s_unused);
+                if (rc == RC_TABLES) slow |= 1ull << j;
+                else if (rc == RC_RETIRED) retired |= 1ull << j;
+                else dropped += 1;
+            }
+            if (H->status != 0) return;
+            const u32 n_ret = (u32)popc64(retired);
+            q_valid += dropped + n_ret; q_found += n_ret; q_retired += n_ret;
+            while (slow != 0) {
+                const u32 j = (u32)ctz64(slow);
+                slow &= slow - 1;
+                const u64 below = (1ull << j) - 1;
+                const u32 r = (u32)popc64(retired & below);     /* retired recipients before this one */
+                if (r) { H->seq += r; retired &= ~below; }
+                if (!pass(c0 + j, true)) return;
+            }
+            const u32 r = (u32)popc64(retired);
+            if (r) H->seq += r;
+        }
+    } else {
+        for (u32 base = 0; base < count; base += ITSB_W) if (!pass(base, false)) return;
+    }
     if (q_valid) {
         stat_add(R, ITSB_TM_KIND0 + ITSB_EV_DELIVER, q_valid);
         if (q_found) stat_add(R, ITSB_TM_DELIVERED, q_found);
@@ -1551,6 +1665,8 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
             stat_add(R, ITSB_TM_BYTES_RECEIVED, (u64)q_retired * K.size);
         }
     }
+#else
+    for (u32 base = 0; base < count; base += ITSB_W) if (!pass(base, false)) return;
 #endif
     arena_release(R, k);
 }
@@ -1572,19 +1688,6 @@ ITSB_FN void set_pkt_regs(Rep& R, const ArenaNode& A) {
 }
 
 enum { XR_CONTINUE = 0, XR_STOP = 1 };
-
-/* Pops the head of the process's socket queue (caller checked q_len != 0). */
-ITSB_FN ArenaNode sock_pop(Rep& R, Sock& S) {
-    u32 n = S.q_head;
-    const ArenaNode A = R.arena[n];
-    S.q_head = A.next;
-    if (A.next == NIL32) S.q_tail = NIL32;
-    S.q_len -= 1;
-    arena_release(R, n);
-    stat_add(R, ITSB_TM_PACKETS_RECEIVED, 1);
-    stat_add(R, ITSB_TM_BYTES_RECEIVED, A.size);
-    return A;
-}
 
 }  // namespace itsb
 #include "itsb_machine.cuh"
@@ -2296,8 +2399,9 @@ ITSB_COLD void conn_outbound(Hdr* H, u32 s, u32 node, u32 dst_ip, u32 dst_port, 
 
 /* correlate_inbound_packet (overrides.py:115-120), called by recv() on the packet it returns */
 ITSB_COLD void conn_inbound_fields(Hdr* H, u32 s, u32 src_ip, u32 ports, u32 dst_ip, u32 size);
-ITSB_COLD void conn_inbound(Hdr* H, u32 s, u32 queued) {
-    const ArenaNode A = H->arena[queued];
+ITSB_COLD void conn_inbound(Hdr* H, u32 s) {
+    Rep R; rebind(R, H);
+    const ArenaNode A = sock_front(R, R.sock[s]);
     conn_inbound_fields(H, s, A.src_ip, A.ports, A.pad, A.size);
 }
 
@@ -2443,7 +2547,7 @@ ITSB_COLD int exec_logged(Hdr* H, u32 p, u64 ins) {
             node_digest_waits(R, S.node, P.sock);
             return XR_STOP;
         }
-        if (H->conntab) conn_inbound(H, P.sock, S.q_head);
+        if (H->conntab) conn_inbound(H, P.sock);
         const ArenaNode A = sock_pop(R, S);
         set_pkt_regs(R, A);
         P.pc += 1;
@@ -2472,7 +2576,7 @@ ITSB_COLD int exec_logged(Hdr* H, u32 p, u64 ins) {
                 node_digest_parked(R, S.node, P.sock, p, b, a);
                 return XR_STOP;
             }
-            if (H->conntab) conn_inbound(H, P.sock, S.q_head);
+            if (H->conntab) conn_inbound(H, P.sock);
             const ArenaNode A = sock_pop(R, S);
             P.phase = 0;
             if (N.epoch != P.r[a & 3]) { P.pc = (u16)(imm & 0xFFFF); return XR_CONTINUE; }      /* FellAsleep */
@@ -2560,13 +2664,19 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
     H->ev_free_top = (u16)L->max_ev;
     for (u32 i = 0; i < L->max_proc; ++i) { memset(&R.pcb[i], 0, sizeof(Pcb)); R.pcb_free[i] = (u16)(L->max_proc - 1 - i); }
     H->pcb_free_top = (u16)L->max_proc;
-    for (u32 i = 0; i < L->max_sock; ++i) { memset(&R.sock[i], 0, sizeof(Sock)); R.sock_free[i] = (u16)(L->max_sock - 1 - i); }
+    for (u32 i = 0; i < L->max_sock; ++i) {
+        memset(&R.sock[i], 0, sizeof(Sock)); memset(&R.sockpkt[i], 0, sizeof(ArenaNode));
+        R.sock_free[i] = (u16)(L->max_sock - 1 - i);
+    }
     H->sock_free_top = (u16)L->max_sock;
     for (u32 i = 0; i < L->n_nodes; ++i) {
         NodeDyn& N = R.node[i];
         N.sock_head = NIL16; N.port_cursor = 1024; N.wake_head = NIL16; N.wake_tail = NIL16; N.epoch = 0; N.awake = 0;
     }
-    for (u32 i = 0; i < L->n_nodes; ++i) { R.ndig[i] = L->max_sig != 0 ? 0u : (u32)ND_SINGLE; R.nmask[i] = 0; }   /* no socket yet */
+    for (u32 i = 0; i < L->n_nodes; ++i) {   /* no socket yet */
+        R.ndig[i] = L->max_sig != 0 ? 0u : ((u32)ND_SINGLE | nd_sock_field(ND_NOSOCK));
+        R.nmask[i] = 0;
+    }
     for (u32 i = 0; i < L->max_proc; ++i) R.pmask[i] = 0;
     for (u32 i = 0; i < ITSB_TM_SIZE; ++i) R.stats[i] = 0;
     H->arena_free_top = L->arena_nodes;
