@@ -301,6 +301,31 @@ int itsb_histogram(itsb_engine* e, uint32_t slot, uint64_t lo, uint64_t width, u
  * would have had, and this call orders what the log holds by (End_Time, that value) before copying it out.     */
 int itsb_read_connections(itsb_engine* e, uint64_t replica, itsb_connection* dst, size_t cap, size_t* n_total);
 
+/* ---- streaming the record logs home -------------------------------------------------------------------------------
+ * Replaces: the record-at-a-time path of the reference -- logging.Handler.emit -> one HTTP POST -> one SQLite connection
+ * per record (itsim/logging.py:27-65, itsim/datastore/database.py:130-164) and the per-connection JSON lines of
+ * Socket.log_pair (network_simple_overrides.py:152-186).  The per-replica logs in HBM are fixed-capacity windows; a
+ * drain empties all of them at once:
+ *   itsb_drain_begin  (engine stream) counts every replica's new records, packs them replica after replica into a
+ *                     device staging buffer with ONE gather kernel -- connection records put in the order log_pair was
+ *                     called in (End_Time, then the counter value of the producing event), as itsb_read_connections
+ *                     does -- resets the per-replica counts, and starts ONE cudaMemcpyAsync per log on a second stream
+ *                     into pinned host memory.  The next itsb_run may be queued right away: it overlaps the copy.
+ *   itsb_drain_end    waits for that copy and hands out pointers into the pinned buffers.  Two sets of buffers
+ *                     alternate, so the pointers stay valid until the drain after the next one begins; at most one
+ *                     drain may be pending besides the one being begun.
+ * Record r's replica: net_first / conn_first hold n_replicas + 1 offsets -- replica i owns [first[i], first[i + 1]).   */
+typedef struct itsb_drain {
+    const itsb_net_event*  net;        uint64_t n_net;
+    const uint64_t*        net_first;
+    const itsb_connection* conn;       uint64_t n_conn;
+    const uint64_t*        conn_first;
+    uint64_t net_dropped, conn_dropped;   /* produced since the last drain beyond a replica's capacity: counted, lost */
+    uint64_t d2h_bytes;                   /* bytes this drain copied device -> host                                   */
+} itsb_drain;
+int itsb_drain_begin(itsb_engine* e);
+int itsb_drain_end(itsb_engine* e, itsb_drain* out);
+
 /* Replaces: the records itsim/logging.py + itsim/datastore would receive (README.md:18-50), reduced on the device:
  * ITSB_TM_SIZE uint64 counters / histogram bins summed over this engine's replicas.                               */
 int itsb_read_telemetry(itsb_engine* e, uint64_t* dst, size_t n);

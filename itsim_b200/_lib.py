@@ -79,6 +79,13 @@ class ModelDesc(C.Structure):
                 ("n_members", C.c_uint32), ("address_tags", C.c_uint32), ("caps", Caps)]
 
 
+class Drain(C.Structure):
+    """``itsb_drain`` (include/itsb.h): one emptying of every replica's record logs."""
+    _fields_ = [("net", C.c_void_p), ("n_net", C.c_uint64), ("net_first", C.c_void_p),
+                ("conn", C.c_void_p), ("n_conn", C.c_uint64), ("conn_first", C.c_void_p),
+                ("net_dropped", C.c_uint64), ("conn_dropped", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
 class EngineError(RuntimeError):
     def __init__(self, code: int, where: str, detail: str = "") -> None:
         self.code = code
@@ -102,6 +109,8 @@ _SIGNATURES = {
     "itsb_histogram": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p,
                                  C.c_void_p]),
     "itsb_read_connections": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "itsb_drain_begin": (C.c_int, [C.c_void_p]),
+    "itsb_drain_end": (C.c_int, [C.c_void_p, C.POINTER(Drain)]),
     "itsb_read_telemetry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "itsb_read_replica_telemetry": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t]),
     "itsb_allreduce_telemetry": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -95,6 +95,99 @@ extern "C" __global__ void k_eval_log(double* v, size_t n) {
     if (i < n) v[i] = log_f64(v[i]);
 }
 
+/* ---- streaming the record logs home (itsb_drain_begin / itsb_drain_end) ---------------------------------------------- */
+/* records each replica holds since the last drain (capped at its capacity) and what it produced beyond that */
+extern "C" __global__ void k_log_count(const unsigned char* hot, uint32_t hot_bytes, uint64_t n, uint32_t log_cap,
+                                       uint32_t conn_cap, unsigned long long* n_net, unsigned long long* n_conn,
+                                       unsigned long long* dropped) {
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const Hdr* H = (const Hdr*)(hot + r * hot_bytes);
+    const uint32_t a = H->log_count, b = H->conn_count;
+    n_net[r] = a < log_cap ? a : log_cap;
+    n_conn[r] = b < conn_cap ? b : conn_cap;
+    if (a > log_cap) atomicAdd(dropped, (unsigned long long)(a - log_cap));
+    if (b > conn_cap) atomicAdd(dropped + 1, (unsigned long long)(b - conn_cap));
+}
+
+/* exclusive prefix sums of the two count arrays, in place, totals behind them ([n]); one CTA: the arrays are small */
+extern "C" __global__ void __launch_bounds__(1024) k_log_scan(unsigned long long* a, unsigned long long* b, uint64_t n) {
+    __shared__ unsigned long long warp_sums[2][32];
+    __shared__ unsigned long long carry[2];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { carry[0] = 0; carry[1] = 0; }
+    __syncthreads();
+    for (uint64_t base = 0; base < n; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        unsigned long long v[2] = {i < n ? a[i] : 0ull, i < n ? b[i] : 0ull}, x[2];
+        for (int k = 0; k < 2; ++k) {
+            x[k] = v[k];
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, x[k], d);
+                if (lane >= (uint32_t)d) x[k] += y;
+            }
+            if (lane == 31) warp_sums[k][warp] = x[k];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            for (int k = 0; k < 2; ++k) {
+                unsigned long long w = warp_sums[k][lane];
+                for (int d = 1; d < 32; d <<= 1) {
+                    unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, w, d);
+                    if (lane >= (uint32_t)d) w += y;
+                }
+                warp_sums[k][lane] = w;
+            }
+        }
+        __syncthreads();
+        for (int k = 0; k < 2; ++k) {
+            const unsigned long long before = carry[k] + (warp ? warp_sums[k][warp - 1] : 0ull) + x[k] - v[k];
+            if (i < n) (k ? b : a)[i] = before;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { carry[0] += warp_sums[0][31]; carry[1] += warp_sums[1][31]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { a[n] = carry[0]; b[n] = carry[1]; }
+}
+
+/* One CTA per replica: its records go to their place in the packed staging buffers, then its log starts over.
+ * Connection records are appended in processing order except those of wake-ups retired in the delivery pass, which
+ * are logged early under the counter value their wake-up would have had; log_pair's call order is (End_Time, that
+ * value).  End_Time never decreases along the log, so only records that share an End_Time can be out of place: each
+ * record finds its rank inside its run of equal End_Times (the runs are the events of one instant: short). */
+extern "C" __global__ void __launch_bounds__(128) k_log_gather(
+    unsigned char* hot, uint32_t hot_bytes, uint64_t n, const itsb_net_event* netlog, uint32_t log_cap,
+    const unsigned char* connlog, uint32_t conn_cap, const unsigned long long* net_first,
+    const unsigned long long* conn_first, itsb_net_event* out_net, itsb_connection* out_conn) {
+    const uint64_t r = blockIdx.x;
+    if (r >= n) return;
+    Hdr* H = (Hdr*)(hot + r * hot_bytes);
+    const uint32_t n_net = (uint32_t)(net_first[r + 1] - net_first[r]);
+    const uint32_t n_conn = (uint32_t)(conn_first[r + 1] - conn_first[r]);
+    if (n_net) {
+        const uint4* src = (const uint4*)(netlog + r * log_cap);
+        uint4* dst = (uint4*)(out_net + net_first[r]);
+        for (uint32_t i = threadIdx.x; i < n_net * 2; i += blockDim.x) dst[i] = src[i];
+    }
+    if (n_conn) {
+        const unsigned char* base = connlog + r * conn_log_bytes(conn_cap);
+        const itsb_connection* recs = (const itsb_connection*)base;
+        const uint32_t* keys = (const uint32_t*)(base + (size_t)conn_cap * sizeof(itsb_connection));
+        itsb_connection* dst = out_conn + conn_first[r];
+        for (uint32_t i = threadIdx.x; i < n_conn; i += blockDim.x) {
+            const itsb_connection C = recs[i];
+            const uint32_t key = keys[i];
+            uint32_t lo = i, rank = 0;
+            while (lo > 0 && recs[lo - 1].t_end == C.t_end) { lo -= 1; if (keys[lo] <= key) rank += 1; }
+            for (uint32_t j = i + 1; j < n_conn && recs[j].t_end == C.t_end; ++j) if (keys[j] < key) rank += 1;
+            dst[lo + rank] = C;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { H->log_count = 0; H->conn_count = 0; }
+}
+
 /* ---- host side ---------------------------------------------------------------------------------------------------------- */
 /* Engine kernels.  Two designs:
  *   a replica per WARP, state staged in shared memory (k_run; k_run_wide for 13-16 resident replicas per SM;
@@ -131,6 +224,20 @@ struct itsb_engine {
     unsigned long long* d_telemetry = nullptr;
     Model* d_model = nullptr;                     /* the table pointers, in device memory (template build) */
     unsigned long long* d_scratch = nullptr;      /* itsb_allreduce_u64 */
+    /* streaming drains: per-replica offsets (two arrays of n + 1), two alternating sets of staging buffers */
+    struct DrainSet {
+        itsb_net_event* d_net = nullptr; itsb_connection* d_conn = nullptr;       /* device, packed */
+        itsb_net_event* h_net = nullptr; itsb_connection* h_conn = nullptr;       /* pinned host */
+        unsigned long long* h_first = nullptr;                                    /* pinned: net_first | conn_first */
+        size_t cap_net = 0, cap_conn = 0, cap_first = 0;
+        uint64_t n_net = 0, n_conn = 0, dropped[2] = {0, 0}, bytes = 0;
+        cudaEvent_t packed = nullptr, home = nullptr;
+        bool pending = false;
+    } drain[2];
+    unsigned long long* d_first = nullptr;        /* net_first[n + 1] | conn_first[n + 1] | dropped[2] */
+    size_t cap_first = 0;
+    cudaStream_t copy_stream = nullptr;
+    unsigned drain_next = 0;
     uint64_t n_replicas = 0;
     uint64_t launches = 0;
     uint32_t warps_per_cta = 0, grid = 0;
@@ -182,12 +289,36 @@ static void choose_kernel(itsb_engine* e) {
         }                                                                                      \
     } while (0)
 
+static void drain_free(itsb_engine* e);
 static void free_replicas(itsb_engine* e) {
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+    drain_free(e);
     cudaFree(e->d_hot); cudaFree(e->d_arena); cudaFree(e->d_arena_free); cudaFree(e->d_trace); cudaFree(e->d_netlog);
     cudaFree(e->d_connlog); cudaFree(e->d_conntab);
     e->d_connlog = nullptr; e->d_conntab = nullptr;
     e->d_hot = nullptr; e->d_arena = nullptr; e->d_arena_free = nullptr; e->d_trace = nullptr; e->d_netlog = nullptr;
     e->n_replicas = 0;
+}
+
+static void drain_free(itsb_engine* e) {
+    for (auto& D : e->drain) {
+        cudaFree(D.d_net); cudaFree(D.d_conn); cudaFreeHost(D.h_net); cudaFreeHost(D.h_conn); cudaFreeHost(D.h_first);
+        if (D.packed) cudaEventDestroy(D.packed);
+        if (D.home) cudaEventDestroy(D.home);
+        D = itsb_engine::DrainSet();
+    }
+    cudaFree(e->d_first); e->d_first = nullptr; e->cap_first = 0;
+}
+
+template <typename T>
+static cudaError_t grow(T*& dev, T*& host, size_t& cap, size_t want) {
+    if (want <= cap) return cudaSuccess;
+    const size_t n = want + want / 4 + 1024;
+    cudaFree(dev); cudaFreeHost(host); dev = nullptr; host = nullptr; cap = 0;
+    cudaError_t rc = cudaMalloc(&dev, n * sizeof(T));
+    if (rc == cudaSuccess) rc = cudaHostAlloc(&host, n * sizeof(T), cudaHostAllocDefault);
+    if (rc == cudaSuccess) cap = n;
+    return rc;
 }
 
 extern "C" {
@@ -505,6 +636,86 @@ static int reduce_telemetry(itsb_engine* e) {
     return ITSB_OK;
 }
 
+/* ---- itsb_drain_begin / itsb_drain_end ------------------------------------------------------------------------------- */
+int itsb_drain_begin(itsb_engine* e) {
+    if (!e || !e->n_replicas) return ITSB_ERR_STATE;
+    const Layout& L = e->rp.layout;
+    if (L.log_cap == 0 && L.conn_cap == 0) { e->err = "the model keeps no record logs"; return ITSB_ERR_STATE; }
+    auto& D = e->drain[e->drain_next & 1];
+    if (D.pending) { e->err = "two drains are already pending: call itsb_drain_end first"; return ITSB_ERR_STATE; }
+    CU(e, cudaSetDevice(e->device));
+    const uint64_t n = e->n_replicas;
+    if (!e->copy_stream) CU(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    if (!D.packed) { CU(e, cudaEventCreateWithFlags(&D.packed, cudaEventDisableTiming)); CU(e, cudaEventCreateWithFlags(&D.home, cudaEventDisableTiming)); }
+    if (e->cap_first < n + 1) {
+        cudaFree(e->d_first); e->d_first = nullptr; e->cap_first = 0;
+        CU(e, cudaMalloc(&e->d_first, (2 * (n + 1) + 2) * sizeof(unsigned long long)));
+        e->cap_first = n + 1;
+    }
+    if (D.cap_first < n + 1) {
+        cudaFreeHost(D.h_first); D.h_first = nullptr; D.cap_first = 0;
+        CU(e, cudaHostAlloc(&D.h_first, 2 * (n + 1) * sizeof(unsigned long long), cudaHostAllocDefault));
+        D.cap_first = n + 1;
+    }
+    unsigned long long* net_first = e->d_first;
+    unsigned long long* conn_first = e->d_first + (n + 1);
+    unsigned long long* dropped = e->d_first + 2 * (n + 1);
+    CU(e, cudaMemsetAsync(dropped, 0, 2 * sizeof(unsigned long long), e->stream));
+    k_log_count<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->d_hot, L.hot_bytes, n, L.log_cap, L.conn_cap,
+                                                                     net_first, conn_first, dropped);
+    CU(e, cudaGetLastError());
+    k_log_scan<<<1, 1024, 0, e->stream>>>(net_first, conn_first, n);
+    CU(e, cudaGetLastError());
+    e->launches += 2;
+    /* the totals size the packed buffers: this is the one wait of a drain (the run before it has to be over anyway) */
+    unsigned long long totals[4];
+    CU(e, cudaMemcpyAsync(&totals[0], net_first + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(&totals[1], conn_first + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaMemcpyAsync(&totals[2], dropped, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaStreamSynchronize(e->stream));
+    D.n_net = totals[0]; D.n_conn = totals[1]; D.dropped[0] = totals[2]; D.dropped[1] = totals[3];
+    CU(e, grow(D.d_net, D.h_net, D.cap_net, (size_t)D.n_net));
+    CU(e, grow(D.d_conn, D.h_conn, D.cap_conn, (size_t)D.n_conn));
+    k_log_gather<<<(unsigned)n, 128, 0, e->stream>>>(e->d_hot, L.hot_bytes, n, e->d_netlog, L.log_cap,
+                                                      (const unsigned char*)e->d_connlog, L.conn_cap, net_first, conn_first,
+                                                      D.d_net, D.d_conn);
+    CU(e, cudaGetLastError());
+    e->launches += 1;
+    /* the offsets travel with the records; copied to their own pinned buffer on the engine stream (the next drain
+       overwrites the device array), the records on the second stream once the gather is done */
+    CU(e, cudaMemcpyAsync(D.h_first, e->d_first, 2 * (n + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    CU(e, cudaEventRecord(D.packed, e->stream));
+    CU(e, cudaStreamWaitEvent(e->copy_stream, D.packed, 0));
+    if (D.n_net) CU(e, cudaMemcpyAsync(D.h_net, D.d_net, D.n_net * sizeof(itsb_net_event), cudaMemcpyDeviceToHost, e->copy_stream));
+    if (D.n_conn) CU(e, cudaMemcpyAsync(D.h_conn, D.d_conn, D.n_conn * sizeof(itsb_connection), cudaMemcpyDeviceToHost, e->copy_stream));
+    CU(e, cudaEventRecord(D.home, e->copy_stream));
+    D.bytes = D.n_net * sizeof(itsb_net_event) + D.n_conn * sizeof(itsb_connection) + 2 * (n + 1) * sizeof(unsigned long long) + 32;
+    D.pending = true;
+    e->drain_next += 1;
+    return ITSB_OK;
+}
+
+int itsb_drain_end(itsb_engine* e, itsb_drain* out) {
+    if (!e || !out) return ITSB_ERR_STATE;
+    /* the oldest pending drain */
+    itsb_engine::DrainSet* D = nullptr;
+    for (unsigned k = 0; k < 2; ++k) {
+        auto& C = e->drain[(e->drain_next + k) & 1];
+        if (C.pending) { D = &C; break; }
+    }
+    if (!D) { e->err = "no drain is pending"; return ITSB_ERR_STATE; }
+    CU(e, cudaSetDevice(e->device));
+    CU(e, cudaEventSynchronize(D->packed));     /* offsets home (engine stream) */
+    CU(e, cudaEventSynchronize(D->home));       /* records home (copy stream) */
+    const uint64_t n = e->n_replicas;
+    out->net = D->h_net; out->n_net = D->n_net; out->net_first = (const uint64_t*)D->h_first;
+    out->conn = D->h_conn; out->n_conn = D->n_conn; out->conn_first = (const uint64_t*)(D->h_first + (n + 1));
+    out->net_dropped = D->dropped[0]; out->conn_dropped = D->dropped[1];
+    out->d2h_bytes = D->bytes;
+    D->pending = false;
+    return ITSB_OK;
+}
+
 int itsb_read_telemetry(itsb_engine* e, uint64_t* dst, size_t n) {
     if (!e || !e->n_replicas || n < ITSB_TM_SIZE) return ITSB_ERR_STATE;
     CU(e, cudaSetDevice(e->device));
@@ -672,6 +883,9 @@ void itsb_destroy(itsb_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); }
+    drain_free(e);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     free_replicas(e);
     for (int i = 0; i < ITSB_NUM_BLOBS; ++i) cudaFree(e->d_tables[i]);
     cudaFree(e->d_ticket); cudaFree(e->d_first_failed); cudaFree(e->d_telemetry); cudaFree(e->d_model); cudaFree(e->d_scratch);

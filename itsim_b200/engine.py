@@ -119,6 +119,37 @@ class Engine:
         self.connections_total = total.value
         return out[:min(cap, total.value)]
 
+    # -- streaming the record logs home (itsb_drain_begin / itsb_drain_end) ----------------------------------------------
+    def drain_begin(self) -> None:
+        """Packs every replica's new ``network_event`` / connection records on the device, empties the per-replica logs
+        and starts the copy to pinned host memory on a second stream; the next ``run`` may be queued right away."""
+        self._check(self._lib.itsb_drain_begin(self._h), "itsb_drain_begin")
+
+    def drain_end(self, copy: bool = False) -> Dict[str, Any]:
+        """Waits for the oldest pending drain.  Returns ``net`` / ``conn`` (structured arrays over ALL replicas,
+        replica after replica), ``net_first`` / ``conn_first`` (``n_replicas + 1`` offsets: replica r owns
+        ``[first[r], first[r + 1])``), the records lost to full per-replica logs, and the bytes copied.  The arrays
+        are views of the engine's pinned buffers, valid until the drain after the next one begins (``copy=True``
+        detaches them)."""
+        d = L.Drain()
+        self._check(self._lib.itsb_drain_end(self._h, C.byref(d)), "itsb_drain_end")
+        n = self.n_replicas
+
+        def view(ptr: Any, count: int, dtype: Any) -> np.ndarray:
+            if not ptr or count == 0:
+                return np.zeros(0, dtype=dtype)
+            buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+            arr = np.frombuffer(buf, dtype=dtype, count=count)
+            return arr.copy() if copy else arr
+
+        return {"net": view(d.net, d.n_net, L.NET_EVENT_DTYPE), "net_first": view(d.net_first, n + 1, np.uint64),
+                "conn": view(d.conn, d.n_conn, L.CONNECTION_DTYPE), "conn_first": view(d.conn_first, n + 1, np.uint64),
+                "net_dropped": int(d.net_dropped), "conn_dropped": int(d.conn_dropped), "d2h_bytes": int(d.d2h_bytes)}
+
+    def drain(self, copy: bool = False) -> Dict[str, Any]:
+        self.drain_begin()
+        return self.drain_end(copy=copy)
+
     def histogram(self, slot: int, lo: int, width: int, nbins: int, only_nonzero: bool = False,
                   comm: Optional[C.c_void_p] = None) -> np.ndarray:
         """Histogram over the replicas of telemetry slot ``slot`` (``_lib.tm_user(k)`` for model counter k); with a

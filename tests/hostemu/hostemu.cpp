@@ -38,6 +38,10 @@ struct itsb_engine {
     std::vector<unsigned char> connlog;      /* per replica: conn_cap records, then conn_cap order keys */
     std::vector<ConnEnt> conntab;
     uint64_t last_events = 0, launches = 0;
+    /* itsb_drain_*: two alternating sets, like the device library */
+    struct DrainSet { std::vector<itsb_net_event> net; std::vector<itsb_connection> conn; std::vector<uint64_t> first;
+                      uint64_t dropped[2] = {0, 0}; bool pending = false; } drain[2];
+    unsigned drain_next = 0;
     std::string err;
     bool loaded = false;
 };
@@ -193,6 +197,52 @@ int itsb_read_connections(itsb_engine* e, uint64_t replica, itsb_connection* dst
         order_connections(recs.data(), keys.data(), held);
         memcpy(dst, recs.data(), n * sizeof(itsb_connection));
     }
+    return ITSB_OK;
+}
+
+int itsb_drain_begin(itsb_engine* e) {
+    if (!e->n_replicas) return ITSB_ERR_STATE;
+    const Layout& L = e->layout;
+    if (L.log_cap == 0 && L.conn_cap == 0) return ITSB_ERR_STATE;
+    auto& D = e->drain[e->drain_next & 1];
+    if (D.pending) return ITSB_ERR_STATE;
+    const uint64_t n = e->n_replicas;
+    D.net.clear(); D.conn.clear(); D.first.assign(2 * (n + 1), 0); D.dropped[0] = D.dropped[1] = 0;
+    for (uint64_t r = 0; r < n; ++r) {
+        Hdr* H = (Hdr*)(e->hot.data() + r * L.hot_bytes);
+        const uint32_t a = H->log_count < L.log_cap ? H->log_count : L.log_cap;
+        const uint32_t b = H->conn_count < L.conn_cap ? H->conn_count : L.conn_cap;
+        D.dropped[0] += H->log_count - a; D.dropped[1] += H->conn_count - b;
+        D.first[r] = D.net.size(); D.first[n + 1 + r] = D.conn.size();
+        if (a) D.net.insert(D.net.end(), e->netlog.begin() + r * L.log_cap, e->netlog.begin() + r * L.log_cap + a);
+        if (b) {
+            const unsigned char* base = e->connlog.data() + r * conn_log_bytes(L.conn_cap);
+            std::vector<itsb_connection> recs(b);
+            std::vector<uint32_t> keys(b);
+            memcpy(recs.data(), base, b * sizeof(itsb_connection));
+            memcpy(keys.data(), base + (size_t)L.conn_cap * sizeof(itsb_connection), b * sizeof(uint32_t));
+            order_connections(recs.data(), keys.data(), b);
+            D.conn.insert(D.conn.end(), recs.begin(), recs.end());
+        }
+        H->log_count = 0; H->conn_count = 0;
+    }
+    D.first[n] = D.net.size(); D.first[2 * n + 1] = D.conn.size();
+    D.pending = true;
+    e->drain_next += 1;
+    e->launches += 3;
+    return ITSB_OK;
+}
+
+int itsb_drain_end(itsb_engine* e, itsb_drain* out) {
+    itsb_engine::DrainSet* D = nullptr;
+    for (unsigned k = 0; k < 2; ++k) { auto& C = e->drain[(e->drain_next + k) & 1]; if (C.pending) { D = &C; break; } }
+    if (!D) return ITSB_ERR_STATE;
+    const uint64_t n = e->n_replicas;
+    out->net = D->net.data(); out->n_net = D->net.size(); out->net_first = D->first.data();
+    out->conn = D->conn.data(); out->n_conn = D->conn.size(); out->conn_first = D->first.data() + (n + 1);
+    out->net_dropped = D->dropped[0]; out->conn_dropped = D->dropped[1];
+    out->d2h_bytes = out->n_net * sizeof(itsb_net_event) + out->n_conn * sizeof(itsb_connection) + 2 * (n + 1) * 8 + 32;
+    D->pending = false;
     return ITSB_OK;
 }
 
