@@ -118,3 +118,71 @@ def test_records_carry_the_tags_greensim_cascades(backend, hostemu):
     assert tag_names(3) == ["MALWARE", "VULNERABLE"]
     # only the overlay's own sockets (port 666: exfiltrate and the command-and-control host) are labelled
     assert {int(r["port"]) for r in got if r["tags"]} == {oracle_netsimple.MalwareModel.BAD_NEWS_BEAR_PORT}
+
+
+def _reference_schemas():
+    reference_schema = "/root/reference/itsim/schemas/items.py"
+    if not os.path.exists(reference_schema):
+        return None
+    scope = {}
+    source = open(reference_schema).read().split("def get_itsim_object_types")[0].replace("import warlock", "")
+    exec(compile(source, reference_schema, "exec"), scope)          # the schema dicts only (warlock is not installed)
+    return scope
+
+
+def test_bulk_tables_equal_the_per_record_documents(hostemu, tmp_path):
+    """The vectorised converters (whole drains at once) give, record for record, the documents of the per-record ones,
+    valid against the reference's three schemas (network_event, node, log), loadable with one executemany per table;
+    and they do it at a rate a drain of millions of records can live with."""
+    import time
+    from itsim_b200 import netsimple, telemetry
+    sim_uuid = "11111111-2222-3333-4444-555555555555"
+    sim = netsimple.build(connection_records=60000, connection_window=8, trace_records=60000)
+    sim.caps["net_event_records"] = 20000
+    sim._lib = hostemu
+    eng = sim.run_replicas(3, seed=0)
+    eng.run(1200.0)
+    trace = eng.trace(1)
+    d = eng.drain(copy=True)
+    rep = telemetry._replica_column(d["net_first"], len(d["net"]))
+    assert len(rep) == len(d["net"]) and rep.max() == 2
+    table = telemetry.network_event_table(d["net"], sim_uuid, replica_of=rep)
+    docs = [json.loads(x) for x in table["json"]]
+    slow = telemetry.network_event_documents(d["net"], sim_uuid=sim_uuid)
+    assert len(docs) == len(slow) > 300
+    for fast, ref in zip(docs, slow):
+        for key in ("sim_uuid", "timestamp", "type", "network_event_type", "pid", "protocol", "src", "dst"):
+            assert fast[key] == ref[key], key
+    assert len(set(table["uuid"].tolist())) == len(docs)               # ids are unique
+    nodes = telemetry.node_table(sim, sim_uuid, replicas=3)
+    node_ids = set(nodes["uuid"].tolist())
+    assert len(node_ids) == 3 * len(sim.nodes) and {x["uuid_node"] for x in docs} <= node_ids
+    assert json.loads(nodes["json"][2])["node_label"] == "Workstation-1 #0"
+    logs = telemetry.log_table(trace, sim_uuid, program_names={netsimple.PROG_MDNS: "mdns_daemon"})
+    assert len(logs["json"]) == len(trace) and "mdns_daemon" in " ".join(logs["json"][:2000].tolist())
+    schemas = _reference_schemas()
+    if schemas is not None:
+        import jsonschema
+        for x in docs[:40]:
+            jsonschema.validate(x, schemas["NETWORK_EVENT_SCHEMA"])
+        for x in nodes["json"][:40]:
+            jsonschema.validate(json.loads(x), schemas["NODE_SCHEMA"])
+        for x in logs["json"][:40]:
+            jsonschema.validate(json.loads(x), schemas["LOG_SCHEMA"])
+    db = sqlite3.connect(str(tmp_path / "itsim.sqlite"))
+    for name, tab in (("network_event", table), ("node", nodes), ("log", logs)):
+        db.execute(f"CREATE TABLE {name} (uuid TEXT PRIMARY KEY, timestamp TEXT, sim_uuid TEXT, json TEXT)")
+        db.executemany(f"INSERT INTO {name} VALUES (?, ?, ?, ?)", telemetry.table_rows(tab))
+        assert db.execute(f"SELECT COUNT(*) FROM {name}").fetchone()[0] == len(tab["uuid"])
+    # the connection lines of Socket.log_pair
+    lines = telemetry.connection_jsonl(d["conn"])
+    slow_conn = telemetry.connection_documents(d["conn"])
+    assert len(lines) == len(slow_conn) > 3000
+    for k in range(0, len(lines), 37):
+        assert json.loads(lines[k]) == slow_conn[k]
+    big = np.tile(d["conn"], 1 + 200000 // len(d["conn"]))[:200000]
+    t0 = time.perf_counter()
+    out = telemetry.connection_jsonl(big)
+    rate = len(out) / (time.perf_counter() - t0)
+    assert json.loads(out[-1]) == telemetry.connection_documents(big[-1:])[0]
+    assert rate > 5e4, rate          # the per-record form manages ~1e5/s before json.dumps; this must not be slower
