@@ -17,7 +17,15 @@ What is timed
           interpreter); the model upload / allocation cost of a cold job is reported beside it in config.
   cpu_baseline / --impl reference
           the oracle (the reference's Python model on the greensim shim -- the reference is pure Python and greensim is
-          not installable here) run one OS process per host core on a bounded sample of the same workload.
+          not installable here) run one OS process per host core on a bounded sample of the same workload; taken BEFORE
+          any GPU work of the process, so that the engine's host threads do not share the cores with it.
+
+Multi-GPU: no PyTorch anywhere.  Under a launcher (``python -m torch.distributed.run`` exports RANK / LOCAL_RANK /
+WORLD_SIZE) every rank drives its GPU through the C ABI and the ranks meet in NCCL (itsim_b200.distributed.RankEnv:
+the NCCL id travels through a file, barrier / max / sum are ncclAllReduce of a few uint64).  ``--gpus N`` without a
+launcher runs the same job from ONE process, one host thread per GPU (itsim_b200.distributed.ShardedEngine).
+``--scaling strong --total-replicas T`` splits a fixed job of T replicas over the GPUs instead of giving each
+``--replicas``.
 """
 import argparse
 import json
@@ -37,6 +45,13 @@ METRIC = "simulated events/sec (batched network_simple replicas)"
 # its traffic goes with the simulated time (100000 replicas x 60 simulated s: 97.36 GB read + 16.78 GB written).
 NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH = {"k_run": (328.9e6 + 160.1e6) / 6000.0}
 NCU_TRAFFIC_BYTES_PER_REPLICA_SECOND = {"k_run_vote": (97.36e9 + 16.78e9) / 100000.0 / 60.0}
+NCU_TRAFFIC_NOTE = ("dram__bytes_read+write per launch, scaled from this kernel's ncu --set full capture under profiles/ "
+                    "(k_run: 6000 replicas x 60 s, per replica and launch; k_run_vote: 100000 replicas x 60 s, per "
+                    "replica and simulated second); dram_gbs = traffic / launch time")
+ROOFLINE_NOTE = ("algorithmic bytes = per-replica state read and written once per run (S_in+S_out, SURVEY 8-d) plus the "
+                 "records a step logs; the engine kernels do not move bytes at the HBM rate: k_run_vote waits on dependent "
+                 "loads of per-replica state (memory latency) and on instruction fetch, k_run on instruction supply; "
+                 "profiles/README.md")
 UNIT = "events/s"
 RESULT_OUT = sys.stdout
 
@@ -54,6 +69,30 @@ def _oracle_job(args):
     pops = model.sim.num_pops
     model.close()
     return events, pops, time.perf_counter() - t0
+
+
+def shim_switch_cost_us(n: int = 20000) -> float:
+    """Cost of one process switch of the greensim shim (the oracle's coroutines are OS threads handing a baton to each
+    other -- greenlet is not installable here -- and that hand-off, not the model, is most of the CPU arm's time):
+    microseconds per heap pop of two processes that do nothing but ``advance(1.0)``."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import greensim
+
+    def idle():
+        while True:
+            greensim.advance(1.0)
+
+    sim = greensim.Simulator()
+    sim.add(idle)
+    sim.add(idle)
+    sim.run(50.0)
+    t0 = time.perf_counter()
+    before = sim.num_pops
+    sim.run(float(n // 2))
+    dt = time.perf_counter() - t0
+    pops = sim.num_pops - before
+    sim._clear()
+    return 1e6 * dt / max(1, pops)
 
 
 def cpu_baseline(horizon: float, replicas_per_core: int = 1, cores: int = 0, seed: int = 0):
@@ -75,7 +114,12 @@ def cpu_baseline(horizon: float, replicas_per_core: int = 1, cores: int = 0, see
                   f"(oracle = reference model on the greensim shim, CPython {sys.version_info.major}."
                   f"{sys.version_info.minor})",
         "events": events, "raw_heap_pops_per_s": pops / wall, "events_per_s_per_core": events / busy,
+        "heap_pops_per_event": pops / max(1, events), "shim_switch_cost_us": shim_switch_cost_us(),
         "wall_s": wall,
+        "why_not_the_12_h_horizon": "config C1's horizon (43 200 s) is ~3.8e6 events = several minutes per replica on "
+                                    "this shim; the contract bounds the CPU sample to 10-30 s, so a replica is run for "
+                                    "the first sample_horizon seconds (the workstations wake up during the first ~600 s;"
+                                    " events/s is events over wall time, so the quiet start costs little of either)",
     }
     return events / wall, info
 
@@ -167,7 +211,115 @@ def run_reference_arm(args) -> None:
     print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
-def replica_histograms(engine, args, L, netsimple, comm, world):
+class _Job:
+    """The replicas this PROCESS advances -- one engine, or one engine per GPU behind ShardedEngine (``--gpus N`` without
+    a launcher) -- and the reductions over the ranks of the job (NCCL through RankEnv; nothing with one process)."""
+
+    def __init__(self, sim, args, env, threads: int):
+        from itsim_b200.distributed import ShardedEngine
+        from itsim_b200.sharding import shard
+        self.env, self.threads = env, threads
+        world = threads if threads > 1 else env.world
+        rank = 0 if threads > 1 else env.rank
+        if args.scaling == "strong":
+            self.total = args.total_replicas or args.replicas
+            self.first, self.count = shard(self.total, rank, world)
+        else:
+            self.total = args.replicas * world
+            self.first, self.count = rank * args.replicas, args.replicas
+        if threads > 1:
+            self.first, self.count = 0, self.total
+            self.sharded = ShardedEngine(sim, self.total, seed=args.seed, devices=list(range(threads)))
+            self.engine = self.sharded.engines[0]
+            self.local_count = self.sharded.shards[0][1]
+        else:
+            self.sharded = None
+            self.engine = sim.run_replicas(self.count, seed=args.seed, first_replica_id=self.first, device=env.local_rank)
+            self.local_count = self.count
+            env.join(self.engine)
+        self.world = world
+        self.logging = bool(args.connections or args.net_events)
+        self.records = {"net": 0, "conn": 0, "net_dropped": 0, "conn_dropped": 0, "d2h_bytes": 0, "drains": 0}
+
+    # -- the engines of this process --------------------------------------------------------------------------------
+    def _engines(self):
+        return self.sharded.engines if self.sharded else [self.engine]
+
+    def run(self, dt):
+        return self.sharded.run(dt) if self.sharded else self.engine.run(dt)
+
+    def run_async(self, dt):
+        (self.sharded or self.engine).run_async(dt)
+
+    def sync(self):
+        return (self.sharded or self.engine).sync()
+
+    def last_run_ms(self):
+        return (self.sharded or self.engine).last_run_ms()
+
+    def launch_count(self):
+        return (self.sharded or self.engine).launch_count()
+
+    def drain_begin(self):
+        for e in self._engines():
+            e.drain_begin()
+
+    def drain_end(self):
+        """Waits for the oldest pending drain of every engine; what came home is counted (and touched: one pass over
+        the timestamps, so that the pages really are in host memory)."""
+        for e in self._engines():
+            d = e.drain_end()
+            self.records["net"] += len(d["net"]); self.records["conn"] += len(d["conn"])
+            self.records["net_dropped"] += d["net_dropped"]; self.records["conn_dropped"] += d["conn_dropped"]
+            self.records["d2h_bytes"] += d["d2h_bytes"]; self.records["drains"] += 1
+            if len(d["conn"]):
+                assert float(d["conn"]["t_end"].max()) >= 0.0
+        return self.records
+
+    def advance(self, total, chunk):
+        """Untimed: `total` simulated seconds in `chunk`-second runs, the record logs emptied after each one when the
+        model keeps them (they are windows sized for a step, not for the whole horizon)."""
+        events, left = 0, total
+        while left > 1e-9:
+            dt = min(chunk, left) if self.logging else left
+            events += self.run(dt)
+            if self.logging:
+                self.drain_begin()
+                self.drain_end()
+            left -= dt
+        return events
+
+    # -- over the ranks ------------------------------------------------------------------------------------------------
+    def barrier(self):
+        if not self.sharded:
+            self.env.barrier()
+
+    def all_max(self, x):
+        return x if self.sharded else self.env.max_float(x)
+
+    def all_sum(self, x):
+        return int(x) if self.sharded else self.env.sum_int(int(x))
+
+    def telemetry_job(self):
+        if self.sharded:
+            return self.sharded.telemetry()
+        return self.engine.allreduce_telemetry(self.env.comm) if self.env.world > 1 else self.engine.telemetry()
+
+    def histogram(self, slot, lo, width, nbins, only_nonzero):
+        if self.sharded:
+            return self.sharded.histogram(slot, lo, width, nbins, only_nonzero)
+        return self.engine.histogram(slot, lo, width, nbins, only_nonzero=only_nonzero,
+                                     comm=self.env.comm if self.env.world > 1 else None)
+
+    def close(self):
+        if self.sharded:
+            self.sharded.close()
+        else:
+            self.env.close()
+            self.engine.close()
+
+
+def replica_histograms(job, args, L, netsimple):
     """Config 3's output: histograms over ALL replicas of the job of beacons per replica, bytes that left the local
     network and the time of the first beacon (`itsb_histogram`: one privatised kernel per statistic, bins summed over
     the ranks with ncclAllReduce when there is a communicator).  Returns (dict, milliseconds for the three)."""
@@ -180,10 +332,10 @@ def replica_histograms(engine, args, L, netsimple, comm, world):
     out = {}
     t0 = time.perf_counter()
     for name, (slot, lo, width, nbins, nonzero) in spec.items():
-        bins = engine.histogram(slot, lo, width, nbins, only_nonzero=nonzero, comm=comm)
+        bins = job.histogram(slot, lo, width, nbins, nonzero)
         out[name] = {"lo": lo, "bin_width": width, "bins": [int(b) for b in bins]}
     ms = 1e3 * (time.perf_counter() - t0)
-    assert sum(out["beacons_per_replica"]["bins"]) == args.replicas * world, "histogram does not cover every replica"
+    assert sum(out["beacons_per_replica"]["bins"]) == job.total, "histogram does not cover every replica"
     return out, ms
 
 
@@ -193,7 +345,10 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--replicas", type=int, default=100000, help="replicas per GPU")
+    ap.add_argument("--replicas", type=int, default=100000, help="replicas per GPU (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --replicas on every GPU; strong: --total-replicas split over the GPUs")
+    ap.add_argument("--total-replicas", type=int, default=0, help="size of the job under --scaling strong")
     ap.add_argument("--slice", type=float, default=120.0, help="simulated seconds per step")
     ap.add_argument("--spinup", type=float, default=1800.0, help="untimed simulated seconds before warm-up")
     ap.add_argument("--seed", type=int, default=0)
@@ -201,14 +356,15 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the untimed full-size self-check after the timed steps")
     ap.add_argument("--arena-nodes", type=int, default=12288)
-    ap.add_argument("--max-events", type=int, default=0, help="future-event pool slots per replica (0 = model default)")
+    ap.add_argument("--max-events", type=int, default=0, help="future-event heap slots per replica (0 = model default)")
     ap.add_argument("--max-procs", type=int, default=0)
     ap.add_argument("--max-sockets", type=int, default=0)
     ap.add_argument("--net-events", type=int, default=0,
                     help="per-replica capacity of the network_event log in HBM (0 = off): the logging-on variant")
     ap.add_argument("--connections", type=int, default=0,
                     help="per-replica capacity of the connection-record log (Socket.log_pair) in HBM (0 = off); with "
-                         "--net-events this is BASELINE.json config 5, full logging")
+                         "--net-events this is BASELINE.json config 5, full logging.  Both logs are drained to the host "
+                         "after every step (itsb_drain_begin / itsb_drain_end), inside the timed regions")
     ap.add_argument("--connection-window", type=int, default=8)
     ap.add_argument("--workload", default="network_simple", choices=["network_simple", "malware", "backdoor", "large_lan"],
                     help="malware = network_simple + the beaconing-malware overlay (BASELINE.json config 3); "
@@ -225,41 +381,20 @@ def main() -> None:
         run_reference_arm(args)
         return
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     import numpy as np
     from itsim_b200 import netsimple, _lib as L
+    from itsim_b200.distributed import RankEnv
     from itsim_b200.engine import summarize
 
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    env = RankEnv()
+    rank, world = env.rank, env.world
+    threads = args.gpus if (world == 1 and args.gpus > 1) else 1      # no launcher: one process, one thread per GPU
+    n_gpus = threads if threads > 1 else world
 
-    def barrier():
-        if dist is not None:
-            import torch
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def allmax(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x: float) -> float:
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    # ---- the CPU arm first, before this process starts any GPU work (its threads would share the cores) -------------
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        _, cpu = cpu_baseline(args.cpu_horizon, 1, 0, args.seed)
 
     # ---- cold job through the public API: compile, upload, allocate, initialise --------------------------------
     t_cold0 = time.perf_counter()
@@ -275,77 +410,91 @@ def main() -> None:
     for key, val in (("max_events", args.max_events), ("max_procs", args.max_procs), ("max_sockets", args.max_sockets)):
         if val:
             sim.caps[key] = val
-    engine = sim.run_replicas(args.replicas, seed=args.seed, first_replica_id=rank * args.replicas, device=local_rank)
+    job = _Job(sim, args, env, threads)
+    engine = job.engine
     t_cold = time.perf_counter() - t_cold0
     state = engine.state_bytes()
     kernel = engine.kernel_name()
     h2d_model = sum(b.nbytes for b in engine.compiled.blobs())
 
-    spin_events = engine.run(args.spinup) if args.spinup > 0 else 0
-    spin_ms = engine.last_run_ms()
+    spin_events = job.advance(args.spinup, args.slice) if args.spinup > 0 else 0
+    spin_ms = job.last_run_ms()
     warm_events = 0
     for _ in range(args.warmup):
-        warm_events += engine.run(args.slice)
-    log_records_before = int(engine.telemetry()[L.TM_USER0 + 7])
-    conn_records_before = int(engine.telemetry()[L.TM_USER0 + 6]) if args.connections else 0
+        warm_events += job.advance(args.slice, args.slice)
+    records_before = dict(job.records)
 
-    # ---- timed region 1: K steps queued back to back, device time ------------------------------------------------
-    sampler = ClockSampler(local_rank)
+    # ---- timed region 1: K steps, device time ------------------------------------------------------------------------
+    # Without record logs the K launches are queued back to back and timed by one pair of CUDA events on the engine's
+    # stream.  With them, every step is followed by its drain (the logs are windows sized for a step), so the steps are
+    # timed one by one -- the engine kernel by its CUDA events, the drain's count / scan / gather kernels and copies by the
+    # host clock around them -- and the device time of the region is their sum.
+    sampler = ClockSampler(env.local_rank)
     sampler.start()
-    launches0 = engine.launch_count()
-    barrier()
-    for _ in range(args.steps):
-        engine.run_async(args.slice)
-    events_dev = engine.sync()
-    ms_dev = engine.last_run_ms()
-    barrier()
-    launches_dev = engine.launch_count() - launches0
-    ms_dev_max = allmax(ms_dev)
-    events_all = allsum(float(events_dev))
+    launches0 = job.launch_count()
+    job.barrier()
+    if not job.logging:
+        for _ in range(args.steps):
+            job.run_async(args.slice)
+        events_dev = job.sync()
+        ms_dev = job.last_run_ms()
+    else:
+        events_dev, ms_dev = 0, 0.0
+        for _ in range(args.steps):
+            events_dev += job.run(args.slice)
+            ms_dev += job.last_run_ms()
+            t0 = time.perf_counter()
+            job.drain_begin()
+            job.drain_end()
+            ms_dev += 1e3 * (time.perf_counter() - t0)
+    job.barrier()
+    launches_dev = job.launch_count() - launches0
+    ms_dev_max = job.all_max(ms_dev)
+    events_all = job.all_sum(events_dev)
     value = events_all / (ms_dev_max * 1e-3)
 
-    # ---- timed region 2: the same K steps, one by one from the host, telemetry read back every step ------------
-    barrier()
+    # ---- timed region 2: the same K steps, one by one from the host through the public API: every step launches,
+    # ---- waits, reads the telemetry vector back, and -- when the model keeps record logs -- brings every record of the
+    # ---- step home (the copy of step k overlaps the kernel of step k + 1) ------------------------------------------
+    job.barrier()
+    records_mid = dict(job.records)
     t0 = time.perf_counter()
     events_e2e = 0
+    pending = False
     for _ in range(args.steps):
-        events_e2e += engine.run(args.slice)
+        job.run_async(args.slice)
+        if pending:
+            job.drain_end()
+        events_e2e += job.sync()
         tm = engine.telemetry()
+        if job.logging:
+            job.drain_begin()
+            pending = True
+    if pending:
+        job.drain_end()
     wall_e2e = time.perf_counter() - t0
     wall_job = time.perf_counter() - t_cold0        # everything since the model was built: compile, upload, allocation,
     events_job = spin_events + warm_events + events_dev + events_e2e      # spin-up, warm-up, both timed regions
-    barrier()
+    job.barrier()
     clocks = sampler.stop()
-    wall_e2e_max = allmax(wall_e2e)
-    e2e_value = allsum(float(events_e2e)) / wall_e2e_max
+    wall_e2e_max = job.all_max(wall_e2e)
+    e2e_value = job.all_sum(events_e2e) / wall_e2e_max
+    d2h_records_per_step = (job.records["d2h_bytes"] - records_mid["d2h_bytes"]) / max(1, args.steps)
 
     # ---- the one collective on the path: telemetry histogram all-reduce ----------------------------------------------
     allreduce_ms = None
-    if dist is not None:
-        import ctypes as C
-        uid = np.zeros(128, dtype=np.uint8)
-        if rank == 0:
-            rc = engine._lib.itsb_nccl_unique_id(uid.ctypes.data, 128)
-            assert rc == 0, rc
-        box = [uid.tobytes()]
-        dist.broadcast_object_list(box, src=0)
-        uid = np.frombuffer(box[0], dtype=np.uint8).copy()
-        comm = C.c_void_p()
-        rc = engine._lib.itsb_nccl_comm_init(engine._h, world, rank, uid.ctypes.data, C.byref(comm))
-        assert rc == 0, engine._lib.itsb_last_error(engine._h)
-        local = engine.telemetry()
-        engine.allreduce_telemetry(comm)          # warm-up (communicator setup)
+    if n_gpus > 1:
+        job.telemetry_job()                       # warm-up (first collective on the communicator)
         t0 = time.perf_counter()
-        total = engine.allreduce_telemetry(comm)
+        total = job.telemetry_job()
         allreduce_ms = 1e3 * (time.perf_counter() - t0)
-        gathered = [None] * world
-        dist.all_gather_object(gathered, local.tolist())
-        assert np.array_equal(total, np.sum(np.array(gathered, dtype=np.uint64), axis=0)), "allreduce mismatch"
-        hists, hist_ms = replica_histograms(engine, args, L, netsimple, comm, world)
-        engine._lib.itsb_nccl_comm_destroy(comm)
+        if not job.sharded:                       # the reduced vector is the sum of the ranks' own vectors, slot by slot
+            local = engine.telemetry()
+            for slot in (0, L.TM_KIND0 + L.EV_DELIVER, L.TM_BYTES_SENT, L.TM_PACKETS_RECEIVED):
+                assert int(total[slot]) == job.all_sum(int(local[slot])), "allreduce mismatch"
     else:
-        total = engine.telemetry()
-        hists, hist_ms = replica_histograms(engine, args, L, netsimple, None, 1)
+        total = job.telemetry_job()
+    hists, hist_ms = replica_histograms(job, args, L, netsimple)
 
     # ---- full-size self-check (untimed): conservation laws on the job's counters, and sampled replicas of the batch
     # ---- equal the same replica ids advanced alone through the same sequence of run() calls -----------------------
@@ -363,14 +512,25 @@ def main() -> None:
             checks["tx_begin_equal_packets_sent"] = int(tm_job[k0 + L.EV_TX_BEGIN]) == int(tm_job[L.TM_PACKETS_SENT])
             checks["latency_histogram_covers_every_transmission"] = \
                 int(tm_job[L.TM_LAT0:L.TM_LAT0 + L.LAT_BINS].sum()) == int(tm_job[k0 + L.EV_TX_BEGIN])
-        sample = sorted({0, args.replicas // 2, args.replicas - 1})
+        if job.logging:
+            checks["no_record_dropped"] = job.records["net_dropped"] == 0 and job.records["conn_dropped"] == 0
+            if n_gpus == 1:
+                checks["every_record_produced_came_home"] = \
+                    int(tm_job[L.TM_USER0 + 6]) == job.records["conn"] and int(tm_job[L.TM_USER0 + 7]) == job.records["net"]
+        sample = sorted({0, job.local_count // 2, job.local_count - 1})
         same = []
         for r in sample:
-            alone = sim.run_replicas(1, seed=args.seed, first_replica_id=rank * args.replicas + r, device=local_rank)
-            if args.spinup > 0:
-                alone.run(args.spinup)
-            for _ in range(args.warmup + 2 * args.steps):
-                alone.run(args.slice)
+            alone = sim.run_replicas(1, seed=args.seed, first_replica_id=job.first + r, device=env.local_rank)
+            alone_job_logging = job.logging
+            calls = ([args.spinup] if args.spinup > 0 else []) + [args.slice] * (args.warmup + 2 * args.steps)
+            for dt in calls:
+                left = dt
+                while left > 1e-9:              # the same sequence of run() calls the batch went through
+                    step = min(args.slice, left) if alone_job_logging else left
+                    alone.run(step)
+                    if alone_job_logging:
+                        alone.drain()
+                    left -= step
             same.append(bool(np.array_equal(alone.replica_telemetry(0), engine.replica_telemetry(r))))
             alone.close()
         checks["replicas_equal_themselves_run_alone"] = dict(zip(map(str, sample), same))
@@ -379,46 +539,53 @@ def main() -> None:
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        events_per_step_gpu = events_dev / args.steps
-        log_records = (int(total[L.TM_USER0 + 7]) // max(1, world) - log_records_before) / (2.0 * args.steps)
-        # S_in + S_out per launch, plus B_log = 32 B per network_event record written in a step (0 when the log is off)
-        conn_records = ((int(total[L.TM_USER0 + 6]) // max(1, world) - conn_records_before) / (2.0 * args.steps)
-                        if args.connections else 0.0)
-        algo_bytes = 2.0 * state["hot"] * args.replicas + 32.0 * log_records + 40.0 * conn_records
+        per_gpu = job.local_count
+        events_per_step_gpu = events_dev / args.steps / (threads if threads > 1 else 1)
+        steps_logged = 2.0 * args.steps
+        log_records = (job.records["net"] - records_before["net"]) / steps_logged / (threads if threads > 1 else 1)
+        conn_records = (job.records["conn"] - records_before["conn"]) / steps_logged / (threads if threads > 1 else 1)
+        # S_in + S_out per launch, plus B_log = 32 B per network_event record and 40 B per connection record of a step
+        algo_bytes = 2.0 * state["hot"] * per_gpu + 32.0 * log_records + 40.0 * conn_records
         launch_s = ms_dev * 1e-3 / args.steps
         achieved = algo_bytes / launch_s / 1e9
         traffic = None
         if kernel in NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH:
-            traffic = NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH[kernel] * args.replicas
+            traffic = NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH[kernel] * per_gpu
         elif kernel in NCU_TRAFFIC_BYTES_PER_REPLICA_SECOND:
-            traffic = NCU_TRAFFIC_BYTES_PER_REPLICA_SECOND[kernel] * args.replicas * args.slice
-        cpu = None
-        if not args.no_cpu_baseline:
-            _, cpu = cpu_baseline(args.cpu_horizon, 1, 0, args.seed)
+            traffic = NCU_TRAFFIC_BYTES_PER_REPLICA_SECOND[kernel] * per_gpu * args.slice
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"{args.workload} "
                             f"({'1024 endpoints + 16 routers' if args.workload == 'large_lan' else '50 endpoints, /24'})"
-                            f" x {args.replicas} replicas per GPU, "
-                            f"step = run({args.slice:g} simulated s) on every replica after {args.spinup:g} s spin-up",
-                "replicas_per_gpu": args.replicas, "slice_s": args.slice, "spinup_s": args.spinup, "seed": args.seed,
+                            + (f" x {args.replicas} replicas per GPU, " if args.scaling == "weak" else
+                               f" x {job.total} replicas in all, split over {n_gpus} GPU(s) ({per_gpu} on rank 0), ")
+                            + f"step = run({args.slice:g} simulated s) on every replica after {args.spinup:g} s spin-up",
+                "replicas_per_gpu": per_gpu, "replicas_total": job.total, "slice_s": args.slice,
+                "spinup_s": args.spinup, "seed": args.seed,
+                "processes": "one per GPU (launcher), NCCL between them" if world > 1 else
+                             ("one, a host thread per GPU" if threads > 1 else "one"),
                 "events_per_step_per_gpu": events_per_step_gpu,
                 "l2": "inputs larger than L2 (replica state %.2f GB per GPU vs 126 MB L2)" %
-                      (args.replicas * (state["hot"] + state["arena"]) / 1e9),
+                      (per_gpu * (state["hot"] + state["arena"]) / 1e9),
                 "hot_bytes_per_replica": state["hot"], "arena_bytes_per_replica": state["arena"],
                 "net_event_records_per_step_per_gpu": log_records,
                 "connection_records_per_step_per_gpu": conn_records,
+                "records": dict(job.records) if job.logging else None,
                 "cold_job_s": t_cold, "cold_job_h2d_bytes": h2d_model,
                 "spinup_events": spin_events, "spinup_ms": spin_ms,
                 "telemetry_allreduce_ms": allreduce_ms,
                 "telemetry": {k: v for k, v in summarize(total).items() if k != "latency_hist"},
                 "replica_histograms": hists, "replica_histograms_ms": hist_ms,
             },
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 320, "d2h_bytes_per_step": 8 * L.TM_SIZE + 24,
-                    "note": "per step: kernel arguments + ticket reset H2D; telemetry vector, event count and status D2H",
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 320,
+                    "d2h_bytes_per_step": 8 * L.TM_SIZE + 24 + d2h_records_per_step,
+                    "note": "per step: kernel arguments + ticket reset H2D; telemetry vector, event count and status D2H"
+                            + ("; plus every network_event / connection record of the step, packed on the device and "
+                               "copied to pinned host memory (itsb_drain_*), the copy overlapping the next step's kernel"
+                               if job.logging else ""),
                     "whole_job": {"value": events_job / wall_job, "unit": UNIT, "wall_s": wall_job, "events": events_job,
                                   "note": "rank 0, host clock from model construction to the last telemetry read: "
                                           "compile + table upload + replica allocation / initialisation + spin-up + "
@@ -427,15 +594,11 @@ def main() -> None:
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "dram_gbs": (traffic / launch_s / 1e9) if traffic else None,
+                "traffic_over_algorithmic": (traffic / algo_bytes) if traffic else None,
                 "peak_source": peak_src, "kernel": kernel,
-                "traffic_note": "dram__bytes_read+write per launch, scaled from this kernel's ncu --set full capture under "
-                                "profiles/ (k_run: 6000 replicas x 60 s, per replica and launch; k_run_vote: 100000 "
-                                "replicas x 60 s, per replica and simulated second); dram_gbs = traffic / launch time",
+                "traffic_note": NCU_TRAFFIC_NOTE,
                 "algorithmic_bytes_per_launch": algo_bytes,
-                "note": "algorithmic bytes = per-replica state read and written once per run (S_in+S_out, SURVEY 8-d); "
-                        "neither engine kernel moves bytes at the HBM rate: k_run is bound by instruction supply (GPC-level "
-                        "instruction-cache requests at 93% of peak), k_run_vote by memory latency (85% of stall samples "
-                        "wait on loads, DRAM at ~13% of peak); profiles/README.md",
+                "note": ROOFLINE_NOTE,
             },
             "clocks": clocks,
             "checks": checks,
@@ -443,9 +606,7 @@ def main() -> None:
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), file=RESULT_OUT, flush=True)
-    engine.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    job.close()
 
 
 if __name__ == "__main__":

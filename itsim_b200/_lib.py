@@ -12,7 +12,8 @@ from typing import Optional
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libitsim_b200.so")
+# ITSB_LIB: another build of the same library (the -DITSB_EXPERIMENTS one, for A/B measurements); never a different engine
+LIB_PATH = os.environ.get("ITSB_LIB") or os.path.join(HERE, "libitsim_b200.so")
 
 ABI_VERSION = 4
 TM_KIND0, TM_PACKETS_SENT, TM_BYTES_SENT, TM_PACKETS_RECEIVED, TM_BYTES_RECEIVED = 0, 9, 10, 11, 12

@@ -493,6 +493,13 @@ int itsb_run_async(itsb_engine* e, double duration) {
     e->rp.duration = duration;
     if (!e->run_pending) CU(e, cudaEventRecord(e->ev_start, e->stream));
     const uint32_t lane_grid = e->grid * (uint32_t)e->kernel_ctas;
+    {   /* lanes per warp that take replicas: all 32 once the batch fills the grid's threads */
+        const uint64_t warps = (uint64_t)lane_grid * 8;
+        uint64_t lpw = (e->n_replicas + warps - 1) / warps;
+        const char* force = getenv("ITSB_VOTE_LANES");
+        if (force && atoi(force) >= 1) lpw = (uint64_t)atoi(force);
+        e->rp.lanes_per_warp = (uint32_t)(lpw < 1 ? 1 : (lpw > 32 ? 32 : lpw));
+    }
     switch (e->kernel) {
     case K_VOTE:     k_run_vote<<<lane_grid, 256, e->so.total, e->stream>>>(e->rp); break;
 #if defined(ITSB_EXPERIMENTS)
@@ -883,10 +890,8 @@ void itsb_destroy(itsb_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); }
-    drain_free(e);
-    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
-    free_replicas(e);
+    free_replicas(e);         /* waits for the copy stream, releases the drain buffers */
+    if (e->copy_stream) { cudaStreamDestroy(e->copy_stream); e->copy_stream = nullptr; }
     for (int i = 0; i < ITSB_NUM_BLOBS; ++i) cudaFree(e->d_tables[i]);
     cudaFree(e->d_ticket); cudaFree(e->d_first_failed); cudaFree(e->d_telemetry); cudaFree(e->d_model); cudaFree(e->d_scratch);
     if (e->ev_start) cudaEventDestroy(e->ev_start);

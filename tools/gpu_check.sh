@@ -16,6 +16,18 @@ bench)
   timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json | head -c 1500; echo;;
 benchwarp)
   ITSB_KERNEL=warp timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_warp.json 2> gpurun_out/bench_warp.err; echo "bench warp rc=$?"; head -c 600 gpurun_out/bench_warp.json; echo;;
+sweep)
+  # small batches (strong scaling: config C2 split 2, 4, 8 ways), both engine designs
+  for n in 12500 25000 50000; do for k in warp vote; do
+    ITSB_KERNEL=$k timeout 600 python bench.py --replicas $n --steps 5 --warmup 2 --no-cpu-baseline --no-verify > gpurun_out/sweep_${k}_${n}.json 2> gpurun_out/sweep_${k}_${n}.err
+    python -c "import json;d=json.load(open('gpurun_out/sweep_${k}_${n}.json'));print('$k',$n,'%.3e'%d['value'],d['roofline']['kernel'])"
+  done; done;;
+experiments)
+  # the regrouping variants of round 1 on this round's engine core (the -DITSB_EXPERIMENTS build)
+  for k in pool sorted lanes; do
+    ITSB_LIB=$PWD/itsim_b200/libitsim_b200_experiments.so ITSB_KERNEL=$k timeout 600 python bench.py --steps 5 --warmup 2 --no-cpu-baseline --no-verify > gpurun_out/exp_${k}.json 2> gpurun_out/exp_${k}.err
+    python -c "import json;d=json.load(open('gpurun_out/exp_${k}.json'));print('$k','%.3e'%d['value'],d['roofline']['kernel'])"
+  done;;
 ncu)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-verify > gpurun_out/ncu_list.log 2>&1; echo "ncu list rc=$?"
