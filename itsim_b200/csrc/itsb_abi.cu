@@ -28,15 +28,20 @@
 extern "C" __global__ void k_run_in_place(const RunParams p);   /* itsb_inplace.cu */
 extern "C" __global__ void k_run_wide(const RunParams p);       /* itsb_wide.cu: 13..16 warps per CTA */
 extern "C" __global__ void k_run_vote(const RunParams p);       /* itsb_lanes.cu: a replica per lane + per-warp majority key */
+extern "C" __global__ void k_run_vote_hbm(const RunParams p);   /* itsb_lanes_hbm.cu: the same for models whose tables stay in HBM */
 #if defined(ITSB_EXPERIMENTS)
 /* Variants measured slower in round 1 (profiles/README.md holds the tables); built only with -DITSB_EXPERIMENTS
  * (python __graft_entry__.py --experiments), never part of the product library. */
 extern "C" __global__ void k_run_phased(const RunParams p);     /* itsb_phased.cu: warps aligned on the loop's two halves */
 extern "C" __global__ void k_run_lanes(const RunParams p);      /* itsb_lanes.cu: a replica per lane, no vote */
 extern "C" __global__ void k_run_sorted(const RunParams p);     /* itsb_sorted.cu: lanes regrouped by next event, CTA-wide */
-extern "C" __global__ void k_run_pool(const RunParams p);       /* itsb_pool.cu: replicas change warps via per-kind rings */
-extern "C" size_t itsb_pool_shared_bytes(void);
 #endif
+/* itsb_pool.cu: k_run_pool<threads, CTAs per SM, slots, ring> -- a replica per lane, replicas change warps through per-kind
+ * rings in shared memory; the shapes are instantiated there */
+extern "C" int itsb_pool_shapes(void);
+extern "C" const char* itsb_pool_shape_name(int shape);
+extern "C" bool itsb_pool_prepare(int shape, size_t table_bytes);
+extern "C" cudaError_t itsb_pool_launch(int shape, int n_sms, size_t table_bytes, RunParams rp, cudaStream_t stream);
 
 /* up to 12 warps per CTA (what shared memory allows the flagship model): 168 registers per thread, no spills */
 extern "C" __global__ void __launch_bounds__(384, 1) k_run(const RunParams p) {
@@ -198,9 +203,9 @@ extern "C" __global__ void __launch_bounds__(128) k_log_gather(
  * records (their per-socket correlation is lane-parallel work in the warp-per-replica kernels).  ITSB_KERNEL=
  * warp | vote overrides (lanes | sorted | pool | phased too in a -DITSB_EXPERIMENTS build), ITSB_KERNEL_CTAS=n sets
  * the CTAs per SM of the lane kernels. */
-enum { K_WARP = 0, K_WIDE, K_IN_PLACE, K_PHASED, K_VOTE, K_LANES, K_SORTED, K_POOL };
+enum { K_WARP = 0, K_WIDE, K_IN_PLACE, K_PHASED, K_VOTE, K_LANES, K_SORTED, K_POOL, K_VOTE_HBM };
 static const char* const KERNEL_NAMES[] = {"k_run", "k_run_wide", "k_run_in_place", "k_run_phased", "k_run_vote",
-                                           "k_run_lanes", "k_run_sorted", "k_run_pool"};
+                                           "k_run_lanes", "k_run_sorted", "k_run_pool", "k_run_vote_hbm"};
 
 struct itsb_engine {
     int device = 0;
@@ -247,6 +252,9 @@ struct itsb_engine {
     int kernel_ctas = 3;                          /* CTAs of 256 threads per SM for the lane-per-replica kernels */
     bool forced_in_place = false;
     bool lane_smem_ok = false;                    /* the lane kernels' dynamic shared memory (model tables) was granted */
+    int pool_shape = 1;                           /* which instantiation of k_run_pool (itsb_pool.cu POOL_SHAPES) */
+    bool pool_ok = false;
+    std::string kernel_label;
     float last_ms = 0.f;
     long long first_failed = -1;
     std::string err;
@@ -257,19 +265,27 @@ static void choose_kernel(itsb_engine* e) {
     const char* c = getenv("ITSB_KERNEL_CTAS");
     e->kernel_ctas = c && atoi(c) >= 1 && atoi(c) <= 8 ? atoi(c) : 3;
     const std::string want = k ? k : "";
-    /* a lane per replica: the model tables must fit beside three CTAs per SM (cudaFuncSetAttribute in itsb_load_model) */
+    /* a lane per replica: the model tables staged beside three CTAs per SM (k_run_vote), or left in HBM when they
+       exceed shared memory (k_run_vote_hbm: config C4) */
     const bool lane_ok = !e->rp.tables_in_hbm && !e->forced_in_place && e->lane_smem_ok;
+    const bool lane_hbm_ok = e->rp.tables_in_hbm && !e->forced_in_place;
     int warp_kernel = e->rp.state_in_hbm ? K_IN_PLACE : (e->warps_per_cta > 12 ? K_WIDE : K_WARP);
 #if defined(ITSB_EXPERIMENTS)
     if (want == "phased" && warp_kernel == K_WARP) warp_kernel = K_PHASED;
 #endif
     if (lane_ok && want == "vote") e->kernel = K_VOTE;
+    else if (lane_hbm_ok && want == "vote") e->kernel = K_VOTE_HBM;
+    else if (lane_ok && e->pool_ok && want == "pool") e->kernel = K_POOL;
 #if defined(ITSB_EXPERIMENTS)
     else if (lane_ok && want == "lanes") e->kernel = K_LANES;
     else if (lane_ok && want == "sorted") e->kernel = K_SORTED;
-    else if (lane_ok && want == "pool") e->kernel = K_POOL;
 #endif
-    else if (want == "warp" || want == "phased" || !lane_ok) e->kernel = warp_kernel;
+    else if (want == "warp" || want == "phased" || (!lane_ok && !lane_hbm_ok)) e->kernel = warp_kernel;
+    else if (lane_hbm_ok) {
+        /* nothing on the shipped-itsim path is lane-parallel, so a lane per replica only needs more replicas than the
+           warp kernel holds in flight (148 SMs x 16-20 warps) to win: measured on config C4 (profiles/README.md) */
+        e->kernel = e->n_replicas >= 4096 ? K_VOTE_HBM : warp_kernel;
+    }
     else {
         /* a lane per replica needs replicas to fill its threads (148 SMs x 768): measured on the default model, the two
            designs cross at 50 000 replicas (12 500: 0.73 vs 2.15, 25 000: 1.26 vs 2.21, 50 000: 2.26 vs 2.24,
@@ -416,10 +432,13 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     e->lane_smem_ok = !e->rp.tables_in_hbm &&
                       cudaFuncSetAttribute(k_run_vote, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->so.total) == cudaSuccess;
     cudaGetLastError();
+    {
+        const char* shape = getenv("ITSB_POOL_SHAPE");
+        e->pool_shape = shape && atoi(shape) >= 0 && atoi(shape) < itsb_pool_shapes() ? atoi(shape) : 1;
+        e->pool_ok = e->lane_smem_ok && itsb_pool_prepare(e->pool_shape, e->so.total);
+    }
 #if defined(ITSB_EXPERIMENTS)
     CU(e, cudaFuncSetAttribute(k_run_phased, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
-    CU(e, cudaFuncSetAttribute(k_run_pool, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(e->so.total + itsb_pool_shared_bytes())));
     if (e->lane_smem_ok) {
         CU(e, cudaFuncSetAttribute(k_run_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->so.total));
         CU(e, cudaFuncSetAttribute(k_run_sorted, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -502,11 +521,12 @@ int itsb_run_async(itsb_engine* e, double duration) {
     }
     switch (e->kernel) {
     case K_VOTE:     k_run_vote<<<lane_grid, 256, e->so.total, e->stream>>>(e->rp); break;
+    case K_VOTE_HBM: k_run_vote_hbm<<<lane_grid, 256, e->so.total, e->stream>>>(e->rp); break;
+    case K_POOL:     CU(e, itsb_pool_launch(e->pool_shape, (int)e->grid, e->so.total, e->rp, e->stream)); break;
 #if defined(ITSB_EXPERIMENTS)
     case K_LANES:    k_run_lanes<<<lane_grid, 256, e->so.total, e->stream>>>(e->rp); break;
     case K_SORTED:   k_run_sorted<<<lane_grid, 256, e->so.total + 256 * (sizeof(PendingEvent) + sizeof(RunCtx) + 2 + 1 + 4) + 64,
                                     e->stream>>>(e->rp); break;
-    case K_POOL:     k_run_pool<<<lane_grid, 256, e->so.total + itsb_pool_shared_bytes(), e->stream>>>(e->rp); break;
     case K_PHASED:   k_run_phased<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp); break;
 #endif
     case K_IN_PLACE: k_run_in_place<<<e->grid, e->warps_per_cta * 32, e->smem_bytes, e->stream>>>(e->rp); break;

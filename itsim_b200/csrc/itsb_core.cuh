@@ -2239,8 +2239,13 @@ ITSB_FN void run_handle(Rep& R, const PendingEvent& E) {
             }
         }
         if (live) {
+#if defined(ITSB_HIDDEN_FAST)
+            if (P.prog == PROG_HIDDEN_WAIT_ONE) hidden_wait_one(H, idx); else
+#endif
+            {
             if (!is_hidden_prog(P.prog)) count_event(R, kind, P.prog, P.node, 0);
             runnable = idx;
+            }
         }
     } else if (kind == ITSB_EV_TX_BEGIN) {
         on_tx_begin(H, ev_pkt(data));
@@ -2253,6 +2258,13 @@ ITSB_FN void run_handle(Rep& R, const PendingEvent& E) {
                 count_event(R, ITSB_EV_THROW, P.prog, P.node, ev_exc(data));
             if (P.state == PS_UNSTARTED) proc_exit(H, idx);
             else runnable = deliver_exception(H, idx, ev_exc(data));
+#if defined(ITSB_HIDDEN_FAST)
+            /* a helper whose handler is the program's EXIT (CleanUp / CancelBalk: `except ...: pass`) ends here */
+            if (runnable != NIL32 && is_hidden_prog(P.prog) && (u32)(R.m.code[P.pc] & 0xFF) == OP_EXIT) {
+                proc_exit(H, idx);
+                runnable = NIL32;
+            }
+#endif
         }
     } else {
         fail(H, ITSB_ERR_BAD_OPCODE, data);

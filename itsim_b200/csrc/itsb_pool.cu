@@ -1,34 +1,33 @@
 /*
- * itsb_pool.cu -- EXPERIMENT (ITSB_KERNEL=pool): a replica per lane, replicas changing warps through per-kind queues in
- * shared memory.
+ * itsb_pool.cu -- k_run_pool: a replica per lane, replicas changing warps through per-kind queues in shared memory.
  *
  * k_run_vote regroups inside one warp: the warp runs the event kind most of its own 32 lanes wait on (6 lanes active on
- * average).  Here a CTA's 256 replicas are not tied to lanes at all.  Each replica sits in a *slot* in shared memory (its
+ * average).  Here a CTA's replicas are not tied to lanes at all.  Each replica sits in a *slot* in shared memory (its
  * address, the run's bookkeeping, its pending event: 64 bytes); a slot whose replica is ready sits in the ring of its
  * pending event's kind.  A warp takes up to 32 slots from the fullest ring, its lanes handle those events -- one kind, so
  * one handler -- take each replica's next event and push the slot onto the ring of that event's kind.  No CTA barrier:
  * the rings are the only synchronisation (atomic reservation of positions, entries published with the lap of their
  * position and cleared by the lane that takes them).  A replica still sees its own events in its own order, so results are
  * bit-identical to the other kernels'.
+ *
+ * Round 1 built this as an experiment and measured it slower than the per-warp vote (2.53 vs 3.75 x 10^9 events/s): the
+ * engine then waited on chains of dependent loads, and grouping does not shorten those.  Round 2 shortened them
+ * (delivery digests, the event heap, inline queue heads: DESIGN.md section 4), which left k_run_vote bound by the rate
+ * at which its SMs can fetch instructions (GPC instruction-cache requests at 91 % of their peak) -- and what grouping
+ * buys is exactly that: the same events in fewer warp instructions.  Shapes (threads x CTAs per SM, slots per CTA) are
+ * template parameters; itsb_pool_launch picks one (ITSB_POOL_SHAPE overrides; measurements in profiles/README.md).
  */
 #define ITSB_LANES 1
 #include "itsb_kernel.cuh"
 
-#ifndef POOL_SLOTS
-#define POOL_SLOTS 256                  /* replicas a CTA holds at a time (measured: 256 with 3 CTAs per SM 2.53, 1024 with 2 CTAs
-                                           1.61, 1024 with 1 CTA 1.37 x 10^9 events/s on the default bench) */
-#endif
-#define POOL_THREADS 256
 #define POOL_RINGS 9                    /* ring index = event kind (0..8) */
-#ifndef ITSB_POOL_MIN_CTAS
-#define ITSB_POOL_MIN_CTAS 3
-#endif
 
 struct PoolSlot { PendingEvent E; RunCtx C; unsigned long long r; };      /* 64 bytes */
 
+template <int SLOTS, int RING>
 struct PoolShared {
-    PoolSlot slot[POOL_SLOTS];
-    unsigned int ring[POOL_RINGS][POOL_SLOTS];      /* slot + 1; 0 = position reserved but not published yet / free */
+    PoolSlot slot[SLOTS];
+    unsigned int ring[POOL_RINGS][RING];            /* (lap << 16) | (slot + 1); 0 = free */
     unsigned int head[POOL_RINGS];
     unsigned int tail[POOL_RINGS];
     unsigned int live;                              /* slots that hold an unfinished replica */
@@ -38,13 +37,15 @@ struct PoolShared {
  * of a position waits for the cell to be free (the entry of the previous lap taken), the consumer of a position waits
  * for ITS lap's entry: an entry of the previous lap that its own consumer has claimed but not read yet can never be
  * mistaken for the new one. */
-__device__ __forceinline__ unsigned int pool_lap(unsigned int pos) { return (pos / POOL_SLOTS) % 0xFFFFu + 1u; }
+template <int RING>
+__device__ __forceinline__ unsigned int pool_lap(unsigned int pos) { return (pos / RING) % 0xFFFFu + 1u; }
 
-__device__ __forceinline__ void pool_push(PoolShared* S, unsigned int kind, unsigned int slot) {
-    const unsigned int pos = atomicAdd(&S->tail[kind], 1u);
-    volatile unsigned int* cell = &S->ring[kind][pos & (POOL_SLOTS - 1)];
-    const unsigned int val = (pool_lap(pos) << 16) | (slot + 1u);
-    while (atomicCAS((unsigned int*)cell, 0u, val) != 0u) { }
+template <int RING>
+__device__ __forceinline__ void pool_push(unsigned int* ring, unsigned int* tail, unsigned int slot) {
+    const unsigned int pos = atomicAdd(tail, 1u);
+    unsigned int* cell = ring + (pos & (RING - 1));
+    const unsigned int val = (pool_lap<RING>(pos) << 16) | (slot + 1u);
+    while (atomicCAS(cell, 0u, val) != 0u) { }
 }
 
 /* binds the views of replica r and starts its run(); returns false if the run is over before its first event */
@@ -69,22 +70,26 @@ __device__ __forceinline__ bool pool_begin(const RunParams& p, const Model* m, u
     return false;
 }
 
-extern "C" __global__ void __launch_bounds__(POOL_THREADS, ITSB_POOL_MIN_CTAS) k_run_pool(const RunParams p) {
+template <int THREADS, int MIN_CTAS, int SLOTS, int RING>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) k_run_pool(const RunParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
+    typedef PoolShared<SLOTS, RING> Shared;
     const Model* m = p.tables_in_hbm ? p.model_dev : stage_model(p.model, smem);
-    PoolShared* S = (PoolShared*)(smem + (p.tables_in_hbm ? 0 : p.static_bytes));
+    Shared* S = (Shared*)(smem + (p.tables_in_hbm ? 0 : p.static_bytes));
     const unsigned int t = threadIdx.x, lane = t & 31;
-    for (unsigned int i = t; i < POOL_RINGS * POOL_SLOTS; i += POOL_THREADS) (&S->ring[0][0])[i] = 0;
+    for (unsigned int i = t; i < POOL_RINGS * RING; i += THREADS) (&S->ring[0][0])[i] = 0;
     if (t < POOL_RINGS) { S->head[t] = 0; S->tail[t] = 0; }
     if (t == 0) S->live = 0;
     __syncthreads();
-    /* every thread seeds its share of the slots with replicas */
-    for (unsigned int sl = t; sl < POOL_SLOTS; sl += POOL_THREADS) {
+    /* the batch is spread evenly over the CTAs: each seeds its share of slots (p.lanes_per_warp carries the share), and a
+       slot whose replica finishes takes the next one of the batch */
+    const unsigned int my_slots = p.lanes_per_warp < (unsigned int)SLOTS ? p.lanes_per_warp : (unsigned int)SLOTS;
+    for (unsigned int sl = t; sl < my_slots; sl += THREADS) {
         unsigned int kind = 0;
         bool ready = false;
         unsigned long long r = atomicAdd(p.ticket, 1ull);
         while (r < p.n_replicas && !(ready = pool_begin(p, m, r, S->slot[sl], kind))) r = atomicAdd(p.ticket, 1ull);
-        if (ready) { atomicAdd(&S->live, 1u); pool_push(S, kind, sl); }
+        if (ready) { atomicAdd(&S->live, 1u); __threadfence_block(); pool_push<RING>(S->ring[kind], &S->tail[kind], sl); }
     }
     __syncthreads();
     /* ---- warps pull slots of one kind, handle, push them on ------------------------------------------------------------ */
@@ -96,16 +101,16 @@ extern "C" __global__ void __launch_bounds__(POOL_THREADS, ITSB_POOL_MIN_CTAS) k
 #pragma unroll
                 for (unsigned int k = 0; k < POOL_RINGS; ++k) {
                     const unsigned int avail = *(volatile unsigned int*)&S->tail[k] - *(volatile unsigned int*)&S->head[k];
-                    if (avail > best_n && avail <= POOL_SLOTS) { best_n = avail; best = k; }
+                    if (avail > best_n && avail <= (unsigned int)RING) { best_n = avail; best = k; }
                 }
                 if (best_n == 0) {
                     if (*(volatile unsigned int*)&S->live == 0) { n = 0xFFFFFFFFu; break; }      /* the CTA's work is done */
-                    __nanosleep(200);
+                    __nanosleep(100);
                     continue;
                 }
                 const unsigned int h = *(volatile unsigned int*)&S->head[best];
                 const unsigned int avail = *(volatile unsigned int*)&S->tail[best] - h;
-                if (avail == 0 || avail > POOL_SLOTS) continue;
+                if (avail == 0 || avail > (unsigned int)RING) continue;
                 const unsigned int take = avail < 32u ? avail : 32u;
                 if (atomicCAS(&S->head[best], h, h + take) == h) { kind = best; first = h; n = take; break; }
             }
@@ -115,8 +120,8 @@ extern "C" __global__ void __launch_bounds__(POOL_THREADS, ITSB_POOL_MIN_CTAS) k
         n = __shfl_sync(0xFFFFFFFFu, n, 0);
         if (n == 0xFFFFFFFFu) break;
         if (lane < n) {
-            volatile unsigned int* cell = &S->ring[kind][(first + lane) & (POOL_SLOTS - 1)];
-            const unsigned int want = pool_lap(first + lane);
+            volatile unsigned int* cell = &S->ring[kind][(first + lane) & (RING - 1)];
+            const unsigned int want = pool_lap<RING>(first + lane);
             unsigned int v;
             while (((v = *cell) >> 16) != want) { }
             *cell = 0u;
@@ -132,7 +137,8 @@ extern "C" __global__ void __launch_bounds__(POOL_THREADS, ITSB_POOL_MIN_CTAS) k
             if (run_take(R, C, E)) {
                 SL.E = E;
                 __threadfence_block();
-                pool_push(S, ev_kind(E.data), s);
+                const unsigned int k2 = ev_kind(E.data);
+                pool_push<RING>(S->ring[k2], &S->tail[k2], s);
             } else {
                 atomicAdd(p.events_done, run_events(R, C));
                 if (R.hdr->status != 0) atomicMin(p.first_failed, (long long)r);
@@ -141,7 +147,7 @@ extern "C" __global__ void __launch_bounds__(POOL_THREADS, ITSB_POOL_MIN_CTAS) k
                 bool ready = false;
                 r = atomicAdd(p.ticket, 1ull);
                 while (r < p.n_replicas && !(ready = pool_begin(p, m, r, SL, k2))) r = atomicAdd(p.ticket, 1ull);
-                if (ready) { __threadfence_block(); pool_push(S, k2, s); }
+                if (ready) { __threadfence_block(); pool_push<RING>(S->ring[k2], &S->tail[k2], s); }
                 else atomicSub(&S->live, 1u);
             }
         }
@@ -149,4 +155,39 @@ extern "C" __global__ void __launch_bounds__(POOL_THREADS, ITSB_POOL_MIN_CTAS) k
     }
 }
 
-extern "C" __attribute__((visibility("hidden"))) size_t itsb_pool_shared_bytes(void) { return sizeof(PoolShared) + 64; }
+/* ---- shapes ------------------------------------------------------------------------------------------------------------- */
+struct PoolShape { int threads, ctas_per_sm, slots; size_t shared; void (*kernel)(const RunParams); const char* name; };
+
+#define POOL_SHAPE(T, C, S, R) {T, C, S, sizeof(PoolShared<S, R>) + 64, k_run_pool<T, C, S, R>, #T "x" #C "/" #S}
+static const PoolShape POOL_SHAPES[] = {
+    POOL_SHAPE(256, 3, 256, 256),       /* round 1's shape */
+    POOL_SHAPE(768, 1, 768, 1024),
+    POOL_SHAPE(512, 1, 768, 1024),
+    POOL_SHAPE(384, 2, 384, 512),
+    POOL_SHAPE(512, 1, 1024, 1024),
+    POOL_SHAPE(384, 1, 768, 1024),
+};
+static const int N_POOL_SHAPES = (int)(sizeof(POOL_SHAPES) / sizeof(POOL_SHAPES[0]));
+
+extern "C" __attribute__((visibility("hidden"))) int itsb_pool_shapes(void) { return N_POOL_SHAPES; }
+extern "C" __attribute__((visibility("hidden"))) const char* itsb_pool_shape_name(int i) { return POOL_SHAPES[i].name; }
+
+/* opt-in shared memory for one shape (tables + slots + rings); returns false when it does not fit */
+extern "C" __attribute__((visibility("hidden"))) bool itsb_pool_prepare(int shape, size_t table_bytes) {
+    const PoolShape& P = POOL_SHAPES[shape];
+    const bool ok = cudaFuncSetAttribute(P.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(table_bytes + P.shared)) == cudaSuccess;
+    cudaGetLastError();
+    return ok;
+}
+
+/* Launches shape `shape` over n_sms SMs.  rp.lanes_per_warp is set to the slots a CTA seeds: the batch spread evenly
+ * over the CTAs, capped by the shape's slots. */
+extern "C" __attribute__((visibility("hidden"))) cudaError_t itsb_pool_launch(int shape, int n_sms, size_t table_bytes, RunParams rp,
+                                                                            cudaStream_t stream) {
+    const PoolShape& P = POOL_SHAPES[shape];
+    const unsigned int grid = (unsigned int)(n_sms * P.ctas_per_sm);
+    unsigned long long share = (rp.n_replicas + grid - 1) / grid;
+    rp.lanes_per_warp = (uint32_t)(share < 1 ? 1 : (share > (unsigned long long)P.slots ? (unsigned long long)P.slots : share));
+    P.kernel<<<grid, P.threads, table_bytes + P.shared, stream>>>(rp);
+    return cudaGetLastError();
+}

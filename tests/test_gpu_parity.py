@@ -206,14 +206,16 @@ def test_fused_loop_head_and_retired_wakeups_change_nothing():
         assert np.array_equal(other[2], results[0][2])
 
 
-@pytest.mark.parametrize("variant", ["vote"])
+@pytest.mark.parametrize("variant", ["vote", "pool", "pool:0", "pool:2", "pool:3"])
 def test_every_engine_kernel_gives_the_same_replicas(variant, monkeypatch):
     """The two designs (a replica per warp: k_run; a replica per lane: k_run_vote, the default from 50 000 replicas up)
     and the experimental variants advance a replica through the same events: every counter of every replica, and the
     clock, equal k_run's.  ITSB_KERNEL selects the kernel when the replicas are created."""
     n, horizon = 1500, 400.0
     engines = {}
-    kernel = variant
+    kernel = variant.split(":")[0]
+    if ":" in variant:
+        monkeypatch.setenv("ITSB_POOL_SHAPE", variant.split(":")[1])     # another instantiation of k_run_pool
     for which in ("warp", kernel):
         monkeypatch.setenv("ITSB_KERNEL", which)
         eng = make().run_replicas(n, seed=21, first_replica_id=1000)

@@ -61,6 +61,41 @@ def test_full_size_instance(backend, hostemu, summaries):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("which,name", [("warp", "k_run_in_place"), ("vote", "k_run_vote_hbm")])
+def test_both_large_model_kernels_give_the_reference_traces(which, name, summaries, monkeypatch):
+    """Config C4's two kernels -- a warp per replica (k_run_in_place) and a lane per replica (k_run_vote_hbm, what
+    itsb_run picks from 4 096 replicas up) -- against the reference classes' run: the small instance event for event,
+    the full-size one by counts and trace digest, traced inside a batch."""
+    import evtrace
+    from itsim_b200 import _lib as L
+    monkeypatch.setenv("ITSB_KERNEL", which)
+    ref = load_golden_trace("machine_large_lan_s1_r2_d20_s4_p16.npz")
+    eng, _ = run("gpu", None, 4, 16, 1, 2, 20.0, len(ref) + 16, n=3)
+    assert_trace_equal(eng.trace(0), ref)
+    eng.close()
+    s = summaries["large_lan_s0_r0_d8_s16_p64"]
+    eng, _ = run("gpu", None, 16, 64, 0, 0, 8.0, s["events"] + 16, n=3)
+    assert eng.kernel_name() == name
+    tm = eng.replica_telemetry(0)
+    for k in range(1, L.NUM_KINDS):
+        assert int(tm[L.TM_KIND0 + k]) == s["counts"][L.KIND_NAMES[k]]
+    assert evtrace.trace_digest(eng.trace(0)) == s["t_digest"]
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_large_batch_on_the_default_kernel_equals_hostemu(hostemu, monkeypatch):
+    """4 200 replicas: itsb_run's own choice is the lane-per-replica kernel; sampled replicas equal the host build."""
+    monkeypatch.delenv("ITSB_KERNEL", raising=False)
+    gpu, _ = run("gpu", None, 16, 64, 3, 0, 2.0, 0, n=4200)
+    assert gpu.kernel_name() == "k_run_vote_hbm"
+    for r in (0, 2100, 4199):
+        emu, _ = run("hostemu", hostemu, 16, 64, 3, r, 2.0, 0, n=1)
+        assert np.array_equal(gpu.replica_telemetry(r), emu.replica_telemetry(0)), r
+    gpu.close()
+
+
+@pytest.mark.gpu
 def test_gpu_batch_equals_hostemu(hostemu):
     gpu, ev_gpu = run("gpu", hostemu, 16, 64, 7, 50, 6.0, 0, n=24)
     emu, ev_emu = run("hostemu", hostemu, 16, 64, 7, 50, 6.0, 0, n=24)

@@ -22,6 +22,17 @@ sweep)
     ITSB_KERNEL=$k timeout 600 python bench.py --replicas $n --steps 5 --warmup 2 --no-cpu-baseline --no-verify > gpurun_out/sweep_${k}_${n}.json 2> gpurun_out/sweep_${k}_${n}.err
     python -c "import json;d=json.load(open('gpurun_out/sweep_${k}_${n}.json'));print('$k',$n,'%.3e'%d['value'],d['roofline']['kernel'])"
   done; done;;
+pool)
+  # k_run_pool, every shape, default bench (short)
+  for sh in 0 1 2 3 4 5; do
+    ITSB_KERNEL=pool ITSB_POOL_SHAPE=$sh timeout 600 python bench.py --steps 5 --warmup 2 --no-cpu-baseline --no-verify > gpurun_out/pool_${sh}.json 2> gpurun_out/pool_${sh}.err
+    python -c "import json;d=json.load(open('gpurun_out/pool_${sh}.json'));print('pool shape $sh','%.3e'%d['value'],d['roofline']['kernel'])"
+  done;;
+lan)
+  for k in warp vote; do
+    ITSB_KERNEL=$k timeout 900 python bench.py --workload large_lan --replicas 10000 --slice 2 --spinup 6 --steps 5 --warmup 2 --no-cpu-baseline > gpurun_out/lan_${k}.json 2> gpurun_out/lan_${k}.err
+    python -c "import json;d=json.load(open('gpurun_out/lan_${k}.json'));print('large_lan $k','%.3e'%d['value'],d['roofline']['kernel'])"
+  done;;
 experiments)
   # the regrouping variants of round 1 on this round's engine core (the -DITSB_EXPERIMENTS build)
   for k in pool sorted lanes; do
