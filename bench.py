@@ -39,19 +39,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "simulated events/sec (batched network_simple replicas)"
-# ncu --set full captures committed under profiles/ (6000 replicas x 60 simulated s, one launch):
-# (dram__bytes_read.sum + dram__bytes_write.sum) / replicas, per engine kernel
-# k_run stages a replica's state once per launch: its traffic goes per launch.  k_run_vote advances the state in place:
-# its traffic goes with the simulated time (100000 replicas x 60 simulated s: 97.36 GB read + 16.78 GB written).
+# ncu --set full captures committed under profiles/ (r2_*_ncu_full.txt): dram__bytes_read.sum + dram__bytes_write.sum
+# of one launch.  k_run stages a replica's state once per launch: its traffic goes per launch (6000 replicas x 60 s).  The
+# lane-per-replica kernels advance the state in place: their traffic goes with the simulated time (100000 replicas x 60
+# simulated s per launch: k_run_pool 77.93 GB read + 25.70 GB written, k_run_vote 61.00 + 22.15 GB).
 NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH = {"k_run": (328.9e6 + 160.1e6) / 6000.0}
-NCU_TRAFFIC_BYTES_PER_REPLICA_SECOND = {"k_run_vote": (97.36e9 + 16.78e9) / 100000.0 / 60.0}
+NCU_TRAFFIC_BYTES_PER_REPLICA_SECOND = {"k_run_pool": (77.93e9 + 25.70e9) / 100000.0 / 60.0,
+                                        "k_run_vote": (61.00e9 + 22.15e9) / 100000.0 / 60.0}
 NCU_TRAFFIC_NOTE = ("dram__bytes_read+write per launch, scaled from this kernel's ncu --set full capture under profiles/ "
-                    "(k_run: 6000 replicas x 60 s, per replica and launch; k_run_vote: 100000 replicas x 60 s, per "
-                    "replica and simulated second); dram_gbs = traffic / launch time")
+                    "(k_run: 6000 replicas x 60 s, per replica and launch; k_run_pool / k_run_vote: 100000 replicas x 60 s, "
+                    "per replica and simulated second); dram_gbs = traffic / launch time")
 ROOFLINE_NOTE = ("algorithmic bytes = per-replica state read and written once per run (S_in+S_out, SURVEY 8-d) plus the "
-                 "records a step logs; the engine kernels do not move bytes at the HBM rate: k_run_vote waits on dependent "
-                 "loads of per-replica state (memory latency) and on instruction fetch, k_run on instruction supply; "
-                 "profiles/README.md")
+                 "records a step logs; the engine kernels do not move bytes at the HBM rate: every one of them runs at the "
+                 "rate its SMs' instruction-cache misses are served by the GPC-level cache (gcc requests at 91-93% of peak "
+                 "in every capture), k_run_pool with 71% of its stall samples waiting on dependent loads of per-replica "
+                 "state on top; profiles/README.md")
 UNIT = "events/s"
 RESULT_OUT = sys.stdout
 

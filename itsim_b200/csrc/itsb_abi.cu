@@ -252,7 +252,7 @@ struct itsb_engine {
     int kernel_ctas = 3;                          /* CTAs of 256 threads per SM for the lane-per-replica kernels */
     bool forced_in_place = false;
     bool lane_smem_ok = false;                    /* the lane kernels' dynamic shared memory (model tables) was granted */
-    int pool_shape = 1;                           /* which instantiation of k_run_pool (itsb_pool.cu POOL_SHAPES) */
+    int pool_shape = 2;                           /* which instantiation of k_run_pool (itsb_pool.cu POOL_SHAPES) */
     bool pool_ok = false;
     std::string kernel_label;
     float last_ms = 0.f;
@@ -287,11 +287,18 @@ static void choose_kernel(itsb_engine* e) {
         e->kernel = e->n_replicas >= 4096 ? K_VOTE_HBM : warp_kernel;
     }
     else {
-        /* a lane per replica needs replicas to fill its threads (148 SMs x 768): measured on the default model, the two
-           designs cross at 50 000 replicas (12 500: 0.73 vs 2.15, 25 000: 1.26 vs 2.21, 50 000: 2.26 vs 2.24,
-           100 000: 3.75 vs 2.27, 200 000: 4.08 vs 2.26 x 10^9 events/s) */
-        const bool enough = e->n_replicas >= 50000;
-        e->kernel = (e->rp.layout.conn_cap == 0 && enough) ? K_VOTE : warp_kernel;
+        /* A lane per replica needs replicas to fill the GPU's threads; a warp per replica (k_run, state in shared memory)
+           does not.  Measured on the default model, round 2 (x 10^9 events/s; profiles/README.md):
+               replicas     k_run   k_run_vote   k_run_pool
+                 12 500      1.48      1.51         2.03
+                 25 000      1.51      2.12         3.25
+                 50 000      1.53      3.10         4.97
+                100 000      1.54      4.77         6.09
+                200 000        -         -          6.18
+           so the pooled lane kernel from 8 192 replicas up, the warp kernel below (and for models that keep connection
+           records: their per-socket correlation is lane-parallel work in the warp-per-replica kernels). */
+        const bool enough = e->n_replicas >= 8192;
+        e->kernel = (e->rp.layout.conn_cap == 0 && enough) ? (e->pool_ok ? K_POOL : K_VOTE) : warp_kernel;
     }
 }
 
@@ -434,7 +441,7 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
     cudaGetLastError();
     {
         const char* shape = getenv("ITSB_POOL_SHAPE");
-        e->pool_shape = shape && atoi(shape) >= 0 && atoi(shape) < itsb_pool_shapes() ? atoi(shape) : 1;
+        e->pool_shape = shape && atoi(shape) >= 0 && atoi(shape) < itsb_pool_shapes() ? atoi(shape) : 2;
         e->pool_ok = e->lane_smem_ok && itsb_pool_prepare(e->pool_shape, e->so.total);
     }
 #if defined(ITSB_EXPERIMENTS)

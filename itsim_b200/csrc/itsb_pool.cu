@@ -166,6 +166,9 @@ static const PoolShape POOL_SHAPES[] = {
     POOL_SHAPE(384, 2, 384, 512),
     POOL_SHAPE(512, 1, 1024, 1024),
     POOL_SHAPE(384, 1, 768, 1024),
+    POOL_SHAPE(640, 1, 768, 1024),
+    POOL_SHAPE(576, 1, 768, 1024),
+    POOL_SHAPE(448, 1, 768, 1024),
 };
 static const int N_POOL_SHAPES = (int)(sizeof(POOL_SHAPES) / sizeof(POOL_SHAPES[0]));
 

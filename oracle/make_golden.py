@@ -110,8 +110,16 @@ def main() -> None:
         return
     path = os.path.join(GOLDEN, "netsimple_summaries.json")
     summaries = json.load(open(path)) if os.path.exists(path) else {}
+    if "--merge" in sys.argv:
+        for name in sorted(os.listdir(GOLDEN)):
+            if name.startswith(".part_"):
+                summaries.update(json.load(open(os.path.join(GOLDEN, name))))
+                os.remove(os.path.join(GOLDEN, name))
+        json.dump(summaries, open(path, "w"), indent=1, sort_keys=True)
+        return
     # 1. full traces, short horizon
-    for seed, replica, horizon in ((0, 0, 1800.0), (7, 3, 900.0), (0, 0, 600.0), (0, 49999, 600.0)):
+    only_keys = [a for a in sys.argv[1:] if a.count(":") == 2]
+    for seed, replica, horizon in (() if only_keys else ((0, 0, 1800.0), (7, 3, 900.0), (0, 0, 600.0), (0, 49999, 600.0))):
         model = netsimple.run_replica(seed, replica, horizon)
         s, arr = summary_of(model, horizon)
         np.savez_compressed(os.path.join(GOLDEN, f"netsimple_trace_s{seed}_r{replica}_{int(horizon)}s.npz"), trace=arr)
@@ -120,18 +128,22 @@ def main() -> None:
         print("trace", seed, replica, horizon, s["events"], flush=True)
     # 2. summaries, 1 h horizon, several streams
     jobs = [(0, r, 3600.0) for r in (0, 1, 2, 3, 63, 49999, 99999)] + [(1, 0, 3600.0), (123456789012, 5, 3600.0)]
-    if "--full" in sys.argv:
-        jobs.append((0, 0, 43200.0))
+    if "--full" in sys.argv:      # config C1 / C2's own horizon: the replicas a whole-job run of C2 is sampled at
+        jobs += [(0, r, 43200.0) for r in (0, 1, 2, 3, 63, 99999)]
+    only = [a for a in sys.argv[1:] if a.count(":") == 2]     # e.g. 0:63:43200: just these keys (parallel generation)
     for seed, replica, horizon in jobs:
         key = f"{seed}:{replica}:{int(horizon)}"
-        if key in summaries:
+        if key in summaries or (only and key not in only):
             continue
-        model = netsimple.run_replica(seed, replica, horizon)
+        model = netsimple.run_replica(seed, replica, horizon, trace_limit=0 if horizon > 10000 else None)
         s, _ = summary_of(model, horizon)
-        summaries[key] = s
         model.close()
         print("summary", key, s["events"], flush=True)
-        json.dump(summaries, open(path, "w"), indent=1, sort_keys=True)
+        if only:        # one process per key: written to its own file, merged by --merge
+            json.dump({key: s}, open(os.path.join(GOLDEN, f".part_{key.replace(':', '_')}.json"), "w"))
+        else:
+            summaries[key] = s
+            json.dump(summaries, open(path, "w"), indent=1, sort_keys=True)
     json.dump(summaries, open(path, "w"), indent=1, sort_keys=True)
 
 

@@ -9,10 +9,13 @@ from conftest import assert_trace_equal, load_golden_trace, telemetry_matches_su
 
 pytestmark = pytest.mark.gpu
 
-# Both engine designs against the same golden vectors: "warp" = a replica per warp, state staged in shared memory
-# (k_run); "vote" = a replica per lane, state in place in HBM (k_run_vote, what itsb_run picks from 50 000 replicas
-# up, i.e. the kernel bench.py times).  ITSB_KERNEL is read when the replicas are created.
-KERNELS = [pytest.param(("warp", "k_run"), id="k_run"), pytest.param(("vote", "k_run_vote"), id="k_run_vote")]
+# Every engine kernel against the same golden vectors: "warp" = a replica per warp, state staged in shared memory
+# (k_run); "pool" = a replica per lane, state in place in HBM, replicas regrouped by the kind of their next event through
+# rings in shared memory (k_run_pool: what itsb_run picks from 8 192 replicas up, i.e. the kernel bench.py times);
+# "vote" = the same with the regrouping confined to a warp (k_run_vote).  ITSB_KERNEL is read when the replicas are
+# created.
+KERNELS = [pytest.param(("warp", "k_run"), id="k_run"), pytest.param(("pool", "k_run_pool"), id="k_run_pool"),
+           pytest.param(("vote", "k_run_vote"), id="k_run_vote")]
 
 
 @pytest.fixture(params=KERNELS)
@@ -95,14 +98,14 @@ def test_full_horizon_c1(golden_summaries, kernel):
 
 def test_bench_sized_batch_on_the_default_kernel_matches_the_oracle(golden_summaries, monkeypatch):
     """What bench.py times, proven against the oracle: 50 000 replicas of seed 0 in one batch, NO kernel override, so
-    itsb_run's own choice is k_run_vote.  (1) the bench's regime (no trace: wake-ups a declared filter rejects are
+    itsb_run's own choice is k_run_pool.  (1) the bench's regime (no trace: wake-ups a declared filter rejects are
     retired in the delivery pass): after 3 600 s every replica that has a golden summary -- ids 0, 1, 2, 3, 63 and
     the last one, 49 999 -- equals it counter for counter; (2) the same batch traced: replicas 0 and 49 999, event for
     event and timestamp for timestamp, against the oracle's golden traces."""
     monkeypatch.delenv("ITSB_KERNEL", raising=False)
     n = 50000
     eng = make(arena_nodes=12288).run_replicas(n, seed=0)
-    assert eng.kernel_name() == "k_run_vote"
+    assert eng.kernel_name() == "k_run_pool"
     events = eng.run(3600.0)
     for r in (0, 1, 2, 3, 63, n - 1):
         telemetry_matches_summary(eng.replica_telemetry(r), golden_summaries[f"0:{r}:3600"])
@@ -112,7 +115,7 @@ def test_bench_sized_batch_on_the_default_kernel_matches_the_oracle(golden_summa
     eng.close()
     first, last = load_golden_trace("netsimple_trace_s0_r0_600s.npz"), load_golden_trace("netsimple_trace_s0_r49999_600s.npz")
     eng = make(trace_records=max(len(first), len(last)) + 16, arena_nodes=12288).run_replicas(n, seed=0)
-    assert eng.kernel_name() == "k_run_vote"
+    assert eng.kernel_name() == "k_run_pool"
     eng.run(600.0)
     assert_trace_equal(eng.trace(0), first)
     assert_trace_equal(eng.trace(n - 1), last)
@@ -238,5 +241,5 @@ def test_the_default_kernel_depends_on_the_batch(monkeypatch):
     assert small.kernel_name() == "k_run"
     small.close()
     big = make(arena_nodes=2048).run_replicas(50000, seed=0)
-    assert big.kernel_name() == "k_run_vote"
+    assert big.kernel_name() == "k_run_pool"
     big.close()

@@ -20,7 +20,8 @@ def engine_log(backend, hostemu, seed, replica, horizon, cap=20000):
     return eng
 
 
-KERNEL_BACKENDS = BACKENDS + [pytest.param("gpu:vote", id="gpu-k_run_vote", marks=pytest.mark.gpu)]
+KERNEL_BACKENDS = BACKENDS + [pytest.param("gpu:vote", id="gpu-k_run_vote", marks=pytest.mark.gpu),
+                              pytest.param("gpu:pool", id="gpu-k_run_pool", marks=pytest.mark.gpu)]
 
 
 @pytest.mark.parametrize("backend", KERNEL_BACKENDS)
@@ -28,7 +29,7 @@ def test_log_matches_the_oracle(backend, hostemu, monkeypatch):
     import netsimple as oracle_netsimple
     seed, replica, horizon = 4, 2, 1500.0
     if backend.startswith("gpu"):
-        monkeypatch.setenv("ITSB_KERNEL", "vote" if backend.endswith("vote") else "warp")
+        monkeypatch.setenv("ITSB_KERNEL", backend.split(":")[1] if ":" in backend else "warp")
         backend = "gpu"
     eng = engine_log(backend, hostemu, seed, replica, horizon)
     got = eng.net_events(0)

@@ -24,9 +24,20 @@ sweep)
   done; done;;
 pool)
   # k_run_pool, every shape, default bench (short)
-  for sh in 0 1 2 3 4 5; do
+  for sh in ${POOL_SHAPES:-0 1 2 3 4 5}; do
     ITSB_KERNEL=pool ITSB_POOL_SHAPE=$sh timeout 600 python bench.py --steps 5 --warmup 2 --no-cpu-baseline --no-verify > gpurun_out/pool_${sh}.json 2> gpurun_out/pool_${sh}.err
     python -c "import json;d=json.load(open('gpurun_out/pool_${sh}.json'));print('pool shape $sh','%.3e'%d['value'],d['roofline']['kernel'])"
+  done;;
+ncupool)
+  ITSB_KERNEL=pool timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_run -s 5 -c 1 -f -o gpurun_out/k_run_pool \
+     python bench.py --replicas 100000 --steps 2 --warmup 3 --spinup 600 --slice 60 --no-cpu-baseline --no-verify > gpurun_out/ncu_pool.log 2>&1; echo "ncu pool rc=$?";;
+nculan)
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_run -s 2 -c 1 -f -o gpurun_out/k_run_vote_hbm \
+     python bench.py --workload large_lan --replicas 10000 --slice 2 --spinup 6 --steps 2 --warmup 2 --no-cpu-baseline --no-verify > gpurun_out/ncu_lan.log 2>&1; echo "ncu lan rc=$?";;
+poolsweep)
+  for n in 12500 25000 50000 200000; do
+    ITSB_KERNEL=pool timeout 600 python bench.py --replicas $n --steps 5 --warmup 2 --no-cpu-baseline --no-verify > gpurun_out/sweep_pool_${n}.json 2> gpurun_out/sweep_pool_${n}.err
+    python -c "import json;d=json.load(open('gpurun_out/sweep_pool_${n}.json'));print('pool',$n,'%.3e'%d['value'],d['roofline']['kernel'])"
   done;;
 lan)
   for k in warp vote; do
