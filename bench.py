@@ -188,12 +188,13 @@ def run_reference_arm(args) -> None:
     cores = os.cpu_count() or 1
     per_step = []
     info = None
+    horizon = args.cpu_horizon / 2          # per step: sized so that --steps 20 --warmup 5 ends within a few minutes
     for _ in range(args.warmup):
-        cpu_baseline(args.cpu_horizon / 4, 1, cores)
+        cpu_baseline(horizon / 4, 1, cores)
     t_events = 0
     t_wall = 0.0
     for _ in range(args.steps):
-        _, info = cpu_baseline(args.cpu_horizon, 1, cores)
+        _, info = cpu_baseline(horizon, 1, cores)
         per_step.append(info["wall_s"])
         t_events += info["events"]
         t_wall += info["wall_s"]
@@ -204,7 +205,7 @@ def run_reference_arm(args) -> None:
         "warmup": args.warmup, "ms_per_step": 1e3 * t_wall / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "network_simple (50 endpoints, /24), whole replicas on host cores, one process per core",
-                   "sample_horizon_s": args.cpu_horizon, "note": "reference is pure Python on greensim; greensim is "
+                   "sample_horizon_s": horizon, "note": "reference is pure Python on greensim; greensim is "
                    "not installable offline, so the reference model runs on the oracle's greensim-compatible shim"},
         "cpu_baseline": info,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -241,7 +242,8 @@ class _Job:
             env.join(self.engine)
         self.world = world
         self.logging = bool(args.connections or args.net_events)
-        self.records = {"net": 0, "conn": 0, "net_dropped": 0, "conn_dropped": 0, "d2h_bytes": 0, "drains": 0}
+        self.records = {"net": 0, "conn": 0, "net_dropped": 0, "conn_dropped": 0, "d2h_bytes": 0, "drains": 0,
+                        "pack_ms": 0.0, "pack_ms_last": 0.0}
 
     # -- the engines of this process --------------------------------------------------------------------------------
     def _engines(self):
@@ -269,8 +271,11 @@ class _Job:
     def drain_end(self):
         """Waits for the oldest pending drain of every engine; what came home is counted (and touched: one pass over
         the timestamps, so that the pages really are in host memory)."""
+        self.records["pack_ms_last"] = 0.0
         for e in self._engines():
             d = e.drain_end()
+            self.records["pack_ms"] += d["pack_ms"]
+            self.records["pack_ms_last"] = max(self.records["pack_ms_last"], d["pack_ms"])
             self.records["net"] += len(d["net"]); self.records["conn"] += len(d["conn"])
             self.records["net_dropped"] += d["net_dropped"]; self.records["conn_dropped"] += d["conn_dropped"]
             self.records["d2h_bytes"] += d["d2h_bytes"]; self.records["drains"] += 1
@@ -354,7 +359,7 @@ def main() -> None:
     ap.add_argument("--slice", type=float, default=120.0, help="simulated seconds per step")
     ap.add_argument("--spinup", type=float, default=1800.0, help="untimed simulated seconds before warm-up")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--cpu-horizon", type=float, default=1800.0, help="simulated seconds per CPU-baseline replica")
+    ap.add_argument("--cpu-horizon", type=float, default=3600.0, help="simulated seconds per CPU-baseline replica")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the untimed full-size self-check after the timed steps")
     ap.add_argument("--arena-nodes", type=int, default=12288)
@@ -429,8 +434,8 @@ def main() -> None:
     # ---- timed region 1: K steps, device time ------------------------------------------------------------------------
     # Without record logs the K launches are queued back to back and timed by one pair of CUDA events on the engine's
     # stream.  With them, every step is followed by its drain (the logs are windows sized for a step), so the steps are
-    # timed one by one -- the engine kernel by its CUDA events, the drain's count / scan / gather kernels and copies by the
-    # host clock around them -- and the device time of the region is their sum.
+    # timed one by one -- the engine kernel and the drain's count / scan / gather kernels each by their own CUDA events
+    # -- and the device time of the region is their sum.  The copy home of the records belongs to e2e (region 2).
     sampler = ClockSampler(env.local_rank)
     sampler.start()
     launches0 = job.launch_count()
@@ -445,10 +450,8 @@ def main() -> None:
         for _ in range(args.steps):
             events_dev += job.run(args.slice)
             ms_dev += job.last_run_ms()
-            t0 = time.perf_counter()
             job.drain_begin()
-            job.drain_end()
-            ms_dev += 1e3 * (time.perf_counter() - t0)
+            ms_dev += job.drain_end()["pack_ms_last"]
     job.barrier()
     launches_dev = job.launch_count() - launches0
     ms_dev_max = job.all_max(ms_dev)

@@ -322,6 +322,7 @@ typedef struct itsb_drain {
     const uint64_t*        conn_first;
     uint64_t net_dropped, conn_dropped;   /* produced since the last drain beyond a replica's capacity: counted, lost */
     uint64_t d2h_bytes;                   /* bytes this drain copied device -> host                                   */
+    double   pack_ms;                     /* device time of the count / scan / gather kernels (CUDA events)          */
 } itsb_drain;
 int itsb_drain_begin(itsb_engine* e);
 int itsb_drain_end(itsb_engine* e, itsb_drain* out);

@@ -84,7 +84,8 @@ class Drain(C.Structure):
     """``itsb_drain`` (include/itsb.h): one emptying of every replica's record logs."""
     _fields_ = [("net", C.c_void_p), ("n_net", C.c_uint64), ("net_first", C.c_void_p),
                 ("conn", C.c_void_p), ("n_conn", C.c_uint64), ("conn_first", C.c_void_p),
-                ("net_dropped", C.c_uint64), ("conn_dropped", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("net_dropped", C.c_uint64), ("conn_dropped", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("pack_ms", C.c_double)]
 
 
 class EngineError(RuntimeError):

@@ -42,6 +42,8 @@ extern "C" int itsb_pool_shapes(void);
 extern "C" const char* itsb_pool_shape_name(int shape);
 extern "C" bool itsb_pool_prepare(int shape, size_t table_bytes);
 extern "C" cudaError_t itsb_pool_launch(int shape, int n_sms, size_t table_bytes, RunParams rp, cudaStream_t stream);
+extern "C" bool itsb_pool_prepare_hbm(int shape, size_t table_bytes);          /* itsb_pool_hbm.cu: tables left in HBM */
+extern "C" cudaError_t itsb_pool_launch_hbm(int shape, int n_sms, size_t table_bytes, RunParams rp, cudaStream_t stream);
 
 /* up to 12 warps per CTA (what shared memory allows the flagship model): 168 registers per thread, no spills */
 extern "C" __global__ void __launch_bounds__(384, 1) k_run(const RunParams p) {
@@ -203,9 +205,9 @@ extern "C" __global__ void __launch_bounds__(128) k_log_gather(
  * records (their per-socket correlation is lane-parallel work in the warp-per-replica kernels).  ITSB_KERNEL=
  * warp | vote overrides (lanes | sorted | pool | phased too in a -DITSB_EXPERIMENTS build), ITSB_KERNEL_CTAS=n sets
  * the CTAs per SM of the lane kernels. */
-enum { K_WARP = 0, K_WIDE, K_IN_PLACE, K_PHASED, K_VOTE, K_LANES, K_SORTED, K_POOL, K_VOTE_HBM };
+enum { K_WARP = 0, K_WIDE, K_IN_PLACE, K_PHASED, K_VOTE, K_LANES, K_SORTED, K_POOL, K_VOTE_HBM, K_POOL_HBM };
 static const char* const KERNEL_NAMES[] = {"k_run", "k_run_wide", "k_run_in_place", "k_run_phased", "k_run_vote",
-                                           "k_run_lanes", "k_run_sorted", "k_run_pool", "k_run_vote_hbm"};
+                                           "k_run_lanes", "k_run_sorted", "k_run_pool", "k_run_vote_hbm", "k_run_pool_hbm"};
 
 struct itsb_engine {
     int device = 0;
@@ -236,7 +238,7 @@ struct itsb_engine {
         unsigned long long* h_first = nullptr;                                    /* pinned: net_first | conn_first */
         size_t cap_net = 0, cap_conn = 0, cap_first = 0;
         uint64_t n_net = 0, n_conn = 0, dropped[2] = {0, 0}, bytes = 0;
-        cudaEvent_t packed = nullptr, home = nullptr;
+        cudaEvent_t packed = nullptr, home = nullptr, t0 = nullptr, t1 = nullptr;
         bool pending = false;
     } drain[2];
     unsigned long long* d_first = nullptr;        /* net_first[n + 1] | conn_first[n + 1] | dropped[2] */
@@ -253,7 +255,7 @@ struct itsb_engine {
     bool forced_in_place = false;
     bool lane_smem_ok = false;                    /* the lane kernels' dynamic shared memory (model tables) was granted */
     int pool_shape = 2;                           /* which instantiation of k_run_pool (itsb_pool.cu POOL_SHAPES) */
-    bool pool_ok = false;
+    bool pool_ok = false, pool_hbm_ok = false;
     std::string kernel_label;
     float last_ms = 0.f;
     long long first_failed = -1;
@@ -275,6 +277,7 @@ static void choose_kernel(itsb_engine* e) {
 #endif
     if (lane_ok && want == "vote") e->kernel = K_VOTE;
     else if (lane_hbm_ok && want == "vote") e->kernel = K_VOTE_HBM;
+    else if (lane_hbm_ok && e->pool_hbm_ok && want == "pool") e->kernel = K_POOL_HBM;
     else if (lane_ok && e->pool_ok && want == "pool") e->kernel = K_POOL;
 #if defined(ITSB_EXPERIMENTS)
     else if (lane_ok && want == "lanes") e->kernel = K_LANES;
@@ -295,10 +298,10 @@ static void choose_kernel(itsb_engine* e) {
                  50 000      1.53      3.10         4.97
                 100 000      1.54      4.77         6.09
                 200 000        -         -          6.18
-           so the pooled lane kernel from 8 192 replicas up, the warp kernel below (and for models that keep connection
-           records: their per-socket correlation is lane-parallel work in the warp-per-replica kernels). */
+           so the pooled lane kernel from 8 192 replicas up, the warp kernel below.  Models that keep connection records
+           (config C5, 20 000 replicas, drained every step): k_run_pool 4.3, k_run 3.4 x 10^8. */
         const bool enough = e->n_replicas >= 8192;
-        e->kernel = (e->rp.layout.conn_cap == 0 && enough) ? (e->pool_ok ? K_POOL : K_VOTE) : warp_kernel;
+        e->kernel = enough ? (e->pool_ok ? K_POOL : K_VOTE) : warp_kernel;
     }
 }
 
@@ -328,6 +331,8 @@ static void drain_free(itsb_engine* e) {
         cudaFree(D.d_net); cudaFree(D.d_conn); cudaFreeHost(D.h_net); cudaFreeHost(D.h_conn); cudaFreeHost(D.h_first);
         if (D.packed) cudaEventDestroy(D.packed);
         if (D.home) cudaEventDestroy(D.home);
+        if (D.t0) cudaEventDestroy(D.t0);
+        if (D.t1) cudaEventDestroy(D.t1);
         D = itsb_engine::DrainSet();
     }
     cudaFree(e->d_first); e->d_first = nullptr; e->cap_first = 0;
@@ -443,6 +448,7 @@ int itsb_load_model(itsb_engine* e, const itsb_model_desc* d, const void* const*
         const char* shape = getenv("ITSB_POOL_SHAPE");
         e->pool_shape = shape && atoi(shape) >= 0 && atoi(shape) < itsb_pool_shapes() ? atoi(shape) : 2;
         e->pool_ok = e->lane_smem_ok && itsb_pool_prepare(e->pool_shape, e->so.total);
+        e->pool_hbm_ok = e->rp.tables_in_hbm && itsb_pool_prepare_hbm(0, e->so.total);
     }
 #if defined(ITSB_EXPERIMENTS)
     CU(e, cudaFuncSetAttribute(k_run_phased, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
@@ -530,6 +536,7 @@ int itsb_run_async(itsb_engine* e, double duration) {
     case K_VOTE:     k_run_vote<<<lane_grid, 256, e->so.total, e->stream>>>(e->rp); break;
     case K_VOTE_HBM: k_run_vote_hbm<<<lane_grid, 256, e->so.total, e->stream>>>(e->rp); break;
     case K_POOL:     CU(e, itsb_pool_launch(e->pool_shape, (int)e->grid, e->so.total, e->rp, e->stream)); break;
+    case K_POOL_HBM: CU(e, itsb_pool_launch_hbm(0, (int)e->grid, e->so.total, e->rp, e->stream)); break;
 #if defined(ITSB_EXPERIMENTS)
     case K_LANES:    k_run_lanes<<<lane_grid, 256, e->so.total, e->stream>>>(e->rp); break;
     case K_SORTED:   k_run_sorted<<<lane_grid, 256, e->so.total + 256 * (sizeof(PendingEvent) + sizeof(RunCtx) + 2 + 1 + 4) + 64,
@@ -680,7 +687,12 @@ int itsb_drain_begin(itsb_engine* e) {
     CU(e, cudaSetDevice(e->device));
     const uint64_t n = e->n_replicas;
     if (!e->copy_stream) CU(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    if (!D.packed) { CU(e, cudaEventCreateWithFlags(&D.packed, cudaEventDisableTiming)); CU(e, cudaEventCreateWithFlags(&D.home, cudaEventDisableTiming)); }
+    if (!D.packed) {
+        CU(e, cudaEventCreateWithFlags(&D.packed, cudaEventDisableTiming));
+        CU(e, cudaEventCreateWithFlags(&D.home, cudaEventDisableTiming));
+        CU(e, cudaEventCreate(&D.t0));
+        CU(e, cudaEventCreate(&D.t1));
+    }
     if (e->cap_first < n + 1) {
         cudaFree(e->d_first); e->d_first = nullptr; e->cap_first = 0;
         CU(e, cudaMalloc(&e->d_first, (2 * (n + 1) + 2) * sizeof(unsigned long long)));
@@ -694,6 +706,7 @@ int itsb_drain_begin(itsb_engine* e) {
     unsigned long long* net_first = e->d_first;
     unsigned long long* conn_first = e->d_first + (n + 1);
     unsigned long long* dropped = e->d_first + 2 * (n + 1);
+    CU(e, cudaEventRecord(D.t0, e->stream));
     CU(e, cudaMemsetAsync(dropped, 0, 2 * sizeof(unsigned long long), e->stream));
     k_log_count<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(e->d_hot, L.hot_bytes, n, L.log_cap, L.conn_cap,
                                                                      net_first, conn_first, dropped);
@@ -714,6 +727,7 @@ int itsb_drain_begin(itsb_engine* e) {
                                                       (const unsigned char*)e->d_connlog, L.conn_cap, net_first, conn_first,
                                                       D.d_net, D.d_conn);
     CU(e, cudaGetLastError());
+    CU(e, cudaEventRecord(D.t1, e->stream));
     e->launches += 1;
     /* the offsets travel with the records; copied to their own pinned buffer on the engine stream (the next drain
        overwrites the device array), the records on the second stream once the gather is done */
@@ -746,6 +760,9 @@ int itsb_drain_end(itsb_engine* e, itsb_drain* out) {
     out->conn = D->h_conn; out->n_conn = D->n_conn; out->conn_first = (const uint64_t*)(D->h_first + (n + 1));
     out->net_dropped = D->dropped[0]; out->conn_dropped = D->dropped[1];
     out->d2h_bytes = D->bytes;
+    float ms = 0.f;
+    CU(e, cudaEventElapsedTime(&ms, D->t0, D->t1));
+    out->pack_ms = ms;
     D->pending = false;
     return ITSB_OK;
 }

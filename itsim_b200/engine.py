@@ -144,7 +144,8 @@ class Engine:
 
         return {"net": view(d.net, d.n_net, L.NET_EVENT_DTYPE), "net_first": view(d.net_first, n + 1, np.uint64),
                 "conn": view(d.conn, d.n_conn, L.CONNECTION_DTYPE), "conn_first": view(d.conn_first, n + 1, np.uint64),
-                "net_dropped": int(d.net_dropped), "conn_dropped": int(d.conn_dropped), "d2h_bytes": int(d.d2h_bytes)}
+                "net_dropped": int(d.net_dropped), "conn_dropped": int(d.conn_dropped), "d2h_bytes": int(d.d2h_bytes),
+                "pack_ms": float(d.pack_ms)}
 
     def drain(self, copy: bool = False) -> Dict[str, Any]:
         self.drain_begin()

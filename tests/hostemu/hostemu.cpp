@@ -242,6 +242,7 @@ int itsb_drain_end(itsb_engine* e, itsb_drain* out) {
     out->conn = D->conn.data(); out->n_conn = D->conn.size(); out->conn_first = D->first.data() + (n + 1);
     out->net_dropped = D->dropped[0]; out->conn_dropped = D->dropped[1];
     out->d2h_bytes = out->n_net * sizeof(itsb_net_event) + out->n_conn * sizeof(itsb_connection) + 2 * (n + 1) * 8 + 32;
+    out->pack_ms = 0.0;
     D->pending = false;
     return ITSB_OK;
 }

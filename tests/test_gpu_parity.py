@@ -209,7 +209,7 @@ def test_fused_loop_head_and_retired_wakeups_change_nothing():
         assert np.array_equal(other[2], results[0][2])
 
 
-@pytest.mark.parametrize("variant", ["vote", "pool", "pool:0", "pool:2", "pool:3"])
+@pytest.mark.parametrize("variant", ["vote", "pool", "pool:0", "pool:1", "pool:3"])
 def test_every_engine_kernel_gives_the_same_replicas(variant, monkeypatch):
     """The two designs (a replica per warp: k_run; a replica per lane: k_run_vote, the default from 50 000 replicas up)
     and the experimental variants advance a replica through the same events: every counter of every replica, and the

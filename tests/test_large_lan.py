@@ -61,7 +61,7 @@ def test_full_size_instance(backend, hostemu, summaries):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which,name", [("warp", "k_run_in_place"), ("vote", "k_run_vote_hbm")])
+@pytest.mark.parametrize("which,name", [("warp", "k_run_in_place"), ("vote", "k_run_vote_hbm"), ("pool", "k_run_pool_hbm")])
 def test_both_large_model_kernels_give_the_reference_traces(which, name, summaries, monkeypatch):
     """Config C4's two kernels -- a warp per replica (k_run_in_place) and a lane per replica (k_run_vote_hbm, what
     itsb_run picks from 4 096 replicas up) -- against the reference classes' run: the small instance event for event,

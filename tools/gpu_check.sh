@@ -31,7 +31,15 @@ pool)
 ncupool)
   ITSB_KERNEL=pool timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_run -s 5 -c 1 -f -o gpurun_out/k_run_pool \
      python bench.py --replicas 100000 --steps 2 --warmup 3 --spinup 600 --slice 60 --no-cpu-baseline --no-verify > gpurun_out/ncu_pool.log 2>&1; echo "ncu pool rc=$?";;
-nculan)
+ncuwholejob)
+  timeout 1200 python tools/whole_job_c2.py > gpurun_out/whole_job_c2.json 2> gpurun_out/whole_job_c2.err; echo "whole job rc=$?"
+  python -c "import json;d=json.load(open('gpurun_out/whole_job_c2.json'));print('C2 whole job: %.3e events in %.1f s device, %.1f s wall, failed=%d, oracle-equal replicas %s'%(d['events'],d['device_s'],d['wall_s'],d['first_failed_replica'],sorted(d['replicas_equal_to_the_oracle_at_the_horizon'])))";;
+c5)
+  for k in warp pool; do
+    ITSB_KERNEL=$k timeout 900 python bench.py --connections 8192 --net-events 1024 --replicas 20000 --steps 6 --warmup 2 --no-cpu-baseline > gpurun_out/c5_${k}.json 2> gpurun_out/c5_${k}.err
+    python -c "import json;d=json.load(open('gpurun_out/c5_${k}.json'));print('C5 $k','%.3e'%d['value'],'e2e %.3e'%d['e2e']['value'],d['roofline']['kernel'],'d2h/step %.3e'%d['e2e']['d2h_bytes_per_step'],d['config']['records'],'checks',d['checks']['all'])"
+  done;;
+lan)
   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_run -s 2 -c 1 -f -o gpurun_out/k_run_vote_hbm \
      python bench.py --workload large_lan --replicas 10000 --slice 2 --spinup 6 --steps 2 --warmup 2 --no-cpu-baseline --no-verify > gpurun_out/ncu_lan.log 2>&1; echo "ncu lan rc=$?";;
 poolsweep)
@@ -39,8 +47,16 @@ poolsweep)
     ITSB_KERNEL=pool timeout 600 python bench.py --replicas $n --steps 5 --warmup 2 --no-cpu-baseline --no-verify > gpurun_out/sweep_pool_${n}.json 2> gpurun_out/sweep_pool_${n}.err
     python -c "import json;d=json.load(open('gpurun_out/sweep_pool_${n}.json'));print('pool',$n,'%.3e'%d['value'],d['roofline']['kernel'])"
   done;;
+wholejob)
+  timeout 1200 python tools/whole_job_c2.py > gpurun_out/whole_job_c2.json 2> gpurun_out/whole_job_c2.err; echo "whole job rc=$?"
+  python -c "import json;d=json.load(open('gpurun_out/whole_job_c2.json'));print('C2 whole job: %.3e events in %.1f s device, %.1f s wall, failed=%d, oracle-equal replicas %s'%(d['events'],d['device_s'],d['wall_s'],d['first_failed_replica'],sorted(d['replicas_equal_to_the_oracle_at_the_horizon'])))";;
+c5)
+  for k in warp pool; do
+    ITSB_KERNEL=$k timeout 900 python bench.py --connections 8192 --net-events 1024 --replicas 20000 --steps 6 --warmup 2 --no-cpu-baseline > gpurun_out/c5_${k}.json 2> gpurun_out/c5_${k}.err
+    python -c "import json;d=json.load(open('gpurun_out/c5_${k}.json'));print('C5 $k','%.3e'%d['value'],'e2e %.3e'%d['e2e']['value'],d['roofline']['kernel'],'d2h/step %.3e'%d['e2e']['d2h_bytes_per_step'],d['config']['records'],'checks',d['checks']['all'])"
+  done;;
 lan)
-  for k in warp vote; do
+  for k in ${LAN_KERNELS:-warp vote pool}; do
     ITSB_KERNEL=$k timeout 900 python bench.py --workload large_lan --replicas 10000 --slice 2 --spinup 6 --steps 5 --warmup 2 --no-cpu-baseline > gpurun_out/lan_${k}.json 2> gpurun_out/lan_${k}.err
     python -c "import json;d=json.load(open('gpurun_out/lan_${k}.json'));print('large_lan $k','%.3e'%d['value'],d['roofline']['kernel'])"
   done;;

@@ -53,7 +53,9 @@ def main() -> None:
     for r in (0, 1, 2, 3, 63, 99999):
         key = f"0:{r}:{int(args.horizon)}"
         if r < args.replicas and key in golden:
-            telemetry_matches_summary(eng.replica_telemetry(r), golden[key])     # raises on the first mismatch
+            mine = eng.replica_telemetry(r).copy()
+            mine[L.TM_KIND0 + L.EV_STOP] -= len(per_slice) - 1        # one STOP per run() call; the oracle made one call
+            telemetry_matches_summary(mine, golden[key])                 # raises on the first mismatch
             checked[str(r)] = golden[key]["events"]
     s = summarize(tm)
     k0 = L.TM_KIND0
