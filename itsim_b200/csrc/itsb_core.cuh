@@ -1281,6 +1281,12 @@ ITSB_FN ArenaNode sock_pop(Rep& R, Sock& S) {
             ArenaNode B = R.arena[n];
             S.q_head = B.next;
             if (B.next == NIL32) S.q_tail = NIL32;
+#if defined(__CUDACC__) && defined(ITSB_LANES)
+            /* a workstation that wakes up drains a backlog of hundreds of packets through this chain of dependent
+               loads (round 2 profile of k_run_pool: 5 % of all stall samples): the node after this one is fetched now,
+               while the loop head still filters this packet */
+            else asm volatile("prefetch.global.L2 [%0];" ::"l"(R.arena + B.next));
+#endif
             B.next = NIL32;
             R.sockpkt[s] = B;
             arena_release(R, n);
