@@ -6,7 +6,7 @@ MAX=${1:-2}; QUICK=${2:-}
 mkdir -p gpurun_out
 tr() { python -m torch.distributed.run --nnodes=1 --nproc-per-node "$1" --master-addr 127.0.0.1 --master-port $((29500 + $1)) bench.py --gpus "$@"; }
 show() { python -c "import json,sys;d=json.load(open('$1'));print('$1','%.3e'%d['value'],'e2e %.3e'%d['e2e']['value'],d['scaling'],d['n_gpus'],'GPUs',d['roofline']['kernel'],d['config'].get('processes'),'allreduce_ms',d['config']['telemetry_allreduce_ms'],'checks',(d['checks'] or {}).get('all'))" 2>&1 | tail -1; }
-for N in 2 4 8; do
+for N in ${SCALE_NS:-2 4 8}; do
   [ "$N" -gt "$MAX" ] && continue
   NCCL_DEBUG=WARN tr $N --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/scale_weak_${N}.json 2> gpurun_out/scale_weak_${N}.err; show gpurun_out/scale_weak_${N}.json
   tr $N --steps 8 --warmup 3 --no-cpu-baseline --scaling strong --total-replicas 100000 > gpurun_out/scale_strong_${N}.json 2> gpurun_out/scale_strong_${N}.err; show gpurun_out/scale_strong_${N}.json
