@@ -259,6 +259,11 @@ struct EvNode {             /* arena node used by the now-queue spill chain and 
     u32 pad[3];
 };
 
+struct SockV {              /* 8 bytes: packets queued "virtually" on a socket (see ND_ASLEEP) */
+    u32 count;
+    u32 bytes;
+};
+
 struct HeapEnt {            /* 16 bytes: one entry of the future-event heap, ordered by (t, seq) */
     u64 t;                  /* timestamp, as its bit pattern (t >= 0: bit order is numeric order) */
     u32 seq;                /* greensim's insertion counter: breaks ties */
@@ -280,6 +285,7 @@ struct Layout {             /* byte offsets inside one replica's hot block */
     u32 off_ndig;           /* delivery digests: one u32 per node (see node_digest_compute) */
     u32 off_nmask, off_pmask;   /* per node / per process: which hostname fields the remembered packets carry (64-bit Bloom) */
     u32 off_sockpkt;        /* per socket: the packet at the head of its queue, inline (override-path models) */
+    u32 off_sockv;          /* per socket: packets its sleeping owner's loop head will pop and reject (count, bytes) */
 };
 
 struct Model {              /* pointers to the static tables (shared-memory copies inside the kernel) */
@@ -348,6 +354,7 @@ struct Rep {                /* register-resident working view of one replica */
     u16* pcb_free;
     Sock* sock;
     ArenaNode* sockpkt;
+    SockV* sockv;
     u16* sock_free;
     NodeDyn* node;
     u32* ndig;
@@ -384,6 +391,7 @@ ITSB_FN void rebind(Rep& R, Hdr* H) {
     R.pcb_free = (u16*)(hot + H->L.off_pcb_free);
     R.sock = (Sock*)(hot + H->L.off_sock);
     R.sockpkt = (ArenaNode*)(hot + H->L.off_sockpkt);
+    R.sockv = (SockV*)(hot + H->L.off_sockv);
     R.sock_free = (u16*)(hot + H->L.off_sock_free);
     R.node = (NodeDyn*)(hot + H->L.off_node);
     R.ndig = (u32*)(hot + H->L.off_ndig);
@@ -935,7 +943,17 @@ ITSB_FN u32 ev_take(Rep& R, int src) {
  *               and the static tables alone.  ND_LISTED: that process remembers at least one packet; nmask[node] then
  *               holds a 64-bit Bloom filter (bit = hostname field & 63) of the packets it remembers, a copy of the
  *               process's pmask: a packet whose bit is clear is certainly not "listed"
- *   socket      with either flag: the index of the socket bound to `port` (ND_NOSOCK: not stated), so a packet that
+ *   ND_ASLEEP   the socket bound to `port` has no waiter and no queued packet, and its owner is parked on the node's
+ *               wake signal at the head of a RECV_FILTER loop (phase 0: `with ws.awake()`) using filter `filter`, with no
+ *               exception handler of its own; ND_LISTED / nmask as above.  Every packet that reaches the socket from now
+ *               on will be popped by that loop head in ONE activation when the workstation wakes; until a packet
+ *               arrives that the filter lets through, nothing can change what the filter sees, so a packet it rejects
+ *               now is certain to be popped, counted and rejected then.  Such a packet is queued *virtually*: counted
+ *               in sockv[socket] (count, bytes) and credited by the loop head when it resumes -- no arena node, no
+ *               chain of dependent loads to drain a backlog of hundreds of packets on wake-up (round-2 profile of
+ *               k_run_pool: 8 % of all stall samples).  The first packet the filter lets through is queued for real and
+ *               withdraws the statement
+ *   socket      with any flag: the index of the socket bound to `port` (ND_NOSOCK: not stated), so a packet that
  *               is accepted finds its socket without walking the node's list
  *
  * A digest is a set of STATEMENTS, each of which must be true whenever it is present; an absent statement (flags 0) only
@@ -943,13 +961,31 @@ ITSB_FN u32 ev_take(Rep& R, int src) {
  * closed, a process parking on or leaving a socket's wait list, a delivery waking a socket's waiters, the node
  * sleeping or waking (epoch), and -- for pmask -- the three list instructions.  tests/hostemu builds with
  * ITSB_CHECK_DIGEST verify every statement against the tables before every use and fail the replica otherwise. */
-enum { ND_RETIRE = 1u << 21, ND_LISTED = 1u << 22, ND_SINGLE = 1u << 23, ND_NOSOCK = 0xFFu, ND_MAX_FILTER = 31u };
+enum { ND_STABLE = 1u << 19, ND_ASLEEP = 1u << 20, ND_RETIRE = 1u << 21, ND_LISTED = 1u << 22, ND_SINGLE = 1u << 23,
+       ND_NOSOCK = 0xFFu, ND_MAX_FILTER = 7u };
 ITSB_FN u32 nd_port(u32 d) { return d & 0xFFFFu; }
-ITSB_FN u32 nd_filter(u32 d) { return (d >> 16) & 31u; }
+ITSB_FN u32 nd_filter(u32 d) { return (d >> 16) & 7u; }
 ITSB_FN u32 nd_sock(u32 d) { return d >> 24; }
 ITSB_FN u32 nd_sock_field(u32 s) { return (s < ND_NOSOCK ? s : (u32)ND_NOSOCK) << 24; }
-/* what is left of a digest when nothing can be retired on its socket any more */
+/* what is left of a digest when nothing can be retired (or queued virtually) on its socket any more */
 ITSB_FN u32 nd_without_retire(u32 d) { return (d & ND_SINGLE) ? (d & (0xFFFFu | ND_SINGLE | 0xFF000000u)) : 0u; }
+
+/* Is process w parked, asleep, at the head of a RECV_FILTER loop on socket s, so that packets reaching s are certain to
+ * be popped by that loop head in one activation when the workstation wakes?  (ND_ASLEEP, below.)  *stable: the
+ * assembler found the loop behind the head stable (itsim_b200/ir.py _stable_loop): packets handed to the program are
+ * handled without blocking and the program comes back to this head, so the statement survives queued packets. */
+ITSB_FN bool nd_owner_asleep(Rep& R, u32 node, u32 s, u32 w, u32* filter, bool* stable) {
+    const Sock& S = R.sock[s];
+    if (w == NIL16 || S.wait_head != NIL16) return false;
+    const Pcb& P = R.pcb[w];
+    if (P.state != PS_WAIT || P.wsig != (u16)(WS_NODE | node) || P.phase != 0 || P.sock != s) return false;
+    const u64 ins = R.m.code[P.pc];
+    *filter = (u32)(ins >> 16) & 0xFF;
+    *stable = ((u32)(ins >> 24) & 1u) != 0;
+    if (S.q_len != 0 && !*stable) return false;
+    /* no handler of its own: an exception ends the process through CLOSE; EXIT, which drops the queue either way */
+    return (u32)(ins & 0xFF) == OP_RECV_FILTER && (u32)(ins >> 48) == 0 && *filter <= ND_MAX_FILTER;
+}
 
 /* the statements recomputed from the tables (socket closed, exception delivered: the rare points) */
 ITSB_COLD void node_digest_refresh(Hdr* H, u32 node) {
@@ -966,6 +1002,15 @@ ITSB_COLD void node_digest_refresh(Hdr* H, u32 node) {
         if (n_socks == 0) { first_port = S.port; first_sock = s; }
         n_socks += 1;
         const u16 w = S.wait_head;
+        u32 fa = 0;
+        bool stable = false;
+        if (!have && nd_owner_asleep(R, node, s, S.owner, &fa, &stable)) {
+            have = true;
+            d = S.port | (fa << 16) | ND_ASLEEP | (stable ? (u32)ND_STABLE : 0u) |
+                (R.pcb[S.owner].list_head != NIL32 ? ND_LISTED : 0u) | nd_sock_field(s);
+            R.nmask[node] = R.pmask[S.owner];
+            continue;
+        }
         if (have || w == NIL16 || S.q_len != 0) continue;
         const Pcb& P = R.pcb[w];
         if (P.wnext != NIL16 || P.phase != 1) continue;
@@ -1002,19 +1047,41 @@ ITSB_FN void node_digest_parked(Rep& R, u32 node, u32 s, u32 p, u32 filter, u32 
 ITSB_FN void node_digest_waits(Rep& R, u32 node, u32 s) {
     if (R.hdr->L.max_sig != 0) return;
     const u32 old = R.ndig[node];
-    if ((old & ND_RETIRE) && nd_port(old) == R.sock[s].port) R.ndig[node] = nd_without_retire(old);
+    if ((old & (ND_RETIRE | ND_ASLEEP)) && nd_port(old) == R.sock[s].port) R.ndig[node] = nd_without_retire(old);
 }
 
 /* a delivery woke every waiter of the socket bound to `port` */
 ITSB_FN void node_digest_woken(Rep& R, u32 node, u32 port) {
     const u32 old = R.ndig[node];
-    if ((old & ND_RETIRE) && nd_port(old) == port) R.ndig[node] = nd_without_retire(old);
+    if ((old & (ND_RETIRE | ND_ASLEEP)) && nd_port(old) == port) R.ndig[node] = nd_without_retire(old);
+}
+
+/* a packet was queued for real on the socket bound to `port`: nothing may be queued virtually behind it */
+ITSB_FN void node_digest_enqueued(Rep& R, u32 node, u32 port) {
+    const u32 old = R.ndig[node];
+    if ((old & ND_ASLEEP) && !(old & ND_STABLE) && nd_port(old) == port) R.ndig[node] = nd_without_retire(old);
+}
+
+/* process p parked on its node's wake signal at the head of a RECV_FILTER loop (phase 0) */
+ITSB_FN void node_digest_asleep(Rep& R, u32 node, u32 p) {
+    if (R.hdr->L.max_sig != 0) return;
+    const Pcb& P = R.pcb[p];
+    const u32 s = P.sock;
+    u32 filter = 0;
+    bool stable = false;
+    if (s == NIL16 || !nd_owner_asleep(R, node, s, p, &filter, &stable) || R.sock[s].owner != p) return;
+    const NodeDyn& N = R.node[node];
+    const Sock& S = R.sock[s];
+    const u32 single = (N.sock_head == s && S.next == NIL16) ? (u32)ND_SINGLE : 0u;
+    R.ndig[node] = S.port | (filter << 16) | ND_ASLEEP | (stable ? (u32)ND_STABLE : 0u) |
+                   (P.list_head != NIL32 ? ND_LISTED : 0u) | single | nd_sock_field(s);
+    if (P.list_head != NIL32) R.nmask[node] = R.pmask[p];
 }
 
 /* the node slept or woke: its epoch moved on, so a loop head parked in recv() remembers a stale one */
 ITSB_FN void node_digest_epoch(Rep& R, u32 node) {
     const u32 old = R.ndig[node];
-    if (old & ND_RETIRE) R.ndig[node] = nd_without_retire(old);
+    if (old & (ND_RETIRE | ND_ASLEEP)) R.ndig[node] = nd_without_retire(old);
 }
 
 /* socket s was just put at the head of the node's socket list */
@@ -1023,7 +1090,7 @@ ITSB_FN void node_digest_opened(Rep& R, u32 node, u32 s) {
     const Sock& S = R.sock[s];
     const u32 old = R.ndig[node];
     if (S.next == NIL16) R.ndig[node] = S.port | ND_SINGLE | nd_sock_field(s);     /* the node's only socket */
-    else R.ndig[node] = (old & ND_RETIRE) ? (old & ~(u32)ND_SINGLE) : 0u;   /* what was said about another socket stands */
+    else R.ndig[node] = (old & (ND_RETIRE | ND_ASLEEP)) ? (old & ~(u32)ND_SINGLE) : 0u;   /* what was said about another socket stands */
 }
 
 #if defined(ITSB_CHECK_DIGEST)
@@ -1036,7 +1103,8 @@ static bool node_digest_valid(Rep& R, u32 node) {
         if (nd_port(d) == 0) { if (N.sock_head != NIL16) return false; }
         else if (N.sock_head == NIL16 || R.sock[N.sock_head].next != NIL16 || R.sock[N.sock_head].port != nd_port(d)) return false;
     }
-    if ((d & (ND_SINGLE | ND_RETIRE)) && nd_port(d) != 0 && nd_sock(d) != ND_NOSOCK) {
+    if ((d & ND_RETIRE) && (d & ND_ASLEEP)) return false;
+    if ((d & (ND_SINGLE | ND_RETIRE | ND_ASLEEP)) && nd_port(d) != 0 && nd_sock(d) != ND_NOSOCK) {
         const Sock& S = R.sock[nd_sock(d)];
         if (S.port != nd_port(d) || S.node != node) return false;
         bool linked = false;
@@ -1059,6 +1127,19 @@ static bool node_digest_valid(Rep& R, u32 node) {
         for (u32 n = P.list_head; n != NIL32; n = R.arena[n].next) want |= 1ull << (R.arena[n].f0 & 63);
         if (R.pmask[S.wait_head] != want) return false;
         if ((d & ND_LISTED) && R.nmask[node] != want) return false;
+    } else if (d & ND_ASLEEP) {
+        if (d & ND_RETIRE) return false;
+        const u32 s = nd_sock(d);
+        if (s == ND_NOSOCK || R.sock[s].port != nd_port(d) || R.sock[s].node != node) return false;
+        u32 f = 0;
+        bool stable = false;
+        const u32 w = R.sock[s].owner;
+        if (!nd_owner_asleep(R, node, s, w, &f, &stable) || f != nd_filter(d) || stable != ((d & ND_STABLE) != 0)) return false;
+        const Pcb& P = R.pcb[w];
+        if (((d & ND_LISTED) != 0) != (P.list_head != NIL32)) return false;
+        u64 want = 0;
+        for (u32 n = P.list_head; n != NIL32; n = R.arena[n].next) want |= 1ull << (R.arena[n].f0 & 63);
+        if (R.pmask[w] != want || ((d & ND_LISTED) && R.nmask[node] != want)) return false;
     } else if (d & ND_LISTED) return false;
     return true;
 }
@@ -1219,6 +1300,7 @@ ITSB_COLD int sock_open_on(Hdr* H, u32 p, u32 node, u32 port, bool own) {
     S.port = (u16)port; S.node = (u16)node; S.owner = (u16)p;
     S.wait_head = NIL16; S.wait_tail = NIL16;
     S.q_head = NIL32; S.q_tail = NIL32; S.q_len = 0;
+    R.sockv[s].count = 0; R.sockv[s].bytes = 0;
     S.next = N.sock_head;
     N.sock_head = (u16)s;
     if (own) P.sock = (u16)s;
@@ -1248,6 +1330,7 @@ ITSB_COLD void sock_close(Hdr* H, u32 p) {
         n = nx;
     }
     S.q_head = NIL32; S.q_tail = NIL32; S.q_len = 0;
+    R.sockv[s].count = 0; R.sockv[s].bytes = 0;      /* packets queued virtually are dropped with the rest */
     S.port = 0;
     u32 top = H->sock_free_top;
     R.sock_free[top] = (u16)s;
@@ -1459,27 +1542,35 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
     const bool digest_retires = fast_ok && H->conntab == nullptr;
     const u32 tag_bit = 1u << (K.tag & 31);
     const bool inl = sock_head_inline(R);
-    enum { RC_TABLES = 0, RC_DROPPED = 1, RC_RETIRED = 2 };
+    enum { RC_TABLES = 0, RC_DROPPED = 1, RC_RETIRED = 2, RC_VIRTUAL = 3 };
 
-    /* a recipient's digest: nobody listens / retired on the spot / look at the tables (s = its socket when stated) */
+    /* a recipient's digest: nobody listens / retired on the spot / queued virtually / look at the tables (s = its
+       socket when the digest states it) */
+    const bool virtual_ok = R.trace == nullptr && H->conntab == nullptr;
     auto classify = [&](u32 node, int& s) -> u32 {
         const u32 dg = R.ndig[node];
 #if defined(ITSB_CHECK_DIGEST)
         if (!node_digest_valid(R, node)) { fail(H, ITSB_ERR_BAD_OPCODE, 0xD16E57ull << 32 | node); return RC_DROPPED; }
 #endif
         if (nd_port(dg) != dst_port) return (dg & ND_SINGLE) ? (u32)RC_DROPPED : (u32)RC_TABLES;   /* its only socket is elsewhere */
-        if ((dg & (ND_SINGLE | ND_RETIRE)) && nd_sock(dg) != ND_NOSOCK) s = (int)nd_sock(dg);
-        if (digest_retires && (dg & ND_RETIRE)) {
+        if ((dg & (ND_SINGLE | ND_RETIRE | ND_ASLEEP)) && nd_sock(dg) != ND_NOSOCK) s = (int)nd_sock(dg);
+        const bool retires = digest_retires && (dg & ND_RETIRE), sleeps = virtual_ok && (dg & ND_ASLEEP);
+        if (retires || sleeps) {
             const itsb_filter F = R.m.filters[nd_filter(dg)];
             if ((F.tags_always & tag_bit) != 0 || ((F.tags_if_host & tag_bit) != 0 && K.f0 == R.m.nodes[node].host))
                 return RC_TABLES;
             /* handed over while it remembers a packet (if_list), or one with this hostname field (if_listed): the
                Bloom bit says "certainly not" for the second; anything else is for the tables to decide */
+            const bool list_class = ((F.tags_if_list | F.tags_if_listed) & tag_bit) != 0;
             if (dg & ND_LISTED) {
                 if (F.tags_if_list & tag_bit) return RC_TABLES;
                 if ((F.tags_if_listed & tag_bit) && ((R.nmask[node] >> (K.f0 & 63)) & 1ull) != 0) return RC_TABLES;
             }
-            return RC_RETIRED;
+            if (retires) return RC_RETIRED;
+            /* asleep: what the filter makes of a tag that depends on the remembered packets can still change if a
+               packet queued ahead is handed to the program first */
+            if (list_class && (dg & ND_STABLE) && R.sock[s].q_len != 0) return RC_TABLES;
+            return RC_VIRTUAL;
         }
         return RC_TABLES;
     };
@@ -1494,16 +1585,20 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
         bool valid = i < count;
         u32 node = first + i;
         int s = -1;
-        bool found = false, retire = false;
+        bool found = false, retire = false, queued_virtually = false;
         if (valid) {
             u32 rc = RC_TABLES;
             if (known) {     /* classified by the caller and left for the tables: only the socket hint is read again */
                 const u32 dg = R.ndig[node];
-                if (nd_port(dg) == dst_port && (dg & (ND_SINGLE | ND_RETIRE)) && nd_sock(dg) != ND_NOSOCK) s = (int)nd_sock(dg);
+                if (nd_port(dg) == dst_port && (dg & (ND_SINGLE | ND_RETIRE | ND_ASLEEP)) && nd_sock(dg) != ND_NOSOCK) s = (int)nd_sock(dg);
             } else {
                 rc = classify(node, s);
             }
             if (rc == RC_RETIRED) { found = true; retire = true; }
+            else if (rc == RC_VIRTUAL) {     /* its sleeping owner's loop head will pop and reject it: counted, not queued */
+                found = true; queued_virtually = true;
+                R.sockv[s].count += 1; R.sockv[s].bytes += K.size;
+            }
             else if (rc == RC_TABLES) {
                 if (s < 0) s = sock_find(R, node, K.dst_ip, dst_port);
                 found = s >= 0;
@@ -1525,7 +1620,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
         }
         const u32 n_found = (u32)popc(w_ballot(found));
         const u32 n_retired = (u32)popc(w_ballot(retire));
-        const bool acc = found && !retire;      /* recipients that really enqueue */
+        const bool acc = found && !retire && !queued_virtually;      /* recipients that really enqueue */
         /* a copy goes onto each accepting socket: into its inline head slot when its queue is empty, else an arena node */
         const bool need_node = acc && (!inl || R.sock[s].q_len != 0);
         const u32 amask = w_ballot(need_node);
@@ -1552,6 +1647,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
             }
             S.q_len += 1;
             for (u16 w = S.wait_head; w != NIL16; w = R.pcb[w].wnext) nwait += 1;
+            if (nwait == 0) node_digest_enqueued(R, node, S.port);
         }
         if (n_acc) H->arena_free_top = atop - n_acc;
         /* _enqueue -> packet signal turn_on: resume this socket's waiters (normally the one blocked in recv) */
@@ -1633,20 +1729,21 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
         for (u32 c0 = 0; c0 < count; c0 += 64) {
             const u32 cn = count - c0 < 64 ? count - c0 : 64;
             u64 slow = 0, retired = 0;
-            u32 dropped = 0;
+            u32 dropped = 0, queued = 0;
 #if defined(__CUDACC__)
 #pragma unroll 1
 #endif
             for (u32 j = 0; j < cn; ++j) {
-                int s_unused = -1;
-                const u32 rc = classify(first + c0 + j, s_unused);
+                int sj = -1;
+                const u32 rc = classify(first + c0 + j, sj);
                 if (rc == RC_TABLES) slow |= 1ull << j;
                 else if (rc == RC_RETIRED) retired |= 1ull << j;
+                else if (rc == RC_VIRTUAL) { R.sockv[sj].count += 1; R.sockv[sj].bytes += K.size; queued += 1; }
                 else dropped += 1;
             }
             if (H->status != 0) return;
             const u32 n_ret = (u32)popc64(retired);
-            q_valid += dropped + n_ret; q_found += n_ret; q_retired += n_ret;
+            q_valid += dropped + n_ret + queued; q_found += n_ret + queued; q_retired += n_ret;
             while (slow != 0) {
                 const u32 j = (u32)ctz64(slow);
                 slow &= slow - 1;
@@ -1925,7 +2022,14 @@ ITSB_FN void run_process(Rep& R, u32 p) {
                     if (!N.awake) {
                         waiters_append(R, N.wake_head, N.wake_tail, p, (u16)(WS_NODE | P.node));
                         P.state = PS_WAIT;
+                        node_digest_asleep(R, P.node, p);
                         return;
+                    }
+                    SockV& V = R.sockv[P.sock];
+                    if (V.count != 0) {           /* what was queued virtually while it slept: popped and rejected here */
+                        stat_add(R, ITSB_TM_PACKETS_RECEIVED, V.count);
+                        stat_add(R, ITSB_TM_BYTES_RECEIVED, V.bytes);
+                        V.count = 0; V.bytes = 0;
                     }
                     P.r[a & 3] = N.epoch;
                     P.phase = 1;
@@ -1995,7 +2099,12 @@ ITSB_COLD u32 deliver_exception(Hdr* H, u32 p, u32 exc) {
         P.timer_ev = NIL16;
         P.timer_tok = (u16)(P.timer_tok + 1);
     } else if (P.state == PS_WAIT && (P.wsig & 0xC000) != WS_SIG) {
-        if (P.wsig & WS_NODE) { NodeDyn& N = R.node[P.wsig & 0x3FFF]; waiters_unlink(R, N.wake_head, N.wake_tail, p); }
+        if (P.wsig & WS_NODE) {
+            const u32 nd = P.wsig & 0x3FFF;
+            NodeDyn& N = R.node[nd];
+            waiters_unlink(R, N.wake_head, N.wake_tail, p);
+            if (R.ndig[nd] & ND_ASLEEP) node_digest_refresh(H, nd);     /* it may be the sleeper the digest speaks of */
+        }
         else if (P.wsig & WS_SOCK) {
             Sock& S = R.sock[P.wsig & 0x3FFF];
             waiters_unlink(R, S.wait_head, S.wait_tail, p);
@@ -2684,6 +2793,7 @@ ITSB_FN void init_replica(Rep& R, u64 replica_id) {
     H->pcb_free_top = (u16)L->max_proc;
     for (u32 i = 0; i < L->max_sock; ++i) {
         memset(&R.sock[i], 0, sizeof(Sock)); memset(&R.sockpkt[i], 0, sizeof(ArenaNode));
+        R.sockv[i].count = 0; R.sockv[i].bytes = 0;
         R.sock_free[i] = (u16)(L->max_sock - 1 - i);
     }
     H->sock_free_top = (u16)L->max_sock;

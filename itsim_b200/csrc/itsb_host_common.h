@@ -35,6 +35,7 @@ static inline Layout compute_layout(const itsb_model_desc& d) {
     L.off_sock = off;      off = align_up(off + (uint32_t)sizeof(Sock) * L.max_sock, 16);
     L.off_sock_free = off; off = align_up(off + 2 * L.max_sock, 16);
     L.off_sockpkt = align_up(off, 32); off = L.off_sockpkt + (uint32_t)sizeof(ArenaNode) * L.max_sock;   /* one sector each */
+    L.off_sockv = off;     off = align_up(off + (uint32_t)sizeof(SockV) * L.max_sock, 16);
     L.off_node = off;      off = align_up(off + (uint32_t)sizeof(NodeDyn) * L.n_nodes, 16);
     L.off_ndig = align_up(off, 32); off = align_up(L.off_ndig + 4 * L.n_nodes, 16);   /* sector-aligned: 8 nodes per sector */
     L.off_nmask = align_up(off, 32); off = align_up(L.off_nmask + 8 * L.n_nodes, 16);

@@ -278,7 +278,43 @@ class Asm:
             word = (op & 0xFF) | ((a & 0xFF) << 8) | ((b & 0xFF) << 16) | ((c & 0xFF) << 24) \
                 | ((self._resolve(imm) & 0xFFFFFFFF) << 32)
             code[pc] = word
+        for pc in range(len(code)):       # operand c of a fused loop head: 1 = its loop is stable (see _stable_loop)
+            if int(code[pc]) & 0xFF == OP_RECV_FILTER and self._stable_loop(code, pc):
+                code[pc] = np.uint64(int(code[pc]) | (1 << 24))
         entries = np.zeros((len(self.entries), 2), dtype=np.uint32)
         for i, (name, prog) in enumerate(self.entries):
             entries[i] = (self._labels[name], prog)
         return code, entries
+
+    # what a program may do with a packet its loop head hands over and still have a "stable" loop: nothing that blocks,
+    # ends the process, or touches the socket other than sending -- so that the packets queued behind are certain to be
+    # popped by the same loop head in the same activation
+    _STABLE_OPS = frozenset((OP_NOP, OP_LI, OP_MOV, OP_ADDI, OP_DRAWI, OP_DRAW_ADDI, OP_SEND, OP_FORWARD, OP_LIST_CLEAR,
+                             OP_LIST_PUSH, OP_STAT, OP_STAT_ADD, OP_STAT_FIRST))
+
+    @classmethod
+    def _stable_loop(cls, code: np.ndarray, head: int) -> bool:
+        """Does every path from the instruction after the RECV_FILTER at ``head`` come back to ``head`` through
+        non-blocking instructions only?  (The engine then knows that a packet the filter is bound to reject can be
+        counted instead of queued while the workstation sleeps: itsb_core.cuh, ND_ASLEEP.)"""
+        seen, todo = set(), [head + 1]
+        while todo:
+            pc = todo.pop()
+            if pc == head or pc in seen:
+                continue
+            if pc >= len(code):
+                return False
+            seen.add(pc)
+            word = int(code[pc])
+            op, imm = word & 0xFF, word >> 32
+            if op in cls._STABLE_OPS:
+                todo.append(pc + 1)
+            elif op == OP_JMP:
+                todo.append(imm & 0xFFFF)
+            elif op in (OP_JEQ, OP_JNE, OP_JASLEEP, OP_LIST_TAKE):
+                todo += [pc + 1, imm & 0xFFFF]
+            elif op in (OP_JEQI, OP_JNEI):
+                todo += [pc + 1, imm & 0xFFFF]
+            else:
+                return False
+        return True
