@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ITSB_ABI_VERSION 4
+#define ITSB_ABI_VERSION 5
 
 /* ---- engine errors (negative) ------------------------------------------------------------------------------ */
 #define ITSB_OK                    0

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # ITSB_LIB: another build of the same library (the -DITSB_EXPERIMENTS one, for A/B measurements); never a different engine
 LIB_PATH = os.environ.get("ITSB_LIB") or os.path.join(HERE, "libitsim_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 TM_KIND0, TM_PACKETS_SENT, TM_BYTES_SENT, TM_PACKETS_RECEIVED, TM_BYTES_RECEIVED = 0, 9, 10, 11, 12
 TM_DELIVERED, TM_DROPPED, TM_USER0, TM_LAT0, LAT_BINS = 13, 14, 15, 23, 64
 TM_USER8, TM_USER_SLOTS = TM_LAT0 + LAT_BINS, 12

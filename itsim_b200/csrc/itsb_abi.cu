@@ -287,7 +287,8 @@ static void choose_kernel(itsb_engine* e) {
     else if (lane_hbm_ok) {
         /* nothing on the shipped-itsim path is lane-parallel, so a lane per replica only needs more replicas than the
            warp kernel holds in flight (148 SMs x 16-20 warps) to win: measured on config C4 (profiles/README.md) */
-        e->kernel = e->n_replicas >= 4096 ? K_VOTE_HBM : warp_kernel;
+        /* config C4, 10 000 replicas (x 10^8 events/s): k_run_in_place 0.90, k_run_vote_hbm 1.12, k_run_pool_hbm 1.49 */
+        e->kernel = e->n_replicas >= 4096 ? (e->pool_hbm_ok ? K_POOL_HBM : K_VOTE_HBM) : warp_kernel;
     }
     else {
         /* A lane per replica needs replicas to fill the GPU's threads; a warp per replica (k_run, state in shared memory)
@@ -531,6 +532,8 @@ int itsb_run_async(itsb_engine* e, double duration) {
         const char* force = getenv("ITSB_VOTE_LANES");
         if (force && atoi(force) >= 1) lpw = (uint64_t)atoi(force);
         e->rp.lanes_per_warp = (uint32_t)(lpw < 1 ? 1 : (lpw > 32 ? 32 : lpw));
+        const char* stick = getenv("ITSB_POOL_STICK");
+        e->rp.pool_stick = stick ? (uint32_t)atoi(stick) : 0u;
     }
     switch (e->kernel) {
     case K_VOTE:     k_run_vote<<<lane_grid, 256, e->so.total, e->stream>>>(e->rp); break;

@@ -1723,8 +1723,13 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
            ones in between consume are accounted for as the pass reaches them, so every wake-up gets the value it
            would have got with the recipients taken strictly one after the other. */
 #if defined(__CUDACC__)
-        if (count > 8)
+        if (count > 8) {
             for (u32 o = 0; o < count; o += 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(R.ndig + first + o));
+            u32 listed_class = 0;       /* does some filter look at the remembered packets for this tag? then the Bloom words too */
+            for (u32 f = 0; f < R.m.n_filters && f <= ND_MAX_FILTER; ++f) listed_class |= R.m.filters[f].tags_if_listed & tag_bit;
+            if (listed_class)
+                for (u32 o = 0; o < count; o += 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(R.nmask + first + o));
+        }
 #endif
         for (u32 c0 = 0; c0 < count; c0 += 64) {
             const u32 cn = count - c0 < 64 ? count - c0 : 64;
@@ -2017,9 +2022,12 @@ ITSB_FN void run_process(Rep& R, u32 p) {
             Sock& S = R.sock[P.sock];
             const itsb_filter F = R.m.filters[b];
             bool handed = false;
+            /* the node's wake state cannot change inside this loop (only NODE_SLEEP / NODE_WAKE of the blinking process
+               move it): read once, together with the socket, instead of after the packet has arrived from HBM */
+            const u32 n_epoch = N.epoch, n_awake = N.awake;
             for (;;) {
                 if (P.phase == 0) {               /* with ws.awake(): wait_until_awake, remember the wake epoch */
-                    if (!N.awake) {
+                    if (!n_awake) {
                         waiters_append(R, N.wake_head, N.wake_tail, p, (u16)(WS_NODE | P.node));
                         P.state = PS_WAIT;
                         node_digest_asleep(R, P.node, p);
@@ -2031,7 +2039,7 @@ ITSB_FN void run_process(Rep& R, u32 p) {
                         stat_add(R, ITSB_TM_BYTES_RECEIVED, V.bytes);
                         V.count = 0; V.bytes = 0;
                     }
-                    P.r[a & 3] = N.epoch;
+                    P.r[a & 3] = n_epoch;
                     P.phase = 1;
                 }
                 if (S.q_len == 0) {               /* socket.recv() */
@@ -2042,7 +2050,7 @@ ITSB_FN void run_process(Rep& R, u32 p) {
                 }
                 const ArenaNode A = sock_pop(R, S);
                 P.phase = 0;
-                if (N.epoch != P.r[a & 3]) { P.pc = (u16)(imm & 0xFFFF); break; }      /* FellAsleep */
+                if (n_epoch != P.r[a & 3]) { P.pc = (u16)(imm & 0xFFFF); break; }      /* FellAsleep */
                 if (filter_passes(R, F, A.tag, A.f0, R.m.nodes[P.node].host, P)) {
                     set_pkt_regs(R, A);
                     handed = true;
@@ -2327,6 +2335,16 @@ ITSB_FN bool run_take(Rep& R, const RunCtx& C, PendingEvent& E) {
     E.data = ev_take(R, src);
     E.tb = tb;
     E.seq = seq;
+#if defined(__CUDACC__) && defined(ITSB_LANES)
+    /* the event is handled in a later round (k_run_vote) or by another warp (k_run_pool): what its handler reads first
+       -- the process control block, or the packet -- starts its way from HBM now */
+    {
+        const u32 kind = ev_kind(E.data);
+        const void* first = (kind == ITSB_EV_TX_BEGIN || kind == ITSB_EV_TX_END || kind == ITSB_EV_DELIVER)
+                                ? (const void*)(R.arena + ev_pkt(E.data)) : (const void*)(R.pcb + ev_idx(E.data));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(first));
+    }
+#endif
     return true;
 }
 

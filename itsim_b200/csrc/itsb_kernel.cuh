@@ -64,6 +64,9 @@ struct RunParams {
     uint32_t state_in_hbm;            /* 1: replicas too large for shared memory are advanced in place (L1/L2-cached) */
     uint32_t tables_in_hbm;           /* 1: the model tables themselves exceed shared memory: read in place (L1-cached) */
     const Model* model_dev;           /* the Model struct in device memory (pointers to the tables in HBM)             */
+    uint32_t pool_stick;              /* k_run_pool: a warp takes the kind the CTA's warps took last while its ring holds
+                                         at least this many slots (0: always the fullest ring) -- warps of an SM then
+                                         tend to run the same handler, i.e. share fetched instruction lines */
     uint32_t lanes_per_warp;          /* k_run_vote: lanes of a warp that take replicas (a batch smaller than the GPU's
                                          threads is spread over all warps instead of filling a few of them)             */
 };

@@ -36,6 +36,7 @@ struct PoolShared {
     unsigned int head[POOL_RINGS];
     unsigned int tail[POOL_RINGS];
     unsigned int live;                              /* slots that hold an unfinished replica */
+    unsigned int cur_kind;                          /* the kind the CTA's warps took last (p.pool_stick) */
 };
 
 /* A ring cell holds (lap << 16) | (slot + 1), lap = 1 + (position / ring size) mod 65535, or 0 when free.  The producer
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_run_pool(const RunParams 
     const unsigned int t = threadIdx.x, lane = t & 31;
     for (unsigned int i = t; i < POOL_RINGS * RING; i += THREADS) (&S->ring[0][0])[i] = 0;
     if (t < POOL_RINGS) { S->head[t] = 0; S->tail[t] = 0; }
-    if (t == 0) S->live = 0;
+    if (t == 0) { S->live = 0; S->cur_kind = 0; }
     __syncthreads();
     /* the batch is spread evenly over the CTAs: each seeds its share of slots (p.lanes_per_warp carries the share), and a
        slot whose replica finishes takes the next one of the batch */
@@ -103,10 +104,18 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_run_pool(const RunParams 
         if (lane == 0) {
             for (;;) {
                 unsigned int best = 0, best_n = 0;
+                if (p.pool_stick != 0) {            /* stay with the kind the other warps are running, while it has work */
+                    const unsigned int ck = *(volatile unsigned int*)&S->cur_kind;
+                    const unsigned int avail = *(volatile unsigned int*)&S->tail[ck] - *(volatile unsigned int*)&S->head[ck];
+                    if (avail >= p.pool_stick && avail <= (unsigned int)RING) { best = ck; best_n = avail; }
+                }
+                if (best_n == 0) {
 #pragma unroll
-                for (unsigned int k = 0; k < POOL_RINGS; ++k) {
-                    const unsigned int avail = *(volatile unsigned int*)&S->tail[k] - *(volatile unsigned int*)&S->head[k];
-                    if (avail > best_n && avail <= (unsigned int)RING) { best_n = avail; best = k; }
+                    for (unsigned int k = 0; k < POOL_RINGS; ++k) {
+                        const unsigned int avail = *(volatile unsigned int*)&S->tail[k] - *(volatile unsigned int*)&S->head[k];
+                        if (avail > best_n && avail <= (unsigned int)RING) { best_n = avail; best = k; }
+                    }
+                    if (best_n != 0 && p.pool_stick != 0) *(volatile unsigned int*)&S->cur_kind = best;
                 }
                 if (best_n == 0) {
                     if (*(volatile unsigned int*)&S->live == 0) { n = 0xFFFFFFFFu; break; }      /* the CTA's work is done */

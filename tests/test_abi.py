@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared_functions():
         assert hasattr(lib, name), name
     from itsim_b200 import _lib
-    assert lib.itsb_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.itsb_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_hostemu_exports_the_same_surface(built):

@@ -85,10 +85,11 @@ def test_both_large_model_kernels_give_the_reference_traces(which, name, summari
 
 @pytest.mark.gpu
 def test_large_batch_on_the_default_kernel_equals_hostemu(hostemu, monkeypatch):
-    """4 200 replicas: itsb_run's own choice is the lane-per-replica kernel; sampled replicas equal the host build."""
+    """4 200 replicas: itsb_run's own choice is the pooled lane-per-replica kernel; sampled replicas equal the host
+    build."""
     monkeypatch.delenv("ITSB_KERNEL", raising=False)
     gpu, _ = run("gpu", None, 16, 64, 3, 0, 2.0, 0, n=4200)
-    assert gpu.kernel_name() == "k_run_vote_hbm"
+    assert gpu.kernel_name() == "k_run_pool_hbm"
     for r in (0, 2100, 4199):
         emu, _ = run("hostemu", hostemu, 16, 64, 3, r, 2.0, 0, n=1)
         assert np.array_equal(gpu.replica_telemetry(r), emu.replica_telemetry(0)), r

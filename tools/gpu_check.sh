@@ -50,6 +50,20 @@ lan)
 malware)
   timeout 900 python bench.py --workload malware --steps 6 --warmup 2 --no-cpu-baseline > gpurun_out/malware.json 2> gpurun_out/malware.err; line gpurun_out/malware.json malware
   timeout 900 python bench.py --workload backdoor --steps 6 --warmup 2 --no-cpu-baseline > gpurun_out/backdoor.json 2> gpurun_out/backdoor.err; line gpurun_out/backdoor.json backdoor;;
+stick)
+  # k_run_pool: warps of an SM staying on one event kind while its ring holds >= N slots (0 = always the fullest ring)
+  for n in ${STICKS:-0 8 16 24}; do
+    ITSB_POOL_STICK=$n timeout 600 python bench.py --steps 6 --warmup 2 --no-cpu-baseline --no-verify > gpurun_out/stick_${n}.json 2> gpurun_out/stick_${n}.err
+    line gpurun_out/stick_${n}.json "pool stick $n"
+  done;;
+racecheck)
+  # the warp-per-replica kernel's "all lanes write the same scalar" model under the race detector: 8 replicas x 300 s
+  ITSB_KERNEL=warp timeout 900 compute-sanitizer --tool racecheck --racecheck-report all python -c "
+import sys; sys.path.insert(0, '.')
+from itsim_b200 import netsimple
+eng = netsimple.build().run_replicas(8, seed=0)
+print('events', eng.run(300.0), eng.kernel_name())
+" > gpurun_out/racecheck.log 2>&1; echo "racecheck rc=$?"; tail -6 gpurun_out/racecheck.log;;
 experiments)
   # the regrouping variants of round 1 on this round's engine core (the -DITSB_EXPERIMENTS build)
   for k in sorted lanes; do
