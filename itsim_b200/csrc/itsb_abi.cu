@@ -533,7 +533,9 @@ int itsb_run_async(itsb_engine* e, double duration) {
         if (force && atoi(force) >= 1) lpw = (uint64_t)atoi(force);
         e->rp.lanes_per_warp = (uint32_t)(lpw < 1 ? 1 : (lpw > 32 ? 32 : lpw));
         const char* stick = getenv("ITSB_POOL_STICK");
-        e->rp.pool_stick = stick ? (uint32_t)atoi(stick) : 0u;
+        e->rp.pool_stick = stick ? (uint32_t)atoi(stick) : 4u;     /* measured: 0 -> 6.0, 1..24 -> 6.3-6.7 x 10^9 */
+        const char* byprog = getenv("ITSB_POOL_BY_PROGRAM");
+        e->rp.pool_by_program = byprog ? (uint32_t)atoi(byprog) : 0u;
     }
     switch (e->kernel) {
     case K_VOTE:     k_run_vote<<<lane_grid, 256, e->so.total, e->stream>>>(e->rp); break;

@@ -50,6 +50,13 @@
  * 32 KB instruction cache level, profiles/).  The dozen functions that run per event are therefore given names
  * that sort first, in call order, so the hot code is one contiguous range behind the event loop instead of being
  * scattered over the 200 KB of the shipped-itsim primitives. */
+#else
+#define ITSB_W 1
+#define ITSB_FN static inline
+#define ITSB_COLD static __attribute__((noinline))
+#endif
+#if defined(__CUDACC__)
+/* (both device shapes: the lane-per-replica kernels turned out to be bound by instruction supply too) */
 #define exec_cold         a0_execute
 #define draw_dist         a1_variate
 #define log_f64           a1z_ln_f64
@@ -64,10 +71,6 @@
 #define sock_close        a9_sk_clos
 #define proc_exit         aa_prcexit
 #define deliver_exception ab_deliv_x
-#else
-#define ITSB_W 1
-#define ITSB_FN static inline
-#define ITSB_COLD static __attribute__((noinline))
 #endif
 
 namespace itsb {

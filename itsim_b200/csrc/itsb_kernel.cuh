@@ -67,6 +67,7 @@ struct RunParams {
     uint32_t pool_stick;              /* k_run_pool: a warp takes the kind the CTA's warps took last while its ring holds
                                          at least this many slots (0: always the fullest ring) -- warps of an SM then
                                          tend to run the same handler, i.e. share fetched instruction lines */
+    uint32_t pool_by_program;         /* k_run_pool: WAKE events queued per program (1) or with the other kinds (0) */
     uint32_t lanes_per_warp;          /* k_run_vote: lanes of a warp that take replicas (a batch smaller than the GPU's
                                          threads is spread over all warps instead of filling a few of them)             */
 };

@@ -25,7 +25,25 @@
 #define POOL_ENTRY(name) name
 #endif
 
-#define POOL_RINGS 9                    /* ring index = event kind (0..8) */
+/* ring index: the event kind (0..8); activations of a parked process (WAKE: the most frequent and the most divergent
+ * kind -- a daemon's receive loop, a query's reply, the DHCP exchange run different code) are split further by the
+ * program they resume, so that the lanes of a batch run the same code and not just the same handler: measured active
+ * lanes per warp instruction 7.4 -> see profiles/README.md */
+#ifndef POOL_PROG_RINGS
+#define POOL_PROG_RINGS 0       /* measured with 16 (default bench): 6.31 vs 6.6-6.7 x 10^9 with the nine kind rings alone --
+                                   the lane that picks a ring reads every ring's cursors, and 25 rings cost more there
+                                   than the finer grouping saves; kept as a build option (-DPOOL_PROG_RINGS=16) */
+#endif
+#define POOL_RINGS (9 + POOL_PROG_RINGS)
+
+__device__ __forceinline__ unsigned int pool_key(Rep& R, const PendingEvent& E, unsigned int by_program) {
+    const unsigned int kind = ev_kind(E.data);
+#if POOL_PROG_RINGS > 0
+    if (by_program != 0 && kind == ITSB_EV_WAKE) return 9u + (R.pcb[ev_idx(E.data)].prog & (POOL_PROG_RINGS - 1));
+#endif
+    (void)R; (void)by_program;
+    return kind;
+}
 
 struct PoolSlot { PendingEvent E; RunCtx C; unsigned long long r; };      /* 64 bytes */
 
@@ -70,7 +88,7 @@ __device__ __forceinline__ bool pool_begin(const RunParams& p, const Model* m, u
     PendingEvent E;
     s.r = r;
     s.C = C;
-    if (run_take(R, C, E)) { s.E = E; kind = ev_kind(E.data); return true; }
+    if (run_take(R, C, E)) { s.E = E; kind = pool_key(R, E, p.pool_by_program); return true; }
     atomicAdd(p.events_done, run_events(R, C));
     if (R.hdr->status != 0) atomicMin(p.first_failed, (long long)r);
     return false;
@@ -151,7 +169,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_run_pool(const RunParams 
             if (run_take(R, C, E)) {
                 SL.E = E;
                 __threadfence_block();
-                const unsigned int k2 = ev_kind(E.data);
+                const unsigned int k2 = pool_key(R, E, p.pool_by_program);
                 pool_push<RING>(S->ring[k2], &S->tail[k2], s);
             } else {
                 atomicAdd(p.events_done, run_events(R, C));

@@ -50,6 +50,16 @@ lan)
 malware)
   timeout 900 python bench.py --workload malware --steps 6 --warmup 2 --no-cpu-baseline > gpurun_out/malware.json 2> gpurun_out/malware.err; line gpurun_out/malware.json malware
   timeout 900 python bench.py --workload backdoor --steps 6 --warmup 2 --no-cpu-baseline > gpurun_out/backdoor.json 2> gpurun_out/backdoor.err; line gpurun_out/backdoor.json backdoor;;
+quick)
+  # after a kernel change: the engine-kernel parity file, then a short default bench
+  timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q > gpurun_out/pytest_quick.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_quick.log; tail -3 gpurun_out/pytest_quick.log
+  timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; line gpurun_out/bench_quick.json "bench (8 steps)";;
+ab)
+  # A/B of two settings of k_run_pool in one visit, alternating (same box, same clocks): ITSB_POOL_BY_PROGRAM 0 / 1
+  for rep in 1 2; do for v in 0 1; do
+    ITSB_POOL_BY_PROGRAM=$v timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-verify > gpurun_out/ab_${v}_${rep}.json 2> gpurun_out/ab_${v}_${rep}.err
+    line gpurun_out/ab_${v}_${rep}.json "by_program=$v run $rep"
+  done; done;;
 stick)
   # k_run_pool: warps of an SM staying on one event kind while its ring holds >= N slots (0 = always the fullest ring)
   for n in ${STICKS:-0 8 16 24}; do
