@@ -610,6 +610,7 @@ ITSB_COLD double draw_dist(Hdr* H, const itsb_dist* Dp) {
 }
 
 /* ---- telemetry ------------------------------------------------------------------------------------------------------ */
+/* (sockv_add / sockv_take below follow the same rule as the counters) */
 /* A counter update.  In the lane-per-replica kernel the counters live in HBM and a read-modify-write makes the lane wait
  * for the load (round 2 profile: ~5 % of all stall samples on these lines); a replica's counters are touched by its own
  * lane only, so the update goes out as a reduction (RED.ADD at the L2, nothing to wait for) and the few reads (the
@@ -617,9 +618,23 @@ ITSB_COLD double draw_dist(Hdr* H, const itsb_dist* Dp) {
 #if defined(__CUDACC__) && defined(ITSB_LANES)
 ITSB_FN void stat_add(Rep& R, u32 slot, u64 v) { atomicAdd((unsigned long long*)&R.stats[slot], (unsigned long long)v); }
 ITSB_FN u64 stat_get(Rep& R, u32 slot) { return __ldcg((const unsigned long long*)&R.stats[slot]); }
+/* a packet queued virtually on socket s (ND_ASLEEP), and the loop head collecting what was queued */
+ITSB_FN void sockv_add(Rep& R, u32 s, u32 bytes) { atomicAdd(&R.sockv[s].count, 1u); atomicAdd(&R.sockv[s].bytes, bytes); }
+ITSB_FN SockV sockv_take(Rep& R, u32 s) {
+    SockV V;
+    V.count = __ldcg(&R.sockv[s].count);
+    if (V.count != 0) { V.bytes = __ldcg(&R.sockv[s].bytes); R.sockv[s].count = 0; R.sockv[s].bytes = 0; } else V.bytes = 0;
+    return V;
+}
 #else
 ITSB_FN void stat_add(Rep& R, u32 slot, u64 v) { R.stats[slot] += v; }
 ITSB_FN u64 stat_get(Rep& R, u32 slot) { return R.stats[slot]; }
+ITSB_FN void sockv_add(Rep& R, u32 s, u32 bytes) { R.sockv[s].count += 1; R.sockv[s].bytes += bytes; }
+ITSB_FN SockV sockv_take(Rep& R, u32 s) {
+    const SockV V = R.sockv[s];
+    if (V.count != 0) { R.sockv[s].count = 0; R.sockv[s].bytes = 0; }
+    return V;
+}
 #endif
 
 ITSB_COLD void trace_put(Hdr* H, u32 kind, u32 prog, u32 node, u32 aux) {
@@ -937,7 +952,7 @@ ITSB_FN u32 ev_take(Rep& R, int src) {
  * per counted event, 85 % of stall samples waiting on those loads).  The digests of a network's nodes are contiguous:
  * 51 x 4 bytes = 7 sectors.
  *
- *   port[0:16]  filter[16:21]  flags[21:24]  socket[24:32]
+ *   port[0:16]  filter[16:19]  flags[19:24]  socket[24:31]  ND_QUEUED[31]
  *   ND_SINGLE   the node has exactly one socket, bound to `port` (no socket at all: ND_SINGLE with port 0, which is
  *               never bound) -- a packet for any other port finds nothing: dropped without looking further
  *   ND_RETIRE   the socket bound to `port` has exactly one waiter, parked inside recv() of a RECV_FILTER loop head
@@ -955,7 +970,10 @@ ITSB_FN u32 ev_take(Rep& R, int src) {
  *               in sockv[socket] (count, bytes) and credited by the loop head when it resumes -- no arena node, no
  *               chain of dependent loads to drain a backlog of hundreds of packets on wake-up (round-2 profile of
  *               k_run_pool: 8 % of all stall samples).  The first packet the filter lets through is queued for real and
- *               withdraws the statement
+ *               withdraws the statement -- unless the assembler found the loop behind the head *stable* (ND_STABLE:
+ *               whatever the program does with a packet it is handed, it does without blocking and comes back to this
+ *               head): then the statement stands, ND_QUEUED records that a real packet is queued, and only packets whose
+ *               fate depends on the remembered packets (which a packet queued ahead might change) go to the tables
  *   socket      with any flag: the index of the socket bound to `port` (ND_NOSOCK: not stated), so a packet that
  *               is accepted finds its socket without walking the node's list
  *
@@ -965,13 +983,13 @@ ITSB_FN u32 ev_take(Rep& R, int src) {
  * sleeping or waking (epoch), and -- for pmask -- the three list instructions.  tests/hostemu builds with
  * ITSB_CHECK_DIGEST verify every statement against the tables before every use and fail the replica otherwise. */
 enum { ND_STABLE = 1u << 19, ND_ASLEEP = 1u << 20, ND_RETIRE = 1u << 21, ND_LISTED = 1u << 22, ND_SINGLE = 1u << 23,
-       ND_NOSOCK = 0xFFu, ND_MAX_FILTER = 7u };
+       ND_QUEUED = 1u << 31, ND_NOSOCK = 0x7Fu, ND_MAX_FILTER = 7u };
 ITSB_FN u32 nd_port(u32 d) { return d & 0xFFFFu; }
 ITSB_FN u32 nd_filter(u32 d) { return (d >> 16) & 7u; }
-ITSB_FN u32 nd_sock(u32 d) { return d >> 24; }
+ITSB_FN u32 nd_sock(u32 d) { return (d >> 24) & 0x7Fu; }
 ITSB_FN u32 nd_sock_field(u32 s) { return (s < ND_NOSOCK ? s : (u32)ND_NOSOCK) << 24; }
 /* what is left of a digest when nothing can be retired (or queued virtually) on its socket any more */
-ITSB_FN u32 nd_without_retire(u32 d) { return (d & ND_SINGLE) ? (d & (0xFFFFu | ND_SINGLE | 0xFF000000u)) : 0u; }
+ITSB_FN u32 nd_without_retire(u32 d) { return (d & ND_SINGLE) ? (d & (0xFFFFu | ND_SINGLE | 0x7F000000u)) : 0u; }
 
 /* Is process w parked, asleep, at the head of a RECV_FILTER loop on socket s, so that packets reaching s are certain to
  * be popped by that loop head in one activation when the workstation wakes?  (ND_ASLEEP, below.)  *stable: the
@@ -1009,7 +1027,7 @@ ITSB_COLD void node_digest_refresh(Hdr* H, u32 node) {
         bool stable = false;
         if (!have && nd_owner_asleep(R, node, s, S.owner, &fa, &stable)) {
             have = true;
-            d = S.port | (fa << 16) | ND_ASLEEP | (stable ? (u32)ND_STABLE : 0u) |
+            d = S.port | (fa << 16) | ND_ASLEEP | (stable ? (u32)ND_STABLE : 0u) | (S.q_len != 0 ? (u32)ND_QUEUED : 0u) |
                 (R.pcb[S.owner].list_head != NIL32 ? ND_LISTED : 0u) | nd_sock_field(s);
             R.nmask[node] = R.pmask[S.owner];
             continue;
@@ -1062,7 +1080,8 @@ ITSB_FN void node_digest_woken(Rep& R, u32 node, u32 port) {
 /* a packet was queued for real on the socket bound to `port`: nothing may be queued virtually behind it */
 ITSB_FN void node_digest_enqueued(Rep& R, u32 node, u32 port) {
     const u32 old = R.ndig[node];
-    if ((old & ND_ASLEEP) && !(old & ND_STABLE) && nd_port(old) == port) R.ndig[node] = nd_without_retire(old);
+    if ((old & ND_ASLEEP) && nd_port(old) == port)
+        R.ndig[node] = (old & ND_STABLE) ? (old | ND_QUEUED) : nd_without_retire(old);
 }
 
 /* process p parked on its node's wake signal at the head of a RECV_FILTER loop (phase 0) */
@@ -1076,7 +1095,7 @@ ITSB_FN void node_digest_asleep(Rep& R, u32 node, u32 p) {
     const NodeDyn& N = R.node[node];
     const Sock& S = R.sock[s];
     const u32 single = (N.sock_head == s && S.next == NIL16) ? (u32)ND_SINGLE : 0u;
-    R.ndig[node] = S.port | (filter << 16) | ND_ASLEEP | (stable ? (u32)ND_STABLE : 0u) |
+    R.ndig[node] = S.port | (filter << 16) | ND_ASLEEP | (stable ? (u32)ND_STABLE : 0u) | (S.q_len != 0 ? (u32)ND_QUEUED : 0u) |
                    (P.list_head != NIL32 ? ND_LISTED : 0u) | single | nd_sock_field(s);
     if (P.list_head != NIL32) R.nmask[node] = R.pmask[p];
 }
@@ -1138,12 +1157,13 @@ static bool node_digest_valid(Rep& R, u32 node) {
         bool stable = false;
         const u32 w = R.sock[s].owner;
         if (!nd_owner_asleep(R, node, s, w, &f, &stable) || f != nd_filter(d) || stable != ((d & ND_STABLE) != 0)) return false;
+        if (((d & ND_QUEUED) != 0) != (R.sock[s].q_len != 0)) return false;
         const Pcb& P = R.pcb[w];
         if (((d & ND_LISTED) != 0) != (P.list_head != NIL32)) return false;
         u64 want = 0;
         for (u32 n = P.list_head; n != NIL32; n = R.arena[n].next) want |= 1ull << (R.arena[n].f0 & 63);
         if (R.pmask[w] != want || ((d & ND_LISTED) && R.nmask[node] != want)) return false;
-    } else if (d & ND_LISTED) return false;
+    } else if (d & (ND_LISTED | ND_QUEUED)) return false;
     return true;
 }
 #endif
@@ -1557,7 +1577,8 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
 #endif
         if (nd_port(dg) != dst_port) return (dg & ND_SINGLE) ? (u32)RC_DROPPED : (u32)RC_TABLES;   /* its only socket is elsewhere */
         if ((dg & (ND_SINGLE | ND_RETIRE | ND_ASLEEP)) && nd_sock(dg) != ND_NOSOCK) s = (int)nd_sock(dg);
-        const bool retires = digest_retires && (dg & ND_RETIRE), sleeps = virtual_ok && (dg & ND_ASLEEP);
+        const bool retires = digest_retires && (dg & ND_RETIRE);
+        const bool sleeps = virtual_ok && (dg & ND_ASLEEP) && nd_sock(dg) != ND_NOSOCK;   /* (queued on a socket it can name) */
         if (retires || sleeps) {
             const itsb_filter F = R.m.filters[nd_filter(dg)];
             if ((F.tags_always & tag_bit) != 0 || ((F.tags_if_host & tag_bit) != 0 && K.f0 == R.m.nodes[node].host))
@@ -1572,7 +1593,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
             if (retires) return RC_RETIRED;
             /* asleep: what the filter makes of a tag that depends on the remembered packets can still change if a
                packet queued ahead is handed to the program first */
-            if (list_class && (dg & ND_STABLE) && R.sock[s].q_len != 0) return RC_TABLES;
+            if (list_class && (dg & ND_QUEUED)) return RC_TABLES;
             return RC_VIRTUAL;
         }
         return RC_TABLES;
@@ -1600,7 +1621,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
             if (rc == RC_RETIRED) { found = true; retire = true; }
             else if (rc == RC_VIRTUAL) {     /* its sleeping owner's loop head will pop and reject it: counted, not queued */
                 found = true; queued_virtually = true;
-                R.sockv[s].count += 1; R.sockv[s].bytes += K.size;
+                sockv_add(R, (u32)s, K.size);
             }
             else if (rc == RC_TABLES) {
                 if (s < 0) s = sock_find(R, node, K.dst_ip, dst_port);
@@ -1746,7 +1767,7 @@ ITSB_FN void on_deliver(Rep& R, u32 k) {
                 const u32 rc = classify(first + c0 + j, sj);
                 if (rc == RC_TABLES) slow |= 1ull << j;
                 else if (rc == RC_RETIRED) retired |= 1ull << j;
-                else if (rc == RC_VIRTUAL) { R.sockv[sj].count += 1; R.sockv[sj].bytes += K.size; queued += 1; }
+                else if (rc == RC_VIRTUAL) { sockv_add(R, (u32)sj, K.size); queued += 1; }
                 else dropped += 1;
             }
             if (H->status != 0) return;
@@ -2036,11 +2057,10 @@ ITSB_FN void run_process(Rep& R, u32 p) {
                         node_digest_asleep(R, P.node, p);
                         return;
                     }
-                    SockV& V = R.sockv[P.sock];
+                    const SockV V = sockv_take(R, P.sock);
                     if (V.count != 0) {           /* what was queued virtually while it slept: popped and rejected here */
                         stat_add(R, ITSB_TM_PACKETS_RECEIVED, V.count);
                         stat_add(R, ITSB_TM_BYTES_RECEIVED, V.bytes);
-                        V.count = 0; V.bytes = 0;
                     }
                     P.r[a & 3] = n_epoch;
                     P.phase = 1;
