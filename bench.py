@@ -42,9 +42,9 @@ METRIC = "simulated events/sec (batched network_simple replicas)"
 # ncu --set full captures committed under profiles/ (r2_*_ncu_full.txt): dram__bytes_read.sum + dram__bytes_write.sum
 # of one launch.  k_run stages a replica's state once per launch: its traffic goes per launch (6000 replicas x 60 s).  The
 # lane-per-replica kernels advance the state in place: their traffic goes with the simulated time (100000 replicas x 60
-# simulated s per launch: k_run_pool 77.93 GB read + 25.70 GB written, k_run_vote 61.00 + 22.15 GB).
+# simulated s per launch: k_run_pool 72.16 GB read + 23.95 GB written, k_run_vote 61.00 + 22.15 GB).
 NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH = {"k_run": (328.9e6 + 160.1e6) / 6000.0}
-NCU_TRAFFIC_BYTES_PER_REPLICA_SECOND = {"k_run_pool": (77.93e9 + 25.70e9) / 100000.0 / 60.0,
+NCU_TRAFFIC_BYTES_PER_REPLICA_SECOND = {"k_run_pool": (72.16e9 + 23.95e9) / 100000.0 / 60.0,
                                         "k_run_vote": (61.00e9 + 22.15e9) / 100000.0 / 60.0}
 NCU_TRAFFIC_NOTE = ("dram__bytes_read+write per launch, scaled from this kernel's ncu --set full capture under profiles/ "
                     "(k_run: 6000 replicas x 60 s, per replica and launch; k_run_pool / k_run_vote: 100000 replicas x 60 s, "
@@ -52,7 +52,7 @@ NCU_TRAFFIC_NOTE = ("dram__bytes_read+write per launch, scaled from this kernel'
 ROOFLINE_NOTE = ("algorithmic bytes = per-replica state read and written once per run (S_in+S_out, SURVEY 8-d) plus the "
                  "records a step logs; the engine kernels do not move bytes at the HBM rate: every one of them runs at the "
                  "rate its SMs' instruction-cache misses are served by the GPC-level cache (gcc requests at 91-93% of peak "
-                 "in every capture), k_run_pool with 71% of its stall samples waiting on dependent loads of per-replica "
+                 "in every capture), k_run_pool with 70% of its stall samples waiting on dependent loads of per-replica "
                  "state on top; profiles/README.md")
 UNIT = "events/s"
 RESULT_OUT = sys.stdout
