@@ -1,6 +1,9 @@
 """
 ORACLE / TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's flagship workload.
 
+PARITY PINNED: ``oracle/ref_example.py`` executes the reference's own example files unmodified on the same Philox stream,
+and ``tests/test_oracle.py`` holds this module's traces, connection records and draw counts against theirs, bit for bit.
+
 ``examples/network_simple`` cannot run against the shipped ``itsim`` package (it imports
 ``Payload``/``PayloadDictionaryType`` from ``itsim.network.packet`` and ``Node``/``Socket`` from ``itsim.machine``,
 none of which exist; ``network_simple_overrides.py:1-6`` calls itself deprecated).  This module restates, on the
