@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_run_pool(const RunParams 
     }
     __syncthreads();
     /* ---- warps pull slots of one kind, handle, push them on ------------------------------------------------------------ */
+    unsigned int idle_ns = 32;          /* back-off of a warp that finds every ring empty (doubles up to 2 us) */
     for (;;) {
         unsigned int kind = 0, first = 0, n = 0;
         if (lane == 0) {
@@ -137,9 +138,15 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_run_pool(const RunParams 
                 }
                 if (best_n == 0) {
                     if (*(volatile unsigned int*)&S->live == 0) { n = 0xFFFFFFFFu; break; }      /* the CTA's work is done */
-                    __nanosleep(100);
+                    /* nothing is ready: every replica of the CTA is in some other warp's hands (a batch smaller than the
+                       CTA's lanes: config C4, strong scaling).  Polling the rings flat out costs the working warps
+                       issue slots and instruction fetches (large-LAN capture: 44 % of all executed instructions were
+                       this loop), so the wait backs off */
+                    __nanosleep(idle_ns);
+                    if (idle_ns < 2048) idle_ns <<= 1;
                     continue;
                 }
+                idle_ns = 32;
                 const unsigned int h = *(volatile unsigned int*)&S->head[best];
                 const unsigned int avail = *(volatile unsigned int*)&S->tail[best] - h;
                 if (avail == 0 || avail > (unsigned int)RING) continue;

@@ -87,6 +87,10 @@ ncu)
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_run -s 5 -c 1 -f -o gpurun_out/k_run_default \
      python bench.py --replicas 100000 --steps 2 --warmup 3 --spinup 600 --slice 60 --no-cpu-baseline --no-verify > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
   ls -la gpurun_out/*.ncu-rep;;
+nculan)
+  # a SMALL large-LAN capture (4 200 replicas x 0.25 simulated s per launch): where the shipped-itsim path spends its time
+  ITSB_KERNEL=pool timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_run -s 3 -c 1 -f -o gpurun_out/k_run_pool_hbm \
+     python bench.py --workload large_lan --replicas 4200 --slice 0.25 --spinup 4 --steps 2 --warmup 2 --no-cpu-baseline --no-verify > gpurun_out/ncu_lan.log 2>&1; echo "ncu lan rc=$?";;
 ncuvote)
   ITSB_KERNEL=vote timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_run -s 5 -c 1 -f -o gpurun_out/k_run_vote \
      python bench.py --replicas 100000 --steps 2 --warmup 3 --spinup 600 --slice 60 --no-cpu-baseline --no-verify > gpurun_out/ncu_vote.log 2>&1; echo "ncu vote rc=$?";;
