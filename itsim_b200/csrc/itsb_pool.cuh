@@ -120,43 +120,50 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) k_run_pool(const RunParams 
     unsigned int idle_ns = 32;          /* back-off of a warp that finds every ring empty (doubles up to 2 us) */
     for (;;) {
         unsigned int kind = 0, first = 0, n = 0;
-        if (lane == 0) {
-            for (;;) {
-                unsigned int best = 0, best_n = 0;
-                if (p.pool_stick != 0) {            /* stay with the kind the other warps are running, while it has work */
-                    const unsigned int ck = *(volatile unsigned int*)&S->cur_kind;
-                    const unsigned int avail = *(volatile unsigned int*)&S->tail[ck] - *(volatile unsigned int*)&S->head[ck];
-                    if (avail >= p.pool_stick && avail <= (unsigned int)RING) { best = ck; best_n = avail; }
-                }
-                if (best_n == 0) {
-#pragma unroll
-                    for (unsigned int k = 0; k < POOL_RINGS; ++k) {
-                        const unsigned int avail = *(volatile unsigned int*)&S->tail[k] - *(volatile unsigned int*)&S->head[k];
-                        if (avail > best_n && avail <= (unsigned int)RING) { best_n = avail; best = k; }
-                    }
-                    if (best_n != 0 && p.pool_stick != 0) *(volatile unsigned int*)&S->cur_kind = best;
-                }
-                if (best_n == 0) {
-                    if (*(volatile unsigned int*)&S->live == 0) { n = 0xFFFFFFFFu; break; }      /* the CTA's work is done */
-                    /* nothing is ready: every replica of the CTA is in some other warp's hands (a batch smaller than the
-                       CTA's lanes: config C4, strong scaling).  Polling the rings flat out costs the working warps
-                       issue slots and instruction fetches (large-LAN capture: 44 % of all executed instructions were
-                       this loop), so the wait backs off */
-                    __nanosleep(idle_ns);
-                    if (idle_ns < 2048) idle_ns <<= 1;
-                    continue;
-                }
-                idle_ns = 32;
-                const unsigned int h = *(volatile unsigned int*)&S->head[best];
-                const unsigned int avail = *(volatile unsigned int*)&S->tail[best] - h;
-                if (avail == 0 || avail > (unsigned int)RING) continue;
-                const unsigned int take = avail < 32u ? avail : 32u;
-                if (atomicCAS(&S->head[best], h, h + take) == h) { kind = best; first = h; n = take; break; }
+        /* the whole warp picks a ring: lane k reads ring k's fill, one max-reduction finds the fullest (the lowest kind on a
+           tie); lane 0 alone claims the slots.  (A single lane walking the rings was 7 % of all executed instructions and
+           ~500 cycles of dependent shared-memory loads per batch.) */
+        static_assert(POOL_RINGS <= 32, "one lane per ring");
+        for (;;) {
+            unsigned int avail = 0;
+            if (lane < POOL_RINGS) {
+                avail = *(volatile unsigned int*)&S->tail[lane] - *(volatile unsigned int*)&S->head[lane];
+                if (avail > (unsigned int)RING) avail = 0;
             }
+            unsigned int best = 0, best_n = 0;
+            if (p.pool_stick != 0) {                /* stay with the kind the other warps are running, while it has work */
+                const unsigned int ck = *(volatile unsigned int*)&S->cur_kind;
+                const unsigned int a = __shfl_sync(0xFFFFFFFFu, avail, ck);
+                if (a >= p.pool_stick) { best = ck; best_n = a; }
+            }
+            if (best_n == 0) {
+                const unsigned int top = __reduce_max_sync(0xFFFFFFFFu, (avail << 5) | (31u - lane));
+                best_n = top >> 5;
+                best = 31u - (top & 31u);
+                if (best_n != 0 && p.pool_stick != 0 && lane == 0) *(volatile unsigned int*)&S->cur_kind = best;
+            }
+            if (best_n == 0) {
+                if (*(volatile unsigned int*)&S->live == 0) { n = 0xFFFFFFFFu; break; }      /* the CTA's work is done */
+                /* nothing is ready: every replica of the CTA is in some other warp's hands (a batch smaller than the
+                   CTA's lanes: config C4, strong scaling).  Polling the rings flat out costs the working warps issue slots
+                   and instruction fetches (large-LAN capture: 44 % of all executed instructions were this loop), so the
+                   wait backs off */
+                __nanosleep(idle_ns);
+                if (idle_ns < 2048) idle_ns <<= 1;
+                continue;
+            }
+            idle_ns = 32;
+            if (lane == 0) {
+                const unsigned int h = *(volatile unsigned int*)&S->head[best];
+                const unsigned int a = *(volatile unsigned int*)&S->tail[best] - h;
+                if (a != 0 && a <= (unsigned int)RING) {
+                    const unsigned int take = a < 32u ? a : 32u;
+                    if (atomicCAS(&S->head[best], h, h + take) == h) { first = h; n = take; }
+                }
+            }
+            n = __shfl_sync(0xFFFFFFFFu, n, 0);
+            if (n != 0) { kind = best; first = __shfl_sync(0xFFFFFFFFu, first, 0); break; }
         }
-        kind = __shfl_sync(0xFFFFFFFFu, kind, 0);
-        first = __shfl_sync(0xFFFFFFFFu, first, 0);
-        n = __shfl_sync(0xFFFFFFFFu, n, 0);
         if (n == 0xFFFFFFFFu) break;
         if (lane < n) {
             volatile unsigned int* cell = &S->ring[kind][(first + lane) & (RING - 1)];

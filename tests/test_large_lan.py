@@ -104,3 +104,20 @@ def test_gpu_batch_equals_hostemu(hostemu):
     for r in range(24):
         assert np.array_equal(gpu.replica_telemetry(r), emu.replica_telemetry(r)), r
     gpu.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["vote", "pool"])
+@pytest.mark.parametrize("subnets", [4, 8])
+def test_mid_size_tables_on_the_lane_kernels(which, subnets, hostemu, monkeypatch):
+    """Models whose staged tables need more than the 48 KB of shared memory a kernel gets without opting in (4 and 8
+    subnets x 64 endpoints: 57 600 and 115 456 bytes) on the lane-per-replica kernels: the launch succeeds and every
+    sampled replica equals the host build."""
+    monkeypatch.setenv("ITSB_KERNEL", which)
+    gpu, ev_gpu = run("gpu", None, subnets, 64, 5, 10, 2.0, 0, n=40)
+    assert gpu.kernel_name().startswith("k_run_" + which), gpu.kernel_name()
+    emu, ev_emu = run("hostemu", hostemu, subnets, 64, 5, 10, 2.0, 0, n=40)
+    assert ev_gpu == ev_emu
+    for r in (0, 13, 39):
+        assert np.array_equal(gpu.replica_telemetry(r), emu.replica_telemetry(r)), r
+    gpu.close()
