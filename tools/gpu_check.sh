@@ -60,6 +60,14 @@ ab)
     ITSB_POOL_BY_PROGRAM=$v timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-verify > gpurun_out/ab_${v}_${rep}.json 2> gpurun_out/ab_${v}_${rep}.err
     line gpurun_out/ab_${v}_${rep}.json "by_program=$v run $rep"
   done; done;;
+ablib)
+  # A/B of two builds in one visit, alternating: the in-tree library vs itsim_b200/libitsim_b200_B.so
+  for rep in 1 2 3; do
+    timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-verify > gpurun_out/ablib_A_${rep}.json 2> gpurun_out/ablib_A_${rep}.err
+    line gpurun_out/ablib_A_${rep}.json "A run $rep"
+    ITSB_LIB=$PWD/itsim_b200/libitsim_b200_B.so timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-verify > gpurun_out/ablib_B_${rep}.json 2> gpurun_out/ablib_B_${rep}.err
+    line gpurun_out/ablib_B_${rep}.json "B run $rep"
+  done;;
 stick)
   # k_run_pool: warps of an SM staying on one event kind while its ring holds >= N slots (0 = always the fullest ring)
   for n in ${STICKS:-0 8 16 24}; do
