@@ -42,9 +42,9 @@ METRIC = "simulated events/sec (batched network_simple replicas)"
 # ncu --set full captures committed under profiles/ (r2_*_ncu_full.txt): dram__bytes_read.sum + dram__bytes_write.sum
 # of one launch.  k_run stages a replica's state once per launch: its traffic goes per launch (6000 replicas x 60 s).  The
 # lane-per-replica kernels advance the state in place: their traffic goes with the simulated time (100000 replicas x 60
-# simulated s per launch: k_run_pool 72.16 GB read + 23.95 GB written, k_run_vote 61.00 + 22.15 GB).
+# simulated s per launch: k_run_pool 72.37 GB read + 23.99 GB written, k_run_vote 61.00 + 22.15 GB).
 NCU_TRAFFIC_BYTES_PER_REPLICA_LAUNCH = {"k_run": (328.9e6 + 160.1e6) / 6000.0}
-NCU_TRAFFIC_BYTES_PER_REPLICA_SECOND = {"k_run_pool": (72.16e9 + 23.95e9) / 100000.0 / 60.0,
+NCU_TRAFFIC_BYTES_PER_REPLICA_SECOND = {"k_run_pool": (72.37e9 + 23.99e9) / 100000.0 / 60.0,
                                         "k_run_vote": (61.00e9 + 22.15e9) / 100000.0 / 60.0}
 NCU_TRAFFIC_NOTE = ("dram__bytes_read+write per launch, scaled from this kernel's ncu --set full capture under profiles/ "
                     "(k_run: 6000 replicas x 60 s, per replica and launch; k_run_pool / k_run_vote: 100000 replicas x 60 s, "

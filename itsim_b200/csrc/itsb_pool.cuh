@@ -57,12 +57,12 @@ struct PoolShared {
     unsigned int cur_kind;                          /* the kind the CTA's warps took last (p.pool_stick) */
 };
 
-/* A ring cell holds (lap << 16) | (slot + 1), lap = 1 + (position / ring size) mod 65535, or 0 when free.  The producer
+/* A ring cell holds (lap << 16) | (slot + 1), lap = 1 + (position / ring size) mod 32768, or 0 when free.  The producer
  * of a position waits for the cell to be free (the entry of the previous lap taken), the consumer of a position waits
  * for ITS lap's entry: an entry of the previous lap that its own consumer has claimed but not read yet can never be
  * mistaken for the new one. */
 template <int RING>
-__device__ __forceinline__ unsigned int pool_lap(unsigned int pos) { return (pos / RING) % 0xFFFFu + 1u; }
+__device__ __forceinline__ unsigned int pool_lap(unsigned int pos) { return ((pos / RING) & 0x7FFFu) + 1u; }
 
 template <int RING>
 __device__ __forceinline__ void pool_push(unsigned int* ring, unsigned int* tail, unsigned int slot) {
