@@ -30,9 +30,10 @@
  * program they resume, so that the lanes of a batch run the same code and not just the same handler: measured active
  * lanes per warp instruction 7.4 -> see profiles/README.md */
 #ifndef POOL_PROG_RINGS
-#define POOL_PROG_RINGS 0       /* measured with 16 (default bench): 6.31 vs 6.6-6.7 x 10^9 with the nine kind rings alone --
-                                   the lane that picks a ring reads every ring's cursors, and 25 rings cost more there
-                                   than the finer grouping saves; kept as a build option (-DPOOL_PROG_RINGS=16) */
+#define POOL_PROG_RINGS 0       /* measured with 16 (default bench): 6.31 vs 6.6-6.7 x 10^9 with the nine kind rings alone when
+                                   one lane walked all the rings, and 6.6-6.8 vs 7.2-7.3 with the warp-wide pick: 25 rings
+                                   mean smaller batches and more changes of code per SM, which cost more than the finer
+                                   grouping saves; kept as a build option (-DPOOL_PROG_RINGS=16, ITSB_POOL_BY_PROGRAM=1) */
 #endif
 #define POOL_RINGS (9 + POOL_PROG_RINGS)
 
