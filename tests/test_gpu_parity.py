@@ -65,6 +65,24 @@ def test_live_oracle_trace_short(kernel):
     eng.close()
 
 
+def test_64_bit_seed_and_replica_ids_against_the_live_oracle(kernel):
+    """Seed and replica ids with their high words set (they enter the Philox counter, oracle/philox.py:146-148): three
+    neighbouring replicas of one batch, each event for event against the oracle run here."""
+    import netsimple as oracle_netsimple
+    seed, first, horizon = 0x9E3779B97F4A7C15, (1 << 40) + 12345, 500.0
+    refs = []
+    for r in range(3):
+        model = oracle_netsimple.run_replica(seed, first + r, horizon)
+        refs.append(model.tracer.as_array())
+        model.close()
+    eng = make(trace_records=max(len(t) for t in refs) + 16).run_replicas(3, seed=seed, first_replica_id=first)
+    assert eng.kernel_name() == kernel
+    eng.run(horizon)
+    for r in range(3):
+        assert_trace_equal(eng.trace(r), refs[r])
+    eng.close()
+
+
 def test_summaries_match_golden_in_one_batch(golden_summaries, kernel):
     """Seed 0, replicas 0..99999 would be config C2; here the batch is the 64 first ids plus id 99999, and every
     replica that has a golden summary must match it counter for counter after 3600 s."""

@@ -112,3 +112,51 @@ def test_fused_loop_head_and_retired_wakeups_change_nothing(hostemu):
         for r in range(3):
             assert np.array_equal(other[1][r], results[0][1][r])
         assert np.array_equal(other[2], results[0][2])
+
+
+# ---- random streams against the live oracle ---------------------------------------------------------------------------------
+# ITSB_SWEEP=N widens the sweep (an offline run of N = 48 is recorded in DESIGN.md §2); the default keeps the suite short.
+import os  # noqa: E402
+
+SWEEP = int(os.environ.get("ITSB_SWEEP", "3"))
+
+
+@pytest.mark.parametrize("i", range(SWEEP))
+def test_random_stream_equals_the_live_oracle(hostemu, i):
+    """(seed, replica id) drawn from all 64 bits of both -- the high words go into the Philox counter
+    (oracle/philox.py:146-148) -- on one of the three override-path models; the whole trace, timestamps included."""
+    import netsimple as oracle_netsimple
+    from itsim_b200 import netsimple
+    rng = np.random.default_rng(20261020 + i)
+    seed = int(rng.integers(0, 1 << 63)) if i % 2 else int(rng.integers(0, 1 << 20))
+    replica = int(rng.integers(0, 1 << 63)) if i % 3 else int(rng.integers(0, 100000))
+    duration = float(rng.choice([400.0, 900.0, 1500.0]))
+    which = ("plain", "malware", "backdoor")[i % 3]
+    if which == "plain":
+        model = oracle_netsimple.run_replica(seed, replica, duration)
+        build = netsimple.build
+    elif which == "malware":
+        model = oracle_netsimple.MalwareModel(seed, replica)
+        model.run(duration)
+        build = netsimple.build_malware
+    else:       # the overlay with the knobs of examples/backdoor/backdoor.py, gaps short enough to see beacons
+        from greensim.random import expo as o_expo, uniform as o_uniform
+        from itsim_b200.random import expo, num_bytes, uniform
+        targets = netsimple.BACKDOOR_C2
+        model = oracle_netsimple.MalwareModel(
+            seed, replica, beacon_gap=o_uniform(2.1, 4.9), privileged_gap=o_uniform(30.0, 50.0), c2_targets=list(targets),
+            beacon_size=oracle_netsimple.num_bytes(o_expo(1024.0), header=128, upper=20 * 1024 * 1024), infected_index=23)
+        model.run(duration)
+
+        def build(trace_records):
+            return netsimple.build_malware(
+                trace_records=trace_records, beacon_gap=uniform(2.1, 4.9), privileged_gap=uniform(30.0, 50.0),
+                c2_targets=targets, beacon_size=num_bytes(expo(1024.0), header=128, upper=20 * 1024 * 1024),
+                infected_index=23)
+    ref = model.tracer.as_array()
+    model.close()
+    sim = build(trace_records=len(ref) + 16)
+    sim._lib = hostemu
+    eng = sim.run_replicas(1, seed=seed, first_replica_id=replica)
+    eng.run(duration)
+    assert_trace_equal(eng.trace(0), ref)
