@@ -102,3 +102,42 @@ def test_gpu_equals_hostemu_on_a_broadcast_batch(hostemu):
         assert np.array_equal(gpu.replica_telemetry(r), emu.replica_telemetry(r)), r
     assert np.all(gpu.now() == 120.0)
     gpu.close()
+
+
+# ---- random streams against the reference's own classes run live -------------------------------------------------------------
+SWEEP = int(os.environ.get("ITSB_SWEEP", "4"))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/itsim"), reason="reference tree not on this box")
+@pytest.mark.parametrize("i", range(SWEEP))
+def test_random_stream_equals_the_reference_classes(hostemu, hostemu_fast, i):
+    """The reference's Link / Node / Socket / DHCP classes (oracle/machine_scenarios.py runs them unmodified) on a
+    (seed, replica) stream no fixture holds, 64-bit values included, against the host build of the device source --
+    both ways the helper hops of select() are compiled (interpreter / ITSB_HIDDEN_FAST)."""
+    import machine_scenarios as ms
+    from itsim_b200 import machine_models
+    rng = np.random.default_rng(777 + i)
+    seed = int(rng.integers(0, 1 << 63)) if i % 2 else int(rng.integers(0, 1 << 16))
+    replica = int(rng.integers(0, 1 << 63)) if i % 3 == 0 else int(rng.integers(0, 1 << 20))
+    which = ("broadcast", "dhcp_exchange", "packet_transfer", "large_lan")[i % 4]
+    if which == "broadcast":
+        duration = float(rng.choice([20.0, 75.0, 150.0]))
+        ref, _ = ms.broadcast(seed=seed, replica=replica, duration=duration)
+    elif which == "dhcp_exchange":
+        duration = float(rng.choice([10.0, 60.0, 200.0]))
+        ref, _ = ms.dhcp_exchange(seed=seed, replica=replica, duration=duration)
+    elif which == "packet_transfer":
+        duration = 10.0
+        ref, _ = ms.packet_transfer(seed=seed, replica=replica)
+    else:
+        duration = float(rng.choice([8.0, 14.0]))
+        ref, _ = ms.large_lan(seed=seed, replica=replica, duration=duration, subnets=3, per_subnet=8)
+    for lib in (hostemu, hostemu_fast):
+        if which == "large_lan":
+            sim = machine_models.large_lan(trace_records=len(ref) + 16, subnets=3, per_subnet=8)
+            sim._lib = lib
+            eng = sim.run_replicas(1, seed=seed, first_replica_id=replica)
+            eng.run(duration)
+        else:
+            eng = run_scenario(which, seed, replica, duration, lib=lib)
+        assert_trace_equal(eng.trace(0), ref)
