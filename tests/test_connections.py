@@ -152,3 +152,28 @@ def test_documents_read_like_the_reference_log_lines(hostemu):
     lonely = next(d for d in docs if d["Local_IP"] == 0)
     assert lonely["Local_Port"] == 0 and lonely["Received_Bytes"] == 0 and lonely["Direction"] == "Outbound"
     json.dumps(docs)
+
+
+# ---- random streams against the live oracle (ITSB_SWEEP=N widens it) ---------------------------------------------------------
+import os  # noqa: E402
+
+SWEEP = int(os.environ.get("ITSB_SWEEP", "2"))
+
+
+@pytest.mark.parametrize("i", range(SWEEP))
+def test_records_of_a_random_stream_match_the_oracle(hostemu, i):
+    """Connection records of a (seed, replica) stream no fixture holds -- 64-bit values included -- with a random
+    correlation window: record for record, start and end times bit for bit."""
+    import netsimple as oracle_netsimple
+    rng = np.random.default_rng(4242 + i)
+    seed = int(rng.integers(0, 1 << 63)) if i % 2 else int(rng.integers(0, 1 << 16))
+    replica = int(rng.integers(0, 1 << 63)) if i % 3 == 0 else int(rng.integers(0, 1 << 20))
+    horizon = float(rng.choice([700.0, 1100.0, 1600.0]))
+    window = int(rng.choice([2, 4, 8, 64]))
+    eng = engine_run("hostemu", hostemu, seed, replica, horizon, window=window, n=1)
+    model = oracle_netsimple.run_replica(seed, replica, horizon, trace=False, conn_window=window)
+    ref = oracle_records(model)
+    model.close()
+    got = eng.connections(0)
+    assert eng.connections_total == len(ref)
+    assert_same(got, ref)
