@@ -160,3 +160,24 @@ def test_random_stream_equals_the_live_oracle(hostemu, i):
     eng = sim.run_replicas(1, seed=seed, first_replica_id=replica)
     eng.run(duration)
     assert_trace_equal(eng.trace(0), ref)
+
+
+@pytest.mark.parametrize("i", range(max(1, SWEEP // 3)))
+def test_untraced_random_stream_equals_the_live_oracle(hostemu, i):
+    """Without a trace the delivery pass takes its short cuts (retired wake-ups, virtual queues of sleeping workstations,
+    Bloom words): every counter of a random stream, run long enough for workstations to sleep and wake, against the
+    oracle's own counts."""
+    import netsimple as oracle_netsimple
+    rng = np.random.default_rng(99 + i)
+    seed = int(rng.integers(0, 1 << 63)) if i % 2 else int(rng.integers(0, 1 << 16))
+    replica = int(rng.integers(0, 1 << 63)) if i % 3 == 0 else int(rng.integers(0, 1 << 20))
+    horizon = float(rng.choice([1900.0, 2600.0, 3300.0]))
+    model = oracle_netsimple.run_replica(seed, replica, horizon, trace=False)
+    s = model.tracer.summary()
+    s.update(model.stats)
+    model.close()
+    sim = make(hostemu)
+    eng = sim.run_replicas(1, seed=seed, first_replica_id=replica)
+    events = eng.run(horizon)
+    assert events == s["events"]
+    telemetry_matches_summary(eng.replica_telemetry(0), s)
