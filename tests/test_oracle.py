@@ -112,3 +112,14 @@ def test_golden_traces_are_what_the_reference_example_produces_now():
     assert_trace_equal(out["trace"], load_golden_trace("netsimple_trace_s7_r3_900s.npz"), rtol=0.0)
     out = ref_example.run_malware_simple(0, 0, 900.0)
     assert_trace_equal(out["trace"], load_golden_trace("malware_trace_s0_r0_900s.npz"), rtol=0.0)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/itsim"), reason="reference tree not on this box")
+def test_every_reference_citation_points_at_an_existing_line():
+    """`file.py:LINE` citations in the docs, the ABI header and the sources: the file exists in the reference and is
+    that long (tools/check_citations.py)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "check_citations.py")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-2000:]
