@@ -196,15 +196,16 @@ extern "C" __global__ void __launch_bounds__(128) k_log_gather(
 }
 
 /* ---- host side ---------------------------------------------------------------------------------------------------------- */
-/* Engine kernels.  Two designs:
+/* Engine kernels.  Three designs on one engine source:
  *   a replica per WARP, state staged in shared memory (k_run; k_run_wide for 13-16 resident replicas per SM;
- *   k_run_in_place with the state left in HBM for replicas larger than shared memory; k_run_phased: experiment);
- *   a replica per LANE, state in place in HBM, the warp running the event kind most of its lanes wait on (k_run_vote;
- *   k_run_lanes without the vote and k_run_sorted with a CTA-wide regrouping: experiments).
- * Default: k_run_vote where it is the faster one -- models whose tables fit shared memory and that keep no connection
- * records (their per-socket correlation is lane-parallel work in the warp-per-replica kernels).  ITSB_KERNEL=
- * warp | vote overrides (lanes | sorted | pool | phased too in a -DITSB_EXPERIMENTS build), ITSB_KERNEL_CTAS=n sets
- * the CTAs per SM of the lane kernels. */
+ *   k_run_in_place with the state left in HBM for replicas larger than shared memory);
+ *   a replica per LANE, state in place in HBM, each warp running the event kind most of its lanes wait on (k_run_vote,
+ *   k_run_vote_hbm);
+ *   a replica per LANE, the replicas of a CTA regrouped by the kind of their next event through rings in shared memory
+ *   (k_run_pool, k_run_pool_hbm): the default from 8 192 replicas up (4 096 for models read in place), the warp
+ *   kernel below that.
+ * ITSB_KERNEL=warp | vote | pool overrides (lanes | sorted | phased too in a -DITSB_EXPERIMENTS build: measured slower,
+ * profiles/README.md), ITSB_KERNEL_CTAS=n sets the CTAs per SM of k_run_vote. */
 enum { K_WARP = 0, K_WIDE, K_IN_PLACE, K_PHASED, K_VOTE, K_LANES, K_SORTED, K_POOL, K_VOTE_HBM, K_POOL_HBM };
 static const char* const KERNEL_NAMES[] = {"k_run", "k_run_wide", "k_run_in_place", "k_run_phased", "k_run_vote",
                                            "k_run_lanes", "k_run_sorted", "k_run_pool", "k_run_vote_hbm", "k_run_pool_hbm"};
@@ -287,7 +288,7 @@ static void choose_kernel(itsb_engine* e) {
     else if (lane_hbm_ok) {
         /* nothing on the shipped-itsim path is lane-parallel, so a lane per replica only needs more replicas than the
            warp kernel holds in flight (148 SMs x 16-20 warps) to win: measured on config C4 (profiles/README.md) */
-        /* config C4, 10 000 replicas (x 10^8 events/s): k_run_in_place 0.90, k_run_vote_hbm 1.12, k_run_pool_hbm 1.49 */
+        /* config C4, 10 000 replicas (x 10^8 events/s): k_run_in_place 0.90, k_run_vote_hbm 1.12, k_run_pool_hbm 1.56 */
         e->kernel = e->n_replicas >= 4096 ? (e->pool_hbm_ok ? K_POOL_HBM : K_VOTE_HBM) : warp_kernel;
     }
     else {
@@ -297,7 +298,7 @@ static void choose_kernel(itsb_engine* e) {
                  12 500      1.48      1.51         2.03
                  25 000      1.51      2.12         3.25
                  50 000      1.53      3.10         4.97
-                100 000      1.54      4.77         6.09
+                100 000      1.54      4.77         6.09  (7.2 with the later changes to k_run_pool)
                 200 000        -         -          6.18
            so the pooled lane kernel from 8 192 replicas up, the warp kernel below.  Models that keep connection records
            (config C5, 20 000 replicas, drained every step): k_run_pool 4.3, k_run 3.4 x 10^8. */
