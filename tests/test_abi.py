@@ -62,3 +62,35 @@ def test_product_never_touches_the_oracle_or_hostemu():
                 code = "\n".join(line.split("#")[0] for line in code.splitlines())
                 assert "hostemu" not in code, name
                 assert not re.search(r"^\s*(from|import)\s+(oracle|evtrace|philox|greensim)\b", code, flags=re.M), name
+
+
+def _integration_stub(lib_path):
+    """Executes the ctypes stub printed in INTEGRATION.md section 1, bound to `lib_path`."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    code = re.search(r"## 1\. The ctypes stub.*?```python\n(.*?)```", text, flags=re.S).group(1)
+    assert 'C.CDLL("libitsim_b200.so")' in code
+    ns = {}
+    exec(compile(code.replace('C.CDLL("libitsim_b200.so")', f"C.CDLL({lib_path!r})"), "INTEGRATION.md", "exec"), ns)
+    return ns
+
+
+@pytest.mark.parametrize("backend", [pytest.param("hostemu", id="hostemu"),
+                                     pytest.param("gpu", id="gpu", marks=pytest.mark.gpu)])
+def test_the_stub_of_integration_md_runs_a_batch(built, backend):
+    """The binding a maintainer of the reference would add, executed as printed: same events
+    and telemetry as the package's own binding, and its structs have the header's layout."""
+    import numpy as np
+    from itsim_b200 import _lib, netsimple
+    path = built.HOSTEMU if backend == "hostemu" else built.LIB
+    stub = _integration_stub(path)
+    sim = netsimple.build()
+    compiled = sim.compile()
+    own = compiled.desc()
+    assert ctypes.sizeof(stub["ModelDesc"]) == ctypes.sizeof(own)
+    desc = stub["ModelDesc"].from_buffer_copy(bytes(own))
+    events, telemetry = stub["run_batch"](compiled.blobs(), desc, 3, 11, 700.0)
+    sim._lib = _lib.bind(ctypes.CDLL(path)) if backend == "hostemu" else None
+    eng = sim.run_replicas(3, seed=11)
+    assert eng.run(700.0) == events > 1000
+    assert np.array_equal(eng.telemetry(), telemetry)
+    assert len(telemetry) == _lib.TM_SIZE
