@@ -1,6 +1,7 @@
 #!/bin/bash
 # One GPU-box visit (1 GPU).  Usage, from the repo root through gpurun: bash tools/gpu_check.sh <step>...
-#   tests smoke bench benchwarp sweep poolsweep pool wholejob c5 lan experiments ncu ncupool
+#   tests smoke bench refarm benchwarp benchvote sweep pool wholejob c5 lan malware quick ab ablib stick racecheck
+#   experiments ncu nculan ncuvote
 # Every step writes under gpurun_out/ and prints one line per result.  No ncu on the large LAN: a full-set replay of a
 # kernel that touches 6.7 GB of state per pass does not finish in any budget.
 set -u
